@@ -1,0 +1,327 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.hpp).
+// Plain C entry points so tests/ and bench.py's cpu_baseline leg can drive the oracle through ctypes.
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "oracle.hpp"
+
+using namespace dpo;
+
+static thread_local std::string g_err;
+#define DPO_TRY try {
+#define DPO_CATCH(ret)                 \
+    }                                  \
+    catch (const std::exception& ex) { \
+        g_err = ex.what();             \
+        return ret;                    \
+    }
+
+extern "C" {
+
+const char* dpo_last_error() { return g_err.c_str(); }
+
+// ----- packed / byte sequences (KAT layer) ----------------------------------
+void* dpo_packed_new(const char* ascii, long long n) {
+    DPO_TRY return new PackedSeq(NewPackedSequence(0, std::string(ascii, (size_t)n), nullptr));
+    DPO_CATCH(nullptr)
+}
+void dpo_packed_free(void* p) { delete (PackedSeq*)p; }
+void* dpo_packed_sub(void* p, long long start, long long end) {
+    DPO_TRY return new PackedSeq(SubSequence(*(PackedSeq*)p, start, end));
+    DPO_CATCH(nullptr)
+}
+void* dpo_packed_rc(void* p) {
+    DPO_TRY return new PackedSeq(ReverseComplement(*(PackedSeq*)p));
+    DPO_CATCH(nullptr)
+}
+long long dpo_packed_len(void* p) { return ((PackedSeq*)p)->length; }
+long long dpo_packed_nbytes(void* p) { return (long long)((PackedSeq*)p)->nbytes; }
+void dpo_packed_bytes(void* p, unsigned char* out) { memcpy(out, ((PackedSeq*)p)->data(), ((PackedSeq*)p)->nbytes); }
+void dpo_packed_fields(void* p, long long* out5) {
+    PackedSeq* s = (PackedSeq*)p;
+    out5[0] = s->offset;
+    out5[1] = s->inset;
+    out5[2] = s->firstLen;
+    out5[3] = s->finalLen;
+    out5[4] = s->length;
+}
+void dpo_packed_string(void* p, char* out) {
+    std::string s = String(*(PackedSeq*)p);
+    memcpy(out, s.data(), s.size());
+}
+long long dpo_packed_kmer_at(void* p, long long index, long long k) { return KmerAt(*(PackedSeq*)p, index, k); }
+long long dpo_packed_next_kmer(void* p, long long cur, long long mask, long long idx) {
+    return NextKmer(*(PackedSeq*)p, cur, mask, idx);
+}
+long long dpo_packed_count_kmers(void* p, long long upTo, long long k, const unsigned char* seeds) {
+    return CountKmers(*(PackedSeq*)p, upTo, k, seeds);
+}
+long long dpo_packed_count_kmers_between(void* p, long long from, long long to, long long upTo, long long k,
+                                         const unsigned char* seeds) {
+    DPO_TRY return CountKmersBetween(*(PackedSeq*)p, from, to, upTo, k, seeds);
+    DPO_CATCH(-1)
+}
+// segments must hold 2*(len+16)+1 entries; returns the number of entries written (2*hits+1)
+long long dpo_packed_write_segments(void* p, long long k, const unsigned char* seeds, long long* segments) {
+    PackedSeq* s = (PackedSeq*)p;
+    size_t cap = (size_t)(2 * (s->length + 16) + 1);
+    for (size_t i = 0; i < cap; i++) segments[i] = INT64_MIN;
+    WriteSegments(*s, segments, k, seeds);
+    size_t last = cap;
+    while (last > 0 && segments[last - 1] == INT64_MIN) last--;
+    return (long long)last;
+}
+long long dpo_packed_short_kmers(void* p, long long k, int collapse, unsigned short* out) {
+    std::vector<uint16_t> v = ShortKmers(*(PackedSeq*)p, k, collapse != 0);
+    memcpy(out, v.data(), v.size() * 2);
+    return (long long)v.size();
+}
+
+void* dpo_byte_new(const char* ascii, long long n) { return new ByteSeq(NewByteSequence(std::string(ascii, (size_t)n))); }
+void dpo_byte_free(void* p) { delete (ByteSeq*)p; }
+void* dpo_byte_sub(void* p, long long start, long long end) { return new ByteSeq(SubSequence(*(ByteSeq*)p, start, end)); }
+void* dpo_byte_rc(void* p) { return new ByteSeq(ReverseComplement(*(ByteSeq*)p)); }
+long long dpo_byte_len(void* p) { return (long long)((ByteSeq*)p)->data.size(); }
+void dpo_byte_fields(void* p, long long* out2) {
+    out2[0] = ((ByteSeq*)p)->offset;
+    out2[1] = ((ByteSeq*)p)->inset;
+}
+void dpo_byte_string(void* p, char* out) {
+    std::string s = String(*(ByteSeq*)p);
+    memcpy(out, s.data(), s.size());
+}
+long long dpo_byte_kmer_at(void* p, long long index, long long k) { return KmerAt(*(ByteSeq*)p, index, k); }
+long long dpo_byte_next_kmer(void* p, long long cur, long long mask, long long idx) {
+    return NextKmer(*(ByteSeq*)p, cur, mask, idx);
+}
+long long dpo_byte_count_kmers(void* p, long long upTo, long long k, long long mask, const unsigned char* seeds) {
+    return CountKmers(*(ByteSeq*)p, upTo, k, mask, seeds);
+}
+long long dpo_byte_count_kmers_between(void* p, long long from, long long to, long long upTo, long long k,
+                                       long long mask, const unsigned char* seeds) {
+    return CountKmersBetween(*(ByteSeq*)p, from, to, upTo, k, mask, seeds);
+}
+long long dpo_byte_write_segments(void* p, long long k, long long mask, const unsigned char* seeds, long long* segments) {
+    ByteSeq* s = (ByteSeq*)p;
+    size_t cap = (size_t)(2 * ((long long)s->data.size() + 16) + 1);
+    for (size_t i = 0; i < cap; i++) segments[i] = INT64_MIN;
+    WriteSegments(*s, segments, k, mask, seeds);
+    size_t last = cap;
+    while (last > 0 && segments[last - 1] == INT64_MIN) last--;
+    return (long long)last;
+}
+long long dpo_byte_short_kmers(void* p, long long k, int collapse, unsigned short* out) {
+    std::vector<uint16_t> v = ShortKmers(*(ByteSeq*)p, k, collapse != 0);
+    memcpy(out, v.data(), v.size() * 2);
+    return (long long)v.size();
+}
+long long dpo_kmer_value(const char* s, long long n) { return KmerValue(std::string(s, (size_t)n)); }
+void dpo_pack_bytes(const unsigned char* s, long long n, unsigned char* data) { packBytes(s, (size_t)n, data); }
+
+// ----- bitsets ----------------------------------------------------------------
+void* dpo_intset_new() { return new IntSet(NewIntSet()); }
+void dpo_intset_free(void* p) { delete (IntSet*)p; }
+void dpo_intset_add(void* p, unsigned long long x) { Add(*(IntSet*)p, x); }
+int dpo_intset_contains(void* p, unsigned long long x) { return Contains(*(IntSet*)p, x) ? 1 : 0; }
+unsigned long long dpo_intset_size(void* p) { return ((IntSet*)p)->count; }
+unsigned long long dpo_intset_count_intersection(void* a, void* b) { return CountIntersection(*(IntSet*)a, *(IntSet*)b); }
+long long dpo_intset_count_intersection_to(void* a, void* b, long long maxCount) {
+    DPO_TRY return (long long)CountIntersectionTo(*(IntSet*)a, *(IntSet*)b, maxCount);
+    DPO_CATCH(-1)
+}
+long long dpo_get_shared_ids(void** sets, long long n, long long minCount, int fast, unsigned long long* out,
+                             long long cap) {
+    DPO_TRY std::vector<const IntSet*> v;
+    for (long long i = 0; i < n; i++) v.push_back((const IntSet*)sets[i]);
+    std::vector<uint64_t> ids = GetSharedIDs(v, minCount, fast != 0);
+    for (size_t i = 0; i < ids.size() && (long long)i < cap; i++) out[i] = ids[i];
+    return (long long)ids.size();
+    DPO_CATCH(-1)
+}
+
+// ----- k-mer statistics ---------------------------------------------------------
+// values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
+int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {
+    DPO_TRY PackedSeq ref = NewPackedSequence(0, std::string(ref_ascii, (size_t)n), nullptr);
+    std::vector<uint64_t> counts;
+    KmerOccurrences(ref, k, counts);
+    std::vector<double> v = KmerValues(counts, k);
+    memcpy(values_out, v.data(), v.size() * sizeof(double));
+    return 0;
+    DPO_CATCH(1)
+}
+int dpo_kmer_counts(const char* ref_ascii, long long n, int k, unsigned long long* counts_out) {
+    DPO_TRY PackedSeq ref = NewPackedSequence(0, std::string(ref_ascii, (size_t)n), nullptr);
+    std::vector<uint64_t> counts;
+    KmerOccurrences(ref, k, counts);
+    memcpy(counts_out, counts.data(), counts.size() * sizeof(uint64_t));
+    return 0;
+    DPO_CATCH(1)
+}
+
+// ----- mapper -----------------------------------------------------------------
+struct OMapper {
+    Mapper m;
+    Counters counters;
+};
+
+void* dpo_mapper_new(const char* ref_ascii, long long ref_len, int circular, int k, const double* kmer_values,
+                     int seed_rate, int edge_size, int chunk_size) {
+    DPO_TRY OMapper* om = new OMapper();
+    PackedSeq ref = NewPackedSequence(0, std::string(ref_ascii, (size_t)ref_len), nullptr);
+    NewMapper(om->m, ref, circular != 0, k, kmer_values, seed_rate, edge_size, chunk_size);
+    om->m.refName = "ref";
+    return om;
+    DPO_CATCH(nullptr)
+}
+void dpo_mapper_free(void* p) { delete (OMapper*)p; }
+long long dpo_mapper_num_seeds(void* p) { return ((OMapper*)p)->m.index.size; }
+long long dpo_mapper_num_chunks(void* p) { return (long long)((OMapper*)p)->m.index.sequences.size(); }
+// seed k-mers in seed-id order
+void dpo_mapper_seed_kmers(void* p, long long* out) {
+    OMapper* om = (OMapper*)p;
+    for (long long i = 0; i < om->m.index.size; i++) out[i] = om->m.index.seedMap[(size_t)i];
+}
+// chunk c: fields {offset, inset, length, nseeds}; segments (gap, kmer(not seed id), gap, ...)
+long long dpo_mapper_chunk(void* p, long long c, long long* fields4, long long* segments, long long cap) {
+    OMapper* om = (OMapper*)p;
+    const SeedSequence& s = om->m.index.sequences[(size_t)c];
+    fields4[0] = s.offset;
+    fields4[1] = s.inset;
+    fields4[2] = s.length;
+    fields4[3] = s.GetNumSeeds();
+    if (segments) {
+        for (size_t i = 0; i < s.segments.size() && (long long)i < cap; i++) {
+            segments[i] = (i & 1) ? om->m.index.seedMap[(size_t)s.segments[i]] : s.segments[i];
+        }
+    }
+    return (long long)s.segments.size();
+}
+
+// Stage dump for one window query (performMapping's inputs): the gapped-seed list of one strand.
+// Seeds are reported as k-mer values (seed ids are an arbitrary labelling).
+long long dpo_window_segments(void* p, const char* read_ascii, long long read_len, long long start, long long end,
+                              int whole, int rc, long long* segments, long long cap, long long* fields3) {
+    DPO_TRY OMapper* om = (OMapper*)p;
+    PackedSeq read = NewPackedSequence(0, std::string(read_ascii, (size_t)read_len), nullptr);
+    PackedSeq w = whole ? read : SubSequence(read, start, end);
+    if (rc) w = ReverseComplement(w);
+    SeedSequence s = NewSeedSequence(om->m.index, w, nullptr);
+    for (size_t i = 0; i < s.segments.size() && (long long)i < cap; i++)
+        segments[i] = (i & 1) ? om->m.index.seedMap[(size_t)s.segments[i]] : s.segments[i];
+    fields3[0] = s.offset;
+    fields3[1] = s.inset;
+    fields3[2] = s.length;
+    return (long long)s.segments.size();
+    DPO_CATCH(-1)
+}
+// candidates of one window strand (SeedIndex.Matches)
+long long dpo_window_candidates(void* p, const char* read_ascii, long long read_len, long long start, long long end,
+                                int whole, int rc, long long* out, long long cap) {
+    DPO_TRY OMapper* om = (OMapper*)p;
+    PackedSeq read = NewPackedSequence(0, std::string(read_ascii, (size_t)read_len), nullptr);
+    PackedSeq w = whole ? read : SubSequence(read, start, end);
+    if (rc) w = ReverseComplement(w);
+    SeedSequence s = NewSeedSequence(om->m.index, w, nullptr);
+    std::vector<uint64_t> ids = Matches(om->m.index, s, 0.25, nullptr);
+    for (size_t i = 0; i < ids.size() && (long long)i < cap; i++) out[i] = (long long)ids[i];
+    return (long long)ids.size();
+    DPO_CATCH(-1)
+}
+// performMapping of one window: rows of 6 {Start, End, QueryOffset, QueryInset, RC, ids}
+long long dpo_window_mappings(void* p, const char* read_ascii, long long read_len, long long start, long long end,
+                              int whole, long long* out, long long cap_rows) {
+    DPO_TRY OMapper* om = (OMapper*)p;
+    PackedSeq read = NewPackedSequence(0, std::string(read_ascii, (size_t)read_len), nullptr);
+    PackedSeq w = whole ? read : SubSequence(read, start, end);
+    std::vector<Mapping> r = performMappingPublic(om->m, w, nullptr);
+    for (size_t i = 0; i < r.size() && (long long)i < cap_rows; i++) {
+        out[i * 6 + 0] = r[i].Start;
+        out[i * 6 + 1] = r[i].End;
+        out[i * 6 + 2] = r[i].QueryOffset;
+        out[i * 6 + 3] = r[i].QueryInset;
+        out[i * 6 + 4] = r[i].RC ? 1 : 0;
+        out[i * 6 + 5] = r[i].ids;
+    }
+    return (long long)r.size();
+    DPO_CATCH(-1)
+}
+
+// Map a batch of reads with `threads` host threads. Results: out_offsets[n+1] and rows of 6 (as above) in a
+// library-owned buffer returned through *rows_out (free with dpo_free). counters_out (11 long longs) optional.
+int dpo_map_batch(void* p, long long n_reads, const char* bases, const long long* offsets, int threads,
+                  long long** rows_out, long long* out_offsets, long long* counters_out) {
+    DPO_TRY OMapper* om = (OMapper*)p;
+    std::vector<std::vector<Mapping>> res((size_t)n_reads);
+    if (threads < 1) threads = 1;
+    std::vector<Counters> cs((size_t)threads);
+    std::atomic<long long> next(0);
+    std::vector<std::string> errs((size_t)threads);
+    auto work = [&](int t) {
+        try {
+            for (;;) {
+                long long i0 = next.fetch_add(64);
+                if (i0 >= n_reads) break;
+                long long i1 = std::min(n_reads, i0 + 64);
+                for (long long i = i0; i < i1; i++) {
+                    PackedSeq q = NewPackedSequence(i, std::string(bases + offsets[i], (size_t)(offsets[i + 1] - offsets[i])),
+                                                    nullptr);
+                    res[(size_t)i] = Map(om->m, q, &cs[(size_t)t]);
+                }
+            }
+        } catch (const std::exception& ex) {
+            errs[(size_t)t] = ex.what();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    long long total = 0;
+    for (long long i = 0; i < n_reads; i++) {
+        out_offsets[i] = total;
+        total += (long long)res[(size_t)i].size();
+    }
+    out_offsets[n_reads] = total;
+    long long* rows = (long long*)malloc(sizeof(long long) * 6 * (size_t)(total > 0 ? total : 1));
+    long long r = 0;
+    for (long long i = 0; i < n_reads; i++) {
+        for (const Mapping& mp : res[(size_t)i]) {
+            rows[r * 6 + 0] = mp.Start;
+            rows[r * 6 + 1] = mp.End;
+            rows[r * 6 + 2] = mp.QueryOffset;
+            rows[r * 6 + 3] = mp.QueryInset;
+            rows[r * 6 + 4] = mp.RC ? 1 : 0;
+            rows[r * 6 + 5] = mp.ids;
+            r++;
+        }
+    }
+    *rows_out = rows;
+    if (counters_out) {
+        Counters tot;
+        for (auto& c : cs) tot.add(c);
+        om->counters.add(tot);
+        counters_out[0] = tot.windows;
+        counters_out[1] = tot.kmer_lookups;
+        counters_out[2] = tot.query_seeds;
+        counters_out[3] = tot.posting_runs;
+        counters_out[4] = tot.posting_entries;
+        counters_out[5] = tot.candidates;
+        counters_out[6] = tot.cand_pass;
+        counters_out[7] = tot.chain_cells;
+        counters_out[8] = tot.chains;
+        counters_out[9] = tot.mappings;
+        counters_out[10] = tot.sort_ties_unpinned;
+    }
+    return 0;
+    DPO_CATCH(1)
+}
+void dpo_free(void* p) { free(p); }
+
+}  // extern "C"
