@@ -1,0 +1,300 @@
+"""downpore_b200 — B200-native (sm_100a) implementation of the `downpore map` hot path.
+
+Python mirror of the reference's Go interface for this path (mapping/mapping.go:22-26, :67):
+
+    mapper = NewMapper(reference, circular, k, kmer_values, seed_rate, edge_size, chunk_size)
+    mappings, offsets = mapper.map_batch(bases, read_offsets)      # Mapper.Map for every read
+    line = mapper.as_string(mapping, query_name, query_len)        # Mapper.AsString
+
+Everything runs through the C ABI of include/downpore_b200.h (libdownpore_b200.so, built from csrc/ by
+__graft_entry__.build() or `make -C downpore_b200/csrc`). There is no CPU fallback: importing works anywhere, but any
+call fails loudly if the CUDA library is missing or no GPU is usable.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdownpore_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+c_i64 = ctypes.c_int64
+c_vp = ctypes.c_void_p
+
+MAPPING_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("q_offset", "<i4"), ("q_inset", "<i4"), ("ids", "<i4"),
+                          ("rc", "u1"), ("pad", "u1", (3,))], align=False)
+assert MAPPING_DTYPE.itemsize == 32
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("ms_total", ctypes.c_double), ("ms_pack", ctypes.c_double), ("ms_extract", ctypes.c_double),
+                ("ms_lookup", ctypes.c_double), ("ms_chain", ctypes.c_double), ("ms_host_logic", ctypes.c_double),
+                ("ms_h2d", ctypes.c_double), ("rounds", c_i64), ("windows", c_i64), ("kmer_lookups", c_i64),
+                ("query_seeds", c_i64), ("posting_runs", c_i64), ("posting_entries", c_i64), ("candidates", c_i64),
+                ("chain_cells", c_i64), ("mappings", c_i64), ("kernel_launches", c_i64), ("bases", c_i64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(force=False):
+    """Compile csrc/ for sm_100a into libdownpore_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "downpore_b200.h"))
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+_SIGNATURES = {
+    "dp_last_error": (ctypes.c_char_p, []),
+    "dp_version": (ctypes.c_char_p, []),
+    "dp_free": (None, [c_vp]),
+    "dp_mapper_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "dp_mapper_destroy": (None, [c_vp]),
+    "dp_mapper_map_batch": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
+    "dp_mapper_map_batch_device": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp),
+                                                  ctypes.POINTER(c_vp)]),
+    "dp_mapper_paf_line": (ctypes.c_int, [c_vp, c_vp, ctypes.c_char_p, c_i64, ctypes.c_char_p, c_vp, ctypes.c_int]),
+    "dp_mapper_get_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(Stats)]),
+    "dp_mapper_index_info": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_mapper_seed_kmers": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_mapper_chunk": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dp_mapper_probe_window": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_i64,
+                                              c_vp, c_vp, c_i64, c_vp, c_vp, c_i64]),
+    "dp_pack": (ctypes.c_int, [c_vp, c_i64, c_vp, ctypes.c_int]),
+    "dp_kmer_counts": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, ctypes.c_int]),
+}
+
+
+def exported_symbols():
+    """Names declared in include/downpore_b200.h."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("downpore_b200: %s is missing — run __graft_entry__.build() (there is no CPU fallback)"
+                               % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class DownporeError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc:
+        raise DownporeError(lib().dp_last_error().decode())
+
+
+def _u8(x):
+    if isinstance(x, str):
+        x = x.encode()
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def pack(ascii_seq, device=0):
+    """sequence.NewPackedSequence (sequence/sequence.go:67-93) through the device pack kernel -> bytes."""
+    a = _u8(ascii_seq)
+    out = np.zeros((a.size + 3) // 4, dtype=np.uint8)
+    _check(lib().dp_pack(a.ctypes.data, a.size, out.ctypes.data, device))
+    return out
+
+
+def kmer_counts(ascii_seq, k, counts=None, device=0):
+    """sequtil.KmerOccurrences (util/sequtil/kmers.go:34-69) for one record, accumulated into `counts`."""
+    a = _u8(ascii_seq)
+    if counts is None:
+        counts = np.zeros(4 ** k, dtype=np.uint64)
+    _check(lib().dp_kmer_counts(a.ctypes.data, a.size, k, counts.ctypes.data, device))
+    return counts
+
+
+def kmer_values(counts, k):
+    """values[] of commands/map.go:46-71 from a k-mer histogram.
+
+    Host-side numpy: in the drop-in this stays in the Go host (the top-1 % cut depends on Go's sort.Sort tie order,
+    SURVEY Q10). Tie order here: (count, k-mer id) ascending, the same canonical order the oracle uses.
+    """
+    counts = np.asarray(counts, dtype=np.uint64).copy()
+    n = counts.size
+    tot = float(counts.sum(dtype=np.uint64))
+    freq = counts.astype(np.float64) / tot
+    target = 0.000005
+    values = np.where(freq <= target, 1.0 - (target - freq), 1.0 - (freq - target))
+    values[counts < 3] = 0.0
+    # TopOccurrences (util/sequtil/kmers.go:87-112): in-place forward/rc merge over ascending ids
+    ids = np.arange(n, dtype=np.int64)
+    rc = np.zeros(n, dtype=np.int64)
+    x = ids.copy()
+    for _ in range(k):
+        rc = (rc << 2) | ((x ^ 3) & 3)
+        x >>= 2
+    merged = counts + counts[rc]
+    merged = np.where(rc == ids, merged, 2 * merged)  # a non-palindromic pair is summed twice by the in-place loop
+    order = np.argsort(merged, kind="stable")
+    top = order[n - n // 100:]
+    values[top] = 0.0
+    values[0] = 0.0
+    return values
+
+
+class Mapper:
+    """mapping.Mapper (mapping/mapping.go:22-26) bound to one CUDA device."""
+
+    def __init__(self, reference, kmer_values, circular=True, k=11, seed_rate=40, edge_size=1000, chunk_size=10000,
+                 device=0, ref_name="ref"):
+        self._h = None
+        ref = _u8(reference)
+        vals = np.ascontiguousarray(kmer_values, dtype=np.float64)
+        if vals.size != 4 ** k:
+            raise ValueError("kmer_values must hold 4^k doubles")
+        h = c_vp()
+        _check(lib().dp_mapper_create(ref.ctypes.data, ref.size, int(bool(circular)), k, vals.ctypes.data, seed_rate,
+                                      edge_size, chunk_size, device, ctypes.byref(h)))
+        self._h = h
+        self.k = k
+        self.circular = bool(circular)
+        self.ref_len = int(ref.size)
+        self.ref_name = ref_name
+        self.edge_size = edge_size
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().dp_mapper_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _collect(self, n, out_p, off_p):
+        off = np.ctypeslib.as_array(ctypes.cast(off_p, ctypes.POINTER(c_i64)), shape=(n + 1,)).copy()
+        total = int(off[n])
+        if total:
+            raw = ctypes.string_at(out_p, total * MAPPING_DTYPE.itemsize)
+            maps = np.frombuffer(raw, dtype=MAPPING_DTYPE).copy()
+        else:
+            maps = np.zeros(0, dtype=MAPPING_DTYPE)
+        lib().dp_free(out_p)
+        lib().dp_free(off_p)
+        return maps, off
+
+    def map_batch(self, bases, offsets):
+        """Mapper.Map over a batch. bases: concatenated ASCII (numpy uint8 or a pinned torch tensor's numpy view);
+        offsets: n+1 int64. Returns (mappings[MAPPING_DTYPE], out_offsets[n+1])."""
+        bases = _u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        out_p, off_p = c_vp(), c_vp()
+        _check(lib().dp_mapper_map_batch(self._h, n, bases.ctypes.data, offsets.ctypes.data, ctypes.byref(out_p),
+                                         ctypes.byref(off_p)))
+        return self._collect(n, out_p, off_p)
+
+    def map_batch_ptr(self, host_ptr, offsets):
+        """Same as map_batch for a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        out_p, off_p = c_vp(), c_vp()
+        _check(lib().dp_mapper_map_batch(self._h, n, host_ptr, offsets.ctypes.data, ctypes.byref(out_p),
+                                         ctypes.byref(off_p)))
+        return self._collect(n, out_p, off_p)
+
+    def map_batch_device(self, device_ptr, offsets):
+        """Same, with the ASCII reads already resident on this mapper's device (device_ptr: int)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        out_p, off_p = c_vp(), c_vp()
+        _check(lib().dp_mapper_map_batch_device(self._h, n, device_ptr, offsets.ctypes.data, ctypes.byref(out_p),
+                                                ctypes.byref(off_p)))
+        return self._collect(n, out_p, off_p)
+
+    def as_string(self, mapping, query_name, query_len):
+        """Mapper.AsString (mapping/mapping.go:112-122): one PAF line."""
+        rec = np.zeros(1, dtype=MAPPING_DTYPE)
+        rec[0] = mapping
+        buf = ctypes.create_string_buffer(1024)
+        n = lib().dp_mapper_paf_line(self._h, rec.ctypes.data, query_name.encode(), query_len, self.ref_name.encode(),
+                                     buf, 1024)
+        if n < 0:
+            raise DownporeError("PAF line too long")
+        return buf.value.decode()
+
+    def paf_lines(self, maps, out_off, names, lengths):
+        lines = []
+        for i in range(len(out_off) - 1):
+            for j in range(out_off[i], out_off[i + 1]):
+                lines.append(self.as_string(maps[j], names[i], int(lengths[i])))
+        return lines
+
+    def stats(self):
+        s = Stats()
+        _check(lib().dp_mapper_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def index_info(self):
+        out = np.zeros(5, dtype=np.int64)
+        _check(lib().dp_mapper_index_info(self._h, out.ctypes.data))
+        return dict(num_seeds=int(out[0]), num_chunks=int(out[1]), chunk_postings=int(out[2]),
+                    seed_postings=int(out[3]), index_bytes=int(out[4]))
+
+    # ---- test probes ----
+    def seed_kmers(self):
+        out = np.zeros(self.index_info()["num_seeds"], dtype=np.int64)
+        _check(lib().dp_mapper_seed_kmers(self._h, out.ctypes.data))
+        return out
+
+    def chunk(self, c):
+        f = np.zeros(4, dtype=np.int64)
+        _check(lib().dp_mapper_chunk(self._h, c, f.ctypes.data, None, None))
+        n = int(f[3])
+        pos = np.zeros(max(n, 1), dtype=np.int32)
+        kmer = np.zeros(max(n, 1), dtype=np.int64)
+        _check(lib().dp_mapper_chunk(self._h, c, f.ctypes.data, pos.ctypes.data, kmer.ctypes.data))
+        return dict(offset=int(f[0]), inset=int(f[1]), length=int(f[2]), nseeds=n, pos=pos[:n], kmer=kmer[:n])
+
+    def probe_window(self, read, start=0, end=0, whole=False):
+        """One performMapping call: per-strand seeds, candidates, and the window's mappings."""
+        a = _u8(read)
+        cap = 2 * (a.size + 8)
+        ns = np.zeros(2, dtype=np.int32)
+        spos = np.zeros(cap, dtype=np.int32)
+        skmer = np.zeros(cap, dtype=np.int64)
+        nc = np.zeros(2, dtype=np.int32)
+        ccap = 4096
+        cand = np.zeros(ccap, dtype=np.int32)
+        nm = np.zeros(1, dtype=np.int32)
+        maps = np.zeros(256, dtype=MAPPING_DTYPE)
+        _check(lib().dp_mapper_probe_window(self._h, a.ctypes.data, a.size, start, end, int(whole), ns.ctypes.data,
+                                            spos.ctypes.data, skmer.ctypes.data, cap, nc.ctypes.data, cand.ctypes.data,
+                                            ccap, nm.ctypes.data, maps.ctypes.data, 256))
+        f, r = int(ns[0]), int(ns[1])
+        return dict(seeds=[(spos[:f].copy(), skmer[:f].copy()), (spos[f:f + r].copy(), skmer[f:f + r].copy())],
+                    candidates=[cand[:nc[0]].copy(), cand[nc[0]:nc[0] + nc[1]].copy()], mappings=maps[:nm[0]].copy())
+
+
+def NewMapper(reference, circular, k, kmer_values, seed_rate, edge_size, chunk_size, num_workers=0, device=0):
+    """mapping.NewMapper (mapping/mapping.go:67). num_workers is accepted for signature parity and ignored: the
+    goroutine pool is replaced by batched GPU rounds."""
+    return Mapper(reference, kmer_values, circular=circular, k=k, seed_rate=seed_rate, edge_size=edge_size,
+                  chunk_size=chunk_size, device=device)

@@ -1,0 +1,1135 @@
+// downpore_b200 — host driver and C ABI (include/downpore_b200.h). No CPU fallback: everything fails loudly without
+// a usable CUDA device.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/downpore_b200.h"
+#include "dp_common.cuh"
+#include "dp_host_map.hpp"
+#include "dp_index.cuh"
+#include "dp_map.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + \
+                                     std::to_string(__LINE__));                                               \
+    } while (0)
+
+template <class T>
+struct DBuf {  // device buffer, grow-only
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        release();
+        size_t want = n + n / 8 + 64;
+        CK(cudaMalloc((void**)&p, want * sizeof(T)));
+        cap = want;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+template <class T>
+struct HBuf {  // pinned host buffer, grow-only
+    T* p = nullptr;
+    size_t cap = 0;
+    ~HBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = n + n / 8 + 64;
+        CK(cudaMallocHost((void**)&p, want * sizeof(T)));
+        cap = want;
+    }
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init() {
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+    }
+    ~Timer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct dp_mapper {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    // parameters
+    int k = 0, circular = 0, seedRate = 0, edge = 0, chunkSize = 0;
+    long long refLen = 0;
+    // index
+    DBuf<unsigned> refWords;
+    DBuf<uint2> table;
+    DBuf<unsigned> seedOff, seedChunks, chunkOff, chunkSeed;
+    DBuf<int> chunkPos, chunkScanLen;
+    DBuf<long long> chunkOffset, chunkInset;
+    std::vector<long long> hChunkOffset, hChunkInset;
+    std::vector<int> hChunkLen, hChunkScanLen;
+    DpIndexDev I{};
+    long long nChunkPostings = 0, nSeedPostings = 0;
+    size_t indexBytes = 0;
+    // map workspace (sized per sub-batch, grow-only)
+    DBuf<unsigned char> dAscii;
+    DBuf<long long> dSeqOff, dWordOff;
+    DBuf<int> dReadLen;
+    DBuf<unsigned> dWords;
+    DBuf<DpWindow> dWins;
+    DBuf<unsigned> wsOff, qSeed, candChunk;
+    DBuf<int> wsN, qPos, candN, outN;
+    DBuf<unsigned short> candDistinct;
+    DBuf<DpMappingDev> outMaps;
+    DBuf<unsigned long long> cursor;
+    DBuf<DpCounters> dCtr;
+    // lookup scratch
+    DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters;
+    DBuf<unsigned char> lsFirst;
+    DBuf<unsigned short> lsOrder;
+    // chain scratch
+    DBuf<unsigned> csHashKey, csRqSeed, csRsSeed;
+    DBuf<unsigned char> csHashFlag;
+    DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
+    DBuf<DpMappingDev> csResults;
+    HBuf<int> hOutN;
+    HBuf<DpMappingDev> hOutMaps;
+    HBuf<DpWindow> hWins;
+    HBuf<unsigned char> hStage;
+    std::vector<Timer> timers;
+    dp_stats stats{};
+    int candStride = 0, outStride = 16, resultCap = 128, chainCap = 64;
+    int extractWarps = 0, lookupWarps = 0, chainWarps = 0;
+
+    ~dp_mapper() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------------------------
+// index construction (mapping.NewMapper, mapping/mapping.go:67-109)
+// ----------------------------------------------------------------------------------------------------------------
+void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
+    const int k = M.k;
+    const long long L = M.refLen;
+    const int e = M.edge;
+    cudaStream_t st = M.stream;
+    const long long nTable = (1ll << (2 * k)) / 32;
+
+    // ---- pack the reference (+ the circular join sequence, mapping.go:93-95) ----
+    long long refWordsN = (L + 15) / 16;
+    long long joinWord = refWordsN + 4;  // zero gap: scans that over-read the reference end see zeros, like the oracle
+    long long joinLen = M.circular ? 2ll * e : 0;
+    long long totalWords = joinWord + (joinLen + 15) / 16 + 4;
+    M.refWords.reserve((size_t)totalWords);
+    CK(cudaMemsetAsync(M.refWords.p, 0, M.refWords.cap * sizeof(unsigned), st));
+    {
+        DBuf<unsigned char> dA;
+        dA.reserve((size_t)(L + joinLen + 64));
+        CK(cudaMemcpyAsync(dA.p, ref, (size_t)L, cudaMemcpyHostToDevice, st));
+        if (M.circular) {
+            CK(cudaMemcpyAsync(dA.p + L, ref + (L - e), (size_t)e, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dA.p + L + e, ref, (size_t)e, cudaMemcpyHostToDevice, st));
+        }
+        DBuf<long long> dOff, dWord;
+        // one warp per sequence would serialise a whole genome on one warp: split the reference into slices
+        // (the kernel takes (offset, word) pairs, so slices of 16-base multiples are independent "sequences")
+        const long long slice = 1 << 14;  // bases per slice, multiple of 16
+        long long nSl = (L + slice - 1) / slice;
+        std::vector<long long> so((size_t)nSl + 2), sw((size_t)nSl + 1);
+        for (long long i = 0; i < nSl; i++) {
+            so[(size_t)i] = i * slice;
+            sw[(size_t)i] = i * slice / 16;
+        }
+        so[(size_t)nSl] = L;
+        long long nSeq = nSl;
+        if (M.circular) {
+            sw[(size_t)nSl] = joinWord;
+            so[(size_t)nSl + 1] = L + joinLen;
+            nSeq = nSl + 1;
+        }
+        dOff.reserve(so.size());
+        dWord.reserve(sw.size());
+        CK(cudaMemcpyAsync(dOff.p, so.data(), so.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dWord.p, sw.data(), sw.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        int blocks = std::min<long long>((nSeq + 7) / 8, (long long)M.smCount * 8);
+        dp_pack_kernel<<<blocks, 256, 0, st>>>(dA.p, dOff.p, dWord.p, M.refWords.p, nSeq);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+    }
+
+    // ---- AddSingleSeeds (seeds/seeds.go:160-200) ----
+    DBuf<unsigned> bits;
+    bits.reserve((size_t)nTable);
+    CK(cudaMemsetAsync(bits.p, 0, (size_t)nTable * sizeof(unsigned), st));
+    {
+        DpSeedSelParams P;
+        P.refLen = L;
+        P.rate = M.seedRate;
+        P.k = k;
+        P.nWindows = (L - M.seedRate > 0) ? (L - M.seedRate + M.seedRate - 1) / M.seedRate : 0;
+        int finalLen = (int)(L % 4);
+        P.skipBack = 4 - finalLen;
+        if (P.nWindows > 0) {
+            if (P.nWindows >= 0xffffffffll) throw std::runtime_error("reference too long for 32-bit window ids");
+            DBuf<double> dVal;
+            dVal.reserve((size_t)(1ull << (2 * k)));
+            CK(cudaMemcpyAsync(dVal.p, values, sizeof(double) << (2 * k), cudaMemcpyHostToDevice, st));
+            DBuf<unsigned> best, f;
+            DBuf<unsigned char> needA, needB;
+            DBuf<unsigned> changed;
+            best.reserve((size_t)P.nWindows);
+            f.reserve((size_t)(1ull << (2 * k)));
+            needA.reserve((size_t)P.nWindows);
+            needB.reserve((size_t)P.nWindows);
+            changed.reserve(1);
+            int blocks = div_up(P.nWindows, 256);
+            dp_seed_best_kernel<<<blocks, 256, 0, st>>>(M.refWords.p, dVal.p, P, best.p);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(needA.p, 1, (size_t)P.nWindows, st));
+            unsigned char* cur = needA.p;
+            unsigned char* nxt = needB.p;
+            int iters = 0;
+            for (;;) {
+                CK(cudaMemsetAsync(f.p, 0xff, sizeof(unsigned) << (2 * k), st));
+                CK(cudaMemsetAsync(changed.p, 0, sizeof(unsigned), st));
+                dp_seed_fmin_kernel<<<blocks, 256, 0, st>>>(best.p, cur, P.nWindows, f.p);
+                dp_seed_need_kernel<<<blocks, 256, 0, st>>>(M.refWords.p, f.p, P, cur, nxt, changed.p);
+                CK(cudaGetLastError());
+                unsigned hc = 0;
+                CK(cudaMemcpyAsync(&hc, changed.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                std::swap(cur, nxt);
+                iters++;
+                if (!hc) break;
+                if (iters > 1000000) throw std::runtime_error("seed selection did not converge");
+            }
+            dp_seed_setbits_kernel<<<blocks, 256, 0, st>>>(best.p, cur, P.nWindows, bits.p);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    // ---- {flags, rank} table ----
+    M.table.reserve((size_t)nTable);
+    unsigned numSeeds = 0;
+    {
+        DBuf<unsigned> pc, prefix;
+        pc.reserve((size_t)nTable + 1);
+        prefix.reserve((size_t)nTable + 1);
+        dp_popc_kernel<<<div_up(nTable, 256), 256, 0, st>>>(bits.p, pc.p, nTable);
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, pc.p, prefix.p, (int)nTable + 1, st);
+        DBuf<unsigned char> tmp;
+        tmp.reserve(tmpBytes);
+        CK(cudaMemsetAsync(pc.p + nTable, 0, sizeof(unsigned), st));
+        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, pc.p, prefix.p, (int)nTable + 1, st));
+        dp_table_kernel<<<div_up(nTable, 256), 256, 0, st>>>(bits.p, prefix.p, M.table.p, nTable);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&numSeeds, prefix.p + nTable, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+
+    // ---- chunk list in the producer's emission order (mapping.go:80-95; canonical ids) ----
+    std::vector<DpChunkDesc> descs;
+    M.hChunkOffset.clear();
+    M.hChunkInset.clear();
+    M.hChunkLen.clear();
+    M.hChunkScanLen.clear();
+    for (int j = 0; j < 10; j++) {
+        long long start = (long long)j * M.chunkSize;
+        long long step = (long long)M.chunkSize * 10 - e;
+        for (long long i = start; i < L - M.chunkSize / 2; i += step) {
+            long long end = std::min<long long>(i + M.chunkSize, L);
+            DpChunkDesc d;
+            d.base = i;
+            d.nVisit = (int)(end - i - k + 1);
+            d.pad = 0;
+            descs.push_back(d);
+            M.hChunkOffset.push_back(i);
+            M.hChunkInset.push_back(L - (end - 1));  // SubSequence: inset + length - (end-1)  (Q3)
+            M.hChunkLen.push_back((int)(end - i));
+            M.hChunkScanLen.push_back((int)(end - i));
+        }
+    }
+    if (M.circular) {
+        DpChunkDesc d;
+        d.base = joinWord * 16;
+        int jl = 2 * e;
+        d.nVisit = jl - k + 1 - ((jl % 4 == 0) ? 4 : 0);  // raw packedSequence: Q2
+        d.pad = 0;
+        descs.push_back(d);
+        M.hChunkOffset.push_back(L - e);      // Append keeps the left part's offset ...
+        M.hChunkInset.push_back(L - (e - 1)); // ... and the right part's inset (sequence.go:173-174)
+        M.hChunkLen.push_back(jl);
+        M.hChunkScanLen.push_back(d.nVisit + k - 1);
+    }
+    const unsigned C = (unsigned)descs.size();
+    if (C == 0) throw std::runtime_error("reference shorter than chunk_size/2: no chunks to index");
+    DBuf<DpChunkDesc> dDescs;
+    dDescs.reserve(C);
+    CK(cudaMemcpyAsync(dDescs.p, descs.data(), C * sizeof(DpChunkDesc), cudaMemcpyHostToDevice, st));
+    M.chunkOffset.reserve(C);
+    M.chunkInset.reserve(C);
+    M.chunkScanLen.reserve(C);
+    CK(cudaMemcpyAsync(M.chunkOffset.p, M.hChunkOffset.data(), C * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(M.chunkInset.p, M.hChunkInset.data(), C * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(M.chunkScanLen.p, M.hChunkScanLen.data(), C * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    // ---- chunk scan: count, exclusive scan, write ----
+    DBuf<unsigned> counts;
+    counts.reserve(C + 1);
+    M.chunkOff.reserve(C + 1);
+    CK(cudaMemsetAsync(counts.p, 0, (C + 1) * sizeof(unsigned), st));
+    int scanBlocks = std::min<int>(div_up(C, 8), M.smCount * 8);
+    dp_chunk_scan_kernel<<<scanBlocks, 256, 0, st>>>(M.refWords.p, M.table.p, dDescs.p, C, k, 0, counts.p, nullptr,
+                                                     nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+    {
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts.p, M.chunkOff.p, (int)C + 1, st);
+        DBuf<unsigned char> tmp;
+        tmp.reserve(tmpBytes);
+        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, counts.p, M.chunkOff.p, (int)C + 1, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    std::vector<unsigned> hCounts(C + 1);
+    CK(cudaMemcpy(hCounts.data(), counts.p, (C + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    unsigned long long P2 = 0;
+    unsigned maxChunkSeeds = 0;
+    for (unsigned c = 0; c < C; c++) {
+        P2 += hCounts[c];
+        maxChunkSeeds = std::max(maxChunkSeeds, hCounts[c]);
+    }
+    if (P2 >= 0xffffffffull) throw std::runtime_error("index too large for 32-bit posting offsets");
+    M.chunkPos.reserve((size_t)P2 + 1);
+    M.chunkSeed.reserve((size_t)P2 + 1);
+    DBuf<unsigned long long> keys, keysSorted;
+    keys.reserve((size_t)P2 + 1);
+    keysSorted.reserve((size_t)P2 + 1);
+    dp_chunk_scan_kernel<<<scanBlocks, 256, 0, st>>>(M.refWords.p, M.table.p, dDescs.p, C, k, 1, nullptr, M.chunkOff.p,
+                                                     M.chunkPos.p, M.chunkSeed.p, keys.p);
+    CK(cudaGetLastError());
+
+    // ---- seed -> distinct chunks: radix sort of (seed, chunk) keys, unique, CSR ----
+    M.seedOff.reserve((size_t)numSeeds + 2);
+    unsigned long long P1 = 0;
+    if (P2 > 0) {
+        int endBit = 32;
+        while ((1ull << (endBit - 32)) < (unsigned long long)numSeeds + 1 && endBit < 64) endBit++;
+        size_t tmpBytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys.p, keysSorted.p, (int)P2, 0, endBit, st);
+        DBuf<unsigned char> tmp;
+        tmp.reserve(tmpBytes);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keys.p, keysSorted.p, (int)P2, 0, endBit, st));
+        DBuf<unsigned long long> nSel;
+        nSel.reserve(1);
+        size_t tmpBytes2 = 0;
+        cub::DeviceSelect::Unique(nullptr, tmpBytes2, keysSorted.p, keys.p, nSel.p, (int)P2, st);
+        DBuf<unsigned char> tmp2;
+        tmp2.reserve(tmpBytes2);
+        CK(cub::DeviceSelect::Unique(tmp2.p, tmpBytes2, keysSorted.p, keys.p, nSel.p, (int)P2, st));
+        CK(cudaMemcpyAsync(&P1, nSel.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    M.seedChunks.reserve((size_t)P1 + 1);
+    {
+        DBuf<unsigned> seedCount;
+        seedCount.reserve((size_t)numSeeds + 2);
+        CK(cudaMemsetAsync(seedCount.p, 0, ((size_t)numSeeds + 2) * sizeof(unsigned), st));
+        if (P1 > 0) {
+            dp_posting_fill_kernel<<<div_up((long long)P1, 256), 256, 0, st>>>(keys.p, (long long)P1, seedCount.p,
+                                                                              M.seedChunks.p);
+            CK(cudaGetLastError());
+        }
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, seedCount.p, M.seedOff.p, (int)numSeeds + 1, st);
+        DBuf<unsigned char> tmp;
+        tmp.reserve(tmpBytes);
+        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, seedCount.p, M.seedOff.p, (int)numSeeds + 1, st));
+        CK(cudaStreamSynchronize(st));
+    }
+
+    DpIndexDev& I = M.I;
+    I.k = k;
+    I.circular = M.circular;
+    I.edge = e;
+    I.maxWindow = 2 * e;
+    I.refLen = L;
+    I.numSeeds = numSeeds;
+    I.numChunks = C;
+    I.maxChunkSeeds = maxChunkSeeds;
+    I.table = M.table.p;
+    I.seedOff = M.seedOff.p;
+    I.seedChunks = M.seedChunks.p;
+    I.chunkOff = M.chunkOff.p;
+    I.chunkPos = M.chunkPos.p;
+    I.chunkSeed = M.chunkSeed.p;
+    I.chunkOffset = M.chunkOffset.p;
+    I.chunkInset = M.chunkInset.p;
+    I.chunkScanLen = M.chunkScanLen.p;
+    M.nChunkPostings = (long long)P2;
+    M.nSeedPostings = (long long)P1;
+    M.indexBytes = M.refWords.bytes() + M.table.bytes() + M.seedOff.bytes() + M.seedChunks.bytes() +
+                   M.chunkOff.bytes() + M.chunkPos.bytes() + M.chunkSeed.bytes() + M.chunkOffset.bytes() +
+                   M.chunkInset.bytes() + M.chunkScanLen.bytes();
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// window rounds
+// ----------------------------------------------------------------------------------------------------------------
+struct Launch {
+    int extractBlocks, lookupBlocks, chainBlocks;
+    int countersInSmem;
+    size_t extractSmem, lookupSmem;
+    int maskWords;
+};
+
+void ensure_window_capacity(dp_mapper& M, size_t nWin, size_t seedEntries) {
+    const DpIndexDev& I = M.I;
+    M.dWins.reserve(nWin);
+    M.wsOff.reserve(2 * nWin);
+    M.wsN.reserve(2 * nWin);
+    M.qSeed.reserve(seedEntries + 64);
+    M.qPos.reserve(seedEntries + 64);
+    M.cursor.reserve(1);
+    M.dCtr.reserve(1);
+    M.candStride = (int)std::min<unsigned>(I.numChunks, 1024u);
+    M.candN.reserve(2 * nWin);
+    M.candChunk.reserve(2 * nWin * (size_t)M.candStride);
+    M.candDistinct.reserve(2 * nWin * (size_t)M.candStride);
+    M.outN.reserve(nWin);
+    M.outMaps.reserve(nWin * (size_t)M.outStride);
+    M.hOutN.reserve(nWin);
+    M.hOutMaps.reserve(nWin * (size_t)M.outStride);
+    // per-warp scratch
+    const int qStride = I.maxWindow + 8;
+    M.extractWarps = M.smCount * 8 * 8;
+    M.lookupWarps = M.smCount * 4 * 8;
+    M.chainWarps = M.smCount * 4 * 8;
+    size_t lw = (size_t)M.lookupWarps;
+    M.lsSeed.reserve(lw * qStride);
+    M.lsOff.reserve(lw * qStride);
+    M.lsPre.reserve(lw * (qStride + 1));
+    M.lsEndW.reserve(lw * qStride);
+    M.lsAll.reserve(lw * qStride);
+    M.lsFirst.reserve(lw * qStride);
+    M.lsOrder.reserve(lw * qStride);
+    if (I.numChunks > 2048) M.lsCounters.reserve(lw * I.numChunks);
+    size_t cw = (size_t)M.chainWarps;
+    int hashSize = 64;
+    while (hashSize < 2 * qStride) hashSize <<= 1;
+    const int sStride = (int)I.maxChunkSeeds + 8;
+    M.csHashKey.reserve(cw * hashSize);
+    M.csHashFlag.reserve(cw * hashSize);
+    M.csRqSeed.reserve(cw * qStride);
+    M.csRqPos.reserve(cw * qStride);
+    M.csRsSeed.reserve(cw * sStride);
+    M.csRsPos.reserve(cw * sStride);
+    M.csChainLen.reserve(cw * qStride);
+    M.csLastB.reserve(cw * qStride);
+    M.csChains.reserve(cw * M.chainCap * 6);
+    M.csResults.reserve(cw * M.resultCap);
+}
+
+enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_N };
+
+// Runs performMapping for `nWin` windows (host array `wins`), leaves counts/mappings in M.hOutN / M.hOutMaps.
+void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
+                 const int* dReadLen) {
+    if (nWin == 0) return;
+    const DpIndexDev& I = M.I;
+    cudaStream_t st = M.stream;
+    size_t seedEntries = 0;
+    for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
+    if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
+    ensure_window_capacity(M, nWin, seedEntries);
+    CK(cudaMemcpyAsync(M.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(M.cursor.p, 0, sizeof(unsigned long long), st));
+
+    const int qStride = I.maxWindow + 8;
+    DpExtractOut Q;
+    Q.wsOff = M.wsOff.p;
+    Q.wsN = M.wsN.p;
+    Q.qSeed = M.qSeed.p;
+    Q.qPos = M.qPos.p;
+    Q.cursor = M.cursor.p;
+    const int maskWords = (I.maxWindow + 31) / 32 + 1;
+    {
+        int warpsPerBlock = 8;
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.extractWarps / 8);
+        size_t smem = (size_t)warpsPerBlock * 2 * maskWords * sizeof(unsigned);
+        CK(cudaEventRecord(M.timers[T_EXTRACT].a, st));
+        dp_extract_kernel<<<blocks, 256, smem, st>>>(I, dWords, dWordOff, M.dWins.p, (int)nWin, Q, maskWords, M.dCtr.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(M.timers[T_EXTRACT].b, st));
+    }
+    {
+        DpLookupScratch S;
+        S.eSeed = M.lsSeed.p;
+        S.eOff = M.lsOff.p;
+        S.ePre = M.lsPre.p;
+        S.eEndW = M.lsEndW.p;
+        S.eFirst = M.lsFirst.p;
+        S.allSeeds = M.lsAll.p;
+        S.order = M.lsOrder.p;
+        S.counters = M.lsCounters.p;
+        S.stride = qStride;
+        int inSmem = I.numChunks <= 2048 ? 1 : 0;
+        int warpsPerBlock = 4;
+        size_t smem = inSmem ? (size_t)warpsPerBlock * I.numChunks * sizeof(unsigned) : 0;
+        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.lookupWarps / 4);
+        CK(cudaEventRecord(M.timers[T_LOOKUP].a, st));
+        dp_lookup_kernel<<<blocks, 128, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, M.candN.p, M.candChunk.p,
+                                                    M.candDistinct.p, M.candStride, M.dCtr.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(M.timers[T_LOOKUP].b, st));
+    }
+    {
+        DpChainScratch S;
+        int hashSize = 64;
+        while (hashSize < 2 * qStride) hashSize <<= 1;
+        S.hashKey = M.csHashKey.p;
+        S.hashFlag = M.csHashFlag.p;
+        S.rqSeed = M.csRqSeed.p;
+        S.rqPos = M.csRqPos.p;
+        S.rsSeed = M.csRsSeed.p;
+        S.rsPos = M.csRsPos.p;
+        S.chainLen = M.csChainLen.p;
+        S.lastB = M.csLastB.p;
+        S.chains = M.csChains.p;
+        S.results = M.csResults.p;
+        S.hashSize = hashSize;
+        S.qStride = qStride;
+        S.sStride = (int)I.maxChunkSeeds + 8;
+        S.chainCap = M.chainCap;
+        S.resultCap = M.resultCap;
+        int warpsPerBlock = 4;
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.chainWarps / 4);
+        CK(cudaEventRecord(M.timers[T_CHAIN].a, st));
+        dp_chain_kernel<<<blocks, 128, 0, st>>>(I, M.dWins.p, dReadLen, (int)nWin, Q, M.candN.p, M.candChunk.p,
+                                                M.candDistinct.p, M.candStride, S, M.outN.p, M.outMaps.p, M.outStride,
+                                                M.dCtr.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(M.timers[T_CHAIN].b, st));
+    }
+    CK(cudaMemcpyAsync(M.hOutN.p, M.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(M.hOutMaps.p, M.outMaps.p, nWin * (size_t)M.outStride * sizeof(DpMappingDev),
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, M.timers[T_EXTRACT].a, M.timers[T_EXTRACT].b));
+    M.stats.ms_extract += ms;
+    CK(cudaEventElapsedTime(&ms, M.timers[T_LOOKUP].a, M.timers[T_LOOKUP].b));
+    M.stats.ms_lookup += ms;
+    CK(cudaEventElapsedTime(&ms, M.timers[T_CHAIN].a, M.timers[T_CHAIN].b));
+    M.stats.ms_chain += ms;
+    M.stats.kernel_launches += 3;
+    M.stats.rounds += 1;
+    M.stats.windows += (int64_t)nWin;
+}
+
+void reset_counters(dp_mapper& M) {
+    M.dCtr.reserve(1);
+    CK(cudaMemsetAsync(M.dCtr.p, 0, sizeof(DpCounters), M.stream));
+}
+
+void fetch_counters(dp_mapper& M) {
+    DpCounters c;
+    CK(cudaMemcpy(&c, M.dCtr.p, sizeof(c), cudaMemcpyDeviceToHost));
+    M.stats.kmer_lookups += (int64_t)c.kmer_lookups;
+    M.stats.query_seeds += (int64_t)c.query_seeds;
+    M.stats.posting_runs += (int64_t)c.posting_runs;
+    M.stats.posting_entries += (int64_t)c.posting_entries;
+    M.stats.candidates += (int64_t)c.candidates;
+    M.stats.chain_cells += (int64_t)c.chain_cells;
+    if (c.overflow) {
+        std::string what = "device capacity exceeded:";
+        if (c.overflow & 1) what += " mappings-per-window";
+        if (c.overflow & 2) what += " chains-per-candidate";
+        if (c.overflow & 4) what += " candidates-per-window-strand";
+        throw std::runtime_error(what);
+    }
+}
+
+struct ReadCache {
+    std::vector<dph::WinRef> wins;
+};
+
+// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device.
+void map_subbatch(dp_mapper& M, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
+                  std::vector<std::vector<dph::Hit>>& results) {
+    const int64_t n = r1 - r0;
+    cudaStream_t st = M.stream;
+    const int k = M.k;
+    // ---- read tables + pack ----
+    std::vector<long long> seqOff((size_t)n + 1), wordOff((size_t)n);
+    std::vector<int> readLen((size_t)n);
+    long long words = 0;
+    for (int64_t i = 0; i < n; i++) {
+        long long len = offsets[r0 + i + 1] - offsets[r0 + i];
+        if (len < 0 || len > 0x7fffff00ll) throw std::runtime_error("bad read length");
+        seqOff[(size_t)i] = offsets[r0 + i] - offsets[r0];
+        wordOff[(size_t)i] = words;
+        readLen[(size_t)i] = (int)len;
+        words += (len + 15) / 16 + 1;
+    }
+    seqOff[(size_t)n] = offsets[r1] - offsets[r0];
+    M.dSeqOff.reserve((size_t)n + 1);
+    M.dWordOff.reserve((size_t)n);
+    M.dReadLen.reserve((size_t)n);
+    M.dWords.reserve((size_t)words + 8);
+    CK(cudaMemcpyAsync(M.dSeqOff.p, seqOff.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(M.dWordOff.p, wordOff.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(M.dReadLen.p, readLen.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    {
+        int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)M.smCount * 16);
+        CK(cudaEventRecord(M.timers[T_PACK].a, st));
+        dp_pack_kernel<<<blocks, 256, 0, st>>>(dAscii, M.dSeqOff.p, M.dWordOff.p, M.dWords.p, n);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(M.timers[T_PACK].b, st));
+        CK(cudaStreamSynchronize(st));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, M.timers[T_PACK].a, M.timers[T_PACK].b));
+        M.stats.ms_pack += ms;
+        M.stats.kernel_launches += 1;
+    }
+    // ---- rounds ----
+    dph::Params P;
+    P.refLen = M.refLen;
+    P.edge = M.edge;
+    P.circular = M.circular != 0;
+    std::vector<ReadCache> cache((size_t)n);
+    std::vector<int> active((size_t)n);
+    for (int64_t i = 0; i < n; i++) active[(size_t)i] = (int)i;
+    // results of every round must stay alive while reads are replayed: keep per-round host copies
+    std::vector<std::vector<DpMappingDev>> roundMaps;
+    const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
+    int nThreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    while (!active.empty()) {
+        double t0 = now_ms();
+        std::vector<std::vector<DpWindow>> reqs((size_t)nThreads);
+        std::vector<std::vector<int>> still((size_t)nThreads);
+        auto work = [&](int t) {
+            dph::ReadMapper rm(P);
+            size_t a0 = active.size() * (size_t)t / (size_t)nThreads, a1 = active.size() * (size_t)(t + 1) / (size_t)nThreads;
+            for (size_t a = a0; a < a1; a++) {
+                int i = active[a];
+                if (readLen[(size_t)i] < minLen) {
+                    results[(size_t)(r0 + i)].clear();
+                    continue;
+                }
+                const ReadCache& rc = cache[(size_t)i];
+                bool done = rm.run(i, readLen[(size_t)i], rc.wins.data(), (int)rc.wins.size(), reqs[(size_t)t],
+                                   results[(size_t)(r0 + i)]);
+                if (!done) still[(size_t)t].push_back(i);
+            }
+        };
+        if (active.size() < 2048) {
+            nThreads = 1;
+            reqs.resize(1);
+            still.resize(1);
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nThreads; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        std::vector<DpWindow> wins;
+        std::vector<int> next;
+        for (size_t t = 0; t < reqs.size(); t++) {
+            wins.insert(wins.end(), reqs[t].begin(), reqs[t].end());
+            next.insert(next.end(), still[t].begin(), still[t].end());
+        }
+        M.stats.ms_host_logic += now_ms() - t0;
+        if (wins.empty()) break;
+        run_windows(M, wins.data(), wins.size(), M.dWords.p, M.dWordOff.p, M.dReadLen.p);
+        t0 = now_ms();
+        // keep this round's mappings and attach them to the reads' caches
+        roundMaps.emplace_back();
+        std::vector<DpMappingDev>& keep = roundMaps.back();
+        size_t total = 0;
+        for (size_t wI = 0; wI < wins.size(); wI++) total += (size_t)M.hOutN.p[wI];
+        keep.resize(total + 1);
+        size_t pos = 0;
+        for (size_t wI = 0; wI < wins.size(); wI++) {
+            int cnt = M.hOutN.p[wI];
+            memcpy(keep.data() + pos, M.hOutMaps.p + wI * (size_t)M.outStride, (size_t)cnt * sizeof(DpMappingDev));
+            dph::WinRef ref;
+            ref.start = wins[wI].start;
+            ref.len = wins[wI].len;
+            ref.whole = wins[wI].whole;
+            ref.n = cnt;
+            ref.maps = keep.data() + pos;
+            cache[(size_t)wins[wI].read].wins.push_back(ref);
+            pos += (size_t)cnt;
+        }
+        active.swap(next);
+        nThreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        M.stats.ms_host_logic += now_ms() - t0;
+    }
+}
+
+void begin_stats(dp_mapper& M, int64_t n_reads, const int64_t* offsets) {
+    memset(&M.stats, 0, sizeof(M.stats));
+    M.stats.bases = offsets[n_reads] - offsets[0];
+    if (M.timers.empty()) {
+        M.timers.resize(T_N);
+        for (auto& t : M.timers) t.init();
+    }
+    reset_counters(M);
+}
+
+void emit_results(const std::vector<std::vector<dph::Hit>>& results, dp_mapping** out, int64_t** out_offsets,
+                  dp_stats& stats) {
+    size_t n = results.size();
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (n + 1));
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        off[i] = (int64_t)total;
+        total += results[i].size();
+    }
+    off[n] = (int64_t)total;
+    dp_mapping* maps = (dp_mapping*)malloc(sizeof(dp_mapping) * (total ? total : 1));
+    size_t p = 0;
+    for (size_t i = 0; i < n; i++) {
+        for (const dph::Hit& h : results[i]) {
+            dp_mapping m;
+            memset(&m, 0, sizeof(m));
+            m.start = h.start;
+            m.end = h.end;
+            m.q_offset = (int32_t)h.qOffset;
+            m.q_inset = (int32_t)h.qInset;
+            m.ids = (int32_t)h.ids;
+            m.rc = h.rc ? 1 : 0;
+            maps[p++] = m;
+        }
+    }
+    stats.mappings = (int64_t)total;
+    *out = maps;
+    *out_offsets = off;
+}
+
+const int64_t kSubBatchReads = 1 << 17;
+const int64_t kSubBatchBytes = 1ll << 30;
+
+}  // namespace
+
+#define API_TRY try {
+#define API_CATCH                      \
+    }                                  \
+    catch (const std::exception& ex) { \
+        g_err = ex.what();             \
+        return 1;                      \
+    }                                  \
+    return 0;
+
+extern "C" {
+
+const char* dp_last_error(void) { return g_err.c_str(); }
+const char* dp_version(void) { return "downpore_b200 0.1 (sm_100a)"; }
+void dp_free(void* p) { free(p); }
+
+int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, int k, const double* kmer_values,
+                     int seed_rate, int edge_size, int chunk_size, int device, dp_mapper** out) {
+    API_TRY
+    if (!ref_ascii || !kmer_values || !out) throw std::runtime_error("null argument");
+    if (k < 5 || k > 15) throw std::runtime_error("k must be in [5, 15] (packedKmerAt returns int32: sequence/asm_amd64.s:29)");
+    if (seed_rate < k + 4) throw std::runtime_error("seed_rate must be at least k+4");
+    if (edge_size < 4 * k) throw std::runtime_error("query_size too small");
+    if (chunk_size < 2 * edge_size || (long long)chunk_size * 10 - edge_size <= 0)
+        throw std::runtime_error("chunk_size must be at least 2*query_size");
+    if (ref_len < 2ll * edge_size || ref_len < seed_rate) throw std::runtime_error("reference shorter than 2*query_size");
+    int nDev = 0;
+    CK(cudaGetDeviceCount(&nDev));
+    if (nDev <= 0) throw std::runtime_error("no CUDA device");
+    if (device < 0 || device >= nDev) throw std::runtime_error("bad device ordinal");
+    CK(cudaSetDevice(device));
+    std::unique_ptr<dp_mapper> M(new dp_mapper());
+    M->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    M->smCount = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    M->k = k;
+    M->circular = circular ? 1 : 0;
+    M->seedRate = seed_rate;
+    M->edge = edge_size;
+    M->chunkSize = chunk_size;
+    M->refLen = ref_len;
+    build_index(*M, ref_ascii, kmer_values);
+    *out = M.release();
+    API_CATCH
+}
+
+void dp_mapper_destroy(dp_mapper* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    delete m;
+}
+
+int dp_mapper_map_batch_device(dp_mapper* m, int64_t n_reads, const uint8_t* d_bases, const int64_t* offsets,
+                               dp_mapping** out, int64_t** out_offsets) {
+    API_TRY
+    if (!m || !offsets || !out || !out_offsets || n_reads < 0) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(m->device));
+    begin_stats(*m, n_reads, offsets);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, m->stream));
+    std::vector<std::vector<dph::Hit>> results((size_t)n_reads);
+    for (int64_t r0 = 0; r0 < n_reads;) {
+        int64_t r1 = r0;
+        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
+        if (r1 == r0) r1 = r0 + 1;
+        map_subbatch(*m, d_bases + offsets[r0], offsets, r0, r1, results);
+        r0 = r1;
+    }
+    CK(cudaEventRecord(e1, m->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    m->stats.ms_total = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    fetch_counters(*m);
+    emit_results(results, out, out_offsets, m->stats);
+    API_CATCH
+}
+
+int dp_mapper_map_batch(dp_mapper* m, int64_t n_reads, const uint8_t* bases, const int64_t* offsets, dp_mapping** out,
+                        int64_t** out_offsets) {
+    API_TRY
+    if (!m || !offsets || !out || !out_offsets || n_reads < 0 || (!bases && n_reads > 0))
+        throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(m->device));
+    begin_stats(*m, n_reads, offsets);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, m->stream));
+    // pinned (or registered) caller memory is copied directly; pageable memory goes through a pinned staging buffer
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    std::vector<std::vector<dph::Hit>> results((size_t)n_reads);
+    for (int64_t r0 = 0; r0 < n_reads;) {
+        int64_t r1 = r0;
+        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
+        if (r1 == r0) r1 = r0 + 1;
+        size_t nbytes = (size_t)(offsets[r1] - offsets[r0]);
+        m->dAscii.reserve(nbytes + 64);
+        double t0 = now_ms();
+        if (pinned) {
+            CK(cudaMemcpyAsync(m->dAscii.p, bases + offsets[r0], nbytes, cudaMemcpyHostToDevice, m->stream));
+        } else {
+            const size_t piece = 32u << 20;
+            m->hStage.reserve(2 * piece);
+            cudaEvent_t ev[2];
+            CK(cudaEventCreate(&ev[0]));
+            CK(cudaEventCreate(&ev[1]));
+            int slot = 0;
+            for (size_t o = 0; o < nbytes; o += piece, slot ^= 1) {
+                size_t len = std::min(piece, nbytes - o);
+                if (o >= 2 * piece) CK(cudaEventSynchronize(ev[slot]));
+                memcpy(m->hStage.p + (size_t)slot * piece, bases + offsets[r0] + o, len);
+                CK(cudaMemcpyAsync(m->dAscii.p + o, m->hStage.p + (size_t)slot * piece, len, cudaMemcpyHostToDevice,
+                                   m->stream));
+                CK(cudaEventRecord(ev[slot], m->stream));
+            }
+            CK(cudaStreamSynchronize(m->stream));
+            cudaEventDestroy(ev[0]);
+            cudaEventDestroy(ev[1]);
+        }
+        CK(cudaStreamSynchronize(m->stream));
+        m->stats.ms_h2d += now_ms() - t0;
+        map_subbatch(*m, m->dAscii.p, offsets, r0, r1, results);
+        r0 = r1;
+    }
+    CK(cudaEventRecord(e1, m->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    m->stats.ms_total = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    fetch_counters(*m);
+    emit_results(results, out, out_offsets, m->stats);
+    API_CATCH
+}
+
+int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* query_name, int64_t query_len,
+                       const char* ref_name, char* buf, int buf_len) {
+    if (!m || !mp || !buf) return -1;
+    long long mappedLength = mp->end - mp->start;
+    if (m->circular && mappedLength < 0) mappedLength = m->refLen - mp->start + mp->end;
+    int n = snprintf(buf, (size_t)buf_len, "%s\t%lld\t%d\t%lld\t%s\t%s\t%lld\t%lld\t%lld\t%d\t%lld\t255", query_name,
+                     (long long)query_len, mp->q_offset, (long long)query_len - mp->q_inset, mp->rc ? "-" : "+",
+                     ref_name, m->refLen, (long long)mp->start, (long long)mp->end, mp->ids, mappedLength);
+    return (n < 0 || n >= buf_len) ? -1 : n;
+}
+
+int dp_mapper_get_stats(const dp_mapper* m, dp_stats* out) {
+    if (!m || !out) return 1;
+    *out = m->stats;
+    return 0;
+}
+
+int dp_mapper_index_info(const dp_mapper* m, int64_t* out5) {
+    if (!m || !out5) return 1;
+    out5[0] = m->I.numSeeds;
+    out5[1] = m->I.numChunks;
+    out5[2] = m->nChunkPostings;
+    out5[3] = m->nSeedPostings;
+    out5[4] = (int64_t)m->indexBytes;
+    return 0;
+}
+
+int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out) {
+    API_TRY
+    CK(cudaSetDevice(m->device));
+    size_t nTable = (size_t)((1ll << (2 * m->k)) / 32);
+    std::vector<uint2> t(nTable);
+    CK(cudaMemcpy(t.data(), m->table.p, nTable * sizeof(uint2), cudaMemcpyDeviceToHost));
+    size_t p = 0;
+    for (size_t w = 0; w < nTable; w++) {
+        unsigned bits = t[w].x;
+        while (bits) {
+            int b = __builtin_ctz(bits);
+            out[p++] = (int64_t)(w * 32 + (size_t)b);
+            bits &= bits - 1;
+        }
+    }
+    if (p != m->I.numSeeds) throw std::runtime_error("seed table inconsistent");
+    API_CATCH
+}
+
+int dp_mapper_chunk(const dp_mapper* m, int64_t c, int64_t* fields4, int32_t* pos, int64_t* kmer) {
+    API_TRY
+    if (c < 0 || c >= (int64_t)m->I.numChunks) throw std::runtime_error("chunk id out of range");
+    CK(cudaSetDevice(m->device));
+    unsigned off[2];
+    CK(cudaMemcpy(off, m->chunkOff.p + c, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    unsigned n = off[1] - off[0];
+    fields4[0] = m->hChunkOffset[(size_t)c];
+    fields4[1] = m->hChunkInset[(size_t)c];
+    fields4[2] = m->hChunkLen[(size_t)c];
+    fields4[3] = n;
+    if (pos && n) CK(cudaMemcpy(pos, m->chunkPos.p + off[0], n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (kmer && n) {
+        std::vector<unsigned> ranks(n);
+        CK(cudaMemcpy(ranks.data(), m->chunkSeed.p + off[0], n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        std::vector<int64_t> seeds(m->I.numSeeds);
+        if (dp_mapper_seed_kmers(m, seeds.data())) throw std::runtime_error(g_err);
+        for (unsigned i = 0; i < n; i++) kmer[i] = seeds[ranks[i]];
+    }
+    API_CATCH
+}
+
+int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read_len, int64_t start, int64_t end,
+                           int whole, int32_t* n_seeds2, int32_t* seed_pos, int64_t* seed_kmer, int64_t seed_cap,
+                           int32_t* n_cand2, int32_t* cand, int64_t cand_cap, int32_t* n_map, dp_mapping* maps,
+                           int64_t map_cap) {
+    API_TRY
+    CK(cudaSetDevice(m->device));
+    if (whole) {
+        start = 0;
+        end = read_len;
+    }
+    if (start < 0 || end > read_len || end - start < m->k + 12 || end - start > 2 * m->edge)
+        throw std::runtime_error("bad probe window");
+    begin_stats(*m, 0, &start);
+    cudaStream_t st = m->stream;
+    m->dAscii.reserve((size_t)read_len + 64);
+    CK(cudaMemcpyAsync(m->dAscii.p, read_ascii, (size_t)read_len, cudaMemcpyHostToDevice, st));
+    long long seqOff[2] = {0, read_len};
+    long long wordOff[1] = {0};
+    int rl[1] = {(int)read_len};
+    m->dSeqOff.reserve(2);
+    m->dWordOff.reserve(1);
+    m->dReadLen.reserve(1);
+    m->dWords.reserve((size_t)read_len / 16 + 8);
+    CK(cudaMemcpyAsync(m->dSeqOff.p, seqOff, sizeof(seqOff), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->dWordOff.p, wordOff, sizeof(wordOff), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->dReadLen.p, rl, sizeof(rl), cudaMemcpyHostToDevice, st));
+    dp_pack_kernel<<<1, 256, 0, st>>>(m->dAscii.p, m->dSeqOff.p, m->dWordOff.p, m->dWords.p, 1);
+    CK(cudaGetLastError());
+    DpWindow w;
+    w.read = 0;
+    w.start = (int)start;
+    w.len = (int)(end - start);
+    w.whole = whole ? 1 : 0;
+    run_windows(*m, &w, 1, m->dWords.p, m->dWordOff.p, m->dReadLen.p);
+    fetch_counters(*m);
+    // seeds
+    unsigned wsOff[2];
+    int wsN[2];
+    CK(cudaMemcpy(wsOff, m->wsOff.p, sizeof(wsOff), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(wsN, m->wsN.p, sizeof(wsN), cudaMemcpyDeviceToHost));
+    if (n_seeds2) {
+        n_seeds2[0] = wsN[0];
+        n_seeds2[1] = wsN[1];
+    }
+    if (seed_pos || seed_kmer) {
+        int tot = wsN[0] + wsN[1];
+        if (tot > seed_cap) throw std::runtime_error("seed_cap too small");
+        std::vector<int64_t> seeds(m->I.numSeeds);
+        if (dp_mapper_seed_kmers(m, seeds.data())) throw std::runtime_error(g_err);
+        std::vector<unsigned> r((size_t)tot + 1);
+        std::vector<int> p((size_t)tot + 1);
+        // strand 0 then strand 1 (they are adjacent in the compact buffer)
+        CK(cudaMemcpy(r.data(), m->qSeed.p + wsOff[0], (size_t)tot * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(p.data(), m->qPos.p + wsOff[0], (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < tot; i++) {
+            if (seed_pos) seed_pos[i] = p[(size_t)i];
+            if (seed_kmer) seed_kmer[i] = seeds[r[(size_t)i]];
+        }
+    }
+    if (n_cand2 || cand) {
+        int cn[2];
+        CK(cudaMemcpy(cn, m->candN.p, sizeof(cn), cudaMemcpyDeviceToHost));
+        if (n_cand2) {
+            n_cand2[0] = cn[0];
+            n_cand2[1] = cn[1];
+        }
+        if (cand) {
+            if (cn[0] + cn[1] > cand_cap) throw std::runtime_error("cand_cap too small");
+            std::vector<unsigned> c0((size_t)cn[0] + 1), c1((size_t)cn[1] + 1);
+            CK(cudaMemcpy(c0.data(), m->candChunk.p, (size_t)cn[0] * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(c1.data(), m->candChunk.p + m->candStride, (size_t)cn[1] * sizeof(unsigned),
+                          cudaMemcpyDeviceToHost));
+            for (int i = 0; i < cn[0]; i++) cand[i] = (int32_t)c0[(size_t)i];
+            for (int i = 0; i < cn[1]; i++) cand[cn[0] + i] = (int32_t)c1[(size_t)i];
+        }
+    }
+    if (n_map) *n_map = m->hOutN.p[0];
+    if (maps) {
+        int cnt = m->hOutN.p[0];
+        if (cnt > map_cap) throw std::runtime_error("map_cap too small");
+        for (int i = 0; i < cnt; i++) {
+            const DpMappingDev& d = m->hOutMaps.p[i];
+            dp_mapping o;
+            memset(&o, 0, sizeof(o));
+            o.start = d.start;
+            o.end = d.end;
+            o.q_offset = d.qOffset;
+            o.q_inset = d.qInset;
+            o.ids = d.ids;
+            o.rc = (uint8_t)(d.rc & 0xff);
+            maps[i] = o;
+        }
+    }
+    API_CATCH
+}
+
+int dp_pack(const uint8_t* ascii, int64_t len, uint8_t* out, int device) {
+    API_TRY
+    if (!ascii || !out || len <= 0) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(device));
+    DBuf<unsigned char> dA, dOut;
+    DBuf<unsigned> dW;
+    DBuf<long long> dOff, dWord;
+    size_t nWords = (size_t)(len + 15) / 16;
+    size_t nBytes = (size_t)(len + 3) / 4;
+    dA.reserve((size_t)len + 64);
+    dW.reserve(nWords + 8);
+    dOut.reserve(nBytes + 8);
+    // slices of 16-base multiples are independent sequences for the kernel
+    const long long slice = 1 << 14;
+    long long nSl = (len + slice - 1) / slice;
+    std::vector<long long> so((size_t)nSl + 1), sw((size_t)nSl);
+    for (long long i = 0; i < nSl; i++) {
+        so[(size_t)i] = i * slice;
+        sw[(size_t)i] = i * slice / 16;
+    }
+    so[(size_t)nSl] = len;
+    dOff.reserve(so.size());
+    dWord.reserve(sw.size());
+    CK(cudaMemcpy(dA.p, ascii, (size_t)len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dOff.p, so.data(), so.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dWord.p, sw.data(), sw.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    dp_pack_kernel<<<(int)std::min<long long>((nSl + 7) / 8, 148 * 16), 256>>>(dA.p, dOff.p, dWord.p, dW.p, nSl);
+    CK(cudaGetLastError());
+    dp_words_to_bytes_kernel<<<div_up((long long)nBytes, 256), 256>>>(dW.p, dOut.p, (long long)nBytes);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dOut.p, nBytes, cudaMemcpyDeviceToHost));
+    API_CATCH
+}
+
+int dp_kmer_counts(const uint8_t* ascii, int64_t len, int k, uint64_t* counts, int device) {
+    API_TRY
+    if (!ascii || !counts || len < k || k < 1 || k > 15) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(device));
+    DBuf<unsigned char> dA;
+    DBuf<unsigned> dW;
+    DBuf<long long> dOff, dWord;
+    DBuf<unsigned long long> dC;
+    size_t nWords = (size_t)(len + 15) / 16;
+    size_t nK = (size_t)1 << (2 * k);
+    dA.reserve((size_t)len + 64);
+    dW.reserve(nWords + 8);
+    dC.reserve(nK);
+    CK(cudaMemset(dW.p, 0, dW.cap * sizeof(unsigned)));
+    const long long slice = 1 << 14;
+    long long nSl = (len + slice - 1) / slice;
+    std::vector<long long> so((size_t)nSl + 1), sw((size_t)nSl);
+    for (long long i = 0; i < nSl; i++) {
+        so[(size_t)i] = i * slice;
+        sw[(size_t)i] = i * slice / 16;
+    }
+    so[(size_t)nSl] = len;
+    dOff.reserve(so.size());
+    dWord.reserve(sw.size());
+    CK(cudaMemcpy(dA.p, ascii, (size_t)len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dOff.p, so.data(), so.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dWord.p, sw.data(), sw.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dC.p, counts, nK * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    dp_pack_kernel<<<(int)std::min<long long>((nSl + 7) / 8, 148 * 16), 256>>>(dA.p, dOff.p, dWord.p, dW.p, nSl);
+    CK(cudaGetLastError());
+    dp_kmer_hist_kernel<<<148 * 8, 256>>>(dW.p, len, k, dC.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(counts, dC.p, nK * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    API_CATCH
+}
+
+}  // extern "C"

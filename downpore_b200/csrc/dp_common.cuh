@@ -1,0 +1,106 @@
+// downpore_b200 — shared declarations for the sm_100a kernels and the host driver.
+//
+// Data layout in HBM:
+//   packed sequences : uint32 words, 16 bases per word, first base in the two most significant bits (the same bit
+//                      order as the reference's packedSequence bytes read big-endian, sequence/sequence.go:42-53).
+//   k-mer table      : uint2[4^k/32] = {32 seed flags, number of seeds before this word}; a seed's id is its rank
+//                      among seed k-mers (seed ids are arbitrary labels in the reference: seeds/seeds.go:189).
+//   seed -> chunks   : CSR (seedOff[S+1], seedChunks[]) of the DISTINCT chunk ids containing each seed, ascending
+//                      (what SeedIndex.sequenceSets holds as bitsets, seeds/seeds.go:15,372-384).
+//   chunk -> seeds   : CSR (chunkOff[C+1], chunkPos[], chunkSeed[]) of every seed occurrence of each chunk in scan
+//                      order (what SeedIndex.sequences[c].segments holds as gaps, seeds/seeds.go:33-50).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DP_WARP 32
+#define DP_FULL 0xffffffffu
+
+struct DpIndexDev {
+    int k;
+    int circular;
+    int edge;                // query_size
+    int maxWindow;           // longest window a query can have (2*edge)
+    long long refLen;
+    unsigned numSeeds;       // S
+    unsigned numChunks;      // C
+    unsigned maxChunkSeeds;  // longest chunk list
+    const uint2* table;      // [4^k/32]
+    const unsigned* seedOff;     // [S+1]
+    const unsigned* seedChunks;  // [seedOff[S]]
+    const unsigned* chunkOff;    // [C+1]
+    const int* chunkPos;         // scan positions
+    const unsigned* chunkSeed;   // seed ranks
+    const long long* chunkOffset;  // SeedSequence.offset of the chunk
+    const long long* chunkInset;   // SeedSequence.inset of the chunk (Q3: one too large for SubSequence chunks)
+    const int* chunkScanLen;       // sum of the chunk's segments (bases actually scanned, Q2)
+};
+
+// One performMapping() call (mapping/mapping.go:489-611): window [start, start+len) of read `read`.
+struct DpWindow {
+    int read;
+    int start;
+    int len;
+    int whole;  // 1: the window is the un-sliced read (len <= 2*edge): raw packedSequence quirks apply (Q2, Q3)
+};
+
+// dp_mapping twin on the device (32 bytes)
+struct DpMappingDev {
+    long long start;
+    long long end;
+    int qOffset;
+    int qInset;
+    int ids;
+    int rc;  // low byte = RC flag; the chain length rides in the upper bytes until the window is finalised
+};
+
+struct DpCounters {
+    unsigned long long kmer_lookups;
+    unsigned long long query_seeds;
+    unsigned long long posting_runs;
+    unsigned long long posting_entries;
+    unsigned long long candidates;
+    unsigned long long chain_cells;
+    unsigned long long mappings;
+    unsigned int overflow;  // bit0: mapping list cap, bit1: chain list cap, bit2: candidate cap
+    unsigned int pad;
+};
+
+__host__ __device__ inline unsigned dp_base_code(unsigned b) { return ((b >> 1) ^ ((b & 4) >> 2)) & 3; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned dp_lane() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned dp_lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// k-mer starting at base p of a packed sequence (k <= 15): 16 bases from p in a 32-bit register, top-aligned
+__device__ __forceinline__ unsigned dp_kmer_at(const unsigned* __restrict__ words, long long p, int k) {
+    long long w = p >> 4;
+    unsigned sh = ((unsigned)p & 15u) * 2u;
+    unsigned hi = __ldg(words + w);
+    unsigned lo = __ldg(words + w + 1);
+    unsigned v = __funnelshift_l(lo, hi, sh);
+    return v >> (32 - 2 * k);
+}
+
+// reverse complement of a k-mer held in the low 2k bits
+__device__ __forceinline__ unsigned dp_revcomp(unsigned kmer, int k) {
+    unsigned y = __brev(~kmer);
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    return y >> (32 - 2 * k);
+}
+
+// flag + rank in one 8-byte gather
+__device__ __forceinline__ bool dp_seed_lookup(const uint2* __restrict__ table, unsigned kmer, unsigned* rank) {
+    uint2 e = __ldg(table + (kmer >> 5));
+    unsigned bit = 1u << (kmer & 31);
+    *rank = e.y + __popc(e.x & (bit - 1));
+    return (e.x & bit) != 0;
+}
+__device__ __forceinline__ bool dp_seed_flag(const uint2* __restrict__ table, unsigned kmer) {
+    return (__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u;
+}
+#endif

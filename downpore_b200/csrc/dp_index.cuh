@@ -1,0 +1,218 @@
+// downpore_b200 — index-construction kernels (sm_100a): pack, seed selection (AddSingleSeeds), chunk scan.
+#pragma once
+#include "dp_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-bit pack (sequence.NewPackedSequence + asm packBytes, sequence/sequence.go:67-93, sequence/asm_amd64.s:33-78).
+// One warp per sequence, one lane per 16-base output word and iteration: each lane reads its 16 ASCII bytes as five
+// 4-byte-aligned words (the neighbouring lane's loads hit the same 32 B sectors, so DRAM traffic stays 1 B/base) and
+// realigns with funnel shifts. Bases past the end of the sequence are packed as zero (the reference zero-pads its
+// tail byte too).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned dp_pack4(unsigned w) {
+    // four ASCII bytes (first base in the low byte) -> 8 bits, first base in the high bits
+    unsigned c = ((w >> 1) ^ ((w & 0x04040404u) >> 2)) & 0x03030303u;
+    return ((c & 0xff) << 6) | (((c >> 8) & 0xff) << 4) | (((c >> 16) & 0xff) << 2) | ((c >> 24) & 0xff);
+}
+
+__global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __restrict__ ascii,
+                                                      const long long* __restrict__ seqOff,    // [n+1] byte offsets
+                                                      const long long* __restrict__ wordOff,   // [n] first output word
+                                                      unsigned* __restrict__ words, long long nSeq) {
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned lane = dp_lane();
+    for (long long r = warp; r < nSeq; r += nWarps) {
+        long long b0 = seqOff[r];
+        long long len = seqOff[r + 1] - b0;
+        long long nw = (len + 15) >> 4;
+        unsigned* out = words + wordOff[r];
+        const unsigned char* src = ascii + b0;
+        unsigned mis = (unsigned)((unsigned long long)src & 3ull);
+        const unsigned* src4 = (const unsigned*)(src - mis);
+        unsigned sh = mis * 8;
+        for (long long j = lane; j < nw; j += 32) {
+            const unsigned* p = src4 + j * 4;
+            long long remain = len - j * 16;  // bases available for this word (>0)
+            unsigned a0 = __ldg(p), a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+            // never read past the last 4-byte word that holds a base of this sequence
+            long long lastByte = (long long)mis + (remain < 16 ? remain : 16) - 1;  // offset from p, in bytes
+            if (lastByte >= 4) a1 = __ldg(p + 1);
+            if (lastByte >= 8) a2 = __ldg(p + 2);
+            if (lastByte >= 12) a3 = __ldg(p + 3);
+            if (lastByte >= 16) a4 = __ldg(p + 4);
+            unsigned w0 = __funnelshift_r(a0, a1, sh);
+            unsigned w1 = __funnelshift_r(a1, a2, sh);
+            unsigned w2 = __funnelshift_r(a2, a3, sh);
+            unsigned w3 = __funnelshift_r(a3, a4, sh);
+            unsigned v = (dp_pack4(w0) << 24) | (dp_pack4(w1) << 16) | (dp_pack4(w2) << 8) | dp_pack4(w3);
+            if (remain < 16) v &= ~0u << (unsigned)(2 * (16 - remain));
+            out[j] = v;
+        }
+    }
+}
+
+// packed words (16 bases, MSB first) -> the reference's byte layout (4 bases per byte, MSB first): byte i of the
+// sequence is bits [31-8*(i%4) .. 24-8*(i%4)] of word i/4.
+__global__ void dp_words_to_bytes_kernel(const unsigned* __restrict__ words, unsigned char* __restrict__ out,
+                                         long long nBytes) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nBytes) out[i] = (unsigned char)(words[i >> 2] >> (24 - 8 * (unsigned)(i & 3)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sequtil.KmerOccurrences (util/sequtil/kmers.go:53-69): dense 4^k histogram of every k-mer of one sequence.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void dp_kmer_hist_kernel(const unsigned* __restrict__ words, long long len, int k,
+                                    unsigned long long* __restrict__ counts) {
+    long long n = len - k + 1;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        atomicAdd(counts + dp_kmer_at(words, p, k), 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AddSingleSeeds (seeds/seeds.go:160-200) as a parallel fixed point.
+//
+// Window w covers bases [w*rate, (w+1)*rate). The reference walks windows in order; window w adds its best k-mer
+// (argmax of values over all k-mers starting in the window, first maximum wins) iff none of the k-mers it *counts*
+// (A_w, the Q4 subset visited by packedCountKmers on the byte-rounded sub-slice) is a seed yet. best_w does not
+// depend on the evolving seed set; only need_w does:
+//     need_w  <=>  for all x in A_w :  f(x) >= w,     f(x) = min { w' : best_w' = x and need_w' }
+// (f(x) = the window at which x becomes a seed). need_0 is true, and need_w only depends on need_w' for w' < w, so
+// iterating need <- F(need) from any start reaches the unique solution after (dependency depth) rounds.
+// ---------------------------------------------------------------------------------------------------------------
+struct DpSeedSelParams {
+    long long refLen;
+    long long nWindows;
+    int rate;
+    int k;
+    int skipBack;  // 4 - finalLen of the raw reference (finalLen = refLen % 4, 0 when divisible: Q2)
+};
+
+// the k-mer positions A_w = [aStart, aStart + aCount) counted for window w (sequence.go:332-337 + asm :81-203)
+__device__ __forceinline__ void dp_counted_range(const DpSeedSelParams& P, long long w, long long* aStart, int* aCount) {
+    long long i = w * P.rate;
+    long long startByte = (i + 3) / 4;        // firstLen = 4 for the raw reference
+    long long endByte = (i + P.rate) / 4;
+    long long nb = endByte - startByte;
+    long long r8 = (nb - 1) * 4 - P.skipBack - P.k + 1;
+    long long r15 = r8 & 3;
+    r8 &= ~3ll;
+    long long groups = (r8 >= 8) ? (r8 >> 2) : 1;  // do-while: at least one block of four (Q1)
+    *aStart = startByte * 4;
+    *aCount = (int)(4 + groups * 4 + r15);         // 4 "initial" k-mers (skipFront = 0) + internal + tail
+}
+
+__global__ void dp_seed_best_kernel(const unsigned* __restrict__ words, const double* __restrict__ values,
+                                    DpSeedSelParams P, unsigned* __restrict__ best) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= P.nWindows) return;
+    long long i = w * P.rate;
+    unsigned kmer = dp_kmer_at(words, i, P.k);
+    double bestValue = __ldg(values + kmer);
+    unsigned bestKmer = kmer;
+    for (long long j = i + 1; j + P.k <= i + P.rate; j++) {  // k-mers starting at i+1 .. i+rate-k
+        kmer = dp_kmer_at(words, j, P.k);
+        double v = __ldg(values + kmer);
+        if (v > bestValue) {
+            bestValue = v;
+            bestKmer = kmer;
+        }
+    }
+    best[w] = bestKmer;
+}
+
+__global__ void dp_seed_fmin_kernel(const unsigned* __restrict__ best, const unsigned char* __restrict__ need,
+                                    long long nWindows, unsigned* __restrict__ f) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nWindows && need[w]) atomicMin(f + best[w], (unsigned)w);
+}
+
+__global__ void dp_seed_need_kernel(const unsigned* __restrict__ words, const unsigned* __restrict__ f,
+                                    DpSeedSelParams P, const unsigned char* __restrict__ needIn,
+                                    unsigned char* __restrict__ needOut, unsigned* __restrict__ changed) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= P.nWindows) return;
+    long long aStart;
+    int aCount;
+    dp_counted_range(P, w, &aStart, &aCount);
+    bool need = true;
+    for (int t = 0; t < aCount && need; t++) {
+        unsigned x = dp_kmer_at(words, aStart + t, P.k);
+        if (__ldg(f + x) < (unsigned)w) need = false;
+    }
+    needOut[w] = need ? 1 : 0;
+    if ((needIn[w] != 0) != need) *changed = 1;
+}
+
+__global__ void dp_seed_setbits_kernel(const unsigned* __restrict__ best, const unsigned char* __restrict__ need,
+                                       long long nWindows, unsigned* __restrict__ bits) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nWindows && need[w]) atomicOr(bits + (best[w] >> 5), 1u << (best[w] & 31));
+}
+
+__global__ void dp_popc_kernel(const unsigned* __restrict__ bits, unsigned* __restrict__ pc, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pc[i] = __popc(bits[i]);
+}
+__global__ void dp_table_kernel(const unsigned* __restrict__ bits, const unsigned* __restrict__ prefix,
+                                uint2* __restrict__ table, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) table[i] = make_uint2(bits[i], prefix[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Chunk scan = NewSeedSequence on every reference chunk (seeds/seeds.go:33-50; mapping/mapping.go:79-106).
+// One warp per chunk; 32 consecutive k-mer positions per iteration; ballot + popc give the ordered compaction.
+// pass 0 counts, pass 1 writes (pos, seed rank) in scan order and the (seed, chunk) sort keys.
+// ---------------------------------------------------------------------------------------------------------------
+struct DpChunkDesc {
+    long long base;  // first base of the chunk in the packed reference array
+    int nVisit;      // k-mers visited by the scan (Q2: raw sequences with len%4==0 lose four)
+    int pad;
+};
+
+__global__ void __launch_bounds__(256) dp_chunk_scan_kernel(const unsigned* __restrict__ words,
+                                                            const uint2* __restrict__ table,
+                                                            const DpChunkDesc* __restrict__ chunks, unsigned nChunks,
+                                                            int k, int pass, unsigned* __restrict__ counts,
+                                                            const unsigned* __restrict__ chunkOff,
+                                                            int* __restrict__ chunkPos, unsigned* __restrict__ chunkSeed,
+                                                            unsigned long long* __restrict__ keys) {
+    unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned nWarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned lane = dp_lane();
+    unsigned lt = dp_lanemask_lt();
+    for (unsigned c = warp; c < nChunks; c += nWarps) {
+        DpChunkDesc d = chunks[c];
+        unsigned n = 0;
+        unsigned off = pass ? chunkOff[c] : 0;
+        for (int j0 = 0; j0 < d.nVisit; j0 += 32) {
+            int j = j0 + (int)lane;
+            bool hit = false;
+            unsigned rank = 0;
+            if (j < d.nVisit) hit = dp_seed_lookup(table, dp_kmer_at(words, d.base + j, k), &rank);
+            unsigned m = __ballot_sync(DP_FULL, hit);
+            if (pass && hit) {
+                unsigned idx = off + n + __popc(m & lt);
+                chunkPos[idx] = j;
+                chunkSeed[idx] = rank;
+                keys[idx] = ((unsigned long long)rank << 32) | c;
+            }
+            n += __popc(m);
+        }
+        if (!pass && lane == 0) counts[c] = n;
+    }
+}
+
+// sorted unique (seed, chunk) keys -> per-seed run lengths and the chunk column
+__global__ void dp_posting_fill_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                       unsigned* __restrict__ seedCount, unsigned* __restrict__ seedChunks) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        unsigned long long key = keys[i];
+        atomicAdd(seedCount + (unsigned)(key >> 32), 1u);
+        seedChunks[i] = (unsigned)key;
+    }
+}

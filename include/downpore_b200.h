@@ -1,0 +1,133 @@
+/*
+ * downpore_b200 — C ABI of the B200-native `downpore map` hot path.
+ *
+ * The reference (jteutenberg/downpore) has no FFI; the seam this library replaces is the Go interface
+ *     mapping.Mapper { Map; MapWorker; AsString }          (mapping/mapping.go:22-26)
+ * and its constructor
+ *     mapping.NewMapper(reference, circular, k, kmerValues, seedRate, edgeSize, chunkSize, numWorkers)
+ *                                                          (mapping/mapping.go:67)
+ * as called from commands/map.go:73 and :84-86. A cgo shim binds exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dp_last_error() returns a thread-local message
+ *     (the reference only log.Fatal()s / panics on this path, so every error is fatal to the host);
+ *   - input buffers are borrowed for the duration of the call only (cgo rule: no Go pointer is retained);
+ *   - output buffers are allocated by the library with malloc() and released with dp_free();
+ *   - a dp_mapper is bound to one CUDA device; create one per GPU and shard read batches across them
+ *     (reads are independent: commands/map.go:84-86). dp_mapper_map_batch may be called from one thread at a
+ *     time per mapper;
+ *   - there is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef DOWNPORE_B200_H
+#define DOWNPORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dp_mapper dp_mapper;
+
+/* One mapping.Mapping (mapping/mapping.go:11-20) without the Query pointer (the caller knows which read it is). */
+typedef struct dp_mapping {
+    int64_t start;     /* Mapping.Start */
+    int64_t end;       /* Mapping.End (inclusive coordinate for window hits: SURVEY Q3) */
+    int32_t q_offset;  /* Mapping.QueryOffset */
+    int32_t q_inset;   /* Mapping.QueryInset */
+    int32_t ids;       /* Mapping.ids: reference bases covered by matched seeds */
+    uint8_t rc;        /* Mapping.RC */
+    uint8_t pad_[3];
+} dp_mapping;
+
+/* Device-side timings and work counters of the most recent dp_mapper_map_batch* call. */
+typedef struct dp_stats {
+    double ms_total;        /* CUDA-event time, first kernel to last kernel of the call (device work only) */
+    double ms_pack;         /* 2-bit pack kernel */
+    double ms_extract;      /* k-mer scan / seed extraction kernel, summed over rounds */
+    double ms_lookup;       /* seed-index lookup (candidate chunks) kernel, summed over rounds */
+    double ms_chain;        /* chaining kernel, summed over rounds */
+    double ms_host_logic;   /* host wall time spent in the per-read Map() strategy between rounds */
+    double ms_h2d;          /* host->device copy time of reads (0 for the device-resident entry point) */
+    int64_t rounds;         /* window-query rounds */
+    int64_t windows;        /* performMapping window queries (both strands each) */
+    int64_t kmer_lookups;   /* k-mer table gathers issued by the extract kernel */
+    int64_t query_seeds;    /* seeds found in query window strands */
+    int64_t posting_runs;   /* included seed occurrences (posting runs walked by the lookup kernel) */
+    int64_t posting_entries;/* posting entries gathered by the lookup kernel */
+    int64_t candidates;     /* candidate chunks produced by the lookup kernel */
+    int64_t chain_cells;    /* |reduced chunk list| + |reduced query list| over candidates reaching the chainer */
+    int64_t mappings;       /* mappings returned */
+    int64_t kernel_launches;/* kernels launched by the call */
+    int64_t bases;          /* sum of read lengths of the call */
+} dp_stats;
+
+/*
+ * mapping.NewMapper (mapping/mapping.go:67-109): packs the reference, selects seed k-mers (AddSingleSeeds,
+ * seeds/seeds.go:160-200), cuts the reference into chunks and builds the seed index, all on `device`.
+ *   ref_ascii/ref_len : the first record of the reference FASTA (commands/map.go:34-36), one byte per base
+ *   kmer_values       : 4^k doubles, commands/map.go:46-71 (stays an input so that Go's sort-dependent tie order at
+ *                       the top-1 % boundary is inherited from the host, not re-implemented)
+ *   seed_rate, edge_size (= query_size), chunk_size : as commands/map.go:39-43
+ */
+int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, int k, const double* kmer_values,
+                     int seed_rate, int edge_size, int chunk_size, int device, dp_mapper** out);
+
+/*
+ * Mapper.Map over a batch of reads (mapping/mapping.go:430-487 for each read; replaces the MapWorker goroutine pool
+ * of mapping.go:613-619 / commands/map.go:84-86).
+ *   bases   : concatenated ASCII reads (host memory; pinned memory is copied without staging)
+ *   offsets : n_reads+1 byte offsets into `bases`
+ *   out     : *out = malloc'ed array of all mappings, grouped per read in input order, each group in the slice order
+ *             Map() returns them in
+ *   out_offsets : *out_offsets = malloc'ed n_reads+1 prefix offsets into *out
+ */
+int dp_mapper_map_batch(dp_mapper* m, int64_t n_reads, const uint8_t* bases, const int64_t* offsets, dp_mapping** out,
+                        int64_t** out_offsets);
+
+/* Same, with `d_bases` (ASCII) already resident in device memory on the mapper's device; `offsets` stays a host array. */
+int dp_mapper_map_batch_device(dp_mapper* m, int64_t n_reads, const uint8_t* d_bases, const int64_t* offsets,
+                               dp_mapping** out, int64_t** out_offsets);
+
+/* mapping.AsString (mapping/mapping.go:112-122): writes one PAF line (no newline) into buf; returns its length or -1. */
+int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* query_name, int64_t query_len,
+                       const char* ref_name, char* buf, int buf_len);
+
+int dp_mapper_get_stats(const dp_mapper* m, dp_stats* out);
+
+/* Index facts: out5 = {num_seeds, num_chunks, chunk_postings (seed occurrences over chunks),
+ * seed_postings (distinct (seed,chunk) pairs), index_bytes on device}. */
+int dp_mapper_index_info(const dp_mapper* m, int64_t* out5);
+
+/* Test probes (stage dumps for parity tests; not needed by a host). */
+/* seed k-mers, ascending k-mer value; out must hold num_seeds entries */
+int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out);
+/* chunk c: fields4 = {offset, inset, length, n_seeds}; pos/kmer (n_seeds each, may be NULL) */
+int dp_mapper_chunk(const dp_mapper* m, int64_t c, int64_t* fields4, int32_t* pos, int64_t* kmer);
+/*
+ * One window query (performMapping, mapping/mapping.go:489-611) on read bases[0..read_len): window [start,end) or the
+ * whole read. Any of the outputs may be NULL. seeds: per strand (0 fwd, 1 rc) n, then (pos, kmer) pairs;
+ * candidates per strand; mappings as returned by performMapping.
+ */
+int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read_len, int64_t start, int64_t end,
+                           int whole, int32_t* n_seeds2, int32_t* seed_pos, int64_t* seed_kmer, int64_t seed_cap,
+                           int32_t* n_cand2, int32_t* cand, int64_t cand_cap, int32_t* n_map, dp_mapping* maps,
+                           int64_t map_cap);
+
+/* 2-bit packing of one sequence exactly as sequence.NewPackedSequence (sequence/sequence.go:67-93) lays it out:
+ * 4 bases per byte, MSB first, tail byte left-aligned; out must hold (len+3)/4 bytes. Runs the device pack kernel. */
+int dp_pack(const uint8_t* ascii, int64_t len, uint8_t* out, int device);
+
+/* sequtil.KmerOccurrences (util/sequtil/kmers.go:34-69) for one record: counts[4^k] += occurrences. */
+int dp_kmer_counts(const uint8_t* ascii, int64_t len, int k, uint64_t* counts, int device);
+
+void dp_mapper_destroy(dp_mapper* m);
+void dp_free(void* p);
+const char* dp_last_error(void);
+/* library version string, e.g. "downpore_b200 0.1 (sm_100a)" */
+const char* dp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOWNPORE_B200_H */

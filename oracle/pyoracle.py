@@ -1,0 +1,405 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so).
+
+ORACLE = TEST INFRASTRUCTURE ONLY. Import this from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs
+only; nothing under downpore_b200/ may import it.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+c_ll = ctypes.c_longlong
+c_vp = ctypes.c_void_p
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
+        subprocess.check_call(["make", "-C", _HERE, "-j4", "all"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = ctypes.CDLL(_LIB)
+    sig = {
+        "dpo_last_error": (ctypes.c_char_p, []),
+        "dpo_packed_new": (c_vp, [c_vp, c_ll]),
+        "dpo_packed_free": (None, [c_vp]),
+        "dpo_packed_sub": (c_vp, [c_vp, c_ll, c_ll]),
+        "dpo_packed_rc": (c_vp, [c_vp]),
+        "dpo_packed_len": (c_ll, [c_vp]),
+        "dpo_packed_nbytes": (c_ll, [c_vp]),
+        "dpo_packed_bytes": (None, [c_vp, c_vp]),
+        "dpo_packed_fields": (None, [c_vp, c_vp]),
+        "dpo_packed_string": (None, [c_vp, c_vp]),
+        "dpo_packed_kmer_at": (c_ll, [c_vp, c_ll, c_ll]),
+        "dpo_packed_next_kmer": (c_ll, [c_vp, c_ll, c_ll, c_ll]),
+        "dpo_packed_count_kmers": (c_ll, [c_vp, c_ll, c_ll, c_vp]),
+        "dpo_packed_count_kmers_between": (c_ll, [c_vp, c_ll, c_ll, c_ll, c_ll, c_vp]),
+        "dpo_packed_write_segments": (c_ll, [c_vp, c_ll, c_vp, c_vp]),
+        "dpo_packed_short_kmers": (c_ll, [c_vp, c_ll, ctypes.c_int, c_vp]),
+        "dpo_byte_new": (c_vp, [c_vp, c_ll]),
+        "dpo_byte_free": (None, [c_vp]),
+        "dpo_byte_sub": (c_vp, [c_vp, c_ll, c_ll]),
+        "dpo_byte_rc": (c_vp, [c_vp]),
+        "dpo_byte_len": (c_ll, [c_vp]),
+        "dpo_byte_fields": (None, [c_vp, c_vp]),
+        "dpo_byte_string": (None, [c_vp, c_vp]),
+        "dpo_byte_kmer_at": (c_ll, [c_vp, c_ll, c_ll]),
+        "dpo_byte_next_kmer": (c_ll, [c_vp, c_ll, c_ll, c_ll]),
+        "dpo_byte_count_kmers": (c_ll, [c_vp, c_ll, c_ll, c_ll, c_vp]),
+        "dpo_byte_count_kmers_between": (c_ll, [c_vp, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp]),
+        "dpo_byte_write_segments": (c_ll, [c_vp, c_ll, c_ll, c_vp, c_vp]),
+        "dpo_byte_short_kmers": (c_ll, [c_vp, c_ll, ctypes.c_int, c_vp]),
+        "dpo_kmer_value": (c_ll, [c_vp, c_ll]),
+        "dpo_pack_bytes": (None, [c_vp, c_ll, c_vp]),
+        "dpo_intset_new": (c_vp, []),
+        "dpo_intset_free": (None, [c_vp]),
+        "dpo_intset_add": (None, [c_vp, ctypes.c_ulonglong]),
+        "dpo_intset_contains": (ctypes.c_int, [c_vp, ctypes.c_ulonglong]),
+        "dpo_intset_size": (ctypes.c_ulonglong, [c_vp]),
+        "dpo_intset_count_intersection": (ctypes.c_ulonglong, [c_vp, c_vp]),
+        "dpo_intset_count_intersection_to": (c_ll, [c_vp, c_vp, c_ll]),
+        "dpo_get_shared_ids": (c_ll, [c_vp, c_ll, c_ll, ctypes.c_int, c_vp, c_ll]),
+        "dpo_kmer_values": (ctypes.c_int, [c_vp, c_ll, ctypes.c_int, c_vp]),
+        "dpo_kmer_counts": (ctypes.c_int, [c_vp, c_ll, ctypes.c_int, c_vp]),
+        "dpo_mapper_new": (c_vp, [c_vp, c_ll, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+        "dpo_mapper_free": (None, [c_vp]),
+        "dpo_mapper_num_seeds": (c_ll, [c_vp]),
+        "dpo_mapper_num_chunks": (c_ll, [c_vp]),
+        "dpo_mapper_seed_kmers": (None, [c_vp, c_vp]),
+        "dpo_mapper_chunk": (c_ll, [c_vp, c_ll, c_vp, c_vp, c_ll]),
+        "dpo_window_segments": (c_ll, [c_vp, c_vp, c_ll, c_ll, c_ll, ctypes.c_int, ctypes.c_int, c_vp, c_ll, c_vp]),
+        "dpo_window_candidates": (c_ll, [c_vp, c_vp, c_ll, c_ll, c_ll, ctypes.c_int, ctypes.c_int, c_vp, c_ll]),
+        "dpo_window_mappings": (c_ll, [c_vp, c_vp, c_ll, c_ll, c_ll, ctypes.c_int, c_vp, c_ll]),
+        "dpo_map_batch": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+        "dpo_free": (None, [c_vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def _err():
+    return lib().dpo_last_error().decode()
+
+
+def _u8(x):
+    if isinstance(x, (bytes, bytearray, str)):
+        x = x.encode() if isinstance(x, str) else x
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+class Packed:
+    """packedSequence (sequence/sequence.go:43-53)."""
+
+    def __init__(self, ascii_or_handle, _own=True):
+        L = lib()
+        if isinstance(ascii_or_handle, int):
+            self.h = ascii_or_handle
+        else:
+            a = _u8(ascii_or_handle)
+            self.h = L.dpo_packed_new(a.ctypes.data, a.size)
+        if not self.h:
+            raise RuntimeError(_err())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().dpo_packed_free(self.h)
+            self.h = None
+
+    def sub(self, start, end):
+        h = lib().dpo_packed_sub(self.h, start, end)
+        if not h:
+            raise RuntimeError(_err())
+        return Packed(h)
+
+    def rc(self):
+        return Packed(lib().dpo_packed_rc(self.h))
+
+    def __len__(self):
+        return lib().dpo_packed_len(self.h)
+
+    def bytes(self):
+        out = np.empty(lib().dpo_packed_nbytes(self.h), dtype=np.uint8)
+        lib().dpo_packed_bytes(self.h, out.ctypes.data)
+        return out
+
+    def fields(self):
+        f = np.zeros(5, dtype=np.int64)
+        lib().dpo_packed_fields(self.h, f.ctypes.data)
+        return dict(offset=int(f[0]), inset=int(f[1]), firstLen=int(f[2]), finalLen=int(f[3]), length=int(f[4]))
+
+    def string(self):
+        out = np.empty(len(self), dtype=np.uint8)
+        lib().dpo_packed_string(self.h, out.ctypes.data)
+        return out.tobytes().decode()
+
+    def kmer_at(self, i, k):
+        return lib().dpo_packed_kmer_at(self.h, i, k)
+
+    def next_kmer(self, cur, mask, idx):
+        return lib().dpo_packed_next_kmer(self.h, cur, mask, idx)
+
+    def count_kmers(self, up_to, k, seeds):
+        return lib().dpo_packed_count_kmers(self.h, up_to, k, seeds.ctypes.data)
+
+    def count_kmers_between(self, frm, to, up_to, k, seeds):
+        r = lib().dpo_packed_count_kmers_between(self.h, frm, to, up_to, k, seeds.ctypes.data)
+        if r < 0:
+            raise RuntimeError(_err())
+        return r
+
+    def write_segments(self, k, seeds):
+        seg = np.empty(2 * (len(self) + 16) + 1, dtype=np.int64)
+        n = lib().dpo_packed_write_segments(self.h, k, seeds.ctypes.data, seg.ctypes.data)
+        return seg[:n].copy()
+
+    def short_kmers(self, k, collapse):
+        out = np.empty(len(self) + 1, dtype=np.uint16)
+        n = lib().dpo_packed_short_kmers(self.h, k, int(collapse), out.ctypes.data)
+        return out[:n].copy()
+
+
+class Byte:
+    """byteSequence (sequence/sequence.go:33-40): independent check of the packed asm emulation."""
+
+    def __init__(self, ascii_or_handle):
+        L = lib()
+        if isinstance(ascii_or_handle, int):
+            self.h = ascii_or_handle
+        else:
+            a = _u8(ascii_or_handle)
+            self.h = L.dpo_byte_new(a.ctypes.data, a.size)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().dpo_byte_free(self.h)
+            self.h = None
+
+    def sub(self, start, end):
+        return Byte(lib().dpo_byte_sub(self.h, start, end))
+
+    def rc(self):
+        return Byte(lib().dpo_byte_rc(self.h))
+
+    def __len__(self):
+        return lib().dpo_byte_len(self.h)
+
+    def fields(self):
+        f = np.zeros(2, dtype=np.int64)
+        lib().dpo_byte_fields(self.h, f.ctypes.data)
+        return dict(offset=int(f[0]), inset=int(f[1]))
+
+    def string(self):
+        out = np.empty(len(self), dtype=np.uint8)
+        lib().dpo_byte_string(self.h, out.ctypes.data)
+        return out.tobytes().decode()
+
+    def kmer_at(self, i, k):
+        return lib().dpo_byte_kmer_at(self.h, i, k)
+
+    def next_kmer(self, cur, mask, idx):
+        return lib().dpo_byte_next_kmer(self.h, cur, mask, idx)
+
+    def count_kmers(self, up_to, k, mask, seeds):
+        return lib().dpo_byte_count_kmers(self.h, up_to, k, mask, seeds.ctypes.data)
+
+    def count_kmers_between(self, frm, to, up_to, k, mask, seeds):
+        return lib().dpo_byte_count_kmers_between(self.h, frm, to, up_to, k, mask, seeds.ctypes.data)
+
+    def write_segments(self, k, mask, seeds):
+        seg = np.empty(2 * (len(self) + 16) + 1, dtype=np.int64)
+        n = lib().dpo_byte_write_segments(self.h, k, mask, seeds.ctypes.data, seg.ctypes.data)
+        return seg[:n].copy()
+
+    def short_kmers(self, k, collapse):
+        out = np.empty(len(self) + 1, dtype=np.uint16)
+        n = lib().dpo_byte_short_kmers(self.h, k, int(collapse), out.ctypes.data)
+        return out[:n].copy()
+
+
+def kmer_value(s):
+    a = _u8(s)
+    return lib().dpo_kmer_value(a.ctypes.data, a.size)
+
+
+def pack_bytes(s, out_len):
+    a = _u8(s)
+    out = np.zeros(out_len, dtype=np.uint8)
+    lib().dpo_pack_bytes(a.ctypes.data, a.size, out.ctypes.data)
+    return out
+
+
+class IntSet:
+    def __init__(self):
+        self.h = lib().dpo_intset_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().dpo_intset_free(self.h)
+            self.h = None
+
+    def add(self, x):
+        lib().dpo_intset_add(self.h, x)
+
+    def contains(self, x):
+        return bool(lib().dpo_intset_contains(self.h, x))
+
+    def size(self):
+        return lib().dpo_intset_size(self.h)
+
+    def count_intersection(self, other):
+        return lib().dpo_intset_count_intersection(self.h, other.h)
+
+    def count_intersection_to(self, other, max_count):
+        r = lib().dpo_intset_count_intersection_to(self.h, other.h, max_count)
+        if r < 0:
+            raise RuntimeError(_err())
+        return r
+
+
+def get_shared_ids(sets, min_count, fast):
+    arr = (c_vp * len(sets))(*[s.h for s in sets])
+    cap = 1 << 20
+    out = np.empty(cap, dtype=np.uint64)
+    n = lib().dpo_get_shared_ids(arr, len(sets), min_count, int(fast), out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(_err())
+    return out[:n].copy()
+
+
+def kmer_values(ref, k):
+    """values[] of commands/map.go:45-71 for a single-record reference (canonical tie order, Q10)."""
+    a = _u8(ref)
+    out = np.empty(4 ** k, dtype=np.float64)
+    if lib().dpo_kmer_values(a.ctypes.data, a.size, k, out.ctypes.data):
+        raise RuntimeError(_err())
+    return out
+
+
+def kmer_counts(ref, k):
+    a = _u8(ref)
+    out = np.empty(4 ** k, dtype=np.uint64)
+    if lib().dpo_kmer_counts(a.ctypes.data, a.size, k, out.ctypes.data):
+        raise RuntimeError(_err())
+    return out
+
+
+COUNTER_NAMES = ["windows", "kmer_lookups", "query_seeds", "posting_runs", "posting_entries", "candidates",
+                 "cand_pass", "chain_cells", "chains", "mappings", "sort_ties_unpinned"]
+
+
+class Mapper:
+    """mapping.Mapper (mapping/mapping.go:22-26) over the oracle."""
+
+    def __init__(self, ref, values, circular=True, k=11, seed_rate=40, edge_size=1000, chunk_size=10000):
+        self.ref = _u8(ref)
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        assert self.values.size == 4 ** k
+        self.k = k
+        self.circular = circular
+        self.h = lib().dpo_mapper_new(self.ref.ctypes.data, self.ref.size, int(circular), k, self.values.ctypes.data,
+                                      seed_rate, edge_size, chunk_size)
+        if not self.h:
+            raise RuntimeError(_err())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().dpo_mapper_free(self.h)
+            self.h = None
+
+    @property
+    def num_seeds(self):
+        return lib().dpo_mapper_num_seeds(self.h)
+
+    @property
+    def num_chunks(self):
+        return lib().dpo_mapper_num_chunks(self.h)
+
+    def seed_kmers(self):
+        out = np.empty(self.num_seeds, dtype=np.int64)
+        lib().dpo_mapper_seed_kmers(self.h, out.ctypes.data)
+        return out
+
+    def chunk(self, c):
+        f = np.zeros(4, dtype=np.int64)
+        n = lib().dpo_mapper_chunk(self.h, c, f.ctypes.data, None, 0)
+        seg = np.empty(n, dtype=np.int64)
+        lib().dpo_mapper_chunk(self.h, c, f.ctypes.data, seg.ctypes.data, n)
+        return dict(offset=int(f[0]), inset=int(f[1]), length=int(f[2]), nseeds=int(f[3]), segments=seg)
+
+    def window_segments(self, read, start=0, end=0, whole=False, rc=False):
+        a = _u8(read)
+        seg = np.empty(2 * (a.size + 16) + 1, dtype=np.int64)
+        f = np.zeros(3, dtype=np.int64)
+        n = lib().dpo_window_segments(self.h, a.ctypes.data, a.size, start, end, int(whole), int(rc), seg.ctypes.data,
+                                      seg.size, f.ctypes.data)
+        if n < 0:
+            raise RuntimeError(_err())
+        return seg[:n].copy(), dict(offset=int(f[0]), inset=int(f[1]), length=int(f[2]))
+
+    def window_candidates(self, read, start=0, end=0, whole=False, rc=False):
+        a = _u8(read)
+        out = np.empty(max(16, self.num_chunks), dtype=np.int64)
+        n = lib().dpo_window_candidates(self.h, a.ctypes.data, a.size, start, end, int(whole), int(rc), out.ctypes.data,
+                                        out.size)
+        if n < 0:
+            raise RuntimeError(_err())
+        return out[:n].copy()
+
+    def window_mappings(self, read, start=0, end=0, whole=False):
+        a = _u8(read)
+        cap = 4096
+        out = np.empty((cap, 6), dtype=np.int64)
+        n = lib().dpo_window_mappings(self.h, a.ctypes.data, a.size, start, end, int(whole), out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError(_err())
+        return out[:n].copy()
+
+    def map_batch(self, bases, offsets, threads=1):
+        """-> (rows[int64, M x 6] = Start, End, QueryOffset, QueryInset, RC, ids; out_offsets[n+1]; counters dict)"""
+        bases = _u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        out_off = np.empty(n + 1, dtype=np.int64)
+        ctr = np.zeros(len(COUNTER_NAMES), dtype=np.int64)
+        rows_p = ctypes.POINTER(c_ll)()
+        rc = lib().dpo_map_batch(self.h, n, bases.ctypes.data, offsets.ctypes.data, threads, ctypes.byref(rows_p),
+                                 out_off.ctypes.data, ctr.ctypes.data)
+        if rc:
+            raise RuntimeError(_err())
+        total = int(out_off[n])
+        rows = np.ctypeslib.as_array(rows_p, shape=(max(total, 1) * 6,))[: total * 6].reshape(total, 6).copy()
+        lib().dpo_free(rows_p)
+        return rows, out_off, dict(zip(COUNTER_NAMES, (int(x) for x in ctr)))
+
+
+def paf_lines(rows, out_off, names, lengths, ref_name, ref_len, circular):
+    """AsString (mapping/mapping.go:112-122) over map_batch output."""
+    lines = []
+    for i in range(len(out_off) - 1):
+        for r in rows[out_off[i]:out_off[i + 1]]:
+            start, end, qoff, qin, rc, ids = (int(v) for v in r)
+            ml = end - start
+            if circular and ml < 0:
+                ml = ref_len - start + end
+            lines.append("%s\t%d\t%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t255" % (
+                names[i], lengths[i], qoff, lengths[i] - qin, "-" if rc else "+", ref_name, ref_len, start, end, ids, ml))
+    return lines
