@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) dp_extract_kernel(DpIndexDev I, const uns
             }
         }
         __syncwarp();
-        lookups += 2ull * (unsigned)(nJ > 0 ? nJ : 0);
+        lookups += 2ull * (unsigned)(nJ > 0 ? nJ : 0) + (q2 ? 1u : 0u);  // Q2: the rc scan visits one k-mer twice
         seeds += (unsigned)(nF + nR + dup);
     }
     if (lane == 0 && (lookups | seeds)) {

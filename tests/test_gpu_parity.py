@@ -1,0 +1,191 @@
+"""GPU parity tests (run with -m gpu on a B200): every stage of the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs. Integer work: the bar is bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyoracle as po  # noqa: E402
+from tools import synth  # noqa: E402
+
+import downpore_b200 as dp  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+K = 11
+
+
+def rows_of(maps):
+    if len(maps) == 0:
+        return np.zeros((0, 6), dtype=np.int64)
+    return np.stack([maps["start"], maps["end"], maps["q_offset"], maps["q_inset"], maps["rc"], maps["ids"]],
+                    axis=1).astype(np.int64)
+
+
+def positions(seg, k=K):
+    gaps, kms = seg[0::2], seg[1::2]
+    return np.cumsum(gaps[:-1]) + k * np.arange(len(kms)), kms
+
+
+def mixed_reads(ref, circular, seed=7, n=200, rl=5000):
+    rd = synth.reads(ref, seed, n, rl, circular=circular)
+    reads = [rd[i * rl:(i + 1) * rl] for i in range(n)]
+    for L in (499, 500, 999, 1000, 1500, 1996, 2000, 2001, 2400, 2999, 3000, 3500, 4000, 4100, 5001, 6001, 7000):
+        x = synth.reads(ref, 100 + L, 3, L, circular=circular)
+        reads += [x[i * L:(i + 1) * L] for i in range(3)]
+    a = synth.reads(ref, 55, 8, 4000, circular=circular)
+    b = synth.reads(ref, 56, 8, 5000, circular=circular)
+    for i in range(8):
+        reads.append(np.concatenate([a[i * 4000:(i + 1) * 4000], b[i * 5000:(i + 1) * 5000]]))
+    return reads
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_pack_kat_and_random():
+    """sequence_test.go:211-233 golden vector through the device pack kernel, then random sequences vs the oracle."""
+    assert dp.pack("CGGT")[0] == 0x6B
+    assert list(dp.pack("CGGT" * 5)) == [0x6B] * 5
+    rng = np.random.default_rng(0)
+    for L in (1, 3, 4, 5, 15, 16, 17, 31, 63, 64, 65, 70, 1000, 16384, 16385, 100003):
+        s = "".join("ACGTNacgtnRY"[c] for c in rng.integers(0, 12, L))
+        assert np.array_equal(dp.pack(s), po.Packed(s).bytes()), L
+
+
+def test_kmer_counts():
+    ref = synth.reference(4, 500_000)
+    for k in (7, 11, 13):
+        assert np.array_equal(dp.kmer_counts(ref, k), po.kmer_counts(ref, k)), k
+
+
+@pytest.fixture(scope="module", params=[(True, 300_000, 2), (False, 300_000, 2), (True, 1_203_457, 5)])
+def pair(request):
+    circular, n, seed = request.param
+    ref = synth.reference(seed, n)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    om = po.Mapper(ref, vals, circular=circular)
+    gm = dp.Mapper(ref, vals, circular=circular)
+    yield ref, circular, om, gm
+    gm.close()
+
+
+def test_index_matches_oracle(pair):
+    """AddSingleSeeds seed set (Q4), chunk layout (Q5, Q13) and every chunk's gapped-seed list (Q2)."""
+    ref, circular, om, gm = pair
+    info = gm.index_info()
+    assert info["num_seeds"] == om.num_seeds and info["num_chunks"] == om.num_chunks
+    assert np.array_equal(np.sort(om.seed_kmers()), gm.seed_kmers())
+    for c in range(om.num_chunks):
+        oc, gc = om.chunk(c), gm.chunk(c)
+        assert (oc["offset"], oc["inset"], oc["length"], oc["nseeds"]) == (gc["offset"], gc["inset"], gc["length"], gc["nseeds"])
+        pos, kms = positions(oc["segments"])
+        assert np.array_equal(pos, gc["pos"]) and np.array_equal(kms, gc["kmer"]), c
+
+
+def test_window_stages(pair):
+    """performMapping stage by stage: seeds (both strands), candidate chunks, window mappings."""
+    ref, circular, om, gm = pair
+    reads = mixed_reads(ref, circular, n=24)
+    for r in reads:
+        L = len(r)
+        wins = [(0, L, True)] if L <= 2000 else [(0, 1000, False), (L - 1000, L, False), (1000, min(2000, L - 1000), False)]
+        for (s, e, whole) in wins:
+            if e - s < 100:
+                continue
+            g = gm.probe_window(r, s, e, whole)
+            for strand in (0, 1):
+                seg, _ = om.window_segments(r, s, e, whole, bool(strand))
+                pos, kms = positions(seg)
+                assert np.array_equal(pos, g["seeds"][strand][0]), (L, s, e, strand)
+                assert np.array_equal(kms, g["seeds"][strand][1]), (L, s, e, strand)
+                assert np.array_equal(om.window_candidates(r, s, e, whole, bool(strand)), g["candidates"][strand])
+            assert np.array_equal(om.window_mappings(r, s, e, whole), rows_of(g["mappings"])), (L, s, e)
+
+
+def test_map_batch_matches_oracle(pair):
+    ref, circular, om, gm = pair
+    reads = mixed_reads(ref, circular)
+    bases, offs = make_golden.concat(reads)
+    orow, ooff, octr = om.map_batch(bases, offs, threads=4)
+    gmaps, goff = gm.map_batch(bases, offs)
+    assert np.array_equal(ooff, goff)
+    assert np.array_equal(orow, rows_of(gmaps))
+    st = gm.stats()
+    for key in ("windows", "kmer_lookups", "query_seeds", "posting_runs", "posting_entries", "candidates",
+                "chain_cells", "mappings"):
+        assert st[key] == octr[key], key
+    # PAF lines through the C ABI formatter == AsString restated in python over the oracle rows
+    names = ["read%d" % i for i in range(len(reads))]
+    lens = [len(r) for r in reads]
+    assert gm.paf_lines(gmaps, goff, names, lens) == po.paf_lines(orow, ooff, names, lens, "ref", len(ref), circular)
+
+
+@pytest.mark.parametrize("name", ["small_circular", "small_linear"])
+def test_golden_fixture(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ref, circular, reads = make_golden.case_inputs(name)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    gm = dp.Mapper(ref, vals, circular=circular)
+    info = gm.index_info()
+    assert info["num_seeds"] == int(g["num_seeds"]) and info["num_chunks"] == int(g["num_chunks"])
+    bases, offs = make_golden.concat(reads)
+    gmaps, goff = gm.map_batch(bases, offs)
+    assert np.array_equal(goff, g["out_off"])
+    assert np.array_equal(rows_of(gmaps), g["rows"])
+
+
+def test_device_resident_entry_point_and_idempotence(pair):
+    import torch
+    ref, circular, om, gm = pair
+    n, L = 500, 4000
+    rd = synth.reads(ref, 77, n, L, circular=circular)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    host_maps, host_off = gm.map_batch(rd, offs)
+    d = torch.from_numpy(rd).cuda()
+    dev_maps, dev_off = gm.map_batch_device(d.data_ptr(), offs)
+    assert np.array_equal(host_off, dev_off) and np.array_equal(rows_of(host_maps), rows_of(dev_maps))
+    pinned = torch.from_numpy(rd).pin_memory()
+    pin_maps, pin_off = gm.map_batch_ptr(pinned.data_ptr(), offs)
+    assert np.array_equal(host_off, pin_off) and np.array_equal(rows_of(host_maps), rows_of(pin_maps))
+    # batch composition must not matter: mapping the two halves separately gives the same groups
+    a_maps, a_off = gm.map_batch(rd[: (n // 2) * L], offs[: n // 2 + 1])
+    b_maps, b_off = gm.map_batch(rd[(n // 2) * L:], offs[n // 2:] - offs[n // 2])
+    assert np.array_equal(rows_of(host_maps), np.concatenate([rows_of(a_maps), rows_of(b_maps)]))
+
+
+def test_other_parameters():
+    """k, seed_rate, query_size and chunk_size other than the defaults (commands/map.go:19-21)."""
+    ref = synth.reference(8, 400_000)
+    for (k, rate, edge, chunk) in ((9, 30, 600, 5000), (13, 48, 1000, 10000), (11, 41, 801, 7001)):
+        vals = dp.kmer_values(dp.kmer_counts(ref, k), k)
+        om = po.Mapper(ref, vals, circular=True, k=k, seed_rate=rate, edge_size=edge, chunk_size=chunk)
+        gm = dp.Mapper(ref, vals, circular=True, k=k, seed_rate=rate, edge_size=edge, chunk_size=chunk)
+        assert np.array_equal(np.sort(om.seed_kmers()), gm.seed_kmers()), (k, rate)
+        rd = synth.reads(ref, 3, 150, 5000)
+        offs = np.arange(151, dtype=np.int64) * 5000
+        orow, ooff, _ = om.map_batch(rd, offs, threads=4)
+        gmaps, goff = gm.map_batch(rd, offs)
+        assert np.array_equal(ooff, goff) and np.array_equal(orow, rows_of(gmaps)), (k, rate, edge, chunk)
+        gm.close()
+
+
+def test_config1_full_parity():
+    """BASELINE config 1: 4.6 Mb circular reference, 10k x 10 kb reads, byte-identical mapping records."""
+    ref = synth.reference(1, 4_600_000)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    om = po.Mapper(ref, vals, circular=True)
+    gm = dp.Mapper(ref, vals, circular=True)
+    assert np.array_equal(np.sort(om.seed_kmers()), gm.seed_kmers())
+    n, L = 10_000, 10_000
+    rd = synth.reads(ref, 11, n, L)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    orow, ooff, octr = om.map_batch(rd, offs, threads=os.cpu_count() or 4)
+    gmaps, goff = gm.map_batch(rd, offs)
+    assert np.array_equal(ooff, goff)
+    assert np.array_equal(orow, rows_of(gmaps))
+    assert gm.stats()["posting_entries"] == octr["posting_entries"]
+    gm.close()
