@@ -16,6 +16,7 @@
 
 #include "../../include/downpore_b200.h"
 #include "dp_common.cuh"
+#include "dp_finish.cuh"
 #include "dp_host_map.hpp"
 #include "dp_index.cuh"
 #include "dp_map.cuh"
@@ -114,7 +115,11 @@ struct dp_mapper {
     DBuf<unsigned> dWords;
     DBuf<DpWindow> dWins;
     DBuf<unsigned> wsOff, qSeed, candChunk;
-    DBuf<int> wsN, qPos, candN, outN;
+    DBuf<int> wsN, qPos, candN, outN, dFinN;
+    DBuf<unsigned> outOff, dFinOff;
+    DBuf<unsigned char> dStatus, scanTmp;
+    DBuf<DpMappingDev> dFinMaps;
+    DBuf<long long> dWordsNeeded;
     DBuf<unsigned short> candDistinct;
     DBuf<DpMappingDev> outMaps;
     DBuf<unsigned long long> cursor;
@@ -128,8 +133,13 @@ struct dp_mapper {
     DBuf<unsigned char> csHashFlag;
     DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
     DBuf<DpMappingDev> csResults;
-    HBuf<int> hOutN;
-    HBuf<DpMappingDev> hOutMaps;
+    HBuf<int> hOutN, hFinN;
+    HBuf<unsigned> hOutOff, hFinOff;
+    HBuf<unsigned char> hStatus;
+    HBuf<DpMappingDev> hOutMaps, hFinMaps;
+    HBuf<long long> hRel;
+    size_t hOutTotal = 0;
+    bool pendingStageTimes = false;
     HBuf<DpWindow> hWins;
     HBuf<unsigned char> hStage;
     std::vector<Timer> timers;
@@ -415,13 +425,6 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
 // ----------------------------------------------------------------------------------------------------------------
 // window rounds
 // ----------------------------------------------------------------------------------------------------------------
-struct Launch {
-    int extractBlocks, lookupBlocks, chainBlocks;
-    int countersInSmem;
-    size_t extractSmem, lookupSmem;
-    int maskWords;
-};
-
 void ensure_window_capacity(dp_mapper& M, size_t nWin, size_t seedEntries) {
     const DpIndexDev& I = M.I;
     M.dWins.reserve(nWin);
@@ -429,16 +432,15 @@ void ensure_window_capacity(dp_mapper& M, size_t nWin, size_t seedEntries) {
     M.wsN.reserve(2 * nWin);
     M.qSeed.reserve(seedEntries + 64);
     M.qPos.reserve(seedEntries + 64);
-    M.cursor.reserve(1);
+    M.cursor.reserve(4);
     M.dCtr.reserve(1);
     M.candStride = (int)std::min<unsigned>(I.numChunks, 1024u);
     M.candN.reserve(2 * nWin);
     M.candChunk.reserve(2 * nWin * (size_t)M.candStride);
     M.candDistinct.reserve(2 * nWin * (size_t)M.candStride);
     M.outN.reserve(nWin);
+    M.outOff.reserve(nWin);
     M.outMaps.reserve(nWin * (size_t)M.outStride);
-    M.hOutN.reserve(nWin);
-    M.hOutMaps.reserve(nWin * (size_t)M.outStride);
     // per-warp scratch
     const int qStride = I.maxWindow + 8;
     M.extractWarps = M.smCount * 8 * 8;
@@ -469,28 +471,24 @@ void ensure_window_capacity(dp_mapper& M, size_t nWin, size_t seedEntries) {
     M.csResults.reserve(cw * M.resultCap);
 }
 
-enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_N };
+enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_N };
+enum { CUR_SEEDS = 0, CUR_OUT = 1, CUR_FIN = 2 };
 
-// Runs performMapping for `nWin` windows (host array `wins`), leaves counts/mappings in M.hOutN / M.hOutMaps.
-void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
-                 const int* dReadLen) {
-    if (nWin == 0) return;
+// Launches the three performMapping stages for the `nWin` windows already in M.dWins (device). Results stay on the
+// device: M.outN / M.outOff / M.outMaps (compact, bump-allocated through cursor[CUR_OUT]).
+void launch_windows(dp_mapper& M, size_t nWin, size_t seedEntries, const unsigned* dWords, const long long* dWordOff,
+                    const int* dReadLen) {
     const DpIndexDev& I = M.I;
     cudaStream_t st = M.stream;
-    size_t seedEntries = 0;
-    for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
-    ensure_window_capacity(M, nWin, seedEntries);
-    CK(cudaMemcpyAsync(M.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(M.cursor.p, 0, sizeof(unsigned long long), st));
-
+    CK(cudaMemsetAsync(M.cursor.p, 0, 4 * sizeof(unsigned long long), st));
     const int qStride = I.maxWindow + 8;
     DpExtractOut Q;
     Q.wsOff = M.wsOff.p;
     Q.wsN = M.wsN.p;
     Q.qSeed = M.qSeed.p;
     Q.qPos = M.qPos.p;
-    Q.cursor = M.cursor.p;
+    Q.cursor = M.cursor.p + CUR_SEEDS;
     const int maskWords = (I.maxWindow + 31) / 32 + 1;
     {
         int warpsPerBlock = 8;
@@ -545,15 +543,19 @@ void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.chainWarps / 4);
         CK(cudaEventRecord(M.timers[T_CHAIN].a, st));
         dp_chain_kernel<<<blocks, 128, 0, st>>>(I, M.dWins.p, dReadLen, (int)nWin, Q, M.candN.p, M.candChunk.p,
-                                                M.candDistinct.p, M.candStride, S, M.outN.p, M.outMaps.p, M.outStride,
-                                                M.dCtr.p);
+                                                M.candDistinct.p, M.candStride, S, M.outN.p, M.outOff.p, M.outMaps.p,
+                                                M.cursor.p + CUR_OUT, (unsigned long long)nWin * M.outStride, M.dCtr.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(M.timers[T_CHAIN].b, st));
     }
-    CK(cudaMemcpyAsync(M.hOutN.p, M.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(M.hOutMaps.p, M.outMaps.p, nWin * (size_t)M.outStride * sizeof(DpMappingDev),
-                       cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    M.stats.kernel_launches += 3;
+    M.stats.rounds += 1;
+    M.stats.windows += (int64_t)nWin;
+    M.pendingStageTimes = true;
+}
+
+void collect_stage_times(dp_mapper& M) {  // call after a stream synchronize
+    if (!M.pendingStageTimes) return;
     float ms;
     CK(cudaEventElapsedTime(&ms, M.timers[T_EXTRACT].a, M.timers[T_EXTRACT].b));
     M.stats.ms_extract += ms;
@@ -561,9 +563,39 @@ void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned
     M.stats.ms_lookup += ms;
     CK(cudaEventElapsedTime(&ms, M.timers[T_CHAIN].a, M.timers[T_CHAIN].b));
     M.stats.ms_chain += ms;
-    M.stats.kernel_launches += 3;
-    M.stats.rounds += 1;
-    M.stats.windows += (int64_t)nWin;
+    M.pendingStageTimes = false;
+}
+
+// Copies the window results of the last launch_windows() to the pinned host mirrors (hOutN, hOutOff, hOutMaps).
+void download_windows(dp_mapper& M, size_t nWin) {
+    cudaStream_t st = M.stream;
+    unsigned long long cur[4];
+    CK(cudaMemcpyAsync(cur, M.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    M.hOutN.reserve(nWin);
+    M.hOutOff.reserve(nWin);
+    CK(cudaMemcpyAsync(M.hOutN.p, M.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(M.hOutOff.p, M.outOff.p, nWin * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    collect_stage_times(M);
+    size_t total = (size_t)cur[CUR_OUT];
+    M.hOutMaps.reserve(total + 1);
+    if (total) {
+        CK(cudaMemcpyAsync(M.hOutMaps.p, M.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    M.hOutTotal = total;
+}
+
+// Host-supplied window list (rounds after the first, and the test probe).
+void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
+                 const int* dReadLen) {
+    if (nWin == 0) return;
+    size_t seedEntries = 0;
+    for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
+    ensure_window_capacity(M, nWin, seedEntries);
+    CK(cudaMemcpyAsync(M.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, M.stream));
+    launch_windows(M, nWin, seedEntries, dWords, dWordOff, dReadLen);
+    download_windows(M, nWin);
 }
 
 void reset_counters(dp_mapper& M) {
@@ -599,111 +631,190 @@ void map_subbatch(dp_mapper& M, const unsigned char* dAscii, const int64_t* offs
     const int64_t n = r1 - r0;
     cudaStream_t st = M.stream;
     const int k = M.k;
-    // ---- read tables + pack ----
-    std::vector<long long> seqOff((size_t)n + 1), wordOff((size_t)n);
-    std::vector<int> readLen((size_t)n);
-    long long words = 0;
+    const int e = M.edge;
+    const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
+    // ---- read tables on the device: lengths, packed-word offsets ----
+    double t0 = now_ms();
+    M.hRel.reserve((size_t)n + 1);
+    long long maxLen = 0;
+    for (int64_t i = 0; i <= n; i++) M.hRel.p[i] = offsets[r0 + i] - offsets[r0];
     for (int64_t i = 0; i < n; i++) {
-        long long len = offsets[r0 + i + 1] - offsets[r0 + i];
-        if (len < 0 || len > 0x7fffff00ll) throw std::runtime_error("bad read length");
-        seqOff[(size_t)i] = offsets[r0 + i] - offsets[r0];
-        wordOff[(size_t)i] = words;
-        readLen[(size_t)i] = (int)len;
-        words += (len + 15) / 16 + 1;
+        long long len = M.hRel.p[i + 1] - M.hRel.p[i];
+        if (len < 0) throw std::runtime_error("read offsets must be non-decreasing");
+        maxLen = std::max(maxLen, len);
     }
-    seqOff[(size_t)n] = offsets[r1] - offsets[r0];
+    if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
+    const long long totalBytes = M.hRel.p[n];
+    const size_t wordCap = (size_t)(totalBytes / 16 + 2 * n + 16);
     M.dSeqOff.reserve((size_t)n + 1);
-    M.dWordOff.reserve((size_t)n);
+    M.dWordsNeeded.reserve((size_t)n + 1);
+    M.dWordOff.reserve((size_t)n + 1);
     M.dReadLen.reserve((size_t)n);
-    M.dWords.reserve((size_t)words + 8);
-    CK(cudaMemcpyAsync(M.dSeqOff.p, seqOff.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(M.dWordOff.p, wordOff.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(M.dReadLen.p, readLen.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    M.dWords.reserve(wordCap);
+    CK(cudaMemcpyAsync(M.dSeqOff.p, M.hRel.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    dp_read_table_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(M.dSeqOff.p, n, M.dReadLen.p, M.dWordsNeeded.p);
+    CK(cudaGetLastError());
+    {
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, M.dWordsNeeded.p, M.dWordOff.p, (int)n + 1, st);
+        M.scanTmp.reserve(tmpBytes);
+        CK(cub::DeviceScan::ExclusiveSum(M.scanTmp.p, tmpBytes, M.dWordsNeeded.p, M.dWordOff.p, (int)n + 1, st));
+    }
     {
         int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)M.smCount * 16);
         CK(cudaEventRecord(M.timers[T_PACK].a, st));
         dp_pack_kernel<<<blocks, 256, 0, st>>>(dAscii, M.dSeqOff.p, M.dWordOff.p, M.dWords.p, n);
         CK(cudaGetLastError());
         CK(cudaEventRecord(M.timers[T_PACK].b, st));
-        CK(cudaStreamSynchronize(st));
+        M.stats.kernel_launches += 3;
+    }
+    // ---- round 0 entirely on the device: windows, performMapping stages, Map()'s first decision ----
+    const size_t nWin0 = 2 * (size_t)n;
+    size_t seedEntries0 = 0;
+    {
+        // worst case: every k-mer of every round-0 window is a seed on both strands
+        long long perRead = 2ll * 2 * (std::min<long long>(maxLen, 2ll * e) + 2);
+        seedEntries0 = (size_t)perRead * (size_t)n;
+        if (seedEntries0 >= 0xffffffffull) throw std::runtime_error("sub-batch too large");
+    }
+    ensure_window_capacity(M, nWin0, seedEntries0);
+    dp_round0_windows_kernel<<<div_up(n, 256), 256, 0, st>>>(M.dReadLen.p, n, e, minLen, M.dWins.p);
+    CK(cudaGetLastError());
+    launch_windows(M, nWin0, seedEntries0, M.dWords.p, M.dWordOff.p, M.dReadLen.p);
+    M.dStatus.reserve((size_t)n);
+    M.dFinN.reserve((size_t)n);
+    M.dFinOff.reserve((size_t)n);
+    M.dFinMaps.reserve((size_t)n * 4 + 64);
+    CK(cudaEventRecord(M.timers[T_FINISH].a, st));
+    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, M.dReadLen.p, n, minLen, M.outN.p, M.outOff.p,
+                                                            M.outMaps.p, M.dStatus.p, M.dFinN.p, M.dFinOff.p,
+                                                            M.dFinMaps.p, M.cursor.p + CUR_FIN,
+                                                            (unsigned long long)M.dFinMaps.cap);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(M.timers[T_FINISH].b, st));
+    M.stats.kernel_launches += 2;
+    M.hStatus.reserve((size_t)n);
+    M.hFinN.reserve((size_t)n);
+    M.hFinOff.reserve((size_t)n);
+    unsigned long long cur[4];
+    CK(cudaMemcpyAsync(M.hStatus.p, M.dStatus.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(M.hFinN.p, M.dFinN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(M.hFinOff.p, M.dFinOff.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur, M.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    M.stats.ms_host_logic += now_ms() - t0;
+    CK(cudaStreamSynchronize(st));
+    collect_stage_times(M);
+    {
         float ms;
         CK(cudaEventElapsedTime(&ms, M.timers[T_PACK].a, M.timers[T_PACK].b));
         M.stats.ms_pack += ms;
-        M.stats.kernel_launches += 1;
+        CK(cudaEventElapsedTime(&ms, M.timers[T_FINISH].a, M.timers[T_FINISH].b));
+        M.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
     }
-    // ---- rounds ----
+    const size_t finTotal = (size_t)std::min<unsigned long long>(cur[CUR_FIN], (unsigned long long)M.dFinMaps.cap);
+    M.hFinMaps.reserve(finTotal + 1);
+    if (finTotal)
+        CK(cudaMemcpyAsync(M.hFinMaps.p, M.dFinMaps.p, finTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    t0 = now_ms();
+    std::vector<int> active;
+    for (int64_t i = 0; i < n; i++) {
+        std::vector<dph::Hit>& out = results[(size_t)(r0 + i)];
+        out.clear();
+        if (M.hStatus.p[i] == DP_READ_DONE) {
+            int cnt = M.hFinN.p[i];
+            const DpMappingDev* src = M.hFinMaps.p + M.hFinOff.p[i];
+            for (int j = 0; j < cnt; j++) {
+                dph::Hit h;
+                h.start = src[j].start;
+                h.end = src[j].end;
+                h.qOffset = src[j].qOffset;
+                h.qInset = src[j].qInset;
+                h.ids = src[j].ids;
+                h.rc = (src[j].rc & 0xff) != 0;
+                out.push_back(h);
+            }
+        } else {
+            active.push_back((int)i);
+        }
+    }
+    M.stats.ms_host_logic += now_ms() - t0;
+    if (active.empty()) return;
+
+    // ---- unresolved reads: replay Map() on the host against cached window results, round by round ----
+    t0 = now_ms();
+    download_windows(M, nWin0);
+    std::vector<ReadCache> cache(active.size());
+    std::vector<int> slotOf;  // read index -> slot in `cache`
+    slotOf.assign((size_t)n, -1);
+    std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
+    {
+        roundMaps.emplace_back();
+        std::vector<DpMappingDev>& keep = roundMaps.back();
+        size_t total = 0;
+        for (int i : active) total += (size_t)M.hOutN.p[2 * i] + (size_t)M.hOutN.p[2 * i + 1];
+        keep.resize(total + 1);
+        size_t pos = 0;
+        for (size_t a = 0; a < active.size(); a++) {
+            int i = active[a];
+            slotOf[(size_t)i] = (int)a;
+            long long len = M.hRel.p[i + 1] - M.hRel.p[i];
+            for (int s = 0; s < 2; s++) {
+                size_t wI = 2 * (size_t)i + s;
+                dph::WinRef ref;
+                if (len <= 2ll * e) {
+                    if (s == 1) continue;
+                    ref.start = 0;
+                    ref.len = (int)len;
+                    ref.whole = 1;
+                } else {
+                    ref.start = s == 0 ? 0 : (int)(len - e);
+                    ref.len = e;
+                    ref.whole = 0;
+                }
+                int cnt = M.hOutN.p[wI];
+                memcpy(keep.data() + pos, M.hOutMaps.p + M.hOutOff.p[wI], (size_t)cnt * sizeof(DpMappingDev));
+                ref.n = cnt;
+                ref.maps = keep.data() + pos;
+                cache[a].wins.push_back(ref);
+                pos += (size_t)cnt;
+            }
+        }
+    }
     dph::Params P;
     P.refLen = M.refLen;
-    P.edge = M.edge;
+    P.edge = e;
     P.circular = M.circular != 0;
-    std::vector<ReadCache> cache((size_t)n);
-    std::vector<int> active((size_t)n);
-    for (int64_t i = 0; i < n; i++) active[(size_t)i] = (int)i;
-    // results of every round must stay alive while reads are replayed: keep per-round host copies
-    std::vector<std::vector<DpMappingDev>> roundMaps;
-    const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
-    int nThreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    dph::ReadMapper rm(P);
+    M.stats.ms_host_logic += now_ms() - t0;
     while (!active.empty()) {
-        double t0 = now_ms();
-        std::vector<std::vector<DpWindow>> reqs((size_t)nThreads);
-        std::vector<std::vector<int>> still((size_t)nThreads);
-        auto work = [&](int t) {
-            dph::ReadMapper rm(P);
-            size_t a0 = active.size() * (size_t)t / (size_t)nThreads, a1 = active.size() * (size_t)(t + 1) / (size_t)nThreads;
-            for (size_t a = a0; a < a1; a++) {
-                int i = active[a];
-                if (readLen[(size_t)i] < minLen) {
-                    results[(size_t)(r0 + i)].clear();
-                    continue;
-                }
-                const ReadCache& rc = cache[(size_t)i];
-                bool done = rm.run(i, readLen[(size_t)i], rc.wins.data(), (int)rc.wins.size(), reqs[(size_t)t],
-                                   results[(size_t)(r0 + i)]);
-                if (!done) still[(size_t)t].push_back(i);
-            }
-        };
-        if (active.size() < 2048) {
-            nThreads = 1;
-            reqs.resize(1);
-            still.resize(1);
-            work(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 1; t < nThreads; t++) th.emplace_back(work, t);
-            work(0);
-            for (auto& x : th) x.join();
-        }
+        t0 = now_ms();
         std::vector<DpWindow> wins;
         std::vector<int> next;
-        for (size_t t = 0; t < reqs.size(); t++) {
-            wins.insert(wins.end(), reqs[t].begin(), reqs[t].end());
-            next.insert(next.end(), still[t].begin(), still[t].end());
+        for (int i : active) {
+            const ReadCache& rc = cache[(size_t)slotOf[(size_t)i]];
+            long long len = M.hRel.p[i + 1] - M.hRel.p[i];
+            bool done = rm.run(i, len, rc.wins.data(), (int)rc.wins.size(), wins, results[(size_t)(r0 + i)]);
+            if (!done) next.push_back(i);
         }
         M.stats.ms_host_logic += now_ms() - t0;
         if (wins.empty()) break;
         run_windows(M, wins.data(), wins.size(), M.dWords.p, M.dWordOff.p, M.dReadLen.p);
         t0 = now_ms();
-        // keep this round's mappings and attach them to the reads' caches
         roundMaps.emplace_back();
         std::vector<DpMappingDev>& keep = roundMaps.back();
-        size_t total = 0;
-        for (size_t wI = 0; wI < wins.size(); wI++) total += (size_t)M.hOutN.p[wI];
-        keep.resize(total + 1);
-        size_t pos = 0;
+        keep.assign(M.hOutMaps.p, M.hOutMaps.p + M.hOutTotal);
+        keep.resize(M.hOutTotal + 1);
         for (size_t wI = 0; wI < wins.size(); wI++) {
-            int cnt = M.hOutN.p[wI];
-            memcpy(keep.data() + pos, M.hOutMaps.p + wI * (size_t)M.outStride, (size_t)cnt * sizeof(DpMappingDev));
             dph::WinRef ref;
             ref.start = wins[wI].start;
             ref.len = wins[wI].len;
             ref.whole = wins[wI].whole;
-            ref.n = cnt;
-            ref.maps = keep.data() + pos;
-            cache[(size_t)wins[wI].read].wins.push_back(ref);
-            pos += (size_t)cnt;
+            ref.n = M.hOutN.p[wI];
+            ref.maps = keep.data() + M.hOutOff.p[wI];
+            cache[(size_t)slotOf[(size_t)wins[wI].read]].wins.push_back(ref);
         }
         active.swap(next);
-        nThreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
         M.stats.ms_host_logic += now_ms() - t0;
     }
 }
@@ -1047,7 +1158,7 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
         int cnt = m->hOutN.p[0];
         if (cnt > map_cap) throw std::runtime_error("map_cap too small");
         for (int i = 0; i < cnt; i++) {
-            const DpMappingDev& d = m->hOutMaps.p[i];
+            const DpMappingDev& d = m->hOutMaps.p[m->hOutOff.p[0] + i];
             dp_mapping o;
             memset(&o, 0, sizeof(o));
             o.start = d.start;

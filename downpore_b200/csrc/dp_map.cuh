@@ -560,7 +560,10 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                                                        const unsigned* __restrict__ candChunk,
                                                        const unsigned short* __restrict__ candDistinct, int candStride,
                                                        DpChainScratch S, int* __restrict__ outN,
-                                                       DpMappingDev* __restrict__ outMaps, int outStride,
+                                                       unsigned* __restrict__ outOff,
+                                                       DpMappingDev* __restrict__ outMaps,
+                                                       unsigned long long* __restrict__ outCursor,
+                                                       unsigned long long outCapacity,
                                                        DpCounters* __restrict__ ctr) {
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
@@ -789,12 +792,16 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                     }
                 }
             }
-            if (nRes > outStride) {
+            // compact output: one bump allocation per window
+            unsigned long long base = nRes ? atomicAdd(outCursor, (unsigned long long)nRes) : 0ull;
+            if (base + (unsigned)nRes > outCapacity) {
                 atomicOr(&ctr->overflow, 1u);
-                nRes = outStride;
+                nRes = 0;
+                base = 0;
             }
             outN[w] = nRes;
-            for (int i = 0; i < nRes; i++) outMaps[(size_t)w * outStride + i] = results[i];
+            outOff[w] = (unsigned)base;
+            for (int i = 0; i < nRes; i++) outMaps[base + i] = results[i];
             cMaps += (unsigned)nRes;
         }
         __syncwarp();
