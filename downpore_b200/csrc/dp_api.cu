@@ -90,10 +90,51 @@ double now_ms() {
 
 }  // namespace
 
+// Per-lane workspace: one stream plus every buffer a sub-batch needs. Two lanes let the host work of one sub-batch
+// (result assembly, the rare replay rounds) overlap the kernels of the next.
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DBuf<unsigned char> dAscii;
+    DBuf<long long> dSeqOff, dWordOff, dWordsNeeded;
+    DBuf<int> dReadLen;
+    DBuf<unsigned> dWords;
+    DBuf<DpWindow> dWins;
+    DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff;
+    DBuf<int> wsN, qPos, candN, outN, dFinN;
+    DBuf<unsigned short> candDistinct;
+    DBuf<DpMappingDev> outMaps, dFinMaps;
+    DBuf<unsigned long long> cursor;
+    DBuf<DpCounters> dCtr;
+    DBuf<unsigned char> dStatus, scanTmp;
+    // lookup scratch
+    DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters;
+    DBuf<unsigned char> lsFirst;
+    DBuf<unsigned short> lsOrder;
+    // chain scratch
+    DBuf<unsigned> csHashKey, csRqSeed, csRsSeed;
+    DBuf<unsigned char> csHashFlag;
+    DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
+    DBuf<DpMappingDev> csResults;
+    HBuf<int> hOutN, hFinN;
+    HBuf<unsigned> hOutOff, hFinOff;
+    HBuf<unsigned char> hStatus, hStage;
+    HBuf<DpMappingDev> hOutMaps, hFinMaps;
+    HBuf<long long> hRel;
+    size_t hOutTotal = 0;
+    bool pendingStageTimes = false;
+    std::vector<Timer> timers;
+    dp_stats stats{};
+    int candStride = 0;
+    int extractWarps = 0, lookupWarps = 0, chainWarps = 0;
+    ~Lane() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct dp_mapper {
     int device = 0;
     int smCount = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // index construction
     // parameters
     int k = 0, circular = 0, seedRate = 0, edge = 0, chunkSize = 0;
     long long refLen = 0;
@@ -108,46 +149,12 @@ struct dp_mapper {
     DpIndexDev I{};
     long long nChunkPostings = 0, nSeedPostings = 0;
     size_t indexBytes = 0;
-    // map workspace (sized per sub-batch, grow-only)
-    DBuf<unsigned char> dAscii;
-    DBuf<long long> dSeqOff, dWordOff;
-    DBuf<int> dReadLen;
-    DBuf<unsigned> dWords;
-    DBuf<DpWindow> dWins;
-    DBuf<unsigned> wsOff, qSeed, candChunk;
-    DBuf<int> wsN, qPos, candN, outN, dFinN;
-    DBuf<unsigned> outOff, dFinOff;
-    DBuf<unsigned char> dStatus, scanTmp;
-    DBuf<DpMappingDev> dFinMaps;
-    DBuf<long long> dWordsNeeded;
-    DBuf<unsigned short> candDistinct;
-    DBuf<DpMappingDev> outMaps;
-    DBuf<unsigned long long> cursor;
-    DBuf<DpCounters> dCtr;
-    // lookup scratch
-    DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters;
-    DBuf<unsigned char> lsFirst;
-    DBuf<unsigned short> lsOrder;
-    // chain scratch
-    DBuf<unsigned> csHashKey, csRqSeed, csRsSeed;
-    DBuf<unsigned char> csHashFlag;
-    DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
-    DBuf<DpMappingDev> csResults;
-    HBuf<int> hOutN, hFinN;
-    HBuf<unsigned> hOutOff, hFinOff;
-    HBuf<unsigned char> hStatus;
-    HBuf<DpMappingDev> hOutMaps, hFinMaps;
-    HBuf<long long> hRel;
-    size_t hOutTotal = 0;
-    bool pendingStageTimes = false;
-    HBuf<DpWindow> hWins;
-    HBuf<unsigned char> hStage;
-    std::vector<Timer> timers;
+    std::vector<std::unique_ptr<Lane>> lanes;
     dp_stats stats{};
-    int candStride = 0, outStride = 16, resultCap = 128, chainCap = 64;
-    int extractWarps = 0, lookupWarps = 0, chainWarps = 0;
+    int outStride = 16, resultCap = 128, chainCap = 64;
 
     ~dp_mapper() {
+        lanes.clear();
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -425,193 +432,193 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
 // ----------------------------------------------------------------------------------------------------------------
 // window rounds
 // ----------------------------------------------------------------------------------------------------------------
-void ensure_window_capacity(dp_mapper& M, size_t nWin, size_t seedEntries) {
+void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries) {
     const DpIndexDev& I = M.I;
-    M.dWins.reserve(nWin);
-    M.wsOff.reserve(2 * nWin);
-    M.wsN.reserve(2 * nWin);
-    M.qSeed.reserve(seedEntries + 64);
-    M.qPos.reserve(seedEntries + 64);
-    M.cursor.reserve(4);
-    M.dCtr.reserve(1);
-    M.candStride = (int)std::min<unsigned>(I.numChunks, 1024u);
-    M.candN.reserve(2 * nWin);
-    M.candChunk.reserve(2 * nWin * (size_t)M.candStride);
-    M.candDistinct.reserve(2 * nWin * (size_t)M.candStride);
-    M.outN.reserve(nWin);
-    M.outOff.reserve(nWin);
-    M.outMaps.reserve(nWin * (size_t)M.outStride);
+    W.dWins.reserve(nWin);
+    W.wsOff.reserve(2 * nWin);
+    W.wsN.reserve(2 * nWin);
+    W.qSeed.reserve(seedEntries + 64);
+    W.qPos.reserve(seedEntries + 64);
+    W.cursor.reserve(4);
+    W.dCtr.reserve(1);
+    W.candStride = (int)std::min<unsigned>(I.numChunks, 1024u);
+    W.candN.reserve(2 * nWin);
+    W.candChunk.reserve(2 * nWin * (size_t)W.candStride);
+    W.candDistinct.reserve(2 * nWin * (size_t)W.candStride);
+    W.outN.reserve(nWin);
+    W.outOff.reserve(nWin);
+    W.outMaps.reserve(nWin * (size_t)M.outStride);
     // per-warp scratch
     const int qStride = I.maxWindow + 8;
-    M.extractWarps = M.smCount * 8 * 8;
-    M.lookupWarps = M.smCount * 4 * 8;
-    M.chainWarps = M.smCount * 4 * 8;
-    size_t lw = (size_t)M.lookupWarps;
-    M.lsSeed.reserve(lw * qStride);
-    M.lsOff.reserve(lw * qStride);
-    M.lsPre.reserve(lw * (qStride + 1));
-    M.lsEndW.reserve(lw * qStride);
-    M.lsAll.reserve(lw * qStride);
-    M.lsFirst.reserve(lw * qStride);
-    M.lsOrder.reserve(lw * qStride);
-    if (I.numChunks > 2048) M.lsCounters.reserve(lw * I.numChunks);
-    size_t cw = (size_t)M.chainWarps;
+    W.extractWarps = M.smCount * 8 * 8;
+    W.lookupWarps = M.smCount * 4 * 8;
+    W.chainWarps = M.smCount * 4 * 8;
+    size_t lw = (size_t)W.lookupWarps;
+    W.lsSeed.reserve(lw * qStride);
+    W.lsOff.reserve(lw * qStride);
+    W.lsPre.reserve(lw * (qStride + 1));
+    W.lsEndW.reserve(lw * qStride);
+    W.lsAll.reserve(lw * qStride);
+    W.lsFirst.reserve(lw * qStride);
+    W.lsOrder.reserve(lw * qStride);
+    if (I.numChunks > 2048) W.lsCounters.reserve(lw * I.numChunks);
+    size_t cw = (size_t)W.chainWarps;
     int hashSize = 64;
     while (hashSize < 2 * qStride) hashSize <<= 1;
     const int sStride = (int)I.maxChunkSeeds + 8;
-    M.csHashKey.reserve(cw * hashSize);
-    M.csHashFlag.reserve(cw * hashSize);
-    M.csRqSeed.reserve(cw * qStride);
-    M.csRqPos.reserve(cw * qStride);
-    M.csRsSeed.reserve(cw * sStride);
-    M.csRsPos.reserve(cw * sStride);
-    M.csChainLen.reserve(cw * qStride);
-    M.csLastB.reserve(cw * qStride);
-    M.csChains.reserve(cw * M.chainCap * 6);
-    M.csResults.reserve(cw * M.resultCap);
+    W.csHashKey.reserve(cw * hashSize);
+    W.csHashFlag.reserve(cw * hashSize);
+    W.csRqSeed.reserve(cw * qStride);
+    W.csRqPos.reserve(cw * qStride);
+    W.csRsSeed.reserve(cw * sStride);
+    W.csRsPos.reserve(cw * sStride);
+    W.csChainLen.reserve(cw * qStride);
+    W.csLastB.reserve(cw * qStride);
+    W.csChains.reserve(cw * M.chainCap * 6);
+    W.csResults.reserve(cw * M.resultCap);
 }
 
 enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_N };
 enum { CUR_SEEDS = 0, CUR_OUT = 1, CUR_FIN = 2 };
 
-// Launches the three performMapping stages for the `nWin` windows already in M.dWins (device). Results stay on the
-// device: M.outN / M.outOff / M.outMaps (compact, bump-allocated through cursor[CUR_OUT]).
-void launch_windows(dp_mapper& M, size_t nWin, size_t seedEntries, const unsigned* dWords, const long long* dWordOff,
+// Launches the three performMapping stages for the `nWin` windows already in W.dWins (device). Results stay on the
+// device: W.outN / W.outOff / W.outMaps (compact, bump-allocated through cursor[CUR_OUT]).
+void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, const unsigned* dWords, const long long* dWordOff,
                     const int* dReadLen) {
     const DpIndexDev& I = M.I;
-    cudaStream_t st = M.stream;
+    cudaStream_t st = W.stream;
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
-    CK(cudaMemsetAsync(M.cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
     const int qStride = I.maxWindow + 8;
     DpExtractOut Q;
-    Q.wsOff = M.wsOff.p;
-    Q.wsN = M.wsN.p;
-    Q.qSeed = M.qSeed.p;
-    Q.qPos = M.qPos.p;
-    Q.cursor = M.cursor.p + CUR_SEEDS;
+    Q.wsOff = W.wsOff.p;
+    Q.wsN = W.wsN.p;
+    Q.qSeed = W.qSeed.p;
+    Q.qPos = W.qPos.p;
+    Q.cursor = W.cursor.p + CUR_SEEDS;
     const int maskWords = (I.maxWindow + 31) / 32 + 1;
     {
         int warpsPerBlock = 8;
-        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.extractWarps / 8);
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.extractWarps / 8);
         size_t smem = (size_t)warpsPerBlock * 2 * maskWords * sizeof(unsigned);
-        CK(cudaEventRecord(M.timers[T_EXTRACT].a, st));
-        dp_extract_kernel<<<blocks, 256, smem, st>>>(I, dWords, dWordOff, M.dWins.p, (int)nWin, Q, maskWords, M.dCtr.p);
+        CK(cudaEventRecord(W.timers[T_EXTRACT].a, st));
+        dp_extract_kernel<<<blocks, 256, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords, W.dCtr.p);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(M.timers[T_EXTRACT].b, st));
+        CK(cudaEventRecord(W.timers[T_EXTRACT].b, st));
     }
     {
         DpLookupScratch S;
-        S.eSeed = M.lsSeed.p;
-        S.eOff = M.lsOff.p;
-        S.ePre = M.lsPre.p;
-        S.eEndW = M.lsEndW.p;
-        S.eFirst = M.lsFirst.p;
-        S.allSeeds = M.lsAll.p;
-        S.order = M.lsOrder.p;
-        S.counters = M.lsCounters.p;
+        S.eSeed = W.lsSeed.p;
+        S.eOff = W.lsOff.p;
+        S.ePre = W.lsPre.p;
+        S.eEndW = W.lsEndW.p;
+        S.eFirst = W.lsFirst.p;
+        S.allSeeds = W.lsAll.p;
+        S.order = W.lsOrder.p;
+        S.counters = W.lsCounters.p;
         S.stride = qStride;
         int inSmem = I.numChunks <= 2048 ? 1 : 0;
         int warpsPerBlock = 4;
         size_t smem = inSmem ? (size_t)warpsPerBlock * I.numChunks * sizeof(unsigned) : 0;
-        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.lookupWarps / 4);
-        CK(cudaEventRecord(M.timers[T_LOOKUP].a, st));
-        dp_lookup_kernel<<<blocks, 128, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, M.candN.p, M.candChunk.p,
-                                                    M.candDistinct.p, M.candStride, M.dCtr.p);
+        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.lookupWarps / 4);
+        CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
+        dp_lookup_kernel<<<blocks, 128, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, W.candN.p, W.candChunk.p,
+                                                    W.candDistinct.p, W.candStride, W.dCtr.p);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(M.timers[T_LOOKUP].b, st));
+        CK(cudaEventRecord(W.timers[T_LOOKUP].b, st));
     }
     {
         DpChainScratch S;
         int hashSize = 64;
         while (hashSize < 2 * qStride) hashSize <<= 1;
-        S.hashKey = M.csHashKey.p;
-        S.hashFlag = M.csHashFlag.p;
-        S.rqSeed = M.csRqSeed.p;
-        S.rqPos = M.csRqPos.p;
-        S.rsSeed = M.csRsSeed.p;
-        S.rsPos = M.csRsPos.p;
-        S.chainLen = M.csChainLen.p;
-        S.lastB = M.csLastB.p;
-        S.chains = M.csChains.p;
-        S.results = M.csResults.p;
+        S.hashKey = W.csHashKey.p;
+        S.hashFlag = W.csHashFlag.p;
+        S.rqSeed = W.csRqSeed.p;
+        S.rqPos = W.csRqPos.p;
+        S.rsSeed = W.csRsSeed.p;
+        S.rsPos = W.csRsPos.p;
+        S.chainLen = W.csChainLen.p;
+        S.lastB = W.csLastB.p;
+        S.chains = W.csChains.p;
+        S.results = W.csResults.p;
         S.hashSize = hashSize;
         S.qStride = qStride;
         S.sStride = (int)I.maxChunkSeeds + 8;
         S.chainCap = M.chainCap;
         S.resultCap = M.resultCap;
         int warpsPerBlock = 4;
-        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.chainWarps / 4);
-        CK(cudaEventRecord(M.timers[T_CHAIN].a, st));
-        dp_chain_kernel<<<blocks, 128, 0, st>>>(I, M.dWins.p, dReadLen, (int)nWin, Q, M.candN.p, M.candChunk.p,
-                                                M.candDistinct.p, M.candStride, S, M.outN.p, M.outOff.p, M.outMaps.p,
-                                                M.cursor.p + CUR_OUT, (unsigned long long)nWin * M.outStride, M.dCtr.p);
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.chainWarps / 4);
+        CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
+        dp_chain_kernel<<<blocks, 128, 0, st>>>(I, W.dWins.p, dReadLen, (int)nWin, Q, W.candN.p, W.candChunk.p,
+                                                W.candDistinct.p, W.candStride, S, W.outN.p, W.outOff.p, W.outMaps.p,
+                                                W.cursor.p + CUR_OUT, (unsigned long long)nWin * M.outStride, W.dCtr.p);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(M.timers[T_CHAIN].b, st));
+        CK(cudaEventRecord(W.timers[T_CHAIN].b, st));
     }
-    M.stats.kernel_launches += 3;
-    M.stats.rounds += 1;
-    M.stats.windows += (int64_t)nWin;
-    M.pendingStageTimes = true;
+    W.stats.kernel_launches += 3;
+    W.stats.rounds += 1;
+    W.stats.windows += (int64_t)nWin;
+    W.pendingStageTimes = true;
 }
 
-void collect_stage_times(dp_mapper& M) {  // call after a stream synchronize
-    if (!M.pendingStageTimes) return;
+void collect_stage_times(Lane& W) {  // call after a stream synchronize
+    if (!W.pendingStageTimes) return;
     float ms;
-    CK(cudaEventElapsedTime(&ms, M.timers[T_EXTRACT].a, M.timers[T_EXTRACT].b));
-    M.stats.ms_extract += ms;
-    CK(cudaEventElapsedTime(&ms, M.timers[T_LOOKUP].a, M.timers[T_LOOKUP].b));
-    M.stats.ms_lookup += ms;
-    CK(cudaEventElapsedTime(&ms, M.timers[T_CHAIN].a, M.timers[T_CHAIN].b));
-    M.stats.ms_chain += ms;
-    M.pendingStageTimes = false;
+    CK(cudaEventElapsedTime(&ms, W.timers[T_EXTRACT].a, W.timers[T_EXTRACT].b));
+    W.stats.ms_extract += ms;
+    CK(cudaEventElapsedTime(&ms, W.timers[T_LOOKUP].a, W.timers[T_LOOKUP].b));
+    W.stats.ms_lookup += ms;
+    CK(cudaEventElapsedTime(&ms, W.timers[T_CHAIN].a, W.timers[T_CHAIN].b));
+    W.stats.ms_chain += ms;
+    W.pendingStageTimes = false;
 }
 
 // Copies the window results of the last launch_windows() to the pinned host mirrors (hOutN, hOutOff, hOutMaps).
-void download_windows(dp_mapper& M, size_t nWin) {
-    cudaStream_t st = M.stream;
+void download_windows(Lane& W, size_t nWin) {
+    cudaStream_t st = W.stream;
     unsigned long long cur[4];
-    CK(cudaMemcpyAsync(cur, M.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
-    M.hOutN.reserve(nWin);
-    M.hOutOff.reserve(nWin);
-    CK(cudaMemcpyAsync(M.hOutN.p, M.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(M.hOutOff.p, M.outOff.p, nWin * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur, W.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    W.hOutN.reserve(nWin);
+    W.hOutOff.reserve(nWin);
+    CK(cudaMemcpyAsync(W.hOutN.p, W.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hOutOff.p, W.outOff.p, nWin * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    collect_stage_times(M);
+    collect_stage_times(W);
     size_t total = (size_t)cur[CUR_OUT];
-    M.hOutMaps.reserve(total + 1);
+    W.hOutMaps.reserve(total + 1);
     if (total) {
-        CK(cudaMemcpyAsync(M.hOutMaps.p, M.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(W.hOutMaps.p, W.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    M.hOutTotal = total;
+    W.hOutTotal = total;
 }
 
 // Host-supplied window list (rounds after the first, and the test probe).
-void run_windows(dp_mapper& M, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
+void run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
                  const int* dReadLen) {
     if (nWin == 0) return;
     size_t seedEntries = 0;
     for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
-    ensure_window_capacity(M, nWin, seedEntries);
-    CK(cudaMemcpyAsync(M.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, M.stream));
-    launch_windows(M, nWin, seedEntries, dWords, dWordOff, dReadLen);
-    download_windows(M, nWin);
+    ensure_window_capacity(M, W, nWin, seedEntries);
+    CK(cudaMemcpyAsync(W.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, W.stream));
+    launch_windows(M, W, nWin, seedEntries, dWords, dWordOff, dReadLen);
+    download_windows(W, nWin);
 }
 
-void reset_counters(dp_mapper& M) {
-    M.dCtr.reserve(1);
-    CK(cudaMemsetAsync(M.dCtr.p, 0, sizeof(DpCounters), M.stream));
+void reset_counters(Lane& W) {
+    W.dCtr.reserve(1);
+    CK(cudaMemsetAsync(W.dCtr.p, 0, sizeof(DpCounters), W.stream));
 }
 
-void fetch_counters(dp_mapper& M) {
+void fetch_counters(Lane& W) {
     DpCounters c;
-    CK(cudaMemcpy(&c, M.dCtr.p, sizeof(c), cudaMemcpyDeviceToHost));
-    M.stats.kmer_lookups += (int64_t)c.kmer_lookups;
-    M.stats.query_seeds += (int64_t)c.query_seeds;
-    M.stats.posting_runs += (int64_t)c.posting_runs;
-    M.stats.posting_entries += (int64_t)c.posting_entries;
-    M.stats.candidates += (int64_t)c.candidates;
-    M.stats.chain_cells += (int64_t)c.chain_cells;
+    CK(cudaMemcpy(&c, W.dCtr.p, sizeof(c), cudaMemcpyDeviceToHost));
+    W.stats.kmer_lookups += (int64_t)c.kmer_lookups;
+    W.stats.query_seeds += (int64_t)c.query_seeds;
+    W.stats.posting_runs += (int64_t)c.posting_runs;
+    W.stats.posting_entries += (int64_t)c.posting_entries;
+    W.stats.candidates += (int64_t)c.candidates;
+    W.stats.chain_cells += (int64_t)c.chain_cells;
     if (c.overflow) {
         std::string what = "device capacity exceeded:";
         if (c.overflow & 1) what += " mappings-per-window";
@@ -625,48 +632,70 @@ struct ReadCache {
     std::vector<dph::WinRef> wins;
 };
 
-// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device.
-void map_subbatch(dp_mapper& M, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
-                  std::vector<std::vector<dph::Hit>>& results) {
+// Output of one sub-batch: mappings grouped per read in input order.
+struct SubOut {
+    std::vector<dp_mapping> maps;
+};
+
+inline dp_mapping to_abi(const dph::Hit& h) {
+    dp_mapping m;
+    memset(&m, 0, sizeof(m));
+    m.start = h.start;
+    m.end = h.end;
+    m.q_offset = (int32_t)h.qOffset;
+    m.q_inset = (int32_t)h.qInset;
+    m.ids = (int32_t)h.ids;
+    m.rc = h.rc ? 1 : 0;
+    return m;
+}
+
+static_assert(sizeof(dp_mapping) == sizeof(DpMappingDev), "ABI record and device record share one layout");
+
+// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device. counts[r0..r1) and
+// `out` (ordered by read) receive the result.
+void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
+                  int* counts, SubOut& out) {
     const int64_t n = r1 - r0;
-    cudaStream_t st = M.stream;
+    cudaStream_t st = W.stream;
     const int k = M.k;
     const int e = M.edge;
     const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
     // ---- read tables on the device: lengths, packed-word offsets ----
     double t0 = now_ms();
-    M.hRel.reserve((size_t)n + 1);
+    W.hRel.reserve((size_t)n + 1);
     long long maxLen = 0;
-    for (int64_t i = 0; i <= n; i++) M.hRel.p[i] = offsets[r0 + i] - offsets[r0];
+    int64_t nWinReal = 0;
+    for (int64_t i = 0; i <= n; i++) W.hRel.p[i] = offsets[r0 + i] - offsets[r0];
     for (int64_t i = 0; i < n; i++) {
-        long long len = M.hRel.p[i + 1] - M.hRel.p[i];
+        long long len = W.hRel.p[i + 1] - W.hRel.p[i];
         if (len < 0) throw std::runtime_error("read offsets must be non-decreasing");
         maxLen = std::max(maxLen, len);
+        if (len >= minLen) nWinReal += (len <= 2ll * e) ? 1 : 2;
     }
     if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
-    const long long totalBytes = M.hRel.p[n];
+    const long long totalBytes = W.hRel.p[n];
     const size_t wordCap = (size_t)(totalBytes / 16 + 2 * n + 16);
-    M.dSeqOff.reserve((size_t)n + 1);
-    M.dWordsNeeded.reserve((size_t)n + 1);
-    M.dWordOff.reserve((size_t)n + 1);
-    M.dReadLen.reserve((size_t)n);
-    M.dWords.reserve(wordCap);
-    CK(cudaMemcpyAsync(M.dSeqOff.p, M.hRel.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    dp_read_table_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(M.dSeqOff.p, n, M.dReadLen.p, M.dWordsNeeded.p);
+    W.dSeqOff.reserve((size_t)n + 1);
+    W.dWordsNeeded.reserve((size_t)n + 1);
+    W.dWordOff.reserve((size_t)n + 1);
+    W.dReadLen.reserve((size_t)n);
+    W.dWords.reserve(wordCap);
+    CK(cudaMemcpyAsync(W.dSeqOff.p, W.hRel.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    dp_read_table_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(W.dSeqOff.p, n, W.dReadLen.p, W.dWordsNeeded.p);
     CK(cudaGetLastError());
     {
         size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, M.dWordsNeeded.p, M.dWordOff.p, (int)n + 1, st);
-        M.scanTmp.reserve(tmpBytes);
-        CK(cub::DeviceScan::ExclusiveSum(M.scanTmp.p, tmpBytes, M.dWordsNeeded.p, M.dWordOff.p, (int)n + 1, st));
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, W.dWordsNeeded.p, W.dWordOff.p, (int)n + 1, st);
+        W.scanTmp.reserve(tmpBytes);
+        CK(cub::DeviceScan::ExclusiveSum(W.scanTmp.p, tmpBytes, W.dWordsNeeded.p, W.dWordOff.p, (int)n + 1, st));
     }
     {
         int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)M.smCount * 16);
-        CK(cudaEventRecord(M.timers[T_PACK].a, st));
-        dp_pack_kernel<<<blocks, 256, 0, st>>>(dAscii, M.dSeqOff.p, M.dWordOff.p, M.dWords.p, n);
+        CK(cudaEventRecord(W.timers[T_PACK].a, st));
+        dp_pack_kernel<<<blocks, 256, 0, st>>>(dAscii, W.dSeqOff.p, W.dWordOff.p, W.dWords.p, n);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(M.timers[T_PACK].b, st));
-        M.stats.kernel_launches += 3;
+        CK(cudaEventRecord(W.timers[T_PACK].b, st));
+        W.stats.kernel_launches += 3;
     }
     // ---- round 0 entirely on the device: windows, performMapping stages, Map()'s first decision ----
     const size_t nWin0 = 2 * (size_t)n;
@@ -677,190 +706,316 @@ void map_subbatch(dp_mapper& M, const unsigned char* dAscii, const int64_t* offs
         seedEntries0 = (size_t)perRead * (size_t)n;
         if (seedEntries0 >= 0xffffffffull) throw std::runtime_error("sub-batch too large");
     }
-    ensure_window_capacity(M, nWin0, seedEntries0);
-    dp_round0_windows_kernel<<<div_up(n, 256), 256, 0, st>>>(M.dReadLen.p, n, e, minLen, M.dWins.p);
+    ensure_window_capacity(M, W, nWin0, seedEntries0);
+    dp_round0_windows_kernel<<<div_up(n, 256), 256, 0, st>>>(W.dReadLen.p, n, e, minLen, W.dWins.p);
     CK(cudaGetLastError());
-    launch_windows(M, nWin0, seedEntries0, M.dWords.p, M.dWordOff.p, M.dReadLen.p);
-    M.dStatus.reserve((size_t)n);
-    M.dFinN.reserve((size_t)n);
-    M.dFinOff.reserve((size_t)n);
-    M.dFinMaps.reserve((size_t)n * 4 + 64);
-    CK(cudaEventRecord(M.timers[T_FINISH].a, st));
-    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, M.dReadLen.p, n, minLen, M.outN.p, M.outOff.p,
-                                                            M.outMaps.p, M.dStatus.p, M.dFinN.p, M.dFinOff.p,
-                                                            M.dFinMaps.p, M.cursor.p + CUR_FIN,
-                                                            (unsigned long long)M.dFinMaps.cap);
+    launch_windows(M, W, nWin0, seedEntries0, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+    W.stats.windows += nWinReal - (int64_t)nWin0;  // empty second slots of short reads are not window queries
+    W.dStatus.reserve((size_t)n);
+    W.dFinN.reserve((size_t)n);
+    W.dFinOff.reserve((size_t)n);
+    W.dFinMaps.reserve((size_t)n * 4 + 64);
+    CK(cudaEventRecord(W.timers[T_FINISH].a, st));
+    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
+                                                            W.outMaps.p, W.dStatus.p, W.dFinN.p, W.dFinOff.p,
+                                                            W.dFinMaps.p, W.cursor.p + CUR_FIN,
+                                                            (unsigned long long)W.dFinMaps.cap);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(M.timers[T_FINISH].b, st));
-    M.stats.kernel_launches += 2;
-    M.hStatus.reserve((size_t)n);
-    M.hFinN.reserve((size_t)n);
-    M.hFinOff.reserve((size_t)n);
+    CK(cudaEventRecord(W.timers[T_FINISH].b, st));
+    W.stats.kernel_launches += 2;
+    W.hStatus.reserve((size_t)n);
+    W.hFinN.reserve((size_t)n);
+    W.hFinOff.reserve((size_t)n);
     unsigned long long cur[4];
-    CK(cudaMemcpyAsync(M.hStatus.p, M.dStatus.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(M.hFinN.p, M.dFinN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(M.hFinOff.p, M.dFinOff.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cur, M.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
-    M.stats.ms_host_logic += now_ms() - t0;
+    CK(cudaMemcpyAsync(W.hStatus.p, W.dStatus.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hFinN.p, W.dFinN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hFinOff.p, W.dFinOff.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur, W.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    W.stats.ms_host_logic += now_ms() - t0;
     CK(cudaStreamSynchronize(st));
-    collect_stage_times(M);
+    collect_stage_times(W);
     {
         float ms;
-        CK(cudaEventElapsedTime(&ms, M.timers[T_PACK].a, M.timers[T_PACK].b));
-        M.stats.ms_pack += ms;
-        CK(cudaEventElapsedTime(&ms, M.timers[T_FINISH].a, M.timers[T_FINISH].b));
-        M.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
+        CK(cudaEventElapsedTime(&ms, W.timers[T_PACK].a, W.timers[T_PACK].b));
+        W.stats.ms_pack += ms;
+        CK(cudaEventElapsedTime(&ms, W.timers[T_FINISH].a, W.timers[T_FINISH].b));
+        W.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
     }
-    const size_t finTotal = (size_t)std::min<unsigned long long>(cur[CUR_FIN], (unsigned long long)M.dFinMaps.cap);
-    M.hFinMaps.reserve(finTotal + 1);
+    const size_t finTotal = (size_t)std::min<unsigned long long>(cur[CUR_FIN], (unsigned long long)W.dFinMaps.cap);
+    W.hFinMaps.reserve(finTotal + 1);
     if (finTotal)
-        CK(cudaMemcpyAsync(M.hFinMaps.p, M.dFinMaps.p, finTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, finTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     t0 = now_ms();
     std::vector<int> active;
-    for (int64_t i = 0; i < n; i++) {
-        std::vector<dph::Hit>& out = results[(size_t)(r0 + i)];
-        out.clear();
-        if (M.hStatus.p[i] == DP_READ_DONE) {
-            int cnt = M.hFinN.p[i];
-            const DpMappingDev* src = M.hFinMaps.p + M.hFinOff.p[i];
-            for (int j = 0; j < cnt; j++) {
-                dph::Hit h;
-                h.start = src[j].start;
-                h.end = src[j].end;
-                h.qOffset = src[j].qOffset;
-                h.qInset = src[j].qInset;
-                h.ids = src[j].ids;
-                h.rc = (src[j].rc & 0xff) != 0;
-                out.push_back(h);
-            }
-        } else {
-            active.push_back((int)i);
-        }
-    }
-    M.stats.ms_host_logic += now_ms() - t0;
-    if (active.empty()) return;
+    for (int64_t i = 0; i < n; i++)
+        if (W.hStatus.p[i] != DP_READ_DONE) active.push_back((int)i);
+    W.stats.ms_host_logic += now_ms() - t0;
 
     // ---- unresolved reads: replay Map() on the host against cached window results, round by round ----
-    t0 = now_ms();
-    download_windows(M, nWin0);
-    std::vector<ReadCache> cache(active.size());
-    std::vector<int> slotOf;  // read index -> slot in `cache`
-    slotOf.assign((size_t)n, -1);
-    std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
-    {
-        roundMaps.emplace_back();
-        std::vector<DpMappingDev>& keep = roundMaps.back();
-        size_t total = 0;
-        for (int i : active) total += (size_t)M.hOutN.p[2 * i] + (size_t)M.hOutN.p[2 * i + 1];
-        keep.resize(total + 1);
-        size_t pos = 0;
-        for (size_t a = 0; a < active.size(); a++) {
-            int i = active[a];
-            slotOf[(size_t)i] = (int)a;
-            long long len = M.hRel.p[i + 1] - M.hRel.p[i];
-            for (int s = 0; s < 2; s++) {
-                size_t wI = 2 * (size_t)i + s;
-                dph::WinRef ref;
-                if (len <= 2ll * e) {
-                    if (s == 1) continue;
-                    ref.start = 0;
-                    ref.len = (int)len;
-                    ref.whole = 1;
-                } else {
-                    ref.start = s == 0 ? 0 : (int)(len - e);
-                    ref.len = e;
-                    ref.whole = 0;
+    std::vector<std::vector<dph::Hit>> late(active.size());
+    std::vector<int> slotOf;  // read index -> slot in `cache` / `late`
+    if (!active.empty()) {
+        t0 = now_ms();
+        download_windows(W, nWin0);
+        std::vector<ReadCache> cache(active.size());
+        slotOf.assign((size_t)n, -1);
+        std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
+        {
+            roundMaps.emplace_back();
+            std::vector<DpMappingDev>& keep = roundMaps.back();
+            size_t total = 0;
+            for (int i : active) total += (size_t)W.hOutN.p[2 * i] + (size_t)W.hOutN.p[2 * i + 1];
+            keep.resize(total + 1);
+            size_t pos = 0;
+            for (size_t a = 0; a < active.size(); a++) {
+                int i = active[a];
+                slotOf[(size_t)i] = (int)a;
+                long long len = W.hRel.p[i + 1] - W.hRel.p[i];
+                for (int s = 0; s < 2; s++) {
+                    size_t wI = 2 * (size_t)i + s;
+                    dph::WinRef ref;
+                    if (len <= 2ll * e) {
+                        if (s == 1) continue;
+                        ref.start = 0;
+                        ref.len = (int)len;
+                        ref.whole = 1;
+                    } else {
+                        ref.start = s == 0 ? 0 : (int)(len - e);
+                        ref.len = e;
+                        ref.whole = 0;
+                    }
+                    int cnt = W.hOutN.p[wI];
+                    memcpy(keep.data() + pos, W.hOutMaps.p + W.hOutOff.p[wI], (size_t)cnt * sizeof(DpMappingDev));
+                    ref.n = cnt;
+                    ref.maps = keep.data() + pos;
+                    cache[a].wins.push_back(ref);
+                    pos += (size_t)cnt;
                 }
-                int cnt = M.hOutN.p[wI];
-                memcpy(keep.data() + pos, M.hOutMaps.p + M.hOutOff.p[wI], (size_t)cnt * sizeof(DpMappingDev));
-                ref.n = cnt;
-                ref.maps = keep.data() + pos;
-                cache[a].wins.push_back(ref);
-                pos += (size_t)cnt;
             }
         }
-    }
-    dph::Params P;
-    P.refLen = M.refLen;
-    P.edge = e;
-    P.circular = M.circular != 0;
-    dph::ReadMapper rm(P);
-    M.stats.ms_host_logic += now_ms() - t0;
-    while (!active.empty()) {
-        t0 = now_ms();
-        std::vector<DpWindow> wins;
-        std::vector<int> next;
-        for (int i : active) {
-            const ReadCache& rc = cache[(size_t)slotOf[(size_t)i]];
-            long long len = M.hRel.p[i + 1] - M.hRel.p[i];
-            bool done = rm.run(i, len, rc.wins.data(), (int)rc.wins.size(), wins, results[(size_t)(r0 + i)]);
-            if (!done) next.push_back(i);
+        dph::Params P;
+        P.refLen = M.refLen;
+        P.edge = e;
+        P.circular = M.circular != 0;
+        dph::ReadMapper rm(P);
+        W.stats.ms_host_logic += now_ms() - t0;
+        std::vector<int> todo = active;
+        while (!todo.empty()) {
+            t0 = now_ms();
+            std::vector<DpWindow> wins;
+            std::vector<int> next;
+            for (int i : todo) {
+                int slot = slotOf[(size_t)i];
+                const ReadCache& rc = cache[(size_t)slot];
+                long long len = W.hRel.p[i + 1] - W.hRel.p[i];
+                bool done = rm.run(i, len, rc.wins.data(), (int)rc.wins.size(), wins, late[(size_t)slot]);
+                if (!done) next.push_back(i);
+            }
+            W.stats.ms_host_logic += now_ms() - t0;
+            if (wins.empty()) break;
+            run_windows(M, W, wins.data(), wins.size(), W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+            t0 = now_ms();
+            roundMaps.emplace_back();
+            std::vector<DpMappingDev>& keep = roundMaps.back();
+            keep.assign(W.hOutMaps.p, W.hOutMaps.p + W.hOutTotal);
+            keep.resize(W.hOutTotal + 1);
+            for (size_t wI = 0; wI < wins.size(); wI++) {
+                dph::WinRef ref;
+                ref.start = wins[wI].start;
+                ref.len = wins[wI].len;
+                ref.whole = wins[wI].whole;
+                ref.n = W.hOutN.p[wI];
+                ref.maps = keep.data() + W.hOutOff.p[wI];
+                cache[(size_t)slotOf[(size_t)wins[wI].read]].wins.push_back(ref);
+            }
+            todo.swap(next);
+            W.stats.ms_host_logic += now_ms() - t0;
         }
-        M.stats.ms_host_logic += now_ms() - t0;
-        if (wins.empty()) break;
-        run_windows(M, wins.data(), wins.size(), M.dWords.p, M.dWordOff.p, M.dReadLen.p);
-        t0 = now_ms();
-        roundMaps.emplace_back();
-        std::vector<DpMappingDev>& keep = roundMaps.back();
-        keep.assign(M.hOutMaps.p, M.hOutMaps.p + M.hOutTotal);
-        keep.resize(M.hOutTotal + 1);
-        for (size_t wI = 0; wI < wins.size(); wI++) {
-            dph::WinRef ref;
-            ref.start = wins[wI].start;
-            ref.len = wins[wI].len;
-            ref.whole = wins[wI].whole;
-            ref.n = M.hOutN.p[wI];
-            ref.maps = keep.data() + M.hOutOff.p[wI];
-            cache[(size_t)slotOf[(size_t)wins[wI].read]].wins.push_back(ref);
-        }
-        active.swap(next);
-        M.stats.ms_host_logic += now_ms() - t0;
     }
+    // ---- assemble the sub-batch output in read order ----
+    t0 = now_ms();
+    size_t total = finTotal;
+    for (auto& v : late) total += v.size();
+    out.maps.resize(total);
+    size_t pos = 0;
+    const dp_mapping* fin = reinterpret_cast<const dp_mapping*>(W.hFinMaps.p);
+    for (int64_t i = 0; i < n; i++) {
+        if (W.hStatus.p[i] == DP_READ_DONE) {
+            int cnt = W.hFinN.p[i];
+            counts[r0 + i] = cnt;
+            if (cnt == 1) out.maps[pos] = fin[W.hFinOff.p[i]];
+            else if (cnt > 1) memcpy(out.maps.data() + pos, fin + W.hFinOff.p[i], (size_t)cnt * sizeof(dp_mapping));
+            pos += (size_t)cnt;
+        } else {
+            const std::vector<dph::Hit>& v = late[(size_t)slotOf[(size_t)i]];
+            counts[r0 + i] = (int)v.size();
+            for (const dph::Hit& h : v) out.maps[pos++] = to_abi(h);
+        }
+    }
+    out.maps.resize(pos);
+    W.stats.ms_host_logic += now_ms() - t0;
 }
 
-void begin_stats(dp_mapper& M, int64_t n_reads, const int64_t* offsets) {
+void add_stats(dp_stats& a, const dp_stats& b) {
+    a.ms_pack += b.ms_pack;
+    a.ms_extract += b.ms_extract;
+    a.ms_lookup += b.ms_lookup;
+    a.ms_chain += b.ms_chain;
+    a.ms_host_logic += b.ms_host_logic;
+    a.ms_h2d += b.ms_h2d;
+    a.rounds += b.rounds;
+    a.windows += b.windows;
+    a.kmer_lookups += b.kmer_lookups;
+    a.query_seeds += b.query_seeds;
+    a.posting_runs += b.posting_runs;
+    a.posting_entries += b.posting_entries;
+    a.candidates += b.candidates;
+    a.chain_cells += b.chain_cells;
+    a.mappings += b.mappings;
+    a.kernel_launches += b.kernel_launches;
+}
+
+Lane& get_lane(dp_mapper& M, size_t idx) {
+    while (M.lanes.size() <= idx) {
+        std::unique_ptr<Lane> L(new Lane());
+        CK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+        L->timers.resize(T_N);
+        for (auto& t : L->timers) t.init();
+        M.lanes.push_back(std::move(L));
+    }
+    return *M.lanes[idx];
+}
+
+const int64_t kSubBatchReads = 1 << 16;
+const int64_t kSubBatchBytes = 1ll << 30;
+
+int lane_count() {
+    const char* env = getenv("DP_LANES");
+    int v = env ? atoi(env) : 2;
+    return std::max(1, std::min(v, 4));
+}
+
+// Copies reads [r0,r1) to the lane's device buffer. Pinned (or registered) caller memory is copied directly;
+// pageable memory goes through the lane's pinned staging buffer in two alternating pieces.
+void upload_ascii(Lane& W, const uint8_t* bases, const int64_t* offsets, int64_t r0, int64_t r1, bool pinned) {
+    size_t nbytes = (size_t)(offsets[r1] - offsets[r0]);
+    W.dAscii.reserve(nbytes + 64);
+    double t0 = now_ms();
+    if (pinned) {
+        CK(cudaMemcpyAsync(W.dAscii.p, bases + offsets[r0], nbytes, cudaMemcpyHostToDevice, W.stream));
+    } else {
+        const size_t piece = 16u << 20;
+        W.hStage.reserve(2 * piece);
+        cudaEvent_t ev[2];
+        CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        int slot = 0;
+        for (size_t o = 0; o < nbytes; o += piece, slot ^= 1) {
+            size_t len = std::min(piece, nbytes - o);
+            if (o >= 2 * piece) CK(cudaEventSynchronize(ev[slot]));
+            memcpy(W.hStage.p + (size_t)slot * piece, bases + offsets[r0] + o, len);
+            CK(cudaMemcpyAsync(W.dAscii.p + o, W.hStage.p + (size_t)slot * piece, len, cudaMemcpyHostToDevice,
+                               W.stream));
+            CK(cudaEventRecord(ev[slot], W.stream));
+        }
+        CK(cudaStreamSynchronize(W.stream));
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    }
+    CK(cudaStreamSynchronize(W.stream));
+    W.stats.ms_h2d += now_ms() - t0;
+}
+
+// Shared driver of the two batch entry points. `hostBases` xor `devBases` is set.
+void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, const uint8_t* devBases,
+                    const int64_t* offsets, dp_mapping** out, int64_t** out_offsets) {
+    CK(cudaSetDevice(M.device));
+    double tStart = now_ms();
+    // sub-batch boundaries
+    std::vector<int64_t> cuts;
+    cuts.push_back(0);
+    for (int64_t r0 = 0; r0 < n_reads;) {
+        int64_t r1 = r0;
+        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
+        if (r1 == r0) r1 = r0 + 1;
+        cuts.push_back(r1);
+        r0 = r1;
+    }
+    const size_t nSub = cuts.size() - 1;
+    const int nLanes = (int)std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1));
+    bool pinned = false;
+    if (hostBases) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, hostBases) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
+    for (int l = 0; l < nLanes; l++) {
+        Lane& W = get_lane(M, (size_t)l);
+        memset(&W.stats, 0, sizeof(W.stats));
+        reset_counters(W);
+    }
+    std::vector<int> counts((size_t)n_reads + 1, 0);
+    std::vector<SubOut> subs(nSub);
+    std::atomic<size_t> nextSub(0);
+    std::vector<std::string> errs((size_t)nLanes);
+    auto work = [&](int l) {
+        try {
+            CK(cudaSetDevice(M.device));
+            Lane& W = *M.lanes[(size_t)l];
+            for (;;) {
+                size_t sI = nextSub.fetch_add(1);
+                if (sI >= nSub) break;
+                int64_t r0 = cuts[sI], r1 = cuts[sI + 1];
+                const unsigned char* dA;
+                if (hostBases) {
+                    upload_ascii(W, hostBases, offsets, r0, r1, pinned);
+                    dA = W.dAscii.p;
+                } else {
+                    dA = devBases + offsets[r0];
+                }
+                map_subbatch(M, W, dA, offsets, r0, r1, counts.data(), subs[sI]);
+            }
+            CK(cudaStreamSynchronize(W.stream));
+            fetch_counters(W);
+        } catch (const std::exception& ex) {
+            errs[(size_t)l] = ex.what();
+            if (errs[(size_t)l].empty()) errs[(size_t)l] = "unknown error";
+        }
+    };
+    std::vector<std::thread> th;
+    for (int l = 1; l < nLanes; l++) th.emplace_back(work, l);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    // ---- concatenate ----
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_reads + 1));
+    int64_t total = 0;
+    for (int64_t i = 0; i < n_reads; i++) {
+        off[i] = total;
+        total += counts[(size_t)i];
+    }
+    off[n_reads] = total;
+    dp_mapping* maps = (dp_mapping*)malloc(sizeof(dp_mapping) * (size_t)(total ? total : 1));
+    size_t pos = 0;
+    for (size_t sI = 0; sI < nSub; sI++) {
+        if (!subs[sI].maps.empty()) memcpy(maps + pos, subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
+        pos += subs[sI].maps.size();
+    }
+    if ((int64_t)pos != total) {
+        free(maps);
+        free(off);
+        throw std::runtime_error("internal error: result assembly mismatch");
+    }
     memset(&M.stats, 0, sizeof(M.stats));
+    for (int l = 0; l < nLanes; l++) add_stats(M.stats, M.lanes[(size_t)l]->stats);
     M.stats.bases = offsets[n_reads] - offsets[0];
-    if (M.timers.empty()) {
-        M.timers.resize(T_N);
-        for (auto& t : M.timers) t.init();
-    }
-    reset_counters(M);
-}
-
-void emit_results(const std::vector<std::vector<dph::Hit>>& results, dp_mapping** out, int64_t** out_offsets,
-                  dp_stats& stats) {
-    size_t n = results.size();
-    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (n + 1));
-    size_t total = 0;
-    for (size_t i = 0; i < n; i++) {
-        off[i] = (int64_t)total;
-        total += results[i].size();
-    }
-    off[n] = (int64_t)total;
-    dp_mapping* maps = (dp_mapping*)malloc(sizeof(dp_mapping) * (total ? total : 1));
-    size_t p = 0;
-    for (size_t i = 0; i < n; i++) {
-        for (const dph::Hit& h : results[i]) {
-            dp_mapping m;
-            memset(&m, 0, sizeof(m));
-            m.start = h.start;
-            m.end = h.end;
-            m.q_offset = (int32_t)h.qOffset;
-            m.q_inset = (int32_t)h.qInset;
-            m.ids = (int32_t)h.ids;
-            m.rc = h.rc ? 1 : 0;
-            maps[p++] = m;
-        }
-    }
-    stats.mappings = (int64_t)total;
+    M.stats.mappings = total;
+    M.stats.ms_total = now_ms() - tStart;
     *out = maps;
     *out_offsets = off;
 }
-
-const int64_t kSubBatchReads = 1 << 17;
-const int64_t kSubBatchBytes = 1ll << 30;
 
 }  // namespace
 
@@ -920,30 +1075,9 @@ void dp_mapper_destroy(dp_mapper* m) {
 int dp_mapper_map_batch_device(dp_mapper* m, int64_t n_reads, const uint8_t* d_bases, const int64_t* offsets,
                                dp_mapping** out, int64_t** out_offsets) {
     API_TRY
-    if (!m || !offsets || !out || !out_offsets || n_reads < 0) throw std::runtime_error("bad argument");
-    CK(cudaSetDevice(m->device));
-    begin_stats(*m, n_reads, offsets);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, m->stream));
-    std::vector<std::vector<dph::Hit>> results((size_t)n_reads);
-    for (int64_t r0 = 0; r0 < n_reads;) {
-        int64_t r1 = r0;
-        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
-        if (r1 == r0) r1 = r0 + 1;
-        map_subbatch(*m, d_bases + offsets[r0], offsets, r0, r1, results);
-        r0 = r1;
-    }
-    CK(cudaEventRecord(e1, m->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    m->stats.ms_total = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    fetch_counters(*m);
-    emit_results(results, out, out_offsets, m->stats);
+    if (!m || !offsets || !out || !out_offsets || n_reads < 0 || (!d_bases && n_reads > 0))
+        throw std::runtime_error("bad argument");
+    map_batch_impl(*m, n_reads, nullptr, d_bases, offsets, out, out_offsets);
     API_CATCH
 }
 
@@ -952,60 +1086,7 @@ int dp_mapper_map_batch(dp_mapper* m, int64_t n_reads, const uint8_t* bases, con
     API_TRY
     if (!m || !offsets || !out || !out_offsets || n_reads < 0 || (!bases && n_reads > 0))
         throw std::runtime_error("bad argument");
-    CK(cudaSetDevice(m->device));
-    begin_stats(*m, n_reads, offsets);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, m->stream));
-    // pinned (or registered) caller memory is copied directly; pageable memory goes through a pinned staging buffer
-    cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    std::vector<std::vector<dph::Hit>> results((size_t)n_reads);
-    for (int64_t r0 = 0; r0 < n_reads;) {
-        int64_t r1 = r0;
-        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
-        if (r1 == r0) r1 = r0 + 1;
-        size_t nbytes = (size_t)(offsets[r1] - offsets[r0]);
-        m->dAscii.reserve(nbytes + 64);
-        double t0 = now_ms();
-        if (pinned) {
-            CK(cudaMemcpyAsync(m->dAscii.p, bases + offsets[r0], nbytes, cudaMemcpyHostToDevice, m->stream));
-        } else {
-            const size_t piece = 32u << 20;
-            m->hStage.reserve(2 * piece);
-            cudaEvent_t ev[2];
-            CK(cudaEventCreate(&ev[0]));
-            CK(cudaEventCreate(&ev[1]));
-            int slot = 0;
-            for (size_t o = 0; o < nbytes; o += piece, slot ^= 1) {
-                size_t len = std::min(piece, nbytes - o);
-                if (o >= 2 * piece) CK(cudaEventSynchronize(ev[slot]));
-                memcpy(m->hStage.p + (size_t)slot * piece, bases + offsets[r0] + o, len);
-                CK(cudaMemcpyAsync(m->dAscii.p + o, m->hStage.p + (size_t)slot * piece, len, cudaMemcpyHostToDevice,
-                                   m->stream));
-                CK(cudaEventRecord(ev[slot], m->stream));
-            }
-            CK(cudaStreamSynchronize(m->stream));
-            cudaEventDestroy(ev[0]);
-            cudaEventDestroy(ev[1]);
-        }
-        CK(cudaStreamSynchronize(m->stream));
-        m->stats.ms_h2d += now_ms() - t0;
-        map_subbatch(*m, m->dAscii.p, offsets, r0, r1, results);
-        r0 = r1;
-    }
-    CK(cudaEventRecord(e1, m->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    m->stats.ms_total = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    fetch_counters(*m);
-    emit_results(results, out, out_offsets, m->stats);
+    map_batch_impl(*m, n_reads, bases, nullptr, offsets, out, out_offsets);
     API_CATCH
 }
 
@@ -1089,34 +1170,36 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     }
     if (start < 0 || end > read_len || end - start < m->k + 12 || end - start > 2 * m->edge)
         throw std::runtime_error("bad probe window");
-    begin_stats(*m, 0, &start);
-    cudaStream_t st = m->stream;
-    m->dAscii.reserve((size_t)read_len + 64);
-    CK(cudaMemcpyAsync(m->dAscii.p, read_ascii, (size_t)read_len, cudaMemcpyHostToDevice, st));
+    Lane& W = get_lane(*m, 0);
+    memset(&W.stats, 0, sizeof(W.stats));
+    reset_counters(W);
+    cudaStream_t st = W.stream;
+    W.dAscii.reserve((size_t)read_len + 64);
+    CK(cudaMemcpyAsync(W.dAscii.p, read_ascii, (size_t)read_len, cudaMemcpyHostToDevice, st));
     long long seqOff[2] = {0, read_len};
     long long wordOff[1] = {0};
     int rl[1] = {(int)read_len};
-    m->dSeqOff.reserve(2);
-    m->dWordOff.reserve(1);
-    m->dReadLen.reserve(1);
-    m->dWords.reserve((size_t)read_len / 16 + 8);
-    CK(cudaMemcpyAsync(m->dSeqOff.p, seqOff, sizeof(seqOff), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m->dWordOff.p, wordOff, sizeof(wordOff), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m->dReadLen.p, rl, sizeof(rl), cudaMemcpyHostToDevice, st));
-    dp_pack_kernel<<<1, 256, 0, st>>>(m->dAscii.p, m->dSeqOff.p, m->dWordOff.p, m->dWords.p, 1);
+    W.dSeqOff.reserve(2);
+    W.dWordOff.reserve(1);
+    W.dReadLen.reserve(1);
+    W.dWords.reserve((size_t)read_len / 16 + 8);
+    CK(cudaMemcpyAsync(W.dSeqOff.p, seqOff, sizeof(seqOff), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(W.dWordOff.p, wordOff, sizeof(wordOff), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(W.dReadLen.p, rl, sizeof(rl), cudaMemcpyHostToDevice, st));
+    dp_pack_kernel<<<1, 256, 0, st>>>(W.dAscii.p, W.dSeqOff.p, W.dWordOff.p, W.dWords.p, 1);
     CK(cudaGetLastError());
     DpWindow w;
     w.read = 0;
     w.start = (int)start;
     w.len = (int)(end - start);
     w.whole = whole ? 1 : 0;
-    run_windows(*m, &w, 1, m->dWords.p, m->dWordOff.p, m->dReadLen.p);
-    fetch_counters(*m);
+    run_windows(*m, W, &w, 1, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+    fetch_counters(W);
     // seeds
     unsigned wsOff[2];
     int wsN[2];
-    CK(cudaMemcpy(wsOff, m->wsOff.p, sizeof(wsOff), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(wsN, m->wsN.p, sizeof(wsN), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(wsOff, W.wsOff.p, sizeof(wsOff), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(wsN, W.wsN.p, sizeof(wsN), cudaMemcpyDeviceToHost));
     if (n_seeds2) {
         n_seeds2[0] = wsN[0];
         n_seeds2[1] = wsN[1];
@@ -1129,8 +1212,8 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
         std::vector<unsigned> r((size_t)tot + 1);
         std::vector<int> p((size_t)tot + 1);
         // strand 0 then strand 1 (they are adjacent in the compact buffer)
-        CK(cudaMemcpy(r.data(), m->qSeed.p + wsOff[0], (size_t)tot * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(p.data(), m->qPos.p + wsOff[0], (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(r.data(), W.qSeed.p + wsOff[0], (size_t)tot * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(p.data(), W.qPos.p + wsOff[0], (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost));
         for (int i = 0; i < tot; i++) {
             if (seed_pos) seed_pos[i] = p[(size_t)i];
             if (seed_kmer) seed_kmer[i] = seeds[r[(size_t)i]];
@@ -1138,7 +1221,7 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     }
     if (n_cand2 || cand) {
         int cn[2];
-        CK(cudaMemcpy(cn, m->candN.p, sizeof(cn), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cn, W.candN.p, sizeof(cn), cudaMemcpyDeviceToHost));
         if (n_cand2) {
             n_cand2[0] = cn[0];
             n_cand2[1] = cn[1];
@@ -1146,19 +1229,19 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
         if (cand) {
             if (cn[0] + cn[1] > cand_cap) throw std::runtime_error("cand_cap too small");
             std::vector<unsigned> c0((size_t)cn[0] + 1), c1((size_t)cn[1] + 1);
-            CK(cudaMemcpy(c0.data(), m->candChunk.p, (size_t)cn[0] * sizeof(unsigned), cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(c1.data(), m->candChunk.p + m->candStride, (size_t)cn[1] * sizeof(unsigned),
+            CK(cudaMemcpy(c0.data(), W.candChunk.p, (size_t)cn[0] * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(c1.data(), W.candChunk.p + W.candStride, (size_t)cn[1] * sizeof(unsigned),
                           cudaMemcpyDeviceToHost));
             for (int i = 0; i < cn[0]; i++) cand[i] = (int32_t)c0[(size_t)i];
             for (int i = 0; i < cn[1]; i++) cand[cn[0] + i] = (int32_t)c1[(size_t)i];
         }
     }
-    if (n_map) *n_map = m->hOutN.p[0];
+    if (n_map) *n_map = W.hOutN.p[0];
     if (maps) {
-        int cnt = m->hOutN.p[0];
+        int cnt = W.hOutN.p[0];
         if (cnt > map_cap) throw std::runtime_error("map_cap too small");
         for (int i = 0; i < cnt; i++) {
-            const DpMappingDev& d = m->hOutMaps.p[m->hOutOff.p[0] + i];
+            const DpMappingDev& d = W.hOutMaps.p[W.hOutOff.p[0] + i];
             dp_mapping o;
             memset(&o, 0, sizeof(o));
             o.start = d.start;
