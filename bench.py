@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — `downpore map` hot path on B200 (BASELINE.json metric: mapped Gbp/s, device-timed, + roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU port of the reference (oracle)
+
+A "step" = one pass of the hot path (pack -> seed extract -> index lookup -> chain -> Map() pairing) over one batch of
+synthetic reads. Workload at every N: BASELINE config 2 per GPU — a 4.6 Mb uniform circular reference and
+`--reads` (default 1M) simulated 10 kb ONT-like reads (4 % sub / 3 % ins / 3 % del) PER GPU (weak scaling: reads are
+sharded, the index is rebuilt identically on every GPU, no data-path collective).
+  value : whole-job Gbp/s (all submitted bases of all ranks / max-over-ranks time) with the ASCII reads already
+          resident in HBM (dp_mapper_map_batch_device);
+  e2e   : the same through dp_mapper_map_batch with pinned HOST buffers, H2D copies and the D2H of the mapping
+          records inside the timed region.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 11
+REF_LEN = 4_600_000
+READ_LEN = 10_000
+REF_SEED, READ_SEED = 1, 12
+EDGE = 1000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous shard [lo, hi) of n_total read indices for `rank` (reads are independent)."""
+    lo = n_total * rank // world
+    hi = n_total * (rank + 1) // world
+    return lo, hi
+
+
+def config_dict(args, world):
+    return {"workload": "BASELINE config 2: synthetic 4.6 Mb circular reference, %d simulated 10 kb ONT-like reads "
+                        "(4%% sub, 3%% ins, 3%% del) per GPU" % args.reads,
+            "reads_per_gpu": args.reads, "read_len": READ_LEN, "ref_len": REF_LEN, "k": K, "seed_rate": 40,
+            "query_size": EDGE, "chunk_size": 10000, "circular": True,
+            "parallelism": "reads sharded over %d GPU(s), index replicated (rebuilt per GPU), no data-path collective" % world,
+            "l2_policy": "inputs larger than L2 (%.1f GB ASCII per GPU per step; every step streams all of it)" % (
+                args.reads * READ_LEN / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the CPU port of the reference's map path (oracle/), all host threads, bounded sample.
+    Under torchrun only rank 0 works; the other ranks exit without joining a process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    from tools import synth
+    cores = os.cpu_count() or 1
+    ref = synth.reference(REF_SEED, REF_LEN)
+    vals = po.kmer_values(ref, K)
+    om = po.Mapper(ref, vals, circular=True)
+    n = args.ref_sample
+    rd = synth.reads(ref, READ_SEED, n, READ_LEN)
+    offs = np.arange(n + 1, dtype=np.int64) * READ_LEN
+    for _ in range(min(args.warmup, 1)):
+        om.map_batch(rd[: 2000 * READ_LEN], offs[:2001], threads=cores)
+    t0 = time.time()
+    for _ in range(args.steps):
+        om.map_batch(rd, offs, threads=cores)
+    dt = (time.time() - t0) / args.steps
+    gbps = n * READ_LEN / dt / 1e9
+    sample = "%d of the workload's reads per step (read set seed %d, indices 0..%d)" % (n, READ_SEED, n - 1)
+    line = {"impl": "reference", "metric": "mapped Gbp/s", "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": config_dict(args, max(world, 1)),
+            "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of the reference (no Go toolchain in this image), mapping phase only"},
+            "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import downpore_b200 as dp
+    from tools import synth
+
+    ref = synth.reference(REF_SEED, REF_LEN)
+    t_c0 = time.time()
+    counts = dp.kmer_counts(ref, K, device=local)
+    vals = dp.kmer_values(counts, K)
+    t1 = time.time()
+    t_counts = t1 - t_c0
+    gm = dp.Mapper(ref, vals, circular=True, device=local)
+    torch.cuda.synchronize()
+    t_index = time.time() - t1
+    info = gm.index_info()
+
+    n = args.reads
+    first = rank * n  # weak scaling: every rank maps its own n reads of the same read set
+    pinned = torch.empty(n * READ_LEN, dtype=torch.uint8).pin_memory()
+    host = pinned.numpy()
+    synth.reads(ref, READ_SEED, n, READ_LEN, first_index=first, out=host)
+    offs = np.arange(n + 1, dtype=np.int64) * READ_LEN
+    d_reads = pinned.to(dev, non_blocking=False)
+    torch.cuda.synchronize()
+    bases_rank = n * READ_LEN
+
+    def step_device():
+        return gm.map_batch_device(d_reads.data_ptr(), offs)
+
+    def step_host():
+        return gm.map_batch_ptr(pinned.data_ptr(), offs)
+
+    # ---- device-resident: `value` ----
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    agg = None
+    barrier(world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    t0 = time.time()
+    for _ in range(args.steps):
+        maps, off = step_device()
+        st = gm.stats()
+        if agg is None:
+            agg = {k: 0 for k in st}
+        for k2, v in st.items():
+            agg[k2] += v
+    torch.cuda.synchronize()
+    barrier(world)
+    dt_dev = time.time() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    dt_dev = max_over_ranks(dt_dev, world, dev)
+    mapped_frac = float((np.diff(off) > 0).mean())
+    d2h_bytes = int(len(maps) * 32 + (n + 1) * 8)
+
+    # ---- end to end from pinned host memory: `e2e` ----
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    barrier(world)
+    dt_e2e = max_over_ranks(time.time() - t0, world, dev)
+
+    total_bases = sum_over_ranks(float(bases_rank), world, dev)
+    value = total_bases * args.steps / dt_dev / 1e9
+    e2e = total_bases * args.steps / dt_e2e / 1e9
+
+    # ---- roofline of every kernel family (algorithmic bytes: SURVEY.md 8d canonical accounting) ----
+    peak, peak_src = measured_peaks()
+    S = args.steps
+    ws = 2 * agg["windows"] / S            # window strands per step
+    bytes_pack = 1.25 * bases_rank
+    bytes_extract = ws * ((EDGE + 3) // 4) + 4.0 * agg["kmer_lookups"] / S
+    bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
+    bytes_chain = 8.0 * agg["chain_cells"] / S
+    kern = {}
+    for name, b, ms in (("pack", bytes_pack, agg["ms_pack"] / S), ("extract", bytes_extract, agg["ms_extract"] / S),
+                        ("lookup", bytes_lookup, agg["ms_lookup"] / S), ("chain", bytes_chain, agg["ms_chain"] / S)):
+        ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
+    dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])
+    traffic = {"pack": None, "extract": None, "lookup": None, "chain": None}
+    roofline = {"kernel": "dp_%s_kernel" % dominant, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
+                "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"], "traffic": traffic[dominant],
+                "peak_source": peak_src,
+                "note": "index (6 MB) and k-mer table (1 MB) are L2-resident for this config, so no kernel is bound by "
+                        "HBM; durations are CUDA-event times on the launching streams, summed over the two "
+                        "overlapping lanes (conservative)",
+                "kernels": kern}
+
+    line = {"metric": "mapped Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": config_dict(args, world),
+            "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(bases_rank + (n + 1) * 8),
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "note": "per GPU; dp_mapper_map_batch on pinned host ASCII"},
+            "gpu_launches": int(agg["kernel_launches"]),
+            "clocks": clocks, "roofline": roofline,
+            "mapped_fraction": mapped_frac, "bases_per_step": total_bases,
+            "index": dict(info, build_s=t_index, kmer_count_and_values_s=t_counts),
+            "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        cores = os.cpu_count() or 1
+        om = po.Mapper(ref, vals, circular=True)
+        ns = args.cpu_sample
+        t0 = time.time()
+        orow, ooff, _ = om.map_batch(host[: ns * READ_LEN], offs[: ns + 1], threads=cores)
+        dt = time.time() - t0
+        # the sample doubles as a parity check of the timed configuration
+        grow = np.stack([maps["start"], maps["end"], maps["q_offset"], maps["q_inset"], maps["rc"], maps["ids"]],
+                        axis=1).astype(np.int64)[: int(off[ns])]
+        parity = bool(np.array_equal(ooff, off[: ns + 1]) and np.array_equal(orow, grow))
+        line["cpu_baseline"] = {"value": ns * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "port",
+                                "sample": "first %d reads of the step's batch, mapping phase only" % ns,
+                                "parity_with_gpu_on_sample": parity}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    gm.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("DP_BENCH_READS", 1_000_000)),
+                    help="reads per GPU per step (BASELINE config 2: 1M)")
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
+    ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference":
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
