@@ -13,6 +13,7 @@ call fails loudly if the CUDA library is missing or no GPU is usable.
 import ctypes
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -110,6 +111,12 @@ def _u8(x):
     return np.ascontiguousarray(x, dtype=np.uint8)
 
 
+def _adopt(ptr, nbytes, dtype):
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    weakref.finalize(buf, lib().dp_free, ptr.value)
+    return np.frombuffer(buf, dtype=dtype)
+
+
 def pack(ascii_seq, device=0):
     """sequence.NewPackedSequence (sequence/sequence.go:67-93) through the device pack kernel -> bytes."""
     a = _u8(ascii_seq)
@@ -189,15 +196,14 @@ class Mapper:
             pass
 
     def _collect(self, n, out_p, off_p):
-        off = np.ctypeslib.as_array(ctypes.cast(off_p, ctypes.POINTER(c_i64)), shape=(n + 1,)).copy()
+        """Wraps the two malloc'ed result buffers as numpy arrays without copying; dp_free runs when the arrays die."""
+        off = _adopt(off_p, (n + 1) * 8, np.int64)
         total = int(off[n])
         if total:
-            raw = ctypes.string_at(out_p, total * MAPPING_DTYPE.itemsize)
-            maps = np.frombuffer(raw, dtype=MAPPING_DTYPE).copy()
+            maps = _adopt(out_p, total * MAPPING_DTYPE.itemsize, MAPPING_DTYPE)
         else:
+            lib().dp_free(out_p)
             maps = np.zeros(0, dtype=MAPPING_DTYPE)
-        lib().dp_free(out_p)
-        lib().dp_free(off_p)
         return maps, off
 
     def map_batch(self, bases, offsets):
