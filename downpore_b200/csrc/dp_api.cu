@@ -107,12 +107,15 @@ struct Lane {
     DBuf<DpCounters> dCtr;
     DBuf<unsigned char> dStatus, scanTmp;
     // lookup scratch
-    DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters;
+    DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters, lsTouched;
+    DBuf<unsigned long long> lsCand;
+    bool lsCountersZeroed = false;
     DBuf<unsigned char> lsFirst;
     DBuf<unsigned short> lsOrder;
     // chain scratch
-    DBuf<unsigned> csHashKey, csRqSeed, csRsSeed;
-    DBuf<unsigned char> csHashFlag;
+    DBuf<unsigned short> csQFirst, csQCnt, csRqId, csRsId;
+    DBuf<unsigned> csQLo;
+    DBuf<unsigned long long> csEnt;
     DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
     DBuf<DpMappingDev> csResults;
     HBuf<int> hOutN, hFinN;
@@ -141,8 +144,9 @@ struct dp_mapper {
     // index
     DBuf<unsigned> refWords;
     DBuf<uint2> table;
-    DBuf<unsigned> seedOff, seedChunks, chunkOff, chunkSeed;
-    DBuf<int> chunkPos, chunkScanLen;
+    DBuf<unsigned> seedOff, seedChunks, chunkOff, chunkSeed, postOff, postChunk, filter;
+    DBuf<int> chunkPos, chunkScanLen, postPos;
+    int filterBits = 0;
     DBuf<long long> chunkOffset, chunkInset;
     std::vector<long long> hChunkOffset, hChunkInset;
     std::vector<int> hChunkLen, hChunkScanLen;
@@ -152,6 +156,7 @@ struct dp_mapper {
     std::vector<std::unique_ptr<Lane>> lanes;
     dp_stats stats{};
     int outStride = 16, resultCap = 128, chainCap = 64;
+    bool attrsSet = false;
 
     ~dp_mapper() {
         lanes.clear();
@@ -371,11 +376,31 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     if (P2 > 0) {
         int endBit = 32;
         while ((1ull << (endBit - 32)) < (unsigned long long)numSeeds + 1 && endBit < 64) endBit++;
+        // stable LSD radix sort: equal (seed, chunk) keys keep their input order, which is ascending scan position
+        M.postPos.reserve((size_t)P2 + 1);
+        M.postChunk.reserve((size_t)P2 + 1);
         size_t tmpBytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys.p, keysSorted.p, (int)P2, 0, endBit, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, M.chunkPos.p, M.postPos.p, (int)P2, 0,
+                                        endBit, st);
         DBuf<unsigned char> tmp;
         tmp.reserve(tmpBytes);
-        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keys.p, keysSorted.p, (int)P2, 0, endBit, st));
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysSorted.p, M.chunkPos.p, M.postPos.p, (int)P2, 0,
+                                           endBit, st));
+        {
+            DBuf<unsigned> seedCountAll;
+            seedCountAll.reserve((size_t)numSeeds + 2);
+            M.postOff.reserve((size_t)numSeeds + 2);
+            CK(cudaMemsetAsync(seedCountAll.p, 0, ((size_t)numSeeds + 2) * sizeof(unsigned), st));
+            dp_posting_all_kernel<<<div_up((long long)P2, 256), 256, 0, st>>>(keysSorted.p, (long long)P2,
+                                                                             seedCountAll.p, M.postChunk.p);
+            CK(cudaGetLastError());
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, seedCountAll.p, M.postOff.p, (int)numSeeds + 1, st);
+            DBuf<unsigned char> t2;
+            t2.reserve(tb);
+            CK(cub::DeviceScan::ExclusiveSum(t2.p, tb, seedCountAll.p, M.postOff.p, (int)numSeeds + 1, st));
+            CK(cudaStreamSynchronize(st));
+        }
         DBuf<unsigned long long> nSel;
         nSel.reserve(1);
         size_t tmpBytes2 = 0;
@@ -404,8 +429,33 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
         CK(cudaStreamSynchronize(st));
     }
 
+    if (P2 == 0) {
+        M.postOff.reserve((size_t)numSeeds + 2);
+        M.postChunk.reserve(1);
+        M.postPos.reserve(1);
+        CK(cudaMemsetAsync(M.postOff.p, 0, ((size_t)numSeeds + 2) * sizeof(unsigned), st));
+    }
+    // ---- shared-memory prefilter for the extract kernel: worthwhile while seeds are sparse in it ----
+    M.filterBits = 0;
+    {
+        const int bits = 20;  // 128 KiB: fits one CTA per SM next to the ballot masks
+        if ((unsigned long long)numSeeds * 4 <= (1ull << bits)) {
+            M.filter.reserve((size_t)1 << (bits - 5));
+            CK(cudaMemsetAsync(M.filter.p, 0, sizeof(unsigned) << (bits - 5), st));
+            dp_filter_build_kernel<<<div_up(nTable, 256), 256, 0, st>>>(M.table.p, nTable, bits, M.filter.p);
+            CK(cudaGetLastError());
+            M.filterBits = bits;
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+
     DpIndexDev& I = M.I;
     I.k = k;
+    I.postOff = M.postOff.p;
+    I.postChunk = M.postChunk.p;
+    I.postPos = M.postPos.p;
+    I.filter = M.filter.p;
+    I.filterBits = M.filterBits;
     I.circular = M.circular;
     I.edge = e;
     I.maxWindow = 2 * e;
@@ -426,6 +476,7 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     M.nSeedPostings = (long long)P1;
     M.indexBytes = M.refWords.bytes() + M.table.bytes() + M.seedOff.bytes() + M.seedChunks.bytes() +
                    M.chunkOff.bytes() + M.chunkPos.bytes() + M.chunkSeed.bytes() + M.chunkOffset.bytes() +
+                   M.postOff.bytes() + M.postChunk.bytes() + M.postPos.bytes() + M.filter.bytes() +
                    M.chunkInset.bytes() + M.chunkScanLen.bytes();
 }
 
@@ -461,19 +512,28 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.lsAll.reserve(lw * qStride);
     W.lsFirst.reserve(lw * qStride);
     W.lsOrder.reserve(lw * qStride);
-    if (I.numChunks > 2048) W.lsCounters.reserve(lw * I.numChunks);
+    // a window strand touches at most min(C, total postings) chunks
+    const size_t tStride = (size_t)I.numChunks + 8;
+    W.lsTouched.reserve(lw * tStride);
+    W.lsCand.reserve(lw * 2 * tStride);
+    if (I.numChunks > 1536 && !W.lsCountersZeroed) {
+        W.lsCounters.reserve(lw * I.numChunks);
+        // the kernel keeps the invariant "all counters zero between window strands": clear once
+        CK(cudaMemsetAsync(W.lsCounters.p, 0, W.lsCounters.cap * sizeof(unsigned), W.stream));
+        W.lsCountersZeroed = true;
+    }
     size_t cw = (size_t)W.chainWarps;
-    int hashSize = 64;
-    while (hashSize < 2 * qStride) hashSize <<= 1;
     const int sStride = (int)I.maxChunkSeeds + 8;
-    W.csHashKey.reserve(cw * hashSize);
-    W.csHashFlag.reserve(cw * hashSize);
-    W.csRqSeed.reserve(cw * qStride);
+    W.csQFirst.reserve(cw * qStride);
+    W.csQCnt.reserve(cw * qStride);
+    W.csQLo.reserve(cw * qStride);
     W.csRqPos.reserve(cw * qStride);
-    W.csRsSeed.reserve(cw * sStride);
-    W.csRsPos.reserve(cw * sStride);
+    W.csRqId.reserve(cw * qStride);
     W.csChainLen.reserve(cw * qStride);
     W.csLastB.reserve(cw * qStride);
+    W.csEnt.reserve(cw * sStride);
+    W.csRsPos.reserve(cw * sStride);
+    W.csRsId.reserve(cw * sStride);
     W.csChains.reserve(cw * M.chainCap * 6);
     W.csResults.reserve(cw * M.resultCap);
 }
@@ -498,11 +558,18 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     Q.cursor = W.cursor.p + CUR_SEEDS;
     const int maskWords = (I.maxWindow + 31) / 32 + 1;
     {
-        int warpsPerBlock = 8;
-        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.extractWarps / 8);
-        size_t smem = (size_t)warpsPerBlock * 2 * maskWords * sizeof(unsigned);
+        const int warpsPerBlock = 32;  // one persistent 1024-thread CTA per SM
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount);
+        size_t smem = ((I.filterBits ? ((size_t)1 << (I.filterBits - 5)) : 0) + (size_t)warpsPerBlock * 2 * maskWords) *
+                      sizeof(unsigned);
+        if (!M.attrsSet) {
+            CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            M.attrsSet = true;
+        }
+        if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
         CK(cudaEventRecord(W.timers[T_EXTRACT].a, st));
-        dp_extract_kernel<<<blocks, 256, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords, W.dCtr.p);
+        dp_extract_kernel<<<blocks, 1024, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords, W.dCtr.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(W.timers[T_EXTRACT].b, st));
     }
@@ -516,32 +583,35 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.allSeeds = W.lsAll.p;
         S.order = W.lsOrder.p;
         S.counters = W.lsCounters.p;
+        S.touched = W.lsTouched.p;
+        S.cand = W.lsCand.p;
         S.stride = qStride;
-        int inSmem = I.numChunks <= 2048 ? 1 : 0;
-        int warpsPerBlock = 4;
+        S.tStride = (int)I.numChunks + 8;
+        int inSmem = I.numChunks <= 1536 ? 1 : 0;
+        int warpsPerBlock = DP_LWARPS;
         size_t smem = inSmem ? (size_t)warpsPerBlock * I.numChunks * sizeof(unsigned) : 0;
-        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.lookupWarps / 4);
+        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
+                                           (size_t)W.lookupWarps / warpsPerBlock);
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
-        dp_lookup_kernel<<<blocks, 128, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, W.candN.p, W.candChunk.p,
+        dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, W.candN.p, W.candChunk.p,
                                                     W.candDistinct.p, W.candStride, W.dCtr.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(W.timers[T_LOOKUP].b, st));
     }
     {
         DpChainScratch S;
-        int hashSize = 64;
-        while (hashSize < 2 * qStride) hashSize <<= 1;
-        S.hashKey = W.csHashKey.p;
-        S.hashFlag = W.csHashFlag.p;
-        S.rqSeed = W.csRqSeed.p;
+        S.qFirst = W.csQFirst.p;
+        S.qCnt = W.csQCnt.p;
+        S.qLo = W.csQLo.p;
         S.rqPos = W.csRqPos.p;
-        S.rsSeed = W.csRsSeed.p;
-        S.rsPos = W.csRsPos.p;
+        S.rqId = W.csRqId.p;
         S.chainLen = W.csChainLen.p;
         S.lastB = W.csLastB.p;
+        S.ent = W.csEnt.p;
+        S.rsPos = W.csRsPos.p;
+        S.rsId = W.csRsId.p;
         S.chains = W.csChains.p;
         S.results = W.csResults.p;
-        S.hashSize = hashSize;
         S.qStride = qStride;
         S.sStride = (int)I.maxChunkSeeds + 8;
         S.chainCap = M.chainCap;
@@ -1040,7 +1110,8 @@ int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, in
     if (!ref_ascii || !kmer_values || !out) throw std::runtime_error("null argument");
     if (k < 5 || k > 15) throw std::runtime_error("k must be in [5, 15] (packedKmerAt returns int32: sequence/asm_amd64.s:29)");
     if (seed_rate < k + 4) throw std::runtime_error("seed_rate must be at least k+4");
-    if (edge_size < 4 * k) throw std::runtime_error("query_size too small");
+    if (edge_size < 4 * k || edge_size > 16000) throw std::runtime_error("query_size must be in [4k, 16000]");
+    if (chunk_size > 60000) throw std::runtime_error("chunk_size must be at most 60000");
     if (chunk_size < 2 * edge_size || (long long)chunk_size * 10 - edge_size <= 0)
         throw std::runtime_error("chunk_size must be at least 2*query_size");
     if (ref_len < 2ll * edge_size || ref_len < seed_rate) throw std::runtime_error("reference shorter than 2*query_size");

@@ -7,6 +7,8 @@
 //                      among seed k-mers (seed ids are arbitrary labels in the reference: seeds/seeds.go:189).
 //   seed -> chunks   : CSR (seedOff[S+1], seedChunks[]) of the DISTINCT chunk ids containing each seed, ascending
 //                      (what SeedIndex.sequenceSets holds as bitsets, seeds/seeds.go:15,372-384).
+//   seed -> postings : CSR (postOff[S+1], postChunk[], postPos[]) of EVERY occurrence of each seed, sorted by
+//                      (chunk, scan position): what the chainer gathers for the query's seeds in a candidate chunk.
 //   chunk -> seeds   : CSR (chunkOff[C+1], chunkPos[], chunkSeed[]) of every seed occurrence of each chunk in scan
 //                      order (what SeedIndex.sequences[c].segments holds as gaps, seeds/seeds.go:33-50).
 #pragma once
@@ -28,6 +30,11 @@ struct DpIndexDev {
     const uint2* table;      // [4^k/32]
     const unsigned* seedOff;     // [S+1]
     const unsigned* seedChunks;  // [seedOff[S]]
+    const unsigned* postOff;     // [S+1]  every occurrence of each seed, sorted by (chunk, scan position)
+    const unsigned* postChunk;   // [postOff[S]]
+    const int* postPos;          // [postOff[S]]
+    const unsigned* filter;      // 2^filterBits-bit one-hash Bloom filter over seed k-mers (0 bits = none)
+    int filterBits;
     const unsigned* chunkOff;    // [C+1]
     const int* chunkPos;         // scan positions
     const unsigned* chunkSeed;   // seed ranks
@@ -100,6 +107,7 @@ __device__ __forceinline__ bool dp_seed_lookup(const uint2* __restrict__ table, 
     *rank = e.y + __popc(e.x & (bit - 1));
     return (e.x & bit) != 0;
 }
+__device__ __forceinline__ unsigned dp_filter_hash(unsigned kmer, int bits) { return (kmer * 2654435761u) >> (32 - bits); }
 __device__ __forceinline__ bool dp_seed_flag(const uint2* __restrict__ table, unsigned kmer) {
     return (__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u;
 }

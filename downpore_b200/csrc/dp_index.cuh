@@ -206,6 +206,32 @@ __global__ void __launch_bounds__(256) dp_chunk_scan_kernel(const unsigned* __re
     }
 }
 
+// every (seed, chunk) key (sorted, with duplicates) -> per-seed occurrence counts and the chunk column of the
+// position-carrying postings
+__global__ void dp_posting_all_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                      unsigned* __restrict__ seedCount, unsigned* __restrict__ postChunk) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        unsigned long long key = keys[i];
+        atomicAdd(seedCount + (unsigned)(key >> 32), 1u);
+        postChunk[i] = (unsigned)key;
+    }
+}
+
+// one-hash Bloom filter over the seed k-mers (shared-memory prefilter of the extract kernel)
+__global__ void dp_filter_build_kernel(const uint2* __restrict__ table, long long nTable, int bits,
+                                       unsigned* __restrict__ filter) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nTable) return;
+    unsigned f = table[w].x;
+    while (f) {
+        int b = __ffs(f) - 1;
+        f &= f - 1;
+        unsigned h = dp_filter_hash((unsigned)(w * 32 + b), bits);
+        atomicOr(filter + (h >> 5), 1u << (h & 31));
+    }
+}
+
 // sorted unique (seed, chunk) keys -> per-seed run lengths and the chunk column
 __global__ void dp_posting_fill_kernel(const unsigned long long* __restrict__ keys, long long n,
                                        unsigned* __restrict__ seedCount, unsigned* __restrict__ seedChunks) {

@@ -25,15 +25,27 @@ struct DpExtractOut {
     unsigned long long* cursor;  // bump allocator over qSeed/qPos
 };
 
-__global__ void __launch_bounds__(256) dp_extract_kernel(DpIndexDev I, const unsigned* __restrict__ readWords,
-                                                         const long long* __restrict__ readWordOff,
-                                                         const DpWindow* __restrict__ wins, int nWin, DpExtractOut O,
-                                                         int maskWords, DpCounters* __restrict__ ctr) {
+__global__ void __launch_bounds__(1024, 1) dp_extract_kernel(DpIndexDev I, const unsigned* __restrict__ readWords,
+                                                             const long long* __restrict__ readWordOff,
+                                                             const DpWindow* __restrict__ wins, int nWin,
+                                                             DpExtractOut O, int maskWords,
+                                                             DpCounters* __restrict__ ctr) {
+    // Persistent CTAs, one per SM: [ Bloom filter over the seed k-mers | per-warp ballot masks ].
+    // The filter answers ~94 % of the k-mer lookups from shared memory; only its positives gather the L2-resident table.
     extern __shared__ unsigned dp_smem[];
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
     const int warpInBlock = threadIdx.x >> 5;
-    unsigned* mF = dp_smem + (size_t)warpInBlock * 2 * maskWords;
+    const int fBits = I.filterBits;
+    const unsigned fWords = fBits ? (1u << (fBits - 5)) : 0u;
+    const unsigned* filt = dp_smem;
+    if (fBits) {
+        const uint4* src = reinterpret_cast<const uint4*>(I.filter);
+        uint4* dst = reinterpret_cast<uint4*>(dp_smem);
+        for (unsigned i = threadIdx.x; i < fWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    unsigned* mF = dp_smem + fWords + (size_t)warpInBlock * 2 * maskWords;
     unsigned* mR = mF + maskWords;
     const int k = I.k;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -52,8 +64,17 @@ __global__ void __launch_bounds__(256) dp_extract_kernel(DpIndexDev I, const uns
             bool hf = false, hr = false;
             if (j < nJ) {
                 unsigned kmer = dp_kmer_at(words, (long long)win.start + j, k);
-                hf = dp_seed_flag(I.table, kmer);
-                hr = dp_seed_flag(I.table, dp_revcomp(kmer, k));
+                unsigned rck = dp_revcomp(kmer, k);
+                if (fBits) {
+                    unsigned h1 = dp_filter_hash(kmer, fBits), h2 = dp_filter_hash(rck, fBits);
+                    hf = (filt[h1 >> 5] >> (h1 & 31)) & 1u;
+                    hr = (filt[h2 >> 5] >> (h2 & 31)) & 1u;
+                    if (hf) hf = dp_seed_flag(I.table, kmer);
+                    if (hr) hr = dp_seed_flag(I.table, rck);
+                } else {
+                    hf = dp_seed_flag(I.table, kmer);
+                    hr = dp_seed_flag(I.table, rck);
+                }
             }
             unsigned bf = __ballot_sync(DP_FULL, hf);
             unsigned br = __ballot_sync(DP_FULL, hr);
@@ -135,7 +156,11 @@ __global__ void __launch_bounds__(256) dp_extract_kernel(DpIndexDev I, const uns
 // The same pass counts, per chunk, the DISTINCT query seeds it contains (upper 16 bits of the counter), which is what
 // IntSet.CountIntersectionTo decides on later (mapping.go:520-523).
 // ===============================================================================================================
-struct DpLookupScratch {  // per-warp global scratch, `stride` entries per array
+#define DP_ECAP 128   // included seed occurrences per window strand held in shared memory
+#define DP_TCAP 256   // touched chunks per window strand held in shared memory
+#define DP_LWARPS 4   // warps per lookup CTA
+
+struct DpLookupScratch {  // per-warp global scratch for oversized window strands, `stride` entries per array
     unsigned* eSeed;
     unsigned* eOff;
     unsigned* ePre;    // exclusive prefix of posting run lengths (stride+1)
@@ -143,8 +168,11 @@ struct DpLookupScratch {  // per-warp global scratch, `stride` entries per array
     unsigned char* eFirst;  // first occurrence of the seed among E
     unsigned* allSeeds;     // seeds present in every chunk (|D| >= C)
     unsigned short* order;  // Q6 column-order simulation
-    unsigned* counters;     // [C] when C does not fit shared memory
+    unsigned* touched;      // chunks whose counter left zero [tStride]
+    unsigned long long* cand;  // (chunk << 32 | counter) of chunks over the threshold [2*tStride]: list + sort space
+    unsigned* counters;     // [C] per warp when C does not fit shared memory; all zero between window strands
     int stride;
+    int tStride;
 };
 
 __device__ __forceinline__ bool dp_run_contains(const unsigned* __restrict__ chunks, unsigned off, unsigned cnt,
@@ -159,25 +187,32 @@ __device__ __forceinline__ bool dp_run_contains(const unsigned* __restrict__ chu
     return lo < cnt && __ldg(chunks + off + lo) == c;
 }
 
-__global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractOut Q, int nWS, DpLookupScratch S,
-                                                        int countersInSmem, int* __restrict__ candN,
-                                                        unsigned* __restrict__ candChunk,
-                                                        unsigned short* __restrict__ candDistinct, int candStride,
-                                                        DpCounters* __restrict__ ctr) {
-    extern __shared__ unsigned dp_smem[];
+__global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                  DpLookupScratch S, int countersInSmem,
+                                                                  int* __restrict__ candN,
+                                                                  unsigned* __restrict__ candChunk,
+                                                                  unsigned short* __restrict__ candDistinct,
+                                                                  int candStride, DpCounters* __restrict__ ctr) {
+    extern __shared__ unsigned dp_smem[];  // per-warp chunk counters when they fit
+    __shared__ unsigned shSeed[DP_LWARPS][DP_ECAP];
+    __shared__ unsigned shOff[DP_LWARPS][DP_ECAP];
+    __shared__ unsigned shPre[DP_LWARPS][DP_ECAP + 1];
+    __shared__ unsigned shEndW[DP_LWARPS][DP_ECAP];
+    __shared__ unsigned char shFirst[DP_LWARPS][DP_ECAP];
+    __shared__ unsigned shTouched[DP_LWARPS][DP_TCAP];
+    __shared__ unsigned long long shCand[DP_LWARPS][DP_TCAP];
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
-    const int warpInBlock = threadIdx.x >> 5;
+    const int wib = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned C = I.numChunks;
-    unsigned* cnt = countersInSmem ? dp_smem + (size_t)warpInBlock * C : S.counters + (size_t)gwarp * C;
+    unsigned* cnt = countersInSmem ? dp_smem + (size_t)wib * C : S.counters + (size_t)gwarp * C;
+    if (countersInSmem) {  // counters are zero between window strands: clear them once per kernel
+        for (unsigned c = lane; c < C; c += 32) cnt[c] = 0;
+        __syncwarp();
+    }
     const size_t so = (size_t)gwarp * S.stride;
-    unsigned* eSeed = S.eSeed + so;
-    unsigned* eOff = S.eOff + so;
-    unsigned* ePre = S.ePre + (size_t)gwarp * (S.stride + 1);
-    unsigned* eEndW = S.eEndW + so;
-    unsigned char* eFirst = S.eFirst + so;
     unsigned* allSeeds = S.allSeeds + so;
     unsigned short* order = S.order + so;
     unsigned long long cRuns = 0, cEntries = 0, cCand = 0;
@@ -189,6 +224,12 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
         unsigned* outChunk = candChunk + (size_t)ws * candStride;
         unsigned short* outDist = candDistinct + (size_t)ws * candStride;
         if (n >= 5) {
+            const bool eSmall = n <= DP_ECAP;
+            unsigned* eSeed = eSmall ? shSeed[wib] : S.eSeed + so;
+            unsigned* eOff = eSmall ? shOff[wib] : S.eOff + so;
+            unsigned* ePre = eSmall ? shPre[wib] : S.ePre + (size_t)gwarp * (S.stride + 1);
+            unsigned* eEndW = eSmall ? shEndW[wib] : S.eEndW + so;
+            unsigned char* eFirst = eSmall ? shFirst[wib] : S.eFirst + so;
             // ---- inclusion filter (seeds.go:340-346), ordered ----
             int nInc = 0, nAll = 0;
             unsigned prevElig = 0xffffffffu;
@@ -236,7 +277,7 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
                     T = minCount;
                 }
                 const bool q6 = minCount >= 13 && minCount <= 24;  // level-16 plane decides alone
-                // ---- distinct seeds present in every chunk ----
+                // ---- distinct seeds present in every chunk (tiny references only) ----
                 int nAllDistinct = 0;
                 for (int a0 = 0; a0 < nAll; a0 += 32) {
                     int a = a0 + (int)lane;
@@ -252,25 +293,27 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
                     }
                     nAllDistinct += __popc(__ballot_sync(DP_FULL, first));
                 }
-                // ---- first occurrences among E, last word of each run, prefix of run lengths ----
+                // ---- first occurrences among E (__match_any_sync), last word of each run, run-length prefix ----
                 unsigned total = 0;
                 for (int j0 = 0; j0 < nInc; j0 += 32) {
                     int j = j0 + (int)lane;
                     unsigned c = 0;
+                    unsigned s = j < nInc ? eSeed[j] : (0x80000000u | lane);
+                    unsigned mm = __match_any_sync(DP_FULL, s);
                     if (j < nInc) {
-                        unsigned s = eSeed[j];
                         c = ePre[j];
-                        bool first = true;
-                        for (int b = 0; b < j; b++)
-                            if (eSeed[b] == s) {
-                                first = false;
-                                break;
-                            }
+                        bool first = (__ffs(mm) - 1) == (int)lane;
+                        if (first && j0 > 0) {
+                            for (int b = 0; b < j0; b++)
+                                if (eSeed[b] == s) {
+                                    first = false;
+                                    break;
+                                }
+                        }
                         eFirst[j] = first ? 1 : 0;
-                        eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
+                        if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
                     }
-                    // warp inclusive scan of c
-                    unsigned x = c;
+                    unsigned x = c;  // warp inclusive scan
                     for (int d = 1; d < 32; d <<= 1) {
                         unsigned y = __shfl_up_sync(DP_FULL, x, d);
                         if ((int)lane >= d) x += y;
@@ -280,12 +323,16 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
                     total += __shfl_sync(DP_FULL, x, 31);
                 }
                 if (lane == 0) ePre[nInc] = total;
-                // ---- clear counters ----
-                for (unsigned c = lane; c < C; c += 32) cnt[c] = 0;
                 __syncwarp();
-                // ---- gather the posting runs: the HBM/L2 gather this kernel is about ----
+                // ---- gather the posting runs into the per-chunk counters; remember which counters left zero ----
+                const bool tSmall = total <= DP_TCAP;
+                unsigned* touched = tSmall ? shTouched[wib] : S.touched + (size_t)gwarp * S.tStride;
+                unsigned long long* cand = tSmall ? shCand[wib] : S.cand + (size_t)gwarp * 2 * S.tStride;
+                int nTouched = 0;
                 for (unsigned p0 = 0; p0 < total; p0 += 32) {
                     unsigned p = p0 + lane;
+                    bool owner = false;
+                    unsigned chunk = 0;
                     if (p < total) {
                         int lo = 0, hi = nInc;  // largest j with ePre[j] <= p
                         while (hi - lo > 1) {
@@ -293,29 +340,73 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
                             if (ePre[mid] <= p) lo = mid;
                             else hi = mid;
                         }
-                        unsigned chunk = __ldg(I.seedChunks + eOff[lo] + (p - ePre[lo]));
-                        atomicAdd(cnt + chunk, 1u + ((unsigned)eFirst[lo] << 16));
+                        chunk = __ldg(I.seedChunks + eOff[lo] + (p - ePre[lo]));
+                        unsigned old = atomicAdd(cnt + chunk, 1u + ((unsigned)eFirst[lo] << 16));
+                        owner = old == 0;
                     }
+                    unsigned mo = __ballot_sync(DP_FULL, owner);
+                    if (owner) touched[nTouched + __popc(mo & lt)] = chunk;
+                    nTouched += __popc(mo);
                 }
                 __syncwarp();
                 cRuns += (unsigned)nInc;
                 cEntries += total;
-                // ---- threshold, ascending chunk id ----
+                // ---- threshold on the touched chunks; counters go back to zero ----
+                int nCand = 0;
+                for (int t0 = 0; t0 < nTouched; t0 += 32) {
+                    int t = t0 + (int)lane;
+                    unsigned chunk = 0, v = 0;
+                    if (t < nTouched) {
+                        chunk = touched[t];
+                        v = cnt[chunk];
+                        cnt[chunk] = 0;
+                    }
+                    bool pass = (int)(v & 0xffffu) >= T;
+                    unsigned mp = __ballot_sync(DP_FULL, pass);
+                    if (pass) cand[nCand + __popc(mp & lt)] = ((unsigned long long)chunk << 32) | v;
+                    nCand += __popc(mp);
+                }
+                __syncwarp();
+                // ---- ascending chunk id (rank sort: chunk ids are distinct), then the rare refinements ----
                 int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (lane 0 owns it)
                 bool simInit = false;
-                for (unsigned c0 = 0; c0 < C; c0 += 32) {
-                    unsigned c = c0 + lane;
-                    unsigned v = (c < C) ? cnt[c] : 0;
+                const unsigned long long* sorted = cand;
+                if (nCand > 1) {
+                    if (nCand <= 32) {  // in place: every lane holds its element before anyone writes
+                        unsigned long long e = (int)lane < nCand ? cand[lane] : ~0ull;
+                        int rank = 0;
+                        for (int y = 0; y < nCand; y++) rank += (cand[y] >> 32) < (e >> 32);
+                        __syncwarp();
+                        if ((int)lane < nCand) cand[rank] = e;
+                    } else {
+                        unsigned long long* dst = S.cand + (size_t)gwarp * 2 * S.tStride + S.tStride;
+                        for (int x0 = 0; x0 < nCand; x0 += 32) {
+                            int x = x0 + (int)lane;
+                            if (x < nCand) {
+                                unsigned long long e = cand[x];
+                                int rank = 0;
+                                for (int y = 0; y < nCand; y++) rank += (cand[y] >> 32) < (e >> 32);
+                                dst[rank] = e;
+                            }
+                        }
+                        sorted = dst;
+                    }
+                    __syncwarp();
+                }
+                for (int r0 = 0; r0 < nCand; r0 += 32) {
+                    const bool have = r0 + (int)lane < nCand;
+                    const unsigned long long mine = have ? sorted[r0 + lane] : 0ull;
+                    unsigned c = (unsigned)(mine >> 32);
+                    unsigned v = (unsigned)mine;
                     int soft = (int)(v & 0xffffu);
-                    bool pass = soft >= T;
+                    bool pass = have;
                     unsigned mp = __ballot_sync(DP_FULL, pass);
                     if (mp && (clamped || q6)) {
-                        // refine borderline lanes one at a time (rare)
                         unsigned todo = mp;
                         while (todo) {
                             int l = __ffs(todo) - 1;
                             todo &= todo - 1;
-                            unsigned cc = c0 + l;
+                            unsigned cc = __shfl_sync(DP_FULL, c, l);
                             unsigned wword = cc >> 6;
                             int sft = __shfl_sync(DP_FULL, soft, l);
                             bool keep = true;
@@ -332,8 +423,7 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
                                 if (lane == 0) {
                                     if (!simInit) {
                                         for (int j = 0; j < nInc; j++) order[j] = (unsigned short)j;
-                                        // start = min over sets of IntSet.start (1 for an empty set)
-                                        unsigned st = 0xffffffffu;
+                                        unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
                                         for (int j = 0; j < nInc; j++) {
                                             unsigned len = ePre[j + 1] - ePre[j];
                                             unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
@@ -399,154 +489,192 @@ __global__ void __launch_bounds__(128) dp_lookup_kernel(DpIndexDev I, DpExtractO
 // SeedSequence.Match -> Reduced -> dynamicMatch -> extendChain (seeds/sequence.go:85-123, 361-576) and the
 // coordinate arithmetic of GetSeedOffset / GetSeedOffsetFromEnd / GetBasesCovered (sequence.go:830-858, 1239-1276)
 // done on scan positions. One warp per window: candidates are visited in ascending chunk id, forward strand first,
-// because the thresholds minMatches / minRCMatches escalate as chains are accepted (Q12). The warp builds both
-// reduced lists cooperatively (ordered ballot compaction); lane 0 runs the greedy chainer.
+// because the thresholds minMatches / minRCMatches escalate as chains are accepted (Q12).
+//
+// chunk.Reduced(querySet) never streams the chunk: each distinct query seed binary-searches its position-carrying
+// posting run for the candidate chunk; the few (position, seed) pairs found are rank-sorted by position and the
+// same-as-previous seeds collapsed. query.Reduced(chunkSet) is the query list filtered by "seed found in the chunk".
+// A seed is identified by the index of its first occurrence in the strand's list (__match_any_sync), so no hashing.
+// dynamicMatch's search for chain starts is a warp ballot per query seed; lane 0 runs the greedy extension.
 // ===============================================================================================================
-struct DpChainScratch {  // per-warp global scratch
-    unsigned* hashKey;        // [hashSize] query seed ranks (0xffffffff = empty)
-    unsigned char* hashFlag;  // [hashSize] bit0: present in the current chunk
-    unsigned* rqSeed;         // reduced query [qStride]
-    int* rqPos;
-    unsigned* rsSeed;         // reduced chunk [sStride]
-    int* rsPos;
-    int* chainLen;            // memo per reduced query seed: 0 = nil  [qStride]
-    int* lastB;               // memo: last chunk index of the chain through this query seed [qStride]
-    int* chains;              // accepted chains of the current candidate: 6 ints each [chainCap*6]
-    DpMappingDev* results;    // window results before sort/dedupe [resultCap]
-    int hashSize;
+#define DP_QCAP 128  // query entries per strand held in shared memory (longer lists use the global scratch)
+#define DP_MCAP 128  // chunk-side entries per candidate held in shared memory
+
+struct DpChainScratch {  // per-warp global scratch for lists that do not fit shared memory, and for rare big records
+    unsigned short* qFirst;  // [qStride]
+    unsigned short* qCnt;    // [qStride]
+    unsigned* qLo;           // [qStride]
+    int* rqPos;              // [qStride]
+    unsigned short* rqId;    // [qStride]
+    int* chainLen;           // [qStride]
+    int* lastB;              // [qStride]
+    unsigned long long* ent; // [sStride]
+    int* rsPos;              // [sStride]
+    unsigned short* rsId;    // [sStride]
+    int* chains;             // accepted chains of the current candidate: 6 ints each [chainCap*6]
+    DpMappingDev* results;   // window results before sort/dedupe [resultCap]
     int qStride;
     int sStride;
     int chainCap;
     int resultCap;
 };
 
-__device__ __forceinline__ unsigned dp_hash(unsigned s) { return s * 2654435761u; }
+struct DpChainLists {  // the working lists of one candidate (shared or global memory)
+    const int* rqPos;
+    const unsigned short* rqId;
+    int nq, qScanLen;
+    const int* rsPos;
+    const unsigned short* rsId;
+    int ns, sScanLen;
+    int* chainLen;
+    int* lastB;
+};
 
-// lane 0 only. Reduced lists: (qs,qp)[nq] query, (ss,sp)[ns] chunk. Accepted chains -> ch[] as
-// {len, firstA, lastA, firstB, lastB, ids}; returns their number (or -1 on chain list overflow).
-__device__ int dp_dynamic_match(const unsigned* qs, const int* qp, int nq, int qScanLen, const unsigned* ss,
-                                const int* sp, int ns, int sScanLen, int minMatch, int k, int* chainLen, int* lastB,
-                                int* ch, int chainCap) {
+// Warp-collective dynamicMatch (sequence.go:401-471). Accepted chains -> ch[] as {len, firstA, lastA, firstB, lastB,
+// ids} (indices into the reduced lists); returns their number, or -1 on chain list overflow. Uniform across lanes.
+__device__ int dp_dynamic_match(const DpChainLists& T, int minMatch, int k, int* ch, int chainCap) {
+    const unsigned lane = dp_lane();
+    const int nq = T.nq, ns = T.ns;
     if (minMatch == 0) minMatch = 1;
     int nGood = 0;
-    int nilCount = nq;
-    for (int x = 0; x < nq; x++) chainLen[x] = 0;
-#define GAPQ(i) (((i) + 1 < nq ? qp[(i) + 1] : qScanLen) - qp[(i)] - k)
-#define GAPS(i) (((i) + 1 < ns ? sp[(i) + 1] : sScanLen) - sp[(i)] - k)
+    int nilCount = nq;  // lane 0's copy is authoritative
+    for (int x = lane; x < nq; x += 32) T.chainLen[x] = 0;
+    __syncwarp();
+#define GAPQ(i) (((i) + 1 < nq ? T.rqPos[(i) + 1] : T.qScanLen) - T.rqPos[(i)] - k)
+#define GAPS(i) (((i) + 1 < ns ? T.rsPos[(i) + 1] : T.sScanLen) - T.rsPos[(i)] - k)
     for (int qi = 0; qi <= nq - minMatch; qi++) {
-        if (qi > 0 && qi + 1 < nq && GAPQ(qi - 1) < 0 && GAPQ(qi) < 0 && qs[qi] == qs[qi - 1] && qs[qi] == qs[qi + 1])
-            continue;  // sequence.go:409 (cannot fire on reduced lists; kept for fidelity)
-        if (chainLen[qi] != 0) continue;
-        unsigned prevSeed = 0xffffffffu;
-        const unsigned qseed = qs[qi];
-        for (int si = 0; si <= ns - minMatch; si++) {
-            unsigned nextSeed = ss[si];
-            if (nextSeed == qseed && nextSeed != prevSeed && (chainLen[qi] == 0 || lastB[qi] != si)) {
-                if (chainLen[qi] == 0) nilCount--;
-                chainLen[qi] = 1;
-                lastB[qi] = si;
-                // ---- extendChain (sequence.go:476-576) ----
-                int curLen = 1;
-                int ids = k;
-                int lastA = qi, lastBi = si;
-                int offsetA = GAPQ(qi);
-                int offsetB = GAPS(si);
-                int ai = qi + 1, bi = si + 1;
-                bool done = false;
-                while (!done && ai < nq && bi < ns) {
-                    int minB, maxB;
-                    if (offsetA < 0) {
-                        minB = -k;
-                        maxB = 0;
-                    } else {
-                        minB = (offsetA * 2) / 3 - k;
-                        maxB = (offsetA * 3) / 2 + k;
-                    }
-                    while (maxB < offsetB) {
-                        offsetA += GAPQ(ai) + k;
-                        ai++;
-                        if (ai >= nq) {
-                            done = true;
-                            break;
-                        }
-                        minB = (offsetA * 2) / 3 - k;
-                        maxB = (offsetA * 3) / 2 + k;
-                    }
-                    if (done) break;
-                    while (offsetB < minB) {
-                        offsetB += GAPS(bi) + k;
-                        bi++;
-                        if (bi >= ns) {
-                            done = true;
-                            break;
-                        }
-                    }
-                    if (done) break;
-                    int oldBi = bi, oldBOffset = offsetB;
-                    bool matched = false;
-                    unsigned seedA = qs[ai];
-                    while (offsetB <= maxB) {
-                        if (seedA == ss[bi]) {
-                            if (chainLen[ai] != 0) {
-                                if (bi == lastB[ai] && chainLen[ai] > curLen) {
-                                    done = true;  // they have a better chain already
+        // sequence.go:409: internal to closely spaced repeats (cannot fire on reduced lists; kept for fidelity)
+        if (qi > 0 && qi + 1 < nq && GAPQ(qi - 1) < 0 && GAPQ(qi) < 0 && T.rqId[qi] == T.rqId[qi - 1] &&
+            T.rqId[qi] == T.rqId[qi + 1])
+            continue;
+        if (T.chainLen[qi] != 0) continue;  // uniform: shared/global memory made visible by the __syncwarp below
+        const unsigned short qid = T.rqId[qi];
+        for (int s0 = 0; s0 < ns; s0 += 32) {
+            int si = s0 + (int)lane;
+            bool cand = si < ns && T.rsId[si] == qid && (si == 0 || T.rsId[si - 1] != qid);
+            unsigned m = __ballot_sync(DP_FULL, cand);
+            while (m) {
+                const int si0 = s0 + __ffs(m) - 1;
+                m &= m - 1;
+                int ret = 0;  // 1: early return requested, -1: overflow
+                if (lane == 0) {
+                    // conditions re-evaluated with the state as it is now (minMatch may have grown)
+                    if (si0 <= ns - minMatch && (T.chainLen[qi] == 0 || T.lastB[qi] != si0)) {
+                        if (T.chainLen[qi] == 0) nilCount--;
+                        T.chainLen[qi] = 1;
+                        T.lastB[qi] = si0;
+                        // ---- extendChain (sequence.go:476-576) ----
+                        int curLen = 1;
+                        int ids = k;
+                        int lastA = qi, lastBi = si0;
+                        int offsetA = GAPQ(qi);
+                        int offsetB = GAPS(si0);
+                        int ai = qi + 1, bi = si0 + 1;
+                        bool done = false;
+                        while (!done && ai < nq && bi < ns) {
+                            int minB, maxB;
+                            if (offsetA < 0) {
+                                minB = -k;
+                                maxB = 0;
+                            } else {
+                                minB = (offsetA * 2) / 3 - k;
+                                maxB = (offsetA * 3) / 2 + k;
+                            }
+                            while (maxB < offsetB) {
+                                offsetA += GAPQ(ai) + k;
+                                ai++;
+                                if (ai >= nq) {
+                                    done = true;
                                     break;
                                 }
+                                minB = (offsetA * 2) / 3 - k;
+                                maxB = (offsetA * 3) / 2 + k;
+                            }
+                            if (done) break;
+                            while (offsetB < minB) {
+                                offsetB += GAPS(bi) + k;
+                                bi++;
+                                if (bi >= ns) {
+                                    done = true;
+                                    break;
+                                }
+                            }
+                            if (done) break;
+                            int oldBi = bi, oldBOffset = offsetB;
+                            bool matched = false;
+                            const unsigned short seedA = T.rqId[ai];
+                            while (offsetB <= maxB) {
+                                if (seedA == T.rsId[bi]) {
+                                    if (T.chainLen[ai] != 0) {
+                                        if (bi == T.lastB[ai] && T.chainLen[ai] > curLen) {
+                                            done = true;  // they have a better chain already
+                                            break;
+                                        }
+                                    } else {
+                                        nilCount--;
+                                    }
+                                    curLen++;
+                                    T.chainLen[ai] = curLen;
+                                    T.lastB[ai] = bi;
+                                    int d2 = T.rsPos[bi] - T.rsPos[lastBi] - k;  // GetBasesCovered, reference side
+                                    ids += k + (d2 < 0 ? d2 : 0);
+                                    lastA = ai;
+                                    lastBi = bi;
+                                    offsetA = GAPQ(ai);
+                                    offsetB = GAPS(bi);
+                                    ai++;
+                                    bi++;
+                                    matched = true;
+                                    break;
+                                } else {
+                                    offsetB += GAPS(bi) + k;
+                                    bi++;
+                                    if (bi >= ns) break;
+                                }
+                            }
+                            if (done) break;
+                            if (!matched) {
+                                offsetA += GAPQ(ai) + k;
+                                ai++;
+                                offsetB = oldBOffset;
+                                bi = oldBi;
+                            }
+                        }
+                        // ---- dynamicMatch bookkeeping (sequence.go:435-465) ----
+                        if (curLen >= minMatch) {
+                            int nextLength = (curLen * 2) / 3;
+                            if (nextLength > minMatch) {
+                                minMatch = nextLength;
+                                for (int j = nGood - 1; j >= 0; j--) {
+                                    if (ch[j * 6] < nextLength) {
+                                        for (int z = 0; z < 6; z++) ch[j * 6 + z] = ch[(nGood - 1) * 6 + z];
+                                        nGood--;
+                                    }
+                                }
+                            }
+                            if (nGood >= chainCap) {
+                                ret = -1;
                             } else {
-                                nilCount--;
-                            }
-                            curLen++;
-                            chainLen[ai] = curLen;
-                            lastB[ai] = bi;
-                            int d2 = sp[bi] - sp[lastBi] - k;  // GetBasesCovered: overlap on the reference side
-                            ids += k + (d2 < 0 ? d2 : 0);
-                            lastA = ai;
-                            lastBi = bi;
-                            offsetA = GAPQ(ai);
-                            offsetB = GAPS(bi);
-                            ai++;
-                            bi++;
-                            matched = true;
-                            break;
-                        } else {
-                            offsetB += GAPS(bi) + k;
-                            bi++;
-                            if (bi >= ns) break;
-                        }
-                    }
-                    if (done) break;
-                    if (!matched) {
-                        offsetA += GAPQ(ai) + k;
-                        ai++;
-                        offsetB = oldBOffset;
-                        bi = oldBi;
-                    }
-                }
-                // ---- dynamicMatch bookkeeping (sequence.go:435-465) ----
-                if (curLen >= minMatch) {
-                    int nextLength = (curLen * 2) / 3;
-                    if (nextLength > minMatch) {
-                        minMatch = nextLength;
-                        for (int j = nGood - 1; j >= 0; j--) {
-                            if (ch[j * 6] < nextLength) {
-                                for (int z = 0; z < 6; z++) ch[j * 6 + z] = ch[(nGood - 1) * 6 + z];
-                                nGood--;
+                                int* r = ch + nGood * 6;
+                                r[0] = curLen;
+                                r[1] = qi;
+                                r[2] = lastA;
+                                r[3] = si0;
+                                r[4] = lastBi;
+                                r[5] = ids;
+                                nGood++;
+                                if (nilCount < curLen) ret = 1;
                             }
                         }
                     }
-                    if (nGood >= chainCap) return -1;
-                    int* r = ch + nGood * 6;
-                    r[0] = curLen;
-                    r[1] = qi;
-                    r[2] = lastA;
-                    r[3] = si;
-                    r[4] = lastBi;
-                    r[5] = ids;
-                    nGood++;
-                    if (nilCount < curLen) return nGood;
                 }
+                __syncwarp();
+                ret = __shfl_sync(DP_FULL, ret, 0);
+                minMatch = __shfl_sync(DP_FULL, minMatch, 0);
+                nGood = __shfl_sync(DP_FULL, nGood, 0);
+                if (ret < 0) return -1;
+                if (ret > 0) return nGood;
             }
-            prevSeed = nextSeed;
         }
     }
 #undef GAPQ
@@ -554,7 +682,7 @@ __device__ int dp_dynamic_match(const unsigned* qs, const int* qp, int nq, int q
     return nGood;
 }
 
-__global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWindow* __restrict__ wins,
+__global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const DpWindow* __restrict__ wins,
                                                        const int* __restrict__ readLen, int nWin, DpExtractOut Q,
                                                        const int* __restrict__ candN,
                                                        const unsigned* __restrict__ candChunk,
@@ -565,19 +693,23 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                                                        unsigned long long* __restrict__ outCursor,
                                                        unsigned long long outCapacity,
                                                        DpCounters* __restrict__ ctr) {
+    // shared memory per warp
+    __shared__ unsigned short shFirst[4][DP_QCAP];
+    __shared__ unsigned short shCnt[4][DP_QCAP];
+    __shared__ unsigned shLo[4][DP_QCAP];
+    __shared__ int shRqPos[4][DP_QCAP];
+    __shared__ unsigned short shRqId[4][DP_QCAP];
+    __shared__ int shChainLen[4][DP_QCAP];
+    __shared__ int shLastB[4][DP_QCAP];
+    __shared__ unsigned long long shEnt[4][DP_MCAP];
+    __shared__ int shRsPos[4][DP_MCAP];
+    __shared__ unsigned short shRsId[4][DP_MCAP];
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
+    const int wib = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = I.k;
-    unsigned* hashKey = S.hashKey + (size_t)gwarp * S.hashSize;
-    unsigned char* hashFlag = S.hashFlag + (size_t)gwarp * S.hashSize;
-    unsigned* rqSeed = S.rqSeed + (size_t)gwarp * S.qStride;
-    int* rqPos = S.rqPos + (size_t)gwarp * S.qStride;
-    unsigned* rsSeed = S.rsSeed + (size_t)gwarp * S.sStride;
-    int* rsPos = S.rsPos + (size_t)gwarp * S.sStride;
-    int* chainLen = S.chainLen + (size_t)gwarp * S.qStride;
-    int* lastB = S.lastB + (size_t)gwarp * S.qStride;
     int* chains = S.chains + (size_t)gwarp * S.chainCap * 6;
     DpMappingDev* results = S.results + (size_t)gwarp * S.resultCap;
     unsigned long long cCells = 0, cMaps = 0;
@@ -604,20 +736,28 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
             const int n = Q.wsN[ws];
             const unsigned qb = Q.wsOff[ws];
             const int qScanLen = strand == 0 ? (L - (q2 ? 4 : 0)) : (L - (q2 ? 3 : 0));
-            // ---- hash set of the strand's seeds (open addressing, at most half full) ----
-            int hsize = 64;
-            while (hsize < 2 * n) hsize <<= 1;
-            const unsigned hmask = (unsigned)hsize - 1;
-            for (int h = lane; h < hsize; h += 32) hashKey[h] = 0xffffffffu;
-            __syncwarp();
-            for (int j = lane; j < n; j += 32) {
-                unsigned s = Q.qSeed[qb + j];
-                unsigned h = dp_hash(s) & hmask;
-                for (;;) {
-                    unsigned old = atomicCAS(hashKey + h, 0xffffffffu, s);
-                    if (old == 0xffffffffu || old == s) break;
-                    h = (h + 1) & hmask;
+            const bool qSmall = n <= DP_QCAP;
+            unsigned short* qFirst = qSmall ? shFirst[wib] : S.qFirst + (size_t)gwarp * S.qStride;
+            unsigned short* qCnt = qSmall ? shCnt[wib] : S.qCnt + (size_t)gwarp * S.qStride;
+            unsigned* qLo = qSmall ? shLo[wib] : S.qLo + (size_t)gwarp * S.qStride;
+            int* rqPos = qSmall ? shRqPos[wib] : S.rqPos + (size_t)gwarp * S.qStride;
+            unsigned short* rqId = qSmall ? shRqId[wib] : S.rqId + (size_t)gwarp * S.qStride;
+            int* chainLen = qSmall ? shChainLen[wib] : S.chainLen + (size_t)gwarp * S.qStride;
+            int* lastB = qSmall ? shLastB[wib] : S.lastB + (size_t)gwarp * S.qStride;
+            // ---- seed identity = index of the first occurrence of the seed in this strand's list ----
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                int j = j0 + (int)lane;
+                unsigned s = j < n ? Q.qSeed[qb + j] : (0x80000000u | lane);  // padding lanes never match
+                unsigned mm = __match_any_sync(DP_FULL, s);
+                int first = j0 + __ffs(mm) - 1;
+                if (j < n && j0 > 0) {
+                    for (int b = 0; b < j0; b++)
+                        if (Q.qSeed[qb + b] == s) {
+                            first = b;
+                            break;
+                        }
                 }
+                if (j < n) qFirst[j] = (unsigned short)first;
             }
             __syncwarp();
             for (int ci = 0; ci < nc; ci++) {
@@ -625,102 +765,146 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                 // 1. CountIntersectionTo(...) < threshold (mapping.go:520-523, 559-562)
                 if ((int)candDistinct[(size_t)ws * candStride + ci] < thr) continue;
                 const unsigned c = candChunk[(size_t)ws * candStride + ci];
-                const unsigned cb = __ldg(I.chunkOff + c);
-                const int cn = (int)(__ldg(I.chunkOff + c + 1) - cb);
-                // 2. chunk.Reduced(querySet) (sequence.go:85-123): members of the query set, same-as-previous collapsed
-                for (int h = lane; h < hsize; h += 32) hashFlag[h] = 0;
-                __syncwarp();
-                int ns = 0;
-                unsigned prevMember = 0xffffffffu;
-                for (int e0 = 0; e0 < cn; e0 += 32) {
-                    int e = e0 + (int)lane;
-                    unsigned s = 0xffffffffu;
-                    int pos = 0;
-                    bool member = false;
-                    if (e < cn) {
-                        s = __ldg(I.chunkSeed + cb + e);
-                        pos = __ldg(I.chunkPos + cb + e);
-                        unsigned h = dp_hash(s) & hmask;
-                        for (;;) {
-                            unsigned key = hashKey[h];
-                            if (key == s) {
-                                member = true;
-                                hashFlag[h] = 1;
-                                break;
-                            }
-                            if (key == 0xffffffffu) break;
-                            h = (h + 1) & hmask;
-                        }
-                    }
-                    unsigned mm = __ballot_sync(DP_FULL, member);
-                    unsigned lower = mm & lt;
-                    int src = lower ? 31 - __clz(lower) : 0;
-                    unsigned ps = __shfl_sync(DP_FULL, s, src);
-                    if (!lower) ps = prevMember;
-                    bool keep = member && s != ps;
-                    unsigned mk = __ballot_sync(DP_FULL, keep);
-                    if (keep) {
-                        int idx = ns + __popc(mk & lt);
-                        rsSeed[idx] = s;
-                        rsPos[idx] = pos;
-                    }
-                    ns += __popc(mk);
-                    if (mm) prevMember = __shfl_sync(DP_FULL, s, 31 - __clz(mm));
-                }
-                __syncwarp();
-                // 3. query.Reduced(chunkSet): both Reduced calls run before the nil test (sequence.go:366-374)
-                int nq = 0;
-                prevMember = 0xffffffffu;
+                // 2. every distinct query seed looks up its postings inside chunk c
+                int m = 0;
                 for (int j0 = 0; j0 < n; j0 += 32) {
                     int j = j0 + (int)lane;
-                    unsigned s = 0xffffffffu;
-                    int pos = 0;
+                    unsigned lo = 0;
+                    int cnt = 0;
+                    if (j < n && qFirst[j] == j) {
+                        unsigned s = Q.qSeed[qb + j];
+                        unsigned b = __ldg(I.postOff + s), e = __ldg(I.postOff + s + 1);
+                        unsigned hi = e;
+                        lo = b;
+                        while (lo < hi) {
+                            unsigned mid = (lo + hi) >> 1;
+                            if (__ldg(I.postChunk + mid) < c) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        while (lo + cnt < e && cnt < 65535 && __ldg(I.postChunk + lo + cnt) == c) cnt++;
+                    }
+                    if (j < n) {
+                        qLo[j] = lo;
+                        qCnt[j] = (unsigned short)cnt;
+                    }
+                    unsigned x = (unsigned)cnt;
+                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(DP_FULL, x, d);
+                    m += (int)x;
+                }
+                __syncwarp();
+                // 3. query.Reduced(chunkSet) (sequence.go:85-123): entries whose seed occurs in the chunk,
+                //    same-as-previous-member collapsed. (Both Reduced calls precede the nil test, sequence.go:366-374.)
+                int nq = 0;
+                int prevMember = -1;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    int j = j0 + (int)lane;
+                    int id = -2 - (int)lane;
                     bool member = false;
                     if (j < n) {
-                        s = Q.qSeed[qb + j];
-                        pos = Q.qPos[qb + j];
-                        unsigned h = dp_hash(s) & hmask;
-                        for (;;) {
-                            unsigned key = hashKey[h];
-                            if (key == s) {
-                                member = hashFlag[h] != 0;
-                                break;
-                            }
-                            h = (h + 1) & hmask;
-                        }
+                        id = qFirst[j];
+                        member = qCnt[id] != 0;
                     }
                     unsigned mm = __ballot_sync(DP_FULL, member);
                     unsigned lower = mm & lt;
                     int src = lower ? 31 - __clz(lower) : 0;
-                    unsigned ps = __shfl_sync(DP_FULL, s, src);
-                    if (!lower) ps = prevMember;
-                    bool keep = member && s != ps;
+                    int pid = __shfl_sync(DP_FULL, id, src);
+                    if (!lower) pid = prevMember;
+                    bool keep = member && id != pid;
                     unsigned mk = __ballot_sync(DP_FULL, keep);
                     if (keep) {
                         int idx = nq + __popc(mk & lt);
-                        rqSeed[idx] = s;
-                        rqPos[idx] = pos;
+                        rqId[idx] = (unsigned short)id;
+                        rqPos[idx] = Q.qPos[qb + j];
                     }
                     nq += __popc(mk);
-                    if (mm) prevMember = __shfl_sync(DP_FULL, s, 31 - __clz(mm));
+                    if (mm) prevMember = __shfl_sync(DP_FULL, id, 31 - __clz(mm));
+                }
+                // 4. chunk.Reduced(querySet): gather (position, seed) pairs, rank-sort by position, collapse
+                if (m > S.sStride) {  // cannot happen: a chunk has at most maxChunkSeeds entries
+                    overflow = true;
+                    continue;
+                }
+                const bool sSmall = m <= DP_MCAP;
+                unsigned long long* ent = sSmall ? shEnt[wib] : S.ent + (size_t)gwarp * S.sStride;
+                int* rsPos = sSmall ? shRsPos[wib] : S.rsPos + (size_t)gwarp * S.sStride;
+                unsigned short* rsId = sSmall ? shRsId[wib] : S.rsId + (size_t)gwarp * S.sStride;
+                {
+                    int base = 0;
+                    for (int j0 = 0; j0 < n; j0 += 32) {
+                        int j = j0 + (int)lane;
+                        int cnt = j < n ? (int)qCnt[j] : 0;
+                        int x = cnt;  // inclusive scan
+                        for (int d = 1; d < 32; d <<= 1) {
+                            int y = __shfl_up_sync(DP_FULL, x, d);
+                            if ((int)lane >= d) x += y;
+                        }
+                        int off = base + x - cnt;
+                        if (cnt) {
+                            unsigned lo = qLo[j];
+                            for (int t = 0; t < cnt; t++)
+                                ent[off + t] = ((unsigned long long)(unsigned)__ldg(I.postPos + lo + t) << 32) | (unsigned)j;
+                        }
+                        base += __shfl_sync(DP_FULL, x, 31);
+                    }
                 }
                 __syncwarp();
+                for (int i0 = 0; i0 < m; i0 += 32) {  // scan positions inside a chunk are distinct: ranks are unique
+                    int i = i0 + (int)lane;
+                    if (i < m) {
+                        unsigned long long mine = ent[i];
+                        int rank = 0;
+                        for (int x = 0; x < m; x++) rank += (ent[x] >> 32) < (mine >> 32);
+                        rsPos[rank] = (int)(mine >> 32);
+                        rsId[rank] = (unsigned short)(mine & 0xffffu);
+                    }
+                }
+                __syncwarp();
+                int ns = 0;
+                prevMember = -1;
+                for (int i0 = 0; i0 < m; i0 += 32) {
+                    int i = i0 + (int)lane;
+                    int id = -2 - (int)lane, pos = 0;
+                    if (i < m) {
+                        id = rsId[i];
+                        pos = rsPos[i];
+                    }
+                    int pid = __shfl_up_sync(DP_FULL, id, 1);
+                    if (lane == 0) pid = prevMember;
+                    bool keep = i < m && id != pid;
+                    unsigned mk = __ballot_sync(DP_FULL, keep);
+                    __syncwarp();
+                    if (keep) {
+                        int idx = ns + __popc(mk & lt);
+                        rsId[idx] = (unsigned short)id;
+                        rsPos[idx] = pos;
+                    }
+                    ns += __popc(mk);
+                    prevMember = __shfl_sync(DP_FULL, id, 31);
+                    __syncwarp();
+                }
                 if (ns < thr || nq < thr) continue;  // Reduced returned nil
                 cCells += (unsigned)(ns + nq);
-                // 4. dynamicMatch on lane 0
+                // 5. dynamicMatch
                 const int sScanLen = __ldg(I.chunkScanLen + c);
-                int nGood = 0;
-                if (lane == 0)
-                    nGood = dp_dynamic_match(rqSeed, rqPos, nq, qScanLen, rsSeed, rsPos, ns, sScanLen, thr, k, chainLen,
-                                             lastB, chains, S.chainCap);
-                nGood = __shfl_sync(DP_FULL, nGood, 0);
+                DpChainLists T;
+                T.rqPos = rqPos;
+                T.rqId = rqId;
+                T.nq = nq;
+                T.qScanLen = qScanLen;
+                T.rsPos = rsPos;
+                T.rsId = rsId;
+                T.ns = ns;
+                T.sScanLen = sScanLen;
+                T.chainLen = chainLen;
+                T.lastB = lastB;
+                int nGood = dp_dynamic_match(T, thr, k, chains, S.chainCap);
                 if (nGood < 0) {
                     overflow = true;
                     if (lane == 0) atomicOr(&ctr->overflow, 2u);
                     nGood = 0;
                 }
                 __syncwarp();
-                // 5. chains -> mappings (mapping.go:528-549 / 567-587), in allGoodChains order; lane 0 keeps the state
+                // 6. chains -> mappings (mapping.go:528-549 / 567-587), in allGoodChains order; lane 0 keeps the state
                 if (lane == 0) {
                     const long long cOffset = __ldg(I.chunkOffset + c);
                     const long long cInset = __ldg(I.chunkInset + c);
@@ -729,8 +913,8 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                         long long start = cOffset + rsPos[r[3]];
                         long long end = I.refLen - cInset - (long long)(sScanLen - rsPos[r[4]] - k);
                         if (I.circular && start > I.refLen) start -= I.refLen;
-                        int first = rqPos[r[1]];                      // GetSeedOffset(MatchA[0])
-                        int fromEnd = qScanLen - rqPos[r[2]] - k;     // GetSeedOffsetFromEnd(MatchA[last])
+                        int first = rqPos[r[1]];                   // GetSeedOffset(MatchA[0])
+                        int fromEnd = qScanLen - rqPos[r[2]] - k;  // GetSeedOffsetFromEnd(MatchA[last])
                         if (first + fromEnd > (L * 2) / 3) continue;
                         DpMappingDev mp;
                         mp.start = start;
@@ -761,12 +945,13 @@ __global__ void __launch_bounds__(128) dp_chain_kernel(DpIndexDev I, const DpWin
                 minRCMatches = __shfl_sync(DP_FULL, minRCMatches, 0);
                 overflow = __shfl_sync(DP_FULL, (int)overflow, 0) != 0;
             }
+            __syncwarp();
         }
         // ---- sort by Start + overlap dedupe (mapping.go:590-608); lane 0 ----
         if (lane == 0) {
-            if (nRes > S.resultCap) {
+            if (overflow || nRes > S.resultCap) {
                 atomicOr(&ctr->overflow, 1u);
-                nRes = S.resultCap;
+                if (nRes > S.resultCap) nRes = S.resultCap;
             }
             if (nRes > 1) {
                 for (int i = 1; i < nRes; i++) {  // stable insertion sort (= Go's sort.Sort for n <= 12)
