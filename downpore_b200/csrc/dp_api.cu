@@ -125,6 +125,8 @@ struct Lane {
     HBuf<long long> hRel;
     size_t hOutTotal = 0;
     bool pendingStageTimes = false;
+    const unsigned char* curAscii = nullptr;  // device-visible ASCII of the current sub-batch (device or mapped host)
+    bool curAsciiIsHost = false;
     std::vector<Timer> timers;
     dp_stats stats{};
     int candStride = 0;
@@ -549,6 +551,15 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     cudaStream_t st = W.stream;
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
+        int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 8);
+        CK(cudaEventRecord(W.timers[T_PACK].a, st));
+        dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+                                                       const_cast<unsigned*>(dWords));
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(W.timers[T_PACK].b, st));
+        W.stats.kernel_launches += 1;
+    }
     const int qStride = I.maxWindow + 8;
     DpExtractOut Q;
     Q.wsOff = W.wsOff.p;
@@ -634,6 +645,8 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
 void collect_stage_times(Lane& W) {  // call after a stream synchronize
     if (!W.pendingStageTimes) return;
     float ms;
+    CK(cudaEventElapsedTime(&ms, W.timers[T_PACK].a, W.timers[T_PACK].b));
+    W.stats.ms_pack += ms;
     CK(cudaEventElapsedTime(&ms, W.timers[T_EXTRACT].a, W.timers[T_EXTRACT].b));
     W.stats.ms_extract += ms;
     CK(cudaEventElapsedTime(&ms, W.timers[T_LOOKUP].a, W.timers[T_LOOKUP].b));
@@ -670,6 +683,8 @@ void run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, const
     size_t seedEntries = 0;
     for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
     ensure_window_capacity(M, W, nWin, seedEntries);
+    if (W.curAsciiIsHost)
+        for (size_t i = 0; i < nWin; i++) W.stats.h2d_bytes += wins[i].len + 32;
     CK(cudaMemcpyAsync(W.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, W.stream));
     launch_windows(M, W, nWin, seedEntries, dWords, dWordOff, dReadLen);
     download_windows(W, nWin);
@@ -759,14 +774,8 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
         W.scanTmp.reserve(tmpBytes);
         CK(cub::DeviceScan::ExclusiveSum(W.scanTmp.p, tmpBytes, W.dWordsNeeded.p, W.dWordOff.p, (int)n + 1, st));
     }
-    {
-        int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)M.smCount * 16);
-        CK(cudaEventRecord(W.timers[T_PACK].a, st));
-        dp_pack_kernel<<<blocks, 256, 0, st>>>(dAscii, W.dSeqOff.p, W.dWordOff.p, W.dWords.p, n);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(W.timers[T_PACK].b, st));
-        W.stats.kernel_launches += 3;
-    }
+    W.stats.kernel_launches += 2;
+    W.curAscii = dAscii;
     // ---- round 0 entirely on the device: windows, performMapping stages, Map()'s first decision ----
     const size_t nWin0 = 2 * (size_t)n;
     size_t seedEntries0 = 0;
@@ -781,6 +790,12 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     CK(cudaGetLastError());
     launch_windows(M, W, nWin0, seedEntries0, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
     W.stats.windows += nWinReal - (int64_t)nWin0;  // empty second slots of short reads are not window queries
+    if (W.curAsciiIsHost) {  // bytes the windowed pack pulls over the link: the round-0 windows (+ one word ahead)
+        for (int64_t i = 0; i < n; i++) {
+            long long len = W.hRel.p[i + 1] - W.hRel.p[i];
+            if (len >= minLen) W.stats.h2d_bytes += (len <= 2ll * e) ? len : std::min<long long>(len, 2ll * (e + 32));
+        }
+    }
     W.dStatus.reserve((size_t)n);
     W.dFinN.reserve((size_t)n);
     W.dFinOff.reserve((size_t)n);
@@ -806,8 +821,6 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     collect_stage_times(W);
     {
         float ms;
-        CK(cudaEventElapsedTime(&ms, W.timers[T_PACK].a, W.timers[T_PACK].b));
-        W.stats.ms_pack += ms;
         CK(cudaEventElapsedTime(&ms, W.timers[T_FINISH].a, W.timers[T_FINISH].b));
         W.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
     }
@@ -944,6 +957,7 @@ void add_stats(dp_stats& a, const dp_stats& b) {
     a.chain_cells += b.chain_cells;
     a.mappings += b.mappings;
     a.kernel_launches += b.kernel_launches;
+    a.h2d_bytes += b.h2d_bytes;
 }
 
 Lane& get_lane(dp_mapper& M, size_t idx) {
@@ -1014,10 +1028,15 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     }
     const size_t nSub = cuts.size() - 1;
     const int nLanes = (int)std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1));
-    bool pinned = false;
-    if (hostBases) {
+    // Pinned (or registered) caller memory is read in place through its device mapping; pageable memory is staged.
+    const unsigned char* mappedBase = nullptr;
+    if (hostBases && !getenv("DP_NO_ZEROCOPY")) {
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, hostBases) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        if (cudaPointerGetAttributes(&attr, hostBases) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            void* dptr = nullptr;
+            if (cudaHostGetDevicePointer(&dptr, const_cast<uint8_t*>(hostBases), 0) == cudaSuccess)
+                mappedBase = static_cast<const unsigned char*>(dptr);
+        }
         cudaGetLastError();
     }
     for (int l = 0; l < nLanes; l++) {
@@ -1038,8 +1057,13 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                 if (sI >= nSub) break;
                 int64_t r0 = cuts[sI], r1 = cuts[sI + 1];
                 const unsigned char* dA;
-                if (hostBases) {
-                    upload_ascii(W, hostBases, offsets, r0, r1, pinned);
+                W.curAsciiIsHost = false;
+                if (hostBases && mappedBase) {
+                    dA = mappedBase + offsets[r0];  // the kernels read the caller's pinned buffer in place
+                    W.curAsciiIsHost = true;
+                } else if (hostBases) {
+                    upload_ascii(W, hostBases, offsets, r0, r1, false);
+                    W.stats.h2d_bytes += offsets[r1] - offsets[r0];
                     dA = W.dAscii.p;
                 } else {
                     dA = devBases + offsets[r0];
@@ -1257,8 +1281,8 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     CK(cudaMemcpyAsync(W.dSeqOff.p, seqOff, sizeof(seqOff), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(W.dWordOff.p, wordOff, sizeof(wordOff), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(W.dReadLen.p, rl, sizeof(rl), cudaMemcpyHostToDevice, st));
-    dp_pack_kernel<<<1, 256, 0, st>>>(W.dAscii.p, W.dSeqOff.p, W.dWordOff.p, W.dWords.p, 1);
-    CK(cudaGetLastError());
+    W.curAscii = W.dAscii.p;
+    W.curAsciiIsHost = false;
     DpWindow w;
     w.read = 0;
     w.start = (int)start;

@@ -52,6 +52,73 @@ __global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Windowed pack: only the windows that are queried are ever packed (Map() touches 2..12 windows of `edge` bases per
+// read, never the middle of a long read: mapping/mapping.go:430-487). `ascii` may be device memory or pinned host
+// memory mapped into the device address space: the latter turns the H2D copy into coalesced zero-copy reads of just
+// the queried bytes. One warp per window; per iteration the lanes load 32 consecutive 16-byte aligned blocks
+// (one LDG.128 each, 512 contiguous bytes per warp), neighbours exchange blocks by shuffle, and 31 packed words are
+// written. Each source byte crosses the bus once (+1/31 overlap).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
+                                                              const long long* __restrict__ seqOff,
+                                                              const long long* __restrict__ wordOff,
+                                                              const DpWindow* __restrict__ wins, int nWin,
+                                                              unsigned* __restrict__ words) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nWarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned lane = dp_lane();
+    for (int w = warp; w < nWin; w += nWarps) {
+        DpWindow win = wins[w];
+        if (win.len <= 0) continue;
+        const long long readBase = seqOff[win.read];
+        const long long readLen = seqOff[win.read + 1] - readBase;
+        // packed words covering the window, plus the following word when it still holds bases of the read
+        long long w0 = win.start >> 4;
+        long long w1 = ((long long)win.start + win.len - 1) >> 4;  // last word holding a window base
+        long long wLast = (readLen - 1) >> 4;                      // last word holding a read base
+        if (w1 < wLast) w1++;                                      // k-mer extraction reads one word ahead
+        const long long nWords = w1 - w0 + 1;
+        unsigned* out = words + wordOff[win.read] + w0;
+        const unsigned char* src = ascii + readBase + w0 * 16;     // first byte of word w0
+        const unsigned long long addr = (unsigned long long)src;
+        const unsigned mis = (unsigned)(addr & 15ull);
+        const uint4* blk = (const uint4*)(src - mis);              // aligned block holding the first byte
+        const unsigned char* srcEnd = ascii + readBase + readLen;  // one past the last byte of the read
+        const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)blk)) >> 4;
+        const unsigned q = mis >> 2, sh = (mis & 3) * 8;
+        for (long long g0 = 0; g0 < nWords; g0 += 31) {
+            long long b = g0 + lane;  // aligned block index this lane loads
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b <= lastBlk && b <= nWords) v = __ldg(blk + b);  // never past the block holding the read's last byte
+            uint4 nx;
+            nx.x = __shfl_down_sync(DP_FULL, v.x, 1);
+            nx.y = __shfl_down_sync(DP_FULL, v.y, 1);
+            nx.z = __shfl_down_sync(DP_FULL, v.z, 1);
+            nx.w = __shfl_down_sync(DP_FULL, v.w, 1);
+            // 16 source bytes of word g = bytes [mis, mis+16) of (v, nx)
+            unsigned a0, a1, a2, a3, a4;
+            switch (q) {  // warp-uniform
+                case 0: a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w; a4 = nx.x; break;
+                case 1: a0 = v.y; a1 = v.z; a2 = v.w; a3 = nx.x; a4 = nx.y; break;
+                case 2: a0 = v.z; a1 = v.w; a2 = nx.x; a3 = nx.y; a4 = nx.z; break;
+                default: a0 = v.w; a1 = nx.x; a2 = nx.y; a3 = nx.z; a4 = nx.w; break;
+            }
+            long long g = g0 + lane;
+            if (lane < 31 && g < nWords) {
+                unsigned x0 = __funnelshift_r(a0, a1, sh);
+                unsigned x1 = __funnelshift_r(a1, a2, sh);
+                unsigned x2 = __funnelshift_r(a2, a3, sh);
+                unsigned x3 = __funnelshift_r(a3, a4, sh);
+                unsigned pv = (dp_pack4(x0) << 24) | (dp_pack4(x1) << 16) | (dp_pack4(x2) << 8) | dp_pack4(x3);
+                long long remain = readLen - (w0 + g) * 16;  // bases of the read in this word
+                if (remain < 16) pv &= remain > 0 ? (~0u << (unsigned)(2 * (16 - remain))) : 0u;
+                out[g] = pv;
+            }
+        }
+    }
+}
+
 // packed words (16 bases, MSB first) -> the reference's byte layout (4 bases per byte, MSB first): byte i of the
 // sequence is bits [31-8*(i%4) .. 24-8*(i%4)] of word i/4.
 __global__ void dp_words_to_bytes_kernel(const unsigned* __restrict__ words, unsigned char* __restrict__ out,

@@ -42,13 +42,13 @@ typedef struct dp_mapping {
 
 /* Device-side timings and work counters of the most recent dp_mapper_map_batch* call. */
 typedef struct dp_stats {
-    double ms_total;        /* CUDA-event time, first kernel to last kernel of the call (device work only) */
-    double ms_pack;         /* 2-bit pack kernel */
+    double ms_total;        /* wall time of the call inside the library */
+    double ms_pack;         /* 2-bit pack kernel (only the queried windows are packed) */
     double ms_extract;      /* k-mer scan / seed extraction kernel, summed over rounds */
     double ms_lookup;       /* seed-index lookup (candidate chunks) kernel, summed over rounds */
     double ms_chain;        /* chaining kernel, summed over rounds */
     double ms_host_logic;   /* host wall time spent in the per-read Map() strategy between rounds */
-    double ms_h2d;          /* host->device copy time of reads (0 for the device-resident entry point) */
+    double ms_h2d;          /* host->device staging copies of pageable reads (0 for pinned or device-resident input) */
     int64_t rounds;         /* window-query rounds */
     int64_t windows;        /* performMapping window queries (both strands each) */
     int64_t kmer_lookups;   /* k-mer table gathers issued by the extract kernel */
@@ -60,6 +60,8 @@ typedef struct dp_stats {
     int64_t mappings;       /* mappings returned */
     int64_t kernel_launches;/* kernels launched by the call */
     int64_t bases;          /* sum of read lengths of the call */
+    int64_t h2d_bytes;      /* read bytes that crossed the host->device link (copied, or pulled zero-copy by the
+                               windowed pack kernel when the caller's buffer is pinned) */
 } dp_stats;
 
 /*
@@ -76,7 +78,8 @@ int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, in
 /*
  * Mapper.Map over a batch of reads (mapping/mapping.go:430-487 for each read; replaces the MapWorker goroutine pool
  * of mapping.go:613-619 / commands/map.go:84-86).
- *   bases   : concatenated ASCII reads (host memory; pinned memory is copied without staging)
+ *   bases   : concatenated ASCII reads in host memory. Pinned / registered memory is read in place by the kernels
+ *             (only the queried windows cross the link); pageable memory is staged through pinned buffers
  *   offsets : n_reads+1 byte offsets into `bases`
  *   out     : *out = malloc'ed array of all mappings, grouped per read in input order, each group in the slice order
  *             Map() returns them in
