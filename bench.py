@@ -267,7 +267,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     S = args.steps
     ws = 2 * agg["windows"] / S            # window strands per step
-    bytes_pack = 1.25 * bases_rank
+    bytes_pack = 1.25 * EDGE * agg["windows"] / S  # only the queried windows are packed
     bytes_extract = ws * ((EDGE + 3) // 4) + 4.0 * agg["kmer_lookups"] / S
     bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
     bytes_chain = 8.0 * agg["chain_cells"] / S
