@@ -34,6 +34,15 @@ REF_SEED, READ_SEED = 1, 12
 EDGE = 1000
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -180,7 +189,7 @@ def run_reference(args):
             "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "C++ restatement of the reference (no Go toolchain in this image), mapping phase only"},
             "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -319,11 +328,16 @@ def run_ours(args):
                                 "sample": "first %d reads of the step's batch, mapping phase only" % ns,
                                 "parity_with_gpu_on_sample": parity}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     gm.close()
 
 
 def main():
+    # Keep stdout clean for the one JSON line: native libraries (NCCL prints its version banner) write to fd 1.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -189,3 +189,25 @@ def test_config1_full_parity():
     assert np.array_equal(orow, rows_of(gmaps))
     assert gm.stats()["posting_entries"] == octr["posting_entries"]
     gm.close()
+
+
+def test_large_reference_global_counters():
+    """C > 1536 chunks: the lookup kernel's per-chunk counters live in global memory (the shared-memory path only
+    covers small references); linear reference, 20 kb reads (BASELINE config 3 in miniature)."""
+    ref = synth.reference(3, 16_400_000)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    om = po.Mapper(ref, vals, circular=False)
+    gm = dp.Mapper(ref, vals, circular=False)
+    assert gm.index_info()["num_chunks"] == om.num_chunks > 1536
+    assert np.array_equal(np.sort(om.seed_kmers()), gm.seed_kmers())
+    n, L = 1500, 20_000
+    rd = synth.reads(ref, 13, n, L, circular=False)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    orow, ooff, octr = om.map_batch(rd, offs, threads=os.cpu_count() or 4)
+    gmaps, goff = gm.map_batch(rd, offs)
+    assert np.array_equal(ooff, goff)
+    assert np.array_equal(orow, rows_of(gmaps))
+    st = gm.stats()
+    for key in ("windows", "posting_runs", "posting_entries", "candidates", "chain_cells"):
+        assert st[key] == octr[key], key
+    gm.close()
