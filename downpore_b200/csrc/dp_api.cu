@@ -485,6 +485,8 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
 // ----------------------------------------------------------------------------------------------------------------
 // window rounds
 // ----------------------------------------------------------------------------------------------------------------
+const unsigned kLookupSmemChunks = 24000;  // 16-bit counters: 4 warps x 48 KB of shared memory at most
+
 void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries) {
     const DpIndexDev& I = M.I;
     W.dWins.reserve(nWin);
@@ -518,8 +520,8 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     const size_t tStride = (size_t)I.numChunks + 8;
     W.lsTouched.reserve(lw * tStride);
     W.lsCand.reserve(lw * 2 * tStride);
-    if (I.numChunks > 1536 && !W.lsCountersZeroed) {
-        W.lsCounters.reserve(lw * I.numChunks);
+    if (I.numChunks > kLookupSmemChunks && !W.lsCountersZeroed) {
+        W.lsCounters.reserve(lw * ((I.numChunks + 1) / 2));
         // the kernel keeps the invariant "all counters zero between window strands": clear once
         CK(cudaMemsetAsync(W.lsCounters.p, 0, W.lsCounters.cap * sizeof(unsigned), W.stream));
         W.lsCountersZeroed = true;
@@ -575,7 +577,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                       sizeof(unsigned);
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             M.attrsSet = true;
         }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
@@ -598,9 +600,9 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.cand = W.lsCand.p;
         S.stride = qStride;
         S.tStride = (int)I.numChunks + 8;
-        int inSmem = I.numChunks <= 1536 ? 1 : 0;
+        int inSmem = I.numChunks <= kLookupSmemChunks ? 1 : 0;
         int warpsPerBlock = DP_LWARPS;
-        size_t smem = inSmem ? (size_t)warpsPerBlock * I.numChunks * sizeof(unsigned) : 0;
+        size_t smem = inSmem ? (size_t)warpsPerBlock * ((I.numChunks + 1) / 2) * sizeof(unsigned) : 0;
         int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
                                            (size_t)W.lookupWarps / warpsPerBlock);
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));

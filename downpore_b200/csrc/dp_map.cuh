@@ -170,7 +170,7 @@ struct DpLookupScratch {  // per-warp global scratch for oversized window strand
     unsigned short* order;  // Q6 column-order simulation
     unsigned* touched;      // chunks whose counter left zero [tStride]
     unsigned long long* cand;  // (chunk << 32 | counter) of chunks over the threshold [2*tStride]: list + sort space
-    unsigned* counters;     // [C] per warp when C does not fit shared memory; all zero between window strands
+    unsigned* counters;     // [(C+1)/2] per warp when they do not fit shared memory; all zero between window strands
     int stride;
     int tStride;
 };
@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned C = I.numChunks;
-    unsigned* cnt = countersInSmem ? dp_smem + (size_t)wib * C : S.counters + (size_t)gwarp * C;
-    if (countersInSmem) {  // counters are zero between window strands: clear them once per kernel
-        for (unsigned c = lane; c < C; c += 32) cnt[c] = 0;
+    // per-chunk soft counters, 16 bits each, two per word; zero between window strands (cleared once per kernel)
+    const unsigned cWords = (C + 1) >> 1;
+    unsigned* cnt = countersInSmem ? dp_smem + (size_t)wib * cWords : S.counters + (size_t)gwarp * cWords;
+    if (countersInSmem) {
+        for (unsigned c = lane; c < cWords; c += 32) cnt[c] = 0;
         __syncwarp();
     }
     const size_t so = (size_t)gwarp * S.stride;
@@ -329,24 +331,47 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                 unsigned* touched = tSmall ? shTouched[wib] : S.touched + (size_t)gwarp * S.tStride;
                 unsigned long long* cand = tSmall ? shCand[wib] : S.cand + (size_t)gwarp * 2 * S.tStride;
                 int nTouched = 0;
-                for (unsigned p0 = 0; p0 < total; p0 += 32) {
-                    unsigned p = p0 + lane;
-                    bool owner = false;
-                    unsigned chunk = 0;
-                    if (p < total) {
-                        int lo = 0, hi = nInc;  // largest j with ePre[j] <= p
-                        while (hi - lo > 1) {
-                            int mid = (lo + hi) >> 1;
-                            if (ePre[mid] <= p) lo = mid;
-                            else hi = mid;
+                if (total >= 12u * (unsigned)nInc) {
+                    // long runs: one run at a time, lanes across its postings (coalesced, no search)
+                    for (int j = 0; j < nInc; j++) {
+                        const unsigned off = eOff[j], len = ePre[j + 1] - ePre[j];
+                        for (unsigned p0 = 0; p0 < len; p0 += 32) {
+                            unsigned p = p0 + lane;
+                            bool owner = false;
+                            unsigned chunk = 0;
+                            if (p < len) {
+                                chunk = __ldg(I.seedChunks + off + p);
+                                unsigned sh = (chunk & 1u) * 16u;
+                                unsigned old = atomicAdd(cnt + (chunk >> 1), 1u << sh);
+                                owner = ((old >> sh) & 0xffffu) == 0;
+                            }
+                            unsigned mo = __ballot_sync(DP_FULL, owner);
+                            if (owner) touched[nTouched + __popc(mo & lt)] = chunk;
+                            nTouched += __popc(mo);
                         }
-                        chunk = __ldg(I.seedChunks + eOff[lo] + (p - ePre[lo]));
-                        unsigned old = atomicAdd(cnt + chunk, 1u + ((unsigned)eFirst[lo] << 16));
-                        owner = old == 0;
                     }
-                    unsigned mo = __ballot_sync(DP_FULL, owner);
-                    if (owner) touched[nTouched + __popc(mo & lt)] = chunk;
-                    nTouched += __popc(mo);
+                } else {
+                    // short runs: flatten all postings over the lanes, each finds its run by binary search
+                    for (unsigned p0 = 0; p0 < total; p0 += 32) {
+                        unsigned p = p0 + lane;
+                        bool owner = false;
+                        unsigned chunk = 0;
+                        if (p < total) {
+                            int lo = 0, hi = nInc;  // largest j with ePre[j] <= p
+                            while (hi - lo > 1) {
+                                int mid = (lo + hi) >> 1;
+                                if (ePre[mid] <= p) lo = mid;
+                                else hi = mid;
+                            }
+                            chunk = __ldg(I.seedChunks + eOff[lo] + (p - ePre[lo]));
+                            unsigned sh = (chunk & 1u) * 16u;
+                            unsigned old = atomicAdd(cnt + (chunk >> 1), 1u << sh);
+                            owner = ((old >> sh) & 0xffffu) == 0;
+                        }
+                        unsigned mo = __ballot_sync(DP_FULL, owner);
+                        if (owner) touched[nTouched + __popc(mo & lt)] = chunk;
+                        nTouched += __popc(mo);
+                    }
                 }
                 __syncwarp();
                 cRuns += (unsigned)nInc;
@@ -358,10 +383,12 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                     unsigned chunk = 0, v = 0;
                     if (t < nTouched) {
                         chunk = touched[t];
-                        v = cnt[chunk];
-                        cnt[chunk] = 0;
+                        unsigned sh = (chunk & 1u) * 16u;
+                        v = (cnt[chunk >> 1] >> sh) & 0xffffu;
                     }
-                    bool pass = (int)(v & 0xffffu) >= T;
+                    __syncwarp();  // two lanes may own the two halves of one word: read everything, then clear
+                    if (t < nTouched) atomicAnd(cnt + (chunk >> 1), ~(0xffffu << ((chunk & 1u) * 16u)));
+                    bool pass = (int)v >= T;
                     unsigned mp = __ballot_sync(DP_FULL, pass);
                     if (pass) cand[nCand + __popc(mp & lt)] = ((unsigned long long)chunk << 32) | v;
                     nCand += __popc(mp);
@@ -458,11 +485,24 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                         }
                         pass = (mp >> lane) & 1;
                     }
-                    if (pass) {
-                        int idx = nCandOut + __popc(mp & lt);
-                        if (idx < candStride) {
-                            outChunk[idx] = c;
-                            outDist[idx] = (unsigned short)((v >> 16) + nAllDistinct);
+                    // IntSet.CountIntersectionTo's operand (mapping.go:520-523): DISTINCT query seeds present in the
+                    // chunk, counted on demand for the few surviving candidates
+                    unsigned todo2 = mp;
+                    while (todo2) {
+                        int l = __ffs(todo2) - 1;
+                        todo2 &= todo2 - 1;
+                        unsigned cc = __shfl_sync(DP_FULL, c, l);
+                        int distinct = 0;
+                        for (int j0 = 0; j0 < nInc; j0 += 32) {
+                            int j = j0 + (int)lane;
+                            bool in = false;
+                            if (j < nInc && eFirst[j]) in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
+                            distinct += __popc(__ballot_sync(DP_FULL, in));
+                        }
+                        int idx = nCandOut + __popc(mp & ((1u << l) - 1));
+                        if (lane == 0 && idx < candStride) {
+                            outChunk[idx] = cc;
+                            outDist[idx] = (unsigned short)(distinct + nAllDistinct);
                         }
                     }
                     nCandOut += __popc(mp);
