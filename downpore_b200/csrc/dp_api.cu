@@ -554,7 +554,10 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
     {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
-        int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 8);
+        // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the other
+        // lane's compute kernels stay resident beside it
+        int perSm = W.curAsciiIsHost ? 2 : 8;
+        int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         CK(cudaEventRecord(W.timers[T_PACK].a, st));
         dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
                                                        const_cast<unsigned*>(dWords));
