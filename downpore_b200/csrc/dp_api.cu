@@ -574,7 +574,9 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     Q.cursor = W.cursor.p + CUR_SEEDS;
     const int maskWords = (I.maxWindow + 31) / 32 + 1;
     {
-        const int warpsPerBlock = 32;  // one persistent 1024-thread CTA per SM
+        // one persistent CTA per SM. When the other lane may be pulling reads over PCIe, every compute kernel leaves
+        // a quarter of the SM's registers and thread slots free so that the pull kernel stays resident beside it.
+        const int warpsPerBlock = W.curAsciiIsHost ? 24 : 32;
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount);
         size_t smem = ((I.filterBits ? ((size_t)1 << (I.filterBits - 5)) : 0) + (size_t)warpsPerBlock * 2 * maskWords) *
                       sizeof(unsigned);
@@ -585,7 +587,8 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
         CK(cudaEventRecord(W.timers[T_EXTRACT].a, st));
-        dp_extract_kernel<<<blocks, 1024, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords, W.dCtr.p);
+        dp_extract_kernel<<<blocks, 32 * warpsPerBlock, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords,
+                                                               W.dCtr.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(W.timers[T_EXTRACT].b, st));
     }
@@ -607,7 +610,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int warpsPerBlock = DP_LWARPS;
         size_t smem = inSmem ? (size_t)warpsPerBlock * ((I.numChunks + 1) / 2) * sizeof(unsigned) : 0;
         int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
-                                           (size_t)W.lookupWarps / warpsPerBlock);
+                                           (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
         dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, W.candN.p, W.candChunk.p,
                                                     W.candDistinct.p, W.candStride, W.dCtr.p);
@@ -633,7 +636,8 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.chainCap = M.chainCap;
         S.resultCap = M.resultCap;
         int warpsPerBlock = 4;
-        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)W.chainWarps / 4);
+        int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock,
+                                           (size_t)M.smCount * (W.curAsciiIsHost ? 4 : 6));
         CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
         dp_chain_kernel<<<blocks, 128, 0, st>>>(I, W.dWins.p, dReadLen, (int)nWin, Q, W.candN.p, W.candChunk.p,
                                                 W.candDistinct.p, W.candStride, S, W.outN.p, W.outOff.p, W.outMaps.p,

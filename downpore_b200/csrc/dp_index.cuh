@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __res
 // (one LDG.128 each, 512 contiguous bytes per warp), neighbours exchange blocks by shuffle, and 31 packed words are
 // written. Each source byte crosses the bus once (+1/31 overlap).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
+__global__ void __launch_bounds__(256, 8) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
                                                               const long long* __restrict__ seqOff,
                                                               const long long* __restrict__ wordOff,
                                                               const DpWindow* __restrict__ wins, int nWin,

@@ -27,7 +27,7 @@ def main():
         print({k: (round(v, 2) if isinstance(v, float) else v) for k, v in st.items()})
     for it in range(2):
         t = time.time(); maps, off = gm.map_batch_ptr(pinned.data_ptr(), offs); dt = time.time() - t
-        print('pinned host: %.1f ms -> %.2f Gbp/s' % (dt * 1e3, n * L / dt / 1e9), 'h2d ms', round(gm.stats()['ms_h2d'], 1))
+        print('pinned host: %.1f ms -> %.2f Gbp/s' % (dt * 1e3, n * L / dt / 1e9), {k: (round(v, 2) if isinstance(v, float) else v) for k, v in gm.stats().items() if k.startswith('ms_') or k in ('h2d_bytes', 'rounds')})
     t = time.time(); maps, off = gm.map_batch(rd, offs); dt = time.time() - t
     print('pageable host: %.1f ms -> %.2f Gbp/s' % (dt * 1e3, n * L / dt / 1e9), 'h2d ms', round(gm.stats()['ms_h2d'], 1))
 
