@@ -20,6 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdownpore_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
+HOST_PATH = os.path.join(_HERE, "..", "tools", "dp_map")  # the `downpore map` host over the C ABI (tools/dp_map.cpp)
 
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
@@ -45,9 +46,11 @@ def build(force=False):
     """Compile csrc/ for sm_100a into libdownpore_b200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp"))]
     srcs.append(os.path.join(_HERE, "..", "include", "downpore_b200.h"))
+    srcs.append(os.path.join(_HERE, "..", "tools", "dp_map.cpp"))
     newest = max(os.path.getmtime(s) for s in srcs)
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
-        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+    stale = [p for p in (LIB_PATH, HOST_PATH) if not os.path.exists(p) or os.path.getmtime(p) < newest]
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC, "all"], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -57,6 +60,8 @@ _SIGNATURES = {
     "dp_last_error": (ctypes.c_char_p, []),
     "dp_version": (ctypes.c_char_p, []),
     "dp_free": (None, [c_vp]),
+    "dp_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
+    "dp_host_free": (None, [c_vp]),
     "dp_mapper_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "dp_mapper_destroy": (None, [c_vp]),

@@ -437,14 +437,16 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
         M.postPos.reserve(1);
         CK(cudaMemsetAsync(M.postOff.p, 0, ((size_t)numSeeds + 2) * sizeof(unsigned), st));
     }
-    // ---- shared-memory prefilter for the extract kernel: worthwhile while seeds are sparse in it ----
+    // ---- shared-memory prefilter for the extract kernel: the seed table OR-folded to 2^bits k-mer prefixes (exact when
+    //      2k <= 20); worthwhile while at most half of its bits are set ----
     M.filterBits = 0;
     {
-        const int bits = 20;  // 128 KiB: fits one CTA per SM next to the ballot masks
-        if ((unsigned long long)numSeeds * 4 <= (1ull << bits)) {
-            M.filter.reserve((size_t)1 << (bits - 5));
-            CK(cudaMemsetAsync(M.filter.p, 0, sizeof(unsigned) << (bits - 5), st));
-            dp_filter_build_kernel<<<div_up(nTable, 256), 256, 0, st>>>(M.table.p, nTable, bits, M.filter.p);
+        const int bits = std::min(20, 2 * k);  // 128 KiB at most: one CTA per SM next to the hit masks
+        if (2 * k <= 20 || (unsigned long long)numSeeds * 2 <= (1ull << bits)) {
+            size_t fw = (((size_t)1 << bits) + 31) / 32;
+            M.filter.reserve(fw);
+            CK(cudaMemsetAsync(M.filter.p, 0, fw * sizeof(unsigned), st));
+            dp_filter_build_kernel<<<div_up(nTable, 256), 256, 0, st>>>(M.table.p, nTable, k, bits, M.filter.p);
             CK(cudaGetLastError());
             M.filterBits = bits;
         }
@@ -572,14 +574,17 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     Q.qSeed = W.qSeed.p;
     Q.qPos = W.qPos.p;
     Q.cursor = W.cursor.p + CUR_SEEDS;
-    const int maskWords = (I.maxWindow + 31) / 32 + 1;
+    const int maskWords = ((I.maxWindow + 1023) / 1024) * 32;  // 32 lanes x blocks of 1024 positions
     {
         // one persistent CTA per SM. When the other lane may be pulling reads over PCIe, every compute kernel leaves
         // a quarter of the SM's registers and thread slots free so that the pull kernel stays resident beside it.
-        const int warpsPerBlock = W.curAsciiIsHost ? 24 : 32;
+        int warpsPerBlock = W.curAsciiIsHost ? 24 : 32;
+        const size_t fWords = I.filterBits ? ((((size_t)1 << I.filterBits) + 31) / 32 + 3) / 4 * 4 : 0;
+        const size_t perWarp = (size_t)2 * maskWords * sizeof(unsigned);
+        const size_t room = 200 * 1024 - fWords * sizeof(unsigned);
+        if (perWarp * warpsPerBlock > room) warpsPerBlock = (int)std::max<size_t>(1, room / perWarp);  // very long windows
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount);
-        size_t smem = ((I.filterBits ? ((size_t)1 << (I.filterBits - 5)) : 0) + (size_t)warpsPerBlock * 2 * maskWords) *
-                      sizeof(unsigned);
+        size_t smem = fWords * sizeof(unsigned) + perWarp * warpsPerBlock;
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1134,8 +1139,19 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
 extern "C" {
 
 const char* dp_last_error(void) { return g_err.c_str(); }
-const char* dp_version(void) { return "downpore_b200 0.1 (sm_100a)"; }
+const char* dp_version(void) { return "downpore_b200 0.2 (sm_100a)"; }
 void dp_free(void* p) { free(p); }
+
+int dp_host_alloc(void** out, size_t bytes) {
+    API_TRY
+    if (!out) throw std::runtime_error("null argument");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    API_CATCH
+}
+
+void dp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 
 int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, int k, const double* kmer_values,
                      int seed_rate, int edge_size, int chunk_size, int device, dp_mapper** out) {

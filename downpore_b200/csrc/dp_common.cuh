@@ -33,7 +33,7 @@ struct DpIndexDev {
     const unsigned* postOff;     // [S+1]  every occurrence of each seed, sorted by (chunk, scan position)
     const unsigned* postChunk;   // [postOff[S]]
     const int* postPos;          // [postOff[S]]
-    const unsigned* filter;      // 2^filterBits-bit one-hash Bloom filter over seed k-mers (0 bits = none)
+    const unsigned* filter;      // 2^filterBits bits: bit p = "some seed k-mer has the filterBits-bit prefix p" (0 = none)
     int filterBits;
     const unsigned* chunkOff;    // [C+1]
     const int* chunkPos;         // scan positions
@@ -107,7 +107,8 @@ __device__ __forceinline__ bool dp_seed_lookup(const uint2* __restrict__ table, 
     *rank = e.y + __popc(e.x & (bit - 1));
     return (e.x & bit) != 0;
 }
-__device__ __forceinline__ unsigned dp_filter_hash(unsigned kmer, int bits) { return (kmer * 2654435761u) >> (32 - bits); }
+// prefix filter: a k-mer (low 2k bits) maps to its top `bits` bits (bits <= 2k)
+__device__ __forceinline__ unsigned dp_filter_hash(unsigned kmer, int k, int bits) { return kmer >> (2 * k - bits); }
 __device__ __forceinline__ bool dp_seed_flag(const uint2* __restrict__ table, unsigned kmer) {
     return (__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u;
 }

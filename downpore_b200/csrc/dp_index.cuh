@@ -285,8 +285,8 @@ __global__ void dp_posting_all_kernel(const unsigned long long* __restrict__ key
     }
 }
 
-// one-hash Bloom filter over the seed k-mers (shared-memory prefilter of the extract kernel)
-__global__ void dp_filter_build_kernel(const uint2* __restrict__ table, long long nTable, int bits,
+// prefix filter over the seed k-mers (shared-memory prefilter of the extract kernel)
+__global__ void dp_filter_build_kernel(const uint2* __restrict__ table, long long nTable, int k, int bits,
                                        unsigned* __restrict__ filter) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nTable) return;
@@ -294,7 +294,7 @@ __global__ void dp_filter_build_kernel(const uint2* __restrict__ table, long lon
     while (f) {
         int b = __ffs(f) - 1;
         f &= f - 1;
-        unsigned h = dp_filter_hash((unsigned)(w * 32 + b), bits);
+        unsigned h = dp_filter_hash((unsigned)(w * 32 + b), k, bits);
         atomicOr(filter + (h >> 5), 1u << (h & 31));
     }
 }

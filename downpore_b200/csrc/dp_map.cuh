@@ -7,11 +7,15 @@
 // Stage 1 — seed extraction: SeedIndex.NewSeedSequence on the window and on its reverse complement
 // (seeds/seeds.go:33-50; the asm scans sequence/asm_amd64.s:81-394).
 //
-// One warp per window. Iteration t looks at forward k-mer positions j = 32t + lane: the k-mer comes from two packed
-// words and a funnel shift, its reverse complement from brev; both are looked up in the 8-byte {flags, rank} table.
-// The reverse-complement strand visits the same positions backwards (rc position = L-k-j), so a single pass serves
-// both strands. Pass 1 stores the two ballot masks per iteration in shared memory and counts; one atomicAdd
-// allocates the window's slice of the compact output; pass 2 re-gathers only the hits and writes them in order.
+// One warp per window, persistent CTAs (one per SM) that keep a prefix filter of the seed table in shared memory.
+// The window is cut into blocks of 1024 forward k-mer positions; inside a block every lane owns 32 CONSECUTIVE
+// positions, so its 32+k-1 bases live in three registers (two coalesced loads, two shuffles, three funnel shifts)
+// and every k-mer of either strand is one funnel shift away:
+//   pass 1 (fully unrolled, no global memory): both strands' k-mers -> filter bit -> two 32-bit candidate masks;
+//   pass A: only the filter positives (~6 %) gather the exact flag word from the L2-resident table -> hit masks;
+//   one atomicAdd allocates the window's slice of the compact output;
+//   pass B: the hits gather {flags, rank} once more and write (seed rank, scan position) in scan order.
+// The reverse-complement strand visits the same positions backwards (rc position = L-k-j), so one pass serves both.
 //
 // Scan position = visit index of the reference's asm scan, which equals the base offset except for the raw-sequence
 // quirks (Q2): an un-sliced read with len%4==0 loses its last four bases on the forward strand, and on the
@@ -25,115 +29,215 @@ struct DpExtractOut {
     unsigned long long* cursor;  // bump allocator over qSeed/qPos
 };
 
+// reverse complement of 16 packed bases (first base in the top bits)
+__device__ __forceinline__ unsigned dp_revcomp16(unsigned w) {
+    unsigned y = __brev(~w);
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
+// The 48 bases a lane owns in one block: fwd a0:a1:a2 (first base on top), and their reverse complement pre-shifted
+// so that the reverse complement of the k-mer at lane position i starts at base 32-i of r0:r1:r2.
+struct DpLaneBases {
+    unsigned a0, a1, a2, r0, r1, r2;
+};
+
+__device__ __forceinline__ DpLaneBases dp_lane_bases(const unsigned* __restrict__ words, long long firstBase, bool live,
+                                                     int k, unsigned lane) {
+    // words g..g+3 of the lane; g advances by two per lane, so the upper pair is the next lane's lower pair
+    // (`live`: this lane or its predecessor owns a visited position, so its words lie inside the packed window)
+    unsigned w0 = 0, w1 = 0, w2, w3;
+    const unsigned* p = words + (firstBase >> 4);
+    if (live) {
+        w0 = __ldg(p);
+        w1 = __ldg(p + 1);
+    }
+    w2 = __shfl_down_sync(DP_FULL, w0, 1);
+    w3 = __shfl_down_sync(DP_FULL, w1, 1);
+    if (lane == 31) {
+        w2 = live ? __ldg(p + 2) : 0u;
+        w3 = live ? __ldg(p + 3) : 0u;
+    }
+    const unsigned sh = ((unsigned)firstBase & 15u) * 2u;
+    DpLaneBases B;
+    B.a0 = __funnelshift_l(w1, w0, sh);
+    B.a1 = __funnelshift_l(w2, w1, sh);
+    B.a2 = __funnelshift_l(w3, w2, sh);
+    const unsigned c0 = dp_revcomp16(B.a2), c1 = dp_revcomp16(B.a1), c2 = dp_revcomp16(B.a0);
+    const unsigned rs = (unsigned)(16 - k) * 2u;  // k <= 15
+    B.r0 = __funnelshift_l(c1, c0, rs);
+    B.r1 = __funnelshift_l(c2, c1, rs);
+    B.r2 = c2 << rs;
+    return B;
+}
+
+// k-mer (top-aligned in 32 bits) at lane position i, forward strand / reverse complement; i may be a run-time value
+__device__ __forceinline__ unsigned dp_fwd_at(const DpLaneBases& B, unsigned i) {
+    return __funnelshift_l(i < 16 ? B.a1 : B.a2, i < 16 ? B.a0 : B.a1, 2u * i);
+}
+__device__ __forceinline__ unsigned dp_rc_at(const DpLaneBases& B, unsigned i) {
+    // base 32-i: i == 0 -> r2 itself; 1..16 -> inside r1; 17..31 -> inside r0; shift = 2*((32-i) & 15)
+    if (i == 0) return B.r2;
+    return __funnelshift_l(i <= 16 ? B.r2 : B.r1, i <= 16 ? B.r1 : B.r0, (64u - 2u * i));
+}
+
 __global__ void __launch_bounds__(1024, 1) dp_extract_kernel(DpIndexDev I, const unsigned* __restrict__ readWords,
                                                              const long long* __restrict__ readWordOff,
                                                              const DpWindow* __restrict__ wins, int nWin,
                                                              DpExtractOut O, int maskWords,
                                                              DpCounters* __restrict__ ctr) {
-    // Persistent CTAs, one per SM: [ Bloom filter over the seed k-mers | per-warp ballot masks ].
-    // The filter answers ~94 % of the k-mer lookups from shared memory; only its positives gather the L2-resident table.
+    // shared memory: [ prefix filter over the seed k-mers | per-warp hit masks: maskWords x {fwd, rc} ]
     extern __shared__ unsigned dp_smem[];
     const unsigned lane = dp_lane();
-    const unsigned lt = dp_lanemask_lt();
     const int warpInBlock = threadIdx.x >> 5;
     const int fBits = I.filterBits;
-    const unsigned fWords = fBits ? (1u << (fBits - 5)) : 0u;
+    const unsigned fWords = fBits ? ((1u << fBits) + 31u) >> 5 : 0u;
+    const unsigned fWordsPad = (fWords + 3u) & ~3u;
     const unsigned* filt = dp_smem;
     if (fBits) {
-        const uint4* src = reinterpret_cast<const uint4*>(I.filter);
-        uint4* dst = reinterpret_cast<uint4*>(dp_smem);
-        for (unsigned i = threadIdx.x; i < fWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (unsigned i = threadIdx.x; i < fWords; i += blockDim.x) dp_smem[i] = __ldg(I.filter + i);
         __syncthreads();
     }
-    unsigned* mF = dp_smem + fWords + (size_t)warpInBlock * 2 * maskWords;
+    unsigned* mF = dp_smem + fWordsPad + (size_t)warpInBlock * 2 * maskWords;
     unsigned* mR = mF + maskWords;
     const int k = I.k;
+    const unsigned kShift = 32u - 2u * (unsigned)k;
+    const unsigned fShift = 32u - (unsigned)fBits;  // top-aligned k-mer -> filter bit index
+    const uint2* __restrict__ table = I.table;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nWarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long lookups = 0, seeds = 0;
     for (int w = warp; w < nWin; w += nWarps) {
         DpWindow win = wins[w];
-        const unsigned* words = readWords + readWordOff[win.read];
         const int L = win.len;
+        if (L <= 0) {  // empty second slot of a short read
+            if (lane == 0) {
+                O.wsOff[2 * w] = 0;
+                O.wsN[2 * w] = 0;
+                O.wsOff[2 * w + 1] = 0;
+                O.wsN[2 * w + 1] = 0;
+            }
+            continue;
+        }
+        const unsigned* words = readWords + readWordOff[win.read];
         const bool q2 = win.whole && ((L & 3) == 0);
         const int nJ = L - k + 1 - (q2 ? 4 : 0);  // forward positions 0..nJ-1 are visited by both strands
-        int nF = 0, nR = 0;
-        int nIter = (nJ + 31) >> 5;
-        for (int t = 0; t < nIter; t++) {
-            int j = t * 32 + (int)lane;
-            bool hf = false, hr = false;
-            if (j < nJ) {
-                unsigned kmer = dp_kmer_at(words, (long long)win.start + j, k);
-                unsigned rck = dp_revcomp(kmer, k);
-                if (fBits) {
-                    unsigned h1 = dp_filter_hash(kmer, fBits), h2 = dp_filter_hash(rck, fBits);
-                    hf = (filt[h1 >> 5] >> (h1 & 31)) & 1u;
-                    hr = (filt[h2 >> 5] >> (h2 & 31)) & 1u;
-                    if (hf) hf = dp_seed_flag(I.table, kmer);
-                    if (hr) hr = dp_seed_flag(I.table, rck);
-                } else {
-                    hf = dp_seed_flag(I.table, kmer);
-                    hr = dp_seed_flag(I.table, rck);
+        const int nBlk = (nJ + 1023) >> 10;
+        unsigned cnt = 0;  // per lane: forward hits | rc hits << 16, over all blocks
+        for (int b = 0; b < nBlk; b++) {
+            const int pb = (b << 10) + ((int)lane << 5);  // first forward position of this lane
+            const int nValid = min(32, max(0, nJ - pb));
+            DpLaneBases B = dp_lane_bases(words, (long long)win.start + pb, pb < nJ + 32, k, lane);
+            unsigned fm, rm;
+            if (fBits) {
+                fm = 0;
+                rm = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    unsigned x = i < 16 ? __funnelshift_l(B.a1, B.a0, 2 * i) : __funnelshift_l(B.a2, B.a1, 2 * (i - 16));
+                    unsigned y = i == 0 ? B.r2
+                                        : (i <= 16 ? __funnelshift_l(B.r2, B.r1, 2 * (16 - i))
+                                                   : __funnelshift_l(B.r1, B.r0, 2 * (32 - i)));
+                    unsigned hx = x >> fShift, hy = y >> fShift;
+                    unsigned bx = __funnelshift_r(filt[hx >> 5], 0u, hx) & 1u;
+                    unsigned by = __funnelshift_r(filt[hy >> 5], 0u, hy) & 1u;
+                    fm |= bx << i;
+                    rm |= by << i;
+                }
+                const unsigned valid = nValid >= 32 ? 0xffffffffu : ((1u << nValid) - 1u);
+                fm &= valid;
+                rm &= valid;
+            } else {
+                fm = rm = nValid >= 32 ? 0xffffffffu : ((1u << nValid) - 1u);
+            }
+            // pass A: exact flags for the filter positives
+            unsigned hf = 0, hr = 0;
+            while (fm | rm) {
+                if (fm) {
+                    unsigned i = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                    hf |= ((__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u) << i;
+                }
+                if (rm) {
+                    unsigned i = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    unsigned kmer = dp_rc_at(B, i) >> kShift;
+                    hr |= ((__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u) << i;
                 }
             }
-            unsigned bf = __ballot_sync(DP_FULL, hf);
-            unsigned br = __ballot_sync(DP_FULL, hr);
-            if (lane == 0) {
-                mF[t] = bf;
-                mR[t] = br;
-            }
-            nF += __popc(bf);
-            nR += __popc(br);
+            mF[(b << 5) + lane] = hf;
+            mR[(b << 5) + lane] = hr;
+            cnt += __popc(hf) | (__popc(hr) << 16);
         }
         __syncwarp();
+        unsigned tot = cnt;
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(DP_FULL, tot, d);
+        const int nF = tot & 0xffff, nR = tot >> 16;
         // Q2 on the rc strand: its first visited k-mer (forward position nJ-1) is visited twice
         int dup = 0;
-        if (q2 && nJ > 0) dup = (mR[(nJ - 1) >> 5] >> ((nJ - 1) & 31)) & 1;
+        if (q2) dup = (mR[(nJ - 1) >> 5] >> ((nJ - 1) & 31)) & 1;
         unsigned base = 0;
-        if (lane == 0) base = (unsigned)atomicAdd(O.cursor, (unsigned long long)(nF + nR + dup));
-        base = __shfl_sync(DP_FULL, base, 0);
         if (lane == 0) {
+            base = (unsigned)atomicAdd(O.cursor, (unsigned long long)(nF + nR + dup));
             O.wsOff[2 * w] = base;
             O.wsN[2 * w] = nF;
             O.wsOff[2 * w + 1] = base + nF;
             O.wsN[2 * w + 1] = nR + dup;
         }
+        base = __shfl_sync(DP_FULL, base, 0);
         const unsigned baseR = base + nF;
         const int rcShift = q2 ? 3 : 0;  // rc scan position = (L-k-j) - rcShift
-        int cumF = 0, cumR = 0;
-        for (int t = 0; t < nIter; t++) {
-            unsigned bf = mF[t], br = mR[t];
-            if ((bf | br) != 0) {
-                int j = t * 32 + (int)lane;
-                bool hf = (bf >> lane) & 1, hr = (br >> lane) & 1;
-                if (hf | hr) {
-                    unsigned kmer = dp_kmer_at(words, (long long)win.start + j, k);
-                    unsigned rank;
+        // pass B: ranks of the hits, written in scan order (forward ascending, rc descending in j)
+        unsigned blockBase = 0;  // hits of earlier blocks: fwd | rc << 16
+        for (int b = 0; b < nBlk; b++) {
+            unsigned hf = mF[(b << 5) + lane], hr = mR[(b << 5) + lane];
+            const unsigned mine = __popc(hf) | (__popc(hr) << 16);
+            unsigned incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned y = __shfl_up_sync(DP_FULL, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            const unsigned before = blockBase + incl - mine;
+            blockBase += __shfl_sync(DP_FULL, incl, 31);
+            if (__any_sync(DP_FULL, (hf | hr) != 0)) {
+                const int pb = (b << 10) + ((int)lane << 5);
+                DpLaneBases B = dp_lane_bases(words, (long long)win.start + pb, pb < nJ + 32, k, lane);
+                unsigned idxF = base + (before & 0xffff);
+                int below = (int)(before >> 16);  // rc hits at smaller forward positions
+                while (hf | hr) {
                     if (hf) {
-                        dp_seed_lookup(I.table, kmer, &rank);
-                        unsigned idx = base + cumF + __popc(bf & lt);
-                        O.qSeed[idx] = rank;
-                        O.qPos[idx] = j;
+                        unsigned i = __ffs(hf) - 1;
+                        hf &= hf - 1;
+                        unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                        uint2 e = __ldg(table + (kmer >> 5));
+                        O.qSeed[idxF] = e.y + __popc(e.x & ((1u << (kmer & 31)) - 1u));
+                        O.qPos[idxF] = pb + (int)i;
+                        idxF++;
                     }
                     if (hr) {
-                        dp_seed_lookup(I.table, dp_revcomp(kmer, k), &rank);
-                        int below = cumR + __popc(br & lt);        // rc hits at smaller forward positions
-                        unsigned idx = baseR + dup + (nR - 1 - below);  // rc order is descending in j
+                        unsigned i = __ffs(hr) - 1;
+                        hr &= hr - 1;
+                        unsigned kmer = dp_rc_at(B, i) >> kShift;
+                        uint2 e = __ldg(table + (kmer >> 5));
+                        unsigned rank = e.y + __popc(e.x & ((1u << (kmer & 31)) - 1u));
+                        const int j = pb + (int)i;
+                        unsigned idx = baseR + dup + (unsigned)(nR - 1 - below);
                         O.qSeed[idx] = rank;
                         O.qPos[idx] = (L - k - j) - rcShift;
                         if (dup && j == nJ - 1) {  // the double visit: scan positions 0 and 1
                             O.qSeed[baseR] = rank;
                             O.qPos[baseR] = 0;
                         }
+                        below++;
                     }
                 }
-                cumF += __popc(bf);
-                cumR += __popc(br);
             }
         }
         __syncwarp();
-        lookups += 2ull * (unsigned)(nJ > 0 ? nJ : 0) + (q2 ? 1u : 0u);  // Q2: the rc scan visits one k-mer twice
-        seeds += (unsigned)(nF + nR + dup);
+        if (lane == 0) {
+            lookups += 2ull * (unsigned)nJ + (q2 ? 1u : 0u);  // Q2: the rc scan visits one k-mer twice
+            seeds += (unsigned)(nF + nR + dup);
+        }
     }
     if (lane == 0 && (lookups | seeds)) {
         atomicAdd(&ctr->kmer_lookups, lookups);

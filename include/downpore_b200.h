@@ -21,6 +21,7 @@
 #ifndef DOWNPORE_B200_H
 #define DOWNPORE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -123,6 +124,14 @@ int dp_pack(const uint8_t* ascii, int64_t len, uint8_t* out, int device);
 
 /* sequtil.KmerOccurrences (util/sequtil/kmers.go:34-69) for one record: counts[4^k] += occurrences. */
 int dp_kmer_counts(const uint8_t* ascii, int64_t len, int k, uint64_t* counts, int device);
+
+/*
+ * Page-locked host memory for read batches (what a cgo host passes as `bases`): dp_mapper_map_batch reads such a
+ * buffer in place from the device (zero-copy pull of the queried windows), so a host that fills batches into
+ * dp_host_alloc'ed memory never pays a staging copy. Portable across devices. Release with dp_host_free.
+ */
+int dp_host_alloc(void** out, size_t bytes);
+void dp_host_free(void* p);
 
 void dp_mapper_destroy(dp_mapper* m);
 void dp_free(void* p);

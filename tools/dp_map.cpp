@@ -1,0 +1,498 @@
+// dp_map — C++ host of `downpore map` over the downpore_b200 C ABI (include/downpore_b200.h).
+//
+// Stands where the reference's Go host stands (commands/map.go:33-116, downpore.go:34-51, sequence/seqio.go:188-267):
+// same arguments, aliases and defaults, same record parsing rules, same PAF records and stderr counters. The Go
+// toolchain is absent from the build image, so this is the host the tests and timings drive; a Go maintainer would
+// bind the same symbols through cgo. All mapping work happens on the GPU behind the ABI: this file
+// only reads files, batches reads and prints.
+//
+//   dp_map -input reads.fasta -reference ref.fasta [-circular true] [-k 11] [-query_size 1000] [-min_length 500]
+//          [-chunk_size 10000] [-seed_rate 40] [-num_workers 4]
+//
+// Environment (the flag surface stays the reference's): DOWNPORE_GPUS = comma separated device ordinals (default 0),
+// DOWNPORE_BATCH / DOWNPORE_BATCH_BYTES = reads / bytes per dp_mapper_map_batch call (default 131072 / 1.5 GiB), DOWNPORE_STATS=1 prints stage timings.
+// Output order: records grouped per read in input order (the reference prints in goroutine completion order).
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../include/downpore_b200.h"
+
+namespace {
+
+[[noreturn]] void fatal(const std::string& msg) {
+    fprintf(stderr, "%s\n", msg.c_str());
+    exit(1);
+}
+
+// ---- file access --------------------------------------------------------------------------------------------------
+struct MappedFile {
+    const unsigned char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    explicit MappedFile(const std::string& path) {
+        fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) fatal("open " + path + ": " + strerror(errno));
+        struct stat st;
+        if (fstat(fd, &st) != 0) fatal("stat " + path);
+        n = (size_t)st.st_size;
+        if (n) {
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) fatal("mmap " + path);
+            madvise(m, n, MADV_SEQUENTIAL);
+            p = (const unsigned char*)m;
+        }
+    }
+    ~MappedFile() {
+        if (p) munmap((void*)p, n);
+        if (fd >= 0) close(fd);
+    }
+};
+
+// ---- record reader: the first-pass rules of readFasta (sequence/seqio.go:188-267) ----------------------------------
+// One line per sequence. The first line is a header; a later line is a sequence iff its first byte is in 'A'..'T';
+// a record is kept iff its line length including the newline is >= min_length; the sequence is the line minus its last
+// byte (also when the final line has no newline); the name is the previous header without its first byte, trimmed.
+// A leading '@' switches to FASTQ: after each sequence line a '+' line and a quality line follow.
+struct Record {
+    const unsigned char* seq;
+    size_t len;
+    const unsigned char* name;
+    size_t nameLen;
+};
+
+class RecordReader {
+public:
+    RecordReader(const unsigned char* p, size_t n, long long minLength) : p_(p), n_(n), minLength_(minLength) {
+        size_t len;
+        bool eof;
+        const unsigned char* line = next_line(len, eof);
+        if (!line || eof) {
+            done_ = true;
+            return;
+        }
+        if (line[0] == '@') fastq_ = true;
+        set_name(line, len);
+    }
+    bool next(Record& r) {
+        while (!done_) {
+            size_t len;
+            bool eof;
+            const unsigned char* line = next_line(len, eof);
+            if (!line || len == 0) {
+                done_ = true;
+                return false;
+            }
+            bool have = false;
+            if (line[0] >= 'A' && line[0] <= 'T') {
+                if ((long long)len >= minLength_) {
+                    r.seq = line;
+                    r.len = len - 1;
+                    r.name = name_;
+                    r.nameLen = nameLen_;
+                    have = true;
+                }
+                if (fastq_) {
+                    size_t l2;
+                    bool e2;
+                    const unsigned char* plus = next_line(l2, e2);
+                    if (!plus || e2 || plus[0] != '+') fatal("Invalid fastq format (on + line)");
+                    next_line(l2, e2);  // quality line; the loop's err is the '+' line's (nil) from here on
+                    eof = false;
+                }
+            } else if (line[0] == '@') {
+                fastq_ = true;
+                set_name(line, len);
+            } else {
+                set_name(line, len);
+            }
+            if (eof) done_ = true;
+            if (have) return true;
+        }
+        return false;
+    }
+
+private:
+    const unsigned char* next_line(size_t& len, bool& eof) {  // bufio.ReadBytes('\n'): the line including its '\n'
+        if (pos_ >= n_) {
+            len = 0;
+            eof = true;
+            return nullptr;
+        }
+        const unsigned char* s = p_ + pos_;
+        const void* nl = memchr(s, '\n', n_ - pos_);
+        if (nl) {
+            len = (size_t)((const unsigned char*)nl - s) + 1;
+            eof = false;
+        } else {
+            len = n_ - pos_;
+            eof = true;
+        }
+        pos_ += len;
+        return s;
+    }
+    void set_name(const unsigned char* line, size_t len) {  // strings.TrimSpace(string(line[1:]))
+        const unsigned char* a = line + 1;
+        const unsigned char* b = line + len;
+        auto sp = [](unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); };
+        while (a < b && sp(*a)) a++;
+        while (b > a && sp(b[-1])) b--;
+        name_ = a;
+        nameLen_ = (size_t)(b - a);
+    }
+    const unsigned char* p_;
+    size_t n_;
+    long long minLength_;
+    size_t pos_ = 0;
+    bool fastq_ = false, done_ = false;
+    const unsigned char* name_ = nullptr;
+    size_t nameLen_ = 0;
+};
+
+// ---- values[] of commands/map.go:46-71 ----------------------------------------------------------------------------
+uint64_t revcomp_id(uint64_t x, int k) {
+    uint64_t r = 0;
+    for (int i = 0; i < k; i++) {
+        r = (r << 2) | ((x ^ 3) & 3);
+        x >>= 2;
+    }
+    return r;
+}
+
+std::vector<double> kmer_values(std::vector<uint64_t>& counts, int k) {
+    const size_t n = counts.size();
+    std::vector<double> values(n);
+    uint64_t tot = 0;
+    for (uint64_t c : counts) tot += c;
+    const double tf = (double)tot, target = 0.000005;
+    for (size_t i = 0; i < n; i++) {
+        double freq = (double)counts[i] / tf;
+        if (counts[i] < 3) values[i] = 0;
+        else if (freq <= target) values[i] = 1.0 - (target - freq);
+        else values[i] = 1.0 - (freq - target);
+    }
+    // TopOccurrences(counts, k, n/100, n/50) (util/sequtil/kmers.go:87-112): forward and reverse-complement counts are
+    // merged in place over ascending ids, the ids sorted by merged count, the top n/100 zeroed. Ties at the cut follow
+    // Go's sort.Sort in the reference (unpinned); here they are broken by ascending id.
+    for (size_t i = 0; i < n; i++) {
+        uint64_t rc = revcomp_id(i, k);
+        uint64_t c = counts[i] + counts[rc];
+        counts[i] = c;
+        counts[rc] = c;
+    }
+    std::vector<uint32_t> ids(n);
+    std::iota(ids.begin(), ids.end(), 0u);
+    std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return counts[a] < counts[b]; });
+    for (size_t i = n - n / 100; i < n; i++) values[ids[i]] = 0;
+    values[0] = 0;
+    return values;
+}
+
+// ---- batches ------------------------------------------------------------------------------------------------------
+struct Batch {
+    uint8_t* bases = nullptr;  // pinned (dp_host_alloc): the kernels pull the queried windows straight out of it
+    size_t cap = 0, used = 0;
+    std::vector<int64_t> offsets;
+    std::vector<std::pair<const unsigned char*, size_t>> names;
+    bool last = false;
+    void reset() {
+        used = 0;
+        offsets.assign(1, 0);
+        names.clear();
+        last = false;
+    }
+};
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    // downpore.go:34-51 parseArgs + commands/command.go:18-58 MakeArgs (shortest unambiguous prefixes as aliases)
+    std::map<std::string, std::string> args = {{"input", ""},          {"reference", ""},      {"circular", "true"},
+                                               {"k", "11"},            {"query_size", "1000"}, {"min_length", "500"},
+                                               {"chunk_size", "10000"}, {"seed_rate", "40"},   {"num_workers", "4"}};
+    const std::map<std::string, std::string> alias = {{"i", "input"},       {"r", "reference"},  {"ci", "circular"},
+                                                      {"k", "k"},           {"q", "query_size"}, {"m", "min_length"},
+                                                      {"ch", "chunk_size"}, {"s", "seed_rate"},  {"n", "num_workers"}};
+    int first = 1;
+    if (argc > 1 && strcmp(argv[1], "map") == 0) first = 2;  // accept `dp_map map -input ...` like `downpore map ...`
+    for (int i = first; i < argc; i += 2) {
+        std::string name = argv[i];
+        name.erase(0, name.find_first_not_of('-'));
+        auto a = alias.find(name);
+        if (a != alias.end()) name = a->second;
+        if (!args.count(name)) fatal("Unrecognised argument:" + name);
+        if (i + 1 >= argc) fatal("Missing value for argument:" + name);
+        args[name] = argv[i + 1];
+    }
+    auto parse_int = [](const std::string& s) {  // commands.ParseInt: base 10, 32 bits
+        char* end = nullptr;
+        errno = 0;
+        long long v = strtoll(s.c_str(), &end, 10);
+        if (s.empty() || *end || errno || v > INT32_MAX || v < INT32_MIN) fatal("Invalid integer argument value:" + s);
+        return (int)v;
+    };
+    const int k = parse_int(args["k"]);
+    parse_int(args["num_workers"]);  // validated like the reference; the goroutine pool is replaced by GPU batches
+    const int minLength = parse_int(args["min_length"]);
+    const std::string& cs = args["circular"];
+    const bool circular = cs == "1" || (!cs.empty() && (cs[0] == 'T' || cs[0] == 't'));
+    const int querySize = parse_int(args["query_size"]);
+    const int chunkSize = parse_int(args["chunk_size"]);
+    const int seedRate = parse_int(args["seed_rate"]);
+    if (args["input"].empty() || args["reference"].empty()) fatal("usage: dp_map -input <fasta/fastq> -reference <fasta> [...]");
+    if (k < 1 || k > 15) fatal("k must be in [1, 15]");
+
+    std::vector<int> devices;
+    {
+        const char* env = getenv("DOWNPORE_GPUS");
+        std::string s = env ? env : "0";
+        size_t pos = 0;
+        while (pos <= s.size()) {
+            size_t c = s.find(',', pos);
+            if (c == std::string::npos) c = s.size();
+            if (c > pos) devices.push_back(atoi(s.substr(pos, c - pos).c_str()));
+            pos = c + 1;
+        }
+        if (devices.empty()) devices.push_back(0);
+    }
+    const size_t batchReads = getenv("DOWNPORE_BATCH") ? (size_t)atoll(getenv("DOWNPORE_BATCH")) : (size_t)131072;
+    const size_t batchBytes =
+        getenv("DOWNPORE_BATCH_BYTES") ? (size_t)atoll(getenv("DOWNPORE_BATCH_BYTES")) : ((size_t)3 << 29);
+    const bool wantStats = getenv("DOWNPORE_STATS") != nullptr;
+
+    // ---- reference: the first record is indexed, every record is counted (commands/map.go:34-36, 45) ----
+    double t0 = now_s();
+    MappedFile refFile(args["reference"]);
+    std::string refName;
+    std::vector<uint8_t> reference;
+    std::vector<uint64_t> counts((size_t)1 << (2 * k), 0);
+    {
+        RecordReader rr(refFile.p, refFile.n, 0);
+        Record r;
+        bool firstRec = true;
+        while (rr.next(r)) {
+            if (firstRec) {
+                reference.assign(r.seq, r.seq + r.len);
+                refName.assign((const char*)r.name, r.nameLen);
+                firstRec = false;
+            }
+            if ((long long)r.len >= k && dp_kmer_counts(r.seq, (int64_t)r.len, k, counts.data(), devices[0]))
+                fatal(std::string("dp_kmer_counts: ") + dp_last_error());
+        }
+        if (firstRec) fatal("no reference sequence");
+    }
+    std::vector<double> values = kmer_values(counts, k);
+    fprintf(stderr, "K-mer counting complete. Preparing to start indexing and querying...\n");
+    double t1 = now_s();
+
+    std::vector<dp_mapper*> mappers(devices.size(), nullptr);
+    {   // one replica of the index per GPU, built concurrently (deterministic, so every replica is identical)
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(devices.size());
+        for (size_t d = 0; d < devices.size(); d++)
+            th.emplace_back([&, d] {
+                if (dp_mapper_create(reference.data(), (int64_t)reference.size(), circular ? 1 : 0, k, values.data(),
+                                     seedRate, querySize, chunkSize, devices[d], &mappers[d]))
+                    errs[d] = dp_last_error();
+            });
+        for (auto& t : th) t.join();
+        for (auto& e : errs)
+            if (!e.empty()) fatal("dp_mapper_create: " + e);
+    }
+    double t2 = now_s();
+
+    // ---- reads: a reader thread fills pinned batches; one mapping thread per GPU drains them; output in input order ----
+    MappedFile in(args["input"]);
+    const size_t nSlots = devices.size() + 2;
+    std::vector<Batch> slots(nSlots);
+    for (auto& b : slots) {
+        b.cap = batchBytes;
+        if (dp_host_alloc((void**)&b.bases, b.cap)) fatal(std::string("dp_host_alloc: ") + dp_last_error());
+        b.reset();
+    }
+    struct Result {
+        dp_mapping* maps = nullptr;
+        int64_t* offs = nullptr;
+        bool ready = false;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> freeSlots, fullSlots;  // slot ids; fullSlots in batch order
+    std::vector<long long> slotSeq(nSlots, -1);
+    for (size_t i = 0; i < nSlots; i++) freeSlots.push_back((int)i);
+    long long produced = 0, nextToMap = 0, nextToPrint = 0;
+    bool readerDone = false;
+    std::map<long long, std::pair<int, Result>> results;  // batch seq -> (slot, result)
+    std::string workerErr;
+    double mapSeconds = 0;
+    long long totalBases = 0;
+
+    std::thread reader([&] {
+        RecordReader rr(in.p, in.n, minLength);
+        Record r;
+        bool more = rr.next(r);
+        while (more) {
+            int s;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !freeSlots.empty() || !workerErr.empty(); });
+                if (!workerErr.empty()) break;
+                s = freeSlots.back();
+                freeSlots.pop_back();
+            }
+            Batch& b = slots[(size_t)s];
+            b.reset();
+            while (more && b.names.size() < batchReads && (b.used + r.len <= b.cap || b.names.empty())) {
+                if (r.len > b.cap) fatal("read longer than the batch buffer");
+                memcpy(b.bases + b.used, r.seq, r.len);
+                b.used += r.len;
+                b.offsets.push_back((int64_t)b.used);
+                b.names.emplace_back(r.name, r.nameLen);
+                more = rr.next(r);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                slotSeq[(size_t)s] = produced++;
+                fullSlots.push_back(s);
+            }
+            cv.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            readerDone = true;
+        }
+        cv.notify_all();
+    });
+
+    auto mapWorker = [&](size_t d) {
+        for (;;) {
+            int s;
+            long long seq;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !fullSlots.empty() || readerDone || !workerErr.empty(); });
+                if (!workerErr.empty()) return;
+                if (fullSlots.empty()) return;
+                s = fullSlots.front();
+                fullSlots.erase(fullSlots.begin());
+                seq = slotSeq[(size_t)s];
+                nextToMap++;
+            }
+            Batch& b = slots[(size_t)s];
+            Result res;
+            double ta = now_s();
+            if (dp_mapper_map_batch(mappers[d], (int64_t)b.names.size(), b.bases, b.offsets.data(), &res.maps, &res.offs)) {
+                std::lock_guard<std::mutex> lk(mu);
+                workerErr = dp_last_error();
+                cv.notify_all();
+                return;
+            }
+            double tb = now_s();
+            res.ready = true;
+            if (wantStats) {
+                dp_stats st;
+                dp_mapper_get_stats(mappers[d], &st);
+                fprintf(stderr,
+                        "[dp_map] gpu %d batch %lld: %zu reads %.1f ms (pack %.1f extract %.1f lookup %.1f chain %.1f host %.1f)\n",
+                        devices[d], seq, b.names.size(), (tb - ta) * 1e3, st.ms_pack, st.ms_extract, st.ms_lookup,
+                        st.ms_chain, st.ms_host_logic);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                mapSeconds += tb - ta;
+                results[seq] = std::make_pair(s, res);
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> workers;
+    for (size_t d = 0; d < devices.size(); d++) workers.emplace_back(mapWorker, d);
+
+    // ---- printer (commands/map.go:88-106), in batch order ----
+    long long mapped = 0, multiple = 0, total = 0, unmapped = 0;
+    std::vector<char> line(1 << 16);
+    std::string nameBuf;
+    static char outBuf[1 << 20];
+    setvbuf(stdout, outBuf, _IOFBF, sizeof(outBuf));
+    for (;;) {
+        int s;
+        Result res;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] {
+                return results.count(nextToPrint) || !workerErr.empty() ||
+                       (readerDone && nextToPrint >= produced);
+            });
+            if (!workerErr.empty()) break;
+            if (!results.count(nextToPrint)) break;  // all batches printed
+            s = results[nextToPrint].first;
+            res = results[nextToPrint].second;
+            results.erase(nextToPrint);
+            nextToPrint++;
+        }
+        Batch& b = slots[(size_t)s];
+        for (size_t i = 0; i < b.names.size(); i++) {
+            const int64_t a = res.offs[i], e = res.offs[i + 1];
+            const int64_t qlen = b.offsets[i + 1] - b.offsets[i];
+            totalBases += qlen;
+            if (e > a) {
+                nameBuf.assign((const char*)b.names[i].first, b.names[i].second);
+                for (int64_t j = a; j < e; j++) {
+                    int n = dp_mapper_paf_line(mappers[0], res.maps + j, nameBuf.c_str(), qlen, refName.c_str(), line.data(),
+                                               (int)line.size());
+                    if (n < 0) fatal("PAF line too long");
+                    fwrite(line.data(), 1, (size_t)n, stdout);
+                    fputc('\n', stdout);
+                }
+                if (e - a == 1) mapped++;
+                else multiple++;
+                total += e - a;
+            } else {
+                unmapped++;
+            }
+        }
+        dp_free(res.maps);
+        dp_free(res.offs);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            freeSlots.push_back(s);
+        }
+        cv.notify_all();
+    }
+    reader.join();
+    for (auto& w : workers) w.join();
+    if (!workerErr.empty()) fatal("dp_mapper_map_batch: " + workerErr);
+    fflush(stdout);
+    double t3 = now_s();
+    fprintf(stderr, "Uniquely mapped: %lld\nMultiple mappings: %lld\ntotal: %lld\nUnmapped: %lld\n", mapped, multiple, total,
+            unmapped);
+    if (wantStats) {
+        int64_t info[5] = {0, 0, 0, 0, 0};
+        dp_mapper_index_info(mappers[0], info);
+        fprintf(stderr,
+                "[dp_map] %s; gpus=%zu seeds=%lld chunks=%lld count+values=%.3fs index=%.3fs read+map+print=%.3fs "
+                "(map calls %.3fs) bases=%lld Gbp/s(end to end)=%.3f\n",
+                dp_version(), devices.size(), (long long)info[0], (long long)info[1], t1 - t0, t2 - t1, t3 - t2, mapSeconds,
+                totalBases, totalBases / (t3 - t2) / 1e9);
+    }
+    for (auto& b : slots) dp_host_free(b.bases);
+    for (dp_mapper* m : mappers) dp_mapper_destroy(m);
+    return 0;
+}
