@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -127,11 +128,14 @@ struct Lane {
     bool pendingStageTimes = false;
     const unsigned char* curAscii = nullptr;  // device-visible ASCII of the current sub-batch (device or mapped host)
     bool curAsciiIsHost = false;
+    cudaEvent_t evReady = nullptr, evPulled = nullptr;  // hand-over to / from the mapper's pull stream
     std::vector<Timer> timers;
     dp_stats stats{};
     int candStride = 0;
     int extractWarps = 0, lookupWarps = 0, chainWarps = 0;
     ~Lane() {
+        if (evReady) cudaEventDestroy(evReady);
+        if (evPulled) cudaEventDestroy(evPulled);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -140,6 +144,11 @@ struct dp_mapper {
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;  // index construction
+    // Reads that live in pinned host memory are pulled over PCIe by ONE stream shared by all lanes: pulls run back to
+    // back at link speed while the lanes' compute kernels and host work overlap them (lanes pulling independently fall
+    // into lock step: both wait on the link, then both wait on the SMs).
+    cudaStream_t pullStream = nullptr;
+    std::mutex pullMu;
     // parameters
     int k = 0, circular = 0, seedRate = 0, edge = 0, chunkSize = 0;
     long long refLen = 0;
@@ -162,6 +171,7 @@ struct dp_mapper {
 
     ~dp_mapper() {
         lanes.clear();
+        if (pullStream) cudaStreamDestroy(pullStream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -550,21 +560,34 @@ enum { CUR_SEEDS = 0, CUR_OUT = 1, CUR_FIN = 2 };
 // Launches the three performMapping stages for the `nWin` windows already in W.dWins (device). Results stay on the
 // device: W.outN / W.outOff / W.outMaps (compact, bump-allocated through cursor[CUR_OUT]).
 void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, const unsigned* dWords, const long long* dWordOff,
-                    const int* dReadLen) {
+                    const int* dReadLen, bool bulkPull = false) {
     const DpIndexDev& I = M.I;
     cudaStream_t st = W.stream;
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
     {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
-        // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the other
-        // lane's compute kernels stay resident beside it
+        // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
+        // compute kernels stay resident beside it
         int perSm = W.curAsciiIsHost ? 2 : 8;
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
-        CK(cudaEventRecord(W.timers[T_PACK].a, st));
-        dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                       const_cast<unsigned*>(dWords));
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(W.timers[T_PACK].b, st));
+        if (W.curAsciiIsHost && bulkPull) {
+            std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
+            CK(cudaEventRecord(W.evReady, st));
+            CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
+            CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
+            dp_pack_windows_kernel<<<blocks, 256, 0, M.pullStream>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+                                                                    const_cast<unsigned*>(dWords));
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_PACK].b, M.pullStream));
+            CK(cudaEventRecord(W.evPulled, M.pullStream));
+            CK(cudaStreamWaitEvent(st, W.evPulled, 0));
+        } else {
+            CK(cudaEventRecord(W.timers[T_PACK].a, st));
+            dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+                                                           const_cast<unsigned*>(dWords));
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_PACK].b, st));
+        }
         W.stats.kernel_launches += 1;
     }
     const int qStride = I.maxWindow + 8;
@@ -802,7 +825,7 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     ensure_window_capacity(M, W, nWin0, seedEntries0);
     dp_round0_windows_kernel<<<div_up(n, 256), 256, 0, st>>>(W.dReadLen.p, n, e, minLen, W.dWins.p);
     CK(cudaGetLastError());
-    launch_windows(M, W, nWin0, seedEntries0, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+    launch_windows(M, W, nWin0, seedEntries0, W.dWords.p, W.dWordOff.p, W.dReadLen.p, /*bulkPull=*/true);
     W.stats.windows += nWinReal - (int64_t)nWin0;  // empty second slots of short reads are not window queries
     if (W.curAsciiIsHost) {  // bytes the windowed pack pulls over the link: the round-0 windows (+ one word ahead)
         for (int64_t i = 0; i < n; i++) {
@@ -978,6 +1001,8 @@ Lane& get_lane(dp_mapper& M, size_t idx) {
     while (M.lanes.size() <= idx) {
         std::unique_ptr<Lane> L(new Lane());
         CK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&L->evReady, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&L->evPulled, cudaEventDisableTiming));
         L->timers.resize(T_N);
         for (auto& t : L->timers) t.init();
         M.lanes.push_back(std::move(L));
@@ -990,8 +1015,8 @@ const int64_t kSubBatchBytes = 1ll << 30;
 
 int lane_count() {
     const char* env = getenv("DP_LANES");
-    int v = env ? atoi(env) : 2;
-    return std::max(1, std::min(v, 4));
+    int v = env ? atoi(env) : 3;
+    return std::max(1, std::min(v, 8));
 }
 
 // Copies reads [r0,r1) to the lane's device buffer. Pinned (or registered) caller memory is copied directly;
@@ -1175,6 +1200,11 @@ int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, in
     CK(cudaGetDeviceProperties(&prop, device));
     M->smCount = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;  // numerically lowest value = highest priority
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&M->pullStream, cudaStreamNonBlocking, hi));
+    }
     M->k = k;
     M->circular = circular ? 1 : 0;
     M->seedRate = seed_rate;
