@@ -27,6 +27,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (one 65536-read sub-batch), profiles/r1c_ncu_summary.txt
+TRAFFIC_PER_LAUNCH = {"pack": None, "extract": None, "lookup": None, "chain": None}
+
 K = 11
 REF_LEN = 4_600_000
 READ_LEN = 10_000
@@ -235,23 +238,28 @@ def run_ours(args):
         step_device()
     sampler = ClockSampler(local)
     agg = None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
     t0 = time.time()
+    ev0.record()
     for _ in range(args.steps):
-        maps, off = step_device()
+        maps, off = step_device()   # returns after the library has synchronised its streams (results are on the host)
         st = gm.stats()
         if agg is None:
             agg = {k: 0 for k in st}
         for k2, v in st.items():
             agg[k2] += v
+    ev1.record()
     torch.cuda.synchronize()
     barrier(world)
-    dt_dev = time.time() - t0
+    wall_dev = time.time() - t0
     clocks = sampler.stop() if rank == 0 else None
-    dt_dev = max_over_ranks(dt_dev, world, dev)
+    # device clock (CUDA events bracketing the K steps) — the wall clock is reported beside it
+    dt_dev = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, dev)
+    wall_dev = max_over_ranks(wall_dev, world, dev)
     mapped_frac = float((np.diff(off) > 0).mean())
     d2h_bytes = int(len(maps) * 32 + (n + 1) * 8)
 
@@ -261,11 +269,14 @@ def run_ours(args):
     barrier(world)
     torch.cuda.synchronize()
     t0 = time.time()
+    ev0.record()
     for _ in range(args.steps):
         step_host()
+    ev1.record()
     torch.cuda.synchronize()
     barrier(world)
-    dt_e2e = max_over_ranks(time.time() - t0, world, dev)
+    wall_e2e = max_over_ranks(time.time() - t0, world, dev)
+    dt_e2e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, dev)
     st_e2e = gm.stats()
 
     total_bases = sum_over_ranks(float(bases_rank), world, dev)
@@ -286,21 +297,37 @@ def run_ours(args):
         ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
     dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])
-    traffic = {"pack": None, "extract": None, "lookup": None, "chain": None}
+    # dram bytes per launch of one 65536-read sub-batch from the committed `ncu --set full` capture (profiles/)
+    traffic = TRAFFIC_PER_LAUNCH
+    gather_gbs = None
+    if rank == 0:
+        try:
+            gather_gbs = dp.probe_gather_gbs(8 << 30, device=local)
+        except Exception:
+            gather_gbs = None
+    # sector traffic of the lookup kernel's posting gathers: every posting run costs whole 32 B sectors
+    sector_bytes_lookup = 32.0 * agg["posting_runs"] / S + 32.0 * (4.0 * agg["posting_entries"] / S) / 32.0
     roofline = {"kernel": "dp_%s_kernel" % dominant, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
-                "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"], "traffic": traffic[dominant],
+                "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"], "traffic": traffic.get(dominant),
                 "peak_source": peak_src,
-                "note": "index (6 MB) and k-mer table (1 MB) are L2-resident for this config, so no kernel is bound by "
-                        "HBM; durations are CUDA-event times on the launching streams, summed over the two "
-                        "overlapping lanes (conservative)",
+                "note": "config 2's index (8.6 MB) and k-mer table (1 MB) are L2-resident, so no kernel of this workload "
+                        "is bound by HBM (ncu: dram throughput < 2 % for every kernel; they are issue/latency bound, "
+                        "see profiles/). achieved = SURVEY 8d algorithmic bytes / CUDA-event time of the kernel on its "
+                        "launching stream, summed over the overlapping lanes (conservative). traffic = ncu dram bytes "
+                        "per launch of a 65536-read sub-batch",
+                "hbm_gather_ceiling_GBs": gather_gbs,
+                "lookup_vs_gather_ceiling": (sector_bytes_lookup / (kern["lookup"]["ms_per_step"] * 1e-3) / 1e9 / gather_gbs
+                                             if gather_gbs and kern["lookup"]["ms_per_step"] > 0 else None),
                 "kernels": kern}
 
     line = {"metric": "mapped Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt_dev / args.steps * 1e3, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": dt_dev / args.steps * 1e3,
+            "wall_ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": config_dict(args, world),
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] + (n + 1) * 8),
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "wall_ms_per_step": wall_e2e / args.steps * 1e3,
                     "host_buffer_bytes_per_step": int(bases_rank),
                     "note": "per GPU; dp_mapper_map_batch on pinned host ASCII. The reads stay in the caller's pinned "
                             "buffer and the windowed pack kernel pulls only the queried windows across PCIe "

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "dp_last_error": (ctypes.c_char_p, []),
     "dp_version": (ctypes.c_char_p, []),
     "dp_free": (None, [c_vp]),
+    "dp_probe_gather_gbs": (ctypes.c_int, [ctypes.c_int, c_i64, ctypes.POINTER(ctypes.c_double)]),
     "dp_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "dp_host_free": (None, [c_vp]),
     "dp_mapper_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
@@ -138,6 +139,13 @@ def kmer_counts(ascii_seq, k, counts=None, device=0):
         counts = np.zeros(4 ** k, dtype=np.uint64)
     _check(lib().dp_kmer_counts(a.ctypes.data, a.size, k, counts.ctypes.data, device))
     return counts
+
+
+def probe_gather_gbs(table_bytes=8 << 30, device=0):
+    """Random 32 B-sector gather bandwidth (GB/s of sector traffic) over a table >> L2: the HBM gather roofline."""
+    out = ctypes.c_double()
+    _check(lib().dp_probe_gather_gbs(device, table_bytes, ctypes.byref(out)))
+    return out.value
 
 
 def kmer_values(counts, k):

@@ -568,7 +568,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
         // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
         // compute kernels stay resident beside it
-        int perSm = W.curAsciiIsHost ? 2 : 8;
+        int perSm = W.curAsciiIsHost ? 2 : 6;
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         if (W.curAsciiIsHost && bulkPull) {
             std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
@@ -601,7 +601,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     {
         // one persistent CTA per SM. When the other lane may be pulling reads over PCIe, every compute kernel leaves
         // a quarter of the SM's registers and thread slots free so that the pull kernel stays resident beside it.
-        int warpsPerBlock = W.curAsciiIsHost ? 24 : 32;
+        int warpsPerBlock = W.curAsciiIsHost ? 20 : 32;
         const size_t fWords = I.filterBits ? ((((size_t)1 << I.filterBits) + 31) / 32 + 3) / 4 * 4 : 0;
         const size_t perWarp = (size_t)2 * maskWords * sizeof(unsigned);
         const size_t room = 200 * 1024 - fWords * sizeof(unsigned);
@@ -1015,7 +1015,7 @@ const int64_t kSubBatchBytes = 1ll << 30;
 
 int lane_count() {
     const char* env = getenv("DP_LANES");
-    int v = env ? atoi(env) : 3;
+    int v = env ? atoi(env) : 4;
     return std::max(1, std::min(v, 8));
 }
 
@@ -1148,6 +1148,31 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     M.stats.ms_total = now_ms() - tStart;
     *out = maps;
     *out_offsets = off;
+}
+
+}  // namespace
+
+namespace {
+// Random 32-byte-sector gather over a table far larger than L2: the "HBM gather roofline" the lookup kernel is held
+// against. Every thread reads `perThread` independent random sectors (one 4-byte word of each, so each
+// gather costs a full 32 B sector of DRAM traffic, exactly like a short posting run).
+__global__ void dp_gather_probe_kernel(const unsigned* __restrict__ table, unsigned long long nSectors, int perThread,
+                                       unsigned* __restrict__ sink) {
+    unsigned long long x = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 1;
+    unsigned acc = 0;
+    for (int i = 0; i < perThread; i += 4) {
+        unsigned long long idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            x ^= x << 13;
+            x ^= x >> 7;
+            x ^= x << 17;
+            idx[u] = (x % nSectors) * 8;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc += __ldg(table + idx[u]);
+    }
+    if (acc == 0x12345678u) *sink = acc;
 }
 
 }  // namespace
@@ -1403,6 +1428,37 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
             maps[i] = o;
         }
     }
+    API_CATCH
+}
+
+int dp_probe_gather_gbs(int device, int64_t table_bytes, double* sector_gbs) {
+    API_TRY
+    if (!sector_gbs || table_bytes < (1 << 20)) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(device));
+    DBuf<unsigned> tab, sink;
+    size_t nWords = (size_t)table_bytes / 4;
+    tab.reserve(nWords);
+    sink.reserve(1);
+    CK(cudaMemset(tab.p, 1, nWords * 4));
+    const unsigned long long nSectors = nWords / 8;
+    const int perThread = 64, threads = 256, blocks = 148 * 64;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int it = 0; it < 4; it++) {
+        CK(cudaEventRecord(a));
+        dp_gather_probe_kernel<<<blocks, threads>>>(tab.p, nSectors, perThread, sink.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (it && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *sector_gbs = 32.0 * perThread * threads * blocks / (best * 1e-3) / 1e9;
     API_CATCH
 }
 

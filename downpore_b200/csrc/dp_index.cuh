@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __res
 // (one LDG.128 each, 512 contiguous bytes per warp), neighbours exchange blocks by shuffle, and 31 packed words are
 // written. Each source byte crosses the bus once (+1/31 overlap).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 8) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
+__global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
                                                               const long long* __restrict__ seqOff,
                                                               const long long* __restrict__ wordOff,
                                                               const DpWindow* __restrict__ wins, int nWin,
@@ -87,33 +87,45 @@ __global__ void __launch_bounds__(256, 8) dp_pack_windows_kernel(const unsigned 
         const unsigned char* srcEnd = ascii + readBase + readLen;  // one past the last byte of the read
         const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)blk)) >> 4;
         const unsigned q = mis >> 2, sh = (mis & 3) * 8;
-        for (long long g0 = 0; g0 < nWords; g0 += 31) {
-            long long b = g0 + lane;  // aligned block index this lane loads
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (b <= lastBlk && b <= nWords) v = __ldg(blk + b);  // never past the block holding the read's last byte
-            uint4 nx;
-            nx.x = __shfl_down_sync(DP_FULL, v.x, 1);
-            nx.y = __shfl_down_sync(DP_FULL, v.y, 1);
-            nx.z = __shfl_down_sync(DP_FULL, v.z, 1);
-            nx.w = __shfl_down_sync(DP_FULL, v.w, 1);
-            // 16 source bytes of word g = bytes [mis, mis+16) of (v, nx)
-            unsigned a0, a1, a2, a3, a4;
-            switch (q) {  // warp-uniform
-                case 0: a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w; a4 = nx.x; break;
-                case 1: a0 = v.y; a1 = v.z; a2 = v.w; a3 = nx.x; a4 = nx.y; break;
-                case 2: a0 = v.z; a1 = v.w; a2 = nx.x; a3 = nx.y; a4 = nx.z; break;
-                default: a0 = v.w; a1 = nx.x; a2 = nx.y; a3 = nx.z; a4 = nx.w; break;
+        // three iterations per trip, all three block loads issued before the first is consumed: the pull is bound by
+        // the latency of the link, so bytes in flight per warp are what buys bandwidth (a 1000-base window = one trip)
+        for (long long g00 = 0; g00 < nWords; g00 += 93) {
+            uint4 vv[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                long long b = g00 + 31 * u + lane;  // aligned block index this lane loads
+                vv[u] = make_uint4(0, 0, 0, 0);
+                if (b <= lastBlk && b <= nWords) vv[u] = __ldg(blk + b);  // never past the block holding the read's last byte
             }
-            long long g = g0 + lane;
-            if (lane < 31 && g < nWords) {
-                unsigned x0 = __funnelshift_r(a0, a1, sh);
-                unsigned x1 = __funnelshift_r(a1, a2, sh);
-                unsigned x2 = __funnelshift_r(a2, a3, sh);
-                unsigned x3 = __funnelshift_r(a3, a4, sh);
-                unsigned pv = (dp_pack4(x0) << 24) | (dp_pack4(x1) << 16) | (dp_pack4(x2) << 8) | dp_pack4(x3);
-                long long remain = readLen - (w0 + g) * 16;  // bases of the read in this word
-                if (remain < 16) pv &= remain > 0 ? (~0u << (unsigned)(2 * (16 - remain))) : 0u;
-                out[g] = pv;
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const long long g0 = g00 + 31 * u;
+                if (g0 >= nWords) break;  // warp-uniform
+                const uint4 v = vv[u];
+                uint4 nx;
+                nx.x = __shfl_down_sync(DP_FULL, v.x, 1);
+                nx.y = __shfl_down_sync(DP_FULL, v.y, 1);
+                nx.z = __shfl_down_sync(DP_FULL, v.z, 1);
+                nx.w = __shfl_down_sync(DP_FULL, v.w, 1);
+                // 16 source bytes of word g = bytes [mis, mis+16) of (v, nx)
+                unsigned a0, a1, a2, a3, a4;
+                switch (q) {  // warp-uniform
+                    case 0: a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w; a4 = nx.x; break;
+                    case 1: a0 = v.y; a1 = v.z; a2 = v.w; a3 = nx.x; a4 = nx.y; break;
+                    case 2: a0 = v.z; a1 = v.w; a2 = nx.x; a3 = nx.y; a4 = nx.z; break;
+                    default: a0 = v.w; a1 = nx.x; a2 = nx.y; a3 = nx.z; a4 = nx.w; break;
+                }
+                long long g = g0 + lane;
+                if (lane < 31 && g < nWords) {
+                    unsigned x0 = __funnelshift_r(a0, a1, sh);
+                    unsigned x1 = __funnelshift_r(a1, a2, sh);
+                    unsigned x2 = __funnelshift_r(a2, a3, sh);
+                    unsigned x3 = __funnelshift_r(a3, a4, sh);
+                    unsigned pv = (dp_pack4(x0) << 24) | (dp_pack4(x1) << 16) | (dp_pack4(x2) << 8) | dp_pack4(x3);
+                    long long remain = readLen - (w0 + g) * 16;  // bases of the read in this word
+                    if (remain < 16) pv &= remain > 0 ? (~0u << (unsigned)(2 * (16 - remain))) : 0u;
+                    out[g] = pv;
+                }
             }
         }
     }

@@ -126,6 +126,12 @@ int dp_pack(const uint8_t* ascii, int64_t len, uint8_t* out, int device);
 int dp_kmer_counts(const uint8_t* ascii, int64_t len, int k, uint64_t* counts, int device);
 
 /*
+ * Measurement aid (bench.py): random 32-byte-sector gather bandwidth over a `table_bytes` table (choose it far larger
+ * than L2) in GB/s of sector traffic: the HBM gather roofline the index-lookup kernel is held against.
+ */
+int dp_probe_gather_gbs(int device, int64_t table_bytes, double* sector_gbs);
+
+/*
  * Page-locked host memory for read batches (what a cgo host passes as `bases`): dp_mapper_map_batch reads such a
  * buffer in place from the device (zero-copy pull of the queried windows), so a host that fills batches into
  * dp_host_alloc'ed memory never pays a staging copy. Portable across devices. Release with dp_host_free.
