@@ -55,8 +55,9 @@ struct DBuf {  // device buffer, grow-only
 };
 
 template <class T>
-struct HBuf {  // pinned host buffer, grow-only
+struct HBuf {  // page-locked host buffer mapped into the device address space (d = device view), grow-only
     T* p = nullptr;
+    T* d = nullptr;
     size_t cap = 0;
     ~HBuf() {
         if (p) cudaFreeHost(p);
@@ -66,7 +67,8 @@ struct HBuf {  // pinned host buffer, grow-only
         if (p) cudaFreeHost(p);
         p = nullptr;
         size_t want = n + n / 8 + 64;
-        CK(cudaMallocHost((void**)&p, want * sizeof(T)));
+        CK(cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&d, p, 0));
         cap = want;
     }
 };
@@ -833,26 +835,20 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
             if (len >= minLen) W.stats.h2d_bytes += (len <= 2ll * e) ? len : std::min<long long>(len, 2ll * (e + 32));
         }
     }
-    W.dStatus.reserve((size_t)n);
-    W.dFinN.reserve((size_t)n);
-    W.dFinOff.reserve((size_t)n);
-    W.dFinMaps.reserve((size_t)n * 4 + 64);
-    CK(cudaEventRecord(W.timers[T_FINISH].a, st));
-    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
-                                                            W.outMaps.p, W.dStatus.p, W.dFinN.p, W.dFinOff.p,
-                                                            W.dFinMaps.p, W.cursor.p + CUR_FIN,
-                                                            (unsigned long long)W.dFinMaps.cap);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(W.timers[T_FINISH].b, st));
-    W.stats.kernel_launches += 2;
+    // Map()'s first decision per read; the kernel writes its results straight into mapped page-locked host memory
+    const size_t finCap = (size_t)n * 4 + 64;
     W.hStatus.reserve((size_t)n);
     W.hFinN.reserve((size_t)n);
     W.hFinOff.reserve((size_t)n);
-    unsigned long long cur[4];
-    CK(cudaMemcpyAsync(W.hStatus.p, W.dStatus.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(W.hFinN.p, W.dFinN.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(W.hFinOff.p, W.dFinOff.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cur, W.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    W.hFinMaps.reserve(finCap);
+    CK(cudaEventRecord(W.timers[T_FINISH].a, st));
+    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
+                                                            W.outMaps.p, W.hStatus.d, W.hFinN.d, W.hFinOff.d,
+                                                            W.hFinMaps.d, W.cursor.p + CUR_FIN,
+                                                            (unsigned long long)finCap);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(W.timers[T_FINISH].b, st));
+    W.stats.kernel_launches += 2;
     W.stats.ms_host_logic += now_ms() - t0;
     CK(cudaStreamSynchronize(st));
     collect_stage_times(W);
@@ -861,15 +857,14 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
         CK(cudaEventElapsedTime(&ms, W.timers[T_FINISH].a, W.timers[T_FINISH].b));
         W.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
     }
-    const size_t finTotal = (size_t)std::min<unsigned long long>(cur[CUR_FIN], (unsigned long long)W.dFinMaps.cap);
-    W.hFinMaps.reserve(finTotal + 1);
-    if (finTotal)
-        CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, finTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     t0 = now_ms();
     std::vector<int> active;
+    bool needDownload = false;
     for (int64_t i = 0; i < n; i++)
-        if (W.hStatus.p[i] != DP_READ_DONE) active.push_back((int)i);
+        if (W.hStatus.p[i] != DP_READ_DONE) {
+            active.push_back((int)i);
+            if (W.hStatus.p[i] == DP_READ_UNRESOLVED_NOHITS) needDownload = true;
+        }
     W.stats.ms_host_logic += now_ms() - t0;
 
     // ---- unresolved reads: replay Map() on the host against cached window results, round by round ----
@@ -877,41 +872,38 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     std::vector<int> slotOf;  // read index -> slot in `cache` / `late`
     if (!active.empty()) {
         t0 = now_ms();
-        download_windows(W, nWin0);
+        if (needDownload) download_windows(W, nWin0);  // rare: the hit buffer was full
         std::vector<ReadCache> cache(active.size());
         slotOf.assign((size_t)n, -1);
         std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
-        {
-            roundMaps.emplace_back();
-            std::vector<DpMappingDev>& keep = roundMaps.back();
-            size_t total = 0;
-            for (int i : active) total += (size_t)W.hOutN.p[2 * i] + (size_t)W.hOutN.p[2 * i + 1];
-            keep.resize(total + 1);
-            size_t pos = 0;
-            for (size_t a = 0; a < active.size(); a++) {
-                int i = active[a];
-                slotOf[(size_t)i] = (int)a;
-                long long len = W.hRel.p[i + 1] - W.hRel.p[i];
-                for (int s = 0; s < 2; s++) {
-                    size_t wI = 2 * (size_t)i + s;
-                    dph::WinRef ref;
-                    if (len <= 2ll * e) {
-                        if (s == 1) continue;
-                        ref.start = 0;
-                        ref.len = (int)len;
-                        ref.whole = 1;
-                    } else {
-                        ref.start = s == 0 ? 0 : (int)(len - e);
-                        ref.len = e;
-                        ref.whole = 0;
-                    }
-                    int cnt = W.hOutN.p[wI];
-                    memcpy(keep.data() + pos, W.hOutMaps.p + W.hOutOff.p[wI], (size_t)cnt * sizeof(DpMappingDev));
-                    ref.n = cnt;
-                    ref.maps = keep.data() + pos;
-                    cache[a].wins.push_back(ref);
-                    pos += (size_t)cnt;
+        if (needDownload) roundMaps.emplace_back(W.hOutMaps.p, W.hOutMaps.p + W.hOutTotal + 1);
+        for (size_t a = 0; a < active.size(); a++) {
+            int i = active[a];
+            slotOf[(size_t)i] = (int)a;
+            long long len = W.hRel.p[i + 1] - W.hRel.p[i];
+            const bool raw = W.hStatus.p[i] == DP_READ_UNRESOLVED;  // raw window hits delivered by the finish kernel
+            const int nA = raw ? (W.hFinN.p[i] & 0xffff) : 0, nB = raw ? (W.hFinN.p[i] >> 16) : 0;
+            for (int s = 0; s < 2; s++) {
+                size_t wI = 2 * (size_t)i + s;
+                dph::WinRef ref;
+                if (len <= 2ll * e) {
+                    if (s == 1) continue;
+                    ref.start = 0;
+                    ref.len = (int)len;
+                    ref.whole = 1;
+                } else {
+                    ref.start = s == 0 ? 0 : (int)(len - e);
+                    ref.len = e;
+                    ref.whole = 0;
                 }
+                if (raw) {
+                    ref.n = s == 0 ? nA : nB;
+                    ref.maps = W.hFinMaps.p + W.hFinOff.p[i] + (s == 0 ? 0 : nA);
+                } else {
+                    ref.n = W.hOutN.p[wI];
+                    ref.maps = roundMaps[0].data() + W.hOutOff.p[wI];
+                }
+                cache[a].wins.push_back(ref);
             }
         }
         dph::Params P;
@@ -955,7 +947,9 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     }
     // ---- assemble the sub-batch output in read order ----
     t0 = now_ms();
-    size_t total = finTotal;
+    size_t total = 0;
+    for (int64_t i = 0; i < n; i++)
+        if (W.hStatus.p[i] == DP_READ_DONE) total += (size_t)W.hFinN.p[i];
     for (auto& v : late) total += v.size();
     out.maps.resize(total);
     size_t pos = 0;
@@ -1015,7 +1009,7 @@ const int64_t kSubBatchBytes = 1ll << 30;
 
 int lane_count() {
     const char* env = getenv("DP_LANES");
-    int v = env ? atoi(env) : 4;
+    int v = env ? atoi(env) : 6;
     return std::max(1, std::min(v, 8));
 }
 
@@ -1055,15 +1049,25 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                     const int64_t* offsets, dp_mapping** out, int64_t** out_offsets) {
     CK(cudaSetDevice(M.device));
     double tStart = now_ms();
-    // sub-batch boundaries
+    // sub-batch boundaries. Sizes ramp up at the start and down at the end: the first pull / first kernels start
+    // (and the last host pass ends) on a quarter-size piece, so less of the pipeline's fill and drain is exposed.
     std::vector<int64_t> cuts;
     cuts.push_back(0);
-    for (int64_t r0 = 0; r0 < n_reads;) {
-        int64_t r1 = r0;
-        while (r1 < n_reads && r1 - r0 < kSubBatchReads && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
-        if (r1 == r0) r1 = r0 + 1;
-        cuts.push_back(r1);
-        r0 = r1;
+    {
+        const int64_t full = kSubBatchReads, tail = full / 4 + full / 2;
+        int idx = 0;
+        for (int64_t r0 = 0; r0 < n_reads; idx++) {
+            int64_t remaining = n_reads - r0;
+            int64_t want = std::min<int64_t>(full, (full / 4) << std::min(idx, 2));
+            if (remaining > tail) want = std::min(want, remaining - tail);
+            else if (remaining > full / 4) want = remaining - full / 4;
+            else want = remaining;
+            int64_t r1 = r0;
+            while (r1 < n_reads && r1 - r0 < want && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
+            if (r1 == r0) r1 = r0 + 1;
+            cuts.push_back(r1);
+            r0 = r1;
+        }
     }
     const size_t nSub = cuts.size() - 1;
     const int nLanes = (int)std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1));
@@ -1122,21 +1126,36 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     for (auto& t : th) t.join();
     for (auto& e : errs)
         if (!e.empty()) throw std::runtime_error(e);
-    // ---- concatenate ----
+    // ---- concatenate (the lanes' threads copy their sub-batches into place in parallel) ----
+    std::vector<int64_t> subBase(nSub + 1, 0);
+    for (size_t sI = 0; sI < nSub; sI++) subBase[sI + 1] = subBase[sI] + (int64_t)subs[sI].maps.size();
+    const int64_t total = subBase[nSub];
     int64_t* off = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_reads + 1));
-    int64_t total = 0;
-    for (int64_t i = 0; i < n_reads; i++) {
-        off[i] = total;
-        total += counts[(size_t)i];
-    }
-    off[n_reads] = total;
     dp_mapping* maps = (dp_mapping*)malloc(sizeof(dp_mapping) * (size_t)(total ? total : 1));
-    size_t pos = 0;
-    for (size_t sI = 0; sI < nSub; sI++) {
-        if (!subs[sI].maps.empty()) memcpy(maps + pos, subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
-        pos += subs[sI].maps.size();
+    if (!off || !maps) {
+        free(off);
+        free(maps);
+        throw std::runtime_error("out of host memory for the result");
     }
-    if ((int64_t)pos != total) {
+    std::atomic<int> bad(0);
+    auto place = [&](int t) {
+        for (size_t sI = (size_t)t; sI < nSub; sI += (size_t)nLanes) {
+            if (!subs[sI].maps.empty())
+                memcpy(maps + subBase[sI], subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
+            int64_t run = subBase[sI];
+            for (int64_t i = cuts[sI]; i < cuts[sI + 1]; i++) {
+                off[i] = run;
+                run += counts[(size_t)i];
+            }
+            if (run != subBase[sI + 1]) bad.store(1);
+        }
+    };
+    th.clear();
+    for (int l = 1; l < nLanes; l++) th.emplace_back(place, l);
+    place(0);
+    for (auto& t : th) t.join();
+    off[n_reads] = total;
+    if (bad.load()) {
         free(maps);
         free(off);
         throw std::runtime_error("internal error: result assembly mismatch");

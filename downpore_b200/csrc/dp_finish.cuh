@@ -10,7 +10,10 @@
 
 #define DP_FIN_CAP 8  // hits per window handled on the device; more -> host path
 
-enum { DP_READ_DONE = 0, DP_READ_UNRESOLVED = 1 };
+// DONE: finMaps holds the read's final mappings. UNRESOLVED: finMaps holds the raw hits of its two round-0 windows
+// (first window's, then the second's; finN = nA | nB << 16) for the host replay. NOHITS: as UNRESOLVED but the hit
+// buffer was full, the host fetches the window results itself.
+enum { DP_READ_DONE = 0, DP_READ_UNRESOLVED = 1, DP_READ_UNRESOLVED_NOHITS = 2 };
 
 // read table: lengths and packed-word demand from the (sub-batch relative) byte offsets
 __global__ void dp_read_table_kernel(const long long* __restrict__ seqOff, long long n, int* __restrict__ readLen,
@@ -132,6 +135,8 @@ __device__ __forceinline__ DpMappingDev dp_store_hit(const DpHit& h) {
     return m;
 }
 
+// status / finN / finOff / finMaps may live in page-locked host memory mapped into the device address space: the
+// kernel then delivers the sub-batch's results straight to the host (posted writes), with no copy call afterwards.
 __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, const int* __restrict__ readLen,
                                                                long long n, int minLen,
                                                                const int* __restrict__ outN,
@@ -149,25 +154,27 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
     DpHit A[DP_FIN_CAP], B[DP_FIN_CAP], M[DP_FIN_CAP];
     int nOut = 0;
     const DpHit* outList = A;
-    unsigned char st = DP_READ_DONE;
-    if (qlen < minLen) {
-        nOut = 0;
-    } else {
-        int nA = outN[2 * r], nB = outN[2 * r + 1];
+    const DpHit* outList2 = B;
+    int nOut2 = 0;
+    bool done = true;
+    int nA = 0, nB = 0;
+    if (qlen >= minLen) {
+        nA = outN[2 * r];
+        nB = outN[2 * r + 1];
         if (nA > DP_FIN_CAP || nB > DP_FIN_CAP) {
-            st = DP_READ_UNRESOLVED;
+            done = false;
         } else {
             for (int i = 0; i < nA; i++) A[i] = dp_load_hit(outMaps[outOff[2 * r] + i]);
             for (int i = 0; i < nB; i++) B[i] = dp_load_hit(outMaps[outOff[2 * r + 1] + i]);
             if (qlen <= 2 * e) {
                 nOut = dp_remove_dominated(A, nA, qlen);  // mapping.go:433-436
             } else {
-                nA = dp_remove_dominated(A, nA, qlen);
-                nB = dp_remove_dominated(B, nB, qlen);
+                int mA = dp_remove_dominated(A, nA, qlen);
+                int mB = dp_remove_dominated(B, nB, qlen);
                 // matchPairs (mapping.go:174-203)
                 int nM = 0;
-                for (int i = nA - 1; i >= 0; i--) {
-                    for (int j = nB - 1; j >= 0; j--) {
+                for (int i = mA - 1; i >= 0; i--) {
+                    for (int j = mB - 1; j >= 0; j--) {
                         if (dp_is_consistent(A[i], B[j], qlen, I.circular != 0, I.refLen)) {
                             const DpHit& first = A[i].rc ? B[j] : A[i];
                             const DpHit& second = A[i].rc ? A[i] : B[j];
@@ -179,10 +186,10 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
                             c.rc = first.rc;
                             c.ids = A[i].ids + B[j].ids;
                             M[nM++] = c;
-                            A[i] = A[nA - 1];
-                            nA--;
-                            B[j] = B[nB - 1];
-                            nB--;
+                            A[i] = A[mA - 1];
+                            mA--;
+                            B[j] = B[mB - 1];
+                            mB--;
                             break;
                         }
                     }
@@ -191,44 +198,42 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
                     outList = M;
                     nOut = nM;
                 } else if (qlen < 3ll * e) {  // mapping.go:444-445: append(openA, openB...)
-                    // A then B; write B behind A in the output below
-                    nOut = -1;
+                    nOut = mA;
+                    nOut2 = mB;
                 } else {
-                    st = DP_READ_UNRESOLVED;
-                }
-                if (nOut == -1) {
-                    unsigned long long base = atomicAdd(finCursor, (unsigned long long)(nA + nB));
-                    if (base + (unsigned)(nA + nB) > finCapacity) {  // no room: let the host path redo this read
-                        status[r] = DP_READ_UNRESOLVED;
-                        finN[r] = 0;
-                        finOff[r] = 0;
-                        return;
-                    }
-                    for (int i = 0; i < nA; i++) finMaps[base + i] = dp_store_hit(A[i]);
-                    for (int i = 0; i < nB; i++) finMaps[base + nA + i] = dp_store_hit(B[i]);
-                    status[r] = DP_READ_DONE;
-                    finN[r] = nA + nB;
-                    finOff[r] = (unsigned)base;
-                    return;
+                    done = false;
                 }
             }
         }
     }
-    if (st == DP_READ_DONE && nOut > 0) {
-        unsigned long long base = atomicAdd(finCursor, (unsigned long long)nOut);
-        if (base + (unsigned)nOut > finCapacity) {
-            status[r] = DP_READ_UNRESOLVED;
+    if (done) {
+        const int tot = nOut + nOut2;
+        unsigned long long base = tot ? atomicAdd(finCursor, (unsigned long long)tot) : 0ull;
+        if (base + (unsigned)tot > finCapacity) {  // no room: let the host path redo this read
+            status[r] = DP_READ_UNRESOLVED_NOHITS;
             finN[r] = 0;
             finOff[r] = 0;
             return;
         }
-        status[r] = st;
         for (int i = 0; i < nOut; i++) finMaps[base + i] = dp_store_hit(outList[i]);
-        finN[r] = nOut;
+        for (int i = 0; i < nOut2; i++) finMaps[base + nOut + i] = dp_store_hit(outList2[i]);
+        status[r] = DP_READ_DONE;
+        finN[r] = tot;
         finOff[r] = (unsigned)base;
     } else {
-        status[r] = st;
-        finN[r] = 0;
-        finOff[r] = 0;
+        // hand the raw window hits to the host replay (removeDominated above worked on copies)
+        const int tot = nA + nB;
+        unsigned long long base = tot ? atomicAdd(finCursor, (unsigned long long)tot) : 0ull;
+        if (base + (unsigned)tot > finCapacity || nA > 0xffff || nB > 0x7fff) {
+            status[r] = DP_READ_UNRESOLVED_NOHITS;
+            finN[r] = 0;
+            finOff[r] = 0;
+            return;
+        }
+        for (int i = 0; i < nA; i++) finMaps[base + i] = outMaps[outOff[2 * r] + i];
+        for (int i = 0; i < nB; i++) finMaps[base + nA + i] = outMaps[outOff[2 * r + 1] + i];
+        status[r] = DP_READ_UNRESOLVED;
+        finN[r] = nA | (nB << 16);
+        finOff[r] = (unsigned)base;
     }
 }
