@@ -155,7 +155,9 @@ def config_dict(args, world):
                         "(4%% sub, 3%% ins, 3%% del) per GPU" % args.reads,
             "reads_per_gpu": args.reads, "read_len": READ_LEN, "ref_len": REF_LEN, "k": K, "seed_rate": 40,
             "query_size": EDGE, "chunk_size": 10000, "circular": True,
-            "parallelism": "reads sharded over %d GPU(s), index replicated (rebuilt per GPU), no data-path collective" % world,
+            "parallelism": "reads sharded over %d GPU(s), index replicated (%s), no data-path collective" % (
+                world, "built on rank 0, one NCCL broadcast of its image" if world > 1 and args.index == "broadcast"
+                else "built per GPU"),
             "l2_policy": "inputs larger than L2 (%.1f GB ASCII per GPU per step; every step streams all of it)" % (
                 args.reads * READ_LEN / 1e9)}
 
@@ -212,9 +214,22 @@ def run_ours(args):
     vals = dp.kmer_values(counts, K)
     t1 = time.time()
     t_counts = t1 - t_c0
-    gm = dp.Mapper(ref, vals, circular=True, device=local)
-    torch.cuda.synchronize()
-    t_index = time.time() - t1
+    t_repl = 0.0
+    if world > 1 and args.index == "broadcast":
+        # the index is built once (rank 0) and replicated by ONE NCCL broadcast of its image over NVLink
+        gm = dp.Mapper(ref, vals, circular=True, device=local) if rank == 0 else None
+        torch.cuda.synchronize()
+        t_index = time.time() - t1
+        barrier(world)
+        t2 = time.time()
+        gm = dp.replicate_index(gm, src=0, device=local)
+        torch.cuda.synchronize()
+        barrier(world)
+        t_repl = time.time() - t2
+    else:
+        gm = dp.Mapper(ref, vals, circular=True, device=local)
+        torch.cuda.synchronize()
+        t_index = time.time() - t1
     info = gm.index_info()
 
     n = args.reads
@@ -279,6 +294,15 @@ def run_ours(args):
     dt_e2e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, dev)
     st_e2e = gm.stats()
 
+    # ---- per-kernel durations for the roofline: one extra untimed-for-`value` step on a single lane, so that the
+    #      CUDA-event brackets on the launching stream see each kernel alone (with several lanes the brackets of
+    #      concurrently running kernels overlap and each reads long) ----
+    os.environ["DP_LANES"] = "1"
+    step_device()
+    step_device()
+    iso = gm.stats()
+    del os.environ["DP_LANES"]
+
     total_bases = sum_over_ranks(float(bases_rank), world, dev)
     value = total_bases * args.steps / dt_dev / 1e9
     e2e = total_bases * args.steps / dt_e2e / 1e9
@@ -292,8 +316,8 @@ def run_ours(args):
     bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
     bytes_chain = 8.0 * agg["chain_cells"] / S
     kern = {}
-    for name, b, ms in (("pack", bytes_pack, agg["ms_pack"] / S), ("extract", bytes_extract, agg["ms_extract"] / S),
-                        ("lookup", bytes_lookup, agg["ms_lookup"] / S), ("chain", bytes_chain, agg["ms_chain"] / S)):
+    for name, b, ms in (("pack", bytes_pack, iso["ms_pack"]), ("extract", bytes_extract, iso["ms_extract"]),
+                        ("lookup", bytes_lookup, iso["ms_lookup"]), ("chain", bytes_chain, iso["ms_chain"])):
         ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
     dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])
@@ -312,9 +336,10 @@ def run_ours(args):
                 "peak_source": peak_src,
                 "note": "config 2's index (8.6 MB) and k-mer table (1 MB) are L2-resident, so no kernel of this workload "
                         "is bound by HBM (ncu: dram throughput < 2 % for every kernel; they are issue/latency bound, "
-                        "see profiles/). achieved = SURVEY 8d algorithmic bytes / CUDA-event time of the kernel on its "
-                        "launching stream, summed over the overlapping lanes (conservative). traffic = ncu dram bytes "
-                        "per launch of a 65536-read sub-batch",
+                        "see profiles/). achieved = SURVEY 8d algorithmic bytes of one step / CUDA-event time of that "
+                        "kernel family on its launching stream over one step run on a single lane (kernels not "
+                        "overlapping; the timed `value` steps run 6 lanes). traffic = ncu dram bytes per launch of a "
+                        "65536-read sub-batch",
                 "hbm_gather_ceiling_GBs": gather_gbs,
                 "lookup_vs_gather_ceiling": (sector_bytes_lookup / (kern["lookup"]["ms_per_step"] * 1e-3) / 1e9 / gather_gbs
                                              if gather_gbs and kern["lookup"]["ms_per_step"] > 0 else None),
@@ -335,7 +360,9 @@ def run_ours(args):
             "gpu_launches": int(agg["kernel_launches"]),
             "clocks": clocks, "roofline": roofline,
             "mapped_fraction": mapped_frac, "bases_per_step": total_bases,
-            "index": dict(info, build_s=t_index, kmer_count_and_values_s=t_counts),
+            "index": dict(info, build_s=t_index, replicate_s=t_repl, kmer_count_and_values_s=t_counts,
+                          replication=("one NCCL broadcast of the index image from rank 0" if world > 1 and
+                                       args.index == "broadcast" else "built on every rank")),
             "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
@@ -375,6 +402,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
+                    help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -66,12 +66,16 @@ _SIGNATURES = {
     "dp_mapper_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "dp_mapper_destroy": (None, [c_vp]),
+    "dp_mapper_index_image_size": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "dp_mapper_index_export": (ctypes.c_int, [c_vp, c_vp, c_i64]),
+    "dp_mapper_create_from_index": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "dp_mapper_map_batch": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "dp_mapper_map_batch_device": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp),
                                                   ctypes.POINTER(c_vp)]),
     "dp_mapper_paf_line": (ctypes.c_int, [c_vp, c_vp, ctypes.c_char_p, c_i64, ctypes.c_char_p, c_vp, ctypes.c_int]),
     "dp_mapper_get_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(Stats)]),
     "dp_mapper_index_info": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_mapper_params": (ctypes.c_int, [c_vp, c_vp]),
     "dp_mapper_seed_kmers": (ctypes.c_int, [c_vp, c_vp]),
     "dp_mapper_chunk": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dp_mapper_probe_window": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_i64,
@@ -198,6 +202,42 @@ class Mapper:
         self.edge_size = edge_size
         self.device = device
 
+    # ---- index image: replicate over GPUs / persist (dp_mapper_index_export, dp_mapper_create_from_index) ----
+    @classmethod
+    def from_index(cls, image_ptr, nbytes, device=0, ref_name="ref"):
+        """Open a mapper on `device` from an index image at address `image_ptr` (device or host memory)."""
+        h = c_vp()
+        _check(lib().dp_mapper_create_from_index(image_ptr, nbytes, device, ctypes.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.device = device
+        self.ref_name = ref_name
+        info = np.zeros(8, dtype=np.int64)
+        _check(lib().dp_mapper_params(h, info.ctypes.data))
+        self.k, self.circular, self.ref_len, self.edge_size = int(info[0]), bool(info[1]), int(info[2]), int(info[3])
+        return self
+
+    def index_image_size(self):
+        n = c_i64()
+        _check(lib().dp_mapper_index_image_size(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def export_index(self, image_ptr, nbytes):
+        """Write the index image to `image_ptr` (device or host memory, at least index_image_size() bytes)."""
+        _check(lib().dp_mapper_index_export(self._h, image_ptr, nbytes))
+
+    def save_index(self, path):
+        """On-disk index: the image bytes, as written by export_index into host memory."""
+        n = self.index_image_size()
+        buf = np.empty(n, dtype=np.uint8)
+        self.export_index(buf.ctypes.data, n)
+        buf.tofile(path)
+
+    @classmethod
+    def load_index(cls, path, device=0, ref_name="ref"):
+        buf = np.fromfile(path, dtype=np.uint8)
+        return cls.from_index(buf.ctypes.data, buf.size, device=device, ref_name=ref_name)
+
     def close(self):
         if self._h:
             lib().dp_mapper_destroy(self._h)
@@ -318,3 +358,26 @@ def NewMapper(reference, circular, k, kmer_values, seed_rate, edge_size, chunk_s
     goroutine pool is replaced by batched GPU rounds."""
     return Mapper(reference, kmer_values, circular=circular, k=k, seed_rate=seed_rate, edge_size=edge_size,
                   chunk_size=chunk_size, device=device)
+
+
+def replicate_index(mapper, src=0, device=0, group=None, ref_name="ref"):
+    """Index replication for read-sharded multi-GPU mapping: the rank `src` holds a built `mapper`; its
+    index image is broadcast ONCE over the process group (NCCL over NVLink when the group is an NCCL group) and every
+    other rank opens a mapper from it. Returns this rank's mapper. No other collective exists on the map path."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
+    size = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == src:
+        size[0] = mapper.index_image_size()
+    dist.broadcast(size, src=src, group=group)
+    n = int(size.item())
+    image = torch.empty(n, dtype=torch.uint8, device=dev)
+    if rank == src:
+        mapper.export_index(image.data_ptr(), n)
+    dist.broadcast(image, src=src, group=group)
+    if rank == src:
+        return mapper
+    return Mapper.from_index(image.data_ptr(), n, device=device, ref_name=ref_name)

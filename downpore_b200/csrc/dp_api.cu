@@ -156,6 +156,7 @@ struct dp_mapper {
     long long refLen = 0;
     // index
     DBuf<unsigned> refWords;
+    DBuf<unsigned char> image;  // set when the mapper was opened from an index image: I points into it
     DBuf<uint2> table;
     DBuf<unsigned> seedOff, seedChunks, chunkOff, chunkSeed, postOff, postChunk, filter;
     DBuf<int> chunkPos, chunkScanLen, postPos;
@@ -490,7 +491,8 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     I.chunkScanLen = M.chunkScanLen.p;
     M.nChunkPostings = (long long)P2;
     M.nSeedPostings = (long long)P1;
-    M.indexBytes = M.refWords.bytes() + M.table.bytes() + M.seedOff.bytes() + M.seedChunks.bytes() +
+    M.refWords.release();  // only index construction reads the packed reference
+    M.indexBytes = M.table.bytes() + M.seedOff.bytes() + M.seedChunks.bytes() +
                    M.chunkOff.bytes() + M.chunkPos.bytes() + M.chunkSeed.bytes() + M.chunkOffset.bytes() +
                    M.postOff.bytes() + M.postChunk.bytes() + M.postPos.bytes() + M.filter.bytes() +
                    M.chunkInset.bytes() + M.chunkScanLen.bytes();
@@ -1196,6 +1198,96 @@ __global__ void dp_gather_probe_kernel(const unsigned* __restrict__ table, unsig
 
 }  // namespace
 
+namespace {
+
+std::unique_ptr<dp_mapper> open_mapper(int device) {
+    int nDev = 0;
+    CK(cudaGetDeviceCount(&nDev));
+    if (nDev <= 0) throw std::runtime_error("no CUDA device");
+    if (device < 0 || device >= nDev) throw std::runtime_error("bad device ordinal");
+    CK(cudaSetDevice(device));
+    std::unique_ptr<dp_mapper> M(new dp_mapper());
+    M->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    M->smCount = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;  // numerically lowest value = highest priority
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&M->pullStream, cudaStreamNonBlocking, hi));
+    return M;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Index image: every array the map path reads, packed into one relocatable byte image behind a small header. One
+// image = one cudaMemcpy / one NCCL broadcast / one file write; a mapper opened from an image points into its copy.
+// ----------------------------------------------------------------------------------------------------------------
+enum { IX_TABLE = 0, IX_FILTER, IX_SEEDOFF, IX_SEEDCHUNKS, IX_POSTOFF, IX_POSTCHUNK, IX_POSTPOS, IX_CHUNKOFF,
+       IX_CHUNKPOS, IX_CHUNKSEED, IX_CHUNKOFFSET, IX_CHUNKINSET, IX_CHUNKSCANLEN, IX_CHUNKLEN, IX_N };
+
+struct DpImageHeader {
+    char magic[8];  // "DPB200IX"
+    uint32_t version;
+    int32_t k, circular, seedRate, edge, chunkSize, filterBits;
+    int64_t refLen;
+    uint32_t numSeeds, numChunks, maxChunkSeeds, pad;
+    int64_t nChunkPostings, nSeedPostings;
+    uint64_t totalBytes;
+    uint64_t off[IX_N], bytes[IX_N];
+};
+const uint32_t kImageVersion = 1;
+const size_t kImageAlign = 256;
+
+void image_layout(const dp_mapper& M, DpImageHeader& H) {
+    memset(&H, 0, sizeof(H));
+    memcpy(H.magic, "DPB200IX", 8);
+    H.version = kImageVersion;
+    H.k = M.k;
+    H.circular = M.circular;
+    H.seedRate = M.seedRate;
+    H.edge = M.edge;
+    H.chunkSize = M.chunkSize;
+    H.filterBits = M.filterBits;
+    H.refLen = M.refLen;
+    H.numSeeds = M.I.numSeeds;
+    H.numChunks = M.I.numChunks;
+    H.maxChunkSeeds = M.I.maxChunkSeeds;
+    H.nChunkPostings = M.nChunkPostings;
+    H.nSeedPostings = M.nSeedPostings;
+    const uint64_t S = M.I.numSeeds, C = M.I.numChunks, P1 = (uint64_t)M.nSeedPostings, P2 = (uint64_t)M.nChunkPostings;
+    H.bytes[IX_TABLE] = (((uint64_t)1 << (2 * M.k)) / 32) * sizeof(uint2);
+    H.bytes[IX_FILTER] = M.filterBits ? ((((uint64_t)1 << M.filterBits) + 31) / 32) * 4 : 0;
+    H.bytes[IX_SEEDOFF] = (S + 1) * 4;
+    H.bytes[IX_SEEDCHUNKS] = P1 * 4;
+    H.bytes[IX_POSTOFF] = (S + 1) * 4;
+    H.bytes[IX_POSTCHUNK] = P2 * 4;
+    H.bytes[IX_POSTPOS] = P2 * 4;
+    H.bytes[IX_CHUNKOFF] = (C + 1) * 4;
+    H.bytes[IX_CHUNKPOS] = P2 * 4;
+    H.bytes[IX_CHUNKSEED] = P2 * 4;
+    H.bytes[IX_CHUNKOFFSET] = C * 8;
+    H.bytes[IX_CHUNKINSET] = C * 8;
+    H.bytes[IX_CHUNKSCANLEN] = C * 4;
+    H.bytes[IX_CHUNKLEN] = C * 4;
+    uint64_t at = (sizeof(DpImageHeader) + kImageAlign - 1) / kImageAlign * kImageAlign;
+    for (int i = 0; i < IX_N; i++) {
+        H.off[i] = at;
+        at += (H.bytes[i] + kImageAlign - 1) / kImageAlign * kImageAlign;
+    }
+    H.totalBytes = at;
+}
+
+void check_image_header(const DpImageHeader& H, int64_t bytes) {
+    if (memcmp(H.magic, "DPB200IX", 8) != 0) throw std::runtime_error("not a downpore_b200 index image");
+    if (H.version != kImageVersion) throw std::runtime_error("index image version mismatch");
+    if ((int64_t)H.totalBytes > bytes) throw std::runtime_error("index image truncated");
+    if (H.k < 5 || H.k > 15 || H.numChunks == 0) throw std::runtime_error("index image header corrupt");
+    for (int i = 0; i < IX_N; i++)
+        if (H.off[i] % kImageAlign || H.off[i] + H.bytes[i] > H.totalBytes) throw std::runtime_error("index image layout corrupt");
+}
+
+}  // namespace
+
 #define API_TRY try {
 #define API_CATCH                      \
     }                                  \
@@ -1233,22 +1325,7 @@ int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, in
     if (chunk_size < 2 * edge_size || (long long)chunk_size * 10 - edge_size <= 0)
         throw std::runtime_error("chunk_size must be at least 2*query_size");
     if (ref_len < 2ll * edge_size || ref_len < seed_rate) throw std::runtime_error("reference shorter than 2*query_size");
-    int nDev = 0;
-    CK(cudaGetDeviceCount(&nDev));
-    if (nDev <= 0) throw std::runtime_error("no CUDA device");
-    if (device < 0 || device >= nDev) throw std::runtime_error("bad device ordinal");
-    CK(cudaSetDevice(device));
-    std::unique_ptr<dp_mapper> M(new dp_mapper());
-    M->device = device;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    M->smCount = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
-    {
-        int lo = 0, hi = 0;  // numerically lowest value = highest priority
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&M->pullStream, cudaStreamNonBlocking, hi));
-    }
+    std::unique_ptr<dp_mapper> M = open_mapper(device);
     M->k = k;
     M->circular = circular ? 1 : 0;
     M->seedRate = seed_rate;
@@ -1256,6 +1333,89 @@ int dp_mapper_create(const uint8_t* ref_ascii, int64_t ref_len, int circular, in
     M->chunkSize = chunk_size;
     M->refLen = ref_len;
     build_index(*M, ref_ascii, kmer_values);
+    *out = M.release();
+    API_CATCH
+}
+
+int dp_mapper_index_image_size(const dp_mapper* m, int64_t* bytes) {
+    API_TRY
+    if (!m || !bytes) throw std::runtime_error("null argument");
+    DpImageHeader H;
+    image_layout(*m, H);
+    *bytes = (int64_t)H.totalBytes;
+    API_CATCH
+}
+
+int dp_mapper_index_export(const dp_mapper* m, void* image, int64_t bytes) {
+    API_TRY
+    if (!m || !image) throw std::runtime_error("null argument");
+    CK(cudaSetDevice(m->device));
+    DpImageHeader H;
+    image_layout(*m, H);
+    if ((int64_t)H.totalBytes > bytes) throw std::runtime_error("image buffer too small");
+    const void* src[IX_N] = {m->I.table,       m->I.filter,      m->I.seedOff,     m->I.seedChunks,  m->I.postOff,
+                             m->I.postChunk,   m->I.postPos,     m->I.chunkOff,    m->I.chunkPos,    m->I.chunkSeed,
+                             m->I.chunkOffset, m->I.chunkInset,  m->I.chunkScanLen, m->hChunkLen.data()};
+    char* dst = static_cast<char*>(image);
+    CK(cudaMemcpy(dst, &H, sizeof(H), cudaMemcpyDefault));
+    for (int i = 0; i < IX_N; i++)
+        if (H.bytes[i]) CK(cudaMemcpy(dst + H.off[i], src[i], H.bytes[i], cudaMemcpyDefault));
+    CK(cudaDeviceSynchronize());
+    API_CATCH
+}
+
+int dp_mapper_create_from_index(const void* image, int64_t bytes, int device, dp_mapper** out) {
+    API_TRY
+    if (!image || !out || bytes < (int64_t)sizeof(DpImageHeader)) throw std::runtime_error("bad argument");
+    std::unique_ptr<dp_mapper> M = open_mapper(device);
+    DpImageHeader H;
+    CK(cudaMemcpy(&H, image, sizeof(H), cudaMemcpyDefault));
+    check_image_header(H, bytes);
+    M->image.reserve((size_t)H.totalBytes);
+    CK(cudaMemcpy(M->image.p, image, (size_t)H.totalBytes, cudaMemcpyDefault));
+    M->k = H.k;
+    M->circular = H.circular;
+    M->seedRate = H.seedRate;
+    M->edge = H.edge;
+    M->chunkSize = H.chunkSize;
+    M->filterBits = H.filterBits;
+    M->refLen = H.refLen;
+    M->nChunkPostings = H.nChunkPostings;
+    M->nSeedPostings = H.nSeedPostings;
+    M->indexBytes = M->image.bytes();
+    const unsigned char* b = M->image.p;
+    DpIndexDev& I = M->I;
+    I.k = H.k;
+    I.circular = H.circular;
+    I.edge = H.edge;
+    I.maxWindow = 2 * H.edge;
+    I.refLen = H.refLen;
+    I.numSeeds = H.numSeeds;
+    I.numChunks = H.numChunks;
+    I.maxChunkSeeds = H.maxChunkSeeds;
+    I.filterBits = H.filterBits;
+    I.table = reinterpret_cast<const uint2*>(b + H.off[IX_TABLE]);
+    I.filter = reinterpret_cast<const unsigned*>(b + H.off[IX_FILTER]);
+    I.seedOff = reinterpret_cast<const unsigned*>(b + H.off[IX_SEEDOFF]);
+    I.seedChunks = reinterpret_cast<const unsigned*>(b + H.off[IX_SEEDCHUNKS]);
+    I.postOff = reinterpret_cast<const unsigned*>(b + H.off[IX_POSTOFF]);
+    I.postChunk = reinterpret_cast<const unsigned*>(b + H.off[IX_POSTCHUNK]);
+    I.postPos = reinterpret_cast<const int*>(b + H.off[IX_POSTPOS]);
+    I.chunkOff = reinterpret_cast<const unsigned*>(b + H.off[IX_CHUNKOFF]);
+    I.chunkPos = reinterpret_cast<const int*>(b + H.off[IX_CHUNKPOS]);
+    I.chunkSeed = reinterpret_cast<const unsigned*>(b + H.off[IX_CHUNKSEED]);
+    I.chunkOffset = reinterpret_cast<const long long*>(b + H.off[IX_CHUNKOFFSET]);
+    I.chunkInset = reinterpret_cast<const long long*>(b + H.off[IX_CHUNKINSET]);
+    I.chunkScanLen = reinterpret_cast<const int*>(b + H.off[IX_CHUNKSCANLEN]);
+    const size_t C = H.numChunks;
+    M->hChunkOffset.resize(C);
+    M->hChunkInset.resize(C);
+    M->hChunkScanLen.resize(C);
+    M->hChunkLen.resize(C);
+    CK(cudaMemcpy(M->hChunkOffset.data(), I.chunkOffset, C * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(M->hChunkInset.data(), I.chunkInset, C * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(M->hChunkScanLen.data(), I.chunkScanLen, C * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(M->hChunkLen.data(), b + H.off[IX_CHUNKLEN], C * 4, cudaMemcpyDeviceToHost));
     *out = M.release();
     API_CATCH
 }
@@ -1311,12 +1471,25 @@ int dp_mapper_index_info(const dp_mapper* m, int64_t* out5) {
     return 0;
 }
 
+int dp_mapper_params(const dp_mapper* m, int64_t* out8) {
+    if (!m || !out8) return 1;
+    out8[0] = m->k;
+    out8[1] = m->circular;
+    out8[2] = m->refLen;
+    out8[3] = m->edge;
+    out8[4] = m->seedRate;
+    out8[5] = m->chunkSize;
+    out8[6] = m->filterBits;
+    out8[7] = m->device;
+    return 0;
+}
+
 int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out) {
     API_TRY
     CK(cudaSetDevice(m->device));
     size_t nTable = (size_t)((1ll << (2 * m->k)) / 32);
     std::vector<uint2> t(nTable);
-    CK(cudaMemcpy(t.data(), m->table.p, nTable * sizeof(uint2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(t.data(), m->I.table, nTable * sizeof(uint2), cudaMemcpyDeviceToHost));
     size_t p = 0;
     for (size_t w = 0; w < nTable; w++) {
         unsigned bits = t[w].x;
@@ -1335,16 +1508,16 @@ int dp_mapper_chunk(const dp_mapper* m, int64_t c, int64_t* fields4, int32_t* po
     if (c < 0 || c >= (int64_t)m->I.numChunks) throw std::runtime_error("chunk id out of range");
     CK(cudaSetDevice(m->device));
     unsigned off[2];
-    CK(cudaMemcpy(off, m->chunkOff.p + c, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(off, m->I.chunkOff + c, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
     unsigned n = off[1] - off[0];
     fields4[0] = m->hChunkOffset[(size_t)c];
     fields4[1] = m->hChunkInset[(size_t)c];
     fields4[2] = m->hChunkLen[(size_t)c];
     fields4[3] = n;
-    if (pos && n) CK(cudaMemcpy(pos, m->chunkPos.p + off[0], n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (pos && n) CK(cudaMemcpy(pos, m->I.chunkPos + off[0], n * sizeof(int), cudaMemcpyDeviceToHost));
     if (kmer && n) {
         std::vector<unsigned> ranks(n);
-        CK(cudaMemcpy(ranks.data(), m->chunkSeed.p + off[0], n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ranks.data(), m->I.chunkSeed + off[0], n * sizeof(unsigned), cudaMemcpyDeviceToHost));
         std::vector<int64_t> seeds(m->I.numSeeds);
         if (dp_mapper_seed_kmers(m, seeds.data())) throw std::runtime_error(g_err);
         for (unsigned i = 0; i < n; i++) kmer[i] = seeds[ranks[i]];

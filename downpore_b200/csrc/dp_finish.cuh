@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
                                                                unsigned long long* __restrict__ finCursor,
                                                                unsigned long long finCapacity) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const long long qlen = readLen[r];
+    const bool live = r < n;  // every lane stays for the warp-wide allocation below
+    const long long qlen = live ? readLen[r] : 0;
     const int e = I.edge;
     DpHit A[DP_FIN_CAP], B[DP_FIN_CAP], M[DP_FIN_CAP];
     int nOut = 0;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
     int nOut2 = 0;
     bool done = true;
     int nA = 0, nB = 0;
-    if (qlen >= minLen) {
+    if (live && qlen >= minLen) {
         nA = outN[2 * r];
         nB = outN[2 * r + 1];
         if (nA > DP_FIN_CAP || nB > DP_FIN_CAP) {
@@ -206,15 +206,28 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
             }
         }
     }
+    // one bump allocation per warp (a single-address atomic per read serialises in L2)
+    bool rawOk = true;
+    if (!done && (nA > 0xffff || nB > 0x7fff)) rawOk = false;
+    const int tot = !live ? 0 : (done ? nOut + nOut2 : (rawOk ? nA + nB : 0));
+    int incl = tot;
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(DP_FULL, incl, d);
+        if ((int)(threadIdx.x & 31) >= d) incl += y;
+    }
+    unsigned long long warpBase = 0;
+    const int warpTot = __shfl_sync(DP_FULL, incl, 31);
+    if ((threadIdx.x & 31) == 31 && warpTot) warpBase = atomicAdd(finCursor, (unsigned long long)warpTot);
+    warpBase = __shfl_sync(DP_FULL, warpBase, 31);
+    if (!live) return;
+    const unsigned long long base = warpBase + (unsigned)(incl - tot);
+    if (base + (unsigned)tot > finCapacity || !rawOk) {  // no room: the host path fetches the windows and redoes this read
+        status[r] = DP_READ_UNRESOLVED_NOHITS;
+        finN[r] = 0;
+        finOff[r] = 0;
+        return;
+    }
     if (done) {
-        const int tot = nOut + nOut2;
-        unsigned long long base = tot ? atomicAdd(finCursor, (unsigned long long)tot) : 0ull;
-        if (base + (unsigned)tot > finCapacity) {  // no room: let the host path redo this read
-            status[r] = DP_READ_UNRESOLVED_NOHITS;
-            finN[r] = 0;
-            finOff[r] = 0;
-            return;
-        }
         for (int i = 0; i < nOut; i++) finMaps[base + i] = dp_store_hit(outList[i]);
         for (int i = 0; i < nOut2; i++) finMaps[base + nOut + i] = dp_store_hit(outList2[i]);
         status[r] = DP_READ_DONE;
@@ -222,14 +235,6 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
         finOff[r] = (unsigned)base;
     } else {
         // hand the raw window hits to the host replay (removeDominated above worked on copies)
-        const int tot = nA + nB;
-        unsigned long long base = tot ? atomicAdd(finCursor, (unsigned long long)tot) : 0ull;
-        if (base + (unsigned)tot > finCapacity || nA > 0xffff || nB > 0x7fff) {
-            status[r] = DP_READ_UNRESOLVED_NOHITS;
-            finN[r] = 0;
-            finOff[r] = 0;
-            return;
-        }
         for (int i = 0; i < nA; i++) finMaps[base + i] = outMaps[outOff[2 * r] + i];
         for (int i = 0; i < nB; i++) finMaps[base + nA + i] = outMaps[outOff[2 * r + 1] + i];
         status[r] = DP_READ_UNRESOLVED;

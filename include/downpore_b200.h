@@ -103,6 +103,20 @@ int dp_mapper_get_stats(const dp_mapper* m, dp_stats* out);
  * seed_postings (distinct (seed,chunk) pairs), index_bytes on device}. */
 int dp_mapper_index_info(const dp_mapper* m, int64_t* out5);
 
+/*
+ * Index image: the whole seed index (k-mer table, prefix filter, seed->chunk and seed->posting CSRs, chunk table) as
+ * one relocatable byte image. It is what gets replicated when reads are sharded over several GPUs — build on one GPU,
+ * export into a device buffer, broadcast it once over NVLink (NCCL), open a mapper from it on every other GPU — and
+ * what an on-disk index is (export into host memory, write the bytes). `image` may be device or host memory in both
+ * directions. A mapper opened from an image maps identically to the mapper it was exported from.
+ */
+int dp_mapper_index_image_size(const dp_mapper* m, int64_t* bytes);
+int dp_mapper_index_export(const dp_mapper* m, void* image, int64_t bytes);
+int dp_mapper_create_from_index(const void* image, int64_t bytes, int device, dp_mapper** out);
+
+/* The mapper's parameters: out8 = {k, circular, ref_len, query_size, seed_rate, chunk_size, filter_bits, device}. */
+int dp_mapper_params(const dp_mapper* m, int64_t* out8);
+
 /* Test probes (stage dumps for parity tests; not needed by a host). */
 /* seed k-mers, ascending k-mer value; out must hold num_seeds entries */
 int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out);

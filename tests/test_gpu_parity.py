@@ -211,3 +211,48 @@ def test_large_reference_global_counters():
     for key in ("windows", "posting_runs", "posting_entries", "candidates", "chain_cells"):
         assert st[key] == octr[key], key
     gm.close()
+
+
+def test_index_image_round_trip(tmp_path):
+    """dp_mapper_index_export / dp_mapper_create_from_index: a mapper opened from an image (host memory, a file, or a
+    device buffer — what the NCCL broadcast delivers) maps exactly like the mapper that was built from the reference."""
+    import torch
+    ref = synth.reference(8, 400_000)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    gm = dp.Mapper(ref, vals, circular=True)
+    reads = mixed_reads(ref, True, seed=17, n=150, rl=6000)
+    bases = np.concatenate(reads)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    want_maps, want_off = gm.map_batch(bases, offs)
+    n = gm.index_image_size()
+    assert n > 1 << 20
+    # (a) host image
+    host = np.empty(n, dtype=np.uint8)
+    gm.export_index(host.ctypes.data, n)
+    assert bytes(host[:8]) == b"DPB200IX"
+    m2 = dp.Mapper.from_index(host.ctypes.data, n)
+    # (b) file
+    path = os.path.join(str(tmp_path), "ref.dpix")
+    gm.save_index(path)
+    m3 = dp.Mapper.load_index(path)
+    # (c) device buffer
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    gm.export_index(dev.data_ptr(), n)
+    m4 = dp.Mapper.from_index(dev.data_ptr(), n)
+    del dev
+    for m in (m2, m3, m4):
+        assert m.index_info()["num_seeds"] == gm.index_info()["num_seeds"]
+        assert (m.k, m.circular, m.ref_len, m.edge_size) == (gm.k, gm.circular, gm.ref_len, gm.edge_size)
+        maps, off = m.map_batch(bases, offs)
+        assert np.array_equal(off, want_off) and np.array_equal(rows_of(maps), rows_of(want_maps))
+        c = m.chunk(3)
+        assert np.array_equal(c["pos"], gm.chunk(3)["pos"]) and np.array_equal(c["kmer"], gm.chunk(3)["kmer"])
+        m.close()
+    # a truncated or foreign image is refused
+    with pytest.raises(dp.DownporeError):
+        dp.Mapper.from_index(host.ctypes.data, n // 2)
+    bad = host.copy()
+    bad[:8] = 0
+    with pytest.raises(dp.DownporeError):
+        dp.Mapper.from_index(bad.ctypes.data, n)
+    gm.close()

@@ -61,3 +61,49 @@ def test_shard_bounds_cover_everything():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in edges) - min(h - l for l, h in edges) <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# replicate_index (the one exchange step of the multi-GPU path): rank 0's index image is broadcast once;
+# on the CPU tier the image is a stand-in byte string and Mapper.from_index is intercepted (no GPU here).
+class _FakeMapper:
+    def __init__(self, blob):
+        self.blob = blob
+
+    def index_image_size(self):
+        return len(self.blob)
+
+    def export_index(self, ptr, n):
+        import ctypes
+        assert n == len(self.blob)
+        ctypes.memmove(ptr, self.blob, n)
+
+
+def _replicate_worker(rank, world, port, out_dir):
+    import ctypes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import downpore_b200 as dp
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    blob = bytes(np.random.default_rng(3).integers(0, 256, 100_003, dtype=np.uint8))
+    got = {}
+
+    def fake_from_index(image_ptr, nbytes, device=0, ref_name="ref"):
+        got["bytes"] = ctypes.string_at(image_ptr, nbytes)
+        return "opened-from-image"
+
+    dp.Mapper.from_index = staticmethod(fake_from_index)
+    src = _FakeMapper(blob) if rank == 0 else None
+    m = dp.replicate_index(src, src=0, device=0)
+    if rank == 0:
+        assert m is src
+    else:
+        assert m == "opened-from-image" and got["bytes"] == blob
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_replicate_index_broadcasts_the_image(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_replicate_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
