@@ -1056,13 +1056,14 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     std::vector<int64_t> cuts;
     cuts.push_back(0);
     {
-        const int64_t full = kSubBatchReads, tail = full / 4 + full / 2;
-        int idx = 0;
+        const bool ramp = !(getenv("DP_RAMP") && atoi(getenv("DP_RAMP")) == 0);  // DP_RAMP=0: equal pieces (profiling)
+        const int64_t full = kSubBatchReads, tail = ramp ? full / 4 + full / 2 : 0;
+        int idx = ramp ? 0 : 2;
         for (int64_t r0 = 0; r0 < n_reads; idx++) {
             int64_t remaining = n_reads - r0;
             int64_t want = std::min<int64_t>(full, (full / 4) << std::min(idx, 2));
             if (remaining > tail) want = std::min(want, remaining - tail);
-            else if (remaining > full / 4) want = remaining - full / 4;
+            else if (ramp && remaining > full / 4) want = remaining - full / 4;
             else want = remaining;
             int64_t r1 = r0;
             while (r1 < n_reads && r1 - r0 < want && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
