@@ -145,6 +145,15 @@ def kmer_counts(ascii_seq, k, counts=None, device=0):
     return counts
 
 
+def host_alloc(nbytes):
+    """dp_host_alloc: page-locked, device-mapped host memory as a uint8 numpy array (freed with the array)."""
+    p = c_vp()
+    _check(lib().dp_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_ubyte * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib().dp_host_free, p.value)
+    return np.frombuffer(buf, dtype=np.uint8)
+
+
 def probe_gather_gbs(table_bytes=8 << 30, device=0):
     """Random 32 B-sector gather bandwidth (GB/s of sector traffic) over a table >> L2: the HBM gather roofline."""
     out = ctypes.c_double()

@@ -121,6 +121,13 @@ struct Lane {
     DBuf<unsigned long long> csEnt;
     DBuf<int> csRqPos, csRsPos, csChainLen, csLastB, csChains;
     DBuf<DpMappingDev> csResults;
+    // fast chain path: tasks, list pool, hand-back list
+    DBuf<DpChainTask> fcTasks;
+    DBuf<unsigned> fcTaskBase, fcPool;
+    DBuf<unsigned long long> fcCursors;  // [0] tasks, [1] pool words, [2] low word = hand-back count
+    DBuf<unsigned char> fcSlow;
+    DBuf<int> fcSlowList;
+    size_t fcTaskCap = 0, fcPoolCap = 0;
     HBuf<int> hOutN, hFinN;
     HBuf<unsigned> hOutOff, hFinOff;
     HBuf<unsigned char> hStatus, hStage;
@@ -556,6 +563,17 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.csRsId.reserve(cw * sStride);
     W.csChains.reserve(cw * M.chainCap * 6);
     W.csResults.reserve(cw * M.resultCap);
+    // fast chain path: ~1.5 candidates and ~40 list entries per window on ONT-like reads; whatever does not fit is
+    // handed back to the general kernel, so these sizes are a speed knob, not a limit
+    W.fcTaskCap = nWin * 8 + 1024;
+    W.fcPoolCap = getenv("DP_FAST_POOL_WORDS") ? (size_t)atoll(getenv("DP_FAST_POOL_WORDS")) : nWin * 256 + 4096;
+    if (W.fcPoolCap > 0xfff00000ull) W.fcPoolCap = 0xfff00000ull;
+    W.fcTasks.reserve(W.fcTaskCap);
+    W.fcTaskBase.reserve(2 * nWin);
+    W.fcPool.reserve(W.fcPoolCap);
+    W.fcCursors.reserve(4);
+    W.fcSlow.reserve(nWin);
+    W.fcSlowList.reserve(nWin);
 }
 
 enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_N };
@@ -670,11 +688,42 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int warpsPerBlock = 4;
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock,
                                            (size_t)M.smCount * (W.curAsciiIsHost ? 4 : 6));
+        const unsigned long long outCap = (unsigned long long)nWin * M.outStride;
+        const bool fast = !(getenv("DP_CHAIN_FAST") && atoi(getenv("DP_CHAIN_FAST")) == 0);
         CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
-        dp_chain_kernel<<<blocks, 128, 0, st>>>(I, W.dWins.p, dReadLen, (int)nWin, Q, W.candN.p, W.candChunk.p,
-                                                W.candDistinct.p, W.candStride, S, W.outN.p, W.outOff.p, W.outMaps.p,
-                                                W.cursor.p + CUR_OUT, (unsigned long long)nWin * M.outStride, W.dCtr.p);
-        CK(cudaGetLastError());
+        if (fast) {
+            DpFastChain F;
+            F.tasks = W.fcTasks.p;
+            F.taskBase = W.fcTaskBase.p;
+            F.pool = W.fcPool.p;
+            F.cursors = W.fcCursors.p;
+            F.taskCap = W.fcTaskCap;
+            F.poolCap = W.fcPoolCap;
+            F.slow = W.fcSlow.p;
+            F.slowList = W.fcSlowList.p;
+            F.nSlow = reinterpret_cast<int*>(W.fcCursors.p + 2);
+            CK(cudaMemsetAsync(W.fcCursors.p, 0, 4 * sizeof(unsigned long long), st));
+            int rBlocks = (int)std::min<size_t>((nWin + 3) / 4, (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
+            dp_reduce_kernel<<<rBlocks, 128, 0, st>>>(I, W.dWins.p, (int)nWin, Q, W.candN.p, W.candChunk.p,
+                                                      W.candDistinct.p, W.candStride, S, F);
+            CK(cudaGetLastError());
+            dp_chain_thread_kernel<<<div_up((long long)nWin, 128), 128, 0, st>>>(
+                I, W.dWins.p, dReadLen, (int)nWin, Q, W.candN.p, W.candChunk.p, W.candDistinct.p, W.candStride, F,
+                W.outN.p, W.outOff.p, W.outMaps.p, W.cursor.p + CUR_OUT, outCap, W.dCtr.p);
+            CK(cudaGetLastError());
+            // windows the fast path handed back (none on typical data: the kernel then exits at once)
+            int sBlocks = std::min(blocks, M.smCount * 2);
+            dp_chain_kernel<<<sBlocks, 128, 0, st>>>(I, W.dWins.p, F.slowList, F.nSlow, dReadLen, (int)nWin, Q, W.candN.p,
+                                                     W.candChunk.p, W.candDistinct.p, W.candStride, S, W.outN.p,
+                                                     W.outOff.p, W.outMaps.p, W.cursor.p + CUR_OUT, outCap, W.dCtr.p);
+            CK(cudaGetLastError());
+            W.stats.kernel_launches += 2;
+        } else {
+            dp_chain_kernel<<<blocks, 128, 0, st>>>(I, W.dWins.p, nullptr, nullptr, dReadLen, (int)nWin, Q, W.candN.p,
+                                                    W.candChunk.p, W.candDistinct.p, W.candStride, S, W.outN.p,
+                                                    W.outOff.p, W.outMaps.p, W.cursor.p + CUR_OUT, outCap, W.dCtr.p);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(W.timers[T_CHAIN].b, st));
     }
     W.stats.kernel_launches += 3;
@@ -1307,7 +1356,9 @@ void dp_free(void* p) { free(p); }
 int dp_host_alloc(void** out, size_t bytes) {
     API_TRY
     if (!out) throw std::runtime_error("null argument");
-    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    unsigned flags = cudaHostAllocPortable | cudaHostAllocMapped;
+    if (getenv("DP_HOST_WC") && atoi(getenv("DP_HOST_WC"))) flags |= cudaHostAllocWriteCombined;
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, flags));
     API_CATCH
 }
 

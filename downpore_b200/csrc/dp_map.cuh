@@ -826,7 +826,175 @@ __device__ int dp_dynamic_match(const DpChainLists& T, int minMatch, int k, int*
     return nGood;
 }
 
+// Working arrays of one warp for the lists of one candidate (shared memory; global scratch for oversized lists)
+struct DpListBuf {
+    unsigned short* qFirst;  // [n] index of the first occurrence of each query entry's seed (seed identity)
+    unsigned short* qCnt;    // [n] postings of the seed inside the candidate chunk (first occurrences only)
+    unsigned* qLo;           // [n] first such posting
+    int* rqPos;              // reduced query list
+    unsigned short* rqId;
+    unsigned long long* shEnt;  // chunk side, DP_MCAP entries of shared memory ...
+    int* shRsPos;
+    unsigned short* shRsId;
+    unsigned long long* gEnt;   // ... or sStride entries of global scratch
+    int* gRsPos;
+    unsigned short* gRsId;
+    int sStride;
+};
+
+// seed identity = index of the first occurrence of the seed in this strand's list (warp-collective)
+__device__ __forceinline__ void dp_seed_identity(const DpExtractOut& Q, unsigned qb, int n, unsigned short* qFirst) {
+    const unsigned lane = dp_lane();
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        int j = j0 + (int)lane;
+        unsigned s = j < n ? Q.qSeed[qb + j] : (0x80000000u | lane);  // padding lanes never match
+        unsigned mm = __match_any_sync(DP_FULL, s);
+        int first = j0 + __ffs(mm) - 1;
+        if (j < n && j0 > 0) {
+            for (int b = 0; b < j0; b++)
+                if (Q.qSeed[qb + b] == s) {
+                    first = b;
+                    break;
+                }
+        }
+        if (j < n) qFirst[j] = (unsigned short)first;
+    }
+    __syncwarp();
+}
+
+// query.Reduced(chunkSet) and chunk.Reduced(querySet) for candidate chunk c (sequence.go:85-123), warp-collective.
+// Returns false if the chunk side does not fit the scratch. Outputs: nq entries in B.rqPos/B.rqId; ns entries in
+// *rsPosOut / *rsIdOut (shared or global, depending on size).
+__device__ bool dp_build_lists(const DpIndexDev& I, const DpExtractOut& Q, unsigned qb, int n, unsigned c,
+                               const DpListBuf& B, int& nqOut, int& nsOut, int*& rsPosOut, unsigned short*& rsIdOut) {
+    const unsigned lane = dp_lane();
+    const unsigned lt = dp_lanemask_lt();
+    // every distinct query seed looks up its postings inside chunk c
+    int m = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        int j = j0 + (int)lane;
+        unsigned lo = 0;
+        int cnt = 0;
+        if (j < n && B.qFirst[j] == j) {
+            unsigned s = Q.qSeed[qb + j];
+            unsigned b = __ldg(I.postOff + s), e = __ldg(I.postOff + s + 1);
+            unsigned hi = e;
+            lo = b;
+            while (lo < hi) {
+                unsigned mid = (lo + hi) >> 1;
+                if (__ldg(I.postChunk + mid) < c) lo = mid + 1;
+                else hi = mid;
+            }
+            while (lo + cnt < e && cnt < 65535 && __ldg(I.postChunk + lo + cnt) == c) cnt++;
+        }
+        if (j < n) {
+            B.qLo[j] = lo;
+            B.qCnt[j] = (unsigned short)cnt;
+        }
+        unsigned x = (unsigned)cnt;
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(DP_FULL, x, d);
+        m += (int)x;
+    }
+    __syncwarp();
+    // query.Reduced(chunkSet): entries whose seed occurs in the chunk, same-as-previous-member collapsed.
+    // (Both Reduced calls precede the nil test, sequence.go:366-374.)
+    int nq = 0;
+    int prevMember = -1;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        int j = j0 + (int)lane;
+        int id = -2 - (int)lane;
+        bool member = false;
+        if (j < n) {
+            id = B.qFirst[j];
+            member = B.qCnt[id] != 0;
+        }
+        unsigned mm = __ballot_sync(DP_FULL, member);
+        unsigned lower = mm & lt;
+        int src = lower ? 31 - __clz(lower) : 0;
+        int pid = __shfl_sync(DP_FULL, id, src);
+        if (!lower) pid = prevMember;
+        bool keep = member && id != pid;
+        unsigned mk = __ballot_sync(DP_FULL, keep);
+        if (keep) {
+            int idx = nq + __popc(mk & lt);
+            B.rqId[idx] = (unsigned short)id;
+            B.rqPos[idx] = Q.qPos[qb + j];
+        }
+        nq += __popc(mk);
+        if (mm) prevMember = __shfl_sync(DP_FULL, id, 31 - __clz(mm));
+    }
+    nqOut = nq;
+    // chunk.Reduced(querySet): gather (position, seed) pairs, rank-sort by position, collapse
+    if (m > B.sStride) return false;  // cannot happen: a chunk has at most maxChunkSeeds entries
+    const bool sSmall = m <= DP_MCAP;
+    unsigned long long* ent = sSmall ? B.shEnt : B.gEnt;
+    int* rsPos = sSmall ? B.shRsPos : B.gRsPos;
+    unsigned short* rsId = sSmall ? B.shRsId : B.gRsId;
+    {
+        int base = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            int j = j0 + (int)lane;
+            int cnt = j < n ? (int)B.qCnt[j] : 0;
+            int x = cnt;  // inclusive scan
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(DP_FULL, x, d);
+                if ((int)lane >= d) x += y;
+            }
+            int off = base + x - cnt;
+            if (cnt) {
+                unsigned lo = B.qLo[j];
+                for (int t = 0; t < cnt; t++)
+                    ent[off + t] = ((unsigned long long)(unsigned)__ldg(I.postPos + lo + t) << 32) | (unsigned)j;
+            }
+            base += __shfl_sync(DP_FULL, x, 31);
+        }
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < m; i0 += 32) {  // scan positions inside a chunk are distinct: ranks are unique
+        int i = i0 + (int)lane;
+        if (i < m) {
+            unsigned long long mine = ent[i];
+            int rank = 0;
+            for (int x = 0; x < m; x++) rank += (ent[x] >> 32) < (mine >> 32);
+            rsPos[rank] = (int)(mine >> 32);
+            rsId[rank] = (unsigned short)(mine & 0xffffu);
+        }
+    }
+    __syncwarp();
+    int ns = 0;
+    prevMember = -1;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+        int i = i0 + (int)lane;
+        int id = -2 - (int)lane, pos = 0;
+        if (i < m) {
+            id = rsId[i];
+            pos = rsPos[i];
+        }
+        int pid = __shfl_up_sync(DP_FULL, id, 1);
+        if (lane == 0) pid = prevMember;
+        bool keep = i < m && id != pid;
+        unsigned mk = __ballot_sync(DP_FULL, keep);
+        __syncwarp();
+        if (keep) {
+            int idx = ns + __popc(mk & lt);
+            rsId[idx] = (unsigned short)id;
+            rsPos[idx] = pos;
+        }
+        ns += __popc(mk);
+        prevMember = __shfl_sync(DP_FULL, id, 31);
+        __syncwarp();
+    }
+    nsOut = ns;
+    rsPosOut = rsPos;
+    rsIdOut = rsId;
+    return true;
+}
+
+// Exact general path, one warp per window: used for the windows the fast path (dp_reduce_kernel + dp_chain_thread_kernel
+// below) hands back (`winList` / `nWinList` set), and for everything when the fast path is switched off.
 __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const DpWindow* __restrict__ wins,
+                                                       const int* __restrict__ winList,
+                                                       const int* __restrict__ nWinList,
                                                        const int* __restrict__ readLen, int nWin, DpExtractOut Q,
                                                        const int* __restrict__ candN,
                                                        const unsigned* __restrict__ candChunk,
@@ -858,7 +1026,9 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
     DpMappingDev* results = S.results + (size_t)gwarp * S.resultCap;
     unsigned long long cCells = 0, cMaps = 0;
 
-    for (int w = gwarp; w < nWin; w += nWarps) {
+    const int nTodo = winList ? min(*nWinList, nWin) : nWin;
+    for (int wi = gwarp; wi < nTodo; wi += nWarps) {
+        const int w = winList ? winList[wi] : wi;
         DpWindow win = wins[w];
         const int L = win.len;
         const int rlen = readLen[win.read];
@@ -888,143 +1058,32 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
             unsigned short* rqId = qSmall ? shRqId[wib] : S.rqId + (size_t)gwarp * S.qStride;
             int* chainLen = qSmall ? shChainLen[wib] : S.chainLen + (size_t)gwarp * S.qStride;
             int* lastB = qSmall ? shLastB[wib] : S.lastB + (size_t)gwarp * S.qStride;
-            // ---- seed identity = index of the first occurrence of the seed in this strand's list ----
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                int j = j0 + (int)lane;
-                unsigned s = j < n ? Q.qSeed[qb + j] : (0x80000000u | lane);  // padding lanes never match
-                unsigned mm = __match_any_sync(DP_FULL, s);
-                int first = j0 + __ffs(mm) - 1;
-                if (j < n && j0 > 0) {
-                    for (int b = 0; b < j0; b++)
-                        if (Q.qSeed[qb + b] == s) {
-                            first = b;
-                            break;
-                        }
-                }
-                if (j < n) qFirst[j] = (unsigned short)first;
-            }
-            __syncwarp();
+            DpListBuf LB;
+            LB.qFirst = qFirst;
+            LB.qCnt = qCnt;
+            LB.qLo = qLo;
+            LB.rqPos = rqPos;
+            LB.rqId = rqId;
+            LB.shEnt = shEnt[wib];
+            LB.shRsPos = shRsPos[wib];
+            LB.shRsId = shRsId[wib];
+            LB.gEnt = S.ent + (size_t)gwarp * S.sStride;
+            LB.gRsPos = S.rsPos + (size_t)gwarp * S.sStride;
+            LB.gRsId = S.rsId + (size_t)gwarp * S.sStride;
+            LB.sStride = S.sStride;
+            dp_seed_identity(Q, qb, n, qFirst);
             for (int ci = 0; ci < nc; ci++) {
                 const int thr = strand == 0 ? minMatches : minRCMatches;
                 // 1. CountIntersectionTo(...) < threshold (mapping.go:520-523, 559-562)
                 if ((int)candDistinct[(size_t)ws * candStride + ci] < thr) continue;
                 const unsigned c = candChunk[(size_t)ws * candStride + ci];
-                // 2. every distinct query seed looks up its postings inside chunk c
-                int m = 0;
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    int j = j0 + (int)lane;
-                    unsigned lo = 0;
-                    int cnt = 0;
-                    if (j < n && qFirst[j] == j) {
-                        unsigned s = Q.qSeed[qb + j];
-                        unsigned b = __ldg(I.postOff + s), e = __ldg(I.postOff + s + 1);
-                        unsigned hi = e;
-                        lo = b;
-                        while (lo < hi) {
-                            unsigned mid = (lo + hi) >> 1;
-                            if (__ldg(I.postChunk + mid) < c) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        while (lo + cnt < e && cnt < 65535 && __ldg(I.postChunk + lo + cnt) == c) cnt++;
-                    }
-                    if (j < n) {
-                        qLo[j] = lo;
-                        qCnt[j] = (unsigned short)cnt;
-                    }
-                    unsigned x = (unsigned)cnt;
-                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(DP_FULL, x, d);
-                    m += (int)x;
-                }
-                __syncwarp();
-                // 3. query.Reduced(chunkSet) (sequence.go:85-123): entries whose seed occurs in the chunk,
-                //    same-as-previous-member collapsed. (Both Reduced calls precede the nil test, sequence.go:366-374.)
-                int nq = 0;
-                int prevMember = -1;
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    int j = j0 + (int)lane;
-                    int id = -2 - (int)lane;
-                    bool member = false;
-                    if (j < n) {
-                        id = qFirst[j];
-                        member = qCnt[id] != 0;
-                    }
-                    unsigned mm = __ballot_sync(DP_FULL, member);
-                    unsigned lower = mm & lt;
-                    int src = lower ? 31 - __clz(lower) : 0;
-                    int pid = __shfl_sync(DP_FULL, id, src);
-                    if (!lower) pid = prevMember;
-                    bool keep = member && id != pid;
-                    unsigned mk = __ballot_sync(DP_FULL, keep);
-                    if (keep) {
-                        int idx = nq + __popc(mk & lt);
-                        rqId[idx] = (unsigned short)id;
-                        rqPos[idx] = Q.qPos[qb + j];
-                    }
-                    nq += __popc(mk);
-                    if (mm) prevMember = __shfl_sync(DP_FULL, id, 31 - __clz(mm));
-                }
-                // 4. chunk.Reduced(querySet): gather (position, seed) pairs, rank-sort by position, collapse
-                if (m > S.sStride) {  // cannot happen: a chunk has at most maxChunkSeeds entries
+                // 2.-4. query.Reduced(chunkSet) and chunk.Reduced(querySet)
+                int nq, ns;
+                int* rsPos;
+                unsigned short* rsId;
+                if (!dp_build_lists(I, Q, qb, n, c, LB, nq, ns, rsPos, rsId)) {
                     overflow = true;
                     continue;
-                }
-                const bool sSmall = m <= DP_MCAP;
-                unsigned long long* ent = sSmall ? shEnt[wib] : S.ent + (size_t)gwarp * S.sStride;
-                int* rsPos = sSmall ? shRsPos[wib] : S.rsPos + (size_t)gwarp * S.sStride;
-                unsigned short* rsId = sSmall ? shRsId[wib] : S.rsId + (size_t)gwarp * S.sStride;
-                {
-                    int base = 0;
-                    for (int j0 = 0; j0 < n; j0 += 32) {
-                        int j = j0 + (int)lane;
-                        int cnt = j < n ? (int)qCnt[j] : 0;
-                        int x = cnt;  // inclusive scan
-                        for (int d = 1; d < 32; d <<= 1) {
-                            int y = __shfl_up_sync(DP_FULL, x, d);
-                            if ((int)lane >= d) x += y;
-                        }
-                        int off = base + x - cnt;
-                        if (cnt) {
-                            unsigned lo = qLo[j];
-                            for (int t = 0; t < cnt; t++)
-                                ent[off + t] = ((unsigned long long)(unsigned)__ldg(I.postPos + lo + t) << 32) | (unsigned)j;
-                        }
-                        base += __shfl_sync(DP_FULL, x, 31);
-                    }
-                }
-                __syncwarp();
-                for (int i0 = 0; i0 < m; i0 += 32) {  // scan positions inside a chunk are distinct: ranks are unique
-                    int i = i0 + (int)lane;
-                    if (i < m) {
-                        unsigned long long mine = ent[i];
-                        int rank = 0;
-                        for (int x = 0; x < m; x++) rank += (ent[x] >> 32) < (mine >> 32);
-                        rsPos[rank] = (int)(mine >> 32);
-                        rsId[rank] = (unsigned short)(mine & 0xffffu);
-                    }
-                }
-                __syncwarp();
-                int ns = 0;
-                prevMember = -1;
-                for (int i0 = 0; i0 < m; i0 += 32) {
-                    int i = i0 + (int)lane;
-                    int id = -2 - (int)lane, pos = 0;
-                    if (i < m) {
-                        id = rsId[i];
-                        pos = rsPos[i];
-                    }
-                    int pid = __shfl_up_sync(DP_FULL, id, 1);
-                    if (lane == 0) pid = prevMember;
-                    bool keep = i < m && id != pid;
-                    unsigned mk = __ballot_sync(DP_FULL, keep);
-                    __syncwarp();
-                    if (keep) {
-                        int idx = ns + __popc(mk & lt);
-                        rsId[idx] = (unsigned short)id;
-                        rsPos[idx] = pos;
-                    }
-                    ns += __popc(mk);
-                    prevMember = __shfl_sync(DP_FULL, id, 31);
-                    __syncwarp();
                 }
                 if (ns < thr || nq < thr) continue;  // Reduced returned nil
                 cCells += (unsigned)(ns + nq);
@@ -1138,5 +1197,442 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
     if (lane == 0 && (cCells | cMaps)) {
         atomicAdd(&ctr->chain_cells, cCells);
         atomicAdd(&ctr->mappings, cMaps);
+    }
+}
+
+// ===============================================================================================================
+// Stage 3, fast path = the same computation as dp_chain_kernel split where its parallelism changes shape:
+//   dp_reduce_kernel        one WARP per window: for every candidate that passes the window's INITIAL thresholds,
+//                           builds the two reduced lists (warp-parallel) and stores them in a compact pool;
+//   dp_chain_thread_kernel  one THREAD per window: the sequential part — the threshold escalation over candidates
+//                           (Q12), dynamicMatch/extendChain, chains -> mappings, sort + dedupe — which in
+//                           dp_chain_kernel occupies one lane of a warp while 31 idle.
+// Thresholds only grow while a window is processed, so a candidate that fails the initial ones fails the final ones:
+// building lists under the initial thresholds is a superset of what the sequential pass needs.
+// Every bounded resource of the fast path (list pool, 8 chains per candidate, 8 mappings per window) has an exact way
+// out: the window is appended to `slowList` and recomputed by dp_chain_kernel, whose scratch is sized for the worst
+// case. Results are identical either way.
+// ===============================================================================================================
+#define DP_FAST_CHAINS 8
+#define DP_FAST_RESULTS 8
+
+struct DpChainTask {  // one candidate whose lists were built
+    unsigned listOff;  // pool offset: nq query entries, ns chunk entries, nq memo words
+    unsigned short nq, ns;  // nq == 0xffff: not built (failed the initial thresholds)
+};
+
+struct DpFastChain {
+    DpChainTask* tasks;        // [taskCap]
+    unsigned* taskBase;        // [2*nWin] first task of each window strand (valid where candN > 0)
+    unsigned* pool;            // packed entries: scan position << 16 | seed identity
+    unsigned long long* cursors;  // [0] tasks, [1] pool words
+    unsigned long long taskCap, poolCap;
+    unsigned char* slow;       // [nWin] window handed to the general path
+    int* slowList;             // [nWin]
+    int* nSlow;
+};
+
+__device__ __forceinline__ void dp_mark_slow(const DpFastChain& F, int w) {
+    F.slow[w] = 1;
+    F.slowList[atomicAdd(F.nSlow, 1)] = w;
+}
+
+__global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const DpWindow* __restrict__ wins, int nWin,
+                                                           DpExtractOut Q, const int* __restrict__ candN,
+                                                           const unsigned* __restrict__ candChunk,
+                                                           const unsigned short* __restrict__ candDistinct,
+                                                           int candStride, DpChainScratch S, DpFastChain F) {
+    __shared__ unsigned short shFirst[4][DP_QCAP];
+    __shared__ unsigned short shCnt[4][DP_QCAP];
+    __shared__ unsigned shLo[4][DP_QCAP];
+    __shared__ int shRqPos[4][DP_QCAP];
+    __shared__ unsigned short shRqId[4][DP_QCAP];
+    __shared__ unsigned long long shEnt[4][DP_MCAP];
+    __shared__ int shRsPos[4][DP_MCAP];
+    __shared__ unsigned short shRsId[4][DP_MCAP];
+    const unsigned lane = dp_lane();
+    const int wib = threadIdx.x >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = gwarp; w < nWin; w += nWarps) {
+        if (lane == 0) F.slow[w] = 0;
+        bool slow = false;
+        for (int strand = 0; strand < 2 && !slow; strand++) {
+            const int ws = 2 * w + strand;
+            const int nc = candN[ws];
+            if (nc == 0) continue;
+            const int n = Q.wsN[ws];
+            const unsigned qb = Q.wsOff[ws];
+            int thr0 = n / 5;
+            if (thr0 < 5) thr0 = 5;
+            // the window strand's task slots
+            unsigned long long tb = 0;
+            if (lane == 0) tb = atomicAdd(F.cursors + 0, (unsigned long long)nc);
+            tb = __shfl_sync(DP_FULL, tb, 0);
+            if (tb + (unsigned)nc > F.taskCap) {
+                slow = true;
+                break;
+            }
+            if (lane == 0) F.taskBase[ws] = (unsigned)tb;
+            const bool qSmall = n <= DP_QCAP;
+            DpListBuf LB;
+            LB.qFirst = qSmall ? shFirst[wib] : S.qFirst + (size_t)gwarp * S.qStride;
+            LB.qCnt = qSmall ? shCnt[wib] : S.qCnt + (size_t)gwarp * S.qStride;
+            LB.qLo = qSmall ? shLo[wib] : S.qLo + (size_t)gwarp * S.qStride;
+            LB.rqPos = qSmall ? shRqPos[wib] : S.rqPos + (size_t)gwarp * S.qStride;
+            LB.rqId = qSmall ? shRqId[wib] : S.rqId + (size_t)gwarp * S.qStride;
+            LB.shEnt = shEnt[wib];
+            LB.shRsPos = shRsPos[wib];
+            LB.shRsId = shRsId[wib];
+            LB.gEnt = S.ent + (size_t)gwarp * S.sStride;
+            LB.gRsPos = S.rsPos + (size_t)gwarp * S.sStride;
+            LB.gRsId = S.rsId + (size_t)gwarp * S.sStride;
+            LB.sStride = S.sStride;
+            dp_seed_identity(Q, qb, n, LB.qFirst);
+            for (int ci = 0; ci < nc; ci++) {
+                DpChainTask t;
+                t.listOff = 0;
+                t.nq = 0xffff;
+                t.ns = 0;
+                if ((int)candDistinct[(size_t)ws * candStride + ci] >= thr0) {
+                    const unsigned c = candChunk[(size_t)ws * candStride + ci];
+                    int nq, ns;
+                    int* rsPos;
+                    unsigned short* rsId;
+                    if (!dp_build_lists(I, Q, qb, n, c, LB, nq, ns, rsPos, rsId) || nq >= 0xffff || ns > 0xffff) {
+                        slow = true;
+                        break;
+                    }
+                    if (ns >= thr0 && nq >= thr0) {
+                        const unsigned need = 2u * (unsigned)nq + (unsigned)ns;
+                        unsigned long long off = 0;
+                        if (lane == 0) off = atomicAdd(F.cursors + 1, (unsigned long long)need);
+                        off = __shfl_sync(DP_FULL, off, 0);
+                        if (off + need > F.poolCap) {
+                            slow = true;
+                            break;
+                        }
+                        unsigned* dst = F.pool + off;
+                        for (int x = lane; x < nq; x += 32) {
+                            dst[x] = ((unsigned)LB.rqPos[x] << 16) | LB.rqId[x];
+                            dst[nq + ns + x] = 0;  // memo: chain length << 16 | last chunk-side index
+                        }
+                        for (int x = lane; x < ns; x += 32) dst[nq + x] = ((unsigned)rsPos[x] << 16) | rsId[x];
+                        t.listOff = (unsigned)off;
+                        t.nq = (unsigned short)nq;
+                        t.ns = (unsigned short)ns;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) F.tasks[tb + ci] = t;
+            }
+        }
+        if (slow && lane == 0) dp_mark_slow(F, w);
+        __syncwarp();
+    }
+}
+
+// dynamicMatch + extendChain (sequence.go:401-576) for one candidate, one thread. qe/se: packed reduced lists
+// (position << 16 | seed identity); memo: per query entry chain length << 16 | last chunk-side index, zero on entry.
+// Accepted chains -> ch[] as {len, firstA, lastA, firstB, lastB, ids}; returns their number or -1 if more than
+// DP_FAST_CHAINS would have to be kept.
+__device__ int dp_dynamic_match_serial(const unsigned* __restrict__ qe, int nq, int qScanLen,
+                                       const unsigned* __restrict__ se, int ns, int sScanLen, unsigned* memo,
+                                       int minMatch, int k, int (*ch)[6]) {
+    if (minMatch == 0) minMatch = 1;
+    int nGood = 0;
+    int nilCount = nq;
+#define QPOS(i) ((int)(qe[(i)] >> 16))
+#define SPOS(i) ((int)(se[(i)] >> 16))
+#define QID(i) (qe[(i)] & 0xffffu)
+#define SID(i) (se[(i)] & 0xffffu)
+#define GAPQ(i) (((i) + 1 < nq ? QPOS((i) + 1) : qScanLen) - QPOS(i) - k)
+#define GAPS(i) (((i) + 1 < ns ? SPOS((i) + 1) : sScanLen) - SPOS(i) - k)
+#define CLEN(i) ((int)(memo[(i)] >> 16))
+#define LASTB(i) ((int)(memo[(i)] & 0xffffu))
+    for (int qi = 0; qi <= nq - minMatch; qi++) {
+        // sequence.go:409: internal to closely spaced repeats (cannot fire on reduced lists; kept for fidelity)
+        if (qi > 0 && qi + 1 < nq && GAPQ(qi - 1) < 0 && GAPQ(qi) < 0 && QID(qi) == QID(qi - 1) && QID(qi) == QID(qi + 1))
+            continue;
+        if (CLEN(qi) != 0) continue;
+        const unsigned qid = QID(qi);
+        for (int si0 = 0; si0 < ns; si0++) {
+            if (SID(si0) != qid || (si0 > 0 && SID(si0 - 1) == qid)) continue;
+            // conditions evaluated with the state as it is now (minMatch may have grown)
+            if (!(si0 <= ns - minMatch && (CLEN(qi) == 0 || LASTB(qi) != si0))) continue;
+            if (CLEN(qi) == 0) nilCount--;
+            memo[qi] = (1u << 16) | (unsigned)si0;
+            // ---- extendChain (sequence.go:476-576) ----
+            int curLen = 1;
+            int ids = k;
+            int lastA = qi, lastBi = si0;
+            int offsetA = GAPQ(qi);
+            int offsetB = GAPS(si0);
+            int ai = qi + 1, bi = si0 + 1;
+            bool done = false;
+            while (!done && ai < nq && bi < ns) {
+                int minB, maxB;
+                if (offsetA < 0) {
+                    minB = -k;
+                    maxB = 0;
+                } else {
+                    minB = (offsetA * 2) / 3 - k;
+                    maxB = (offsetA * 3) / 2 + k;
+                }
+                while (maxB < offsetB) {
+                    offsetA += GAPQ(ai) + k;
+                    ai++;
+                    if (ai >= nq) {
+                        done = true;
+                        break;
+                    }
+                    minB = (offsetA * 2) / 3 - k;
+                    maxB = (offsetA * 3) / 2 + k;
+                }
+                if (done) break;
+                while (offsetB < minB) {
+                    offsetB += GAPS(bi) + k;
+                    bi++;
+                    if (bi >= ns) {
+                        done = true;
+                        break;
+                    }
+                }
+                if (done) break;
+                int oldBi = bi, oldBOffset = offsetB;
+                bool matched = false;
+                const unsigned seedA = QID(ai);
+                while (offsetB <= maxB) {
+                    if (seedA == SID(bi)) {
+                        if (CLEN(ai) != 0) {
+                            if (bi == LASTB(ai) && CLEN(ai) > curLen) {
+                                done = true;  // they have a better chain already
+                                break;
+                            }
+                        } else {
+                            nilCount--;
+                        }
+                        curLen++;
+                        memo[ai] = ((unsigned)curLen << 16) | (unsigned)bi;
+                        int d2 = SPOS(bi) - SPOS(lastBi) - k;  // GetBasesCovered, reference side
+                        ids += k + (d2 < 0 ? d2 : 0);
+                        lastA = ai;
+                        lastBi = bi;
+                        offsetA = GAPQ(ai);
+                        offsetB = GAPS(bi);
+                        ai++;
+                        bi++;
+                        matched = true;
+                        break;
+                    } else {
+                        offsetB += GAPS(bi) + k;
+                        bi++;
+                        if (bi >= ns) break;
+                    }
+                }
+                if (done) break;
+                if (!matched) {
+                    offsetA += GAPQ(ai) + k;
+                    ai++;
+                    offsetB = oldBOffset;
+                    bi = oldBi;
+                }
+            }
+            // ---- dynamicMatch bookkeeping (sequence.go:435-465) ----
+            if (curLen >= minMatch) {
+                int nextLength = (curLen * 2) / 3;
+                if (nextLength > minMatch) {
+                    minMatch = nextLength;
+                    for (int j = nGood - 1; j >= 0; j--) {
+                        if (ch[j][0] < nextLength) {
+                            for (int z = 0; z < 6; z++) ch[j][z] = ch[nGood - 1][z];
+                            nGood--;
+                        }
+                    }
+                }
+                if (nGood >= DP_FAST_CHAINS) return -1;
+                ch[nGood][0] = curLen;
+                ch[nGood][1] = qi;
+                ch[nGood][2] = lastA;
+                ch[nGood][3] = si0;
+                ch[nGood][4] = lastBi;
+                ch[nGood][5] = ids;
+                nGood++;
+                if (nilCount < curLen) return nGood;
+            }
+        }
+    }
+#undef QPOS
+#undef SPOS
+#undef QID
+#undef SID
+#undef GAPQ
+#undef GAPS
+#undef CLEN
+#undef LASTB
+    return nGood;
+}
+
+__global__ void __launch_bounds__(128) dp_chain_thread_kernel(DpIndexDev I, const DpWindow* __restrict__ wins,
+                                                              const int* __restrict__ readLen, int nWin,
+                                                              DpExtractOut Q, const int* __restrict__ candN,
+                                                              const unsigned* __restrict__ candChunk,
+                                                              const unsigned short* __restrict__ candDistinct,
+                                                              int candStride, DpFastChain F, int* __restrict__ outN,
+                                                              unsigned* __restrict__ outOff,
+                                                              DpMappingDev* __restrict__ outMaps,
+                                                              unsigned long long* __restrict__ outCursor,
+                                                              unsigned long long outCapacity,
+                                                              DpCounters* __restrict__ ctr) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = dp_lane();
+    const int k = I.k;
+    DpMappingDev results[DP_FAST_RESULTS];
+    int nRes = 0;
+    unsigned cells = 0;
+    bool live = w < nWin && F.slow[w] == 0;
+    bool giveUp = false;
+    if (live) {
+        DpWindow win = wins[w];
+        const int L = win.len;
+        if (L > 0) {
+            const int rlen = readLen[win.read];
+            const bool q2 = win.whole && ((L & 3) == 0);
+            // SeedSequence.offset / inset of the window (Q3: SubSequence stores inset one too large)
+            const int wOffset = win.whole ? 0 : win.start;
+            const int wInset = win.whole ? 0 : (rlen - (win.start + L) + 1);
+            int minMatches = Q.wsN[2 * w] / 5;
+            int minRCMatches = Q.wsN[2 * w + 1] / 5;
+            if (minMatches < 5) minMatches = 5;
+            if (minRCMatches < 5) minRCMatches = 5;
+            for (int strand = 0; strand < 2 && !giveUp; strand++) {
+                const int ws = 2 * w + strand;
+                const int nc = candN[ws];
+                if (nc == 0) continue;
+                const unsigned tb = F.taskBase[ws];
+                const int qScanLen = strand == 0 ? (L - (q2 ? 4 : 0)) : (L - (q2 ? 3 : 0));
+                for (int ci = 0; ci < nc && !giveUp; ci++) {
+                    const int thr = strand == 0 ? minMatches : minRCMatches;
+                    // CountIntersectionTo(...) < threshold (mapping.go:520-523, 559-562)
+                    if ((int)candDistinct[(size_t)ws * candStride + ci] < thr) continue;
+                    const DpChainTask t = F.tasks[tb + ci];
+                    if (t.nq == 0xffff) continue;  // a Reduced list was shorter than the initial threshold already
+                    const int nq = t.nq, ns = t.ns;
+                    if (ns < thr || nq < thr) continue;  // Reduced returned nil
+                    cells += (unsigned)(ns + nq);
+                    const unsigned c = candChunk[(size_t)ws * candStride + ci];
+                    const int sScanLen = __ldg(I.chunkScanLen + c);
+                    const unsigned* qe = F.pool + t.listOff;
+                    const unsigned* se = qe + nq;
+                    unsigned* memo = F.pool + t.listOff + nq + ns;
+                    int ch[DP_FAST_CHAINS][6];
+                    const int nGood = dp_dynamic_match_serial(qe, nq, qScanLen, se, ns, sScanLen, memo, thr, k, ch);
+                    if (nGood < 0) {
+                        giveUp = true;
+                        break;
+                    }
+                    // chains -> mappings (mapping.go:528-549 / 567-587), in allGoodChains order
+                    const long long cOffset = __ldg(I.chunkOffset + c);
+                    const long long cInset = __ldg(I.chunkInset + c);
+                    for (int g = 0; g < nGood; g++) {
+                        const int* r = ch[g];
+                        const int sFirst = (int)(se[r[3]] >> 16), sLast = (int)(se[r[4]] >> 16);
+                        long long start = cOffset + sFirst;
+                        long long end = I.refLen - cInset - (long long)(sScanLen - sLast - k);
+                        if (I.circular && start > I.refLen) start -= I.refLen;
+                        int first = (int)(qe[r[1]] >> 16);                   // GetSeedOffset(MatchA[0])
+                        int fromEnd = qScanLen - (int)(qe[r[2]] >> 16) - k;  // GetSeedOffsetFromEnd(MatchA[last])
+                        if (first + fromEnd > (L * 2) / 3) continue;
+                        if (nRes >= DP_FAST_RESULTS) {
+                            giveUp = true;
+                            break;
+                        }
+                        DpMappingDev mp;
+                        mp.start = start;
+                        mp.end = end;
+                        if (strand == 0) {
+                            mp.qOffset = first + wOffset;
+                            mp.qInset = fromEnd + wInset;
+                        } else {  // rcQuery.offset = window inset, rcQuery.inset = window offset
+                            mp.qInset = first + wInset;
+                            mp.qOffset = fromEnd + wOffset;
+                        }
+                        mp.ids = r[5];
+                        mp.rc = strand;
+                        results[nRes++] = mp;
+                        int limit = (r[0] * 4) / 5;
+                        if (strand == 0) {
+                            if (limit > minMatches) minMatches = limit;
+                            if (limit > minRCMatches) minRCMatches = limit;
+                        } else {
+                            if (limit > minRCMatches) minRCMatches = limit;
+                        }
+                    }
+                }
+            }
+            if (giveUp) {  // the general path recomputes this window from the candidates
+                dp_mark_slow(F, w);
+                nRes = 0;
+                cells = 0;
+            } else if (nRes > 1) {
+                // ---- sort by Start + overlap dedupe (mapping.go:590-608) ----
+                for (int i = 1; i < nRes; i++) {  // stable insertion sort (= Go's sort.Sort for n <= 12)
+                    DpMappingDev x = results[i];
+                    int j = i;
+                    while (j > 0 && x.start < results[j - 1].start) {
+                        results[j] = results[j - 1];
+                        j--;
+                    }
+                    results[j] = x;
+                }
+                for (int i = nRes - 1; i > 0; i--) {
+                    DpMappingDev ra = results[i - 1], rb = results[i];
+                    if (ra.rc == rb.rc && rb.start < ra.end) {
+                        if (ra.end - ra.start > rb.end - rb.start) {
+                            results[i] = results[nRes - 1];
+                            nRes--;
+                        } else {
+                            results[i - 1] = results[i];
+                            results[i] = results[nRes - 1];
+                            nRes--;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // compact output: one bump allocation per warp
+    const bool writes = live && !giveUp;
+    int incl = writes ? nRes : 0;
+    const int mine = incl;
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(DP_FULL, incl, d);
+        if ((int)lane >= d) incl += y;
+    }
+    const int warpTot = __shfl_sync(DP_FULL, incl, 31);
+    unsigned long long warpBase = 0;
+    if (lane == 31 && warpTot) warpBase = atomicAdd(outCursor, (unsigned long long)warpTot);
+    warpBase = __shfl_sync(DP_FULL, warpBase, 31);
+    unsigned wCells = cells, wMaps = 0;
+    if (writes) {
+        unsigned long long base = warpBase + (unsigned)(incl - mine);
+        int cnt = mine;
+        if (base + (unsigned)cnt > outCapacity) {
+            atomicOr(&ctr->overflow, 1u);
+            cnt = 0;
+            base = 0;
+        }
+        outN[w] = cnt;
+        outOff[w] = (unsigned)base;
+        for (int i = 0; i < cnt; i++) outMaps[base + i] = results[i];
+        wMaps = (unsigned)cnt;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        wCells += __shfl_xor_sync(DP_FULL, wCells, d);
+        wMaps += __shfl_xor_sync(DP_FULL, wMaps, d);
+    }
+    if (lane == 0 && (wCells | wMaps)) {
+        atomicAdd(&ctr->chain_cells, (unsigned long long)wCells);
+        atomicAdd(&ctr->mappings, (unsigned long long)wMaps);
     }
 }

@@ -12,10 +12,20 @@ def main():
     ref = synth.reference(1, 4_600_000)
     vals = dp.kmer_values(dp.kmer_counts(ref, 11), 11)
     gm = dp.Mapper(ref, vals, circular=True)
-    pinned = torch.empty(n * L, dtype=torch.uint8).pin_memory()
-    synth.reads(ref, 12, n, L, out=pinned.numpy())
+    if os.environ.get('USE_DP_ALLOC'):
+        hostbuf = dp.host_alloc(n * L)
+        synth.reads(ref, 12, n, L, out=hostbuf)
+        pinned = torch.from_numpy(hostbuf)
+        d = torch.empty(n * L, dtype=torch.uint8, device='cuda')
+        torch.cuda.current_stream().synchronize()
+        import ctypes
+        cudart = ctypes.CDLL('libcudart.so')
+        cudart.cudaMemcpy(ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(pinned.data_ptr()), ctypes.c_size_t(n * L), 1)
+    else:
+        pinned = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+        synth.reads(ref, 12, n, L, out=pinned.numpy())
+        d = pinned.cuda()
     offs = np.arange(n + 1, dtype=np.int64) * L
-    d = pinned.cuda()
     keys = ('ms_total', 'ms_pack', 'ms_extract', 'ms_lookup', 'ms_chain', 'ms_host_logic', 'rounds')
     for lanes in [int(x) for x in os.environ.get('LANES', '2,3,4,6').split(',')]:
         os.environ['DP_LANES'] = str(lanes)

@@ -256,3 +256,32 @@ def test_index_image_round_trip(tmp_path):
     with pytest.raises(dp.DownporeError):
         dp.Mapper.from_index(bad.ctypes.data, n)
     gm.close()
+
+
+@pytest.mark.parametrize("env", [{"DP_CHAIN_FAST": "0"}, {}, {"DP_FAST_POOL_WORDS": "3000"}, {"DP_FAST_POOL_WORDS": "1"}])
+def test_chain_paths_agree_with_oracle(env):
+    """The chaining stage has a fast path (dp_reduce_kernel + dp_chain_thread_kernel) and an exact general kernel that
+    takes over whatever the fast path hands back. All routes — general only, fast, fast with a starved list pool (most
+    windows handed back), fast with no pool at all — must give the oracle's records."""
+    ref = synth.reference(12, 500_000)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    om = po.Mapper(ref, vals, circular=True)
+    reads = mixed_reads(ref, True, seed=23, n=400, rl=7000)
+    bases = np.concatenate(reads)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    orow, ooff, _ = om.map_batch(bases, offs, threads=4)
+    old = {k2: os.environ.get(k2) for k2 in ("DP_CHAIN_FAST", "DP_FAST_POOL_WORDS")}
+    try:
+        os.environ.update(env)
+        gm = dp.Mapper(ref, vals, circular=True)
+        maps, off = gm.map_batch(bases, offs)
+        st = gm.stats()
+        gm.close()
+    finally:
+        for k2, v in old.items():
+            if v is None:
+                os.environ.pop(k2, None)
+            else:
+                os.environ[k2] = v
+    assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow)
+    assert st["mappings"] == len(orow)
