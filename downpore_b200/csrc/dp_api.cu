@@ -662,7 +662,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
                                            (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
-        dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), S, inSmem, W.candN.p, W.candChunk.p,
+        dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), nullptr, nullptr, S, inSmem, W.candN.p, W.candChunk.p,
                                                     W.candDistinct.p, W.candStride, W.dCtr.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(W.timers[T_LOOKUP].b, st));

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(1024, 1) dp_extract_kernel(DpIndexDev I, const
 #define DP_ECAP 128   // included seed occurrences per window strand held in shared memory
 #define DP_TCAP 256   // touched chunks per window strand held in shared memory
 #define DP_LWARPS 4   // warps per lookup CTA
+#define DP_DUPCAP 32  // included runs that repeat an earlier run's seed, listed per window strand
 
 struct DpLookupScratch {  // per-warp global scratch for oversized window strands, `stride` entries per array
     unsigned* eSeed;
@@ -291,7 +292,143 @@ __device__ __forceinline__ bool dp_run_contains(const unsigned* __restrict__ chu
     return lo < cnt && __ldg(chunks + off + lo) == c;
 }
 
+// Everything the candidate refinement needs about the included runs of one window strand
+struct DpRefineCtx {
+    const unsigned* eOff;   // [nInc] first posting of each included run (in seedChunks)
+    const unsigned* ePre;   // [nInc+1] exclusive prefix of run lengths
+    const unsigned* eEndW;  // [nInc] last 64-chunk word of each run (valid when clamped || q6)
+    const unsigned char* eFirst;  // [nInc] first occurrence of the seed among the included runs
+    const unsigned short* dup;    // the runs that are NOT first occurrences (valid when 0 <= nDup)
+    int nDup;                     // -1: too many to list, use eFirst
+    unsigned short* order;        // [nInc] scratch of the Q6 column-order simulation
+    int nInc, minCount, T;
+    bool clamped, q6;
+    int nAllDistinct;
+};
+
+// Candidates over the count threshold, ascending by chunk id, as (chunk << 32 | soft count): applies the level clamp's
+// early stop (Q11) and the level-16 under-count (Q6), computes the DISTINCT query seeds present in each survivor
+// (IntSet.CountIntersectionTo's operand, mapping.go:520-523) and writes (chunk, distinct) pairs. Warp-collective;
+// returns the number of survivors (which may exceed candStride: the caller flags that).
+__device__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const unsigned long long* sorted, int nCand,
+                              unsigned* outChunk, unsigned short* outDist, int candStride) {
+    const unsigned lane = dp_lane();
+    const int nInc = X.nInc, minCount = X.minCount, T = X.T;
+    const bool clamped = X.clamped, q6 = X.q6;
+    const unsigned* eOff = X.eOff;
+    const unsigned* ePre = X.ePre;
+    const unsigned* eEndW = X.eEndW;
+    unsigned short* order = X.order;
+    int nCandOut = 0;
+    int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (lane 0 owns it)
+    bool simInit = false;
+    for (int r0 = 0; r0 < nCand; r0 += 32) {
+        const bool have = r0 + (int)lane < nCand;
+        const unsigned long long mine = have ? sorted[r0 + lane] : 0ull;
+        unsigned c = (unsigned)(mine >> 32);
+        unsigned v = (unsigned)mine;
+        int soft = (int)(v & 0xffffu);
+        unsigned mp = __ballot_sync(DP_FULL, have);
+        if (mp && (clamped || q6)) {
+            unsigned todo = mp;
+            while (todo) {
+                int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                unsigned cc = __shfl_sync(DP_FULL, c, l);
+                unsigned wword = cc >> 6;
+                int sft = __shfl_sync(DP_FULL, soft, l);
+                bool keep = true;
+                if (clamped) {
+                    int live = 0;
+                    for (int j0 = 0; j0 < nInc; j0 += 32) {
+                        int j = j0 + (int)lane;
+                        live += __popc(__ballot_sync(DP_FULL, j < nInc && eEndW[j] >= wword));
+                    }
+                    if (live < minCount) keep = false;
+                }
+                if (keep && q6 && sft == T) {
+                    // advance the drop simulation of bitset.go:332-353 to word `wword`
+                    if (lane == 0) {
+                        if (!simInit) {
+                            for (int j = 0; j < nInc; j++) order[j] = (unsigned short)j;
+                            unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
+                            for (int j = 0; j < nInc; j++) {
+                                unsigned len = ePre[j + 1] - ePre[j];
+                                unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
+                                if (s0 < st) st = s0;
+                            }
+                            simWord = (int)st - 1;
+                        }
+                        for (int i = simWord + 1; i <= (int)wword; i++) {
+                            int t = 0;
+                            while (t < simLive) {
+                                if (eEndW[order[t]] + 1 <= (unsigned)i) {
+                                    order[t] = order[simLive - 1];
+                                    simLive--;
+                                } else {
+                                    t++;
+                                }
+                            }
+                        }
+                        if ((int)wword > simWord) simWord = (int)wword;
+                    }
+                    simInit = true;
+                    __syncwarp();
+                    bool in = false;
+                    if (lane < 8) {
+                        unsigned j = order[lane];
+                        in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
+                    }
+                    unsigned mi = __ballot_sync(DP_FULL, in);
+                    if ((mi & 0x80u) && !(mi & 0x7fu)) keep = false;  // count-1 < T
+                }
+                if (!keep) mp &= ~(1u << l);
+            }
+        }
+        // distinct query seeds present in each survivor = its soft count (one per included run containing it) minus
+        // the runs that repeat an earlier run's seed and contain it
+        unsigned todo2 = mp;
+        while (todo2) {
+            int l = __ffs(todo2) - 1;
+            todo2 &= todo2 - 1;
+            unsigned cc = __shfl_sync(DP_FULL, c, l);
+            int distinct;
+            if (X.nDup >= 0) {
+                int rep = 0;
+                for (int d0 = 0; d0 < X.nDup; d0 += 32) {
+                    int d = d0 + (int)lane;
+                    bool in = false;
+                    if (d < X.nDup) {
+                        int j = X.dup[d];
+                        in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
+                    }
+                    rep += __popc(__ballot_sync(DP_FULL, in));
+                }
+                distinct = __shfl_sync(DP_FULL, soft, l) - rep;
+            } else {
+                distinct = 0;
+                for (int j0 = 0; j0 < nInc; j0 += 32) {
+                    int j = j0 + (int)lane;
+                    bool in = false;
+                    if (j < nInc && X.eFirst[j]) in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
+                    distinct += __popc(__ballot_sync(DP_FULL, in));
+                }
+            }
+            int idx = nCandOut + __popc(mp & ((1u << l) - 1));
+            if (lane == 0 && idx < candStride) {
+                outChunk[idx] = cc;
+                outDist[idx] = (unsigned short)(distinct + X.nAllDistinct);
+            }
+        }
+        nCandOut += __popc(mp);
+    }
+    return nCandOut;
+}
+
+
 __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                  const int* __restrict__ wsList,
+                                                                  const int* __restrict__ nWsList,
                                                                   DpLookupScratch S, int countersInSmem,
                                                                   int* __restrict__ candN,
                                                                   unsigned* __restrict__ candChunk,
@@ -305,6 +442,7 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
     __shared__ unsigned char shFirst[DP_LWARPS][DP_ECAP];
     __shared__ unsigned shTouched[DP_LWARPS][DP_TCAP];
     __shared__ unsigned long long shCand[DP_LWARPS][DP_TCAP];
+    __shared__ unsigned short shDup[DP_LWARPS][DP_DUPCAP];
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
     const int wib = threadIdx.x >> 5;
@@ -323,7 +461,9 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
     unsigned short* order = S.order + so;
     unsigned long long cRuns = 0, cEntries = 0, cCand = 0;
 
-    for (int ws = gwarp; ws < nWS; ws += nWarps) {
+    const int nTodo = wsList ? min(*nWsList, nWS) : nWS;  // a list: the window strands the block kernel deferred
+    for (int wi = gwarp; wi < nTodo; wi += nWarps) {
+        const int ws = wsList ? wsList[wi] : wi;
         const int n = Q.wsN[ws];
         const unsigned qb = Q.wsOff[ws];
         int nCandOut = 0;
@@ -401,11 +541,13 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                 }
                 // ---- first occurrences among E (__match_any_sync), last word of each run, run-length prefix ----
                 unsigned total = 0;
+                int nDup = 0;
                 for (int j0 = 0; j0 < nInc; j0 += 32) {
                     int j = j0 + (int)lane;
                     unsigned c = 0;
                     unsigned s = j < nInc ? eSeed[j] : (0x80000000u | lane);
                     unsigned mm = __match_any_sync(DP_FULL, s);
+                    bool isDup = false;
                     if (j < nInc) {
                         c = ePre[j];
                         bool first = (__ffs(mm) - 1) == (int)lane;
@@ -417,7 +559,18 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                                 }
                         }
                         eFirst[j] = first ? 1 : 0;
+                        isDup = !first;
                         if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
+                    }
+                    {   // list of the runs that repeat an earlier run's seed (few): what the distinct count subtracts
+                        unsigned md = __ballot_sync(DP_FULL, isDup);
+                        if (nDup >= 0) {
+                            if (nDup + __popc(md) > DP_DUPCAP) nDup = -1;
+                            else {
+                                if (isDup) shDup[wib][nDup + __popc(md & lt)] = (unsigned short)j;
+                                nDup += __popc(md);
+                            }
+                        }
                     }
                     unsigned x = c;  // warp inclusive scan
                     for (int d = 1; d < 32; d <<= 1) {
@@ -499,8 +652,6 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                 }
                 __syncwarp();
                 // ---- ascending chunk id (rank sort: chunk ids are distinct), then the rare refinements ----
-                int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (lane 0 owns it)
-                bool simInit = false;
                 const unsigned long long* sorted = cand;
                 if (nCand > 1) {
                     if (nCand <= 32) {  // in place: every lane holds its element before anyone writes
@@ -524,93 +675,21 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
                     }
                     __syncwarp();
                 }
-                for (int r0 = 0; r0 < nCand; r0 += 32) {
-                    const bool have = r0 + (int)lane < nCand;
-                    const unsigned long long mine = have ? sorted[r0 + lane] : 0ull;
-                    unsigned c = (unsigned)(mine >> 32);
-                    unsigned v = (unsigned)mine;
-                    int soft = (int)(v & 0xffffu);
-                    bool pass = have;
-                    unsigned mp = __ballot_sync(DP_FULL, pass);
-                    if (mp && (clamped || q6)) {
-                        unsigned todo = mp;
-                        while (todo) {
-                            int l = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            unsigned cc = __shfl_sync(DP_FULL, c, l);
-                            unsigned wword = cc >> 6;
-                            int sft = __shfl_sync(DP_FULL, soft, l);
-                            bool keep = true;
-                            if (clamped) {
-                                int live = 0;
-                                for (int j0 = 0; j0 < nInc; j0 += 32) {
-                                    int j = j0 + (int)lane;
-                                    live += __popc(__ballot_sync(DP_FULL, j < nInc && eEndW[j] >= wword));
-                                }
-                                if (live < minCount) keep = false;
-                            }
-                            if (keep && q6 && sft == T) {
-                                // advance the drop simulation of bitset.go:332-353 to word `wword`
-                                if (lane == 0) {
-                                    if (!simInit) {
-                                        for (int j = 0; j < nInc; j++) order[j] = (unsigned short)j;
-                                        unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
-                                        for (int j = 0; j < nInc; j++) {
-                                            unsigned len = ePre[j + 1] - ePre[j];
-                                            unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
-                                            if (s0 < st) st = s0;
-                                        }
-                                        simWord = (int)st - 1;
-                                    }
-                                    for (int i = simWord + 1; i <= (int)wword; i++) {
-                                        int t = 0;
-                                        while (t < simLive) {
-                                            if (eEndW[order[t]] + 1 <= (unsigned)i) {
-                                                order[t] = order[simLive - 1];
-                                                simLive--;
-                                            } else {
-                                                t++;
-                                            }
-                                        }
-                                    }
-                                    if ((int)wword > simWord) simWord = (int)wword;
-                                }
-                                simInit = true;
-                                __syncwarp();
-                                bool in = false;
-                                if (lane < 8) {
-                                    unsigned j = order[lane];
-                                    in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
-                                }
-                                unsigned mi = __ballot_sync(DP_FULL, in);
-                                if ((mi & 0x80u) && !(mi & 0x7fu)) keep = false;  // count-1 < T
-                            }
-                            if (!keep) mp &= ~(1u << l);
-                        }
-                        pass = (mp >> lane) & 1;
-                    }
-                    // IntSet.CountIntersectionTo's operand (mapping.go:520-523): DISTINCT query seeds present in the
-                    // chunk, counted on demand for the few surviving candidates
-                    unsigned todo2 = mp;
-                    while (todo2) {
-                        int l = __ffs(todo2) - 1;
-                        todo2 &= todo2 - 1;
-                        unsigned cc = __shfl_sync(DP_FULL, c, l);
-                        int distinct = 0;
-                        for (int j0 = 0; j0 < nInc; j0 += 32) {
-                            int j = j0 + (int)lane;
-                            bool in = false;
-                            if (j < nInc && eFirst[j]) in = dp_run_contains(I.seedChunks, eOff[j], ePre[j + 1] - ePre[j], cc);
-                            distinct += __popc(__ballot_sync(DP_FULL, in));
-                        }
-                        int idx = nCandOut + __popc(mp & ((1u << l) - 1));
-                        if (lane == 0 && idx < candStride) {
-                            outChunk[idx] = cc;
-                            outDist[idx] = (unsigned short)(distinct + nAllDistinct);
-                        }
-                    }
-                    nCandOut += __popc(mp);
-                }
+                DpRefineCtx X;
+                X.eOff = eOff;
+                X.ePre = ePre;
+                X.eEndW = eEndW;
+                X.eFirst = eFirst;
+                X.dup = shDup[wib];
+                X.nDup = nDup;
+                X.order = order;
+                X.nInc = nInc;
+                X.minCount = minCount;
+                X.T = T;
+                X.clamped = clamped;
+                X.q6 = q6;
+                X.nAllDistinct = nAllDistinct;
+                nCandOut = dp_refine_emit(I, X, sorted, nCand, outChunk, outDist, candStride);
                 if (nCandOut > candStride) {
                     if (lane == 0) atomicOr(&ctr->overflow, 4u);
                     nCandOut = candStride;
