@@ -113,6 +113,8 @@ struct Lane {
     DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters, lsTouched;
     DBuf<unsigned long long> lsCand;
     bool lsCountersZeroed = false;
+    DBuf<int> lbDefer;        // block lookup kernel: deferred window strands
+    DBuf<unsigned> lbWork;    // [0] work counter, [1] deferred count
     DBuf<unsigned char> lsFirst;
     DBuf<unsigned short> lsOrder;
     // chain scratch
@@ -508,7 +510,40 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
 // ----------------------------------------------------------------------------------------------------------------
 // window rounds
 // ----------------------------------------------------------------------------------------------------------------
-const unsigned kLookupSmemChunks = 24000;  // 16-bit counters: 4 warps x 48 KB of shared memory at most
+const unsigned kLookupSmemChunksDefault = 24000;  // 16-bit counters: 4 warps x 48 KB of shared memory at most
+unsigned lookup_smem_chunks() {  // DP_LOOKUP_SMEM_CHUNKS: tests force the warp kernel's global-memory counters
+    const char* env = getenv("DP_LOOKUP_SMEM_CHUNKS");
+    return env ? (unsigned)atoi(env) : kLookupSmemChunksDefault;
+}
+#define kLookupSmemChunks lookup_smem_chunks()
+const unsigned kLookupBlockMinChunks = 2048;  // from here on a CTA per window strand (dp_lookup_block_kernel)
+
+struct LookupBlockPlan {
+    bool use = false;
+    int tileChunks = 0, eCap = 512, threads = 1024, ctasPerSm = 1;
+    size_t smem = 0;
+};
+
+LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
+    LookupBlockPlan P;
+    const char* env = getenv("DP_LOOKUP_BLOCK");
+    bool want = I.numChunks >= kLookupBlockMinChunks;
+    if (env) want = atoi(env) != 0;
+    // the CTA's global scratch for oversized window strands is shared with the warp kernel's: tStride = C + 8 entries
+    if (!want || (long long)I.numChunks + 8 <= (long long)I.maxWindow + 1) return P;
+    const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~3 KB of static shared memory
+    const size_t eBytes = (size_t)P.eCap * 21 + 16;  // five uint32 arrays (+2 sentinels) and one byte array
+    size_t tile = ((size_t)I.numChunks + 7) / 8 * 8;
+    if (tile * 2 + eBytes > maxSmem) tile = (maxSmem - eBytes) / 2 / 8 * 8;
+    if (getenv("DP_LOOKUP_TILE")) tile = std::min<size_t>(tile, std::max(8, atoi(getenv("DP_LOOKUP_TILE")) / 8 * 8));  // tests
+    P.tileChunks = (int)tile;
+    P.smem = (tile * 2 + eBytes + 15) / 16 * 16;
+    size_t fit = (227 * 1024) / (P.smem + 4096);
+    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 8));
+    P.threads = P.ctasPerSm >= 4 ? 256 : (P.ctasPerSm >= 2 ? 512 : 1024);
+    P.use = true;
+    return P;
+}
 
 void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries) {
     const DpIndexDev& I = M.I;
@@ -529,7 +564,11 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     // per-warp scratch
     const int qStride = I.maxWindow + 8;
     W.extractWarps = M.smCount * 8 * 8;
-    W.lookupWarps = M.smCount * 4 * 8;
+    // lookup scratch is indexed by warp in dp_lookup_kernel and by CTA in dp_lookup_block_kernel (<= 8 per SM)
+    const LookupBlockPlan LP = plan_block_lookup(I);
+    W.lookupWarps = LP.use ? M.smCount * 4 * 2 : M.smCount * 4 * 8;
+    W.lbDefer.reserve(2 * nWin);
+    W.lbWork.reserve(4);
     W.chainWarps = M.smCount * 4 * 8;
     size_t lw = (size_t)W.lookupWarps;
     W.lsSeed.reserve(lw * qStride);
@@ -633,6 +672,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CK(cudaFuncSetAttribute(dp_lookup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
             M.attrsSet = true;
         }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
@@ -659,12 +699,37 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int inSmem = I.numChunks <= kLookupSmemChunks ? 1 : 0;
         int warpsPerBlock = DP_LWARPS;
         size_t smem = inSmem ? (size_t)warpsPerBlock * ((I.numChunks + 1) / 2) * sizeof(unsigned) : 0;
-        int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
-                                           (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
+        const LookupBlockPlan LP = plan_block_lookup(I);
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
-        dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), nullptr, nullptr, S, inSmem, W.candN.p, W.candChunk.p,
-                                                    W.candDistinct.p, W.candStride, W.dCtr.p);
-        CK(cudaGetLastError());
+        if (LP.use) {
+            DpLookupBlockCfg G;
+            G.tileChunks = LP.tileChunks;
+            G.eCap = LP.eCap;
+            G.work = W.lbWork.p;
+            G.deferList = W.lbDefer.p;
+            G.nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
+            CK(cudaMemsetAsync(W.lbWork.p, 0, 4 * sizeof(unsigned), st));
+            int ctas = LP.ctasPerSm;
+            if (W.curAsciiIsHost && ctas > 1) ctas -= ctas / 4 ? ctas / 4 : 0;  // headroom for the pull kernel
+            int blocks = (int)std::min<size_t>(2 * nWin, (size_t)M.smCount * ctas);
+            dp_lookup_block_kernel<<<blocks, LP.threads, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
+                                                                       W.candDistinct.p, W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            // window strands the CTA kernel deferred (a seed present in every chunk): none on real references
+            int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 2);
+            dp_lookup_kernel<<<dBlocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), G.deferList, G.nDefer, S, inSmem,
+                                                                   W.candN.p, W.candChunk.p, W.candDistinct.p,
+                                                                   W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            W.stats.kernel_launches += 1;
+        } else {
+            int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
+                                               (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
+            dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), nullptr, nullptr, S, inSmem,
+                                                                   W.candN.p, W.candChunk.p, W.candDistinct.p,
+                                                                   W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(W.timers[T_LOOKUP].b, st));
     }
     {

@@ -708,6 +708,338 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
 }
 
 // ===============================================================================================================
+// Stage 2 for indexes with many chunks — one CTA per window strand (dp_lookup_block_kernel).
+//
+// With C chunks a warp-private set of counters costs 2C bytes; beyond a few thousand chunks that either leaves the SM
+// nearly empty or (beyond 24 000) spills the counters to global memory, where every posting becomes a random
+// read-modify-write. Here the whole CTA owns ONE set of 16-bit counters in shared memory (up to ~110 000 chunks per
+// pass; more chunks = more passes over chunk ranges) and all its warps stream the posting runs of one window strand
+// into it: 256 postings per warp item, eight independent coalesced loads per lane in flight, shared-memory atomics.
+// The counters are then scanned (and zeroed) with 16-byte loads; the few chunks over the threshold are sorted by id
+// and handed to the same refinement / distinct-count routine as the warp kernel (dp_refine_emit).
+// At human-genome scale a window strand gathers ~10^5 postings (hundreds of KB): this is the HBM-bound kernel of the
+// path, and its traffic is sequential inside each run.
+// The inclusion filter runs thread-per-seed with a block-wide ordered compaction. Window strands that contain a seed
+// present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel through a list.
+// ===============================================================================================================
+#define DP_BSEG 256    // postings per gather item
+#define DP_BCAND 256   // candidates over the threshold held in shared memory
+#define DP_BDUP 64     // repeated-seed runs listed per window strand
+
+struct DpLookupBlockCfg {
+    int tileChunks;  // chunks covered by the shared-memory counters per pass (multiple of 8)
+    int eCap;        // included runs held in shared memory (more: global scratch)
+    unsigned* work;  // dynamic work counter, zero at launch
+    int* deferList;  // window strands left to dp_lookup_kernel
+    int* nDefer;
+};
+
+struct DpBlockShared {
+    unsigned wTot[32];
+    unsigned wLast[32];
+    int ws;
+    int nCand;
+    int nDup;
+    int nCandOut;
+};
+
+// exclusive prefix sum over the CTA (blockDim.x <= 1024); total returned in `total`
+__device__ __forceinline__ unsigned dp_block_excl_scan(unsigned v, unsigned* wTot, unsigned& total) {
+    const unsigned lane = dp_lane();
+    const unsigned warp = threadIdx.x >> 5, nWarp = blockDim.x >> 5;
+    unsigned x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned y = __shfl_up_sync(DP_FULL, x, d);
+        if ((int)lane >= d) x += y;
+    }
+    if (lane == 31) wTot[warp] = x;
+    __syncthreads();
+    unsigned t = lane < nWarp ? wTot[lane] : 0u;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned y = __shfl_up_sync(DP_FULL, t, d);
+        if ((int)lane >= d) t += y;
+    }
+    const unsigned base = warp ? __shfl_sync(DP_FULL, t, warp - 1) : 0u;
+    total = __shfl_sync(DP_FULL, t, nWarp - 1);
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                  DpLookupScratch S, DpLookupBlockCfg G,
+                                                                  int* __restrict__ candN,
+                                                                  unsigned* __restrict__ candChunk,
+                                                                  unsigned short* __restrict__ candDistinct,
+                                                                  int candStride, DpCounters* __restrict__ ctr) {
+    extern __shared__ unsigned dp_smem[];
+    __shared__ DpBlockShared sh;
+    __shared__ unsigned long long shCand[DP_BCAND];
+    __shared__ unsigned short shDup[DP_BDUP];
+    const int tid = threadIdx.x, nT = blockDim.x;
+    const unsigned lane = dp_lane();
+    const unsigned lt = dp_lanemask_lt();
+    const int warp = tid >> 5, nWarp = nT >> 5;
+    const unsigned C = I.numChunks;
+    const int tileWords = G.tileChunks >> 1;
+    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | eFirst
+    unsigned* cnt = dp_smem;
+    unsigned* smSeed = cnt + tileWords;
+    unsigned* smOff = smSeed + G.eCap;
+    unsigned* smPre = smOff + G.eCap;
+    unsigned* smItem = smPre + G.eCap + 1;
+    unsigned* smEndW = smItem + G.eCap + 1;
+    unsigned char* smFirst = reinterpret_cast<unsigned char*>(smEndW + G.eCap);
+    for (int i = tid; i < tileWords; i += nT) cnt[i] = 0;
+    // global scratch of this CTA for oversized window strands
+    const size_t so = (size_t)blockIdx.x * S.stride;
+    unsigned short* order = S.order + so;
+    unsigned long long* gCand = S.cand + (size_t)blockIdx.x * 2 * S.tStride;
+    unsigned long long cRuns = 0, cEntries = 0, cCand = 0;  // thread 0 only
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) {
+            sh.ws = (int)atomicAdd(G.work, 1u);
+            sh.nCand = 0;
+            sh.nDup = 0;
+            sh.nCandOut = 0;
+        }
+        __syncthreads();
+        const int ws = sh.ws;
+        if (ws >= nWS) break;
+        const int n = Q.wsN[ws];
+        const unsigned qb = Q.wsOff[ws];
+        bool defer = false;
+        if (n >= 5) {
+            const bool eSmall = n <= G.eCap;
+            unsigned* eSeed = eSmall ? smSeed : S.eSeed + so;
+            unsigned* eOff = eSmall ? smOff : S.eOff + so;
+            unsigned* ePre = eSmall ? smPre : S.ePre + (size_t)blockIdx.x * (S.stride + 1);
+            unsigned* eItem = eSmall ? smItem : S.touched + (size_t)blockIdx.x * S.tStride;
+            unsigned* eEndW = eSmall ? smEndW : S.eEndW + so;
+            unsigned char* eFirst = eSmall ? smFirst : S.eFirst + so;
+            // ---- inclusion filter (seeds.go:340-346): thread per seed, ordered compaction over the CTA ----
+            int nInc = 0;
+            unsigned carry = 0xffffffffu;  // seed of the last eligible occurrence of earlier rounds
+            int sawAll = 0;
+            for (int j0 = 0; j0 < n; j0 += nT) {
+                const int j = j0 + tid;
+                const bool valid = j < n;
+                unsigned s = 0xffffffffu, o = 0, c = 0;
+                if (valid) {
+                    s = Q.qSeed[qb + j];
+                    o = __ldg(I.seedOff + s);
+                    c = __ldg(I.seedOff + s + 1) - o;
+                }
+                const bool elig = valid && c < C;
+                if (valid && c >= C) sawAll = 1;
+                const unsigned me = __ballot_sync(DP_FULL, elig);
+                const unsigned lastSeed = __shfl_sync(DP_FULL, s, me ? 31 - __clz(me) : 0);
+                if (lane == 0) sh.wLast[warp] = me ? lastSeed : 0xffffffffu;
+                __syncthreads();
+                // seed of the nearest eligible occurrence before this warp
+                unsigned pv = (int)lane < warp ? sh.wLast[lane] : 0xffffffffu;
+                unsigned mv = __ballot_sync(DP_FULL, pv != 0xffffffffu);
+                unsigned warpCarry = __shfl_sync(DP_FULL, pv, mv ? 31 - __clz(mv) : 0);
+                if (!mv) warpCarry = carry;
+                const unsigned lower = me & lt;
+                unsigned ps = __shfl_sync(DP_FULL, s, lower ? 31 - __clz(lower) : 0);
+                if (!lower) ps = warpCarry;
+                const bool inc = elig && s != ps;
+                const unsigned mi = __ballot_sync(DP_FULL, inc);
+                // carry for the next round: the last eligible occurrence of this round
+                unsigned av = (int)lane < nWarp ? sh.wLast[lane] : 0xffffffffu;
+                unsigned ma = __ballot_sync(DP_FULL, av != 0xffffffffu);
+                if (ma) carry = __shfl_sync(DP_FULL, av, 31 - __clz(ma));
+                unsigned roundTot;
+                const unsigned base = dp_block_excl_scan(inc ? 1u : 0u, sh.wTot, roundTot);  // two barriers inside
+                (void)mi;
+                if (inc) {
+                    const unsigned idx = (unsigned)nInc + base;
+                    eSeed[idx] = s;
+                    eOff[idx] = o;
+                    ePre[idx] = c;  // run length for now; prefix-summed below
+                }
+                nInc += (int)roundTot;
+            }
+            defer = __syncthreads_or(sawAll) != 0;
+            if (!defer && nInc >= 5) {
+                const int minCount = (nInc + 2) >> 2;
+                int T;
+                bool clamped = false;
+                if (minCount >= 9 && minCount <= 12) {
+                    T = 8;
+                    clamped = true;
+                } else if (minCount >= 17 && minCount <= 24) {
+                    T = 16;
+                    clamped = true;
+                } else {
+                    T = minCount;
+                }
+                const bool q6 = minCount >= 13 && minCount <= 24;  // level-16 plane decides alone
+                // ---- run-length prefix, item prefix (items of DP_BSEG postings), last word of each run ----
+                unsigned total = 0, nItems = 0;
+                for (int j0 = 0; j0 < nInc; j0 += nT) {
+                    const int j = j0 + tid;
+                    unsigned c = 0;
+                    if (j < nInc) {
+                        c = ePre[j];
+                        if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
+                    }
+                    unsigned tA, tB;
+                    const unsigned pa = dp_block_excl_scan(c, sh.wTot, tA);
+                    const unsigned pb = dp_block_excl_scan((c + DP_BSEG - 1) / DP_BSEG, sh.wTot, tB);
+                    if (j < nInc) {
+                        ePre[j] = total + pa;
+                        eItem[j] = nItems + pb;
+                    }
+                    total += tA;
+                    nItems += tB;
+                }
+                if (tid == 0) {
+                    ePre[nInc] = total;
+                    eItem[nInc] = nItems;
+                }
+                __syncthreads();
+                // ---- per pass over a chunk range: gather into the counters, then scan + zero them ----
+                for (unsigned tileLo = 0; tileLo < C; tileLo += (unsigned)G.tileChunks) {
+                    for (unsigned it = (unsigned)warp; it < nItems; it += (unsigned)nWarp) {
+                        int lo = 0, hi = nInc;  // largest run j with eItem[j] <= it
+                        while (hi - lo > 1) {
+                            int mid = (lo + hi) >> 1;
+                            if (eItem[mid] <= it) lo = mid;
+                            else hi = mid;
+                        }
+                        const unsigned seg = it - eItem[lo];
+                        const unsigned runLen = ePre[lo + 1] - ePre[lo];
+                        const unsigned off = eOff[lo] + seg * DP_BSEG;
+                        const unsigned len = min((unsigned)DP_BSEG, runLen - seg * DP_BSEG);
+                        unsigned ch[DP_BSEG / 32];
+#pragma unroll
+                        for (int u = 0; u < DP_BSEG / 32; u++) {
+                            const unsigned p = lane + 32u * u;
+                            ch[u] = p < len ? __ldg(I.seedChunks + off + p) : 0xffffffffu;
+                        }
+#pragma unroll
+                        for (int u = 0; u < DP_BSEG / 32; u++) {
+                            const unsigned c = ch[u] - tileLo;  // out-of-pass chunks and the padding wrap or exceed
+                            if (c < (unsigned)G.tileChunks && ch[u] != 0xffffffffu)
+                                atomicAdd(cnt + (c >> 1), 1u << ((c & 1u) * 16u));
+                        }
+                    }
+                    __syncthreads();
+                    uint4* cnt4 = reinterpret_cast<uint4*>(cnt);
+                    for (int w4 = tid; w4 < (tileWords >> 2); w4 += nT) {
+                        const uint4 v = cnt4[w4];
+                        if (v.x | v.y | v.z | v.w) {
+                            cnt4[w4] = make_uint4(0, 0, 0, 0);
+                            const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int h = 0; h < 8; h++) {
+                                const unsigned cv = (vv[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
+                                if ((int)cv >= T) {
+                                    const int slot = atomicAdd(&sh.nCand, 1);
+                                    const unsigned long long e =
+                                        ((unsigned long long)(tileLo + 8u * (unsigned)w4 + (unsigned)h) << 32) | cv;
+                                    if (slot < DP_BCAND) shCand[slot] = e;
+                                    else if (slot < S.tStride) gCand[slot] = e;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    cRuns += (unsigned)nInc;
+                    cEntries += total;
+                }
+                int nCand = sh.nCand;
+                if (nCand > S.tStride) nCand = S.tStride;  // cannot happen: at most C chunks
+                if (nCand > 0) {
+                    // ---- ascending chunk id (rank sort: chunk ids are distinct) ----
+                    const unsigned long long* sorted = shCand;
+                    if (nCand <= DP_BCAND) {
+                        unsigned long long e = 0;
+                        int rank = 0;
+                        if (tid < nCand) {
+                            e = shCand[tid];
+                            for (int y = 0; y < nCand; y++) rank += (shCand[y] >> 32) < (e >> 32);
+                        }
+                        __syncthreads();
+                        if (tid < nCand) shCand[rank] = e;
+                    } else {
+                        for (int x = tid; x < DP_BCAND; x += nT) gCand[x] = shCand[x];
+                        __syncthreads();
+                        unsigned long long* dst = gCand + S.tStride;
+                        for (int x = tid; x < nCand; x += nT) {
+                            const unsigned long long e = gCand[x];
+                            int rank = 0;
+                            for (int y = 0; y < nCand; y++) rank += (gCand[y] >> 32) < (e >> 32);
+                            dst[rank] = e;
+                        }
+                        sorted = dst;
+                    }
+                    // ---- runs that repeat an earlier run's seed (for the distinct counts) ----
+                    for (int j = tid; j < nInc; j += nT) {
+                        const unsigned s = eSeed[j];
+                        bool first = true;
+                        for (int b = 0; b < j; b++)
+                            if (eSeed[b] == s) {
+                                first = false;
+                                break;
+                            }
+                        eFirst[j] = first ? 1 : 0;
+                        if (!first) {
+                            const int slot = atomicAdd(&sh.nDup, 1);
+                            if (slot < DP_BDUP) shDup[slot] = (unsigned short)j;
+                        }
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        DpRefineCtx X;
+                        X.eOff = eOff;
+                        X.ePre = ePre;
+                        X.eEndW = eEndW;
+                        X.eFirst = eFirst;
+                        X.dup = shDup;
+                        X.nDup = sh.nDup <= DP_BDUP ? sh.nDup : -1;
+                        X.order = order;
+                        X.nInc = nInc;
+                        X.minCount = minCount;
+                        X.T = T;
+                        X.clamped = clamped;
+                        X.q6 = q6;
+                        X.nAllDistinct = 0;
+                        int nOut = dp_refine_emit(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
+                                                  candDistinct + (size_t)ws * candStride, candStride);
+                        if (nOut > candStride) {
+                            if (lane == 0) atomicOr(&ctr->overflow, 4u);
+                            nOut = candStride;
+                        }
+                        if (lane == 0) sh.nCandOut = nOut;
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (tid == 0) {
+            if (defer) {
+                G.deferList[atomicAdd(G.nDefer, 1)] = ws;
+            } else {
+                candN[ws] = sh.nCandOut;
+                cCand += (unsigned)sh.nCandOut;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && (cRuns | cCand)) {
+        atomicAdd(&ctr->posting_runs, cRuns);
+        atomicAdd(&ctr->posting_entries, cEntries);
+        atomicAdd(&ctr->candidates, cCand);
+    }
+}
+
+// ===============================================================================================================
 // Stage 3 — chaining: the candidate loop of performMapping (mapping/mapping.go:518-608) with
 // SeedSequence.Match -> Reduced -> dynamicMatch -> extendChain (seeds/sequence.go:85-123, 361-576) and the
 // coordinate arithmetic of GetSeedOffset / GetSeedOffsetFromEnd / GetBasesCovered (sequence.go:830-858, 1239-1276)
