@@ -532,7 +532,7 @@ LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
     // the CTA's global scratch for oversized window strands is shared with the warp kernel's: tStride = C + 8 entries
     if (!want || (long long)I.numChunks + 8 <= (long long)I.maxWindow + 1) return P;
     const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~3 KB of static shared memory
-    const size_t eBytes = (size_t)P.eCap * 21 + 16;  // five uint32 arrays (+2 sentinels) and one byte array
+    const size_t eBytes = (size_t)P.eCap * 21 + 16 + 2 * DP_BITEMS * 4;  // five uint32 arrays (+2 sentinels), one byte array, item list
     size_t tile = ((size_t)I.numChunks + 7) / 8 * 8;
     if (tile * 2 + eBytes > maxSmem) tile = (maxSmem - eBytes) / 2 / 8 * 8;
     if (getenv("DP_LOOKUP_TILE")) tile = std::min<size_t>(tile, std::max(8, atoi(getenv("DP_LOOKUP_TILE")) / 8 * 8));  // tests

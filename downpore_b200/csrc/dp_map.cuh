@@ -714,15 +714,18 @@ __global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I,
 // nearly empty or (beyond 24 000) spills the counters to global memory, where every posting becomes a random
 // read-modify-write. Here the whole CTA owns ONE set of 16-bit counters in shared memory (up to ~110 000 chunks per
 // pass; more chunks = more passes over chunk ranges) and all its warps stream the posting runs of one window strand
-// into it: 256 postings per warp item, eight independent coalesced loads per lane in flight, shared-memory atomics.
-// The counters are then scanned (and zeroed) with 16-byte loads; the few chunks over the threshold are sorted by id
+// into it: items of 128 consecutive postings, four items (16 loads per lane) in flight per warp, shared-memory
+// atomics. A chunk becomes a
+// candidate the moment its counter reaches the threshold (counts only grow), so the counters are never scanned: the
+// few candidates read their final count, the counters are blanked with 16-byte stores, the candidates are sorted by id
 // and handed to the same refinement / distinct-count routine as the warp kernel (dp_refine_emit).
 // At human-genome scale a window strand gathers ~10^5 postings (hundreds of KB): this is the HBM-bound kernel of the
 // path, and its traffic is sequential inside each run.
 // The inclusion filter runs thread-per-seed with a block-wide ordered compaction. Window strands that contain a seed
 // present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel through a list.
 // ===============================================================================================================
-#define DP_BSEG 256    // postings per gather item
+#define DP_BSEG 128    // postings per gather item
+#define DP_BITEMS 1024 // gather items listed in shared memory at a time
 #define DP_BCAND 256   // candidates over the threshold held in shared memory
 #define DP_BDUP 64     // repeated-seed runs listed per window strand
 
@@ -741,6 +744,7 @@ struct DpBlockShared {
     int nCand;
     int nDup;
     int nCandOut;
+    unsigned nextItem;
 };
 
 // exclusive prefix sum over the CTA (blockDim.x <= 1024); total returned in `total`
@@ -781,14 +785,16 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
     const int warp = tid >> 5, nWarp = nT >> 5;
     const unsigned C = I.numChunks;
     const int tileWords = G.tileChunks >> 1;
-    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | eFirst
+    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | item starts | item lengths | eFirst
     unsigned* cnt = dp_smem;
     unsigned* smSeed = cnt + tileWords;
     unsigned* smOff = smSeed + G.eCap;
     unsigned* smPre = smOff + G.eCap;
     unsigned* smItem = smPre + G.eCap + 1;
     unsigned* smEndW = smItem + G.eCap + 1;
-    unsigned char* smFirst = reinterpret_cast<unsigned char*>(smEndW + G.eCap);
+    unsigned* smItemStart = smEndW + G.eCap;
+    unsigned* smItemLen = smItemStart + DP_BITEMS;
+    unsigned char* smFirst = reinterpret_cast<unsigned char*>(smItemLen + DP_BITEMS);
     for (int i = tid; i < tileWords; i += nT) cnt[i] = 0;
     // global scratch of this CTA for oversized window strands
     const size_t so = (size_t)blockIdx.x * S.stride;
@@ -901,52 +907,85 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
                     eItem[nInc] = nItems;
                 }
                 __syncthreads();
-                // ---- per pass over a chunk range: gather into the counters, then scan + zero them ----
+                // ---- per pass over a chunk range: stream the runs into the counters; a chunk becomes a candidate the
+                //      moment its counter reaches T (counts only grow, so that happens once); then read the final counts
+                //      of the candidates and blank the counters ----
                 for (unsigned tileLo = 0; tileLo < C; tileLo += (unsigned)G.tileChunks) {
-                    for (unsigned it = (unsigned)warp; it < nItems; it += (unsigned)nWarp) {
-                        int lo = 0, hi = nInc;  // largest run j with eItem[j] <= it
-                        while (hi - lo > 1) {
-                            int mid = (lo + hi) >> 1;
-                            if (eItem[mid] <= it) lo = mid;
-                            else hi = mid;
+                    const int slot0 = sh.nCand;  // uniform: the previous pass ended with a barrier
+                    const bool onePass = tileLo == 0 && (unsigned)G.tileChunks >= C;
+                    // one counter update; the lane that takes a counter to T reports the chunk as a candidate
+#define DP_COUNT_POSTING(chunkId)                                                          \
+    do {                                                                                   \
+        const unsigned c_ = (chunkId) - tileLo;                                            \
+        if (onePass || c_ < (unsigned)G.tileChunks) {                                      \
+            const unsigned shf_ = (c_ & 1u) * 16u;                                         \
+            const unsigned old_ = atomicAdd(cnt + (c_ >> 1), 1u << shf_);                  \
+            if ((int)((old_ >> shf_) & 0xffffu) + 1 == T) {                                \
+                const int slot_ = atomicAdd(&sh.nCand, 1);                                 \
+                const unsigned long long e_ = (unsigned long long)(chunkId) << 32;         \
+                if (slot_ < DP_BCAND) shCand[slot_] = e_;                                  \
+                else if (slot_ < S.tStride) gCand[slot_] = e_;                             \
+            }                                                                              \
+        }                                                                                  \
+    } while (0)
+                    // The runs are cut into items of <= 128 consecutive postings, listed in shared memory DP_BITEMS at
+                    // a time; a warp takes four items at once, issues all their loads (16 per lane, 2 KB per warp in
+                    // flight) and only then counts: the gather is bound by how many bytes the SM keeps in flight.
+                    for (unsigned d0 = 0; d0 < nItems; d0 += DP_BITEMS) {
+                        const unsigned dN = min((unsigned)DP_BITEMS, nItems - d0);
+                        if (tid == 0) sh.nextItem = 0;
+                        for (int j = tid; j < nInc; j += nT) {
+                            const unsigned first = eItem[j], last = eItem[j + 1];  // this run's items
+                            const unsigned runLen = ePre[j + 1] - ePre[j];
+                            for (unsigned it = max(first, d0); it < min(last, d0 + dN); it++) {
+                                const unsigned seg = it - first;
+                                smItemStart[it - d0] = eOff[j] + seg * DP_BSEG;
+                                smItemLen[it - d0] = min((unsigned)DP_BSEG, runLen - seg * DP_BSEG);
+                            }
                         }
-                        const unsigned seg = it - eItem[lo];
-                        const unsigned runLen = ePre[lo + 1] - ePre[lo];
-                        const unsigned off = eOff[lo] + seg * DP_BSEG;
-                        const unsigned len = min((unsigned)DP_BSEG, runLen - seg * DP_BSEG);
-                        unsigned ch[DP_BSEG / 32];
+                        __syncthreads();
+                        for (;;) {
+                            unsigned it = 0;
+                            if (lane == 0) it = atomicAdd(&sh.nextItem, 4u);
+                            it = __shfl_sync(DP_FULL, it, 0);
+                            if (it >= dN) break;
+                            unsigned start[4], len[4], v[4][4];
 #pragma unroll
-                        for (int u = 0; u < DP_BSEG / 32; u++) {
-                            const unsigned p = lane + 32u * u;
-                            ch[u] = p < len ? __ldg(I.seedChunks + off + p) : 0xffffffffu;
-                        }
+                            for (int d = 0; d < 4; d++) {
+                                const bool have = it + d < dN;
+                                start[d] = have ? smItemStart[it + d] : 0u;
+                                len[d] = have ? smItemLen[it + d] : 0u;
+                            }
 #pragma unroll
-                        for (int u = 0; u < DP_BSEG / 32; u++) {
-                            const unsigned c = ch[u] - tileLo;  // out-of-pass chunks and the padding wrap or exceed
-                            if (c < (unsigned)G.tileChunks && ch[u] != 0xffffffffu)
-                                atomicAdd(cnt + (c >> 1), 1u << ((c & 1u) * 16u));
+                            for (int d = 0; d < 4; d++)
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const unsigned p = lane + 32u * u;
+                                    v[d][u] = p < len[d] ? __ldg(I.seedChunks + start[d] + p) : 0u;
+                                }
+#pragma unroll
+                            for (int d = 0; d < 4; d++)
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (32u * u < len[d]) {  // warp-uniform
+                                        if (lane + 32u * u < len[d]) DP_COUNT_POSTING(v[d][u]);
+                                    }
                         }
+                        __syncthreads();
+                    }
+#undef DP_COUNT_POSTING
+                    __syncthreads();
+                    const int slot1 = min(sh.nCand, S.tStride);
+                    for (int x = slot0 + tid; x < slot1; x += nT) {  // final counts of this pass's candidates
+                        unsigned long long e = x < DP_BCAND ? shCand[x] : gCand[x];
+                        const unsigned c = (unsigned)(e >> 32) - tileLo;
+                        e |= (cnt[c >> 1] >> ((c & 1u) * 16u)) & 0xffffu;
+                        if (x < DP_BCAND) shCand[x] = e;
+                        else gCand[x] = e;
                     }
                     __syncthreads();
                     uint4* cnt4 = reinterpret_cast<uint4*>(cnt);
-                    for (int w4 = tid; w4 < (tileWords >> 2); w4 += nT) {
-                        const uint4 v = cnt4[w4];
-                        if (v.x | v.y | v.z | v.w) {
-                            cnt4[w4] = make_uint4(0, 0, 0, 0);
-                            const unsigned vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int h = 0; h < 8; h++) {
-                                const unsigned cv = (vv[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
-                                if ((int)cv >= T) {
-                                    const int slot = atomicAdd(&sh.nCand, 1);
-                                    const unsigned long long e =
-                                        ((unsigned long long)(tileLo + 8u * (unsigned)w4 + (unsigned)h) << 32) | cv;
-                                    if (slot < DP_BCAND) shCand[slot] = e;
-                                    else if (slot < S.tStride) gCand[slot] = e;
-                                }
-                            }
-                        }
-                    }
+                    for (int w4 = tid; w4 < (tileWords >> 2); w4 += nT) cnt4[w4] = make_uint4(0, 0, 0, 0);
                     __syncthreads();
                 }
                 if (tid == 0) {
