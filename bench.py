@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (one 65536-read sub-batch), profiles/r1c_ncu_summary.txt
-TRAFFIC_PER_LAUNCH = {"pack": None, "extract": None, "lookup": None, "chain": None}
+TRAFFIC_PER_LAUNCH = {"pack": None, "extract": None, "lookup": None, "chain": None, "lookup_block": None}
 
 K = 11
 REF_LEN = 4_600_000
@@ -198,6 +198,52 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def hbm_regime(dp, synth, device, peak, peak_src, gather_gbs, ref_len=1_000_000_000, n=20_000, L=15_000):
+    """dp_lookup_block_kernel on an index far larger than L2: posting bytes per second against the HBM peak."""
+    import torch
+    ref = synth.reference(4, ref_len)
+    t0 = time.time()
+    vals = dp.kmer_values(dp.kmer_counts(ref, K, device=device), K)
+    gm = dp.Mapper(ref, vals, circular=False, device=device)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    info = gm.index_info()
+    pinned = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+    synth.reads(ref, 14, n, L, circular=False, out=pinned.numpy())
+    del ref
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    d_reads = pinned.to(torch.device("cuda", device))
+    os.environ["DP_LANES"] = "1"   # kernels alone on the device: the CUDA-event brackets are per-kernel times
+    os.environ["DP_RAMP"] = "0"
+    try:
+        for _ in range(3):
+            maps, off = gm.map_batch_device(d_reads.data_ptr(), offs)
+        t0 = time.time()
+        maps, off = gm.map_batch_device(d_reads.data_ptr(), offs)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        st = gm.stats()
+    finally:
+        del os.environ["DP_LANES"], os.environ["DP_RAMP"]
+    gm.close()
+    canon = 16.0 * st["posting_runs"] + 8.0 * st["posting_entries"]     # SURVEY 8d accounting (8 B per posting)
+    actual = 8.0 * st["posting_runs"] + 4.0 * st["posting_entries"]      # what the kernel reads (4 B per posting)
+    ms = st["ms_lookup"]
+    return {"workload": "synthetic %.1f Gb linear reference, %d x %d b reads, device-resident, one lane" % (ref_len / 1e9, n, L),
+            "kernel": "dp_lookup_block_kernel", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+            "achieved": canon / (ms * 1e-3) / 1e9, "frac": canon / (ms * 1e-3) / 1e9 / peak,
+            "achieved_actual_bytes": actual / (ms * 1e-3) / 1e9, "frac_actual_bytes": actual / (ms * 1e-3) / 1e9 / peak,
+            "traffic": TRAFFIC_PER_LAUNCH.get("lookup_block"),
+            "ms_lookup": ms, "posting_runs": st["posting_runs"], "posting_entries": st["posting_entries"],
+            "window_strands": 2 * st["windows"], "hbm_gather_ceiling_GBs": gather_gbs,
+            "Gbp_per_s": n * L / dt / 1e9, "mapped_fraction": float((np.diff(off) > 0).mean()),
+            "stage_ms": {k2: st[k2] for k2 in ("ms_pack", "ms_extract", "ms_lookup", "ms_chain")},
+            "index": dict(info, build_s=t_build),
+            "note": "achieved = SURVEY 8d algorithmic bytes (16 B per included run + 8 B per posting) / CUDA-event time of "
+                    "the lookup kernels of one map call; the kernel's posting array holds 4 B per posting, so the bytes "
+                    "it really moves are achieved_actual_bytes (ncu dram bytes per launch in `traffic`)"}
+
+
 def run_ours(args):
     import torch
     rank, world, local = dist_setup(args.gpus)
@@ -365,6 +411,14 @@ def run_ours(args):
                                        args.index == "broadcast" else "built on every rank")),
             "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
 
+    # ---- the index-lookup kernel where it IS bound by HBM (rank 0, N=1): a 1 Gb reference (BASELINE config 4 shape at
+    #      a third of the size: 101k chunks, 180M postings, 4 GB index >> L2), 15 kb reads, single lane ----
+    if rank == 0 and world == 1 and not args.no_hbm_regime:
+        try:
+            line["roofline_hbm_regime"] = hbm_regime(dp, synth, local, peak, peak_src, gather_gbs)
+        except Exception as ex:  # never lose the headline line to the auxiliary measurement
+            line["roofline_hbm_regime"] = {"error": str(ex)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as po
@@ -402,6 +456,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-regime", action="store_true", help="skip the 1 Gb-reference lookup measurement")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
                     help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")
     args = ap.parse_args()

@@ -310,7 +310,7 @@ struct DpRefineCtx {
 // early stop (Q11) and the level-16 under-count (Q6), computes the DISTINCT query seeds present in each survivor
 // (IntSet.CountIntersectionTo's operand, mapping.go:520-523) and writes (chunk, distinct) pairs. Warp-collective;
 // returns the number of survivors (which may exceed candStride: the caller flags that).
-__device__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const unsigned long long* sorted, int nCand,
+__device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const unsigned long long* sorted, int nCand,
                               unsigned* outChunk, unsigned short* outDist, int candStride) {
     const unsigned lane = dp_lane();
     const int nInc = X.nInc, minCount = X.minCount, T = X.T;
@@ -426,7 +426,7 @@ __device__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const u
 }
 
 
-__global__ void __launch_bounds__(32 * DP_LWARPS) dp_lookup_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+__global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
                                                                   const int* __restrict__ wsList,
                                                                   const int* __restrict__ nWsList,
                                                                   DpLookupScratch S, int countersInSmem,
