@@ -27,8 +27,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (one 65536-read sub-batch), profiles/r1c_ncu_summary.txt
-TRAFFIC_PER_LAUNCH = {"pack": None, "extract": None, "lookup": None, "chain": None, "lookup_block": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
+# profiles/r1d_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = reduce + chain_thread + finish) and
+# profiles/r1d_ncu_lookup_block_1Gb.txt (80000 window strands against the 1 Gb reference)
+TRAFFIC_PER_LAUNCH = {"pack": 170.1e6, "extract": 50.7e6, "lookup": 41.1e6, "chain": 180.7e6, "lookup_block": 13.87e9}
 
 K = 11
 REF_LEN = 4_600_000
