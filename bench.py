@@ -28,9 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
-# profiles/r1d_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = reduce + chain_thread + finish) and
+# profiles/r1d_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = chain_thread + finish) and
 # profiles/r1d_ncu_lookup_block_1Gb.txt (80000 window strands against the 1 Gb reference)
-TRAFFIC_PER_LAUNCH = {"pack": 170.1e6, "extract": 50.7e6, "lookup": 41.1e6, "chain": 180.7e6, "lookup_block": 13.87e9}
+TRAFFIC_PER_LAUNCH = {"pack": 170.1e6, "extract": 50.7e6, "lookup": 41.1e6, "reduce": 94.4e6, "chain": 86.3e6,
+                      "lookup_block": 13.87e9}
 
 K = 11
 REF_LEN = 4_600_000
@@ -365,7 +366,8 @@ def run_ours(args):
     bytes_chain = 8.0 * agg["chain_cells"] / S
     kern = {}
     for name, b, ms in (("pack", bytes_pack, iso["ms_pack"]), ("extract", bytes_extract, iso["ms_extract"]),
-                        ("lookup", bytes_lookup, iso["ms_lookup"]), ("chain", bytes_chain, iso["ms_chain"])):
+                        ("lookup", bytes_lookup, iso["ms_lookup"]), ("reduce", bytes_chain, iso["ms_reduce"]),
+                        ("chain", bytes_chain, iso["ms_chain"])):
         ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
     dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])

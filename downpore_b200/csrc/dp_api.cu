@@ -137,6 +137,7 @@ struct Lane {
     HBuf<long long> hRel;
     size_t hOutTotal = 0;
     bool pendingStageTimes = false;
+    bool reduceTimed = false;
     const unsigned char* curAscii = nullptr;  // device-visible ASCII of the current sub-batch (device or mapped host)
     bool curAsciiIsHost = false;
     cudaEvent_t evReady = nullptr, evPulled = nullptr;  // hand-over to / from the mapper's pull stream
@@ -615,7 +616,7 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.fcSlowList.reserve(nWin);
 }
 
-enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_N };
+enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_REDUCE, T_N };
 enum { CUR_SEEDS = 0, CUR_OUT = 1, CUR_FIN = 2 };
 
 // Launches the three performMapping stages for the `nWin` windows already in W.dWins (device). Results stay on the
@@ -756,6 +757,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         const unsigned long long outCap = (unsigned long long)nWin * M.outStride;
         const bool fast = !(getenv("DP_CHAIN_FAST") && atoi(getenv("DP_CHAIN_FAST")) == 0);
         CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
+        W.reduceTimed = fast;
         if (fast) {
             DpFastChain F;
             F.tasks = W.fcTasks.p;
@@ -772,6 +774,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             dp_reduce_kernel<<<rBlocks, 128, 0, st>>>(I, W.dWins.p, (int)nWin, Q, W.candN.p, W.candChunk.p,
                                                       W.candDistinct.p, W.candStride, S, F);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_REDUCE].b, st));
             dp_chain_thread_kernel<<<div_up((long long)nWin, 128), 128, 0, st>>>(
                 I, W.dWins.p, dReadLen, (int)nWin, Q, W.candN.p, W.candChunk.p, W.candDistinct.p, W.candStride, F,
                 W.outN.p, W.outOff.p, W.outMaps.p, W.cursor.p + CUR_OUT, outCap, W.dCtr.p);
@@ -808,6 +811,12 @@ void collect_stage_times(Lane& W) {  // call after a stream synchronize
     W.stats.ms_lookup += ms;
     CK(cudaEventElapsedTime(&ms, W.timers[T_CHAIN].a, W.timers[T_CHAIN].b));
     W.stats.ms_chain += ms;
+    if (W.reduceTimed) {  // fast path: [a .. reduce.b] is the list reduction, the rest the sequential chaining
+        float mr;
+        CK(cudaEventElapsedTime(&mr, W.timers[T_CHAIN].a, W.timers[T_REDUCE].b));
+        W.stats.ms_reduce += mr;
+        W.stats.ms_chain -= mr;
+    }
     W.pendingStageTimes = false;
 }
 
@@ -1092,6 +1101,7 @@ void add_stats(dp_stats& a, const dp_stats& b) {
     a.ms_extract += b.ms_extract;
     a.ms_lookup += b.ms_lookup;
     a.ms_chain += b.ms_chain;
+    a.ms_reduce += b.ms_reduce;
     a.ms_host_logic += b.ms_host_logic;
     a.ms_h2d += b.ms_h2d;
     a.rounds += b.rounds;

@@ -47,7 +47,7 @@ typedef struct dp_stats {
     double ms_pack;         /* 2-bit pack kernel (only the queried windows are packed) */
     double ms_extract;      /* k-mer scan / seed extraction kernel, summed over rounds */
     double ms_lookup;       /* seed-index lookup (candidate chunks) kernel, summed over rounds */
-    double ms_chain;        /* chaining kernel, summed over rounds */
+    double ms_chain;        /* chaining kernels (sequential chaining, hand-backs, Map()'s first decision), summed over rounds */
     double ms_host_logic;   /* host wall time spent in the per-read Map() strategy between rounds */
     double ms_h2d;          /* host->device staging copies of pageable reads (0 for pinned or device-resident input) */
     int64_t rounds;         /* window-query rounds */
@@ -63,6 +63,7 @@ typedef struct dp_stats {
     int64_t bases;          /* sum of read lengths of the call */
     int64_t h2d_bytes;      /* read bytes that crossed the host->device link (copied, or pulled zero-copy by the
                                windowed pack kernel when the caller's buffer is pinned) */
+    double ms_reduce;       /* list-reduction kernel of the chaining fast path (not included in ms_chain) */
 } dp_stats;
 
 /*
