@@ -436,7 +436,7 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
         CK(cudaMemcpyAsync(&P1, nSel.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    M.seedChunks.reserve((size_t)P1 + 1);
+    M.seedChunks.reserve((size_t)P1 + 4);  // (the block lookup reads aligned 16-byte pieces)
     {
         DBuf<unsigned> seedCount;
         seedCount.reserve((size_t)numSeeds + 2);
@@ -519,29 +519,52 @@ unsigned lookup_smem_chunks() {  // DP_LOOKUP_SMEM_CHUNKS: tests force the warp 
 #define kLookupSmemChunks lookup_smem_chunks()
 const unsigned kLookupBlockMinChunks = 2048;  // from here on a CTA per window strand (dp_lookup_block_kernel)
 
+// per-warp / per-CTA stride of the lookup scratch lists: a window strand touches at most C chunks; the CTA kernel also
+// keeps the item prefix of an oversized window strand (<= maxWindow + 1 entries) there
+size_t lookup_tstride(const DpIndexDev& I) { return std::max<size_t>(I.numChunks, (size_t)I.maxWindow + 1) + 8; }
+
 struct LookupBlockPlan {
     bool use = false;
-    int tileChunks = 0, eCap = 512, threads = 1024, ctasPerSm = 1;
+    int gShift = 0, cntWords = 0, eCap = 512, gListCap = DP_BGLIST, gBatch = DP_BEXACT, ctasPerSm = 1;
     size_t smem = 0;
 };
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
     LookupBlockPlan P;
     const char* env = getenv("DP_LOOKUP_BLOCK");
     bool want = I.numChunks >= kLookupBlockMinChunks;
     if (env) want = atoi(env) != 0;
-    // the CTA's global scratch for oversized window strands is shared with the warp kernel's: tStride = C + 8 entries
-    if (!want || (long long)I.numChunks + 8 <= (long long)I.maxWindow + 1) return P;
-    const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~3 KB of static shared memory
-    const size_t eBytes = (size_t)P.eCap * 21 + 16 + 2 * DP_BITEMS * 4;  // five uint32 arrays (+2 sentinels), one byte array, item list
-    size_t tile = ((size_t)I.numChunks + 7) / 8 * 8;
-    if (tile * 2 + eBytes > maxSmem) tile = (maxSmem - eBytes) / 2 / 8 * 8;
-    if (getenv("DP_LOOKUP_TILE")) tile = std::min<size_t>(tile, std::max(8, atoi(getenv("DP_LOOKUP_TILE")) / 8 * 8));  // tests
-    P.tileChunks = (int)tile;
-    P.smem = (tile * 2 + eBytes + 15) / 16 * 16;
-    size_t fit = (227 * 1024) / (P.smem + 4096);
-    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 8));
-    P.threads = P.ctasPerSm >= 4 ? 256 : (P.ctasPerSm >= 2 ? 512 : 1024);
+    if (!want) return P;
+    const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~4 KB of static shared memory
+    auto counter_words = [&](int gs) { return (size_t)(((((size_t)I.numChunks - 1) >> gs) + 1 + 1) / 2 + 3) / 4 * 4; };
+    auto smem_bytes = [&](int gs) {
+        // counters | five uint32 arrays (+2 sentinels) | item list | exact recount table | one byte array
+        return (counter_words(gs) * 4 + (size_t)P.eCap * 20 + 8 + 2 * DP_BITEMS * 4 + (gs ? DP_BEXACT * 4 : 0) + P.eCap + 15) / 16 * 16;
+    };
+    // a counter covers 2^gShift adjacent chunks. 16-bit group counts stay exact while maxWindow * 2^gShift <= 65535 (a
+    // window strand has at most maxWindow included runs and a run holds each chunk once).
+    int maxShift = 0;
+    while (maxShift < 8 && ((long long)I.maxWindow << (maxShift + 1)) <= 65535) maxShift++;
+    // the smallest gShift whose counters take <= 40 KB keeps four CTAs per SM resident and the groups selective (a random
+    // group collects ~4 * (chunks per seed / C) * 2^gShift of the threshold); beyond 16 chunks per group only when
+    // shared memory leaves no choice
+    int gs = 0;
+    while (gs < maxShift && gs < 4 && counter_words(gs) * 4 > 40 * 1024) gs++;
+    while (gs < maxShift && smem_bytes(gs) > maxSmem) gs++;
+    if (getenv("DP_LOOKUP_GSHIFT")) gs = std::min(maxShift, std::max(0, env_int("DP_LOOKUP_GSHIFT", 0)));  // tests
+    if (smem_bytes(gs) > maxSmem) throw std::runtime_error("reference has too many chunks for the lookup kernel's shared-memory counters");
+    P.gShift = gs;
+    P.cntWords = (int)counter_words(gs);
+    P.smem = smem_bytes(gs);
+    P.gListCap = std::min(DP_BGLIST, std::max(1, env_int("DP_LOOKUP_GLIST", DP_BGLIST)));                // tests
+    P.gBatch = std::min(DP_BEXACT >> gs, std::max(1, env_int("DP_LOOKUP_GBATCH", DP_BEXACT >> gs)));   // tests
+    size_t fit = (227 * 1024) / (P.smem + 5 * 1024);
+    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 4));  // 64 registers x 256 threads: four CTAs per SM
     P.use = true;
     return P;
 }
@@ -580,7 +603,7 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.lsFirst.reserve(lw * qStride);
     W.lsOrder.reserve(lw * qStride);
     // a window strand touches at most min(C, total postings) chunks
-    const size_t tStride = (size_t)I.numChunks + 8;
+    const size_t tStride = lookup_tstride(I);
     W.lsTouched.reserve(lw * tStride);
     W.lsCand.reserve(lw * 2 * tStride);
     if (I.numChunks > kLookupSmemChunks && !W.lsCountersZeroed) {
@@ -673,7 +696,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CK(cudaFuncSetAttribute(dp_lookup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            CK(cudaFuncSetAttribute(dp_lookup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             M.attrsSet = true;
         }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
@@ -696,7 +719,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.touched = W.lsTouched.p;
         S.cand = W.lsCand.p;
         S.stride = qStride;
-        S.tStride = (int)I.numChunks + 8;
+        S.tStride = (int)lookup_tstride(I);
         int inSmem = I.numChunks <= kLookupSmemChunks ? 1 : 0;
         int warpsPerBlock = DP_LWARPS;
         size_t smem = inSmem ? (size_t)warpsPerBlock * ((I.numChunks + 1) / 2) * sizeof(unsigned) : 0;
@@ -704,8 +727,11 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
         if (LP.use) {
             DpLookupBlockCfg G;
-            G.tileChunks = LP.tileChunks;
+            G.gShift = LP.gShift;
+            G.cntWords = LP.cntWords;
             G.eCap = LP.eCap;
+            G.gListCap = LP.gListCap;
+            G.gBatch = LP.gBatch;
             G.work = W.lbWork.p;
             G.deferList = W.lbDefer.p;
             G.nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
@@ -713,7 +739,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             int ctas = LP.ctasPerSm;
             if (W.curAsciiIsHost && ctas > 1) ctas -= ctas / 4 ? ctas / 4 : 0;  // headroom for the pull kernel
             int blocks = (int)std::min<size_t>(2 * nWin, (size_t)M.smCount * ctas);
-            dp_lookup_block_kernel<<<blocks, LP.threads, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
+            dp_lookup_block_kernel<<<blocks, DP_BTHREADS, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
                                                                        W.candDistinct.p, W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
             // window strands the CTA kernel deferred (a seed present in every chunk): none on real references

@@ -711,27 +711,41 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 // Stage 2 for indexes with many chunks — one CTA per window strand (dp_lookup_block_kernel).
 //
 // With C chunks a warp-private set of counters costs 2C bytes; beyond a few thousand chunks that either leaves the SM
-// nearly empty or (beyond 24 000) spills the counters to global memory, where every posting becomes a random
-// read-modify-write. Here the whole CTA owns ONE set of 16-bit counters in shared memory (up to ~110 000 chunks per
-// pass; more chunks = more passes over chunk ranges) and all its warps stream the posting runs of one window strand
-// into it: items of 128 consecutive postings, four items (16 loads per lane) in flight per warp, shared-memory
-// atomics. A chunk becomes a
-// candidate the moment its counter reaches the threshold (counts only grow), so the counters are never scanned: the
-// few candidates read their final count, the counters are blanked with 16-byte stores, the candidates are sorted by id
-// and handed to the same refinement / distinct-count routine as the warp kernel (dp_refine_emit).
-// At human-genome scale a window strand gathers ~10^5 postings (hundreds of KB): this is the HBM-bound kernel of the
-// path, and its traffic is sequential inside each run.
-// The inclusion filter runs thread-per-seed with a block-wide ordered compaction. Window strands that contain a seed
-// present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel through a list.
+// nearly empty or spills the counters to global memory, where every posting becomes a random read-modify-write.
+// Here a CTA of 256 threads owns ONE set of 16-bit counters in shared memory and all its warps stream the posting runs
+// of one window strand into it. To keep several CTAs resident per SM at human-genome scale (10^5 chunks and more) the
+// counters are COARSE: counter g counts the postings of the 2^gShift adjacent chunks g*2^gShift ... (a group's count
+// is >= the count of each of its chunks, so every chunk over the threshold lies in a group over the threshold).
+//
+//   1. inclusion filter, thread per query seed, block-wide ordered compaction                 (seeds.go:340-346)
+//   2. the runs are cut into items of 128 postings aligned to 16 bytes; a warp takes four items at once, issues its
+//      four 16-byte loads per lane (2 KB per warp in flight), then adds into the group counters with shared-memory
+//      reductions (no return value, no per-posting test)
+//   3. one pass over the counters finds the groups that reached the threshold and blanks the counters (16-byte
+//      loads/stores); with gShift = 0 these are the candidates and their exact counts
+//   4. gShift > 0: for the few groups over the threshold (the true locus; random groups stay far below it) every run
+//      binary-searches the group's first chunk and adds its <= 2^gShift postings to an exact per-chunk table
+//   5. candidates sorted by chunk id -> dp_refine_emit, as in the warp kernel
+//
+// At human-genome scale a window strand gathers 10^4-10^5 postings (hundreds of KB): this is the HBM-bound kernel of
+// the path; its traffic is sequential inside each run and every posting is read once.
+// Window strands that contain a seed present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel
+// through a list.
 // ===============================================================================================================
-#define DP_BSEG 128    // postings per gather item
-#define DP_BITEMS 1024 // gather items listed in shared memory at a time
-#define DP_BCAND 256   // candidates over the threshold held in shared memory
-#define DP_BDUP 64     // repeated-seed runs listed per window strand
+#define DP_BTHREADS 256 // threads per CTA
+#define DP_BSEG 128     // postings per gather item
+#define DP_BITEMS 512   // gather items listed in shared memory at a time
+#define DP_BCAND 256    // candidates over the threshold held in shared memory
+#define DP_BDUP 64      // repeated-seed runs listed per window strand
+#define DP_BGLIST 256   // groups over the threshold listed in shared memory (more: global scratch)
+#define DP_BEXACT 2048  // words of the exact recount table: DP_BEXACT >> gShift groups are recounted at a time
 
 struct DpLookupBlockCfg {
-    int tileChunks;  // chunks covered by the shared-memory counters per pass (multiple of 8)
+    int gShift;      // a counter covers 2^gShift adjacent chunks
+    int cntWords;    // 32-bit words of packed 16-bit counters (multiple of 4)
     int eCap;        // included runs held in shared memory (more: global scratch)
+    int gListCap;    // groups listed in shared memory before the list spills (<= DP_BGLIST; tests shrink it)
+    int gBatch;      // groups recounted at a time (<= DP_BEXACT >> gShift; tests shrink it)
     unsigned* work;  // dynamic work counter, zero at launch
     int* deferList;  // window strands left to dp_lookup_kernel
     int* nDefer;
@@ -744,6 +758,7 @@ struct DpBlockShared {
     int nCand;
     int nDup;
     int nCandOut;
+    int nGroup;
     unsigned nextItem;
 };
 
@@ -769,37 +784,46 @@ __device__ __forceinline__ unsigned dp_block_excl_scan(unsigned v, unsigned* wTo
     return base + x - v;
 }
 
-__global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
-                                                                  DpLookupScratch S, DpLookupBlockCfg G,
-                                                                  int* __restrict__ candN,
-                                                                  unsigned* __restrict__ candChunk,
-                                                                  unsigned short* __restrict__ candDistinct,
-                                                                  int candStride, DpCounters* __restrict__ ctr) {
+// one posting into the packed 16-bit group counters (shared-memory reduction, result unused)
+__device__ __forceinline__ void dp_group_count(unsigned* cnt, unsigned chunk, int gShift) {
+    const unsigned g = chunk >> gShift;
+    atomicAdd(cnt + (g >> 1), 1u << ((g & 1u) << 4));
+}
+
+__global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                         DpLookupScratch S, DpLookupBlockCfg G,
+                                                                         int* __restrict__ candN,
+                                                                         unsigned* __restrict__ candChunk,
+                                                                         unsigned short* __restrict__ candDistinct,
+                                                                         int candStride, DpCounters* __restrict__ ctr) {
     extern __shared__ unsigned dp_smem[];
     __shared__ DpBlockShared sh;
     __shared__ unsigned long long shCand[DP_BCAND];
     __shared__ unsigned short shDup[DP_BDUP];
+    __shared__ unsigned shGroup[DP_BGLIST];
     const int tid = threadIdx.x, nT = blockDim.x;
     const unsigned lane = dp_lane();
-    const unsigned lt = dp_lanemask_lt();
     const int warp = tid >> 5, nWarp = nT >> 5;
     const unsigned C = I.numChunks;
-    const int tileWords = G.tileChunks >> 1;
-    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | item starts | item lengths | eFirst
+    const int gShift = G.gShift;
+    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | item starts | item ranges | exact | eFirst
     unsigned* cnt = dp_smem;
-    unsigned* smSeed = cnt + tileWords;
+    unsigned* smSeed = cnt + G.cntWords;
     unsigned* smOff = smSeed + G.eCap;
     unsigned* smPre = smOff + G.eCap;
     unsigned* smItem = smPre + G.eCap + 1;
     unsigned* smEndW = smItem + G.eCap + 1;
     unsigned* smItemStart = smEndW + G.eCap;
-    unsigned* smItemLen = smItemStart + DP_BITEMS;
-    unsigned char* smFirst = reinterpret_cast<unsigned char*>(smItemLen + DP_BITEMS);
-    for (int i = tid; i < tileWords; i += nT) cnt[i] = 0;
+    unsigned* smItemRange = smItemStart + DP_BITEMS;
+    unsigned* exact = smItemRange + DP_BITEMS;
+    unsigned char* smFirst = reinterpret_cast<unsigned char*>(exact + (gShift ? DP_BEXACT : 0));
+    for (int i = tid; i < G.cntWords; i += nT) cnt[i] = 0;
     // global scratch of this CTA for oversized window strands
     const size_t so = (size_t)blockIdx.x * S.stride;
     unsigned short* order = S.order + so;
     unsigned long long* gCand = S.cand + (size_t)blockIdx.x * 2 * S.tStride;
+    unsigned* gGroup = reinterpret_cast<unsigned*>(gCand + S.tStride);  // (the sort space: free until the sort)
+    const uint4* chunks4 = reinterpret_cast<const uint4*>(I.seedChunks);
     unsigned long long cRuns = 0, cEntries = 0, cCand = 0;  // thread 0 only
     __syncthreads();
 
@@ -809,6 +833,7 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
             sh.nCand = 0;
             sh.nDup = 0;
             sh.nCandOut = 0;
+            sh.nGroup = 0;
         }
         __syncthreads();
         const int ws = sh.ws;
@@ -848,18 +873,16 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
                 unsigned mv = __ballot_sync(DP_FULL, pv != 0xffffffffu);
                 unsigned warpCarry = __shfl_sync(DP_FULL, pv, mv ? 31 - __clz(mv) : 0);
                 if (!mv) warpCarry = carry;
-                const unsigned lower = me & lt;
+                const unsigned lower = me & dp_lanemask_lt();
                 unsigned ps = __shfl_sync(DP_FULL, s, lower ? 31 - __clz(lower) : 0);
                 if (!lower) ps = warpCarry;
                 const bool inc = elig && s != ps;
-                const unsigned mi = __ballot_sync(DP_FULL, inc);
                 // carry for the next round: the last eligible occurrence of this round
                 unsigned av = (int)lane < nWarp ? sh.wLast[lane] : 0xffffffffu;
                 unsigned ma = __ballot_sync(DP_FULL, av != 0xffffffffu);
                 if (ma) carry = __shfl_sync(DP_FULL, av, 31 - __clz(ma));
                 unsigned roundTot;
                 const unsigned base = dp_block_excl_scan(inc ? 1u : 0u, sh.wTot, roundTot);  // two barriers inside
-                (void)mi;
                 if (inc) {
                     const unsigned idx = (unsigned)nInc + base;
                     eSeed[idx] = s;
@@ -883,18 +906,21 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
                     T = minCount;
                 }
                 const bool q6 = minCount >= 13 && minCount <= 24;  // level-16 plane decides alone
-                // ---- run-length prefix, item prefix (items of DP_BSEG postings), last word of each run ----
+                // ---- run-length prefix, item prefix, last word of each run ----
+                // items of run [off, off+c): the 128-posting pieces of [off & ~3, off+c) (16-byte aligned starts)
                 unsigned total = 0, nItems = 0;
                 for (int j0 = 0; j0 < nInc; j0 += nT) {
                     const int j = j0 + tid;
-                    unsigned c = 0;
+                    unsigned c = 0, items = 0;
                     if (j < nInc) {
                         c = ePre[j];
-                        if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
+                        const unsigned off = eOff[j];
+                        if (c) items = (off + c - (off & ~3u) + DP_BSEG - 1) / DP_BSEG;
+                        if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + off + c - 1) >> 6) : 0u;
                     }
                     unsigned tA, tB;
                     const unsigned pa = dp_block_excl_scan(c, sh.wTot, tA);
-                    const unsigned pb = dp_block_excl_scan((c + DP_BSEG - 1) / DP_BSEG, sh.wTot, tB);
+                    const unsigned pb = dp_block_excl_scan(items, sh.wTot, tB);
                     if (j < nInc) {
                         ePre[j] = total + pa;
                         eItem[j] = nItems + pb;
@@ -907,86 +933,129 @@ __global__ void __launch_bounds__(1024, 1) dp_lookup_block_kernel(DpIndexDev I, 
                     eItem[nInc] = nItems;
                 }
                 __syncthreads();
-                // ---- per pass over a chunk range: stream the runs into the counters; a chunk becomes a candidate the
-                //      moment its counter reaches T (counts only grow, so that happens once); then read the final counts
-                //      of the candidates and blank the counters ----
-                for (unsigned tileLo = 0; tileLo < C; tileLo += (unsigned)G.tileChunks) {
-                    const int slot0 = sh.nCand;  // uniform: the previous pass ended with a barrier
-                    const bool onePass = tileLo == 0 && (unsigned)G.tileChunks >= C;
-                    // one counter update; the lane that takes a counter to T reports the chunk as a candidate
-#define DP_COUNT_POSTING(chunkId)                                                          \
-    do {                                                                                   \
-        const unsigned c_ = (chunkId) - tileLo;                                            \
-        if (onePass || c_ < (unsigned)G.tileChunks) {                                      \
-            const unsigned shf_ = (c_ & 1u) * 16u;                                         \
-            const unsigned old_ = atomicAdd(cnt + (c_ >> 1), 1u << shf_);                  \
-            if ((int)((old_ >> shf_) & 0xffffu) + 1 == T) {                                \
-                const int slot_ = atomicAdd(&sh.nCand, 1);                                 \
-                const unsigned long long e_ = (unsigned long long)(chunkId) << 32;         \
-                if (slot_ < DP_BCAND) shCand[slot_] = e_;                                  \
-                else if (slot_ < S.tStride) gCand[slot_] = e_;                             \
-            }                                                                              \
-        }                                                                                  \
-    } while (0)
-                    // The runs are cut into items of <= 128 consecutive postings, listed in shared memory DP_BITEMS at
-                    // a time; a warp takes four items at once, issues all their loads (16 per lane, 2 KB per warp in
-                    // flight) and only then counts: the gather is bound by how many bytes the SM keeps in flight.
-                    for (unsigned d0 = 0; d0 < nItems; d0 += DP_BITEMS) {
-                        const unsigned dN = min((unsigned)DP_BITEMS, nItems - d0);
-                        if (tid == 0) sh.nextItem = 0;
-                        for (int j = tid; j < nInc; j += nT) {
-                            const unsigned first = eItem[j], last = eItem[j + 1];  // this run's items
-                            const unsigned runLen = ePre[j + 1] - ePre[j];
-                            for (unsigned it = max(first, d0); it < min(last, d0 + dN); it++) {
-                                const unsigned seg = it - first;
-                                smItemStart[it - d0] = eOff[j] + seg * DP_BSEG;
-                                smItemLen[it - d0] = min((unsigned)DP_BSEG, runLen - seg * DP_BSEG);
-                            }
+                // ---- stream the runs into the group counters ----
+                for (unsigned d0 = 0; d0 < nItems; d0 += DP_BITEMS) {
+                    const unsigned dN = min((unsigned)DP_BITEMS, nItems - d0);
+                    if (tid == 0) sh.nextItem = 0;
+                    for (int j = tid; j < nInc; j += nT) {
+                        const unsigned first = eItem[j], last = eItem[j + 1];  // this run's items
+                        if (last <= d0 || first >= d0 + dN) continue;
+                        const unsigned off = eOff[j], end = off + (ePre[j + 1] - ePre[j]);
+                        const unsigned a = off & ~3u;
+                        for (unsigned it = max(first, d0); it < min(last, d0 + dN); it++) {
+                            const unsigned st = a + (it - first) * DP_BSEG;
+                            const unsigned lo = max(off, st) - st, hi = min(end, st + DP_BSEG) - st;
+                            smItemStart[it - d0] = st >> 2;
+                            smItemRange[it - d0] = lo | (hi << 8);
                         }
-                        __syncthreads();
-                        for (;;) {
-                            unsigned it = 0;
-                            if (lane == 0) it = atomicAdd(&sh.nextItem, 4u);
-                            it = __shfl_sync(DP_FULL, it, 0);
-                            if (it >= dN) break;
-                            unsigned start[4], len[4], v[4][4];
-#pragma unroll
-                            for (int d = 0; d < 4; d++) {
-                                const bool have = it + d < dN;
-                                start[d] = have ? smItemStart[it + d] : 0u;
-                                len[d] = have ? smItemLen[it + d] : 0u;
-                            }
-#pragma unroll
-                            for (int d = 0; d < 4; d++)
-#pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const unsigned p = lane + 32u * u;
-                                    v[d][u] = p < len[d] ? __ldg(I.seedChunks + start[d] + p) : 0u;
-                                }
-#pragma unroll
-                            for (int d = 0; d < 4; d++)
-#pragma unroll
-                                for (int u = 0; u < 4; u++)
-                                    if (32u * u < len[d]) {  // warp-uniform
-                                        if (lane + 32u * u < len[d]) DP_COUNT_POSTING(v[d][u]);
-                                    }
-                        }
-                        __syncthreads();
-                    }
-#undef DP_COUNT_POSTING
-                    __syncthreads();
-                    const int slot1 = min(sh.nCand, S.tStride);
-                    for (int x = slot0 + tid; x < slot1; x += nT) {  // final counts of this pass's candidates
-                        unsigned long long e = x < DP_BCAND ? shCand[x] : gCand[x];
-                        const unsigned c = (unsigned)(e >> 32) - tileLo;
-                        e |= (cnt[c >> 1] >> ((c & 1u) * 16u)) & 0xffffu;
-                        if (x < DP_BCAND) shCand[x] = e;
-                        else gCand[x] = e;
                     }
                     __syncthreads();
+                    for (;;) {
+                        unsigned it = 0;
+                        if (lane == 0) it = atomicAdd(&sh.nextItem, 4u);
+                        it = __shfl_sync(DP_FULL, it, 0);
+                        if (it >= dN) break;
+                        uint4 v[4];
+                        unsigned rg[4];
+#pragma unroll
+                        for (int d = 0; d < 4; d++) {
+                            const bool have = it + d < dN;
+                            rg[d] = have ? smItemRange[it + d] : 0u;
+                            const unsigned st4 = have ? smItemStart[it + d] : 0u;
+                            v[d] = make_uint4(0, 0, 0, 0);
+                            if (4u * lane < (rg[d] >> 8)) v[d] = __ldg(chunks4 + st4 + lane);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 4; d++) {
+                            const unsigned lo = rg[d] & 0xffu, hi = rg[d] >> 8;
+                            const unsigned b = 4u * lane;
+                            if (lo == 0 && hi == DP_BSEG) {  // warp-uniform: an interior item
+                                dp_group_count(cnt, v[d].x, gShift);
+                                dp_group_count(cnt, v[d].y, gShift);
+                                dp_group_count(cnt, v[d].z, gShift);
+                                dp_group_count(cnt, v[d].w, gShift);
+                            } else if (hi) {
+                                if (b >= lo && b < hi) dp_group_count(cnt, v[d].x, gShift);
+                                if (b + 1 >= lo && b + 1 < hi) dp_group_count(cnt, v[d].y, gShift);
+                                if (b + 2 >= lo && b + 2 < hi) dp_group_count(cnt, v[d].z, gShift);
+                                if (b + 3 >= lo && b + 3 < hi) dp_group_count(cnt, v[d].w, gShift);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                // ---- counters over the threshold; blank the counters ----
+                {
+                    const unsigned T2 = (unsigned)T | ((unsigned)T << 16);
                     uint4* cnt4 = reinterpret_cast<uint4*>(cnt);
-                    for (int w4 = tid; w4 < (tileWords >> 2); w4 += nT) cnt4[w4] = make_uint4(0, 0, 0, 0);
+                    for (int w4 = tid; w4 < (G.cntWords >> 2); w4 += nT) {
+                        const uint4 x = cnt4[w4];
+                        cnt4[w4] = make_uint4(0, 0, 0, 0);
+                        const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            unsigned m = __vcmpgeu2(xs[i], T2);
+                            while (m) {
+                                const unsigned half = (m & 0xffffu) ? 0u : 1u;
+                                m &= half ? 0x0000ffffu : 0xffff0000u;
+                                const unsigned g = ((unsigned)w4 * 4u + (unsigned)i) * 2u + half;
+                                const unsigned count = (xs[i] >> (half * 16u)) & 0xffffu;
+                                if (gShift == 0) {
+                                    const int slot = atomicAdd(&sh.nCand, 1);
+                                    const unsigned long long e = ((unsigned long long)g << 32) | count;
+                                    if (slot < DP_BCAND) shCand[slot] = e;
+                                    else if (slot < S.tStride) gCand[slot] = e;
+                                } else {
+                                    const int slot = atomicAdd(&sh.nGroup, 1);
+                                    if (slot < G.gListCap) shGroup[slot] = g;
+                                    else gGroup[slot] = g;
+                                }
+                            }
+                        }
+                    }
                     __syncthreads();
+                }
+                // ---- exact per-chunk counts of the groups over the threshold ----
+                if (gShift) {
+                    const int nG = sh.nGroup;
+                    const unsigned gSize = 1u << gShift;
+                    for (int b0 = 0; b0 < nG; b0 += G.gBatch) {
+                        const int bn = min(G.gBatch, nG - b0);
+                        for (int x = tid; x < (bn << gShift); x += nT) exact[x] = 0;
+                        __syncthreads();
+                        for (int idx = tid; idx < bn * nInc; idx += nT) {
+                            const int gi = idx / nInc, j = idx - gi * nInc;
+                            const int gx = b0 + gi;
+                            const unsigned g = gx < G.gListCap ? shGroup[gx] : gGroup[gx];
+                            const unsigned cLo = g << gShift, cHi = cLo + gSize;
+                            const unsigned off = eOff[j], len = ePre[j + 1] - ePre[j];
+                            unsigned lo = 0, hi = len;
+                            while (lo < hi) {
+                                const unsigned mid = (lo + hi) >> 1;
+                                if (__ldg(I.seedChunks + off + mid) < cLo) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            for (unsigned p = lo; p < len; p++) {
+                                const unsigned c = __ldg(I.seedChunks + off + p);
+                                if (c >= cHi) break;
+                                atomicAdd(exact + ((unsigned)gi << gShift) + (c - cLo), 1u);
+                            }
+                        }
+                        __syncthreads();
+                        for (int x = tid; x < (bn << gShift); x += nT) {
+                            const unsigned count = exact[x];
+                            if ((int)count >= T) {
+                                const int gx = b0 + (x >> gShift);
+                                const unsigned g = gx < G.gListCap ? shGroup[gx] : gGroup[gx];
+                                const unsigned chunk = (g << gShift) + ((unsigned)x & (gSize - 1u));
+                                const int slot = atomicAdd(&sh.nCand, 1);
+                                const unsigned long long e = ((unsigned long long)chunk << 32) | count;
+                                if (slot < DP_BCAND) shCand[slot] = e;
+                                else if (slot < S.tStride) gCand[slot] = e;
+                            }
+                        }
+                        __syncthreads();
+                    }
                 }
                 if (tid == 0) {
                     cRuns += (unsigned)nInc;

@@ -224,8 +224,9 @@ def large_ref():
 @pytest.mark.parametrize("env", [
     {},                                                        # warp per window strand, shared-memory counters
     {"DP_LOOKUP_SMEM_CHUNKS": "100"},                          # warp kernel, counters in global memory
-    {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one pass
-    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_TILE": "512"},         # CTA kernel, four passes over chunk ranges
+    {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one counter per chunk
+    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "3"},         # CTA kernel, a counter per 8 chunks + exact recount
+    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "5", "DP_LOOKUP_GLIST": "2", "DP_LOOKUP_GBATCH": "3"},  # spilled group list
 ])
 def test_lookup_kernels_on_a_large_reference(large_ref, env):
     """Every route through the index lookup gives the oracle's records and counters."""
@@ -244,10 +245,12 @@ def test_lookup_kernels_on_a_large_reference(large_ref, env):
         assert st[key] == octr[key], key
 
 
-@pytest.mark.parametrize("env", [{"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_TILE": "64"}])
+@pytest.mark.parametrize("env", [{"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "1"},
+                                 {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "3", "DP_LOOKUP_GLIST": "1", "DP_LOOKUP_GBATCH": "1"}])
 def test_block_lookup_on_mixed_reads(env):
     """The CTA-per-window-strand lookup on a small circular reference with short, chimeric and whole-read windows
-    (few seeds per strand: every threshold level below 13 occurs), also with its counters cut into many passes."""
+    (few seeds per strand: every threshold level below 13 occurs), also with coarse counters (many groups pass the
+    low thresholds: the group list spills and is recounted one group at a time)."""
     ref = synth.reference(12, 500_000)
     vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
     om = po.Mapper(ref, vals, circular=True)
@@ -269,6 +272,7 @@ def test_block_lookup_on_mixed_reads(env):
     # host replay serves the repeat from its cache)
     for key in ("posting_runs", "posting_entries", "candidates"):
         assert st[key] == st0[key] <= octr[key], key
+    assert st["kernel_launches"] > st0["kernel_launches"]  # the CTA route launches the deferral kernel as well
 
 
 def test_index_image_round_trip(tmp_path):
