@@ -540,21 +540,19 @@ LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
     bool want = I.numChunks >= kLookupBlockMinChunks;
     if (env) want = atoi(env) != 0;
     if (!want) return P;
+    P.eCap = std::max(64, std::min(2048, env_int("DP_LOOKUP_ECAP", P.eCap)));  // measurements
     const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~4 KB of static shared memory
-    auto counter_words = [&](int gs) { return (size_t)(((((size_t)I.numChunks - 1) >> gs) + 1 + 1) / 2 + 3) / 4 * 4; };
+    auto counter_words = [&](int gs) { return (size_t)((((size_t)I.numChunks - 1) >> gs) + 1 + 3) / 4 * 4; };
     auto smem_bytes = [&](int gs) {
-        // counters | five uint32 arrays (+2 sentinels) | item list | exact recount table | one byte array
-        return (counter_words(gs) * 4 + (size_t)P.eCap * 20 + 8 + 2 * DP_BITEMS * 4 + (gs ? DP_BEXACT * 4 : 0) + P.eCap + 15) / 16 * 16;
+        // counters | dummy counters | five uint32 arrays (+2 sentinels) | item list | exact recount table | one byte array
+        return (counter_words(gs) * 4 + 128 + (size_t)P.eCap * 20 + 8 + 2 * DP_BITEMS * 4 + (gs ? DP_BEXACT * 4 : 0) + P.eCap + 15) / 16 * 16;
     };
-    // a counter covers 2^gShift adjacent chunks. 16-bit group counts stay exact while maxWindow * 2^gShift <= 65535 (a
-    // window strand has at most maxWindow included runs and a run holds each chunk once).
-    int maxShift = 0;
-    while (maxShift < 8 && ((long long)I.maxWindow << (maxShift + 1)) <= 65535) maxShift++;
-    // the smallest gShift whose counters take <= 40 KB keeps four CTAs per SM resident and the groups selective (a random
-    // group collects ~4 * (chunks per seed / C) * 2^gShift of the threshold); beyond 16 chunks per group only when
-    // shared memory leaves no choice
+    // a 32-bit counter covers 2^gShift adjacent chunks. The smallest gShift whose counters take <= 40 KB keeps four CTAs
+    // per SM resident and the groups selective: a random group collects ~4 * (chunks per seed / C) * 2^gShift of the
+    // threshold, ~1/6 at 16 chunks per group on the synthetic genomes; more only when shared memory leaves no choice
+    const int maxShift = 10;
     int gs = 0;
-    while (gs < maxShift && gs < 4 && counter_words(gs) * 4 > 40 * 1024) gs++;
+    while (gs < 5 && counter_words(gs) * 4 > 20 * 1024) gs++;
     while (gs < maxShift && smem_bytes(gs) > maxSmem) gs++;
     if (getenv("DP_LOOKUP_GSHIFT")) gs = std::min(maxShift, std::max(0, env_int("DP_LOOKUP_GSHIFT", 0)));  // tests
     if (smem_bytes(gs) > maxSmem) throw std::runtime_error("reference has too many chunks for the lookup kernel's shared-memory counters");
@@ -564,7 +562,8 @@ LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
     P.gListCap = std::min(DP_BGLIST, std::max(1, env_int("DP_LOOKUP_GLIST", DP_BGLIST)));                // tests
     P.gBatch = std::min(DP_BEXACT >> gs, std::max(1, env_int("DP_LOOKUP_GBATCH", DP_BEXACT >> gs)));   // tests
     size_t fit = (227 * 1024) / (P.smem + 5 * 1024);
-    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 4));  // 64 registers x 256 threads: four CTAs per SM
+    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 4));
+    P.ctasPerSm = std::max(1, std::min(P.ctasPerSm, env_int("DP_LOOKUP_CTAS", 4)));                     // measurements
     P.use = true;
     return P;
 }
@@ -696,7 +695,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CK(cudaFuncSetAttribute(dp_lookup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             M.attrsSet = true;
         }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
@@ -739,8 +738,10 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             int ctas = LP.ctasPerSm;
             if (W.curAsciiIsHost && ctas > 1) ctas -= ctas / 4 ? ctas / 4 : 0;  // headroom for the pull kernel
             int blocks = (int)std::min<size_t>(2 * nWin, (size_t)M.smCount * ctas);
-            dp_lookup_block_kernel<<<blocks, DP_BTHREADS, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
-                                                                       W.candDistinct.p, W.candStride, W.dCtr.p);
+            // 256 threads, four CTAs per SM (64 registers), six 16-byte loads per lane in flight: measured best of
+            // {128, 256} threads x {2..6} CTAs x {4, 6, 8} items on a 1 Gb reference
+            dp_lookup_block_kernel<256, 4, 6><<<blocks, 256, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
+                                                                           W.candDistinct.p, W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
             // window strands the CTA kernel deferred (a seed present in every chunk): none on real references
             int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 2);

@@ -303,6 +303,7 @@ struct DpRefineCtx {
     unsigned short* order;        // [nInc] scratch of the Q6 column-order simulation
     int nInc, minCount, T;
     bool clamped, q6;
+    bool dupInCount;  // bits 16-31 of a candidate's count word = the repeated-seed runs containing it (no search needed)
     int nAllDistinct;
 };
 
@@ -393,7 +394,9 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
             todo2 &= todo2 - 1;
             unsigned cc = __shfl_sync(DP_FULL, c, l);
             int distinct;
-            if (X.nDup >= 0) {
+            if (X.dupInCount) {
+                distinct = __shfl_sync(DP_FULL, soft - (int)(v >> 16), l);
+            } else if (X.nDup >= 0) {
                 int rep = 0;
                 for (int d0 = 0; d0 < X.nDup; d0 += 32) {
                     int d = d0 + (int)lane;
@@ -688,6 +691,7 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
                 X.T = T;
                 X.clamped = clamped;
                 X.q6 = q6;
+                X.dupInCount = false;
                 X.nAllDistinct = nAllDistinct;
                 nCandOut = dp_refine_emit(I, X, sorted, nCand, outChunk, outDist, candStride);
                 if (nCandOut > candStride) {
@@ -712,15 +716,15 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 //
 // With C chunks a warp-private set of counters costs 2C bytes; beyond a few thousand chunks that either leaves the SM
 // nearly empty or spills the counters to global memory, where every posting becomes a random read-modify-write.
-// Here a CTA of 256 threads owns ONE set of 16-bit counters in shared memory and all its warps stream the posting runs
+// Here a CTA of 256 threads owns ONE set of 32-bit counters in shared memory and all its warps stream the posting runs
 // of one window strand into it. To keep several CTAs resident per SM at human-genome scale (10^5 chunks and more) the
 // counters are COARSE: counter g counts the postings of the 2^gShift adjacent chunks g*2^gShift ... (a group's count
 // is >= the count of each of its chunks, so every chunk over the threshold lies in a group over the threshold).
 //
 //   1. inclusion filter, thread per query seed, block-wide ordered compaction                 (seeds.go:340-346)
 //   2. the runs are cut into items of 128 postings aligned to 16 bytes; a warp takes four items at once, issues its
-//      four 16-byte loads per lane (2 KB per warp in flight), then adds into the group counters with shared-memory
-//      reductions (no return value, no per-posting test)
+//      four 16-byte loads per lane (2 KB per warp in flight), then adds into the group counters with predicated
+//      shared-memory reductions (no return value, no per-posting test or branch: ~6 instructions per posting)
 //   3. one pass over the counters finds the groups that reached the threshold and blanks the counters (16-byte
 //      loads/stores); with gShift = 0 these are the candidates and their exact counts
 //   4. gShift > 0: for the few groups over the threshold (the true locus; random groups stay far below it) every run
@@ -732,7 +736,6 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 // Window strands that contain a seed present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel
 // through a list.
 // ===============================================================================================================
-#define DP_BTHREADS 256 // threads per CTA
 #define DP_BSEG 128     // postings per gather item
 #define DP_BITEMS 512   // gather items listed in shared memory at a time
 #define DP_BCAND 256    // candidates over the threshold held in shared memory
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 
 struct DpLookupBlockCfg {
     int gShift;      // a counter covers 2^gShift adjacent chunks
-    int cntWords;    // 32-bit words of packed 16-bit counters (multiple of 4)
+    int cntWords;    // 32-bit group counters (multiple of 4)
     int eCap;        // included runs held in shared memory (more: global scratch)
     int gListCap;    // groups listed in shared memory before the list spills (<= DP_BGLIST; tests shrink it)
     int gBatch;      // groups recounted at a time (<= DP_BEXACT >> gShift; tests shrink it)
@@ -784,13 +787,22 @@ __device__ __forceinline__ unsigned dp_block_excl_scan(unsigned v, unsigned* wTo
     return base + x - v;
 }
 
-// one posting into the packed 16-bit group counters (shared-memory reduction, result unused)
-__device__ __forceinline__ void dp_group_count(unsigned* cnt, unsigned chunk, int gShift) {
-    const unsigned g = chunk >> gShift;
-    atomicAdd(cnt + (g >> 1), 1u << ((g & 1u) << 4));
+// 16 bytes of a posting run: streamed once, never reused by this SM (no L1 allocation)
+__device__ __forceinline__ uint4 dp_load_postings(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
-__global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+// one posting into the group counters: shared-memory reduction (no return value); a posting outside the item's range
+// goes to the lane's private dummy counter instead (no branch, no bank conflict among the dummies)
+__device__ __forceinline__ void dp_group_count(unsigned cntAddr, unsigned dummyAddr, unsigned chunk, int gShift, bool valid) {
+    const unsigned addr = valid ? cntAddr + ((chunk >> gShift) << 2) : dummyAddr;
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
+}
+
+template <int THREADS, int MINB, int NI>  // CTA size; resident CTAs per SM the register budget is cut for; items a warp has in flight
+__global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
                                                                          DpLookupScratch S, DpLookupBlockCfg G,
                                                                          int* __restrict__ candN,
                                                                          unsigned* __restrict__ candChunk,
@@ -806,9 +818,10 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
     const int warp = tid >> 5, nWarp = nT >> 5;
     const unsigned C = I.numChunks;
     const int gShift = G.gShift;
-    // dynamic shared memory: counters | eSeed | eOff | ePre | eItem | eEndW | item starts | item ranges | exact | eFirst
+    // dynamic shared memory: counters | 32 dummy counters | eSeed | eOff | ePre | eItem | eEndW | item starts |
+    // item ranges | exact | eFirst
     unsigned* cnt = dp_smem;
-    unsigned* smSeed = cnt + G.cntWords;
+    unsigned* smSeed = cnt + G.cntWords + 32;
     unsigned* smOff = smSeed + G.eCap;
     unsigned* smPre = smOff + G.eCap;
     unsigned* smItem = smPre + G.eCap + 1;
@@ -824,12 +837,15 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
     unsigned long long* gCand = S.cand + (size_t)blockIdx.x * 2 * S.tStride;
     unsigned* gGroup = reinterpret_cast<unsigned*>(gCand + S.tStride);  // (the sort space: free until the sort)
     const uint4* chunks4 = reinterpret_cast<const uint4*>(I.seedChunks);
+    const unsigned cntAddr = (unsigned)__cvta_generic_to_shared(cnt);
+    const unsigned dummyAddr = cntAddr + ((unsigned)G.cntWords + lane) * 4u;  // 32 words after the counters, never read
     unsigned long long cRuns = 0, cEntries = 0, cCand = 0;  // thread 0 only
+    unsigned nextWs = tid == 0 ? atomicAdd(G.work, 1u) : 0u;  // (the next one is fetched while this one is processed)
     __syncthreads();
 
     for (;;) {
         if (tid == 0) {
-            sh.ws = (int)atomicAdd(G.work, 1u);
+            sh.ws = (int)min(nextWs, 0x7fffffffu);
             sh.nCand = 0;
             sh.nDup = 0;
             sh.nCandOut = 0;
@@ -838,6 +854,7 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
         __syncthreads();
         const int ws = sh.ws;
         if (ws >= nWS) break;
+        if (tid == 0) nextWs = atomicAdd(G.work, 1u);
         const int n = Q.wsN[ws];
         const unsigned qb = Q.wsOff[ws];
         bool defer = false;
@@ -952,41 +969,35 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                     __syncthreads();
                     for (;;) {
                         unsigned it = 0;
-                        if (lane == 0) it = atomicAdd(&sh.nextItem, 4u);
+                        if (lane == 0) it = atomicAdd(&sh.nextItem, (unsigned)NI);
                         it = __shfl_sync(DP_FULL, it, 0);
                         if (it >= dN) break;
-                        uint4 v[4];
-                        unsigned rg[4];
+                        uint4 v[NI];
+                        unsigned rg[NI];
 #pragma unroll
-                        for (int d = 0; d < 4; d++) {
+                        for (int d = 0; d < NI; d++) {
                             const bool have = it + d < dN;
                             rg[d] = have ? smItemRange[it + d] : 0u;
                             const unsigned st4 = have ? smItemStart[it + d] : 0u;
                             v[d] = make_uint4(0, 0, 0, 0);
-                            if (4u * lane < (rg[d] >> 8)) v[d] = __ldg(chunks4 + st4 + lane);
+                            if (4u * lane < (rg[d] >> 8)) v[d] = dp_load_postings(chunks4 + st4 + lane);
                         }
 #pragma unroll
-                        for (int d = 0; d < 4; d++) {
-                            const unsigned lo = rg[d] & 0xffu, hi = rg[d] >> 8;
-                            const unsigned b = 4u * lane;
-                            if (lo == 0 && hi == DP_BSEG) {  // warp-uniform: an interior item
-                                dp_group_count(cnt, v[d].x, gShift);
-                                dp_group_count(cnt, v[d].y, gShift);
-                                dp_group_count(cnt, v[d].z, gShift);
-                                dp_group_count(cnt, v[d].w, gShift);
-                            } else if (hi) {
-                                if (b >= lo && b < hi) dp_group_count(cnt, v[d].x, gShift);
-                                if (b + 1 >= lo && b + 1 < hi) dp_group_count(cnt, v[d].y, gShift);
-                                if (b + 2 >= lo && b + 2 < hi) dp_group_count(cnt, v[d].z, gShift);
-                                if (b + 3 >= lo && b + 3 < hi) dp_group_count(cnt, v[d].w, gShift);
-                            }
+                        for (int d = 0; d < NI; d++) {
+                            if (!rg[d]) continue;  // (warp-uniform: fewer than four items were left)
+                            // posting 4*lane+e of the item counts iff lo <= 4*lane+e < hi (unsigned wrap-around compare)
+                            const unsigned lo = rg[d] & 0xffu, span = (rg[d] >> 8) - lo;
+                            const unsigned bl = 4u * lane - lo;
+                            dp_group_count(cntAddr, dummyAddr, v[d].x, gShift, bl < span);
+                            dp_group_count(cntAddr, dummyAddr, v[d].y, gShift, bl + 1u < span);
+                            dp_group_count(cntAddr, dummyAddr, v[d].z, gShift, bl + 2u < span);
+                            dp_group_count(cntAddr, dummyAddr, v[d].w, gShift, bl + 3u < span);
                         }
                     }
                     __syncthreads();
                 }
                 // ---- counters over the threshold; blank the counters ----
                 {
-                    const unsigned T2 = (unsigned)T | ((unsigned)T << 16);
                     uint4* cnt4 = reinterpret_cast<uint4*>(cnt);
                     for (int w4 = tid; w4 < (G.cntWords >> 2); w4 += nT) {
                         const uint4 x = cnt4[w4];
@@ -994,15 +1005,11 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                         const unsigned xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            unsigned m = __vcmpgeu2(xs[i], T2);
-                            while (m) {
-                                const unsigned half = (m & 0xffffu) ? 0u : 1u;
-                                m &= half ? 0x0000ffffu : 0xffff0000u;
-                                const unsigned g = ((unsigned)w4 * 4u + (unsigned)i) * 2u + half;
-                                const unsigned count = (xs[i] >> (half * 16u)) & 0xffffu;
+                            if ((int)xs[i] >= T) {
+                                const unsigned g = (unsigned)w4 * 4u + (unsigned)i;
                                 if (gShift == 0) {
                                     const int slot = atomicAdd(&sh.nCand, 1);
-                                    const unsigned long long e = ((unsigned long long)g << 32) | count;
+                                    const unsigned long long e = ((unsigned long long)g << 32) | xs[i];
                                     if (slot < DP_BCAND) shCand[slot] = e;
                                     else if (slot < S.tStride) gCand[slot] = e;
                                 } else {
@@ -1011,6 +1018,24 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                                     else gGroup[slot] = g;
                                 }
                             }
+                        }
+                    }
+                    __syncthreads();
+                }
+                // ---- runs that repeat an earlier run's seed (for the distinct counts) ----
+                if (gShift ? sh.nGroup > 0 : sh.nCand > 0) {
+                    for (int j = tid; j < nInc; j += nT) {
+                        const unsigned s = eSeed[j];
+                        bool first = true;
+                        for (int b = 0; b < j; b++)
+                            if (eSeed[b] == s) {
+                                first = false;
+                                break;
+                            }
+                        eFirst[j] = first ? 1 : 0;
+                        if (!first) {
+                            const int slot = atomicAdd(&sh.nDup, 1);
+                            if (slot < DP_BDUP) shDup[slot] = (unsigned short)j;
                         }
                     }
                     __syncthreads();
@@ -1029,6 +1054,7 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                             const unsigned g = gx < G.gListCap ? shGroup[gx] : gGroup[gx];
                             const unsigned cLo = g << gShift, cHi = cLo + gSize;
                             const unsigned off = eOff[j], len = ePre[j + 1] - ePre[j];
+                            const unsigned one = eFirst[j] ? 1u : 0x10001u;  // upper half: runs repeating an earlier seed
                             unsigned lo = 0, hi = len;
                             while (lo < hi) {
                                 const unsigned mid = (lo + hi) >> 1;
@@ -1038,13 +1064,13 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                             for (unsigned p = lo; p < len; p++) {
                                 const unsigned c = __ldg(I.seedChunks + off + p);
                                 if (c >= cHi) break;
-                                atomicAdd(exact + ((unsigned)gi << gShift) + (c - cLo), 1u);
+                                atomicAdd(exact + ((unsigned)gi << gShift) + (c - cLo), one);
                             }
                         }
                         __syncthreads();
                         for (int x = tid; x < (bn << gShift); x += nT) {
-                            const unsigned count = exact[x];
-                            if ((int)count >= T) {
+                            const unsigned count = exact[x];  // soft count | repeated-seed runs << 16
+                            if ((int)(count & 0xffffu) >= T) {
                                 const int gx = b0 + (x >> gShift);
                                 const unsigned g = gx < G.gListCap ? shGroup[gx] : gGroup[gx];
                                 const unsigned chunk = (g << gShift) + ((unsigned)x & (gSize - 1u));
@@ -1066,7 +1092,7 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                 if (nCand > 0) {
                     // ---- ascending chunk id (rank sort: chunk ids are distinct) ----
                     const unsigned long long* sorted = shCand;
-                    if (nCand <= DP_BCAND) {
+                    if (nCand <= DP_BCAND && nCand <= nT) {
                         unsigned long long e = 0;
                         int rank = 0;
                         if (tid < nCand) {
@@ -1087,22 +1113,6 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                         }
                         sorted = dst;
                     }
-                    // ---- runs that repeat an earlier run's seed (for the distinct counts) ----
-                    for (int j = tid; j < nInc; j += nT) {
-                        const unsigned s = eSeed[j];
-                        bool first = true;
-                        for (int b = 0; b < j; b++)
-                            if (eSeed[b] == s) {
-                                first = false;
-                                break;
-                            }
-                        eFirst[j] = first ? 1 : 0;
-                        if (!first) {
-                            const int slot = atomicAdd(&sh.nDup, 1);
-                            if (slot < DP_BDUP) shDup[slot] = (unsigned short)j;
-                        }
-                    }
-                    __syncthreads();
                     if (warp == 0) {
                         DpRefineCtx X;
                         X.eOff = eOff;
@@ -1117,6 +1127,7 @@ __global__ void __launch_bounds__(DP_BTHREADS, 4) dp_lookup_block_kernel(DpIndex
                         X.T = T;
                         X.clamped = clamped;
                         X.q6 = q6;
+                        X.dupInCount = gShift != 0;
                         X.nAllDistinct = 0;
                         int nOut = dp_refine_emit(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
                                                   candDistinct + (size_t)ws * candStride, candStride);
