@@ -201,8 +201,9 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def hbm_regime(dp, synth, device, peak, peak_src, gather_gbs, ref_len=1_000_000_000, n=20_000, L=15_000):
-    """dp_lookup_block_kernel on an index far larger than L2: posting bytes per second against the HBM peak."""
+def hbm_regime(dp, synth, device, peak, peak_src, gather_gbs, ref_len=3_100_000_000, n=20_000, L=15_000):
+    """dp_lookup_block_kernel on BASELINE config 4's human-scale reference (index far larger than L2): posting bytes per
+    second against the HBM peak."""
     import torch
     ref = synth.reference(4, ref_len)
     t0 = time.time()
@@ -415,8 +416,8 @@ def run_ours(args):
                                        args.index == "broadcast" else "built on every rank")),
             "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
 
-    # ---- the index-lookup kernel where it IS bound by HBM (rank 0, N=1): a 1 Gb reference (BASELINE config 4 shape at
-    #      a third of the size: 101k chunks, 180M postings, 4 GB index >> L2), 15 kb reads, single lane ----
+    # ---- the index-lookup kernel where it IS bound by HBM (rank 0, N=1): the 3.1 Gb reference of BASELINE config 4
+    #      (313k chunks, 677M postings, 15 GB index >> L2), 15 kb reads, single lane ----
     if rank == 0 and world == 1 and not args.no_hbm_regime:
         try:
             line["roofline_hbm_regime"] = hbm_regime(dp, synth, local, peak, peak_src, gather_gbs)
@@ -460,7 +461,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-hbm-regime", action="store_true", help="skip the 1 Gb-reference lookup measurement")
+    ap.add_argument("--no-hbm-regime", action="store_true", help="skip the lookup measurement on the 3.1 Gb reference (BASELINE config 4)")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
                     help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")
     args = ap.parse_args()

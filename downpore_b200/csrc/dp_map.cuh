@@ -321,7 +321,7 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
     const unsigned* eEndW = X.eEndW;
     unsigned short* order = X.order;
     int nCandOut = 0;
-    int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (lane 0 owns it)
+    int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (warp-uniform)
     bool simInit = false;
     for (int r0 = 0; r0 < nCand; r0 += 32) {
         const bool have = r0 + (int)lane < nCand;
@@ -348,31 +348,47 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
                     if (live < minCount) keep = false;
                 }
                 if (keep && q6 && sft == T) {
-                    // advance the drop simulation of bitset.go:332-353 to word `wword`
-                    if (lane == 0) {
-                        if (!simInit) {
-                            for (int j = 0; j < nInc; j++) order[j] = (unsigned short)j;
-                            unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
-                            for (int j = 0; j < nInc; j++) {
-                                unsigned len = ePre[j + 1] - ePre[j];
-                                unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
-                                if (s0 < st) st = s0;
-                            }
-                            simWord = (int)st - 1;
+                    // advance the drop simulation of bitset.go:332-353 to word `wword`. The reference visits every word i
+                    // and drops (swap with the last live set, in scan order) the sets whose last word is before i; nothing
+                    // happens at a word where no set ends, so only the words where a live set ends are visited
+                    if (!simInit) {
+                        for (int j = (int)lane; j < nInc; j += 32) order[j] = (unsigned short)j;
+                        unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
+                        for (int j = (int)lane; j < nInc; j += 32) {
+                            unsigned len = ePre[j + 1] - ePre[j];
+                            unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
+                            if (s0 < st) st = s0;
                         }
-                        for (int i = simWord + 1; i <= (int)wword; i++) {
-                            int t = 0;
-                            while (t < simLive) {
+                        for (int d = 16; d; d >>= 1) st = min(st, __shfl_xor_sync(DP_FULL, st, d));
+                        simWord = (int)st - 1;
+                        __syncwarp();
+                    }
+                    for (;;) {
+                        // the next word at which a live set is dropped: the smallest (last word + 1), but not before
+                        // simWord + 1 (sets that ended earlier are all dropped by the first pass)
+                        unsigned nxt = 0xffffffffu;
+                        for (int t = (int)lane; t < simLive; t += 32) nxt = min(nxt, eEndW[order[t]] + 1u);
+                        for (int d = 16; d; d >>= 1) nxt = min(nxt, __shfl_xor_sync(DP_FULL, nxt, d));
+                        if (nxt == 0xffffffffu) break;
+                        const int i = max((int)nxt, simWord + 1);
+                        if (i > (int)wword) break;
+                        if (lane == 0) {
+                            int t = 0, live = simLive;
+                            while (t < live) {
                                 if (eEndW[order[t]] + 1 <= (unsigned)i) {
-                                    order[t] = order[simLive - 1];
-                                    simLive--;
+                                    order[t] = order[live - 1];
+                                    live--;
                                 } else {
                                     t++;
                                 }
                             }
+                            simLive = live;
                         }
-                        if ((int)wword > simWord) simWord = (int)wword;
+                        simLive = __shfl_sync(DP_FULL, simLive, 0);
+                        simWord = i;
+                        __syncwarp();
                     }
+                    if ((int)wword > simWord) simWord = (int)wword;
                     simInit = true;
                     __syncwarp();
                     bool in = false;
