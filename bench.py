@@ -248,6 +248,32 @@ def hbm_regime(dp, synth, device, peak, peak_src, gather_gbs, ref_len=3_100_000_
                     "it really moves are achieved_actual_bytes (ncu dram bytes per launch in `traffic`)"}
 
 
+def bind_to_gpu_numa_node(local):
+    """The e2e path pulls the queried windows over PCIe out of this rank's pinned buffer: keep the rank's threads (and so
+    the pages they first touch) on the NUMA node its GPU hangs off. Returns (node, original affinity) or (None, None)."""
+    if os.environ.get("DP_BENCH_NUMA", "1") == "0":
+        return None, None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        before = os.sched_getaffinity(0)
+        mine = before & cpus
+        if len(mine) < 2 or mine == before:
+            return (node if mine == before else None), None
+        os.sched_setaffinity(0, mine)
+        return node, before
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     import torch
     rank, world, local = dist_setup(args.gpus)
@@ -255,6 +281,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa_node, affinity_before = bind_to_gpu_numa_node(local)
     import downpore_b200 as dp
     from tools import synth
 
@@ -400,7 +427,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": dt_dev / args.steps * 1e3,
             "wall_ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": config_dict(args, world),
+            "config": dict(config_dict(args, world), host_numa_node_rank0=numa_node),
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] + (n + 1) * 8),
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
                     "wall_ms_per_step": wall_e2e / args.steps * 1e3,
@@ -427,7 +454,9 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as po
-        cores = os.cpu_count() or 1
+        if affinity_before:
+            os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every core this process may use
+        cores = len(os.sched_getaffinity(0)) or 1
         om = po.Mapper(ref, vals, circular=True)
         ns = args.cpu_sample
         t0 = time.time()

@@ -97,6 +97,7 @@ double now_ms() {
 // (result assembly, the rare replay rounds) overlap the kernels of the next.
 struct Lane {
     cudaStream_t stream = nullptr;
+    cudaEvent_t evSync = nullptr;  // cudaEventBlockingSync: the lane's thread sleeps instead of spinning (sync_mode_blocking)
     DBuf<unsigned char> dAscii;
     DBuf<long long> dSeqOff, dWordOff, dWordsNeeded;
     DBuf<int> dReadLen;
@@ -148,6 +149,7 @@ struct Lane {
     ~Lane() {
         if (evReady) cudaEventDestroy(evReady);
         if (evPulled) cudaEventDestroy(evPulled);
+        if (evSync) cudaEventDestroy(evSync);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -847,6 +849,32 @@ void collect_stage_times(Lane& W) {  // call after a stream synchronize
     W.pendingStageTimes = false;
 }
 
+// How a lane's host thread waits for its stream. Spinning (the runtime's default with few contexts) answers fastest,
+// but lanes x ranks-per-node threads spinning on fewer cores starve each other and the Map() replay. DP_SYNC=spin|block
+// overrides; by default block when LOCAL_WORLD_SIZE (torchrun) x lanes exceeds the cores this process may run on.
+int lane_count();
+bool sync_mode_blocking() {
+    static const bool blocking = [] {
+        const char* e = getenv("DP_SYNC");
+        if (e && !strcmp(e, "spin")) return false;
+        if (e && !strcmp(e, "block")) return true;
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+        const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+        return (unsigned)(ranks * lane_count()) > cores;
+    }();
+    return blocking;
+}
+
+void lane_sync(Lane& W) {
+    if (sync_mode_blocking()) {
+        CK(cudaEventRecord(W.evSync, W.stream));
+        CK(cudaEventSynchronize(W.evSync));
+    } else {
+        CK(cudaStreamSynchronize(W.stream));
+    }
+}
+
 // Copies the window results of the last launch_windows() to the pinned host mirrors (hOutN, hOutOff, hOutMaps).
 void download_windows(Lane& W, size_t nWin) {
     cudaStream_t st = W.stream;
@@ -856,13 +884,13 @@ void download_windows(Lane& W, size_t nWin) {
     W.hOutOff.reserve(nWin);
     CK(cudaMemcpyAsync(W.hOutN.p, W.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hOutOff.p, W.outOff.p, nWin * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    lane_sync(W);
     collect_stage_times(W);
     size_t total = (size_t)cur[CUR_OUT];
     W.hOutMaps.reserve(total + 1);
     if (total) {
         CK(cudaMemcpyAsync(W.hOutMaps.p, W.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        lane_sync(W);
     }
     W.hOutTotal = total;
 }
@@ -1002,7 +1030,7 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     CK(cudaEventRecord(W.timers[T_FINISH].b, st));
     W.stats.kernel_launches += 2;
     W.stats.ms_host_logic += now_ms() - t0;
-    CK(cudaStreamSynchronize(st));
+    lane_sync(W);
     collect_stage_times(W);
     {
         float ms;
@@ -1150,6 +1178,7 @@ Lane& get_lane(dp_mapper& M, size_t idx) {
         CK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&L->evReady, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&L->evPulled, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&L->evSync, cudaEventDisableTiming | cudaEventBlockingSync));
         L->timers.resize(T_N);
         for (auto& t : L->timers) t.init();
         M.lanes.push_back(std::move(L));
@@ -1267,7 +1296,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                 }
                 map_subbatch(M, W, dA, offsets, r0, r1, counts.data(), subs[sI]);
             }
-            CK(cudaStreamSynchronize(W.stream));
+            lane_sync(W);
             fetch_counters(W);
         } catch (const std::exception& ex) {
             errs[(size_t)l] = ex.what();
