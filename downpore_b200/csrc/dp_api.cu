@@ -98,7 +98,7 @@ double now_ms() {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t evSync = nullptr;  // cudaEventBlockingSync: the lane's thread sleeps instead of spinning (sync_mode_blocking)
-    DBuf<unsigned char> dAscii;
+    DBuf<unsigned char> dAscii, dStage;
     DBuf<long long> dSeqOff, dWordOff, dWordsNeeded;
     DBuf<int> dReadLen;
     DBuf<unsigned> dWords;
@@ -656,13 +656,37 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         // compute kernels stay resident beside it
         int perSm = W.curAsciiIsHost ? 2 : 6;
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
-        if (W.curAsciiIsHost && bulkPull) {
+        const int stageStride = ((I.maxWindow + 15) / 16 + 3) * 16;  // the 16-byte blocks of the longest window
+        const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * stageStride <= 96 * 1024;
+        if (W.curAsciiIsHost && bulkPull && tmaPull) {
+            // the PCIe leg as TMA bulk copies into an HBM staging buffer (a few single-warp CTAs on the shared pull
+            // stream), then the pack from HBM at full width on the lane's own stream
+            W.dStage.reserve(nWin * (size_t)stageStride);
+            {
+                std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
+                CK(cudaEventRecord(W.evReady, st));
+                CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
+                CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
+                const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
+                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * stageStride, M.pullStream>>>(
+                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(W.evPulled, M.pullStream));
+            }
+            CK(cudaStreamWaitEvent(st, W.evPulled, 0));
+            int fullBlocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 6);
+            dp_pack_windows_kernel<<<fullBlocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+                                                               const_cast<unsigned*>(dWords), W.dStage.p, stageStride);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_PACK].b, st));
+            W.stats.kernel_launches += 1;
+        } else if (W.curAsciiIsHost && bulkPull) {
             std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
             CK(cudaEventRecord(W.evReady, st));
             CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
             CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
             dp_pack_windows_kernel<<<blocks, 256, 0, M.pullStream>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                                    const_cast<unsigned*>(dWords));
+                                                                    const_cast<unsigned*>(dWords), nullptr, 0);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, M.pullStream));
             CK(cudaEventRecord(W.evPulled, M.pullStream));
@@ -670,7 +694,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         } else {
             CK(cudaEventRecord(W.timers[T_PACK].a, st));
             dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                           const_cast<unsigned*>(dWords));
+                                                           const_cast<unsigned*>(dWords), nullptr, 0);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, st));
         }
@@ -696,6 +720,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         size_t smem = fWords * sizeof(unsigned) + perWarp * warpsPerBlock;
         if (!M.attrsSet) {
             CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             M.attrsSet = true;

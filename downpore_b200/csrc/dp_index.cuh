@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
                                                               const long long* __restrict__ seqOff,
                                                               const long long* __restrict__ wordOff,
                                                               const DpWindow* __restrict__ wins, int nWin,
-                                                              unsigned* __restrict__ words) {
+                                                              unsigned* __restrict__ words,
+                                                              const unsigned char* __restrict__ stage, int stageStride) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nWarps = (gridDim.x * blockDim.x) >> 5;
     unsigned lane = dp_lane();
@@ -84,8 +85,10 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
         const unsigned long long addr = (unsigned long long)src;
         const unsigned mis = (unsigned)(addr & 15ull);
         const uint4* blk = (const uint4*)(src - mis);              // aligned block holding the first byte
+        // (staged: dp_pull_windows_kernel has copied exactly these blocks to slot w of the staging buffer)
+        if (stage) blk = (const uint4*)(stage + (size_t)w * (size_t)stageStride);
         const unsigned char* srcEnd = ascii + readBase + readLen;  // one past the last byte of the read
-        const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)blk)) >> 4;
+        const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)(src - mis))) >> 4;
         const unsigned q = mis >> 2, sh = (mis & 3) * 8;
         // three iterations per trip, all three block loads issued before the first is consumed: the pull is bound by
         // the latency of the link, so bytes in flight per warp are what buys bandwidth (a 1000-base window = one trip)
@@ -129,6 +132,112 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The PCIe leg of the windowed pack as a copy-engine-like kernel: the 16-byte blocks that dp_pack_windows_kernel reads
+// for window w are moved from the caller's pinned buffer (host memory mapped into the device address space) to slot w
+// of a staging buffer in HBM by TMA bulk copies — host -> shared memory (cp.async.bulk, completion on an mbarrier) ->
+// HBM (bulk store) — issued by ONE thread per CTA over a ring of shared-memory slots. A few dozen such CTAs saturate
+// the link (measured: 16 CTAs x 8 slots = 49.8 GB/s of 2 KB pieces, the same as 148 x 8 warps of LDG.128,
+// scripts/pcie_probe2.cu), so the SMs stay free for the compute kernels of the other lanes; the pack itself then runs
+// from HBM. The other 31 lanes of the warp only prepare the copy descriptors, 32 windows at a time.
+// ---------------------------------------------------------------------------------------------------------------
+#define DP_PULL_SLOTS 16   // ring slots per CTA
+#define DP_PULL_AHEAD 12   // loads in flight per CTA (the other slots are being stored)
+
+__global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char* __restrict__ ascii,
+                                                             const long long* __restrict__ seqOff,
+                                                             const DpWindow* __restrict__ wins, int nWin,
+                                                             unsigned char* __restrict__ stage, int stageStride) {
+    extern __shared__ __align__(128) unsigned char dp_pull_smem[];  // DP_PULL_SLOTS x stageStride
+    __shared__ __align__(8) unsigned long long bars[DP_PULL_SLOTS];
+    __shared__ unsigned long long dSrc[2][32];
+    __shared__ unsigned dBytes[2][32];
+    const unsigned lane = dp_lane();
+    const unsigned slot0 = (unsigned)__cvta_generic_to_shared(dp_pull_smem);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    if (lane == 0) {
+        for (int s = 0; s < DP_PULL_SLOTS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // this CTA's windows: a contiguous range (neighbouring windows are neighbours in host memory)
+    const int per = (nWin + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int wBeg = min(nWin, (int)blockIdx.x * per), wEnd = min(nWin, wBeg + per);
+    const int n = wEnd - wBeg;
+    // descriptors of windows [wBeg + 32c, wBeg + 32c + 32) into buffer c & 1
+    auto describe = [&](int c) {
+        const int w = wBeg + 32 * c + (int)lane;
+        unsigned long long src = 0;
+        unsigned bytes = 0;
+        if (w < wEnd) {
+            const DpWindow win = wins[w];
+            if (win.len > 0) {
+                const long long readBase = seqOff[win.read];
+                const long long readLen = seqOff[win.read + 1] - readBase;
+                const long long w0 = win.start >> 4;
+                long long w1 = ((long long)win.start + win.len - 1) >> 4;
+                if (w1 < ((readLen - 1) >> 4)) w1++;
+                const long long nWords = w1 - w0 + 1;
+                const unsigned char* s0 = ascii + readBase + w0 * 16;
+                const unsigned mis = (unsigned)((unsigned long long)s0 & 15ull);
+                const unsigned char* blk = s0 - mis;
+                const long long lastBlk = (long long)((unsigned long long)(ascii + readBase + readLen - 1) - (unsigned long long)blk) >> 4;
+                src = (unsigned long long)blk;
+                bytes = (unsigned)(min(lastBlk, nWords) + 1) * 16u;
+            }
+        }
+        dSrc[c & 1][lane] = src;
+        dBytes[c & 1][lane] = bytes;
+    };
+    const int nChunks = (n + 31) >> 5;
+    if (nChunks > 0) describe(0);
+    __syncwarp();
+    int issued = 0;           // lane 0: windows whose load has been issued
+    unsigned phaseBits = 0;   // lane 0: parity each slot's mbarrier completes next (windows without bytes skip a use)
+    for (int c = 0; c < nChunks; c++) {
+        if (c + 1 < nChunks) describe(c + 1);  // (chunk c+1's descriptors are ready before lane 0 needs them)
+        __syncwarp();
+        if (lane == 0) {
+            const int cEnd = min(n, 32 * (c + 1));
+            // the issue pointer runs DP_PULL_AHEAD windows ahead of the store pointer, but never past chunk c + 1
+            for (int i = 32 * c; i < cEnd; i++) {
+                const int lim = min(min(n, 32 * (c + 2)), i + DP_PULL_AHEAD);
+                while (issued < lim) {
+                    const int j = issued;
+                    const unsigned bytes = dBytes[(j >> 5) & 1][j & 31];
+                    if (bytes) {
+                        if (j >= DP_PULL_SLOTS)  // the store that last read this slot has finished reading it
+                            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DP_PULL_SLOTS - DP_PULL_AHEAD - 1) : "memory");
+                        const unsigned s = (unsigned)(j % DP_PULL_SLOTS);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(slot0 + s * (unsigned)stageStride), "l"(dSrc[(j >> 5) & 1][j & 31]), "r"(bytes), "r"(bar0 + 8u * s)
+                                     : "memory");
+                    }
+                    issued++;
+                }
+                const unsigned bytes = dBytes[(i >> 5) & 1][i & 31];
+                const unsigned s = (unsigned)(i % DP_PULL_SLOTS);
+                if (bytes) {
+                    const unsigned parity = (phaseBits >> s) & 1u;
+                    phaseBits ^= 1u << s;
+                    unsigned ok = 0;
+                    while (!ok)
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(ok) : "r"(bar0 + 8u * s), "r"(parity) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(stage + (size_t)(wBeg + i) * (size_t)stageStride), "r"(slot0 + s * (unsigned)stageStride), "r"(bytes)
+                                 : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per window, empty or not
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // packed words (16 bases, MSB first) -> the reference's byte layout (4 bases per byte, MSB first): byte i of the
