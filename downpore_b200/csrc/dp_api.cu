@@ -103,7 +103,7 @@ struct Lane {
     DBuf<int> dReadLen;
     DBuf<unsigned> dWords;
     DBuf<DpWindow> dWins;
-    DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff;
+    DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff, dStagePos;
     DBuf<int> wsN, qPos, candN, outN, dFinN;
     DBuf<unsigned short> candDistinct;
     DBuf<DpMappingDev> outMaps, dFinMaps;
@@ -651,32 +651,40 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     cudaStream_t st = W.stream;
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    if (!M.attrsSet) {
+        CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        M.attrsSet = true;
+    }
     {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
         // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
         // compute kernels stay resident beside it
         int perSm = W.curAsciiIsHost ? 2 : 6;
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         const int stageStride = ((I.maxWindow + 15) / 16 + 3) * 16;  // the 16-byte blocks of the longest window
-        const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * stageStride <= 96 * 1024;
+        const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * 2 * stageStride <= 96 * 1024;
         if (W.curAsciiIsHost && bulkPull && tmaPull) {
             // the PCIe leg as TMA bulk copies into an HBM staging buffer (a few single-warp CTAs on the shared pull
             // stream), then the pack from HBM at full width on the lane's own stream
-            W.dStage.reserve(nWin * (size_t)stageStride);
+            W.dStage.reserve((nWin + 1) * (size_t)stageStride);
+            W.dStagePos.reserve(nWin);
             {
                 std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
                 CK(cudaEventRecord(W.evReady, st));
                 CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
                 CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
-                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * stageStride, M.pullStream>>>(
-                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride);
+                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * stageStride, M.pullStream>>>(
+                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
             CK(cudaStreamWaitEvent(st, W.evPulled, 0));
             int fullBlocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 6);
             dp_pack_windows_kernel<<<fullBlocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                               const_cast<unsigned*>(dWords), W.dStage.p, stageStride);
+                                                               const_cast<unsigned*>(dWords), W.dStage.p, W.dStagePos.p);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, st));
             W.stats.kernel_launches += 1;
@@ -686,7 +694,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
             CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
             dp_pack_windows_kernel<<<blocks, 256, 0, M.pullStream>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                                    const_cast<unsigned*>(dWords), nullptr, 0);
+                                                                    const_cast<unsigned*>(dWords), nullptr, nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, M.pullStream));
             CK(cudaEventRecord(W.evPulled, M.pullStream));
@@ -694,7 +702,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         } else {
             CK(cudaEventRecord(W.timers[T_PACK].a, st));
             dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
-                                                           const_cast<unsigned*>(dWords), nullptr, 0);
+                                                           const_cast<unsigned*>(dWords), nullptr, nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, st));
         }
@@ -718,13 +726,6 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         if (perWarp * warpsPerBlock > room) warpsPerBlock = (int)std::max<size_t>(1, room / perWarp);  // very long windows
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount);
         size_t smem = fWords * sizeof(unsigned) + perWarp * warpsPerBlock;
-        if (!M.attrsSet) {
-            CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            M.attrsSet = true;
-        }
         if (smem > 200 * 1024) throw std::runtime_error("query_size too large for the extract kernel's shared memory");
         CK(cudaEventRecord(W.timers[T_EXTRACT].a, st));
         dp_extract_kernel<<<blocks, 32 * warpsPerBlock, smem, st>>>(I, dWords, dWordOff, W.dWins.p, (int)nWin, Q, maskWords,

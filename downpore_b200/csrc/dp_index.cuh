@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
                                                               const long long* __restrict__ wordOff,
                                                               const DpWindow* __restrict__ wins, int nWin,
                                                               unsigned* __restrict__ words,
-                                                              const unsigned char* __restrict__ stage, int stageStride) {
+                                                              const unsigned char* __restrict__ stage,
+                                                              const unsigned* __restrict__ stagePos) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nWarps = (gridDim.x * blockDim.x) >> 5;
     unsigned lane = dp_lane();
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
         const unsigned long long addr = (unsigned long long)src;
         const unsigned mis = (unsigned)(addr & 15ull);
         const uint4* blk = (const uint4*)(src - mis);              // aligned block holding the first byte
-        // (staged: dp_pull_windows_kernel has copied exactly these blocks to slot w of the staging buffer)
-        if (stage) blk = (const uint4*)(stage + (size_t)w * (size_t)stageStride);
+        // (staged: dp_pull_windows_kernel has copied these blocks to stage + 16 * stagePos[w])
+        if (stage) blk = (const uint4*)stage + stagePos[w];
         const unsigned char* srcEnd = ascii + readBase + readLen;  // one past the last byte of the read
         const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)(src - mis))) >> 4;
         const unsigned q = mis >> 2, sh = (mis & 3) * 8;
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
 __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char* __restrict__ ascii,
                                                              const long long* __restrict__ seqOff,
                                                              const DpWindow* __restrict__ wins, int nWin,
-                                                             unsigned char* __restrict__ stage, int stageStride) {
-    extern __shared__ __align__(128) unsigned char dp_pull_smem[];  // DP_PULL_SLOTS x stageStride
+                                                             unsigned char* __restrict__ stage, int stageStride,
+                                                             unsigned* __restrict__ stagePos) {
+    extern __shared__ __align__(128) unsigned char dp_pull_smem[];  // DP_PULL_SLOTS x 2 * stageStride
     __shared__ __align__(8) unsigned long long bars[DP_PULL_SLOTS];
     __shared__ unsigned long long dSrc[2][32];
     __shared__ unsigned dBytes[2][32];
@@ -188,6 +190,24 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                 bytes = (unsigned)(min(lastBlk, nWords) + 1) * 16u;
             }
         }
+        // A window that starts where its predecessor ends (the tail window of one read and the head window of the
+        // next are neighbours in the caller's buffer) rides in the predecessor's copy: half as many, twice as long
+        // PCIe reads. Pairs only: a follower's predecessor is never a follower itself.
+        const unsigned long long pSrc = __shfl_up_sync(DP_FULL, src, 1);
+        const unsigned pBytes = __shfl_up_sync(DP_FULL, bytes, 1);
+        bool adj = lane > 0 && bytes && pBytes && src >= pSrc && src <= pSrc + pBytes + 64ull &&
+                   (src - pSrc) + bytes <= 2ull * (unsigned long long)stageStride;
+        const bool pAdj = __shfl_up_sync(DP_FULL, adj, 1);
+        const bool follower = adj && !(lane > 1 && pAdj);
+        const unsigned long long nSrc = __shfl_down_sync(DP_FULL, src, 1);
+        const unsigned nBytes = __shfl_down_sync(DP_FULL, bytes, 1);
+        const bool nFollower = __shfl_down_sync(DP_FULL, follower, 1) && lane < 31;
+        if (w < wEnd) {
+            const unsigned long long base = (unsigned long long)w * (unsigned)(stageStride >> 4);  // in 16-byte blocks
+            stagePos[w] = (unsigned)(follower ? base - (unsigned)(stageStride >> 4) + ((src - pSrc) >> 4) : base);
+        }
+        if (nFollower) bytes = (unsigned)(nSrc - src) + nBytes;  // leader: one copy covers both windows
+        if (follower) bytes = 0;
         dSrc[c & 1][lane] = src;
         dBytes[c & 1][lane] = bytes;
     };
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                         const unsigned s = (unsigned)(j % DP_PULL_SLOTS);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(bytes) : "memory");
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(slot0 + s * (unsigned)stageStride), "l"(dSrc[(j >> 5) & 1][j & 31]), "r"(bytes), "r"(bar0 + 8u * s)
+                                     ::"r"(slot0 + s * 2u * (unsigned)stageStride), "l"(dSrc[(j >> 5) & 1][j & 31]), "r"(bytes), "r"(bar0 + 8u * s)
                                      : "memory");
                     }
                     issued++;
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                                      : "=r"(ok) : "r"(bar0 + 8u * s), "r"(parity) : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(stage + (size_t)(wBeg + i) * (size_t)stageStride), "r"(slot0 + s * (unsigned)stageStride), "r"(bytes)
+                                 ::"l"(stage + (size_t)(wBeg + i) * (size_t)stageStride), "r"(slot0 + s * 2u * (unsigned)stageStride), "r"(bytes)
                                  : "memory");
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per window, empty or not

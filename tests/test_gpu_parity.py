@@ -157,6 +157,26 @@ def test_device_resident_entry_point_and_idempotence(pair):
     assert np.array_equal(rows_of(host_maps), np.concatenate([rows_of(a_maps), rows_of(b_maps)]))
 
 
+@pytest.mark.parametrize("env", [{}, {"DP_PULL_CTAS": "3"}, {"DP_PULL_TMA": "0"}])
+def test_pinned_host_reads_on_mixed_reads(pair, env):
+    """dp_mapper_map_batch on page-locked reads: only the queried windows cross the link, as TMA bulk copies into an HBM
+    staging buffer (neighbouring windows of consecutive reads share one copy) or, DP_PULL_TMA=0, as zero-copy loads.
+    Ragged, short (whole-read windows, len % 4 == 0) and chimeric reads, shifted by one byte so that no read starts
+    on a 16-byte boundary by construction."""
+    import torch
+    ref, circular, om, gm = pair
+    reads = mixed_reads(ref, circular, seed=41, n=333, rl=4999)
+    bases = np.concatenate([np.frombuffer(b"A", dtype=np.uint8)] + reads)
+    offs = (np.concatenate([[0], np.cumsum([len(r) for r in reads])]) + 1).astype(np.int64)
+    orow, ooff, _ = om.map_batch(bases[1:], offs - 1, threads=4)
+    pinned = torch.from_numpy(bases).pin_memory()
+    with _Env(env):
+        maps, off = gm.map_batch_ptr(pinned.data_ptr(), offs)
+        st = gm.stats()
+    assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow)
+    assert 0 < st["h2d_bytes"] < len(bases)  # windows only
+
+
 def test_other_parameters():
     """k, seed_rate, query_size and chunk_size other than the defaults (commands/map.go:19-21)."""
     ref = synth.reference(8, 400_000)
