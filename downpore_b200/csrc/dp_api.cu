@@ -103,7 +103,7 @@ struct Lane {
     DBuf<int> dReadLen;
     DBuf<unsigned> dWords;
     DBuf<DpWindow> dWins;
-    DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff, dStagePos;
+    DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff, dStagePos, dPullWork;
     DBuf<int> wsN, qPos, candN, outN, dFinN;
     DBuf<unsigned short> candDistinct;
     DBuf<DpMappingDev> outMaps, dFinMaps;
@@ -651,6 +651,9 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     cudaStream_t st = W.stream;
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    // compute kernels leave part of every SM free while another lane's pull kernel reads host memory (measured with
+    // the zero-copy pack kernel; DP_HEADROOM=0/1 overrides)
+    const bool headroom = W.curAsciiIsHost && env_int("DP_HEADROOM", 1) != 0;
     if (!M.attrsSet) {
         CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -670,14 +673,16 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             // stream), then the pack from HBM at full width on the lane's own stream
             W.dStage.reserve((nWin + 1) * (size_t)stageStride);
             W.dStagePos.reserve(nWin);
+            W.dPullWork.reserve(1);
             {
                 std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
                 CK(cudaEventRecord(W.evReady, st));
                 CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
                 CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
+                CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
                 dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * stageStride, M.pullStream>>>(
-                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p);
+                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p, W.dPullWork.p);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
@@ -719,7 +724,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     {
         // one persistent CTA per SM. When the other lane may be pulling reads over PCIe, every compute kernel leaves
         // a quarter of the SM's registers and thread slots free so that the pull kernel stays resident beside it.
-        int warpsPerBlock = W.curAsciiIsHost ? 20 : 32;
+        int warpsPerBlock = headroom ? 20 : 32;
         const size_t fWords = I.filterBits ? ((((size_t)1 << I.filterBits) + 31) / 32 + 3) / 4 * 4 : 0;
         const size_t perWarp = (size_t)2 * maskWords * sizeof(unsigned);
         const size_t room = 200 * 1024 - fWords * sizeof(unsigned);
@@ -764,7 +769,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             G.nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
             CK(cudaMemsetAsync(W.lbWork.p, 0, 4 * sizeof(unsigned), st));
             int ctas = LP.ctasPerSm;
-            if (W.curAsciiIsHost && ctas > 1) ctas -= ctas / 4 ? ctas / 4 : 0;  // headroom for the pull kernel
+            if (headroom && ctas > 1) ctas -= ctas / 4 ? ctas / 4 : 0;  // headroom for the pull kernel
             int blocks = (int)std::min<size_t>(2 * nWin, (size_t)M.smCount * ctas);
             // 256 threads, four CTAs per SM (64 registers), six 16-byte loads per lane in flight: measured best of
             // {128, 256} threads x {2..6} CTAs x {4, 6, 8} items on a 1 Gb reference
@@ -780,7 +785,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             W.stats.kernel_launches += 1;
         } else {
             int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
-                                               (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
+                                               (size_t)M.smCount * (headroom ? 6 : 8));
             dp_lookup_kernel<<<blocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), nullptr, nullptr, S, inSmem,
                                                                    W.candN.p, W.candChunk.p, W.candDistinct.p,
                                                                    W.candStride, W.dCtr.p);
@@ -808,7 +813,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.resultCap = M.resultCap;
         int warpsPerBlock = 4;
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock,
-                                           (size_t)M.smCount * (W.curAsciiIsHost ? 4 : 6));
+                                           (size_t)M.smCount * (headroom ? 4 : 6));
         const unsigned long long outCap = (unsigned long long)nWin * M.outStride;
         const bool fast = !(getenv("DP_CHAIN_FAST") && atoi(getenv("DP_CHAIN_FAST")) == 0);
         CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
@@ -825,7 +830,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             F.slowList = W.fcSlowList.p;
             F.nSlow = reinterpret_cast<int*>(W.fcCursors.p + 2);
             CK(cudaMemsetAsync(W.fcCursors.p, 0, 4 * sizeof(unsigned long long), st));
-            int rBlocks = (int)std::min<size_t>((nWin + 3) / 4, (size_t)M.smCount * (W.curAsciiIsHost ? 6 : 8));
+            int rBlocks = (int)std::min<size_t>((nWin + 3) / 4, (size_t)M.smCount * (headroom ? 6 : 8));
             dp_reduce_kernel<<<rBlocks, 128, 0, st>>>(I, W.dWins.p, (int)nWin, Q, W.candN.p, W.candChunk.p,
                                                       W.candDistinct.p, W.candStride, S, F);
             CK(cudaGetLastError());

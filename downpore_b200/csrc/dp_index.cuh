@@ -151,11 +151,12 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                                                              const long long* __restrict__ seqOff,
                                                              const DpWindow* __restrict__ wins, int nWin,
                                                              unsigned char* __restrict__ stage, int stageStride,
-                                                             unsigned* __restrict__ stagePos) {
+                                                             unsigned* __restrict__ stagePos, unsigned* __restrict__ work) {
     extern __shared__ __align__(128) unsigned char dp_pull_smem[];  // DP_PULL_SLOTS x 2 * stageStride
     __shared__ __align__(8) unsigned long long bars[DP_PULL_SLOTS];
     __shared__ unsigned long long dSrc[2][32];
     __shared__ unsigned dBytes[2][32];
+    __shared__ unsigned dDst[2][32];  // destination in the staging buffer, in 16-byte blocks
     const unsigned lane = dp_lane();
     const unsigned slot0 = (unsigned)__cvta_generic_to_shared(dp_pull_smem);
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
@@ -164,16 +165,20 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    // this CTA's windows: a contiguous range (neighbouring windows are neighbours in host memory)
-    const int per = (nWin + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int wBeg = min(nWin, (int)blockIdx.x * per), wEnd = min(nWin, wBeg + per);
-    const int n = wEnd - wBeg;
-    // descriptors of windows [wBeg + 32c, wBeg + 32c + 32) into buffer c & 1
-    auto describe = [&](int c) {
-        const int w = wBeg + 32 * c + (int)lane;
+    // Work is handed out in chunks of 32 consecutive windows through a counter (`work`, zero at launch): the CTAs share
+    // their SMs with the compute kernels of the other lanes and run at different speeds.
+    const unsigned nChunks = ((unsigned)nWin + 31u) >> 5;
+    auto grab = [&]() {
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(work, 1u);
+        return __shfl_sync(DP_FULL, c, 0);
+    };
+    // copy descriptors of the windows of chunk c into buffer `buf`
+    auto describe = [&](unsigned c, int buf) {
+        const int w = (int)(32u * c + lane);
         unsigned long long src = 0;
         unsigned bytes = 0;
-        if (w < wEnd) {
+        if (w < nWin) {
             const DpWindow win = wins[w];
             if (win.len > 0) {
                 const long long readBase = seqOff[win.read];
@@ -195,35 +200,36 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
         // PCIe reads. Pairs only: a follower's predecessor is never a follower itself.
         const unsigned long long pSrc = __shfl_up_sync(DP_FULL, src, 1);
         const unsigned pBytes = __shfl_up_sync(DP_FULL, bytes, 1);
-        bool adj = lane > 0 && bytes && pBytes && src >= pSrc && src <= pSrc + pBytes + 64ull &&
-                   (src - pSrc) + bytes <= 2ull * (unsigned long long)stageStride;
+        const bool adj = lane > 0 && bytes && pBytes && src >= pSrc && src <= pSrc + pBytes + 64ull &&
+                         (src - pSrc) + bytes <= 2ull * (unsigned long long)stageStride;
         const bool pAdj = __shfl_up_sync(DP_FULL, adj, 1);
-        const bool follower = adj && !(lane > 1 && pAdj);
+        const bool follower = adj && !pAdj;
         const unsigned long long nSrc = __shfl_down_sync(DP_FULL, src, 1);
         const unsigned nBytes = __shfl_down_sync(DP_FULL, bytes, 1);
         const bool nFollower = __shfl_down_sync(DP_FULL, follower, 1) && lane < 31;
-        if (w < wEnd) {
-            const unsigned long long base = (unsigned long long)w * (unsigned)(stageStride >> 4);  // in 16-byte blocks
-            stagePos[w] = (unsigned)(follower ? base - (unsigned)(stageStride >> 4) + ((src - pSrc) >> 4) : base);
-        }
+        const unsigned base = (unsigned)w * (unsigned)(stageStride >> 4);  // in 16-byte blocks
+        const unsigned dst = follower ? base - (unsigned)(stageStride >> 4) + (unsigned)((src - pSrc) >> 4) : base;
+        if (w < nWin) stagePos[w] = dst;
         if (nFollower) bytes = (unsigned)(nSrc - src) + nBytes;  // leader: one copy covers both windows
         if (follower) bytes = 0;
-        dSrc[c & 1][lane] = src;
-        dBytes[c & 1][lane] = bytes;
+        dSrc[buf][lane] = src;
+        dBytes[buf][lane] = bytes;
+        dDst[buf][lane] = dst;
     };
-    const int nChunks = (n + 31) >> 5;
-    if (nChunks > 0) describe(0);
-    __syncwarp();
+    // lane 0 numbers the windows it handles 0, 1, 2, ... (32 per chunk taken, bytes = 0 where there is nothing to copy);
+    // window i uses ring slot i % DP_PULL_SLOTS and descriptor buffer (i / 32) & 1
     int issued = 0;           // lane 0: windows whose load has been issued
     unsigned phaseBits = 0;   // lane 0: parity each slot's mbarrier completes next (windows without bytes skip a use)
-    for (int c = 0; c < nChunks; c++) {
-        if (c + 1 < nChunks) describe(c + 1);  // (chunk c+1's descriptors are ready before lane 0 needs them)
+    unsigned cur = grab();
+    if (cur < nChunks) describe(cur, 0);
+    for (int k = 0; cur < nChunks; k++) {
+        const unsigned nxt = grab();
+        if (nxt < nChunks) describe(nxt, (k + 1) & 1);  // (ready before lane 0 runs ahead into it)
         __syncwarp();
         if (lane == 0) {
-            const int cEnd = min(n, 32 * (c + 1));
-            // the issue pointer runs DP_PULL_AHEAD windows ahead of the store pointer, but never past chunk c + 1
-            for (int i = 32 * c; i < cEnd; i++) {
-                const int lim = min(min(n, 32 * (c + 2)), i + DP_PULL_AHEAD);
+            const int ahead = nxt < nChunks ? 32 * (k + 2) : 32 * (k + 1);
+            for (int i = 32 * k; i < 32 * (k + 1); i++) {
+                const int lim = min(ahead, i + DP_PULL_AHEAD);
                 while (issued < lim) {
                     const int j = issued;
                     const unsigned bytes = dBytes[(j >> 5) & 1][j & 31];
@@ -249,13 +255,14 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                                      : "=r"(ok) : "r"(bar0 + 8u * s), "r"(parity) : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(stage + (size_t)(wBeg + i) * (size_t)stageStride), "r"(slot0 + s * 2u * (unsigned)stageStride), "r"(bytes)
+                                 ::"l"(stage + (size_t)dDst[(i >> 5) & 1][i & 31] * 16u), "r"(slot0 + s * 2u * (unsigned)stageStride), "r"(bytes)
                                  : "memory");
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per window, empty or not
             }
         }
         __syncwarp();
+        cur = nxt;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
