@@ -527,7 +527,7 @@ size_t lookup_tstride(const DpIndexDev& I) { return std::max<size_t>(I.numChunks
 
 struct LookupBlockPlan {
     bool use = false;
-    int gShift = 0, cntWords = 0, eCap = 512, gListCap = DP_BGLIST, gBatch = DP_BEXACT, ctasPerSm = 1;
+    int gShift = 0, cntWords = 0, eCap = 512, gListCap = DP_BGLIST, gBatch = DP_BEXACT, ctasPerSm = 1, seg = 128, threads = 256, exactWords = DP_BEXACT;
     size_t smem = 0;
 };
 
@@ -536,36 +536,55 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-LookupBlockPlan plan_block_lookup(const DpIndexDev& I) {
+LookupBlockPlan plan_block_lookup(const DpIndexDev& I, double avgRun) {
     LookupBlockPlan P;
     const char* env = getenv("DP_LOOKUP_BLOCK");
     bool want = I.numChunks >= kLookupBlockMinChunks;
     if (env) want = atoi(env) != 0;
     if (!want) return P;
+    // what a window strand is expected to look like: seeds per strand, postings per strand
+    const double estSeeds = (double)(I.edge - I.k + 1) * (double)I.numSeeds / (double)(1ull << (2 * I.k));
+    const double estPostings = estSeeds * avgRun;
+    // runs of a few dozen postings (k = 13, or a few thousand chunks) would leave 128-posting items mostly empty
+    P.seg = avgRun < 64.0 ? 32 : 128;
+    if (getenv("DP_LOOKUP_SEG")) P.seg = env_int("DP_LOOKUP_SEG", 128) == 32 ? 32 : 128;  // tests
+    // A few thousand postings per window strand (BASELINE config 3) are streamed in a few microseconds; what bounds
+    // the kernel then is how many window strands an SM works on at once: 128-thread CTAs, eight per SM, with the
+    // shared-memory footprint cut to fit. Human-scale indexes (tens of thousands of postings per window strand) do
+    // better with 256 threads and four CTAs per SM (measured).
+    const bool small = P.seg == 32 && estPostings < 8192.0;
+    P.threads = small ? 128 : 256;
+    if (getenv("DP_LOOKUP_THREADS")) P.threads = P.seg == 32 && env_int("DP_LOOKUP_THREADS", 256) == 128 ? 128 : 256;  // tests
+    P.eCap = estSeeds * 2.0 <= 256.0 ? 256 : 512;
     P.eCap = std::max(64, std::min(2048, env_int("DP_LOOKUP_ECAP", P.eCap)));  // measurements
+    P.exactWords = P.threads == 128 ? DP_BEXACT / 2 : DP_BEXACT;
     const size_t maxSmem = 220 * 1024;  // of 227 KB per CTA; the kernel has ~4 KB of static shared memory
     auto counter_words = [&](int gs) { return (size_t)((((size_t)I.numChunks - 1) >> gs) + 1 + 3) / 4 * 4; };
     auto smem_bytes = [&](int gs) {
         // counters | dummy counters | five uint32 arrays (+2 sentinels) | item list | exact recount table | one byte array
-        return (counter_words(gs) * 4 + 128 + (size_t)P.eCap * 20 + 8 + 2 * DP_BITEMS * 4 + (gs ? DP_BEXACT * 4 : 0) + P.eCap + 15) / 16 * 16;
+        return (counter_words(gs) * 4 + 128 + (size_t)P.eCap * 20 + 8 + 2 * DP_BITEMS * 4 + (gs ? P.exactWords * 4 : 0) + P.eCap + 15) / 16 * 16;
     };
-    // a 32-bit counter covers 2^gShift adjacent chunks. The smallest gShift whose counters take <= 40 KB keeps four CTAs
-    // per SM resident and the groups selective: a random group collects ~4 * (chunks per seed / C) * 2^gShift of the
-    // threshold, ~1/6 at 16 chunks per group on the synthetic genomes; more only when shared memory leaves no choice
+    // a 32-bit counter covers 2^gShift adjacent chunks. The smallest gShift whose counters take <= 20 KB (8 KB for the
+    // small CTAs) keeps the CTAs resident and the groups selective: a random group collects
+    // ~4 * (chunks per seed / C) * 2^gShift of the threshold — ~1/3 at 32 chunks per group on the synthetic 3.1 Gb
+    // genome, past 64 the random groups start to cross it (measured: 5.3 ms -> 26 ms -> 580 ms at gShift 5, 6, 7 on
+    // 1 Gb); more than 32 chunks per group only when shared memory leaves no choice
     const int maxShift = 10;
+    const size_t target = (size_t)(P.threads == 128 ? 8 : 20) * 1024;
     int gs = 0;
-    while (gs < 5 && counter_words(gs) * 4 > 20 * 1024) gs++;
+    while (gs < 5 && counter_words(gs) * 4 > target) gs++;
     while (gs < maxShift && smem_bytes(gs) > maxSmem) gs++;
     if (getenv("DP_LOOKUP_GSHIFT")) gs = std::min(maxShift, std::max(0, env_int("DP_LOOKUP_GSHIFT", 0)));  // tests
     if (smem_bytes(gs) > maxSmem) throw std::runtime_error("reference has too many chunks for the lookup kernel's shared-memory counters");
     P.gShift = gs;
     P.cntWords = (int)counter_words(gs);
     P.smem = smem_bytes(gs);
-    P.gListCap = std::min(DP_BGLIST, std::max(1, env_int("DP_LOOKUP_GLIST", DP_BGLIST)));                // tests
-    P.gBatch = std::min(DP_BEXACT >> gs, std::max(1, env_int("DP_LOOKUP_GBATCH", DP_BEXACT >> gs)));   // tests
-    size_t fit = (227 * 1024) / (P.smem + 5 * 1024);
-    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, 4));
-    P.ctasPerSm = std::max(1, std::min(P.ctasPerSm, env_int("DP_LOOKUP_CTAS", 4)));                     // measurements
+    P.gListCap = std::min(DP_BGLIST, std::max(1, env_int("DP_LOOKUP_GLIST", DP_BGLIST)));                        // tests
+    P.gBatch = std::min(P.exactWords >> gs, std::max(1, env_int("DP_LOOKUP_GBATCH", P.exactWords >> gs)));     // tests
+    if (P.gBatch < 1) P.gBatch = 1;
+    size_t fit = (227 * 1024) / (P.smem + 5 * 1024);  // ~4 KB static + 1 KB the driver reserves per CTA
+    P.ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(fit, P.threads == 128 ? 8 : 4));  // 64 registers per thread
+    P.ctasPerSm = std::max(1, std::min(P.ctasPerSm, env_int("DP_LOOKUP_CTAS", 8)));           // measurements
     P.use = true;
     return P;
 }
@@ -590,7 +609,7 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     const int qStride = I.maxWindow + 8;
     W.extractWarps = M.smCount * 8 * 8;
     // lookup scratch is indexed by warp in dp_lookup_kernel and by CTA in dp_lookup_block_kernel (<= 8 per SM)
-    const LookupBlockPlan LP = plan_block_lookup(I);
+    const LookupBlockPlan LP = plan_block_lookup(I, (double)M.nSeedPostings / std::max(1u, I.numSeeds));
     W.lookupWarps = LP.use ? M.smCount * 4 * 2 : M.smCount * 4 * 8;
     W.lbDefer.reserve(2 * nWin);
     W.lbWork.reserve(4);
@@ -658,7 +677,9 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<128, 8, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         M.attrsSet = true;
     }
     {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
@@ -755,7 +776,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int inSmem = I.numChunks <= kLookupSmemChunks ? 1 : 0;
         int warpsPerBlock = DP_LWARPS;
         size_t smem = inSmem ? (size_t)warpsPerBlock * ((I.numChunks + 1) / 2) * sizeof(unsigned) : 0;
-        const LookupBlockPlan LP = plan_block_lookup(I);
+        const LookupBlockPlan LP = plan_block_lookup(I, (double)M.nSeedPostings / std::max(1u, I.numSeeds));
         CK(cudaEventRecord(W.timers[T_LOOKUP].a, st));
         if (LP.use) {
             DpLookupBlockCfg G;
@@ -764,6 +785,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             G.eCap = LP.eCap;
             G.gListCap = LP.gListCap;
             G.gBatch = LP.gBatch;
+            G.exactWords = LP.exactWords;
             G.work = W.lbWork.p;
             G.deferList = W.lbDefer.p;
             G.nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
@@ -773,8 +795,10 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             int blocks = (int)std::min<size_t>(2 * nWin, (size_t)M.smCount * ctas);
             // 256 threads, four CTAs per SM (64 registers), six 16-byte loads per lane in flight: measured best of
             // {128, 256} threads x {2..6} CTAs x {4, 6, 8} items on a 1 Gb reference
-            dp_lookup_block_kernel<256, 4, 6><<<blocks, 256, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p,
-                                                                           W.candDistinct.p, W.candStride, W.dCtr.p);
+            auto kern = LP.seg == 32 ? (LP.threads == 128 ? dp_lookup_block_kernel<128, 8, 6, 32> : dp_lookup_block_kernel<256, 4, 6, 32>)
+                                     : dp_lookup_block_kernel<256, 4, 6, 128>;
+            kern<<<blocks, LP.threads, LP.smem, st>>>(I, Q, (int)(2 * nWin), S, G, W.candN.p, W.candChunk.p, W.candDistinct.p,
+                                              W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
             // window strands the CTA kernel deferred (a seed present in every chunk): none on real references
             int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 2);

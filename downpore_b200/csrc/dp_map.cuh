@@ -752,7 +752,6 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 // Window strands that contain a seed present in EVERY chunk (tiny references only) are deferred to dp_lookup_kernel
 // through a list.
 // ===============================================================================================================
-#define DP_BSEG 128     // postings per gather item
 #define DP_BITEMS 512   // gather items listed in shared memory at a time
 #define DP_BCAND 256    // candidates over the threshold held in shared memory
 #define DP_BDUP 64      // repeated-seed runs listed per window strand
@@ -764,7 +763,8 @@ struct DpLookupBlockCfg {
     int cntWords;    // 32-bit group counters (multiple of 4)
     int eCap;        // included runs held in shared memory (more: global scratch)
     int gListCap;    // groups listed in shared memory before the list spills (<= DP_BGLIST; tests shrink it)
-    int gBatch;      // groups recounted at a time (<= DP_BEXACT >> gShift; tests shrink it)
+    int gBatch;      // groups recounted at a time (<= exactWords >> gShift; tests shrink it)
+    int exactWords;  // words of the exact recount table (<= DP_BEXACT)
     unsigned* work;  // dynamic work counter, zero at launch
     int* deferList;  // window strands left to dp_lookup_kernel
     int* nDefer;
@@ -817,7 +817,10 @@ __device__ __forceinline__ void dp_group_count(unsigned cntAddr, unsigned dummyA
     asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
 }
 
-template <int THREADS, int MINB, int NI>  // CTA size; resident CTAs per SM the register budget is cut for; items a warp has in flight
+// THREADS: CTA size; MINB: resident CTAs per SM the register budget is cut for; NI: 16-byte loads a lane has in flight;
+// SEG: postings per gather item — 128 (a warp per item) for long runs, 32 (8 lanes per item, four items per warp-wide
+// load) for indexes whose runs are a few dozen postings long, where 128-posting items would be mostly empty
+template <int THREADS, int MINB, int NI, int SEG>
 __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
                                                                          DpLookupScratch S, DpLookupBlockCfg G,
                                                                          int* __restrict__ candN,
@@ -845,7 +848,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
     unsigned* smItemStart = smEndW + G.eCap;
     unsigned* smItemRange = smItemStart + DP_BITEMS;
     unsigned* exact = smItemRange + DP_BITEMS;
-    unsigned char* smFirst = reinterpret_cast<unsigned char*>(exact + (gShift ? DP_BEXACT : 0));
+    unsigned char* smFirst = reinterpret_cast<unsigned char*>(exact + (gShift ? G.exactWords : 0));
     for (int i = tid; i < G.cntWords; i += nT) cnt[i] = 0;
     // global scratch of this CTA for oversized window strands
     const size_t so = (size_t)blockIdx.x * S.stride;
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
                     if (j < nInc) {
                         c = ePre[j];
                         const unsigned off = eOff[j];
-                        if (c) items = (off + c - (off & ~3u) + DP_BSEG - 1) / DP_BSEG;
+                        if (c) items = (off + c - (off & ~3u) + SEG - 1) / SEG;
                         if (clamped || q6) eEndW[j] = c ? (__ldg(I.seedChunks + off + c - 1) >> 6) : 0u;
                     }
                     unsigned tA, tB;
@@ -976,34 +979,38 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
                         const unsigned off = eOff[j], end = off + (ePre[j + 1] - ePre[j]);
                         const unsigned a = off & ~3u;
                         for (unsigned it = max(first, d0); it < min(last, d0 + dN); it++) {
-                            const unsigned st = a + (it - first) * DP_BSEG;
-                            const unsigned lo = max(off, st) - st, hi = min(end, st + DP_BSEG) - st;
+                            const unsigned st = a + (it - first) * SEG;
+                            const unsigned lo = max(off, st) - st, hi = min(end, st + SEG) - st;
                             smItemStart[it - d0] = st >> 2;
                             smItemRange[it - d0] = lo | (hi << 8);
                         }
                     }
                     __syncthreads();
+                    constexpr unsigned LPI = SEG / 4;   // lanes per item (16 bytes = 4 postings per lane)
+                    constexpr unsigned IPR = 32 / LPI;  // items per warp-wide load
+                    const unsigned sub = lane / LPI, ln = lane % LPI;
                     for (;;) {
                         unsigned it = 0;
-                        if (lane == 0) it = atomicAdd(&sh.nextItem, (unsigned)NI);
+                        if (lane == 0) it = atomicAdd(&sh.nextItem, (unsigned)NI * IPR);
                         it = __shfl_sync(DP_FULL, it, 0);
                         if (it >= dN) break;
                         uint4 v[NI];
                         unsigned rg[NI];
 #pragma unroll
                         for (int d = 0; d < NI; d++) {
-                            const bool have = it + d < dN;
-                            rg[d] = have ? smItemRange[it + d] : 0u;
-                            const unsigned st4 = have ? smItemStart[it + d] : 0u;
+                            const unsigned idx = it + (unsigned)d * IPR + sub;
+                            const bool have = idx < dN;
+                            rg[d] = have ? smItemRange[idx] : 0u;
+                            const unsigned st4 = have ? smItemStart[idx] : 0u;
                             v[d] = make_uint4(0, 0, 0, 0);
-                            if (4u * lane < (rg[d] >> 8)) v[d] = dp_load_postings(chunks4 + st4 + lane);
+                            if (4u * ln < (rg[d] >> 8)) v[d] = dp_load_postings(chunks4 + st4 + ln);
                         }
 #pragma unroll
                         for (int d = 0; d < NI; d++) {
-                            if (!rg[d]) continue;  // (warp-uniform: fewer than four items were left)
-                            // posting 4*lane+e of the item counts iff lo <= 4*lane+e < hi (unsigned wrap-around compare)
+                            if (IPR == 1 && !rg[d]) continue;  // (warp-uniform: fewer than NI items were left)
+                            // posting 4*ln+e of the item counts iff lo <= 4*ln+e < hi (unsigned wrap-around compare)
                             const unsigned lo = rg[d] & 0xffu, span = (rg[d] >> 8) - lo;
-                            const unsigned bl = 4u * lane - lo;
+                            const unsigned bl = 4u * ln - lo;
                             dp_group_count(cntAddr, dummyAddr, v[d].x, gShift, bl < span);
                             dp_group_count(cntAddr, dummyAddr, v[d].y, gShift, bl + 1u < span);
                             dp_group_count(cntAddr, dummyAddr, v[d].z, gShift, bl + 2u < span);

@@ -244,8 +244,9 @@ def large_ref():
 @pytest.mark.parametrize("env", [
     {},                                                        # warp per window strand, shared-memory counters
     {"DP_LOOKUP_SMEM_CHUNKS": "100"},                          # warp kernel, counters in global memory
-    {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one counter per chunk
-    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "3"},         # CTA kernel, a counter per 8 chunks + exact recount
+    {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one counter per chunk, 32-posting items
+    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_SEG": "128"},          # 128-posting items (indexes with long runs)
+    {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_SEG": "128", "DP_LOOKUP_GSHIFT": "3"},  # a counter per 8 chunks + exact recount
     {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "5", "DP_LOOKUP_GLIST": "2", "DP_LOOKUP_GBATCH": "3"},  # spilled group list
 ])
 def test_lookup_kernels_on_a_large_reference(large_ref, env):
@@ -265,7 +266,7 @@ def test_lookup_kernels_on_a_large_reference(large_ref, env):
         assert st[key] == octr[key], key
 
 
-@pytest.mark.parametrize("env", [{"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "1"},
+@pytest.mark.parametrize("env", [{"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "1", "DP_LOOKUP_SEG": "128"},
                                  {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "3", "DP_LOOKUP_GLIST": "1", "DP_LOOKUP_GBATCH": "1"}])
 def test_block_lookup_on_mixed_reads(env):
     """The CTA-per-window-strand lookup on a small circular reference with short, chimeric and whole-read windows
