@@ -28,9 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
-# profiles/r1d_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = chain_thread + finish) and
+# profiles/r1k_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = chain_thread + finish) and
 # profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of config 4)
-TRAFFIC_PER_LAUNCH = {"pack": 170.1e6, "extract": 50.7e6, "lookup": 41.1e6, "reduce": 94.4e6, "chain": 86.3e6,
+TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 50.8e6, "reduce": 95.8e6, "chain": 86.9e6,
                       "lookup_block": 56.87e9}
 
 K = 11

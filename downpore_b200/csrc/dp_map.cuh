@@ -301,17 +301,76 @@ struct DpRefineCtx {
     const unsigned short* dup;    // the runs that are NOT first occurrences (valid when 0 <= nDup)
     int nDup;                     // -1: too many to list, use eFirst
     unsigned short* order;        // [nInc] scratch of the Q6 column-order simulation
+    int* sim;                     // [2] shared memory: simulation state (word reached, live sets)
     int nInc, minCount, T;
     bool clamped, q6;
-    bool dupInCount;  // bits 16-31 of a candidate's count word = the repeated-seed runs containing it (no search needed)
     int nAllDistinct;
 };
+
+// Q6 column-order simulation: advances the drop simulation of bitset.go:332-353 to word `wword`. The reference visits
+// every word i and drops (swap with the last live set, in scan order) the sets whose last word is before i; nothing
+// happens at a word where no set ends, so only the words where a live set ends are visited. Warp-collective; the state
+// (simWord, simLive) is warp-uniform and persists over the candidates of one window strand (ascending words).
+__device__ __noinline__ void dp_q6_advance(const DpIndexDev& I, const DpRefineCtx& X, unsigned wword, bool simInit) {
+    const unsigned lane = dp_lane();
+    int simWord = X.sim[0], simLive = simInit ? X.sim[1] : X.nInc;
+    const int nInc = X.nInc;
+    const unsigned* eOff = X.eOff;
+    const unsigned* ePre = X.ePre;
+    const unsigned* eEndW = X.eEndW;
+    unsigned short* order = X.order;
+    if (!simInit) {
+        for (int j = (int)lane; j < nInc; j += 32) order[j] = (unsigned short)j;
+        unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
+        for (int j = (int)lane; j < nInc; j += 32) {
+            unsigned len = ePre[j + 1] - ePre[j];
+            unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
+            if (s0 < st) st = s0;
+        }
+        for (int d = 16; d; d >>= 1) st = min(st, __shfl_xor_sync(DP_FULL, st, d));
+        simWord = (int)st - 1;
+        __syncwarp();
+    }
+    for (;;) {
+        // the next word at which a live set is dropped: the smallest (last word + 1), but not before
+        // simWord + 1 (sets that ended earlier are all dropped by the first pass)
+        unsigned nxt = 0xffffffffu;
+        for (int t = (int)lane; t < simLive; t += 32) nxt = min(nxt, eEndW[order[t]] + 1u);
+        for (int d = 16; d; d >>= 1) nxt = min(nxt, __shfl_xor_sync(DP_FULL, nxt, d));
+        if (nxt == 0xffffffffu) break;
+        const int i = max((int)nxt, simWord + 1);
+        if (i > (int)wword) break;
+        if (lane == 0) {
+            int t = 0, live = simLive;
+            while (t < live) {
+                if (eEndW[order[t]] + 1 <= (unsigned)i) {
+                    order[t] = order[live - 1];
+                    live--;
+                } else {
+                    t++;
+                }
+            }
+            simLive = live;
+        }
+        simLive = __shfl_sync(DP_FULL, simLive, 0);
+        simWord = i;
+        __syncwarp();
+    }
+    if ((int)wword > simWord) simWord = (int)wword;
+    __syncwarp();
+    if (lane == 0) {
+        X.sim[0] = simWord;
+        X.sim[1] = simLive;
+    }
+    __syncwarp();
+}
 
 // Candidates over the count threshold, ascending by chunk id, as (chunk << 32 | soft count): applies the level clamp's
 // early stop (Q11) and the level-16 under-count (Q6), computes the DISTINCT query seeds present in each survivor
 // (IntSet.CountIntersectionTo's operand, mapping.go:520-523) and writes (chunk, distinct) pairs. Warp-collective;
 // returns the number of survivors (which may exceed candStride: the caller flags that).
-__device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const unsigned long long* sorted, int nCand,
+template <bool DUP_IN_COUNT>  // bits 16-31 of a candidate's count word = the repeated-seed runs containing it (no search)
+__device__ __forceinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCtx& X, const unsigned long long* sorted, int nCand,
                               unsigned* outChunk, unsigned short* outDist, int candStride) {
     const unsigned lane = dp_lane();
     const int nInc = X.nInc, minCount = X.minCount, T = X.T;
@@ -321,7 +380,6 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
     const unsigned* eEndW = X.eEndW;
     unsigned short* order = X.order;
     int nCandOut = 0;
-    int simWord = -1, simLive = nInc;  // Q6 column-order simulation state (warp-uniform)
     bool simInit = false;
     for (int r0 = 0; r0 < nCand; r0 += 32) {
         const bool have = r0 + (int)lane < nCand;
@@ -348,47 +406,7 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
                     if (live < minCount) keep = false;
                 }
                 if (keep && q6 && sft == T) {
-                    // advance the drop simulation of bitset.go:332-353 to word `wword`. The reference visits every word i
-                    // and drops (swap with the last live set, in scan order) the sets whose last word is before i; nothing
-                    // happens at a word where no set ends, so only the words where a live set ends are visited
-                    if (!simInit) {
-                        for (int j = (int)lane; j < nInc; j += 32) order[j] = (unsigned short)j;
-                        unsigned st = 0xffffffffu;  // min over sets of IntSet.start (1 if empty)
-                        for (int j = (int)lane; j < nInc; j += 32) {
-                            unsigned len = ePre[j + 1] - ePre[j];
-                            unsigned s0 = len ? (__ldg(I.seedChunks + eOff[j]) >> 6) : 1u;
-                            if (s0 < st) st = s0;
-                        }
-                        for (int d = 16; d; d >>= 1) st = min(st, __shfl_xor_sync(DP_FULL, st, d));
-                        simWord = (int)st - 1;
-                        __syncwarp();
-                    }
-                    for (;;) {
-                        // the next word at which a live set is dropped: the smallest (last word + 1), but not before
-                        // simWord + 1 (sets that ended earlier are all dropped by the first pass)
-                        unsigned nxt = 0xffffffffu;
-                        for (int t = (int)lane; t < simLive; t += 32) nxt = min(nxt, eEndW[order[t]] + 1u);
-                        for (int d = 16; d; d >>= 1) nxt = min(nxt, __shfl_xor_sync(DP_FULL, nxt, d));
-                        if (nxt == 0xffffffffu) break;
-                        const int i = max((int)nxt, simWord + 1);
-                        if (i > (int)wword) break;
-                        if (lane == 0) {
-                            int t = 0, live = simLive;
-                            while (t < live) {
-                                if (eEndW[order[t]] + 1 <= (unsigned)i) {
-                                    order[t] = order[live - 1];
-                                    live--;
-                                } else {
-                                    t++;
-                                }
-                            }
-                            simLive = live;
-                        }
-                        simLive = __shfl_sync(DP_FULL, simLive, 0);
-                        simWord = i;
-                        __syncwarp();
-                    }
-                    if ((int)wword > simWord) simWord = (int)wword;
+                    dp_q6_advance(I, X, wword, simInit);
                     simInit = true;
                     __syncwarp();
                     bool in = false;
@@ -410,7 +428,7 @@ __device__ __noinline__ int dp_refine_emit(const DpIndexDev& I, const DpRefineCt
             todo2 &= todo2 - 1;
             unsigned cc = __shfl_sync(DP_FULL, c, l);
             int distinct;
-            if (X.dupInCount) {
+            if (DUP_IN_COUNT) {
                 distinct = __shfl_sync(DP_FULL, soft - (int)(v >> 16), l);
             } else if (X.nDup >= 0) {
                 int rep = 0;
@@ -462,6 +480,7 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
     __shared__ unsigned shTouched[DP_LWARPS][DP_TCAP];
     __shared__ unsigned long long shCand[DP_LWARPS][DP_TCAP];
     __shared__ unsigned short shDup[DP_LWARPS][DP_DUPCAP];
+    __shared__ int shSim[DP_LWARPS][2];
     const unsigned lane = dp_lane();
     const unsigned lt = dp_lanemask_lt();
     const int wib = threadIdx.x >> 5;
@@ -702,14 +721,14 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
                 X.dup = shDup[wib];
                 X.nDup = nDup;
                 X.order = order;
+                X.sim = shSim[wib];
                 X.nInc = nInc;
                 X.minCount = minCount;
                 X.T = T;
                 X.clamped = clamped;
                 X.q6 = q6;
-                X.dupInCount = false;
                 X.nAllDistinct = nAllDistinct;
-                nCandOut = dp_refine_emit(I, X, sorted, nCand, outChunk, outDist, candStride);
+                nCandOut = dp_refine_emit<false>(I, X, sorted, nCand, outChunk, outDist, candStride);
                 if (nCandOut > candStride) {
                     if (lane == 0) atomicOr(&ctr->overflow, 4u);
                     nCandOut = candStride;
@@ -779,6 +798,7 @@ struct DpBlockShared {
     int nCandOut;
     int nGroup;
     unsigned nextItem;
+    int sim[2];
 };
 
 // exclusive prefix sum over the CTA (blockDim.x <= 1024); total returned in `total`
@@ -1145,15 +1165,17 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
                         X.dup = shDup;
                         X.nDup = sh.nDup <= DP_BDUP ? sh.nDup : -1;
                         X.order = order;
+                        X.sim = sh.sim;
                         X.nInc = nInc;
                         X.minCount = minCount;
                         X.T = T;
                         X.clamped = clamped;
                         X.q6 = q6;
-                        X.dupInCount = gShift != 0;
                         X.nAllDistinct = 0;
-                        int nOut = dp_refine_emit(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
-                                                  candDistinct + (size_t)ws * candStride, candStride);
+                        int nOut = gShift ? dp_refine_emit<true>(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
+                                                                 candDistinct + (size_t)ws * candStride, candStride)
+                                          : dp_refine_emit<false>(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
+                                                                  candDistinct + (size_t)ws * candStride, candStride);
                         if (nOut > candStride) {
                             if (lane == 0) atomicOr(&ctr->overflow, 4u);
                             nOut = candStride;
