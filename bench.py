@@ -433,8 +433,9 @@ def run_ours(args):
                     "wall_ms_per_step": wall_e2e / args.steps * 1e3,
                     "host_buffer_bytes_per_step": int(bases_rank),
                     "note": "per GPU; dp_mapper_map_batch on pinned host ASCII. The reads stay in the caller's pinned "
-                            "buffer and the windowed pack kernel pulls only the queried windows across PCIe "
-                            "(zero-copy), so h2d bytes < host buffer bytes; mapping records come back by D2H copy"},
+                            "buffer and a TMA pull kernel (cp.async.bulk: host -> shared memory -> HBM staging) moves only "
+                            "the queried windows across PCIe, so h2d bytes < host buffer bytes; the finish kernel writes "
+                            "the mapping records into mapped host memory"},
             "gpu_launches": int(agg["kernel_launches"]),
             "clocks": clocks, "roofline": roofline,
             "mapped_fraction": mapped_frac, "bases_per_step": total_bases,
