@@ -177,6 +177,35 @@ def test_pinned_host_reads_on_mixed_reads(pair, env):
     assert 0 < st["h2d_bytes"] < len(bases)  # windows only
 
 
+def test_edge_inputs(pair):
+    """Empty batch; empty, tiny (< k + 12 bases: no mapping), all-N and lowercase reads between ordinary ones; the same
+    through pageable, pinned and device-resident entry points."""
+    import torch
+    ref, circular, om, gm = pair
+    maps, off = gm.map_batch(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64))
+    assert len(maps) == 0 and list(off) == [0]
+    good = synth.reads(ref, 91, 6, 3000, circular=circular)
+    reads = [good[0:3000], np.zeros(0, dtype=np.uint8), np.frombuffer(b"ACGTACGTACGTACGTACGTAC", dtype=np.uint8),
+             np.frombuffer(b"N" * 2500, dtype=np.uint8), np.char.lower(good[3000:6000].view("S1")).view(np.uint8),
+             good[6000:9000], np.frombuffer(b"A", dtype=np.uint8), np.zeros(0, dtype=np.uint8), good[9000:12000],
+             np.frombuffer(b"acgtn" * 200, dtype=np.uint8), good[12000:18000]]
+    bases = np.concatenate(reads)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    orow, ooff, _ = om.map_batch(bases, offs, threads=2)
+    for mode in ("pageable", "pinned", "device"):
+        if mode == "pageable":
+            maps, off = gm.map_batch(bases, offs)
+        elif mode == "pinned":
+            t = torch.from_numpy(bases).pin_memory()
+            maps, off = gm.map_batch_ptr(t.data_ptr(), offs)
+        else:
+            t = torch.from_numpy(bases).cuda()
+            maps, off = gm.map_batch_device(t.data_ptr(), offs)
+        assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), mode
+    assert off[2] == off[1] and off[3] == off[2]  # the empty and the tiny read have no mapping
+    assert off[5] > off[4]                        # lowercase maps like uppercase
+
+
 def test_other_parameters():
     """k, seed_rate, query_size and chunk_size other than the defaults (commands/map.go:19-21)."""
     ref = synth.reference(8, 400_000)

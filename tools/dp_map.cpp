@@ -195,9 +195,11 @@ std::vector<double> kmer_values(std::vector<uint64_t>& counts, int k) {
         counts[i] = c;
         counts[rc] = c;
     }
+    // (only the SET of the n/100 largest under the total order (count, id) is needed: a selection, not a sort)
     std::vector<uint32_t> ids(n);
     std::iota(ids.begin(), ids.end(), 0u);
-    std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return counts[a] < counts[b]; });
+    auto less = [&](uint32_t a, uint32_t b) { return counts[a] != counts[b] ? counts[a] < counts[b] : a < b; };
+    std::nth_element(ids.begin(), ids.begin() + (n - n / 100), ids.end(), less);
     for (size_t i = n - n / 100; i < n; i++) values[ids[i]] = 0;
     values[0] = 0;
     return values;
@@ -323,8 +325,7 @@ int main(int argc, char** argv) {
     const size_t nSlots = devices.size() + 2;
     std::vector<Batch> slots(nSlots);
     for (auto& b : slots) {
-        b.cap = batchBytes;
-        if (dp_host_alloc((void**)&b.bases, b.cap)) fatal(std::string("dp_host_alloc: ") + dp_last_error());
+        b.cap = std::min(batchBytes, in.n + 4096);  // page-locked on first use: a small input pins a small buffer once
         b.reset();
     }
     struct Result {
@@ -358,6 +359,7 @@ int main(int argc, char** argv) {
                 freeSlots.pop_back();
             }
             Batch& b = slots[(size_t)s];
+            if (!b.bases && dp_host_alloc((void**)&b.bases, b.cap)) fatal(std::string("dp_host_alloc: ") + dp_last_error());
             b.reset();
             while (more && b.names.size() < batchReads && (b.used + r.len <= b.cap || b.names.empty())) {
                 if (r.len > b.cap) fatal("read longer than the batch buffer");
@@ -492,7 +494,8 @@ int main(int argc, char** argv) {
                 dp_version(), devices.size(), (long long)info[0], (long long)info[1], t1 - t0, t2 - t1, t3 - t2, mapSeconds,
                 totalBases, totalBases / (t3 - t2) / 1e9);
     }
-    for (auto& b : slots) dp_host_free(b.bases);
+    for (auto& b : slots)
+        if (b.bases) dp_host_free(b.bases);
     for (dp_mapper* m : mappers) dp_mapper_destroy(m);
     return 0;
 }
