@@ -855,6 +855,11 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             F.nSlow = reinterpret_cast<int*>(W.fcCursors.p + 2);
             CK(cudaMemsetAsync(W.fcCursors.p, 0, 4 * sizeof(unsigned long long), st));
             int rBlocks = (int)std::min<size_t>((nWin + 3) / 4, (size_t)M.smCount * (headroom ? 6 : 8));
+            {   // slab sizes of the warps' local allocators: at most half of either pool can be lost in slab tails
+                const unsigned long long activeWarps = std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)rBlocks * 4, nWin));
+                F.taskSlab = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(64, F.taskCap / (2 * activeWarps)));
+                F.poolSlab = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(2048, F.poolCap / (2 * activeWarps)));
+            }
             dp_reduce_kernel<<<rBlocks, 128, 0, st>>>(I, W.dWins.p, (int)nWin, Q, W.candN.p, W.candChunk.p,
                                                       W.candDistinct.p, W.candStride, S, F);
             CK(cudaGetLastError());

@@ -1802,6 +1802,7 @@ struct DpFastChain {
     unsigned* pool;            // packed entries: scan position << 16 | seed identity
     unsigned long long* cursors;  // [0] tasks, [1] pool words
     unsigned long long taskCap, poolCap;
+    unsigned taskSlab, poolSlab;  // a warp reserves this many task slots / pool words per global atomic
     unsigned char* slow;       // [nWin] window handed to the general path
     int* slowList;             // [nWin]
     int* nSlow;
@@ -1829,6 +1830,24 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
     const int wib = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    // Task slots and pool words are bump-allocated from two global cursors. A round trip to a global atomic costs a
+    // warp about a microsecond, so a warp reserves a slab per atomic and hands out pieces of it locally (the unused
+    // tail of a slab is lost: the pool is sized for it).
+    unsigned long long tCur = 0, tEnd = 0, pCur = 0, pEnd = 0;  // warp-uniform
+    auto take = [&](unsigned long long& cur, unsigned long long& end, unsigned long long* cursor, unsigned need,
+                    unsigned slab) {
+        if (cur + need > end) {
+            const unsigned long long want = need > slab ? need : slab;
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(cursor, want);
+            b = __shfl_sync(DP_FULL, b, 0);
+            cur = b;
+            end = b + want;
+        }
+        const unsigned long long off = cur;
+        cur += need;
+        return off;
+    };
     for (int w = gwarp; w < nWin; w += nWarps) {
         if (lane == 0) F.slow[w] = 0;
         bool slow = false;
@@ -1841,9 +1860,7 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
             int thr0 = n / 5;
             if (thr0 < 5) thr0 = 5;
             // the window strand's task slots
-            unsigned long long tb = 0;
-            if (lane == 0) tb = atomicAdd(F.cursors + 0, (unsigned long long)nc);
-            tb = __shfl_sync(DP_FULL, tb, 0);
+            const unsigned long long tb = take(tCur, tEnd, F.cursors + 0, (unsigned)nc, F.taskSlab);
             if (tb + (unsigned)nc > F.taskCap) {
                 slow = true;
                 break;
@@ -1880,9 +1897,7 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
                     }
                     if (ns >= thr0 && nq >= thr0) {
                         const unsigned need = 2u * (unsigned)nq + (unsigned)ns;
-                        unsigned long long off = 0;
-                        if (lane == 0) off = atomicAdd(F.cursors + 1, (unsigned long long)need);
-                        off = __shfl_sync(DP_FULL, off, 0);
+                        const unsigned long long off = take(pCur, pEnd, F.cursors + 1, need, F.poolSlab);
                         if (off + need > F.poolCap) {
                             slow = true;
                             break;
