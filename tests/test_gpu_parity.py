@@ -240,6 +240,43 @@ def test_config1_full_parity():
     gm.close()
 
 
+def test_config2_scale_properties():
+    """BASELINE config 2's shape at a fifth of its size (200k x 10 kb reads = 2 Gbp, several sub-batches on several
+    lanes), checked through properties that need no oracle: every uniquely mapped read lies at the locus and strand it
+    was simulated from; the call is idempotent; the pinned-host entry point (TMA pull) and the device-resident one
+    return identical records; a 5 000-read slice agrees with the oracle."""
+    import torch
+    ref = synth.reference(1, 4_600_000)
+    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
+    gm = dp.Mapper(ref, vals, circular=True)
+    n, L = 200_000, 10_000
+    pinned = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+    _, truth = synth.reads(ref, 12, n, L, out=pinned.numpy(), with_truth=True)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    maps, off = gm.map_batch_ptr(pinned.data_ptr(), offs)
+    rows = rows_of(maps)
+    maps2, off2 = gm.map_batch_ptr(pinned.data_ptr(), offs)
+    assert np.array_equal(off, off2) and np.array_equal(rows, rows_of(maps2))
+    d = pinned.cuda()
+    maps3, off3 = gm.map_batch_device(d.data_ptr(), offs)
+    assert np.array_equal(off, off3) and np.array_equal(rows, rows_of(maps3))
+    per_read = np.diff(off)
+    assert (per_read > 0).mean() > 0.999
+    uniq = np.nonzero(per_read == 1)[0]
+    r = rows[off[uniq]]
+    lead = np.where(r[:, 4] != 0, r[:, 3], r[:, 2])            # unmapped query bases before the reference start
+    delta = (r[:, 0] - (truth[uniq, 0] + lead)) % len(ref)
+    delta = np.minimum(delta, len(ref) - delta)
+    assert (r[:, 4] == truth[uniq, 1]).all()
+    near = delta < 200 + 0.15 * lead
+    assert near.mean() > 0.999, (float(near.mean()), int(delta[~near].max()))  # (reads across the origin may differ)
+    om = po.Mapper(ref, vals, circular=True)
+    ns = 5000
+    orow, ooff, _ = om.map_batch(pinned.numpy()[: ns * L], offs[: ns + 1], threads=os.cpu_count() or 4)
+    assert np.array_equal(ooff, off[: ns + 1]) and np.array_equal(orow, rows[: off[ns]])
+    gm.close()
+
+
 class _Env:
     def __init__(self, env):
         self.env = env
