@@ -13,6 +13,7 @@
 // DOWNPORE_BATCH / DOWNPORE_BATCH_BYTES = reads / bytes per dp_mapper_map_batch call (default 131072 / 1.5 GiB), DOWNPORE_STATS=1 prints stage timings.
 // Output order: records grouped per read in input order (the reference prints in goroutine completion order).
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -211,14 +212,29 @@ struct Batch {
     size_t cap = 0, used = 0;
     std::vector<int64_t> offsets;
     std::vector<std::pair<const unsigned char*, size_t>> names;
+    std::vector<const unsigned char*> srcs;  // where each read's bases lie in the input file
     bool last = false;
     void reset() {
         used = 0;
         offsets.assign(1, 0);
         names.clear();
+        srcs.clear();
         last = false;
     }
 };
+
+// fn(t, lo, hi) over [0, n) cut into contiguous pieces, one per thread
+template <class F>
+void parallel_ranges(size_t n, size_t threads, F fn) {
+    threads = std::max<size_t>(1, std::min(threads, n));
+    if (threads == 1) {
+        fn((size_t)0, (size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < threads; t++) th.emplace_back([=] { fn(t, n * t / threads, n * (t + 1) / threads); });
+    for (auto& x : th) x.join();
+}
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -278,6 +294,10 @@ int main(int argc, char** argv) {
     const size_t batchBytes =
         getenv("DOWNPORE_BATCH_BYTES") ? (size_t)atoll(getenv("DOWNPORE_BATCH_BYTES")) : ((size_t)3 << 29);
     const bool wantStats = getenv("DOWNPORE_STATS") != nullptr;
+    // host threads for copying reads into the batch buffers and for formatting PAF lines (DOWNPORE_HOST_THREADS)
+    const size_t hostThreads = getenv("DOWNPORE_HOST_THREADS")
+                                   ? (size_t)std::max(1, atoi(getenv("DOWNPORE_HOST_THREADS")))
+                                   : (size_t)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
 
     // ---- reference: the first record is indexed, every record is counted (commands/map.go:34-36, 45) ----
     double t0 = now_s();
@@ -363,12 +383,18 @@ int main(int argc, char** argv) {
             b.reset();
             while (more && b.names.size() < batchReads && (b.used + r.len <= b.cap || b.names.empty())) {
                 if (r.len > b.cap) fatal("read longer than the batch buffer");
-                memcpy(b.bases + b.used, r.seq, r.len);
+                b.srcs.push_back(r.seq);
                 b.used += r.len;
                 b.offsets.push_back((int64_t)b.used);
                 b.names.emplace_back(r.name, r.nameLen);
                 more = rr.next(r);
             }
+            // the parser is serial (seqio.go's rules carry state from line to line); the copy into the page-locked
+            // batch is not
+            parallel_ranges(b.srcs.size(), hostThreads, [&b](size_t, size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; i++)
+                    memcpy(b.bases + b.offsets[i], b.srcs[i], (size_t)(b.offsets[i + 1] - b.offsets[i]));
+            });
             {
                 std::lock_guard<std::mutex> lk(mu);
                 slotSeq[(size_t)s] = produced++;
@@ -429,8 +455,6 @@ int main(int argc, char** argv) {
 
     // ---- printer (commands/map.go:88-106), in batch order ----
     long long mapped = 0, multiple = 0, total = 0, unmapped = 0;
-    std::vector<char> line(1 << 16);
-    std::string nameBuf;
     static char outBuf[1 << 20];
     setvbuf(stdout, outBuf, _IOFBF, sizeof(outBuf));
     for (;;) {
@@ -450,25 +474,43 @@ int main(int argc, char** argv) {
             nextToPrint++;
         }
         Batch& b = slots[(size_t)s];
-        for (size_t i = 0; i < b.names.size(); i++) {
-            const int64_t a = res.offs[i], e = res.offs[i + 1];
-            const int64_t qlen = b.offsets[i + 1] - b.offsets[i];
-            totalBases += qlen;
-            if (e > a) {
-                nameBuf.assign((const char*)b.names[i].first, b.names[i].second);
-                for (int64_t j = a; j < e; j++) {
-                    int n = dp_mapper_paf_line(mappers[0], res.maps + j, nameBuf.c_str(), qlen, refName.c_str(), line.data(),
-                                               (int)line.size());
-                    if (n < 0) fatal("PAF line too long");
-                    fwrite(line.data(), 1, (size_t)n, stdout);
-                    fputc('\n', stdout);
+        // the lines of a batch are formatted by several threads, each into its own buffer, and written in read order
+        const size_t nPieces = std::max<size_t>(1, std::min(hostThreads, b.names.size() / 4096 + 1));
+        std::vector<std::string> text(nPieces);
+        std::vector<std::array<long long, 5>> cnt(nPieces, std::array<long long, 5>{0, 0, 0, 0, 0});
+        parallel_ranges(b.names.size(), nPieces, [&](size_t t, size_t lo, size_t hi) {
+            std::vector<char> line(1 << 16);
+            std::string nameBuf;
+            std::string& out = text[t];
+            out.reserve((hi - lo) * 96);
+            for (size_t i = lo; i < hi; i++) {
+                const int64_t a = res.offs[i], e = res.offs[i + 1];
+                const int64_t qlen = b.offsets[i + 1] - b.offsets[i];
+                cnt[t][4] += qlen;
+                if (e > a) {
+                    nameBuf.assign((const char*)b.names[i].first, b.names[i].second);
+                    for (int64_t j = a; j < e; j++) {
+                        int n = dp_mapper_paf_line(mappers[0], res.maps + j, nameBuf.c_str(), qlen, refName.c_str(),
+                                                   line.data(), (int)line.size());
+                        if (n < 0) fatal("PAF line too long");
+                        out.append(line.data(), (size_t)n);
+                        out.push_back('\n');
+                    }
+                    if (e - a == 1) cnt[t][0]++;
+                    else cnt[t][1]++;
+                    cnt[t][2] += e - a;
+                } else {
+                    cnt[t][3]++;
                 }
-                if (e - a == 1) mapped++;
-                else multiple++;
-                total += e - a;
-            } else {
-                unmapped++;
             }
+        });
+        for (size_t t = 0; t < nPieces; t++) {
+            fwrite(text[t].data(), 1, text[t].size(), stdout);
+            mapped += cnt[t][0];
+            multiple += cnt[t][1];
+            total += cnt[t][2];
+            unmapped += cnt[t][3];
+            totalBases += cnt[t][4];
         }
         dp_free(res.maps);
         dp_free(res.offs);
