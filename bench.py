@@ -37,7 +37,17 @@ K = 11
 REF_LEN = 4_600_000
 READ_LEN = 10_000
 REF_SEED, READ_SEED = 1, 12
+CIRCULAR = True
+WORKLOAD = "BASELINE config 2"
 EDGE = 1000
+
+
+def select_workload(name):
+    """--workload config2 (default: the configuration the metric is quoted on) | config3 (64 Mb linear reference,
+    20 kb reads; SURVEY 8d seeds 3 / 13). Same contract and JSON line either way."""
+    global REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD
+    if name == "config3":
+        REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD = 64_000_000, 20_000, 3, 13, False, "BASELINE config 3"
 
 
 _JSON_OUT = None
@@ -154,10 +164,11 @@ def shard_bounds(n_total, rank, world):
 
 
 def config_dict(args, world):
-    return {"workload": "BASELINE config 2: synthetic 4.6 Mb circular reference, %d simulated 10 kb ONT-like reads "
-                        "(4%% sub, 3%% ins, 3%% del) per GPU" % args.reads,
+    return {"workload": "%s: synthetic %.1f Mb %s reference, %d simulated %d kb ONT-like reads "
+                        "(4%% sub, 3%% ins, 3%% del) per GPU" % (WORKLOAD, REF_LEN / 1e6, "circular" if CIRCULAR else "linear",
+                                                               args.reads, READ_LEN // 1000),
             "reads_per_gpu": args.reads, "read_len": READ_LEN, "ref_len": REF_LEN, "k": K, "seed_rate": 40,
-            "query_size": EDGE, "chunk_size": 10000, "circular": True,
+            "query_size": EDGE, "chunk_size": 10000, "circular": CIRCULAR,
             "parallelism": "reads sharded over %d GPU(s), index replicated (%s), no data-path collective" % (
                 world, "built on rank 0, one NCCL broadcast of its image" if world > 1 and args.index == "broadcast"
                 else "built per GPU"),
@@ -178,9 +189,9 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     ref = synth.reference(REF_SEED, REF_LEN)
     vals = po.kmer_values(ref, K)
-    om = po.Mapper(ref, vals, circular=True)
+    om = po.Mapper(ref, vals, circular=CIRCULAR)
     n = args.ref_sample
-    rd = synth.reads(ref, READ_SEED, n, READ_LEN)
+    rd = synth.reads(ref, READ_SEED, n, READ_LEN, circular=CIRCULAR)
     offs = np.arange(n + 1, dtype=np.int64) * READ_LEN
     for _ in range(min(args.warmup, 1)):
         om.map_batch(rd[: 2000 * READ_LEN], offs[:2001], threads=cores)
@@ -294,7 +305,7 @@ def run_ours(args):
     t_repl = 0.0
     if world > 1 and args.index == "broadcast":
         # the index is built once (rank 0) and replicated by ONE NCCL broadcast of its image over NVLink
-        gm = dp.Mapper(ref, vals, circular=True, device=local) if rank == 0 else None
+        gm = dp.Mapper(ref, vals, circular=CIRCULAR, device=local) if rank == 0 else None
         torch.cuda.synchronize()
         t_index = time.time() - t1
         barrier(world)
@@ -304,7 +315,7 @@ def run_ours(args):
         barrier(world)
         t_repl = time.time() - t2
     else:
-        gm = dp.Mapper(ref, vals, circular=True, device=local)
+        gm = dp.Mapper(ref, vals, circular=CIRCULAR, device=local)
         torch.cuda.synchronize()
         t_index = time.time() - t1
     info = gm.index_info()
@@ -313,7 +324,7 @@ def run_ours(args):
     first = rank * n  # weak scaling: every rank maps its own n reads of the same read set
     pinned = torch.empty(n * READ_LEN, dtype=torch.uint8).pin_memory()
     host = pinned.numpy()
-    synth.reads(ref, READ_SEED, n, READ_LEN, first_index=first, out=host)
+    synth.reads(ref, READ_SEED, n, READ_LEN, circular=CIRCULAR, first_index=first, out=host)
     offs = np.arange(n + 1, dtype=np.int64) * READ_LEN
     d_reads = pinned.to(dev, non_blocking=False)
     torch.cuda.synchronize()
@@ -409,10 +420,14 @@ def run_ours(args):
             gather_gbs = None
     # sector traffic of the lookup kernel's posting gathers: every posting run costs whole 32 B sectors
     sector_bytes_lookup = 32.0 * agg["posting_runs"] / S + 32.0 * (4.0 * agg["posting_entries"] / S) / 32.0
-    roofline = {"kernel": "dp_%s_kernel" % dominant, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
-                "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"], "traffic": traffic.get(dominant),
+    kname = "dp_%s_kernel" % dominant
+    if dominant == "lookup" and info["num_chunks"] >= 2048:
+        kname = "dp_lookup_block_kernel"
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
+                "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"],
+                "traffic": traffic.get(dominant) if args.workload == "config2" else None,
                 "peak_source": peak_src,
-                "note": "config 2's index (8.6 MB) and k-mer table (1 MB) are L2-resident, so no kernel of this workload "
+                "note": "config 2's index (7.3 MB) and k-mer table (1 MB) are L2-resident, so no kernel of this workload "
                         "is bound by HBM (ncu: dram throughput < 2 % for every kernel; they are issue/latency bound, "
                         "see profiles/). achieved = SURVEY 8d algorithmic bytes of one step / CUDA-event time of that "
                         "kernel family on its launching stream over one step run on a single lane (kernels not "
@@ -458,7 +473,7 @@ def run_ours(args):
         if affinity_before:
             os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every core this process may use
         cores = len(os.sched_getaffinity(0)) or 1
-        om = po.Mapper(ref, vals, circular=True)
+        om = po.Mapper(ref, vals, circular=CIRCULAR)
         ns = args.cpu_sample
         t0 = time.time()
         orow, ooff, _ = om.map_batch(host[: ns * READ_LEN], offs[: ns + 1], threads=cores)
@@ -488,6 +503,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=int(os.environ.get("DP_BENCH_READS", 1_000_000)),
                     help="reads per GPU per step (BASELINE config 2: 1M)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 = the configuration the metric is quoted on (default); config3 = 64 Mb linear reference, "
+                         "20 kb reads (use --reads 500000: 10 GB of ASCII per GPU per step)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -495,6 +513,7 @@ def main():
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
                     help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:
