@@ -1067,18 +1067,24 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
                 }
                 // ---- runs that repeat an earlier run's seed (for the distinct counts) ----
                 if (gShift ? sh.nGroup > 0 : sh.nCand > 0) {
-                    for (int j = tid; j < nInc; j += nT) {
-                        const unsigned s = eSeed[j];
-                        bool first = true;
-                        for (int b = 0; b < j; b++)
-                            if (eSeed[b] == s) {
-                                first = false;
-                                break;
+                    // within a warp's 32 runs by __match_any_sync; against the earlier runs four seeds per load
+                    const uint4* eSeed4 = reinterpret_cast<const uint4*>(eSeed);
+                    for (int j0 = warp * 32; j0 < nInc; j0 += nT) {  // (warp-uniform bounds)
+                        const int j = j0 + (int)lane;
+                        const unsigned s = j < nInc ? eSeed[j] : (0x80000000u | lane);  // (seed ranks are below 2^31)
+                        const unsigned mm = __match_any_sync(DP_FULL, s);
+                        bool first = (__ffs(mm) - 1) == (int)lane;
+                        if (j < nInc && first)
+                            for (int b4 = 0; b4 < (j0 >> 2) && first; b4++) {
+                                const uint4 q = eSeed4[b4];
+                                first = !(q.x == s || q.y == s || q.z == s || q.w == s);
                             }
-                        eFirst[j] = first ? 1 : 0;
-                        if (!first) {
-                            const int slot = atomicAdd(&sh.nDup, 1);
-                            if (slot < DP_BDUP) shDup[slot] = (unsigned short)j;
+                        if (j < nInc) {
+                            eFirst[j] = first ? 1 : 0;
+                            if (!first) {
+                                const int slot = atomicAdd(&sh.nDup, 1);
+                                if (slot < DP_BDUP) shDup[slot] = (unsigned short)j;
+                            }
                         }
                     }
                     __syncthreads();
