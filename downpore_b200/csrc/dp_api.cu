@@ -671,7 +671,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     if (seedEntries >= 0xffffffffull) throw std::runtime_error("window round too large for 32-bit seed offsets");
     CK(cudaMemsetAsync(W.cursor.p, 0, 4 * sizeof(unsigned long long), st));
     // compute kernels leave part of every SM free while another lane's pull kernel reads host memory (measured with
-    // the zero-copy pack kernel; DP_HEADROOM=0/1 overrides)
+    // the zero-copy pack kernel; with the TMA pull it makes no measurable difference; DP_HEADROOM=0/1 overrides)
     const bool headroom = W.curAsciiIsHost && env_int("DP_HEADROOM", 1) != 0;
     if (!M.attrsSet) {
         CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -682,7 +682,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         CK(cudaFuncSetAttribute(dp_lookup_block_kernel<128, 8, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         M.attrsSet = true;
     }
-    {   // pack exactly the queried windows (zero-copy from pinned host memory when that is where the reads live)
+    {   // pack exactly the queried windows (out of pinned host memory when that is where the reads live)
         // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
         // compute kernels stay resident beside it
         int perSm = W.curAsciiIsHost ? 2 : 6;

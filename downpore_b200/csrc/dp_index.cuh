@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __res
 
 // ---------------------------------------------------------------------------------------------------------------
 // Windowed pack: only the windows that are queried are ever packed (Map() touches 2..12 windows of `edge` bases per
-// read, never the middle of a long read: mapping/mapping.go:430-487). `ascii` may be device memory or pinned host
-// memory mapped into the device address space: the latter turns the H2D copy into coalesced zero-copy reads of just
-// the queried bytes. One warp per window; per iteration the lanes load 32 consecutive 16-byte aligned blocks
+// read, never the middle of a long read: mapping/mapping.go:430-487). `ascii` may be device memory, pinned host
+// memory mapped into the device address space (coalesced zero-copy reads of just the queried bytes: the few windows
+// of later Map() rounds), or — `stage` — the HBM staging buffer dp_pull_windows_kernel has filled from such host
+// memory (the bulk of the round-0 windows). One warp per window; per iteration the lanes load 32 consecutive 16-byte aligned blocks
 // (one LDG.128 each, 512 contiguous bytes per warp), neighbours exchange blocks by shuffle, and 31 packed words are
 // written. Each source byte crosses the bus once (+1/31 overlap).
 // ---------------------------------------------------------------------------------------------------------------

@@ -61,8 +61,8 @@ typedef struct dp_stats {
     int64_t mappings;       /* mappings returned */
     int64_t kernel_launches;/* kernels launched by the call */
     int64_t bases;          /* sum of read lengths of the call */
-    int64_t h2d_bytes;      /* read bytes that crossed the host->device link (copied, or pulled zero-copy by the
-                               windowed pack kernel when the caller's buffer is pinned) */
+    int64_t h2d_bytes;      /* read bytes that crossed the host->device link (copied, or - when the caller's buffer is
+                               page-locked - only the queried windows, moved by the TMA pull kernel) */
     double ms_reduce;       /* list-reduction kernel of the chaining fast path (not included in ms_chain) */
 } dp_stats;
 
@@ -148,8 +148,9 @@ int dp_probe_gather_gbs(int device, int64_t table_bytes, double* sector_gbs);
 
 /*
  * Page-locked host memory for read batches (what a cgo host passes as `bases`): dp_mapper_map_batch reads such a
- * buffer in place from the device (zero-copy pull of the queried windows), so a host that fills batches into
- * dp_host_alloc'ed memory never pays a staging copy. Portable across devices. Release with dp_host_free.
+ * buffer in place from the device (only the queried windows cross the link: TMA bulk copies out of the mapped buffer),
+ * so a host that fills batches into dp_host_alloc'ed memory never pays a staging copy. Portable across devices.
+ * Release with dp_host_free.
  */
 int dp_host_alloc(void** out, size_t bytes);
 void dp_host_free(void* p);
