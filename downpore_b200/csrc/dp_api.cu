@@ -807,6 +807,23 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                                                                    W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
             W.stats.kernel_launches += 1;
+        } else if (I.numChunks <= DP_SMALL_CHUNKS && env_int("DP_LOOKUP_SMALL", 1) != 0) {
+            // small references: the lean register-resident kernel takes the window strands with at most 32 seeds (the
+            // bulk), the general kernel the ones it hands back
+            int* deferList = W.lbDefer.p;
+            int* nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
+            CK(cudaMemsetAsync(W.lbWork.p, 0, 4 * sizeof(unsigned), st));
+            int sBlocks = (int)std::min<size_t>((2 * nWin + DP_SMALL_WARPS - 1) / DP_SMALL_WARPS,
+                                                (size_t)M.smCount * (headroom ? 9 : 12));
+            dp_lookup_small_kernel<<<sBlocks, 32 * DP_SMALL_WARPS, (size_t)DP_SMALL_WARPS * I.numChunks * sizeof(unsigned), st>>>(
+                I, Q, (int)(2 * nWin), deferList, nDefer, W.candN.p, W.candChunk.p, W.candDistinct.p, W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 4);
+            dp_lookup_kernel<<<dBlocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), deferList, nDefer, S, inSmem,
+                                                                   W.candN.p, W.candChunk.p, W.candDistinct.p,
+                                                                   W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            W.stats.kernel_launches += 1;
         } else {
             int blocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
                                                (size_t)M.smCount * (headroom ? 6 : 8));

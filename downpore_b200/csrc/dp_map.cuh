@@ -747,6 +747,156 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
 }
 
 // ===============================================================================================================
+// Stage 2, common case of small references (dp_lookup_small_kernel): a window strand with at most 32 seeds against an
+// index of at most DP_SMALL_CHUNKS chunks. Everything dp_lookup_kernel keeps in shared-memory lists lives in registers
+// here (one included run per lane), and the generality is gone:
+//   * n <= 32 means minCount = (nInc + 2) / 4 <= 8, so the threshold is exact: no level clamp (Q11), no level-16
+//     under-count (Q6), no early stop;
+//   * one 32-bit counter per chunk holds the soft count (every included run) in its lower and the DISTINCT count
+//     (first occurrences of a seed only) in its upper half-word, so the distinct count needs no search;
+//   * a chunk becomes a candidate when its soft count reaches T (counts only grow: once); the table is blanked
+//     wholesale afterwards.
+// Window strands outside the common case (more than 32 seeds, a seed present in every chunk, more than 32 candidates)
+// are handed to dp_lookup_kernel through a list, with identical results.
+// ===============================================================================================================
+#define DP_SMALL_CHUNKS 2048
+#define DP_SMALL_WARPS 4
+
+__global__ void __launch_bounds__(32 * DP_SMALL_WARPS, 12) dp_lookup_small_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                                int* __restrict__ deferList,
+                                                                                int* __restrict__ nDefer,
+                                                                                int* __restrict__ candN,
+                                                                                unsigned* __restrict__ candChunk,
+                                                                                unsigned short* __restrict__ candDistinct,
+                                                                                int candStride, DpCounters* __restrict__ ctr) {
+    extern __shared__ unsigned dp_smem[];  // DP_SMALL_WARPS x C counters
+    const unsigned lane = dp_lane();
+    const unsigned lt = dp_lanemask_lt();
+    const int wib = threadIdx.x >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned C = I.numChunks;
+    unsigned* cnt = dp_smem + (size_t)wib * C;
+    for (unsigned c = lane; c < C; c += 32) cnt[c] = 0;
+    __syncwarp();
+    unsigned long long cRuns = 0, cEntries = 0, cCand = 0;
+    for (int ws = gwarp; ws < nWS; ws += nWarps) {
+        const int n = Q.wsN[ws];
+        int nOut = 0;
+        bool defer = n > 32;
+        if (n >= 5 && !defer) {
+            const unsigned qb = Q.wsOff[ws];
+            const bool valid = (int)lane < n;
+            unsigned s = 0xffffffffu, o = 0, c = 0;
+            if (valid) {
+                s = Q.qSeed[qb + lane];
+                o = __ldg(I.seedOff + s);
+                c = __ldg(I.seedOff + s + 1) - o;
+            }
+            defer = __any_sync(DP_FULL, valid && c >= C);  // a seed present in every chunk: the general kernel's business
+            if (!defer) {
+                // ---- inclusion filter (seeds.go:340-346): every occurrence is eligible here, repeats of the
+                //      previous occurrence's seed are skipped ----
+                const unsigned sPrev = __shfl_up_sync(DP_FULL, s, 1);
+                const bool inc = valid && (lane == 0 || s != sPrev);
+                const unsigned mi = __ballot_sync(DP_FULL, inc);
+                const int nInc = __popc(mi);
+                if (nInc >= 5) {
+                    const int T = (nInc + 2) >> 2;  // <= 8: exact level
+                    // compact the included runs: lane t holds the t-th
+                    const int src = (int)lane < nInc ? (int)__fns(mi, 0, (int)lane + 1) : 0;
+                    const unsigned es = __shfl_sync(DP_FULL, s, src);
+                    const unsigned eo = __shfl_sync(DP_FULL, o, src);
+                    const unsigned ecAll = __shfl_sync(DP_FULL, c, src);
+                    const unsigned ec = (int)lane < nInc ? ecAll : 0u;
+                    // first occurrence of the seed among the included runs
+                    const unsigned mm = __match_any_sync(DP_FULL, (int)lane < nInc ? es : (0x80000000u | lane));
+                    const unsigned add = (__ffs(mm) - 1) == (int)lane ? 0x10001u : 1u;
+                    // exclusive prefix of the run lengths
+                    unsigned x = ec;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned y = __shfl_up_sync(DP_FULL, x, d);
+                        if ((int)lane >= d) x += y;
+                    }
+                    const unsigned pre = x - ec;
+                    const unsigned total = __shfl_sync(DP_FULL, x, 31);
+                    // ---- flattened gather: posting p belongs to the run r with pre_r <= p < pre_r + ec_r ----
+                    unsigned candChunkReg = 0;  // lane t: the t-th chunk whose soft count reached T
+                    int nCand = 0;
+                    for (unsigned p0 = 0; p0 < total && nCand <= 32; p0 += 32) {
+                        const unsigned p = p0 + lane;
+                        int lo = 0, hi = nInc;
+                        for (int step = 0; step < 5; step++) {  // largest r with pre_r <= p (nInc <= 32)
+                            const int mid = (lo + hi) >> 1;
+                            const unsigned v = __shfl_sync(DP_FULL, pre, mid);
+                            if (hi - lo > 1) {
+                                if (v <= p) lo = mid;
+                                else hi = mid;
+                            }
+                        }
+                        const unsigned ro = __shfl_sync(DP_FULL, eo, lo);
+                        const unsigned rp = __shfl_sync(DP_FULL, pre, lo);
+                        const unsigned ra = __shfl_sync(DP_FULL, add, lo);
+                        bool reached = false;
+                        unsigned chunk = 0;
+                        if (p < total) {
+                            chunk = __ldg(I.seedChunks + ro + (p - rp));
+                            const unsigned old = atomicAdd(cnt + chunk, ra);
+                            reached = (int)(old & 0xffffu) + 1 == T;
+                        }
+                        const unsigned mr = __ballot_sync(DP_FULL, reached);
+                        if (mr) {
+                            // append this round's chunks to the candidate registers (lane nCand + rank)
+                            const int base = nCand;
+                            nCand += __popc(mr);
+                            if (nCand <= 32) {
+                                const int want = (int)lane - base;  // which of this round's chunks lands on this lane
+                                const int from = want >= 0 && want < __popc(mr) ? (int)__fns(mr, 0, want + 1) : 0;
+                                const unsigned got = __shfl_sync(DP_FULL, chunk, from);
+                                if (want >= 0 && want < __popc(mr)) candChunkReg = got;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (nCand > 32) {
+                        defer = true;  // (the general kernel lists candidates in memory)
+                    } else {
+                        cRuns += (unsigned)nInc;
+                        cEntries += total;
+                        // final counts, ascending chunk id, output
+                        const unsigned w = (int)lane < nCand ? cnt[candChunkReg] : 0u;
+                        int rank = 0;
+                        for (int y = 0; y < nCand; y++) rank += __shfl_sync(DP_FULL, candChunkReg, y) < candChunkReg;
+                        if ((int)lane < nCand && rank < candStride) {
+                            candChunk[(size_t)ws * candStride + rank] = candChunkReg;
+                            candDistinct[(size_t)ws * candStride + rank] = (unsigned short)(w >> 16);
+                        }
+                        nOut = nCand;
+                        if (nOut > candStride) {
+                            if (lane == 0) atomicOr(&ctr->overflow, 4u);
+                            nOut = candStride;
+                        }
+                    }
+                    __syncwarp();
+                    if (total) for (unsigned c2 = lane; c2 < C; c2 += 32) cnt[c2] = 0;
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) {
+            if (defer) deferList[atomicAdd(nDefer, 1)] = ws;
+            else candN[ws] = nOut;
+        }
+        if (!defer) cCand += (unsigned)nOut;
+    }
+    if (lane == 0 && (cRuns | cCand)) {
+        atomicAdd(&ctr->posting_runs, cRuns);
+        atomicAdd(&ctr->posting_entries, cEntries);
+        atomicAdd(&ctr->candidates, cCand);
+    }
+}
+
+// ===============================================================================================================
 // Stage 2 for indexes with many chunks — one CTA per window strand (dp_lookup_block_kernel).
 //
 // With C chunks a warp-private set of counters costs 2C bytes; beyond a few thousand chunks that either leaves the SM

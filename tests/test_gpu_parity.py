@@ -308,7 +308,8 @@ def large_ref():
 
 
 @pytest.mark.parametrize("env", [
-    {},                                                        # warp per window strand, shared-memory counters
+    {},                                                        # lean register kernel + the general warp kernel for what it defers
+    {"DP_LOOKUP_SMALL": "0"},                                  # general warp kernel only, shared-memory counters
     {"DP_LOOKUP_SMEM_CHUNKS": "100"},                          # warp kernel, counters in global memory
     {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one counter per chunk, 32-posting items
     {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_SEG": "128"},          # 128-posting items (indexes with long runs)
@@ -345,10 +346,12 @@ def test_block_lookup_on_mixed_reads(env):
     bases = np.concatenate(reads)
     offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
     orow, ooff, octr = om.map_batch(bases, offs, threads=4)
-    gm = dp.Mapper(ref, vals, circular=True)
-    gm.map_batch(bases, offs)
-    st0 = gm.stats()  # warp-per-window-strand route
-    gm.close()
+    with _Env({"DP_LOOKUP_SMALL": "0"}):
+        gm = dp.Mapper(ref, vals, circular=True)
+        maps0, off0 = gm.map_batch(bases, offs)
+        st0 = gm.stats()  # general warp-per-window-strand route only
+        gm.close()
+    assert np.array_equal(off0, ooff) and np.array_equal(rows_of(maps0), orow)
     with _Env(env):
         gm = dp.Mapper(ref, vals, circular=True)
         maps, off = gm.map_batch(bases, offs)
