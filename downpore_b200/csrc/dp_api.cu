@@ -818,7 +818,10 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             dp_lookup_small_kernel<<<sBlocks, 32 * DP_SMALL_WARPS, (size_t)DP_SMALL_WARPS * I.numChunks * sizeof(unsigned), st>>>(
                 I, Q, (int)(2 * nWin), deferList, nDefer, W.candN.p, W.candChunk.p, W.candDistinct.p, W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
-            int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 4);
+            // (about a tenth of config 2's window strands have more than 32 seeds: few per warp, so the pass lasts as
+            // long as one warp's serial chain of them — spread them over as many warps as fit)
+            int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
+                                                (size_t)M.smCount * (headroom ? 6 : 8));
             dp_lookup_kernel<<<dBlocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), deferList, nDefer, S, inSmem,
                                                                    W.candN.p, W.candChunk.p, W.candDistinct.p,
                                                                    W.candStride, W.dCtr.p);

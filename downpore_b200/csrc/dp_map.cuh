@@ -1721,6 +1721,87 @@ __device__ bool dp_build_lists(const DpIndexDev& I, const DpExtractOut& Q, unsig
     return true;
 }
 
+// The two Reduced lists of dp_build_lists for a window strand with at most 32 seeds, in registers: lane j holds seed
+// occurrence j (`s`, its scan position `qPos`, `first` = lane of the seed's first occurrence, and for first occurrences
+// the bounds [pb, pe) of the seed's position-carrying posting run). Returns false when the chunk side has more than 32
+// entries (the caller then takes the general routine). On success lane t < nq holds the t-th query-side word in
+// `rqWord`, lane t < ns the t-th chunk-side word in `rsWord` (scan position << 16 | seed identity).
+__device__ __forceinline__ bool dp_build_lists_small(const DpIndexDev& I, int n, unsigned c, int first, int qPos, unsigned pb,
+                                                     unsigned pe, unsigned* sortScratch, int& nq, int& ns,
+                                                     unsigned& rqWord, unsigned& rsWord) {
+    const unsigned lane = dp_lane();
+    const unsigned lt = dp_lanemask_lt();
+    const bool isFirst = (int)lane < n && first == (int)lane;
+    // every distinct query seed looks up its postings inside chunk c
+    unsigned lo = pb;
+    unsigned cnt = 0;
+    if (isFirst) {
+        unsigned hi = pe;
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (__ldg(I.postChunk + mid) < c) lo = mid + 1;
+            else hi = mid;
+        }
+        while (lo + cnt < pe && __ldg(I.postChunk + lo + cnt) == c) cnt++;
+    }
+    unsigned x = cnt;  // inclusive scan of the counts
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned y = __shfl_up_sync(DP_FULL, x, d);
+        if ((int)lane >= d) x += y;
+    }
+    const unsigned pre = x - cnt;
+    const unsigned m = __shfl_sync(DP_FULL, x, 31);
+    if (m > 32u) return false;
+    // query.Reduced(chunkSet): occurrences whose seed is in the chunk, same-as-previous-member collapsed
+    const unsigned cntFirst = __shfl_sync(DP_FULL, cnt, first & 31);
+    const bool member = (int)lane < n && cntFirst != 0;
+    const unsigned mmask = __ballot_sync(DP_FULL, member);
+    const unsigned lower = mmask & lt;
+    int pid = __shfl_sync(DP_FULL, first, lower ? 31 - __clz(lower) : 0);
+    if (!lower) pid = -1;
+    const bool keep = member && first != pid;
+    const unsigned mk = __ballot_sync(DP_FULL, keep);
+    nq = __popc(mk);
+    {
+        const unsigned word = ((unsigned)qPos << 16) | (unsigned)first;
+        const int src = (int)lane < nq ? (int)__fns(mk, 0, (int)lane + 1) : 0;
+        rqWord = __shfl_sync(DP_FULL, word, src);
+    }
+    // chunk.Reduced(querySet): (position, seed) pairs of the chunk side, sorted by position, collapsed
+    unsigned ent = 0xffffffffu;  // position << 16 | seed identity (lane of the first occurrence)
+    {
+        int rl = 0, rh = 32;  // largest lane r with pre_r <= lane (runs of zero length are never selected, see below)
+        for (int step = 0; step < 5; step++) {
+            const int mid = (rl + rh) >> 1;
+            const unsigned v = __shfl_sync(DP_FULL, pre, mid);
+            if (v <= lane) rl = mid;
+            else rh = mid;
+        }
+        const unsigned rLo = __shfl_sync(DP_FULL, lo, rl);
+        const unsigned rPre = __shfl_sync(DP_FULL, pre, rl);
+        if (lane < m) ent = ((unsigned)__ldg(I.postPos + rLo + (lane - rPre)) << 16) | (unsigned)rl;
+    }
+    // (scan positions inside a chunk are distinct: ranks are unique)
+    int rank = 0;
+    for (unsigned y = 0; y < m; y++) rank += (__shfl_sync(DP_FULL, ent, (int)y) >> 16) < (ent >> 16);
+    __syncwarp();
+    if (lane < m) sortScratch[rank] = ent;
+    __syncwarp();
+    const unsigned sorted = lane < m ? sortScratch[lane] : 0xffffffffu;
+    __syncwarp();
+    const unsigned id = sorted & 0xffffu;
+    unsigned prevId = __shfl_up_sync(DP_FULL, id, 1);
+    if (lane == 0) prevId = 0xffffffffu;
+    const bool keepS = lane < m && id != prevId;
+    const unsigned ms = __ballot_sync(DP_FULL, keepS);
+    ns = __popc(ms);
+    {
+        const int src = (int)lane < ns ? (int)__fns(ms, 0, (int)lane + 1) : 0;
+        rsWord = __shfl_sync(DP_FULL, sorted, src);
+    }
+    return true;
+}
+
 // Exact general path, one warp per window: used for the windows the fast path (dp_reduce_kernel + dp_chain_thread_kernel
 // below) hands back (`winList` / `nWinList` set), and for everything when the fast path is switched off.
 __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const DpWindow* __restrict__ wins,
@@ -2036,7 +2117,23 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
             LB.gRsPos = S.rsPos + (size_t)gwarp * S.sStride;
             LB.gRsId = S.rsId + (size_t)gwarp * S.sStride;
             LB.sStride = S.sStride;
-            dp_seed_identity(Q, qb, n, LB.qFirst);
+            // window strands with at most 32 seeds (the bulk on small references) build their lists in registers
+            const bool small = n <= 32;
+            int firstR = 0, qPosR = 0;
+            unsigned pbR = 0, peR = 0;
+            if (small) {
+                const unsigned sR = (int)lane < n ? Q.qSeed[qb + lane] : (0x80000000u | lane);  // padding lanes never match
+                const unsigned mm = __match_any_sync(DP_FULL, sR);
+                firstR = __ffs(mm) - 1;
+                if ((int)lane < n) {
+                    qPosR = Q.qPos[qb + lane];
+                    if (firstR == (int)lane) {
+                        pbR = __ldg(I.postOff + sR);
+                        peR = __ldg(I.postOff + sR + 1);
+                    }
+                }
+            }
+            bool identDone = false;
             for (int ci = 0; ci < nc; ci++) {
                 DpChainTask t;
                 t.listOff = 0;
@@ -2045,11 +2142,20 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
                 if ((int)candDistinct[(size_t)ws * candStride + ci] >= thr0) {
                     const unsigned c = candChunk[(size_t)ws * candStride + ci];
                     int nq, ns;
-                    int* rsPos;
-                    unsigned short* rsId;
-                    if (!dp_build_lists(I, Q, qb, n, c, LB, nq, ns, rsPos, rsId) || nq >= 0xffff || ns > 0xffff) {
-                        slow = true;
-                        break;
+                    int* rsPos = nullptr;
+                    unsigned short* rsId = nullptr;
+                    unsigned rqWord = 0, rsWord = 0;
+                    bool inRegs = small && dp_build_lists_small(I, n, c, firstR, qPosR, pbR, peR,
+                                                                reinterpret_cast<unsigned*>(shEnt[wib]), nq, ns, rqWord, rsWord);
+                    if (!inRegs) {
+                        if (!identDone) {
+                            dp_seed_identity(Q, qb, n, LB.qFirst);
+                            identDone = true;
+                        }
+                        if (!dp_build_lists(I, Q, qb, n, c, LB, nq, ns, rsPos, rsId) || nq >= 0xffff || ns > 0xffff) {
+                            slow = true;
+                            break;
+                        }
                     }
                     if (ns >= thr0 && nq >= thr0) {
                         const unsigned need = 2u * (unsigned)nq + (unsigned)ns;
@@ -2059,11 +2165,18 @@ __global__ void __launch_bounds__(128, 8) dp_reduce_kernel(DpIndexDev I, const D
                             break;
                         }
                         unsigned* dst = F.pool + off;
-                        for (int x = lane; x < nq; x += 32) {
+                        if (inRegs) {
+                            if ((int)lane < nq) {
+                                dst[lane] = rqWord;
+                                dst[nq + ns + lane] = 0;  // memo: chain length << 16 | last chunk-side index
+                            }
+                            if ((int)lane < ns) dst[nq + lane] = rsWord;
+                        }
+                        for (int x = lane; !inRegs && x < nq; x += 32) {
                             dst[x] = ((unsigned)LB.rqPos[x] << 16) | LB.rqId[x];
                             dst[nq + ns + x] = 0;  // memo: chain length << 16 | last chunk-side index
                         }
-                        for (int x = lane; x < ns; x += 32) dst[nq + x] = ((unsigned)rsPos[x] << 16) | rsId[x];
+                        for (int x = lane; !inRegs && x < ns; x += 32) dst[nq + x] = ((unsigned)rsPos[x] << 16) | rsId[x];
                         t.listOff = (unsigned)off;
                         t.nq = (unsigned short)nq;
                         t.ns = (unsigned short)ns;
