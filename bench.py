@@ -28,10 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
-# profiles/r1k_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = chain_thread + finish) and
+# profiles/r1k_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = dp_chain_thread_kernel) and
 # profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of config 4)
-TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 50.8e6, "reduce": 95.8e6, "chain": 86.9e6,
-                      "lookup_block": 56.87e9}
+TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 50.8e6, "reduce": 95.8e6, "chain": 81.1e6,
+                      "finish": 5.8e6, "lookup_block": 56.87e9}
 
 K = 11
 REF_LEN = 4_600_000
@@ -404,9 +404,12 @@ def run_ours(args):
     bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
     bytes_chain = 8.0 * agg["chain_cells"] / S
     kern = {}
+    # (iso["ms_chain"] includes Map()'s first decision, dp_finish_round0_kernel: a kernel of its own, listed as such)
+    ms_finish = iso.get("ms_finish", 0.0)
+    bytes_finish = 32.0 * agg["mappings"] / S
     for name, b, ms in (("pack", bytes_pack, iso["ms_pack"]), ("extract", bytes_extract, iso["ms_extract"]),
                         ("lookup", bytes_lookup, iso["ms_lookup"]), ("reduce", bytes_chain, iso["ms_reduce"]),
-                        ("chain", bytes_chain, iso["ms_chain"])):
+                        ("chain", bytes_chain, iso["ms_chain"] - ms_finish), ("finish", bytes_finish, ms_finish)):
         ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
     dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])
@@ -420,9 +423,10 @@ def run_ours(args):
             gather_gbs = None
     # sector traffic of the lookup kernel's posting gathers: every posting run costs whole 32 B sectors
     sector_bytes_lookup = 32.0 * agg["posting_runs"] / S + 32.0 * (4.0 * agg["posting_entries"] / S) / 32.0
-    kname = "dp_%s_kernel" % dominant
-    if dominant == "lookup" and info["num_chunks"] >= 2048:
-        kname = "dp_lookup_block_kernel"
+    kname = {"pack": "dp_pack_windows_kernel", "extract": "dp_extract_kernel", "reduce": "dp_reduce_kernel",
+             "chain": "dp_chain_thread_kernel", "finish": "dp_finish_round0_kernel",
+             "lookup": "dp_lookup_block_kernel" if info["num_chunks"] >= 2048 else
+                       "dp_lookup_small_kernel + dp_lookup_kernel (window strands with more than 32 seeds)"}[dominant]
     roofline = {"kernel": kname, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
                 "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"],
                 "traffic": traffic.get(dominant) if args.workload == "config2" else None,

@@ -1116,6 +1116,7 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
         float ms;
         CK(cudaEventElapsedTime(&ms, W.timers[T_FINISH].a, W.timers[T_FINISH].b));
         W.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
+        W.stats.ms_finish += ms;
     }
     t0 = now_ms();
     std::vector<int> active;
@@ -1237,6 +1238,7 @@ void add_stats(dp_stats& a, const dp_stats& b) {
     a.ms_lookup += b.ms_lookup;
     a.ms_chain += b.ms_chain;
     a.ms_reduce += b.ms_reduce;
+    a.ms_finish += b.ms_finish;
     a.ms_host_logic += b.ms_host_logic;
     a.ms_h2d += b.ms_h2d;
     a.rounds += b.rounds;

@@ -64,6 +64,7 @@ typedef struct dp_stats {
     int64_t h2d_bytes;      /* read bytes that crossed the host->device link (copied, or - when the caller's buffer is
                                page-locked - only the queried windows, moved by the TMA pull kernel) */
     double ms_reduce;       /* list-reduction kernel of the chaining fast path (not included in ms_chain) */
+    double ms_finish;       /* Map()'s first decision on the device (dp_finish_round0_kernel); included in ms_chain */
 } dp_stats;
 
 /*
