@@ -150,20 +150,43 @@ __global__ void __launch_bounds__(1024, 1) dp_extract_kernel(DpIndexDev I, const
                 fm = rm = nValid >= 32 ? 0xffffffffu : ((1u << nValid) - 1u);
             }
             // pass A: exact flags for the filter positives
+            // (two positives per strand per trip: all four table loads are issued before the first is used)
             unsigned hf = 0, hr = 0;
             while (fm | rm) {
+                unsigned wF0 = 0, wF1 = 0, wR0 = 0, wR1 = 0;  // flag words; a missing positive contributes none
+                unsigned sF0 = 0, sF1 = 0, sR0 = 0, sR1 = 0;  // (kmer & 31) | position << 8
                 if (fm) {
-                    unsigned i = __ffs(fm) - 1;
+                    const unsigned i = __ffs(fm) - 1;
                     fm &= fm - 1;
-                    unsigned kmer = dp_fwd_at(B, i) >> kShift;
-                    hf |= ((__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u) << i;
+                    const unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                    wF0 = __ldg(&table[kmer >> 5].x);
+                    sF0 = (kmer & 31u) | (i << 8);
                 }
                 if (rm) {
-                    unsigned i = __ffs(rm) - 1;
+                    const unsigned i = __ffs(rm) - 1;
                     rm &= rm - 1;
-                    unsigned kmer = dp_rc_at(B, i) >> kShift;
-                    hr |= ((__ldg(&table[kmer >> 5].x) >> (kmer & 31)) & 1u) << i;
+                    const unsigned kmer = dp_rc_at(B, i) >> kShift;
+                    wR0 = __ldg(&table[kmer >> 5].x);
+                    sR0 = (kmer & 31u) | (i << 8);
                 }
+                if (fm) {
+                    const unsigned i = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                    wF1 = __ldg(&table[kmer >> 5].x);
+                    sF1 = (kmer & 31u) | (i << 8);
+                }
+                if (rm) {
+                    const unsigned i = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    const unsigned kmer = dp_rc_at(B, i) >> kShift;
+                    wR1 = __ldg(&table[kmer >> 5].x);
+                    sR1 = (kmer & 31u) | (i << 8);
+                }
+                hf |= ((wF0 >> (sF0 & 31u)) & 1u) << (sF0 >> 8);
+                hf |= ((wF1 >> (sF1 & 31u)) & 1u) << (sF1 >> 8);
+                hr |= ((wR0 >> (sR0 & 31u)) & 1u) << (sR0 >> 8);
+                hr |= ((wR1 >> (sR1 & 31u)) & 1u) << (sR1 >> 8);
             }
             mF[(b << 5) + lane] = hf;
             mR[(b << 5) + lane] = hr;
