@@ -930,9 +930,10 @@ __global__ void __launch_bounds__(32 * DP_SMALL_WARPS, 12) dp_lookup_small_kerne
 // is >= the count of each of its chunks, so every chunk over the threshold lies in a group over the threshold).
 //
 //   1. inclusion filter, thread per query seed, block-wide ordered compaction                 (seeds.go:340-346)
-//   2. the runs are cut into items of 128 postings aligned to 16 bytes; a warp takes four items at once, issues its
-//      four 16-byte loads per lane (2 KB per warp in flight), then adds into the group counters with predicated
-//      shared-memory reductions (no return value, no per-posting test or branch: ~6 instructions per posting)
+//   2. the runs are cut into items of 128 postings (32 for indexes with short runs) aligned to 16 bytes; a warp takes
+//      NI = 6 warp-wide loads' worth of items at once, issues its six 16-byte loads per lane (3 KB per warp in flight),
+//      then adds into the group counters with shared-memory reductions (no return value, no per-posting test or
+//      branch — a posting outside its item's range goes to the lane's dummy counter: ~6 instructions per posting)
 //   3. one pass over the counters finds the groups that reached the threshold and blanks the counters (16-byte
 //      loads/stores); with gShift = 0 these are the candidates and their exact counts
 //   4. gShift > 0: for the few groups over the threshold (the true locus; random groups stay far below it) every run
