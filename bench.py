@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 # profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of config 4)
 TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 50.8e6, "reduce": 95.8e6, "chain": 81.1e6,
                       "finish": 5.8e6, "lookup_block": 56.87e9}
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures (config 2 is L2-resident: SURVEY 8d asks for
+# issue utilisation beside the HBM fraction there); lookup = dp_lookup_small_kernel (profiles/r1q_ncu_lookup_small.txt)
+ISSUE_ACTIVE_PCT = {"pack": 55.5, "extract": 61.2, "lookup": 68.1, "reduce": 47.1, "chain": 37.8, "finish": 5.9,
+                    "lookup_block": 48.2}
 
 K = 11
 REF_LEN = 4_600_000
@@ -437,6 +441,7 @@ def run_ours(args):
                         "kernel family on its launching stream over one step run on a single lane (kernels not "
                         "overlapping; the timed `value` steps run 6 lanes). traffic = ncu dram bytes per launch of a "
                         "65536-read sub-batch",
+                "issue_active_pct_ncu": ISSUE_ACTIVE_PCT if args.workload == "config2" else None,
                 "hbm_gather_ceiling_GBs": gather_gbs,
                 "lookup_vs_gather_ceiling": (sector_bytes_lookup / (kern["lookup"]["ms_per_step"] * 1e-3) / 1e9 / gather_gbs
                                              if gather_gbs and kern["lookup"]["ms_per_step"] > 0 else None),
