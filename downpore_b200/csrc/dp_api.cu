@@ -967,6 +967,9 @@ void download_windows(Lane& W, size_t nWin) {
     lane_sync(W);
     collect_stage_times(W);
     size_t total = (size_t)cur[CUR_OUT];
+    // (the kernels' bump cursor runs past the buffer when a window had more mappings than the device keeps: they flag
+    // it and write nothing out of bounds; say so instead of failing in the copy below)
+    if (total > W.outMaps.cap) throw std::runtime_error("device capacity exceeded: mappings-per-window");
     W.hOutMaps.reserve(total + 1);
     if (total) {
         CK(cudaMemcpyAsync(W.hOutMaps.p, W.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
