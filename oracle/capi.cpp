@@ -143,6 +143,28 @@ long long dpo_get_shared_ids(void** sets, long long n, long long minCount, int f
     DPO_CATCH(-1)
 }
 
+// ----- overlap path groundwork: a bare SeedIndex and AddSeeds (seeds.go:62-156) ---------------------------------
+void* dpo_seedindex_new(int k) {
+    DPO_TRY SeedIndex* g = new SeedIndex();
+    NewSeedIndex(*g, k);
+    return g;
+    DPO_CATCH(nullptr)
+}
+void dpo_seedindex_free(void* h) { delete (SeedIndex*)h; }
+int dpo_seedindex_add_seeds(void* h, const char* ascii, long long n, long long minSeeds, const double* ranks,
+                            const unsigned char* quality) {
+    DPO_TRY PackedSeq seq = NewPackedSequence(0, std::string(ascii, (size_t)n), nullptr);
+    AddSeeds(*(SeedIndex*)h, seq, minSeeds, ranks, quality);
+    return 0;
+    DPO_CATCH(-1)
+}
+// seed k-mers in registration order (seedMap)
+long long dpo_seedindex_seeds(void* h, long long* out, long long cap) {
+    const SeedIndex& g = *(const SeedIndex*)h;
+    for (long long i = 0; i < g.size && i < cap; i++) out[i] = g.seedMap[(size_t)i];
+    return g.size;
+}
+
 // ----- k-mer statistics ---------------------------------------------------------
 // values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
 int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {

@@ -168,6 +168,7 @@ struct SeedIndex {
 void NewSeedIndex(SeedIndex& g, gint k);                                          // seeds.go:23-31
 SeedSequence NewSeedSequence(const SeedIndex& g, const PackedSeq& seq, Counters* c);  // seeds.go:33-50
 void AddSingleSeeds(SeedIndex& g, const PackedSeq& seq, gint seedRate, const double* ranks);  // seeds.go:160-200
+void AddSeeds(SeedIndex& g, const PackedSeq& seq, gint minSeeds, const double* kmerRanks, const uint8_t* quality);  // seeds.go:62-156 (overlap path)
 void AddSequence(SeedIndex& g, SeedSequence&& seq);                               // seeds.go:272-290
 void IndexSequences(SeedIndex& g);                                                // seeds.go:292-305,372-384
 std::vector<uint64_t> Matches(const SeedIndex& g, const SeedSequence& query, double hitFraction, Counters* c);  // :335-353

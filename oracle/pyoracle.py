@@ -285,6 +285,42 @@ def get_shared_ids(sets, min_count, fast):
     return out[:n].copy()
 
 
+class SeedIndex:
+    """A bare seeds.SeedIndex with AddSeeds (seeds/seeds.go:62-156): groundwork for the overlap path, not used by map."""
+
+    def __init__(self, k):
+        lib().dpo_seedindex_new.restype = c_vp
+        self.h = lib().dpo_seedindex_new(int(k))
+        self.k = int(k)
+        if not self.h:
+            raise RuntimeError(_err())
+
+    def __del__(self):
+        try:
+            lib().dpo_seedindex_free(c_vp(self.h))
+        except Exception:
+            pass
+
+    def add_seeds(self, seq, min_seeds, ranks, quality=None):
+        a = _u8(seq)
+        ranks = np.ascontiguousarray(ranks, dtype=np.float64)
+        assert ranks.size == 4 ** self.k
+        q = None if quality is None else np.ascontiguousarray(quality, dtype=np.uint8)
+        assert q is None or q.size == a.size
+        rc = lib().dpo_seedindex_add_seeds(c_vp(self.h), a.ctypes.data_as(ctypes.c_char_p), ctypes.c_longlong(a.size),
+                                           ctypes.c_longlong(int(min_seeds)), ranks.ctypes.data_as(c_vp),
+                                           None if q is None else q.ctypes.data_as(c_vp))
+        if rc != 0:
+            raise RuntimeError(_err())
+
+    def seeds(self):
+        lib().dpo_seedindex_seeds.restype = ctypes.c_longlong
+        n = lib().dpo_seedindex_seeds(c_vp(self.h), None, ctypes.c_longlong(0))
+        out = np.empty(max(int(n), 1), dtype=np.int64)
+        lib().dpo_seedindex_seeds(c_vp(self.h), out.ctypes.data_as(c_vp), ctypes.c_longlong(int(n)))
+        return out[: int(n)].copy()
+
+
 def kmer_values(ref, k):
     """values[] of commands/map.go:45-71 for a single-record reference (canonical tie order, Q10)."""
     a = _u8(ref)

@@ -392,6 +392,63 @@ void AddSingleSeeds(SeedIndex& g, const PackedSeq& seq, gint seedRate, const dou
     }
 }
 
+// seeds.go:62-156 — batch seed selection of the overlap path (round-2 groundwork: not used by `map`).
+// `quality` is seq.Quality() (nil for FASTA). The reference computes CountKmers first and then discards the result
+// (`count = 0`, seeds.go:76), so every call tops the index up by `minSeeds` k-mers: the best-valued k-mer of each
+// k-block that contains no seed yet, blocks 3k apart. Quirks kept: the k-mer at position 0 is never a candidate; slots
+// of topN that no block filled stay 0, so k-mer 0 (and its reverse complement) are registered as seeds.
+void AddSeeds(SeedIndex& g, const PackedSeq& seq, gint minSeeds, const double* kmerRanks, const uint8_t* quality) {
+    gint k = g.seedSize;
+    gint mask = 0;
+    for (gint i = 0; i < k; i++) mask = (mask << 2) | 3;
+    gint count = 0;
+    if (count < minSeeds) {
+        std::vector<uint64_t> topN((size_t)(minSeeds - count), 0);
+        std::vector<double> topNValues((size_t)(minSeeds - count), 0.0);
+        gint kmer = KmerAt(seq, 0, k);
+        gint nextIndex = k;
+        while (nextIndex < seq.Len() - k) {
+            bool reset = false;
+            double bestValue = 0.0;
+            gint bestSeed = 0;
+            for (gint i = 0; nextIndex < seq.Len() && i < k; i++) {
+                kmer = NextKmer(seq, kmer, mask, nextIndex);
+                nextIndex++;
+                if (g.kmers[(size_t)kmer]) {
+                    reset = true;
+                    break;
+                }
+                double value = kmerRanks[kmer];
+                if (quality) value *= (double)quality[nextIndex - k / 2];
+                if (value > bestValue) {
+                    bestValue = value;
+                    bestSeed = kmer;
+                }
+            }
+            if (!reset) {
+                size_t n = 0;
+                for (; n < topNValues.size() && topNValues[n] < bestValue; n++) {
+                    if (n > 0) {
+                        topNValues[n - 1] = topNValues[n];
+                        topN[n - 1] = topN[n];
+                    }
+                }
+                if (n > 0) {
+                    topNValues[n - 1] = bestValue;
+                    topN[n - 1] = (uint64_t)bestSeed;
+                }
+            }
+            nextIndex += k;
+            if (nextIndex < seq.Len() - k) kmer = KmerAt(seq, nextIndex, k);
+            nextIndex += k;
+        }
+        for (uint64_t km : topN) {  // the body of the lock (seeds.go:131-154)
+            register_seed(g, (gint)km);
+            register_seed(g, (gint)ReverseComplementKmer(km, (uint64_t)k));
+        }
+    }
+}
+
 void AddSequence(SeedIndex& g, SeedSequence&& seq) {  // seeds.go:272-290
     gint maxSeed = 0;
     for (size_t i = 1; i < seq.segments.size(); i += 2) {
