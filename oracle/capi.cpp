@@ -165,6 +165,54 @@ long long dpo_seedindex_seeds(void* h, long long* out, long long cap) {
     return g.size;
 }
 
+// NewSeedSequence (seeds.go:33-50) of a sequence against the bare index: segments -> out (returns their number, or the
+// needed size if cap is too small); fields = {length, offset, inset}
+long long dpo_seedindex_seed_sequence(void* h, const char* ascii, long long n, long long* out, long long cap, long long* fields) {
+    DPO_TRY PackedSeq seq = NewPackedSequence(0, std::string(ascii, (size_t)n), nullptr);
+    SeedSequence s = NewSeedSequence(*(SeedIndex*)h, seq, nullptr);
+    for (size_t i = 0; i < s.segments.size() && (long long)i < cap; i++) out[i] = s.segments[i];
+    if (fields) {
+        fields[0] = s.length;
+        fields[1] = s.offset;
+        fields[2] = s.inset;
+    }
+    return (long long)s.segments.size();
+    DPO_CATCH(-1)
+}
+// SeedSequence.ReverseComplement (seeds/sequence.go:134-159) on raw segments
+long long dpo_seedindex_rc(void* h, const long long* segments, long long nseg, long long* out) {
+    DPO_TRY SeedSequence s;
+    s.segments.assign(segments, segments + nseg);
+    const SeedIndex& g = *(const SeedIndex*)h;
+    SeedSequence r = ReverseComplementSeq(s, g.seedSize, g);
+    for (long long i = 0; i < nseg; i++) out[i] = r.segments[(size_t)i];
+    return nseg;
+    DPO_CATCH(-1)
+}
+// chunkWorker (overlap/overlap.go:253-318) for one seed sequence. out: per piece {nSegments, length, offset, inset,
+// segments...}; returns the number of values written (or needed), pieces in *nPieces
+long long dpo_chunk_seed_sequence(const long long* segments, long long nseg, long long length, long long chunkSize,
+                                  long long minSeeds, long long overlap, long long k, long long* out, long long cap,
+                                  long long* nPieces) {
+    DPO_TRY SeedSequence s;
+    s.segments.assign(segments, segments + nseg);
+    s.length = length;
+    std::vector<SeedSequence> pieces = ChunkSeedSequence(s, chunkSize, minSeeds, overlap, k);
+    long long w = 0;
+    for (const SeedSequence& p : pieces) {
+        const long long vals[4] = {(long long)p.segments.size(), p.length, p.offset, p.inset};
+        for (int i = 0; i < 4; i++, w++)
+            if (w < cap) out[w] = vals[i];
+        for (gint v : p.segments) {
+            if (w < cap) out[w] = v;
+            w++;
+        }
+    }
+    if (nPieces) *nPieces = (long long)pieces.size();
+    return w;
+    DPO_CATCH(-1)
+}
+
 // ----- k-mer statistics ---------------------------------------------------------
 // values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
 int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {

@@ -169,6 +169,9 @@ void NewSeedIndex(SeedIndex& g, gint k);                                        
 SeedSequence NewSeedSequence(const SeedIndex& g, const PackedSeq& seq, Counters* c);  // seeds.go:33-50
 void AddSingleSeeds(SeedIndex& g, const PackedSeq& seq, gint seedRate, const double* ranks);  // seeds.go:160-200
 void AddSeeds(SeedIndex& g, const PackedSeq& seq, gint minSeeds, const double* kmerRanks, const uint8_t* quality);  // seeds.go:62-156 (overlap path)
+SeedSequence ReverseComplementSeq(const SeedSequence& s, gint k, const SeedIndex& g);  // seeds/sequence.go:134-159 (overlap path)
+SeedSequence SubSequenceSeeds(const SeedSequence& s, gint start, gint end, gint length, gint offset, gint inset);  // :46-50
+std::vector<SeedSequence> ChunkSeedSequence(const SeedSequence& s, gint chunkSize, gint minSeeds, gint overlap, gint k);  // overlap/overlap.go:253-318
 void AddSequence(SeedIndex& g, SeedSequence&& seq);                               // seeds.go:272-290
 void IndexSequences(SeedIndex& g);                                                // seeds.go:292-305,372-384
 std::vector<uint64_t> Matches(const SeedIndex& g, const SeedSequence& query, double hitFraction, Counters* c);  // :335-353

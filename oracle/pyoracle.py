@@ -313,12 +313,56 @@ class SeedIndex:
         if rc != 0:
             raise RuntimeError(_err())
 
+    def seed_sequence(self, seq):
+        """NewSeedSequence (seeds.go:33-50): (segments [gap, seed, gap, ..., gap], length, offset, inset)."""
+        a = _u8(seq)
+        lib().dpo_seedindex_seed_sequence.restype = ctypes.c_longlong
+        cap = 2 * a.size + 3
+        out = np.empty(cap, dtype=np.int64)
+        f = np.zeros(3, dtype=np.int64)
+        n = lib().dpo_seedindex_seed_sequence(c_vp(self.h), a.ctypes.data_as(ctypes.c_char_p), ctypes.c_longlong(a.size),
+                                              out.ctypes.data_as(c_vp), ctypes.c_longlong(cap), f.ctypes.data_as(c_vp))
+        if n < 0:
+            raise RuntimeError(_err())
+        return out[: int(n)].copy(), int(f[0]), int(f[1]), int(f[2])
+
+    def reverse_complement(self, segments):
+        """SeedSequence.ReverseComplement (seeds/sequence.go:134-159) on raw segments."""
+        seg = np.ascontiguousarray(segments, dtype=np.int64)
+        out = np.empty_like(seg)
+        lib().dpo_seedindex_rc.restype = ctypes.c_longlong
+        if lib().dpo_seedindex_rc(c_vp(self.h), seg.ctypes.data_as(c_vp), ctypes.c_longlong(seg.size), out.ctypes.data_as(c_vp)) < 0:
+            raise RuntimeError(_err())
+        return out
+
     def seeds(self):
         lib().dpo_seedindex_seeds.restype = ctypes.c_longlong
         n = lib().dpo_seedindex_seeds(c_vp(self.h), None, ctypes.c_longlong(0))
         out = np.empty(max(int(n), 1), dtype=np.int64)
         lib().dpo_seedindex_seeds(c_vp(self.h), out.ctypes.data_as(c_vp), ctypes.c_longlong(int(n)))
         return out[: int(n)].copy()
+
+
+def chunk_seed_sequence(segments, length, chunk_size, min_seeds, overlap, k):
+    """chunkWorker (overlap/overlap.go:253-318) for one seed sequence: [(segments, length, offset, inset), ...]."""
+    seg = np.ascontiguousarray(segments, dtype=np.int64)
+    lib().dpo_chunk_seed_sequence.restype = ctypes.c_longlong
+    cap = 8 * seg.size + 64
+    out = np.empty(cap, dtype=np.int64)
+    npieces = ctypes.c_longlong(0)
+    w = lib().dpo_chunk_seed_sequence(seg.ctypes.data_as(c_vp), ctypes.c_longlong(seg.size), ctypes.c_longlong(int(length)),
+                                      ctypes.c_longlong(int(chunk_size)), ctypes.c_longlong(int(min_seeds)),
+                                      ctypes.c_longlong(int(overlap)), ctypes.c_longlong(int(k)), out.ctypes.data_as(c_vp),
+                                      ctypes.c_longlong(cap), ctypes.byref(npieces))
+    if w < 0:
+        raise RuntimeError(_err())
+    assert w <= cap
+    pieces, at = [], 0
+    for _ in range(npieces.value):
+        ns, ln, off, ins = (int(x) for x in out[at:at + 4])
+        pieces.append((out[at + 4:at + 4 + ns].copy(), ln, off, ins))
+        at += 4 + ns
+    return pieces
 
 
 def kmer_values(ref, k):

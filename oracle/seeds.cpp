@@ -449,6 +449,104 @@ void AddSeeds(SeedIndex& g, const PackedSeq& seq, gint minSeeds, const double* k
     }
 }
 
+// seeds/sequence.go:134-159 — the reverse-complement query of the overlap path: gaps reversed, every seed replaced by
+// the seed id of its reverse-complement k-mer (kmerMap is 0 for a k-mer that is no seed: AddSeeds registers both
+// strands, so that does not happen there). offset/inset stay those of the forward read.
+SeedSequence ReverseComplementSeq(const SeedSequence& s, gint k, const SeedIndex& g) {
+    size_t n = s.segments.size();
+    SeedSequence r;
+    r.segments.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        gint v = s.segments[i];
+        if ((i & 1) == 0) {
+            r.segments[n - 1 - i] = v;
+        } else {
+            uint64_t rc = ReverseComplementKmer((uint64_t)g.seedMap[(size_t)v], (uint64_t)k);
+            r.segments[n - 1 - i] = (gint)g.kmerMap[(size_t)rc];
+        }
+    }
+    r.id = s.id;
+    r.length = s.length;
+    r.offset = s.offset;
+    r.inset = s.inset;
+    r.rc = !s.rc;
+    return r;
+}
+
+// seeds/sequence.go:46-50 (the Go slice aliases the parent's segments; nothing on this path writes through it)
+SeedSequence SubSequenceSeeds(const SeedSequence& s, gint start, gint end, gint length, gint offset, gint inset) {
+    SeedSequence r;
+    r.segments.assign(s.segments.begin() + start * 2, s.segments.begin() + end * 2 + 3);
+    r.length = length;
+    r.offset = offset;
+    r.inset = inset;
+    r.rc = s.rc;
+    r.id = s.id;
+    return r;
+}
+
+static gint GetNextSeedOffset(const SeedSequence& s, gint index, gint k) {  // sequence.go:1278-1280
+    return s.segments[(size_t)(index * 2 + 2)] + k;
+}
+
+// overlap/overlap.go:253-318 (chunkWorker, one sequence): the pieces handed to index.AddSequence, in order. A read's
+// seed sequence is cut in SEED space: up to 100 seeds or chunkSize bases per piece, stepping back 5 seeds or overlap/2
+// bases between pieces; a piece with fewer than minSeeds seeds is dropped; from 150 seeds before the end on, one last
+// piece runs to the end.
+std::vector<SeedSequence> ChunkSeedSequence(const SeedSequence& s, gint chunkSize, gint minSeeds, gint overlap, gint k) {
+    std::vector<SeedSequence> out;
+    gint numChunks = s.Len() / chunkSize + 1;
+    if (numChunks == 1 || s.GetNumSeeds() < minSeeds * 3) {
+        if (s.GetNumSeeds() >= minSeeds) out.push_back(s);
+        return out;
+    }
+    gint prevSeedIndex = 0;
+    gint totalOffset = GetSeedOffset(s, 0, k);
+    gint lengthInBases = 0;
+    for (;;) {
+        gint seedCount = 0;
+        if (prevSeedIndex >= s.GetNumSeeds() - 150) {
+            if (prevSeedIndex == 0) {
+                out.push_back(s);
+            } else {
+                gint newFirstGap = GetNextSeedOffset(s, prevSeedIndex - 1, k) - k;
+                lengthInBases += GetSeedOffsetFromEnd(s, prevSeedIndex, k) + k + newFirstGap;
+                out.push_back(SubSequenceSeeds(s, prevSeedIndex, s.GetNumSeeds() - 1, lengthInBases, totalOffset - newFirstGap, 0));
+            }
+            break;
+        }
+        for (; lengthInBases < chunkSize && seedCount < 100 && prevSeedIndex + seedCount < s.GetNumSeeds(); seedCount++)
+            lengthInBases += GetNextSeedOffset(s, prevSeedIndex + seedCount, k);
+        if (seedCount >= minSeeds) {
+            gint newFirstGap = GetNextSeedOffset(s, prevSeedIndex - 1, k) - k;
+            lengthInBases += newFirstGap;
+            out.push_back(SubSequenceSeeds(s, prevSeedIndex, prevSeedIndex + seedCount - 1, lengthInBases, totalOffset - newFirstGap,
+                                           s.length - totalOffset - lengthInBases + newFirstGap));
+            totalOffset += lengthInBases - newFirstGap;
+            lengthInBases = 0;
+            prevSeedIndex += seedCount;
+            if (prevSeedIndex >= s.GetNumSeeds()) break;
+            for (seedCount = 0; seedCount < 5 && lengthInBases < overlap / 2 && prevSeedIndex > 0; seedCount++) {
+                prevSeedIndex--;
+                gint step = GetNextSeedOffset(s, prevSeedIndex, k);
+                lengthInBases += step;
+                totalOffset -= step;
+            }
+            lengthInBases = 0;
+        } else {
+            prevSeedIndex += seedCount;
+            for (seedCount = 0; lengthInBases < overlap / 2 && prevSeedIndex > 0; seedCount++) {
+                prevSeedIndex--;
+                gint step = GetNextSeedOffset(s, prevSeedIndex, k);
+                lengthInBases += step;
+                totalOffset -= step;
+            }
+            lengthInBases = 0;
+        }
+    }
+    return out;
+}
+
 void AddSequence(SeedIndex& g, SeedSequence&& seq) {  // seeds.go:272-290
     gint maxSeed = 0;
     for (size_t i = 1; i < seq.segments.size(); i += 2) {
