@@ -213,6 +213,39 @@ long long dpo_chunk_seed_sequence(const long long* segments, long long nseg, lon
     DPO_CATCH(-1)
 }
 
+// seedAligner.PairwiseAlignments (seeds/alignment.go:426-616) as matchWorker calls it (overlap/overlap.go:346-363):
+// aSet / bSet = the seeds of a / b; a fresh aligner of NewSeedAligner(maxLength). out: per match {length, MatchA...,
+// MatchB...} in the order returned; returns values written (or needed), matches in *nMatches. -1 + error text when the
+// reference would panic.
+long long dpo_pairwise_alignments(const long long* aSeg, long long na, const long long* bSeg, long long nb,
+                                  long long minMatches, long long k, long long maxLength, long long* out, long long cap,
+                                  long long* nMatches) {
+    DPO_TRY SeedSequence a, b;
+    a.segments.assign(aSeg, aSeg + na);
+    b.segments.assign(bSeg, bSeg + nb);
+    IntSet aSet = NewIntSet(), bSet = NewIntSet();
+    for (long long i = 1; i < na; i += 2) Add(aSet, (uint64_t)aSeg[i]);
+    for (long long i = 1; i < nb; i += 2) Add(bSet, (uint64_t)bSeg[i]);
+    SeedAligner al = NewSeedAligner(maxLength);
+    std::vector<SeedMatch> ms = PairwiseAlignments(al, a, b, aSet, bSet, minMatches, k);
+    long long w = 0;
+    for (const SeedMatch& m : ms) {
+        if (w < cap) out[w] = (long long)m.MatchA.size();
+        w++;
+        for (gint v : m.MatchA) {
+            if (w < cap) out[w] = v;
+            w++;
+        }
+        for (gint v : m.MatchB) {
+            if (w < cap) out[w] = v;
+            w++;
+        }
+    }
+    if (nMatches) *nMatches = (long long)ms.size();
+    return w;
+    DPO_CATCH(-1)
+}
+
 // ----- k-mer statistics ---------------------------------------------------------
 // values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
 int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {

@@ -172,6 +172,24 @@ void AddSeeds(SeedIndex& g, const PackedSeq& seq, gint minSeeds, const double* k
 SeedSequence ReverseComplementSeq(const SeedSequence& s, gint k, const SeedIndex& g);  // seeds/sequence.go:134-159 (overlap path)
 SeedSequence SubSequenceSeeds(const SeedSequence& s, gint start, gint end, gint length, gint offset, gint inset);  // :46-50
 std::vector<SeedSequence> ChunkSeedSequence(const SeedSequence& s, gint chunkSize, gint minSeeds, gint overlap, gint k);  // overlap/overlap.go:253-318
+// seeds/alignment.go:274-616 (overlap path): pool of pair states addressed by index (-1 = nil)
+struct PairState {
+    gint aPos = 0, bPos = 0, aGap = 0, bGap = 0, aGapIndex = 0, length = 0;
+    int prev = -1;
+    gint stackIndex = 0;
+};
+struct SeedAligner {
+    std::vector<PairState> stackPool;
+    std::vector<int> statesStack;
+    gint nextState = 0;
+    std::vector<gint> reduced, aMapping;
+    std::vector<int> open, initials, results;
+};
+SeedAligner NewSeedAligner(gint maxLength);                                       // alignment.go:298-306
+gint gapRangeMin(gint gap, gint k);                                               // :411-424
+gint gapRangeMax(gint gap, gint k);
+std::vector<SeedMatch> PairwiseAlignments(SeedAligner& al, const SeedSequence& a, const SeedSequence& b, const IntSet& aSet,
+                                          const IntSet& bSet, gint minMatches, gint k);  // :426-616
 void AddSequence(SeedIndex& g, SeedSequence&& seq);                               // seeds.go:272-290
 void IndexSequences(SeedIndex& g);                                                // seeds.go:292-305,372-384
 std::vector<uint64_t> Matches(const SeedIndex& g, const SeedSequence& query, double hitFraction, Counters* c);  // :335-353

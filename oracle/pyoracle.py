@@ -365,6 +365,29 @@ def chunk_seed_sequence(segments, length, chunk_size, min_seeds, overlap, k):
     return pieces
 
 
+def pairwise_alignments(a_segments, b_segments, min_matches, k, max_length=500):
+    """seedAligner.PairwiseAlignments (seeds/alignment.go:426-616) with aSet/bSet = the seeds of a/b:
+    [(MatchA, MatchB), ...] in the order returned. Raises RuntimeError where the reference would panic."""
+    a = np.ascontiguousarray(a_segments, dtype=np.int64)
+    b = np.ascontiguousarray(b_segments, dtype=np.int64)
+    lib().dpo_pairwise_alignments.restype = ctypes.c_longlong
+    cap = 1 << 20
+    out = np.empty(cap, dtype=np.int64)
+    nm = ctypes.c_longlong(0)
+    w = lib().dpo_pairwise_alignments(a.ctypes.data_as(c_vp), ctypes.c_longlong(a.size), b.ctypes.data_as(c_vp),
+                                      ctypes.c_longlong(b.size), ctypes.c_longlong(int(min_matches)), ctypes.c_longlong(int(k)),
+                                      ctypes.c_longlong(int(max_length)), out.ctypes.data_as(c_vp), ctypes.c_longlong(cap),
+                                      ctypes.byref(nm))
+    if w < 0:
+        raise RuntimeError(_err())
+    res, at = [], 0
+    for _ in range(nm.value):
+        n = int(out[at])
+        res.append((out[at + 1:at + 1 + n].copy(), out[at + 1 + n:at + 1 + 2 * n].copy()))
+        at += 1 + 2 * n
+    return res
+
+
 def kmer_values(ref, k):
     """values[] of commands/map.go:45-71 for a single-record reference (canonical tie order, Q10)."""
     a = _u8(ref)
