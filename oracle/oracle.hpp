@@ -7,6 +7,10 @@
 // so that their observable quirks are reproduced
 // and not "fixed".
 //
+// Round-2 groundwork for the `overlap` path also lives here and is used by tests only: AddSeeds,
+// SeedSequence.ReverseComplement, chunkWorker's seed-space chunking (seeds.cpp) and seedAligner.PairwiseAlignments
+// (alignment.cpp); each is cross-checked against a second restatement in tests/test_oracle_overlap_*.py.
+//
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may build, load or call anything in this directory.
 //
