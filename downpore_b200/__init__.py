@@ -36,7 +36,8 @@ class Stats(ctypes.Structure):
                 ("ms_h2d", ctypes.c_double), ("rounds", c_i64), ("windows", c_i64), ("kmer_lookups", c_i64),
                 ("query_seeds", c_i64), ("posting_runs", c_i64), ("posting_entries", c_i64), ("candidates", c_i64),
                 ("chain_cells", c_i64), ("mappings", c_i64), ("kernel_launches", c_i64), ("bases", c_i64),
-                ("h2d_bytes", c_i64), ("ms_reduce", ctypes.c_double), ("ms_finish", ctypes.c_double)]
+                ("h2d_bytes", c_i64), ("ms_reduce", ctypes.c_double), ("ms_finish", ctypes.c_double),
+                ("retries", c_i64), ("short_reads", c_i64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

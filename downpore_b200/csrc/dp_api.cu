@@ -95,8 +95,21 @@ double now_ms() {
 
 // Per-lane workspace: one stream plus every buffer a sub-batch needs. Two lanes let the host work of one sub-batch
 // (result assembly, the rare replay rounds) overlap the kernels of the next.
+// Capacities of one launch of the window kernels. None is a limit of the library: a launch that runs out of one flags
+// it (DpCounters.overflow), the host grows it and recomputes the affected reads (map_range below) — the reference keeps
+// every hit (mapping/mapping.go:504 sizes `results` by the candidate count, :518-552 append without bound).
+struct Caps {
+    int outStride = 16;         // window results kept per window ON AVERAGE over a launch (one bump-allocated pool)
+    int resultCap = 128;        // mappings of one window before sort/dedupe (general chain kernel)
+    int chainCap = 64;          // chains kept for one candidate (general chain kernel)
+    unsigned candStride = 1024; // candidate chunks per window strand (min(C, .))
+};
+const int kCapMax = 1 << 20;
+
 struct Lane {
     cudaStream_t stream = nullptr;
+    Caps caps;
+    HBuf<DpCounters> hCtr;  // counters + overflow flags of the current attempt, as of its last synchronise
     cudaEvent_t evSync = nullptr;  // cudaEventBlockingSync: the lane's thread sleeps instead of spinning (sync_mode_blocking)
     DBuf<unsigned char> dAscii, dStage;
     DBuf<long long> dSeqOff, dWordOff, dWordsNeeded;
@@ -181,8 +194,6 @@ struct dp_mapper {
     size_t indexBytes = 0;
     std::vector<std::unique_ptr<Lane>> lanes;
     dp_stats stats{};
-    int outStride = 16, resultCap = 128, chainCap = 64;
-    bool attrsSet = false;
 
     ~dp_mapper() {
         lanes.clear();
@@ -598,13 +609,14 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.qPos.reserve(seedEntries + 64);
     W.cursor.reserve(4);
     W.dCtr.reserve(1);
-    W.candStride = (int)std::min<unsigned>(I.numChunks, 1024u);
+    W.candStride = (int)std::min<unsigned>(I.numChunks, W.caps.candStride);
     W.candN.reserve(2 * nWin);
     W.candChunk.reserve(2 * nWin * (size_t)W.candStride);
     W.candDistinct.reserve(2 * nWin * (size_t)W.candStride);
     W.outN.reserve(nWin);
     W.outOff.reserve(nWin);
-    W.outMaps.reserve(nWin * (size_t)M.outStride);
+    W.outMaps.reserve(nWin * (size_t)W.caps.outStride);
+    W.hCtr.reserve(1);
     // per-warp scratch
     const int qStride = I.maxWindow + 8;
     W.extractWarps = M.smCount * 8 * 8;
@@ -613,7 +625,11 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.lookupWarps = LP.use ? M.smCount * 4 * 2 : M.smCount * 4 * 8;
     W.lbDefer.reserve(2 * nWin);
     W.lbWork.reserve(4);
-    W.chainWarps = M.smCount * 4 * 8;
+    {   // the general chain kernel's per-warp scratch grows with the capacities: fewer warps then (2 GB of scratch)
+        const size_t perWarp = (size_t)W.caps.resultCap * sizeof(DpMappingDev) + (size_t)W.caps.chainCap * 6 * sizeof(int);
+        const size_t fit = ((size_t)2 << 30) / perWarp;
+        W.chainWarps = (int)std::max<size_t>(128, std::min<size_t>((size_t)M.smCount * 4 * 8, fit / 4 * 4));
+    }
     size_t lw = (size_t)W.lookupWarps;
     W.lsSeed.reserve(lw * qStride);
     W.lsOff.reserve(lw * qStride);
@@ -644,8 +660,8 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntri
     W.csEnt.reserve(cw * sStride);
     W.csRsPos.reserve(cw * sStride);
     W.csRsId.reserve(cw * sStride);
-    W.csChains.reserve(cw * M.chainCap * 6);
-    W.csResults.reserve(cw * M.resultCap);
+    W.csChains.reserve(cw * W.caps.chainCap * 6);
+    W.csResults.reserve(cw * W.caps.resultCap);
     // fast chain path: ~1.5 candidates and ~40 list entries per window on ONT-like reads; whatever does not fit is
     // handed back to the general kernel, so these sizes are a speed knob, not a limit
     W.fcTaskCap = nWin * 8 + 1024;
@@ -673,15 +689,6 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
     // compute kernels leave part of every SM free while another lane's pull kernel reads host memory (measured with
     // the zero-copy pack kernel; with the TMA pull it makes no measurable difference; DP_HEADROOM=0/1 overrides)
     const bool headroom = W.curAsciiIsHost && env_int("DP_HEADROOM", 1) != 0;
-    if (!M.attrsSet) {
-        CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CK(cudaFuncSetAttribute(dp_lookup_block_kernel<128, 8, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        M.attrsSet = true;
-    }
     {   // pack exactly the queried windows (out of pinned host memory when that is where the reads live)
         // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
         // compute kernels stay resident beside it
@@ -853,12 +860,13 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         S.results = W.csResults.p;
         S.qStride = qStride;
         S.sStride = (int)I.maxChunkSeeds + 8;
-        S.chainCap = M.chainCap;
-        S.resultCap = M.resultCap;
+        S.chainCap = W.caps.chainCap;
+        S.resultCap = W.caps.resultCap;
         int warpsPerBlock = 4;
         int blocks = (int)std::min<size_t>((nWin + warpsPerBlock - 1) / warpsPerBlock,
                                            (size_t)M.smCount * (headroom ? 4 : 6));
-        const unsigned long long outCap = (unsigned long long)nWin * M.outStride;
+        blocks = std::min(blocks, W.chainWarps / warpsPerBlock);  // (the scratch is sized for chainWarps warps)
+        const unsigned long long outCap = (unsigned long long)nWin * W.caps.outStride;
         const bool fast = !(getenv("DP_CHAIN_FAST") && atoi(getenv("DP_CHAIN_FAST")) == 0);
         CK(cudaEventRecord(W.timers[T_CHAIN].a, st));
         W.reduceTimed = fast;
@@ -955,33 +963,36 @@ void lane_sync(Lane& W) {
     }
 }
 
-// Copies the window results of the last launch_windows() to the pinned host mirrors (hOutN, hOutOff, hOutMaps).
-void download_windows(Lane& W, size_t nWin) {
+// Copies the window results of the last launch_windows() to the pinned host mirrors (hOutN, hOutOff, hOutMaps) together
+// with the attempt's counters. Returns the launch's overflow bits: non-zero means the results are incomplete and the
+// caller must recompute with more room (nothing is copied then).
+unsigned download_windows(Lane& W, size_t nWin) {
     cudaStream_t st = W.stream;
     unsigned long long cur[4];
     CK(cudaMemcpyAsync(cur, W.cursor.p, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hCtr.p, W.dCtr.p, sizeof(DpCounters), cudaMemcpyDeviceToHost, st));
     W.hOutN.reserve(nWin);
     W.hOutOff.reserve(nWin);
     CK(cudaMemcpyAsync(W.hOutN.p, W.outN.p, nWin * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hOutOff.p, W.outOff.p, nWin * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     lane_sync(W);
     collect_stage_times(W);
+    if (W.hCtr.p->overflow) return W.hCtr.p->overflow;
     size_t total = (size_t)cur[CUR_OUT];
-    // (the kernels' bump cursor runs past the buffer when a window had more mappings than the device keeps: they flag
-    // it and write nothing out of bounds; say so instead of failing in the copy below)
-    if (total > W.outMaps.cap) throw std::runtime_error("device capacity exceeded: mappings-per-window");
+    if (total > W.outMaps.cap) throw std::runtime_error("internal error: window result pool overrun without a flag");
     W.hOutMaps.reserve(total + 1);
     if (total) {
         CK(cudaMemcpyAsync(W.hOutMaps.p, W.outMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
         lane_sync(W);
     }
     W.hOutTotal = total;
+    return 0;
 }
 
-// Host-supplied window list (rounds after the first, and the test probe).
-void run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
-                 const int* dReadLen) {
-    if (nWin == 0) return;
+// Host-supplied window list (rounds after the first, and the test probe). Returns the overflow bits (see above).
+unsigned run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, const unsigned* dWords, const long long* dWordOff,
+                     const int* dReadLen) {
+    if (nWin == 0) return 0;
     size_t seedEntries = 0;
     for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
     ensure_window_capacity(M, W, nWin, seedEntries);
@@ -989,30 +1000,49 @@ void run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, const
         for (size_t i = 0; i < nWin; i++) W.stats.h2d_bytes += wins[i].len + 32;
     CK(cudaMemcpyAsync(W.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, W.stream));
     launch_windows(M, W, nWin, seedEntries, dWords, dWordOff, dReadLen);
-    download_windows(W, nWin);
+    return download_windows(W, nWin);
 }
 
+// The device counters belong to one attempt at one sub-batch: zeroed when it starts, delivered to W.hCtr with its
+// results (finish kernel / download_windows), added to the lane's statistics only when the attempt succeeded.
 void reset_counters(Lane& W) {
     W.dCtr.reserve(1);
+    W.hCtr.reserve(1);
     CK(cudaMemsetAsync(W.dCtr.p, 0, sizeof(DpCounters), W.stream));
 }
 
-void fetch_counters(Lane& W) {
-    DpCounters c;
-    CK(cudaMemcpy(&c, W.dCtr.p, sizeof(c), cudaMemcpyDeviceToHost));
+void absorb_counters(Lane& W) {
+    const DpCounters& c = *W.hCtr.p;
     W.stats.kmer_lookups += (int64_t)c.kmer_lookups;
     W.stats.query_seeds += (int64_t)c.query_seeds;
     W.stats.posting_runs += (int64_t)c.posting_runs;
     W.stats.posting_entries += (int64_t)c.posting_entries;
     W.stats.candidates += (int64_t)c.candidates;
     W.stats.chain_cells += (int64_t)c.chain_cells;
-    if (c.overflow) {
-        std::string what = "device capacity exceeded:";
-        if (c.overflow & 1) what += " mappings-per-window";
-        if (c.overflow & 2) what += " chains-per-candidate";
-        if (c.overflow & 4) what += " candidates-per-window-strand";
-        throw std::runtime_error(what);
+}
+
+// An abandoned attempt keeps its time and launches in the statistics (they were spent) but not its work counts.
+void forget_attempt(Lane& W, const dp_stats& before) {
+    W.stats.windows = before.windows;
+    W.stats.h2d_bytes = before.h2d_bytes;
+    W.stats.retries += 1;
+}
+
+// Grows the flagged capacities fourfold. Returns false when one is at its ceiling already.
+bool grow_caps(Caps& c, unsigned bits, unsigned numChunks) {
+    bool ok = true;
+    auto up = [&](int& v) {
+        if (v >= kCapMax) ok = false;
+        v = (int)std::min<long long>((long long)v * 4, kCapMax);
+    };
+    if (bits & DP_OV_OUTPOOL) up(c.outStride);
+    if (bits & DP_OV_RESULTS) up(c.resultCap);
+    if (bits & DP_OV_CHAINS) up(c.chainCap);
+    if (bits & DP_OV_CANDS) {
+        if (c.candStride >= numChunks) ok = false;  // (a window strand has at most C candidates)
+        c.candStride = (unsigned)std::min<unsigned long long>((unsigned long long)c.candStride * 4, numChunks);
     }
+    return ok;
 }
 
 struct ReadCache {
@@ -1038,12 +1068,22 @@ inline dp_mapping to_abi(const dph::Hit& h) {
 
 static_assert(sizeof(dp_mapping) == sizeof(DpMappingDev), "ABI record and device record share one layout");
 
-// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device. counts[r0..r1) and
-// `out` (ordered by read) receive the result.
-void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
-                  int* counts, SubOut& out) {
+// Upper bound of the seed entries the round-0 windows of one read can produce (both strands; a strand visits at most
+// len - k + 1 k-mers, one of them twice on a raw rc strand, Q2): what the compact seed lists of a launch are sized by.
+inline size_t round0_seed_bound(long long len, int e, int minLen) {
+    if (len < minLen) return 0;
+    return len <= 2ll * e ? 2 * (size_t)(len + 2) : 4 * (size_t)(e + 2);
+}
+
+// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device, with the lane's current
+// capacities (W.caps). Returns 0 and fills counts[r0..r1) and `out` (ordered by read), or returns the DP_OV_* bits of
+// a capacity that was too small: nothing is delivered then and the caller reruns the range with more room (map_range).
+unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
+                      int* counts, SubOut& out) {
     const int64_t n = r1 - r0;
     cudaStream_t st = W.stream;
+    const dp_stats before = W.stats;
+    reset_counters(W);
     const int k = M.k;
     const int e = M.edge;
     const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
@@ -1051,13 +1091,16 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     double t0 = now_ms();
     W.hRel.reserve((size_t)n + 1);
     long long maxLen = 0;
-    int64_t nWinReal = 0;
+    int64_t nWinReal = 0, nShort = 0;
+    size_t seedEntries0 = 0;  // worst case: every k-mer of every round-0 window is a seed on both strands
     for (int64_t i = 0; i <= n; i++) W.hRel.p[i] = offsets[r0 + i] - offsets[r0];
     for (int64_t i = 0; i < n; i++) {
         long long len = W.hRel.p[i + 1] - W.hRel.p[i];
         if (len < 0) throw std::runtime_error("read offsets must be non-decreasing");
         maxLen = std::max(maxLen, len);
         if (len >= minLen) nWinReal += (len <= 2ll * e) ? 1 : 2;
+        else nShort++;
+        seedEntries0 += round0_seed_bound(len, e, minLen);
     }
     if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
     const long long totalBytes = W.hRel.p[n];
@@ -1080,13 +1123,7 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     W.curAscii = dAscii;
     // ---- round 0 entirely on the device: windows, performMapping stages, Map()'s first decision ----
     const size_t nWin0 = 2 * (size_t)n;
-    size_t seedEntries0 = 0;
-    {
-        // worst case: every k-mer of every round-0 window is a seed on both strands
-        long long perRead = 2ll * 2 * (std::min<long long>(maxLen, 2ll * e) + 2);
-        seedEntries0 = (size_t)perRead * (size_t)n;
-        if (seedEntries0 >= 0xffffffffull) throw std::runtime_error("sub-batch too large");
-    }
+    if (seedEntries0 >= 0xffffffffull) throw std::runtime_error("internal error: sub-batch cut too large");  // (map_batch_impl cuts by this bound)
     ensure_window_capacity(M, W, nWin0, seedEntries0);
     dp_round0_windows_kernel<<<div_up(n, 256), 256, 0, st>>>(W.dReadLen.p, n, e, minLen, W.dWins.p);
     CK(cudaGetLastError());
@@ -1108,7 +1145,7 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
                                                             W.outMaps.p, W.hStatus.d, W.hFinN.d, W.hFinOff.d,
                                                             W.hFinMaps.d, W.cursor.p + CUR_FIN,
-                                                            (unsigned long long)finCap);
+                                                            (unsigned long long)finCap, W.dCtr.p, W.hCtr.d);
     CK(cudaGetLastError());
     CK(cudaEventRecord(W.timers[T_FINISH].b, st));
     W.stats.kernel_launches += 2;
@@ -1121,6 +1158,11 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
         W.stats.ms_chain += ms;  // Map()'s pairing step is accounted with the chaining stage
         W.stats.ms_finish += ms;
     }
+    if (W.hCtr.p->overflow) {  // a capacity of round 0 was too small: the caller grows it and reruns the range
+        forget_attempt(W, before);
+        return W.hCtr.p->overflow;
+    }
+    W.stats.short_reads += nShort;
     t0 = now_ms();
     std::vector<int> active;
     bool needDownload = false;
@@ -1136,7 +1178,13 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
     std::vector<int> slotOf;  // read index -> slot in `cache` / `late`
     if (!active.empty()) {
         t0 = now_ms();
-        if (needDownload) download_windows(W, nWin0);  // rare: the hit buffer was full
+        if (needDownload) {  // rare: the hit buffer was full
+            if (unsigned ov = download_windows(W, nWin0)) {
+                forget_attempt(W, before);
+                W.stats.short_reads -= nShort;
+                return ov;
+            }
+        }
         std::vector<ReadCache> cache(active.size());
         slotOf.assign((size_t)n, -1);
         std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
@@ -1190,7 +1238,11 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
             }
             W.stats.ms_host_logic += now_ms() - t0;
             if (wins.empty()) break;
-            run_windows(M, W, wins.data(), wins.size(), W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+            if (unsigned ov = run_windows(M, W, wins.data(), wins.size(), W.dWords.p, W.dWordOff.p, W.dReadLen.p)) {
+                forget_attempt(W, before);
+                W.stats.short_reads -= nShort;
+                return ov;
+            }
             t0 = now_ms();
             roundMaps.emplace_back();
             std::vector<DpMappingDev>& keep = roundMaps.back();
@@ -1232,7 +1284,50 @@ void map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int6
         }
     }
     out.maps.resize(pos);
+    absorb_counters(W);
     W.stats.ms_host_logic += now_ms() - t0;
+    return 0;
+}
+
+// (DP_CAP_OUT / DP_CAP_RESULTS / DP_CAP_CHAINS / DP_CAP_CANDS: tests start from tiny capacities to walk the retries)
+Caps default_caps() {
+    Caps c;
+    c.outStride = std::max(1, std::min(kCapMax, env_int("DP_CAP_OUT", c.outStride)));
+    c.resultCap = std::max(1, std::min(kCapMax, env_int("DP_CAP_RESULTS", c.resultCap)));
+    c.chainCap = std::max(1, std::min(kCapMax, env_int("DP_CAP_CHAINS", c.chainCap)));
+    c.candStride = (unsigned)std::max(1, env_int("DP_CAP_CANDS", (int)c.candStride));
+    return c;
+}
+
+// map_subbatch with the exact way out of every device capacity: on overflow the flagged capacity grows fourfold and the
+// range is recomputed; when the candidate lists would outgrow the lane's memory budget the range is cut into pieces
+// first (a single read always fits: a window strand has at most C candidates). The lane's capacities return to their
+// defaults afterwards (the buffers stay grown).
+void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
+               int* counts, SubOut& out) {
+    const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);  // (tests: 0 = single reads)
+    for (;;) {
+        const int64_t n = r1 - r0;
+        const size_t candBytes = (size_t)4 * (size_t)n * std::min<size_t>(M.I.numChunks, W.caps.candStride) * 6;
+        if (candBytes > candBudget && n > 1) {
+            const int64_t pieces = std::min<int64_t>(n, (int64_t)((candBytes + candBudget - 1) / candBudget));
+            out.maps.clear();
+            for (int64_t p = 0; p < pieces; p++) {
+                const int64_t a = r0 + n * p / pieces, b = r0 + n * (p + 1) / pieces;
+                if (a == b) continue;
+                SubOut part;
+                const Caps keep = W.caps;
+                map_range(M, W, dAscii + (offsets[a] - offsets[r0]), offsets, a, b, counts, part);
+                W.caps = keep;
+                out.maps.insert(out.maps.end(), part.maps.begin(), part.maps.end());
+            }
+            return;
+        }
+        const unsigned ov = map_subbatch(M, W, dAscii, offsets, r0, r1, counts, out);
+        if (!ov) return;
+        if (!grow_caps(W.caps, ov, M.I.numChunks))
+            throw std::runtime_error("a window of this batch needs more than 2^20 mappings or chains on the device");
+    }
 }
 
 void add_stats(dp_stats& a, const dp_stats& b) {
@@ -1255,6 +1350,8 @@ void add_stats(dp_stats& a, const dp_stats& b) {
     a.mappings += b.mappings;
     a.kernel_launches += b.kernel_launches;
     a.h2d_bytes += b.h2d_bytes;
+    a.retries += b.retries;
+    a.short_reads += b.short_reads;
 }
 
 Lane& get_lane(dp_mapper& M, size_t idx) {
@@ -1273,6 +1370,7 @@ Lane& get_lane(dp_mapper& M, size_t idx) {
 
 const int64_t kSubBatchReads = 1 << 16;
 const int64_t kSubBatchBytes = 1ll << 30;
+const size_t kSubBatchSeedEntries = 400u << 20;  // 3.2 GB of seed lists per lane at most
 
 int lane_count() {
     const char* env = getenv("DP_LANES");
@@ -1330,8 +1428,15 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
             if (remaining > tail) want = std::min(want, remaining - tail);
             else if (ramp && remaining > full / 4) want = remaining - full / 4;
             else want = remaining;
+            // (also bounded by the worst-case seed entries of its round-0 windows: 8 bytes each in the lane's compact
+            // seed lists, 32-bit offsets — large query_size values cut smaller sub-batches instead of failing)
             int64_t r1 = r0;
-            while (r1 < n_reads && r1 - r0 < want && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) r1++;
+            size_t seedBound = 0;
+            while (r1 < n_reads && r1 - r0 < want && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) {
+                seedBound += round0_seed_bound(offsets[r1 + 1] - offsets[r1], M.edge, M.k + 12);
+                if (seedBound > kSubBatchSeedEntries && r1 > r0) break;
+                r1++;
+            }
             if (r1 == r0) r1 = r0 + 1;
             cuts.push_back(r1);
             r0 = r1;
@@ -1353,7 +1458,6 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     for (int l = 0; l < nLanes; l++) {
         Lane& W = get_lane(M, (size_t)l);
         memset(&W.stats, 0, sizeof(W.stats));
-        reset_counters(W);
     }
     std::vector<int> counts((size_t)n_reads + 1, 0);
     std::vector<SubOut> subs(nSub);
@@ -1379,10 +1483,11 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                 } else {
                     dA = devBases + offsets[r0];
                 }
-                map_subbatch(M, W, dA, offsets, r0, r1, counts.data(), subs[sI]);
+                W.caps = default_caps();
+                map_range(M, W, dA, offsets, r0, r1, counts.data(), subs[sI]);
+                W.caps = default_caps();
             }
             lane_sync(W);
-            fetch_counters(W);
         } catch (const std::exception& ex) {
             errs[(size_t)l] = ex.what();
             if (errs[(size_t)l].empty()) errs[(size_t)l] = "unknown error";
@@ -1481,6 +1586,13 @@ std::unique_ptr<dp_mapper> open_mapper(int device) {
     int lo = 0, hi = 0;  // numerically lowest value = highest priority
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&M->pullStream, cudaStreamNonBlocking, hi));
+    // (per device; set here, before any lane thread exists)
+    CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(dp_lookup_block_kernel<128, 8, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return M;
 }
 
@@ -1754,6 +1866,7 @@ int dp_mapper_params(const dp_mapper* m, int64_t* out8) {
 
 int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out) {
     API_TRY
+    if (!m || !out) throw std::runtime_error("null argument");
     CK(cudaSetDevice(m->device));
     size_t nTable = (size_t)((1ll << (2 * m->k)) / 32);
     std::vector<uint2> t(nTable);
@@ -1773,6 +1886,7 @@ int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out) {
 
 int dp_mapper_chunk(const dp_mapper* m, int64_t c, int64_t* fields4, int32_t* pos, int64_t* kmer) {
     API_TRY
+    if (!m || !fields4) throw std::runtime_error("null argument");
     if (c < 0 || c >= (int64_t)m->I.numChunks) throw std::runtime_error("chunk id out of range");
     CK(cudaSetDevice(m->device));
     unsigned off[2];
@@ -1798,6 +1912,7 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
                            int32_t* n_cand2, int32_t* cand, int64_t cand_cap, int32_t* n_map, dp_mapping* maps,
                            int64_t map_cap) {
     API_TRY
+    if (!m || !read_ascii) throw std::runtime_error("null argument");
     CK(cudaSetDevice(m->device));
     if (whole) {
         start = 0;
@@ -1807,7 +1922,6 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
         throw std::runtime_error("bad probe window");
     Lane& W = get_lane(*m, 0);
     memset(&W.stats, 0, sizeof(W.stats));
-    reset_counters(W);
     cudaStream_t st = W.stream;
     W.dAscii.reserve((size_t)read_len + 64);
     CK(cudaMemcpyAsync(W.dAscii.p, read_ascii, (size_t)read_len, cudaMemcpyHostToDevice, st));
@@ -1828,8 +1942,15 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     w.start = (int)start;
     w.len = (int)(end - start);
     w.whole = whole ? 1 : 0;
-    run_windows(*m, W, &w, 1, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
-    fetch_counters(W);
+    W.caps = default_caps();
+    for (;;) {  // (the same exact way out of the device capacities as map_range)
+        reset_counters(W);
+        const unsigned ov = run_windows(*m, W, &w, 1, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+        if (!ov) break;
+        if (!grow_caps(W.caps, ov, m->I.numChunks)) throw std::runtime_error("window needs more than 2^20 mappings or chains");
+    }
+    absorb_counters(W);
+    W.caps = default_caps();
     // seeds
     unsigned wsOff[2];
     int wsN[2];

@@ -69,9 +69,14 @@ struct DpCounters {
     unsigned long long candidates;
     unsigned long long chain_cells;
     unsigned long long mappings;
-    unsigned int overflow;  // bit0: mapping list cap, bit1: chain list cap, bit2: candidate cap
+    unsigned int overflow;  // DP_OV_* bits: a capacity of this launch was too small; the host reruns it with more room
     unsigned int pad;
 };
+// (none of these is a limit of the library: the host grows the flagged capacity and recomputes, see dp_api.cu)
+#define DP_OV_RESULTS 1u  // mappings of one window before sort/dedupe (general chain kernel)
+#define DP_OV_CHAINS 2u   // chains kept for one candidate (general chain kernel)
+#define DP_OV_CANDS 4u    // candidate chunks of one window strand
+#define DP_OV_OUTPOOL 8u  // the launch's pool of window results
 
 __host__ __device__ inline unsigned dp_base_code(unsigned b) { return ((b >> 1) ^ ((b & 4) >> 2)) & 3; }
 

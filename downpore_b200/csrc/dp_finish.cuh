@@ -146,8 +146,13 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
                                                                int* __restrict__ finN, unsigned* __restrict__ finOff,
                                                                DpMappingDev* __restrict__ finMaps,
                                                                unsigned long long* __restrict__ finCursor,
-                                                               unsigned long long finCapacity) {
+                                                               unsigned long long finCapacity,
+                                                               const DpCounters* __restrict__ ctr,
+                                                               DpCounters* __restrict__ hostCtr) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // the launch's work counters and overflow flags travel with the results (every kernel that updates them has
+    // finished: same stream)
+    if (r == 0 && hostCtr) *hostCtr = *ctr;
     const bool live = r < n;  // every lane stays for the warp-wide allocation below
     const long long qlen = live ? readLen[r] : 0;
     const int e = I.edge;

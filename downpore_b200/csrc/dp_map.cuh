@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(32 * DP_LWARPS, 8) dp_lookup_kernel(DpIndexDev
                 X.nAllDistinct = nAllDistinct;
                 nCandOut = dp_refine_emit<false>(I, X, sorted, nCand, outChunk, outDist, candStride);
                 if (nCandOut > candStride) {
-                    if (lane == 0) atomicOr(&ctr->overflow, 4u);
+                    if (lane == 0) atomicOr(&ctr->overflow, DP_OV_CANDS);
                     nCandOut = candStride;
                 }
             }
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(32 * DP_SMALL_WARPS, 12) dp_lookup_small_kerne
                         }
                         nOut = nCand;
                         if (nOut > candStride) {
-                            if (lane == 0) atomicOr(&ctr->overflow, 4u);
+                            if (lane == 0) atomicOr(&ctr->overflow, DP_OV_CANDS);
                             nOut = candStride;
                         }
                     }
@@ -1357,7 +1357,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
                                           : dp_refine_emit<false>(I, X, sorted, nCand, candChunk + (size_t)ws * candStride,
                                                                   candDistinct + (size_t)ws * candStride, candStride);
                         if (nOut > candStride) {
-                            if (lane == 0) atomicOr(&ctr->overflow, 4u);
+                            if (lane == 0) atomicOr(&ctr->overflow, DP_OV_CANDS);
                             nOut = candStride;
                         }
                         if (lane == 0) sh.nCandOut = nOut;
@@ -1937,9 +1937,8 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
                 T.chainLen = chainLen;
                 T.lastB = lastB;
                 int nGood = dp_dynamic_match(T, thr, k, chains, S.chainCap);
-                if (nGood < 0) {
-                    overflow = true;
-                    if (lane == 0) atomicOr(&ctr->overflow, 2u);
+                if (nGood < 0) {  // (the host reruns the launch with a longer chain list)
+                    if (lane == 0) atomicOr(&ctr->overflow, DP_OV_CHAINS);
                     nGood = 0;
                 }
                 __syncwarp();
@@ -1989,7 +1988,7 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
         // ---- sort by Start + overlap dedupe (mapping.go:590-608); lane 0 ----
         if (lane == 0) {
             if (overflow || nRes > S.resultCap) {
-                atomicOr(&ctr->overflow, 1u);
+                atomicOr(&ctr->overflow, DP_OV_RESULTS);
                 if (nRes > S.resultCap) nRes = S.resultCap;
             }
             if (nRes > 1) {
@@ -2019,7 +2018,7 @@ __global__ void __launch_bounds__(128, 6) dp_chain_kernel(DpIndexDev I, const Dp
             // compact output: one bump allocation per window
             unsigned long long base = nRes ? atomicAdd(outCursor, (unsigned long long)nRes) : 0ull;
             if (base + (unsigned)nRes > outCapacity) {
-                atomicOr(&ctr->overflow, 1u);
+                atomicOr(&ctr->overflow, DP_OV_OUTPOOL);
                 nRes = 0;
                 base = 0;
             }
@@ -2501,7 +2500,7 @@ __global__ void __launch_bounds__(128) dp_chain_thread_kernel(DpIndexDev I, cons
         unsigned long long base = warpBase + (unsigned)(incl - mine);
         int cnt = mine;
         if (base + (unsigned)cnt > outCapacity) {
-            atomicOr(&ctr->overflow, 1u);
+            atomicOr(&ctr->overflow, DP_OV_OUTPOOL);
             cnt = 0;
             base = 0;
         }

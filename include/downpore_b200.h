@@ -65,6 +65,9 @@ typedef struct dp_stats {
                                page-locked - only the queried windows, moved by the TMA pull kernel) */
     double ms_reduce;       /* list-reduction kernel of the chaining fast path (not included in ms_chain) */
     double ms_finish;       /* Map()'s first decision on the device (dp_finish_round0_kernel); included in ms_chain */
+    int64_t retries;        /* sub-batch attempts recomputed with larger device capacities (repeat-rich references) */
+    int64_t short_reads;    /* reads shorter than k+12 bases: returned without mappings (the reference's scans over-read
+                               such slices: undefined there) */
 } dp_stats;
 
 /*

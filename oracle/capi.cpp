@@ -281,6 +281,21 @@ void* dpo_mapper_new(const char* ref_ascii, long long ref_len, int circular, int
     return om;
     DPO_CATCH(nullptr)
 }
+// lean: -1 auto / 0 / 1 (memory-lean index, oracle.hpp); threads: workers of the per-chunk seed scans
+void* dpo_mapper_new_ex(const char* ref_ascii, long long ref_len, int circular, int k, const double* kmer_values,
+                        int seed_rate, int edge_size, int chunk_size, int lean, int threads) {
+    DPO_TRY OMapper* om = new OMapper();
+    PackedSeq ref;
+    {
+        std::string text(ref_ascii, (size_t)ref_len);
+        ref = NewPackedSequence(0, text, nullptr);
+    }
+    NewMapper(om->m, ref, circular != 0, k, kmer_values, seed_rate, edge_size, chunk_size, lean, threads);
+    om->m.refName = "ref";
+    return om;
+    DPO_CATCH(nullptr)
+}
+int dpo_mapper_is_lean(void* p) { return ((OMapper*)p)->m.index.lean ? 1 : 0; }
 void dpo_mapper_free(void* p) { delete (OMapper*)p; }
 long long dpo_mapper_num_seeds(void* p) { return ((OMapper*)p)->m.index.size; }
 long long dpo_mapper_num_chunks(void* p) { return (long long)((OMapper*)p)->m.index.sequences.size(); }
@@ -292,7 +307,7 @@ void dpo_mapper_seed_kmers(void* p, long long* out) {
 // chunk c: fields {offset, inset, length, nseeds}; segments (gap, kmer(not seed id), gap, ...)
 long long dpo_mapper_chunk(void* p, long long c, long long* fields4, long long* segments, long long cap) {
     OMapper* om = (OMapper*)p;
-    const SeedSequence& s = om->m.index.sequences[(size_t)c];
+    const SeedSequence s = ChunkSequence(om->m.index, (size_t)c);
     fields4[0] = s.offset;
     fields4[1] = s.inset;
     fields4[2] = s.length;

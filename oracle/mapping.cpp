@@ -3,7 +3,10 @@
 #include "oracle.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <deque>
+#include <thread>
 #include <stdexcept>
 
 namespace dpo {
@@ -68,31 +71,72 @@ std::vector<double> KmerValues(std::vector<uint64_t>& kmerCounts, gint k) {
 // mapping/mapping.go
 // ---------------------------------------------------------------------------
 void NewMapper(Mapper& m, const PackedSeq& reference, bool circular, gint k, const double* kmerValues, gint seedRate,
-               gint edgeSize, gint chunkSize) {  // mapping.go:67-109
+               gint edgeSize, gint chunkSize, int lean, int threads) {  // mapping.go:67-109
     NewSeedIndex(m.index, k);
     m.reference = reference;
     m.edgeSize = edgeSize;
     m.circular = circular;
     AddSingleSeeds(m.index, reference, seedRate, kmerValues);
-    gint ind = 0;
-    auto emit = [&](const PackedSeq& chunk) {
-        SeedSequence ss = NewSeedSequence(m.index, chunk, nullptr);
-        ss.id = ind;  // seq.SetID(ind)
-        AddSequence(m.index, std::move(ss));
-        ind++;
-    };
+    // the chunks in the producer's emission order (mapping.go:80-95)
+    std::vector<PackedSeq> chunks;
     for (gint j = 0; j < 10; j++) {
         gint start = j * chunkSize;
         gint step = chunkSize * 10 - edgeSize;
         for (gint i = start; i < reference.Len() - chunkSize / 2; i += step) {
             gint end = i + chunkSize;
             if (i >= reference.Len()) end = reference.Len();
-            emit(SubSequence(reference, i, end));
+            chunks.push_back(SubSequence(reference, i, end));
         }
     }
     if (circular) {
-        emit(Append(SubSequence(reference, reference.Len() - edgeSize, reference.Len()), 0,
-                    SubSequence(reference, 0, edgeSize)));
+        chunks.push_back(Append(SubSequence(reference, reference.Len() - edgeSize, reference.Len()), 0,
+                                SubSequence(reference, 0, edgeSize)));
+    }
+    // Memory-lean mode (oracle.hpp): decided by what the two bitset families would cost (#seeds x #chunks bits each)
+    if (lean < 0) {
+        const char* env = getenv("DPO_LEAN_BYTES");
+        const double limit = env ? atof(env) : 4e9;
+        lean = 2.0 * (double)m.index.size * (double)chunks.size() / 8.0 > limit ? 1 : 0;
+    }
+    m.index.lean = lean != 0;
+    // NewSeedSequence per chunk only reads the index's k-mer tables: independent calls, stored in emission order
+    // (the reference's goroutines deliver them in arrival order and ids follow, Q5: canonical = emission order)
+    const size_t C = chunks.size();
+    std::vector<SeedSequence> built(C);
+    if (m.index.lean) m.index.leanSegments.resize(C);
+    if (threads < 1) threads = 1;
+    std::atomic<size_t> next(0);
+    std::vector<std::string> errs((size_t)threads);
+    auto work = [&](int t) {
+        try {
+            for (;;) {
+                size_t c0 = next.fetch_add(16);
+                if (c0 >= C) break;
+                for (size_t c = c0; c < std::min(C, c0 + 16); c++) {
+                    built[c] = NewSeedSequence(m.index, chunks[c], nullptr);
+                    built[c].id = (gint)c;  // seq.SetID(ind)
+                    if (m.index.lean) {     // (16 -> 4 bytes per value at once: the transient footprint stays small)
+                        std::vector<int32_t> seg(built[c].segments.begin(), built[c].segments.end());
+                        for (size_t z = 0; z < seg.size(); z++)
+                            if ((gint)seg[z] != built[c].segments[z]) throw std::runtime_error("oracle: lean segment out of range");
+                        m.index.leanSegments[c] = std::move(seg);
+                        std::vector<gint>().swap(built[c].segments);
+                    }
+                }
+            }
+        } catch (const std::exception& ex) {
+            errs[(size_t)t] = ex.what();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    for (size_t c = 0; c < C; c++) {
+        if (m.index.lean) m.index.sequences.push_back(std::move(built[c]));  // (segments already in leanSegments[c])
+        else AddSequence(m.index, std::move(built[c]));
     }
     IndexSequences(m.index);
 }
@@ -245,10 +289,14 @@ MList performMapping(MapCtx& x, const PackedSeq& query) {  // mapping.go:489-611
     for (gint i = 0; i < seedQuery.GetNumSeeds(); i++) Add(seedSet, (uint64_t)seedQuery.GetSeed(i));
     set_match_counters(x.c);
     for (uint64_t idx : matchingIndices) {
-        const IntSet& matchSet = index.seedSets[idx];
+        IntSet leanSet;
+        if (index.lean) leanSet = ChunkSeedSet(index, (size_t)idx);
+        const IntSet& matchSet = index.lean ? leanSet : index.seedSets[idx];
         if (CountIntersectionTo(matchSet, seedSet, minMatches) < (uint64_t)minMatches) continue;
         if (x.c) x.c->cand_pass++;
-        const SeedSequence& match = index.sequences[idx];
+        SeedSequence leanSeq;
+        if (index.lean) leanSeq = ChunkSequence(index, (size_t)idx);
+        const SeedSequence& match = index.lean ? leanSeq : index.sequences[idx];
         bool isnil = false;
         std::vector<SeedMatch> seedMatches = Match(match, seedQuery, seedSet, matchSet, minMatches, k, &isnil);
         for (const SeedMatch& seedMatch : seedMatches) {
@@ -279,10 +327,14 @@ MList performMapping(MapCtx& x, const PackedSeq& query) {  // mapping.go:489-611
     Clear(seedSet);
     for (gint i = 0; i < rcQuery.GetNumSeeds(); i++) Add(seedSet, (uint64_t)rcQuery.GetSeed(i));
     for (uint64_t idx : matchingRCIndices) {
-        const IntSet& matchSet = index.seedSets[idx];
+        IntSet leanSet;
+        if (index.lean) leanSet = ChunkSeedSet(index, (size_t)idx);
+        const IntSet& matchSet = index.lean ? leanSet : index.seedSets[idx];
         if (CountIntersectionTo(matchSet, seedSet, minRCMatches) < (uint64_t)minRCMatches) continue;
         if (x.c) x.c->cand_pass++;
-        const SeedSequence& match = index.sequences[idx];
+        SeedSequence leanSeq;
+        if (index.lean) leanSeq = ChunkSequence(index, (size_t)idx);
+        const SeedSequence& match = index.lean ? leanSeq : index.sequences[idx];
         bool isnil = false;
         std::vector<SeedMatch> seedMatches = Match(match, rcQuery, seedSet, matchSet, minRCMatches, k, &isnil);
         for (const SeedMatch& seedMatch : seedMatches) {

@@ -168,7 +168,21 @@ struct SeedIndex {
     std::vector<int32_t> kmerMap;
     std::vector<gint> seedMap;
     gint size = 0;
+    // Memory-lean mode (references where the two bitset families would need tens of GB: #seeds x #chunks / 8 bytes
+    // each). The index then keeps every chunk's segments as int32 and, per seed, the ascending list of the chunks
+    // containing it; `sequenceSets` / `seedSets` stay empty and `sequences[c].segments` are empty. The IntSet a
+    // query needs is materialised on demand by replaying the very Add() sequence that AddSequence / IndexSequences
+    // would have run (SeedChunkSet / ChunkSeedSet below), so every downstream routine (GetSharedIDs, the soft-union
+    // emulations, CountIntersectionTo, Reduced, Match) runs unchanged on identical inputs.
+    bool lean = false;
+    std::vector<std::vector<int32_t>> leanSegments;  // [chunk] gap, seed, gap, ..., gap
+    std::vector<uint64_t> leanSeedOff;               // [size+1]
+    std::vector<uint32_t> leanSeedChunks;            // distinct chunk ids per seed, ascending
 };
+uint64_t SeedChunkCount(const SeedIndex& g, gint seed);     // sequenceSets[seed].count
+IntSet SeedChunkSet(const SeedIndex& g, gint seed);         // lean: sequenceSets[seed] rebuilt (seeds.go:372-384 order)
+IntSet ChunkSeedSet(const SeedIndex& g, size_t chunk);      // lean: seedSets[chunk] rebuilt (seeds.go:272-290 order)
+SeedSequence ChunkSequence(const SeedIndex& g, size_t chunk);  // lean: sequences[chunk] with its segments restored
 void NewSeedIndex(SeedIndex& g, gint k);                                          // seeds.go:23-31
 SeedSequence NewSeedSequence(const SeedIndex& g, const PackedSeq& seq, Counters* c);  // seeds.go:33-50
 void AddSingleSeeds(SeedIndex& g, const PackedSeq& seq, gint seedRate, const double* ranks);  // seeds.go:160-200
@@ -222,8 +236,10 @@ struct Mapper {
     std::string refName;
 };
 // NewMapper (mapping.go:67-109). Chunk ids = producer emission order (canonical choice for Q5).
+// lean: -1 = decide by the size of the bitsets (DPO_LEAN_BYTES, default 4 GB), 0 / 1 = forced; threads: workers for
+// the per-chunk NewSeedSequence calls (independent; results are stored in emission order).
 void NewMapper(Mapper& m, const PackedSeq& reference, bool circular, gint k, const double* kmerValues,
-               gint seedRate, gint edgeSize, gint chunkSize);
+               gint seedRate, gint edgeSize, gint chunkSize, int lean = -1, int threads = 1);
 // Map (mapping.go:430-487). Returned mappings are in the slice order the reference returns.
 std::vector<Mapping> Map(const Mapper& m, const PackedSeq& query, Counters* c);
 std::vector<Mapping> performMappingPublic(const Mapper& m, const PackedSeq& query, Counters* c);  // mapping.go:489-611

@@ -76,6 +76,9 @@ def lib():
         "dpo_kmer_values": (ctypes.c_int, [c_vp, c_ll, ctypes.c_int, c_vp]),
         "dpo_kmer_counts": (ctypes.c_int, [c_vp, c_ll, ctypes.c_int, c_vp]),
         "dpo_mapper_new": (c_vp, [c_vp, c_ll, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+        "dpo_mapper_new_ex": (c_vp, [c_vp, c_ll, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                              ctypes.c_int, ctypes.c_int]),
+        "dpo_mapper_is_lean": (ctypes.c_int, [c_vp]),
         "dpo_mapper_free": (None, [c_vp]),
         "dpo_mapper_num_seeds": (c_ll, [c_vp]),
         "dpo_mapper_num_chunks": (c_ll, [c_vp]),
@@ -412,16 +415,25 @@ COUNTER_NAMES = ["windows", "kmer_lookups", "query_seeds", "posting_runs", "post
 class Mapper:
     """mapping.Mapper (mapping/mapping.go:22-26) over the oracle."""
 
-    def __init__(self, ref, values, circular=True, k=11, seed_rate=40, edge_size=1000, chunk_size=10000):
+    def __init__(self, ref, values, circular=True, k=11, seed_rate=40, edge_size=1000, chunk_size=10000, lean=None,
+                 threads=None):
+        """lean: None = decided by the size the index bitsets would have, True/False = forced (memory-lean index:
+        the bitsets are rebuilt per query from lists, everything downstream runs unchanged; oracle.hpp).
+        threads: workers of the per-chunk seed scans of the index build (default: all cores)."""
         self.ref = _u8(ref)
         self.values = np.ascontiguousarray(values, dtype=np.float64)
         assert self.values.size == 4 ** k
         self.k = k
         self.circular = circular
-        self.h = lib().dpo_mapper_new(self.ref.ctypes.data, self.ref.size, int(circular), k, self.values.ctypes.data,
-                                      seed_rate, edge_size, chunk_size)
+        self.h = lib().dpo_mapper_new_ex(self.ref.ctypes.data, self.ref.size, int(circular), k, self.values.ctypes.data,
+                                         seed_rate, edge_size, chunk_size, -1 if lean is None else int(bool(lean)),
+                                         threads or (os.cpu_count() or 1))
         if not self.h:
             raise RuntimeError(_err())
+
+    @property
+    def lean(self):
+        return bool(lib().dpo_mapper_is_lean(self.h))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -2,6 +2,8 @@
 // Follows seeds/seeds.go and the hot part of seeds/sequence.go of the reference.
 #include "oracle.hpp"
 
+#include <deque>
+
 #include <stdexcept>
 
 namespace dpo {
@@ -547,6 +549,69 @@ std::vector<SeedSequence> ChunkSeedSequence(const SeedSequence& s, gint chunkSiz
     return out;
 }
 
+// ---- memory-lean mode: the same sets, rebuilt per query from lists (see oracle.hpp) ----
+static void IndexSequencesLean(SeedIndex& g) {
+    const size_t S = (size_t)g.size, C = g.sequences.size();
+    std::vector<uint32_t> last(S, 0xffffffffu);
+    g.leanSeedOff.assign(S + 1, 0);
+    for (size_t c = 0; c < C; c++) {
+        const std::vector<int32_t>& seg = g.leanSegments[c];
+        for (size_t j = 1; j < seg.size(); j += 2) {
+            const size_t seed = (size_t)seg[j];
+            if (last[seed] != (uint32_t)c) {
+                last[seed] = (uint32_t)c;
+                g.leanSeedOff[seed + 1]++;
+            }
+        }
+    }
+    for (size_t s2 = 0; s2 < S; s2++) g.leanSeedOff[s2 + 1] += g.leanSeedOff[s2];
+    g.leanSeedChunks.assign((size_t)g.leanSeedOff[S], 0);
+    std::vector<uint64_t> fill(g.leanSeedOff.begin(), g.leanSeedOff.end() - 1);
+    std::fill(last.begin(), last.end(), 0xffffffffu);
+    for (size_t c = 0; c < C; c++) {
+        const std::vector<int32_t>& seg = g.leanSegments[c];
+        for (size_t j = 1; j < seg.size(); j += 2) {
+            const size_t seed = (size_t)seg[j];
+            if (last[seed] != (uint32_t)c) {
+                last[seed] = (uint32_t)c;
+                g.leanSeedChunks[(size_t)fill[seed]++] = (uint32_t)c;
+            }
+        }
+    }
+    g.sequenceSets.clear();
+    g.sequenceSets.shrink_to_fit();
+}
+
+uint64_t SeedChunkCount(const SeedIndex& g, gint seed) {
+    if (!g.lean) return g.sequenceSets[(size_t)seed].count;
+    return g.leanSeedOff[(size_t)seed + 1] - g.leanSeedOff[(size_t)seed];
+}
+
+IntSet SeedChunkSet(const SeedIndex& g, gint seed) {
+    if (!g.lean) return g.sequenceSets[(size_t)seed];
+    IntSet s = NewIntSet();  // register_seed (seeds.go:190)
+    // IndexSequences walks the chunks in descending id order (seeds.go:372-384)
+    for (uint64_t p = g.leanSeedOff[(size_t)seed + 1]; p > g.leanSeedOff[(size_t)seed]; p--) Add(s, (uint64_t)g.leanSeedChunks[(size_t)p - 1]);
+    return s;
+}
+
+SeedSequence ChunkSequence(const SeedIndex& g, size_t chunk) {
+    SeedSequence s = g.sequences[chunk];
+    if (g.lean) s.segments.assign(g.leanSegments[chunk].begin(), g.leanSegments[chunk].end());
+    return s;
+}
+
+IntSet ChunkSeedSet(const SeedIndex& g, size_t chunk) {
+    if (!g.lean) return g.seedSets[chunk];
+    const std::vector<int32_t>& seg = g.leanSegments[chunk];  // AddSequence (seeds.go:272-290)
+    gint maxSeed = 0;
+    for (size_t i = 1; i < seg.size(); i += 2)
+        if (seg[i] > maxSeed) maxSeed = seg[i];
+    IntSet seedSet = NewIntSetCapacity(maxSeed + 1);
+    for (size_t i = 1; i < seg.size(); i += 2) Add(seedSet, (uint64_t)seg[i]);
+    return seedSet;
+}
+
 void AddSequence(SeedIndex& g, SeedSequence&& seq) {  // seeds.go:272-290
     gint maxSeed = 0;
     for (size_t i = 1; i < seq.segments.size(); i += 2) {
@@ -562,6 +627,10 @@ void AddSequence(SeedIndex& g, SeedSequence&& seq) {  // seeds.go:272-290
 // seeds.go:292-305 + 372-384. The seed-range partition over 4 goroutines covers every seed exactly once and
 // each worker walks the chunks in descending id order; a single descending walk is equivalent.
 void IndexSequences(SeedIndex& g) {
+    if (g.lean) {
+        IndexSequencesLean(g);
+        return;
+    }
     for (gint i = (gint)g.sequences.size() - 1; i >= 0; i--) {
         const SeedSequence& s = g.sequences[(size_t)i];
         for (size_t j = 1; j < s.segments.size(); j += 2) {
@@ -575,10 +644,23 @@ std::vector<uint64_t> Matches(const SeedIndex& g, const SeedSequence& query, dou
     std::vector<const IntSet*> allSeedSets;  // seeds.go:335-353
     gint prevSeed = -1;
     uint64_t maxSeqs = (uint64_t)g.sequences.size();
+    std::deque<IntSet> rebuilt;  // lean mode: the sets of this query, each distinct seed rebuilt once
+    std::vector<std::pair<gint, const IntSet*>> have;
     for (size_t i = 1; i < query.segments.size(); i += 2) {
         gint seed = query.segments[i];
-        const IntSet* adj = &g.sequenceSets[(size_t)seed];
-        if (seed != prevSeed && adj->count < maxSeqs) {
+        if (seed != prevSeed && SeedChunkCount(g, seed) < maxSeqs) {
+            const IntSet* adj = nullptr;
+            if (!g.lean) {
+                adj = &g.sequenceSets[(size_t)seed];
+            } else {
+                for (auto& h : have)
+                    if (h.first == seed) adj = h.second;
+                if (!adj) {
+                    rebuilt.push_back(SeedChunkSet(g, seed));
+                    adj = &rebuilt.back();
+                    have.emplace_back(seed, adj);
+                }
+            }
             allSeedSets.push_back(adj);
             prevSeed = seed;
         }

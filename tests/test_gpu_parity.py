@@ -206,36 +206,6 @@ def test_edge_inputs(pair):
     assert off[5] > off[4]                        # lowercase maps like uppercase
 
 
-def test_capacity_is_an_error_not_a_wrong_answer():
-    """A reference made of 24 copies of one 12 kb unit: a read window hits every copy, more mappings per window than
-    the device keeps (16). The call must either fail loudly (`device capacity exceeded`) or agree with the oracle —
-    never return a truncated answer."""
-    rng = np.random.default_rng(5)
-    unit = synth.reference(77, 12_000)
-    copies = []
-    for _ in range(24):
-        u = unit.copy()
-        pos = rng.integers(0, len(u), size=12)       # a dozen substitutions per copy
-        u[pos] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=12)]
-        copies.append(u)
-    ref = np.concatenate(copies)
-    vals = dp.kmer_values(dp.kmer_counts(ref, K), K)
-    om = po.Mapper(ref, vals, circular=False)
-    n, L = 40, 6000
-    rd = synth.reads(ref, 5, n, L, circular=False)
-    offs = np.arange(n + 1, dtype=np.int64) * L
-    orow, ooff, _ = om.map_batch(rd, offs, threads=2)
-    gm = dp.Mapper(ref, vals, circular=False)
-    try:
-        maps, off = gm.map_batch(rd, offs)
-    except dp.DownporeError as ex:
-        assert "capacity exceeded" in str(ex)
-    else:
-        assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow)
-    finally:
-        gm.close()
-
-
 def test_other_parameters():
     """k, seed_rate, query_size and chunk_size other than the defaults (commands/map.go:19-21)."""
     ref = synth.reference(8, 400_000)

@@ -79,6 +79,36 @@ void dps_reference(uint64_t seed, int64_t len, char* out, int threads) {
     for (auto& t : th) t.join();
 }
 
+// The `rep` variant of a reference: about `frac` of the bases of ref[0..len) are overwritten in place by
+// copies of `families` random repeat units of min_len..max_len bases, every copy with its own substitution divergence
+// drawn uniformly from [0, max_div] and a fair strand coin. Serial and seeded: identical bytes everywhere.
+void dps_make_repeats(char* ref, int64_t len, uint64_t seed, int families, double frac, int64_t min_len, int64_t max_len,
+                      double max_div) {
+    Xoshiro256ss rng(seed * 0xA24BAED4963EE407ULL + 99);
+    std::vector<std::vector<char>> fam((size_t)families);
+    for (auto& f : fam) {
+        int64_t L = min_len + (int64_t)rng.below((uint64_t)(max_len - min_len + 1));
+        f.resize((size_t)L);
+        for (auto& c : f) c = kBases[rng.below(4)];
+    }
+    const int64_t target = (int64_t)(frac * (double)len);
+    int64_t placed = 0;
+    while (placed < target) {
+        const std::vector<char>& f = fam[(size_t)rng.below((uint64_t)families)];
+        const int64_t L = (int64_t)f.size();
+        if (L >= len) break;
+        const int64_t pos = (int64_t)rng.below((uint64_t)(len - L));
+        const double div = rng.uniform() * max_div;
+        const int strand = (int)(rng.next() >> 63);
+        for (int64_t j = 0; j < L; j++) {
+            char b = strand ? kBases[3 - code_of(f[(size_t)(L - 1 - j)])] : f[(size_t)j];
+            if (rng.uniform() < div) b = kBases[(code_of(b) + 1 + (int)rng.below(3)) & 3];
+            ref[pos + j] = b;
+        }
+        placed += L;
+    }
+}
+
 // Reads first_index .. first_index+n-1 of the read set `seed`, each exactly read_len bases, concatenated into `out`.
 // truth (optional, 2 int64 per read): template start on the reference, strand (0 '+', 1 '-').
 void dps_reads(const char* ref, int64_t ref_len, int circular, uint64_t seed, int64_t first_index, int64_t n,

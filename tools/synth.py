@@ -30,6 +30,9 @@ def _load():
                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _lib.dps_reads.restype = None
+        _lib.dps_make_repeats.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int, ctypes.c_double,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_double]
+        _lib.dps_make_repeats.restype = None
     return _lib
 
 
@@ -41,6 +44,14 @@ def reference(seed, length):
     """uint8 numpy array of `length` ASCII bases (uniform i.i.d. ACGT)."""
     out = np.empty(length, dtype=np.uint8)
     _load().dps_reference(seed, length, out.ctypes.data, _threads())
+    return out
+
+
+def reference_rep(seed, length, families=50, frac=0.10, min_len=300, max_len=6000, max_div=0.15):
+    """The `rep` variant of reference(seed, length): about `frac` of its bases replaced by copies of
+    `families` random repeat units of min_len..max_len bases at 0..max_div substitution divergence, either strand."""
+    out = reference(seed, length)
+    _load().dps_make_repeats(out.ctypes.data, length, seed, families, frac, min_len, max_len, max_div)
     return out
 
 
