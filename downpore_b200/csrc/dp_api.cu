@@ -187,6 +187,8 @@ struct dp_mapper {
     DBuf<int> chunkPos, chunkScanLen, postPos;
     int filterBits = 0;
     DBuf<long long> chunkOffset, chunkInset;
+    DBuf<unsigned> midPost;
+    DBuf<uint4> midSeed;  // derived from seedOff / seedChunks when the mapper is opened (not part of the image)
     std::vector<long long> hChunkOffset, hChunkInset;
     std::vector<int> hChunkLen, hChunkScanLen;
     DpIndexDev I{};
@@ -207,6 +209,8 @@ namespace {
 // ----------------------------------------------------------------------------------------------------------------
 // index construction (mapping.NewMapper, mapping/mapping.go:67-109)
 // ----------------------------------------------------------------------------------------------------------------
+void build_mid_postings(dp_mapper& M);
+
 void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     const int k = M.k;
     const long long L = M.refLen;
@@ -519,6 +523,45 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
                    M.chunkOff.bytes() + M.chunkPos.bytes() + M.chunkSeed.bytes() + M.chunkOffset.bytes() +
                    M.postOff.bytes() + M.postChunk.bytes() + M.postPos.bytes() + M.filter.bytes() +
                    M.chunkInset.bytes() + M.chunkScanLen.bytes();
+    build_mid_postings(M);
+}
+
+// dp_lookup_mid_kernel: a byte counter per chunk for each warp, at least three CTAs of four warps per SM
+const unsigned kLookupMidMaxChunks = 16384;
+
+// The mid-lookup copy of the seed -> chunks runs (DpIndexDev::midOff / midPost): derived data, rebuilt whenever a mapper
+// is opened (from a reference or from an index image), for indexes dp_lookup_mid_kernel can take.
+void build_mid_postings(dp_mapper& M) {
+    DpIndexDev& I = M.I;
+    I.midSeed = nullptr;
+    I.midPost = nullptr;
+    if (I.numChunks > kLookupMidMaxChunks || I.numSeeds == 0) return;
+    cudaStream_t st = M.stream;
+    const unsigned S = I.numSeeds;
+    DBuf<unsigned> blocks;
+    blocks.reserve((size_t)S + 1);
+    DBuf<unsigned> midOff;
+    midOff.reserve((size_t)S + 1);
+    M.midSeed.reserve((size_t)S);
+    dp_mid_blocks_kernel<<<div_up((long long)S + 1, 256), 256, 0, st>>>(I.seedOff, S, blocks.p);
+    CK(cudaGetLastError());
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, blocks.p, midOff.p, (int)S + 1, st);
+    DBuf<unsigned char> tmp;
+    tmp.reserve(tmpBytes);
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, blocks.p, midOff.p, (int)S + 1, st));
+    unsigned total = 0;
+    CK(cudaMemcpyAsync(&total, midOff.p + S, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (total >= (1u << 28)) return;  // (item descriptors carry a 28-bit block index; far beyond any index of <= 16384 chunks)
+    M.midPost.reserve((size_t)total * 4 + 4);
+    const unsigned padWord = (dp_mid_words(I.numChunks) - 32u) * 4u;
+    dp_mid_fill_kernel<<<M.smCount * 8, 256, 0, st>>>(I.seedOff, I.seedChunks, midOff.p, S, padWord, M.midPost.p, M.midSeed.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    I.midSeed = M.midSeed.p;
+    I.midPost = reinterpret_cast<const uint4*>(M.midPost.p);
+    M.indexBytes += M.midSeed.bytes() + M.midPost.bytes();
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -547,10 +590,18 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+bool use_mid_lookup(const DpIndexDev& I) {
+    if (getenv("DP_LOOKUP_BLOCK") && atoi(getenv("DP_LOOKUP_BLOCK")) != 0) return false;
+    if (!I.midPost) return false;
+    const int mid = env_int("DP_LOOKUP_MID", -1);  // tests: 1 forces it on small references, 0 switches it off
+    if (mid >= 0) return mid != 0;
+    return I.numChunks > DP_SMALL_CHUNKS;
+}
+
 LookupBlockPlan plan_block_lookup(const DpIndexDev& I, double avgRun) {
     LookupBlockPlan P;
     const char* env = getenv("DP_LOOKUP_BLOCK");
-    bool want = I.numChunks >= kLookupBlockMinChunks;
+    bool want = I.numChunks >= kLookupBlockMinChunks && !use_mid_lookup(I);
     if (env) want = atoi(env) != 0;
     if (!want) return P;
     // what a window strand is expected to look like: seeds per strand, postings per strand
@@ -810,6 +861,26 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             // window strands the CTA kernel deferred (a seed present in every chunk): none on real references
             int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock, (size_t)M.smCount * 2);
             dp_lookup_kernel<<<dBlocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), G.deferList, G.nDefer, S, inSmem,
+                                                                   W.candN.p, W.candChunk.p, W.candDistinct.p,
+                                                                   W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            W.stats.kernel_launches += 1;
+        } else if (use_mid_lookup(I)) {
+            // a few thousand chunks (BASELINE config 3): warp per window strand, many loads in flight, 16-bit counters
+            // in shared memory; the general kernel takes what it hands back
+            int* deferList = W.lbDefer.p;
+            int* nDefer = reinterpret_cast<int*>(W.lbWork.p + 1);
+            CK(cudaMemsetAsync(W.lbWork.p, 0, 4 * sizeof(unsigned), st));
+            const size_t mSmem = (size_t)DP_MID_WARPS * dp_mid_words(I.numChunks) * sizeof(unsigned);
+            int ctas = (int)std::max<size_t>(1, std::min<size_t>(5, (227 * 1024) / (mSmem + sizeof(DpMidWarp) * DP_MID_WARPS + 64 + 1024)));
+            ctas = std::max(1, std::min(ctas, env_int("DP_LOOKUP_CTAS", 8)));  // measurements
+            int mBlocks = (int)std::min<size_t>((2 * nWin + DP_MID_WARPS - 1) / DP_MID_WARPS, (size_t)M.smCount * ctas);
+            dp_lookup_mid_kernel<6><<<mBlocks, 32 * DP_MID_WARPS, mSmem, st>>>(
+                I, Q, (int)(2 * nWin), deferList, nDefer, W.candN.p, W.candChunk.p, W.candDistinct.p, W.candStride, W.dCtr.p);
+            CK(cudaGetLastError());
+            int dBlocks = (int)std::min<size_t>((2 * nWin + warpsPerBlock - 1) / warpsPerBlock,
+                                                (size_t)M.smCount * (headroom ? 6 : 8));
+            dp_lookup_kernel<<<dBlocks, 32 * DP_LWARPS, smem, st>>>(I, Q, (int)(2 * nWin), deferList, nDefer, S, inSmem,
                                                                    W.candN.p, W.candChunk.p, W.candDistinct.p,
                                                                    W.candStride, W.dCtr.p);
             CK(cudaGetLastError());
@@ -1590,6 +1661,7 @@ std::unique_ptr<dp_mapper> open_mapper(int device) {
     CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(dp_lookup_mid_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_block_kernel<128, 8, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1796,6 +1868,7 @@ int dp_mapper_create_from_index(const void* image, int64_t bytes, int device, dp
     CK(cudaMemcpy(M->hChunkInset.data(), I.chunkInset, C * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(M->hChunkScanLen.data(), I.chunkScanLen, C * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(M->hChunkLen.data(), b + H.off[IX_CHUNKLEN], C * 4, cudaMemcpyDeviceToHost));
+    build_mid_postings(*M);
     *out = M.release();
     API_CATCH
 }

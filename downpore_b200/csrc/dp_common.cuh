@@ -41,6 +41,11 @@ struct DpIndexDev {
     const long long* chunkOffset;  // SeedSequence.offset of the chunk
     const long long* chunkInset;   // SeedSequence.inset of the chunk (Q3: one too large for SubSequence chunks)
     const int* chunkScanLen;       // sum of the chunk's segments (bases actually scanned, Q2)
+    // derived copy of the seed -> chunks runs for dp_lookup_mid_kernel (indexes of at most 16384 chunks; else null):
+    // every run starts on a 16-byte block and is padded to whole blocks; a posting is stored ready to count,
+    // (byte offset of the chunk's counter word) << 16 | (PRMT selector that puts a 1 into the chunk's byte of that word)
+    const uint4* midSeed;  // [S] {first posting in seedChunks, run length, first 16-byte block in midPost, last chunk >> 6}
+    const uint4* midPost;
 };
 
 // One performMapping() call (mapping/mapping.go:489-611): window [start, start+len) of read `read`.

@@ -458,3 +458,34 @@ __global__ void dp_posting_fill_kernel(const unsigned long long* __restrict__ ke
         seedChunks[i] = (unsigned)key;
     }
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// The mid-lookup copy of the seed -> chunks runs (DpIndexDev::midOff / midPost)
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void dp_mid_blocks_kernel(const unsigned* __restrict__ seedOff, unsigned numSeeds, unsigned* __restrict__ blocks) {
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= numSeeds) blocks[s] = s < numSeeds ? (seedOff[s + 1] - seedOff[s] + 3u) >> 2 : 0u;
+}
+
+// padWord: byte offset of the first dummy counter word (a padding posting adds zero to one of the 32 dummy words)
+__global__ void dp_mid_fill_kernel(const unsigned* __restrict__ seedOff, const unsigned* __restrict__ seedChunks,
+                                   const unsigned* __restrict__ midOff, unsigned numSeeds, unsigned padWord,
+                                   unsigned* __restrict__ midPost, uint4* __restrict__ midSeed) {
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const unsigned nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned s = warp; s < numSeeds; s += nWarps) {
+        const unsigned o = seedOff[s], n = seedOff[s + 1] - o;
+        const unsigned b = midOff[s] * 4u, slots = (midOff[s + 1] - midOff[s]) * 4u;
+        if (lane == 0) midSeed[s] = make_uint4(o, n, midOff[s], n ? seedChunks[o + n - 1] >> 6 : 0u);
+        for (unsigned i = lane; i < slots; i += 32) {
+            unsigned p;
+            if (i < n) {
+                const unsigned c = seedChunks[o + i];
+                p = ((c & ~3u) << 16) | (0x1111u ^ (1u << ((c & 3u) << 2)));
+            } else {
+                p = ((padWord + (i & 31u) * 4u) << 16) | 0x1111u;
+            }
+            midPost[b + i] = p;
+        }
+    }
+}

@@ -1003,6 +1003,18 @@ __device__ __forceinline__ uint4 dp_load_postings(const uint4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// 16 bytes of an index table that should outlive the streams passing through L2 beside it
+__device__ __forceinline__ unsigned long long dp_policy_evict_last() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 dp_load_index16(const uint4* p, unsigned long long pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
 
 // one posting into the group counters: shared-memory reduction (no return value); a posting outside the item's range
 // goes to the lane's private dummy counter instead (no branch, no bank conflict among the dummies)
@@ -1377,6 +1389,398 @@ __global__ void __launch_bounds__(THREADS, MINB) dp_lookup_block_kernel(DpIndexD
         __syncthreads();
     }
     if (tid == 0 && (cRuns | cCand)) {
+        atomicAdd(&ctr->posting_runs, cRuns);
+        atomicAdd(&ctr->posting_entries, cEntries);
+        atomicAdd(&ctr->candidates, cCand);
+    }
+}
+
+// ===============================================================================================================
+// Stage 2 for indexes of a few thousand chunks — one WARP per window strand with many loads in flight
+// (dp_lookup_mid_kernel; BASELINE config 3: 6 465 chunks, ~70 seeds and ~1 650 postings per window strand).
+//
+// The whole index (tens of MB) sits in L2 here, so the kernel is bound by the chain of dependent loads of one window
+// strand and by the shared-memory reductions, not by bytes. dp_lookup_kernel walks that chain one posting per lane at a
+// time (~50 round trips); the CTA-per-window-strand kernel spends ~20 barriers on 1 650 postings. This kernel keeps the
+// warp as the unit (no barrier anywhere) and takes the round trips out of the chain:
+//   * the header of the next window strand is loaded an iteration ahead and its seeds are copied into shared memory by
+//     cp.async while the current window strand is counted;
+//   * ONE 16-byte gather per seed (DpIndexDev::midSeed: first posting, run length, first block of the padded copy, last
+//     chunk >> 6) replaces the two CSR offsets and the run's last posting, four seeds per lane issued together;
+//   * the runs are read from a copy made when the mapper is opened (DpIndexDev::midPost): every run starts on a 16-byte
+//     block and is padded to whole blocks, a posting is stored ready to count — (byte offset of the chunk's counter
+//     word) << 16 | (PRMT selector placing a 1 in the chunk's byte) — so a posting costs LEA.HI + PRMT + ATOMS and no
+//     range test. Items of up to 8 blocks (8 lanes x uint4, four items per warp-wide load); a lane keeps a ring of NI
+//     loads in flight and refills a slot as soon as it has counted it. The index loads carry an L2 evict_last policy:
+//     the seed lists of 10^5 window strands stream through L2 beside them;
+//   * at most DP_MID_ECAP = 128 included runs means a chunk's count stays below 256: ONE BYTE per chunk, four chunks
+//     per 32-bit word of the warp's slice of shared memory (6.5 KB for config 3, so 20 warps stay resident per SM).
+//     Postings are added with shared-memory reductions (no return value: nothing waits on them); one pass of 16-byte
+//     loads finds the bytes that reached the threshold (adding 128 - T cannot carry: bit 7 = "count >= T") and blanks
+//     the counters on the way;
+//   * repeated seeds among the included runs (needed for the distinct-seed count) are found through a hash table that
+//     borrows the still blank counter array: slot -> index of the run that claimed it, always verified against the
+//     run's seed; the rare slot taken by a different seed is settled by a warp-wide compare.
+// Level clamp (Q11), level-16 under-count (Q6) and the distinct counts: dp_refine_emit, as in the other kernels.
+// Window strands outside its bounds (more than DP_MID_ECAP seeds, a seed present in every chunk, more than DP_MID_CAND
+// chunks over the threshold) go to dp_lookup_kernel through a list, with identical results.
+// Measured (profiles/r2i_*): 9.13 -> 4.83 ms per 262 144 reads of config 3 against dp_lookup_block_kernel.
+// ===============================================================================================================
+#define DP_MID_WARPS 4
+#define DP_MID_ECAP 128   // query seeds per window strand (a byte counter holds up to 255)
+#define DP_MID_ITEMS 128  // gather items listed at a time
+#define DP_MID_CAND 64    // chunks over the threshold
+#define DP_MID_DUP 32     // repeated-seed runs listed
+
+struct DpMidWarp {  // shared memory of one warp
+    unsigned eSeed[DP_MID_ECAP];
+    unsigned eOff[DP_MID_ECAP];
+    unsigned ePre[DP_MID_ECAP + 1];
+    unsigned eItem[DP_MID_ECAP + 1];
+    unsigned eEndW[DP_MID_ECAP];
+    unsigned eMid[DP_MID_ECAP];         // first 16-byte block of the run in the mid-lookup copy of the postings
+    unsigned itemStart[DP_MID_ITEMS];   // first 16-byte block of the item | (blocks - 1) << 28
+    unsigned long long cand[DP_MID_CAND];
+    unsigned short order[DP_MID_ECAP];
+    unsigned short dup[DP_MID_DUP];
+    unsigned char eFirst[DP_MID_ECAP];
+    int sim[2];
+    int nCand;
+    int pad;
+};
+
+// words of one warp's byte counters (+ 32 dummy words), a multiple of 4
+__host__ __device__ inline unsigned dp_mid_words(unsigned numChunks) { return ((((numChunks + 3u) >> 2) + 3u) & ~3u) + 32u; }
+
+// the seeds of a window strand into a warp's shared memory, four per lane, without passing through registers
+__device__ __forceinline__ void dp_mid_stage_seeds(unsigned seedAddr, const unsigned* __restrict__ qSeed, unsigned qb, int n,
+                                                   unsigned lane) {
+    if (n < 5 || n > DP_MID_ECAP) return;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int j = r * 32 + (int)lane;
+        if (j < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(seedAddr + 4u * (unsigned)j), "l"(qSeed + qb + j) : "memory");
+    }
+}
+
+template <int NI>
+__global__ void __launch_bounds__(32 * DP_MID_WARPS, 5) dp_lookup_mid_kernel(DpIndexDev I, DpExtractOut Q, int nWS,
+                                                                             int* __restrict__ deferList,
+                                                                             int* __restrict__ nDefer,
+                                                                             int* __restrict__ candN,
+                                                                             unsigned* __restrict__ candChunk,
+                                                                             unsigned short* __restrict__ candDistinct,
+                                                                             int candStride, DpCounters* __restrict__ ctr) {
+    extern __shared__ unsigned dp_smem[];  // DP_MID_WARPS x dp_mid_words(C): byte counters | 32 dummy words
+    __shared__ DpMidWarp shW[DP_MID_WARPS];
+    const unsigned lane = dp_lane();
+    const unsigned lt = dp_lanemask_lt();
+    const int wib = threadIdx.x >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned C = I.numChunks;
+    const unsigned cWords = dp_mid_words(C) - 32u;
+    unsigned* cnt = dp_smem + (size_t)wib * (cWords + 32u);
+    unsigned short* h16 = reinterpret_cast<unsigned short*>(cnt);  // the blank counters double as the seed hash table
+    const unsigned hSlots = C >> 1;                                 // 16-bit slots inside the C counter bytes
+    DpMidWarp& W = shW[wib];
+    for (unsigned c = lane; c < cWords; c += 32) cnt[c] = 0;
+    __syncwarp();
+    const unsigned cntAddr = (unsigned)__cvta_generic_to_shared(cnt);
+    const uint4* post4 = I.midPost;
+    const unsigned long long keep = dp_policy_evict_last();  // the index outlives the seed lists streaming through L2
+    unsigned long long cRuns = 0, cEntries = 0, cCand = 0;
+    // The seeds of the NEXT window strand are copied into W.eSeed (cp.async, no registers) while the current one is
+    // counted, and its header is loaded an iteration ahead: two of the dependent round trips leave the chain.
+    const unsigned seedAddr = (unsigned)__cvta_generic_to_shared(W.eSeed);
+    int ws = gwarp;
+    int n = 0;
+    unsigned qb = 0;
+    if (ws < nWS) {
+        n = Q.wsN[ws];
+        qb = Q.wsOff[ws];
+        dp_mid_stage_seeds(seedAddr, Q.qSeed, qb, n, lane);
+    }
+    for (; ws < nWS; ws += nWarps) {
+        int nNext = 0;
+        unsigned qbNext = 0;
+        if (ws + nWarps < nWS) {
+            nNext = Q.wsN[ws + nWarps];
+            qbNext = Q.wsOff[ws + nWarps];
+        }
+        bool staged = false;
+        int nOut = 0;
+        bool defer = n > DP_MID_ECAP;
+        if (n >= 5 && !defer) {
+            // ---- the window strand's seeds and posting runs: 4 per lane, all loads of a level issued together ----
+            unsigned s[4], o[4], c[4], m[4], ew[4];
+            asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int j = r * 32 + (int)lane;
+                s[r] = j < n ? W.eSeed[j] : 0xffffffffu;  // (a lane reads what it copied itself)
+            }
+            __syncwarp();  // the compaction below rewrites W.eSeed
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const bool valid = r * 32 + (int)lane < n;
+                // one 16-byte gather per seed: {first posting, run length, first block of the padded copy, last chunk >> 6}
+                uint4 e = make_uint4(0, 0, 0, 0);
+                if (valid) e = dp_load_index16(I.midSeed + s[r], keep);
+                o[r] = e.x;
+                c[r] = e.y;
+                m[r] = e.z;
+                ew[r] = e.w;
+            }
+            bool sawAll = false;
+#pragma unroll
+            for (int r = 0; r < 4; r++) sawAll |= (r * 32 + (int)lane < n) && c[r] >= C;
+            defer = __any_sync(DP_FULL, sawAll);  // a seed present in every chunk: the general kernel's business
+            if (!defer) {
+                // ---- inclusion filter (seeds.go:340-346): every occurrence is eligible here; repeats of the previous
+                //      occurrence's seed are skipped. Ordered compaction into shared memory ----
+                int nInc = 0;
+                unsigned carry = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const bool valid = r * 32 + (int)lane < n;
+                    unsigned prev = __shfl_up_sync(DP_FULL, s[r], 1);
+                    if (lane == 0) prev = carry;
+                    const bool inc = valid && s[r] != prev;
+                    carry = __shfl_sync(DP_FULL, s[r], 31);
+                    const unsigned mi = __ballot_sync(DP_FULL, inc);
+                    if (inc) {
+                        const int idx = nInc + __popc(mi & lt);
+                        W.eSeed[idx] = s[r];
+                        W.eOff[idx] = o[r];
+                        W.ePre[idx] = c[r];  // run length for now; prefix-summed below
+                        W.eMid[idx] = m[r];
+                        W.eEndW[idx] = ew[r];  // bounds the run for the level clamp's early stop (Q11) and the Q6 simulation
+                    }
+                    nInc += __popc(mi);
+                }
+                __syncwarp();
+                if (nInc >= 5) {
+                    const int minCount = (nInc + 2) >> 2;
+                    int T;
+                    bool clamped = false;
+                    if (minCount >= 9 && minCount <= 12) {
+                        T = 8;
+                        clamped = true;
+                    } else if (minCount >= 17 && minCount <= 24) {
+                        T = 16;
+                        clamped = true;
+                    } else {
+                        T = minCount;
+                    }
+                    const bool q6 = minCount >= 13 && minCount <= 24;  // level-16 plane decides alone
+                    // ---- per included run: repeated seed?, prefixes of postings and items ----
+                    unsigned total = 0, nItems = 0;
+                    int nDup = 0;
+                    const int nRounds = (nInc + 31) >> 5;
+                    for (int r = 0; r < nRounds; r++) {
+                        const int j = r * 32 + (int)lane;
+                        const bool have = j < nInc;
+                        const unsigned es = have ? W.eSeed[j] : (0x80000000u | lane);  // (seed ranks are below 2^31)
+                        const unsigned ec = have ? W.ePre[j] : 0u;
+                        // repeated seed: inside the round by __match_any_sync, against earlier rounds through the hash
+                        const unsigned mm = __match_any_sync(DP_FULL, es);
+                        const bool leader = have && (__ffs(mm) - 1) == (int)lane;
+                        const unsigned slot = __umulhi(es * 0x9E3779B1u, hSlots);
+                        const unsigned t = leader ? (unsigned)h16[slot] : 0u;
+                        __syncwarp();
+                        bool isDup = have && !leader, unsure = false;
+                        if (leader) {
+                            if (t == 0) h16[slot] = (unsigned short)(j + 1);
+                            else if (W.eSeed[t - 1] == es) isDup = true;
+                            else unsure = true;  // the slot belongs to another seed: compare with every earlier run
+                        }
+                        unsigned mu = __ballot_sync(DP_FULL, unsure);
+                        while (mu) {
+                            const int l = __ffs(mu) - 1;
+                            mu &= mu - 1;
+                            const unsigned ss = __shfl_sync(DP_FULL, es, l);
+                            bool found = false;
+                            for (int q = 0; q < r; q++) found |= W.eSeed[q * 32 + (int)lane] == ss;
+                            if (__any_sync(DP_FULL, found) && (int)lane == l) isDup = true;
+                        }
+                        if (have) W.eFirst[j] = isDup ? 0 : 1;
+                        const unsigned md = __ballot_sync(DP_FULL, isDup);
+                        if (nDup >= 0) {
+                            if (nDup + __popc(md) > DP_MID_DUP) nDup = -1;
+                            else {
+                                if (isDup) W.dup[nDup + __popc(md & lt)] = (unsigned short)j;
+                                nDup += __popc(md);
+                            }
+                        }
+                        // items of the run: pieces of 8 blocks (32 postings) of its padded copy
+                        const unsigned items = (ec + 31u) >> 5;
+                        unsigned xa = ec, xb = items;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const unsigned ya = __shfl_up_sync(DP_FULL, xa, d), yb = __shfl_up_sync(DP_FULL, xb, d);
+                            if ((int)lane >= d) {
+                                xa += ya;
+                                xb += yb;
+                            }
+                        }
+                        if (have) {
+                            W.ePre[j] = total + xa - ec;
+                            W.eItem[j] = nItems + xb - items;
+                        }
+                        total += __shfl_sync(DP_FULL, xa, 31);
+                        nItems += __shfl_sync(DP_FULL, xb, 31);
+                    }
+                    if (lane == 0) {
+                        W.ePre[nInc] = total;
+                        W.eItem[nInc] = nItems;
+                        W.nCand = 0;
+                    }
+                    __syncwarp();
+                    // hand the borrowed hash slots back blank
+                    for (int j = (int)lane; j < nInc; j += 32) h16[__umulhi(W.eSeed[j] * 0x9E3779B1u, hSlots)] = 0;
+                    __syncwarp();
+                    // W.eSeed is dead from here on: the next window strand's seeds arrive while this one is counted
+                    dp_mid_stage_seeds(seedAddr, Q.qSeed, qbNext, nNext, lane);
+                    staged = true;
+                    // ---- stream the runs into the byte counters ----
+                    for (unsigned d0 = 0; d0 < nItems; d0 += DP_MID_ITEMS) {
+                        const unsigned dN = min((unsigned)DP_MID_ITEMS, nItems - d0);
+                        for (int j = (int)lane; j < nInc; j += 32) {
+                            const unsigned first = W.eItem[j], last = W.eItem[j + 1];  // this run's items
+                            if (last <= d0 || first >= d0 + dN) continue;
+                            const unsigned blocks = (W.ePre[j + 1] - W.ePre[j] + 3u) >> 2, mo = W.eMid[j];
+                            for (unsigned it = max(first, d0); it < min(last, d0 + dN); it++) {
+                                const unsigned b0 = (it - first) << 3;
+                                W.itemStart[it - d0] = (mo + b0) | ((min(8u, blocks - b0) - 1u) << 28);
+                            }
+                        }
+                        __syncwarp();
+                        // 8 lanes x 16 bytes per item, 4 items per warp-wide load; a ring of NI loads per lane: a slot is
+                        // refilled as soon as it has been counted, so NI - 1 loads stay in flight throughout
+                        const unsigned sub = lane >> 3, ln = lane & 7u;
+                        uint4 v[NI];
+                        unsigned ok = 0;  // bit d: slot d holds a block of postings
+#pragma unroll
+                        for (int d = 0; d < NI; d++) {
+                            const unsigned idx = (unsigned)d * 4u + sub;
+                            const unsigned desc = idx < dN ? W.itemStart[idx] : 0u;
+                            if (idx < dN && ln <= (desc >> 28)) {
+                                v[d] = dp_load_index16(post4 + (desc & 0x0fffffffu) + ln, keep);
+                                ok |= 1u << d;
+                            }
+                        }
+                        for (unsigned it = 0; it < dN; it += NI * 4) {
+#pragma unroll
+                            for (int d = 0; d < NI; d++) {
+                                if (ok & (1u << d)) {
+                                    const unsigned vv[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {  // a posting = counter word offset << 16 | byte selector
+                                        unsigned one;
+                                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(one) : "r"(1u), "r"(0u), "r"(vv[e]));
+                                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cntAddr + (vv[e] >> 16)), "r"(one) : "memory");
+                                    }
+                                }
+                                // refill the slot
+                                const unsigned idx = it + (unsigned)(NI * 4) + (unsigned)d * 4u + sub;
+                                const unsigned desc = idx < dN ? W.itemStart[idx] : 0u;
+                                ok &= ~(1u << d);
+                                if (idx < dN && ln <= (desc >> 28)) {
+                                    v[d] = dp_load_index16(post4 + (desc & 0x0fffffffu) + ln, keep);
+                                    ok |= 1u << d;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    // ---- bytes that reached the threshold (SIMD byte compare); the counters are blanked on the way ----
+                    if (total) {
+                        uint4* cnt4 = reinterpret_cast<uint4*>(cnt);
+                        // a chunk is counted at most once per run and there are at most 128 runs: adding 128 - T to every
+                        // byte cannot carry, and bit 7 of a byte then says "count >= T"
+                        const unsigned K4 = (unsigned)(128 - T) * 0x01010101u;
+                        for (unsigned c4 = lane; c4 < (cWords >> 2); c4 += 32) {
+                            const uint4 x = cnt4[c4];
+                            cnt4[c4] = make_uint4(0, 0, 0, 0);
+                            const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+                            const unsigned hit = ((x.x + K4) | (x.y + K4) | (x.z + K4) | (x.w + K4)) & 0x80808080u;
+                            if (hit) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+#pragma unroll
+                                    for (int b8 = 0; b8 < 4; b8++) {
+                                        const unsigned v = (xs[i] >> (8 * b8)) & 0xffu;
+                                        if ((int)v >= T) {
+                                            const int slotC = atomicAdd(&W.nCand, 1);
+                                            if (slotC < DP_MID_CAND)
+                                                W.cand[slotC] = ((unsigned long long)(c4 * 16u + (unsigned)i * 4u + (unsigned)b8) << 32) | v;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const int nCand = W.nCand;
+                    if (nCand > DP_MID_CAND) {
+                        defer = true;  // (the general kernel lists candidates in memory)
+                    } else {
+                        cRuns += (unsigned)nInc;
+                        cEntries += total;
+                        if (nCand > 0) {
+                            // ascending chunk id (rank sort in registers: chunk ids are distinct)
+                            unsigned long long e0 = (int)lane < nCand ? W.cand[lane] : ~0ull;
+                            unsigned long long e1 = (int)lane + 32 < nCand ? W.cand[lane + 32] : ~0ull;
+                            int r0 = 0, r1 = 0;
+                            for (int y = 0; y < nCand; y++) {
+                                const unsigned cy = (unsigned)(W.cand[y] >> 32);
+                                r0 += cy < (unsigned)(e0 >> 32);
+                                r1 += cy < (unsigned)(e1 >> 32);
+                            }
+                            __syncwarp();
+                            if ((int)lane < nCand) W.cand[r0] = e0;
+                            if ((int)lane + 32 < nCand) W.cand[r1] = e1;
+                            __syncwarp();
+                            DpRefineCtx X;
+                            X.eOff = W.eOff;
+                            X.ePre = W.ePre;
+                            X.eEndW = W.eEndW;
+                            X.eFirst = W.eFirst;
+                            X.dup = W.dup;
+                            X.nDup = nDup;
+                            X.order = W.order;
+                            X.sim = W.sim;
+                            X.nInc = nInc;
+                            X.minCount = minCount;
+                            X.T = T;
+                            X.clamped = clamped;
+                            X.q6 = q6;
+                            X.nAllDistinct = 0;
+                            nOut = dp_refine_emit<false>(I, X, W.cand, nCand, candChunk + (size_t)ws * candStride,
+                                                         candDistinct + (size_t)ws * candStride, candStride);
+                            if (nOut > candStride) {
+                                if (lane == 0) atomicOr(&ctr->overflow, DP_OV_CANDS);
+                                nOut = candStride;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) {
+            if (defer) deferList[atomicAdd(nDefer, 1)] = ws;
+            else candN[ws] = nOut;
+        }
+        if (!defer) cCand += (unsigned)nOut;
+        if (!staged) {
+            __syncwarp();
+            dp_mid_stage_seeds(seedAddr, Q.qSeed, qbNext, nNext, lane);
+        }
+        n = nNext;
+        qb = qbNext;
+    }
+    if (lane == 0 && (cRuns | cCand)) {
         atomicAdd(&ctr->posting_runs, cRuns);
         atomicAdd(&ctr->posting_entries, cEntries);
         atomicAdd(&ctr->candidates, cCand);

@@ -309,6 +309,8 @@ def large_ref():
 
 @pytest.mark.parametrize("env", [
     {},                                                        # lean register kernel + the general warp kernel for what it defers
+    {"DP_LOOKUP_MID": "1"},                                    # warp per window strand, 16-byte item loads (the config-3 route)
+    {"DP_LOOKUP_MID": "1", "DP_CAP_CANDS": "1"},               # ... with the candidate-capacity retry
     {"DP_LOOKUP_SMALL": "0"},                                  # general warp kernel only, shared-memory counters
     {"DP_LOOKUP_SMEM_CHUNKS": "100"},                          # warp kernel, counters in global memory
     {"DP_LOOKUP_BLOCK": "1"},                                  # CTA per window strand, one counter per chunk, 32-posting items
@@ -333,7 +335,7 @@ def test_lookup_kernels_on_a_large_reference(large_ref, env):
         assert st[key] == octr[key], key
 
 
-@pytest.mark.parametrize("env", [{"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "1", "DP_LOOKUP_SEG": "128"},
+@pytest.mark.parametrize("env", [{"DP_LOOKUP_MID": "1"}, {"DP_LOOKUP_BLOCK": "1"}, {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "1", "DP_LOOKUP_SEG": "128"},
                                  {"DP_LOOKUP_BLOCK": "1", "DP_LOOKUP_GSHIFT": "3", "DP_LOOKUP_GLIST": "1", "DP_LOOKUP_GBATCH": "1"}])
 def test_block_lookup_on_mixed_reads(env):
     """The CTA-per-window-strand lookup on a small circular reference with short, chimeric and whole-read windows
