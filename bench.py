@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
 # profiles/r1k_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = dp_chain_thread_kernel) and
 # profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of config 4)
-TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 50.8e6, "reduce": 95.8e6, "chain": 81.1e6,
+TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 41.0e6, "reduce": 95.8e6, "chain": 81.1e6,
                       "finish": 5.8e6, "lookup_block": 56.87e9}
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures (config 2 is L2-resident: SURVEY 8d asks for
 # issue utilisation beside the HBM fraction there); lookup = dp_lookup_small_kernel (profiles/r1q_ncu_lookup_small.txt)
@@ -38,20 +38,27 @@ ISSUE_ACTIVE_PCT = {"pack": 55.5, "extract": 61.2, "lookup": 68.1, "reduce": 47.
                     "lookup_block": 48.2}
 
 K = 11
-REF_LEN = 4_600_000
-READ_LEN = 10_000
-REF_SEED, READ_SEED = 1, 12
-CIRCULAR = True
-WORKLOAD = "BASELINE config 2"
 EDGE = 1000
+# BASELINE.json configs (SURVEY 8d seeds). `reads` = reads per GPU per step (weak scaling: reads are sharded).
+WORKLOADS = {
+    "config2": dict(name="BASELINE config 2", ref_len=4_600_000, read_len=10_000, ref_seed=1, read_seed=12, circular=True,
+                    reads=1_000_000),
+    "config3": dict(name="BASELINE config 3", ref_len=64_000_000, read_len=20_000, ref_seed=3, read_seed=13, circular=False,
+                    reads=250_000),
+    "config4": dict(name="BASELINE config 4", ref_len=3_100_000_000, read_len=15_000, ref_seed=4, read_seed=14,
+                    circular=False, reads=500_000),
+}
+REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD = 4_600_000, 10_000, 1, 12, True, "BASELINE config 2"
 
 
 def select_workload(name):
     """--workload config2 (default: the configuration the metric is quoted on) | config3 (64 Mb linear reference,
-    20 kb reads; SURVEY 8d seeds 3 / 13). Same contract and JSON line either way."""
+    20 kb reads). Same contract and JSON line either way; the default run also measures config 3 (and config 4 on eight
+    GPUs) and reports them in `configs`."""
     global REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD
-    if name == "config3":
-        REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD = 64_000_000, 20_000, 3, 13, False, "BASELINE config 3"
+    w = WORKLOADS[name]
+    REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD = (w["ref_len"], w["read_len"], w["ref_seed"], w["read_seed"],
+                                                                  w["circular"], w["name"])
 
 
 _JSON_OUT = None
@@ -204,11 +211,12 @@ def run_reference(args):
         om.map_batch(rd, offs, threads=cores)
     dt = (time.time() - t0) / args.steps
     gbps = n * READ_LEN / dt / 1e9
-    sample = "%d of the workload's reads per step (read set seed %d, indices 0..%d)" % (n, READ_SEED, n - 1)
+    sample = ("%d of the workload's %d reads timed per step (read set seed %d, indices 0..%d); a rate, so comparable "
+              "with the GPU arm's whole workload" % (n, args.reads, READ_SEED, n - 1))
     line = {"impl": "reference", "metric": "mapped Gbp/s", "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": config_dict(args, max(world, 1)),
+            "config": config_dict(args, max(world, 1)), "sample_reads_per_step": n,
             "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "C++ restatement of the reference (no Go toolchain in this image), mapping phase only"},
             "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -289,29 +297,23 @@ def bind_to_gpu_numa_node(local):
         return None, None
 
 
-def run_ours(args):
-    import torch
-    rank, world, local = dist_setup(args.gpus)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    numa_node, affinity_before = bind_to_gpu_numa_node(local)
-    import downpore_b200 as dp
-    from tools import synth
-
+def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want_iso=True):
+    """One workload (the module-level REF_LEN/READ_LEN/... selected by select_workload) on this rank's GPU: builds or
+    receives the index, maps `args.reads` reads per step device-resident (`value`) and from pinned host memory (`e2e`),
+    and times every kernel family on a single lane. Returns a dict of rank-local and reduced results."""
     ref = synth.reference(REF_SEED, REF_LEN)
     t_c0 = time.time()
-    counts = dp.kmer_counts(ref, K, device=local)
-    vals = dp.kmer_values(counts, K)
-    t1 = time.time()
-    t_counts = t1 - t_c0
-    t_repl = 0.0
+    t_counts = t_index = t_repl = 0.0
     if world > 1 and args.index == "broadcast":
         # SURVEY 8e: the index is built once (rank 0) and replicated by ONE NCCL broadcast of its image over NVLink
-        gm = dp.Mapper(ref, vals, circular=CIRCULAR, device=local) if rank == 0 else None
-        torch.cuda.synchronize()
-        t_index = time.time() - t1
+        gm = None
+        if rank == 0:
+            vals = dp.kmer_values(dp.kmer_counts(ref, K, device=local), K)
+            t_counts = time.time() - t_c0
+            t1 = time.time()
+            gm = dp.Mapper(ref, vals, circular=CIRCULAR, device=local)
+            torch.cuda.synchronize()
+            t_index = time.time() - t1
         barrier(world)
         t2 = time.time()
         gm = dp.replicate_index(gm, src=0, device=local)
@@ -319,6 +321,9 @@ def run_ours(args):
         barrier(world)
         t_repl = time.time() - t2
     else:
+        vals = dp.kmer_values(dp.kmer_counts(ref, K, device=local), K)
+        t_counts = time.time() - t_c0
+        t1 = time.time()
         gm = dp.Mapper(ref, vals, circular=CIRCULAR, device=local)
         torch.cuda.synchronize()
         t_index = time.time() - t1
@@ -341,7 +346,7 @@ def run_ours(args):
         return gm.map_batch_ptr(pinned.data_ptr(), offs)
 
     # ---- device-resident: `value` ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     sampler = ClockSampler(local)
     agg = None
@@ -352,7 +357,7 @@ def run_ours(args):
         sampler.start()
     t0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         maps, off = step_device()   # returns after the library has synchronised its streams (results are on the host)
         st = gm.stats()
         if agg is None:
@@ -371,13 +376,13 @@ def run_ours(args):
     d2h_bytes = int(len(maps) * 32 + (n + 1) * 8)
 
     # ---- end to end from pinned host memory: `e2e` ----
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(min(warmup, 2)):
         step_host()
     barrier(world)
     torch.cuda.synchronize()
     t0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
     ev1.record()
     torch.cuda.synchronize()
@@ -386,117 +391,241 @@ def run_ours(args):
     dt_e2e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, world, dev)
     st_e2e = gm.stats()
 
-    # ---- per-kernel durations for the roofline: one extra untimed-for-`value` step on a single lane, so that the
+    # ---- per-kernel durations for the roofline: extra untimed-for-`value` steps on a single lane, so that the
     #      CUDA-event brackets on the launching stream see each kernel alone (with several lanes the brackets of
     #      concurrently running kernels overlap and each reads long) ----
-    os.environ["DP_LANES"] = "1"
-    step_device()
-    step_device()
-    iso = gm.stats()
-    del os.environ["DP_LANES"]
+    iso = None
+    if want_iso:
+        os.environ["DP_LANES"] = "1"
+        step_device()
+        step_device()
+        iso = gm.stats()
+        del os.environ["DP_LANES"]
 
     total_bases = sum_over_ranks(float(bases_rank), world, dev)
-    value = total_bases * args.steps / dt_dev / 1e9
-    e2e = total_bases * args.steps / dt_e2e / 1e9
-
+    S = steps
+    res = {"value": total_bases * steps / dt_dev / 1e9, "e2e": total_bases * steps / dt_e2e / 1e9,
+           "ms_per_step": dt_dev / steps * 1e3, "wall_ms_per_step": wall_dev / steps * 1e3,
+           "e2e_ms_per_step": dt_e2e / steps * 1e3, "e2e_wall_ms_per_step": wall_e2e / steps * 1e3,
+           "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] + (n + 1) * 8), "d2h_bytes_per_step": d2h_bytes,
+           "host_buffer_bytes_per_step": int(bases_rank), "mapped_fraction": mapped_frac, "bases_per_step": total_bases,
+           "clocks": clocks, "gpu_launches": int(agg["kernel_launches"]), "steps": steps, "warmup": warmup,
+           "index": dict(info, build_s=t_index, replicate_s=t_repl, kmer_count_and_values_s=t_counts,
+                         replication=("one NCCL broadcast of the index image from rank 0" if world > 1 and
+                                      args.index == "broadcast" else "built on every rank")),
+           "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
     # ---- roofline of every kernel family (algorithmic bytes: SURVEY.md 8d canonical accounting) ----
-    peak, peak_src = measured_peaks()
-    S = args.steps
-    ws = 2 * agg["windows"] / S            # window strands per step
-    bytes_pack = 1.25 * EDGE * agg["windows"] / S  # only the queried windows are packed
-    bytes_extract = ws * ((EDGE + 3) // 4) + 4.0 * agg["kmer_lookups"] / S
-    bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
-    bytes_chain = 8.0 * agg["chain_cells"] / S
-    kern = {}
-    # (iso["ms_chain"] includes Map()'s first decision, dp_finish_round0_kernel: a kernel of its own, listed as such)
-    ms_finish = iso.get("ms_finish", 0.0)
-    bytes_finish = 32.0 * agg["mappings"] / S
-    for name, b, ms in (("pack", bytes_pack, iso["ms_pack"]), ("extract", bytes_extract, iso["ms_extract"]),
-                        ("lookup", bytes_lookup, iso["ms_lookup"]), ("reduce", bytes_chain, iso["ms_reduce"]),
-                        ("chain", bytes_chain, iso["ms_chain"] - ms_finish), ("finish", bytes_finish, ms_finish)):
-        ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b, "achieved_GBs": ach, "frac": ach / peak}
-    dominant = max(kern, key=lambda k2: kern[k2]["ms_per_step"])
-    # dram bytes per launch of one 65536-read sub-batch from the committed `ncu --set full` capture (profiles/)
-    traffic = TRAFFIC_PER_LAUNCH
+    if iso is not None:
+        peak, peak_src = measured_peaks()
+        ws = 2 * agg["windows"] / S            # window strands per step
+        bytes_pack = 1.25 * EDGE * agg["windows"] / S  # only the queried windows are packed
+        bytes_extract = ws * ((EDGE + 3) // 4) + 4.0 * agg["kmer_lookups"] / S
+        bytes_lookup = 16.0 * agg["posting_runs"] / S + 8.0 * agg["posting_entries"] / S
+        bytes_lookup_actual = 16.0 * agg["posting_runs"] / S + 4.0 * agg["posting_entries"] / S  # 16 B gather per run, 4 B per posting
+        bytes_chain = 8.0 * agg["chain_cells"] / S
+        # (iso["ms_chain"] includes Map()'s first decision, dp_finish_round0_kernel: a kernel of its own, listed as such)
+        ms_finish = iso.get("ms_finish", 0.0)
+        bytes_finish = 32.0 * agg["mappings"] / S
+        kern = {}
+        for name, b2, ms in (("pack", bytes_pack, iso["ms_pack"]), ("extract", bytes_extract, iso["ms_extract"]),
+                             ("lookup", bytes_lookup, iso["ms_lookup"]), ("reduce", bytes_chain, iso["ms_reduce"]),
+                             ("chain", bytes_chain, iso["ms_chain"] - ms_finish), ("finish", bytes_finish, ms_finish)):
+            ach = b2 / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kern[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": b2, "achieved_GBs": ach, "frac": ach / peak}
+        ms_l = iso["ms_lookup"]
+        kern["lookup"]["actual_bytes_per_step"] = bytes_lookup_actual
+        kern["lookup"]["frac_actual_bytes"] = bytes_lookup_actual / (ms_l * 1e-3) / 1e9 / peak if ms_l > 0 else 0.0
+        res["kernels"] = kern
+        res["peak"], res["peak_src"] = peak, peak_src
+        res["sector_bytes_lookup"] = 32.0 * agg["posting_runs"] / S + 4.0 * agg["posting_entries"] / S
+    res["_maps"], res["_off"], res["_host"], res["_offs"], res["_ref"], res["_vals"] = maps, off, host, offs, ref, (
+        vals if not (world > 1 and args.index == "broadcast" and rank != 0) else None)
+    gm.close()
+    del d_reads, pinned
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_sample(po, res, ns, cores, all_cores=None):
+    """The oracle port on the first `ns` reads of the rank's batch: CPU baseline and parity check in one. It gets every
+    core the process may use (`all_cores`: the affinity before the rank was bound to its GPU's NUMA node); the binding
+    is restored afterwards, so that the next workload's pinned buffers are first touched on the GPU's node again."""
+    bound = os.sched_getaffinity(0)
+    if all_cores:
+        os.sched_setaffinity(0, all_cores)
+    try:
+        om = po.Mapper(res["_ref"], res["_vals"], circular=CIRCULAR)
+        host, offs, maps, off = res["_host"], res["_offs"], res["_maps"], res["_off"]
+        t0 = time.time()
+        orow, ooff, _ = om.map_batch(host[: ns * READ_LEN], offs[: ns + 1], threads=cores)
+        dt = time.time() - t0
+    finally:
+        if all_cores:
+            os.sched_setaffinity(0, bound)
+    grow = np.stack([maps["start"], maps["end"], maps["q_offset"], maps["q_inset"], maps["rc"], maps["ids"]],
+                    axis=1).astype(np.int64)[: int(off[ns])]
+    parity = bool(np.array_equal(ooff, off[: ns + 1]) and np.array_equal(orow, grow))
+    return {"value": ns * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "port",
+            "sample": "first %d reads of the step's batch, mapping phase only" % ns, "parity_with_gpu_on_sample": parity}
+
+
+LOOKUP_KERNEL = {"config2": "dp_lookup_small_kernel + dp_lookup_kernel (window strands with more than 32 seeds)",
+                 "config3": "dp_lookup_mid_kernel", "config4": "dp_lookup_block_kernel"}
+
+
+def side_workload(dp, synth, torch, po, args, name, rank, world, local, dev, cores, parity_reads, all_cores=None):
+    """A further BASELINE config measured in the same run; returns the summary stored under line['configs'][name]."""
+    keep = (REF_LEN, READ_LEN, REF_SEED, READ_SEED, CIRCULAR, WORKLOAD, args.reads)
+    select_workload(name)
+    args.reads = WORKLOADS[name]["reads"] if args.side_reads <= 0 else args.side_reads
+    try:
+        steps, warmup = max(1, min(args.steps, 5)), max(3, min(args.warmup, 3))
+        r = measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup)
+        k = r["kernels"]
+        out = {"workload": config_dict(args, world)["workload"], "reads_per_gpu": args.reads, "n_gpus": world,
+               "steps": steps, "warmup": warmup, "value": r["value"], "unit": "Gbp/s", "ms_per_step": r["ms_per_step"],
+               "e2e": {"value": r["e2e"], "unit": "Gbp/s", "ms_per_step": r["e2e_ms_per_step"],
+                       "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+               "mapped_fraction": r["mapped_fraction"], "index": r["index"], "gpu_launches": r["gpu_launches"],
+               "roofline": {"kernel": LOOKUP_KERNEL[name], "bound": "hbm" if name == "config4" else "l2/issue",
+                            "achieved": k["lookup"]["achieved_GBs"], "peak": r["peak"], "unit": "GB/s",
+                            "frac": k["lookup"]["frac"], "frac_actual_bytes": k["lookup"]["frac_actual_bytes"],
+                            "ms_lookup_per_step_single_lane": k["lookup"]["ms_per_step"], "kernels": k},
+               "stats_per_step": r["stats_per_step"]}
+        if rank == 0 and parity_reads > 0 and not args.no_cpu_baseline and r["_vals"] is not None:
+            out["cpu_baseline"] = cpu_sample(po, r, min(parity_reads, args.reads), cores, all_cores)
+        return out
+    finally:
+        (globals()["REF_LEN"], globals()["READ_LEN"], globals()["REF_SEED"], globals()["READ_SEED"], globals()["CIRCULAR"],
+         globals()["WORKLOAD"], args.reads) = keep
+
+
+def run_ours(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    numa_node, affinity_before = bind_to_gpu_numa_node(local)
+    import downpore_b200 as dp
+    from tools import synth
+    po = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po   # CPU baseline / parity sample only (never on the measured path)
+
+    r = measure(dp, synth, torch, args, rank, world, local, dev, args.steps, args.warmup)
+    kern, peak, peak_src = r["kernels"], r["peak"], r["peak_src"]
     gather_gbs = None
     if rank == 0:
         try:
             gather_gbs = dp.probe_gather_gbs(8 << 30, device=local)
         except Exception:
             gather_gbs = None
-    # sector traffic of the lookup kernel's posting gathers: every posting run costs whole 32 B sectors
-    sector_bytes_lookup = 32.0 * agg["posting_runs"] / S + 32.0 * (4.0 * agg["posting_entries"] / S) / 32.0
-    kname = {"pack": "dp_pack_windows_kernel", "extract": "dp_extract_kernel", "reduce": "dp_reduce_kernel",
-             "chain": "dp_chain_thread_kernel", "finish": "dp_finish_round0_kernel",
-             "lookup": "dp_lookup_block_kernel" if info["num_chunks"] >= 2048 else
-                       "dp_lookup_small_kernel + dp_lookup_kernel (window strands with more than 32 seeds)"}[dominant]
-    roofline = {"kernel": kname, "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
+    # The roofline object is about the index-lookup kernels (the gather kernel BASELINE.json's north star names; by the
+    # committed ncu launch list, profiles/, the lookup family and dp_extract_kernel have the largest shares, 24 % each);
+    # every family is listed in `kernels`.
+    dominant = "lookup"
+    l2_resident = args.workload in ("config2", "config3")
+    roofline = {"kernel": LOOKUP_KERNEL[args.workload], "bound": "hbm", "achieved": kern[dominant]["achieved_GBs"],
                 "peak": peak, "unit": "GB/s", "frac": kern[dominant]["frac"],
-                "traffic": traffic.get(dominant) if args.workload == "config2" else None,
+                "traffic": TRAFFIC_PER_LAUNCH.get(dominant) if args.workload == "config2" else None,
                 "peak_source": peak_src,
-                "note": "config 2's index (7.3 MB) and k-mer table (1 MB) are L2-resident, so no kernel of this workload "
-                        "is bound by HBM (ncu: dram throughput < 2 % for every kernel; they are issue/latency bound, "
-                        "see profiles/). achieved = SURVEY 8d algorithmic bytes of one step / CUDA-event time of that "
-                        "kernel family on its launching stream over one step run on a single lane (kernels not "
-                        "overlapping; the timed `value` steps run 6 lanes). traffic = ncu dram bytes per launch of a "
-                        "65536-read sub-batch",
-                "issue_active_pct_ncu": ISSUE_ACTIVE_PCT if args.workload == "config2" else None,
+                "frac_actual_bytes": kern[dominant]["frac_actual_bytes"],
+                "regime": ("l2/issue: the index (7.3 MB) and the k-mer table (1 MB) are L2-resident, ncu dram throughput "
+                           "< 2 % for every kernel of this workload; the HBM fraction says how far the kernel is from "
+                           "being HBM-bound, issue_active_frac_ncu how busy it keeps the SMs" if l2_resident else "hbm"),
+                "issue_active_frac_ncu": (ISSUE_ACTIVE_PCT[dominant] / 100.0) if args.workload == "config2" else None,
+                "note": "achieved = SURVEY 8d algorithmic bytes of one step (16 B per included run + 8 B per posting) / "
+                        "CUDA-event time of the lookup kernels on their launching stream over one step run on a single "
+                        "lane (kernels not overlapping; the timed `value` steps run 6 lanes). frac_actual_bytes counts "
+                        "the 4 B per posting the index really holds. traffic = ncu dram bytes per launch of a 65536-read "
+                        "sub-batch (profiles/). hbm_regime_* = the same kernel family where it IS bound by HBM: the 3.1 Gb "
+                        "reference of BASELINE config 4",
                 "hbm_gather_ceiling_GBs": gather_gbs,
-                "lookup_vs_gather_ceiling": (sector_bytes_lookup / (kern["lookup"]["ms_per_step"] * 1e-3) / 1e9 / gather_gbs
-                                             if gather_gbs and kern["lookup"]["ms_per_step"] > 0 else None),
+                "lookup_sector_GBs": (r["sector_bytes_lookup"] / (kern["lookup"]["ms_per_step"] * 1e-3) / 1e9
+                                      if kern["lookup"]["ms_per_step"] > 0 else None),
+                "issue_active_pct_ncu": ISSUE_ACTIVE_PCT if args.workload == "config2" else None,
                 "kernels": kern}
+    for name, kv in kern.items():  # flat copies: the driver's parser keeps scalars of this object
+        roofline["ms_%s" % name] = kv["ms_per_step"]
+        roofline["frac_%s" % name] = kv["frac"]
 
-    line = {"metric": "mapped Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt_dev / args.steps * 1e3,
-            "wall_ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True,
+    n = args.reads
+    line = {"metric": "mapped Gbp/s", "value": r["value"], "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "wall_ms_per_step": r["wall_ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": dict(config_dict(args, world), host_numa_node_rank0=numa_node),
-            "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] + (n + 1) * 8),
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "wall_ms_per_step": wall_e2e / args.steps * 1e3,
-                    "host_buffer_bytes_per_step": int(bases_rank),
+            "config": config_dict(args, world), "host_numa_node_rank0": numa_node,
+            "e2e": {"value": r["e2e"], "unit": "Gbp/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"],
+                    "wall_ms_per_step": r["e2e_wall_ms_per_step"],
+                    "host_buffer_bytes_per_step": r["host_buffer_bytes_per_step"],
                     "note": "per GPU; dp_mapper_map_batch on pinned host ASCII. The reads stay in the caller's pinned "
                             "buffer and a TMA pull kernel (cp.async.bulk: host -> shared memory -> HBM staging) moves only "
                             "the queried windows across PCIe, so h2d bytes < host buffer bytes; the finish kernel writes "
-                            "the mapping records into mapped host memory"},
-            "gpu_launches": int(agg["kernel_launches"]),
-            "clocks": clocks, "roofline": roofline,
-            "mapped_fraction": mapped_frac, "bases_per_step": total_bases,
-            "index": dict(info, build_s=t_index, replicate_s=t_repl, kmer_count_and_values_s=t_counts,
-                          replication=("one NCCL broadcast of the index image from rank 0" if world > 1 and
-                                       args.index == "broadcast" else "built on every rank")),
-            "stats_per_step": {k2: (v / S) for k2, v in agg.items()}}
+                            "the mapping records in read order into mapped host memory"},
+            "gpu_launches": r["gpu_launches"],
+            "clocks": r["clocks"], "roofline": roofline,
+            "mapped_fraction": r["mapped_fraction"], "bases_per_step": r["bases_per_step"],
+            "bases_note": "Gbp/s counts ALL submitted bases; Map() touches 2-12 windows of 1000 bases per read",
+            "index": r["index"], "stats_per_step": r["stats_per_step"]}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
+    cores = 1
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = len(affinity_before or os.sched_getaffinity(0)) or 1
+        if world == 1:
+            line["cpu_baseline"] = cpu_sample(po, r, min(args.cpu_sample, n), cores, affinity_before)
+    del r
+
+    # ---- the other BASELINE configs in the same run: config 3 at every N; config 4 (3.1 Gb reference, index built on
+    #      rank 0 and replicated by one broadcast, reads sharded) on eight GPUs ----
+    configs = {}
+    if args.workload == "config2" and not args.no_side_configs:
+        try:
+            configs["config3"] = side_workload(dp, synth, torch, po, args, "config3", rank, world, local, dev, cores,
+                                               2000 if world == 1 else 500, affinity_before)
+        except Exception as ex:  # never lose the headline line to an auxiliary measurement
+            configs["config3"] = {"error": str(ex)}
+        if world >= 8 or args.config4:
+            try:
+                configs["config4"] = side_workload(dp, synth, torch, po, args, "config4", rank, world, local, dev, cores, 0,
+                                                   affinity_before)
+            except Exception as ex:
+                configs["config4"] = {"error": str(ex)}
+    if configs:
+        line["configs"] = configs
+        for cname, c in configs.items():  # flat copies where the driver's parser keeps them
+            if "error" in c:
+                roofline["%s_error" % cname] = c["error"]
+                continue
+            roofline["%s_value_Gbps" % cname] = c["value"]
+            roofline["%s_e2e_Gbps" % cname] = c["e2e"]["value"]
+            roofline["%s_ms_per_step" % cname] = c["ms_per_step"]
+            roofline["%s_reads_per_gpu" % cname] = c["reads_per_gpu"]
+            roofline["%s_lookup_ms_single_lane" % cname] = c["roofline"]["ms_lookup_per_step_single_lane"]
+            roofline["%s_lookup_frac" % cname] = c["roofline"]["frac"]
+            roofline["%s_lookup_frac_actual_bytes" % cname] = c["roofline"]["frac_actual_bytes"]
+            roofline["%s_replicate_s" % cname] = c["index"]["replicate_s"]
+            roofline["%s_index_bytes" % cname] = c["index"]["index_bytes"]
+            if "cpu_baseline" in c:
+                roofline["%s_cpu_Gbps" % cname] = c["cpu_baseline"]["value"]
+                roofline["%s_parity_on_sample" % cname] = c["cpu_baseline"]["parity_with_gpu_on_sample"]
 
     # ---- the index-lookup kernel where it IS bound by HBM (rank 0, N=1): the 3.1 Gb reference of BASELINE config 4
     #      (313k chunks, 677M postings, 15 GB index >> L2), 15 kb reads, single lane ----
     if rank == 0 and world == 1 and not args.no_hbm_regime:
         try:
-            line["roofline_hbm_regime"] = hbm_regime(dp, synth, local, peak, peak_src, gather_gbs)
+            h = hbm_regime(dp, synth, local, peak, peak_src, gather_gbs)
+            line["roofline_hbm_regime"] = h
+            for k2 in ("frac", "frac_actual_bytes", "achieved", "achieved_actual_bytes", "ms_lookup", "Gbp_per_s", "kernel",
+                       "workload", "traffic"):
+                roofline["hbm_regime_%s" % k2] = h[k2]
         except Exception as ex:  # never lose the headline line to the auxiliary measurement
             line["roofline_hbm_regime"] = {"error": str(ex)}
-
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import pyoracle as po
-        if affinity_before:
-            os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every core this process may use
-        cores = len(os.sched_getaffinity(0)) or 1
-        om = po.Mapper(ref, vals, circular=CIRCULAR)
-        ns = args.cpu_sample
-        t0 = time.time()
-        orow, ooff, _ = om.map_batch(host[: ns * READ_LEN], offs[: ns + 1], threads=cores)
-        dt = time.time() - t0
-        # the sample doubles as a parity check of the timed configuration
-        grow = np.stack([maps["start"], maps["end"], maps["q_offset"], maps["q_inset"], maps["rc"], maps["ids"]],
-                        axis=1).astype(np.int64)[: int(off[ns])]
-        parity = bool(np.array_equal(ooff, off[: ns + 1]) and np.array_equal(orow, grow))
-        line["cpu_baseline"] = {"value": ns * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "port",
-                                "sample": "first %d reads of the step's batch, mapping phase only" % ns,
-                                "parity_with_gpu_on_sample": parity}
     if rank == 0:
         emit(line)
-    gm.close()
 
 
 def main():
@@ -512,12 +641,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=int(os.environ.get("DP_BENCH_READS", 1_000_000)),
                     help="reads per GPU per step (BASELINE config 2: 1M)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
                     help="config2 = the configuration the metric is quoted on (default); config3 = 64 Mb linear reference, "
                          "20 kb reads (use --reads 500000: 10 GB of ASCII per GPU per step)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip BASELINE configs 3 (every N) and 4 (N = 8) after the headline workload")
+    ap.add_argument("--config4", action="store_true", help="also run BASELINE config 4 (3.1 Gb reference) below eight GPUs")
+    ap.add_argument("--side-reads", type=int, default=0, help="reads per GPU per step of the side configs (default: their own)")
     ap.add_argument("--no-hbm-regime", action="store_true", help="skip the lookup measurement on the 3.1 Gb reference (BASELINE config 4)")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
                     help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")

@@ -107,6 +107,7 @@ struct Caps {
 const int kCapMax = 1 << 20;
 
 struct Lane {
+    double hp[6] = {0, 0, 0, 0, 0, 0};  // DP_HOST_PROFILE: host ms in tables / launches / wait / post / replay / assemble
     cudaStream_t stream = nullptr;
     Caps caps;
     HBuf<DpCounters> hCtr;  // counters + overflow flags of the current attempt, as of its last synchronise
@@ -119,10 +120,10 @@ struct Lane {
     DBuf<unsigned> wsOff, qSeed, candChunk, outOff, dFinOff, dStagePos, dPullWork;
     DBuf<int> wsN, qPos, candN, outN, dFinN;
     DBuf<unsigned short> candDistinct;
-    DBuf<DpMappingDev> outMaps, dFinMaps;
+    DBuf<DpMappingDev> outMaps;
     DBuf<unsigned long long> cursor;
     DBuf<DpCounters> dCtr;
-    DBuf<unsigned char> dStatus, scanTmp;
+    DBuf<unsigned char> scanTmp;
     // lookup scratch
     DBuf<unsigned> lsSeed, lsOff, lsPre, lsEndW, lsAll, lsCounters, lsTouched;
     DBuf<unsigned long long> lsCand;
@@ -144,9 +145,11 @@ struct Lane {
     DBuf<unsigned char> fcSlow;
     DBuf<int> fcSlowList;
     size_t fcTaskCap = 0, fcPoolCap = 0;
-    HBuf<int> hOutN, hFinN;
+    HBuf<int> hOutN, hUnresN;
     HBuf<unsigned> hOutOff, hFinOff;
-    HBuf<unsigned char> hStatus, hStage;
+    HBuf<unsigned char> hStage;
+    HBuf<DpUnresolved> hUnres;
+    DBuf<DpUnresolved> dUnres;
     HBuf<DpMappingDev> hOutMaps, hFinMaps;
     HBuf<long long> hRel;
     size_t hOutTotal = 0;
@@ -1174,6 +1177,7 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         seedEntries0 += round0_seed_bound(len, e, minLen);
     }
     if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
+    W.hp[0] += now_ms() - t0;
     const long long totalBytes = W.hRel.p[n];
     const size_t wordCap = (size_t)(totalBytes / 16 + 2 * n + 16);
     W.dSeqOff.reserve((size_t)n + 1);
@@ -1206,22 +1210,49 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
             if (len >= minLen) W.stats.h2d_bytes += (len <= 2ll * e) ? len : std::min<long long>(len, 2ll * (e + 32));
         }
     }
-    // Map()'s first decision per read; the kernel writes its results straight into mapped page-locked host memory
-    const size_t finCap = (size_t)n * 4 + 64;
-    W.hStatus.reserve((size_t)n);
-    W.hFinN.reserve((size_t)n);
-    W.hFinOff.reserve((size_t)n);
-    W.hFinMaps.reserve(finCap);
+    // Map()'s first decision per read, delivered in read order: count pass, device-wide scan, write pass straight into
+    // mapped page-locked host memory (consecutive reads, consecutive records: coalesced posted writes)
+    const int kUnresHead = 4096;  // unresolved reads copied with the results; a longer list is fetched afterwards
+    W.dFinN.reserve((size_t)n + 1);
+    W.dFinOff.reserve((size_t)n + 1);
+    W.hFinOff.reserve((size_t)n + 1);
+    W.dUnres.reserve((size_t)n + 1);
+    W.hUnres.reserve((size_t)kUnresHead);
+    W.hUnresN.reserve(1);
+    if (W.hFinMaps.cap < (size_t)n * 4 + 64) W.hFinMaps.reserve((size_t)n * 4 + 64);
     CK(cudaEventRecord(W.timers[T_FINISH].a, st));
-    dp_finish_round0_kernel<<<div_up(n, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
-                                                            W.outMaps.p, W.hStatus.d, W.hFinN.d, W.hFinOff.d,
-                                                            W.hFinMaps.d, W.cursor.p + CUR_FIN,
-                                                            (unsigned long long)finCap, W.dCtr.p, W.hCtr.d);
+    dp_finish_round0_kernel<false><<<div_up(n + 1, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
+                                                                       W.outMaps.p, W.dFinN.p, nullptr, nullptr, 0, nullptr,
+                                                                       nullptr, 0, W.dCtr.p, nullptr);
     CK(cudaGetLastError());
+    {
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, W.dFinN.p, W.dFinOff.p, (int)n + 1, st);
+        W.scanTmp.reserve(tmpBytes);
+        CK(cub::DeviceScan::ExclusiveSum(W.scanTmp.p, tmpBytes, W.dFinN.p, W.dFinOff.p, (int)n + 1, st));
+    }
+    auto write_pass = [&]() {
+        CK(cudaMemsetAsync(W.cursor.p + CUR_FIN, 0, sizeof(unsigned long long), st));
+        dp_finish_round0_kernel<true><<<div_up(n, 128), 128, 0, st>>>(
+            M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p, W.outMaps.p, nullptr, W.dFinOff.p, W.hFinMaps.d,
+            (unsigned long long)W.hFinMaps.cap, W.dUnres.p, reinterpret_cast<int*>(W.cursor.p + CUR_FIN), (int)n + 1, W.dCtr.p,
+            W.hCtr.d);
+        CK(cudaGetLastError());
+    };
+    write_pass();
     CK(cudaEventRecord(W.timers[T_FINISH].b, st));
-    W.stats.kernel_launches += 2;
+    CK(cudaMemcpyAsync(W.hFinOff.p, W.dFinOff.p, ((size_t)n + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hUnres.p, W.dUnres.p, (size_t)std::min<int64_t>(n, kUnresHead) * sizeof(DpUnresolved),
+                       cudaMemcpyDeviceToHost, st));
+    W.stats.kernel_launches += 4;
     W.stats.ms_host_logic += now_ms() - t0;
-    lane_sync(W);
+    W.hp[1] += now_ms() - t0;
+    {
+        const double tw = now_ms();
+        lane_sync(W);
+        W.hp[2] += now_ms() - tw;
+    }
     collect_stage_times(W);
     {
         float ms;
@@ -1233,60 +1264,59 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         forget_attempt(W, before);
         return W.hCtr.p->overflow;
     }
-    W.stats.short_reads += nShort;
     t0 = now_ms();
-    std::vector<int> active;
-    bool needDownload = false;
-    for (int64_t i = 0; i < n; i++)
-        if (W.hStatus.p[i] != DP_READ_DONE) {
-            active.push_back((int)i);
-            if (W.hStatus.p[i] == DP_READ_UNRESOLVED_NOHITS) needDownload = true;
-        }
+    const unsigned* fOff = W.hFinOff.p;
+    const size_t devTotal = fOff[n];
+    if (devTotal > W.hFinMaps.cap) {  // more records than the delivery buffer holds (repeat-rich reads): grow, write again
+        W.hFinMaps.reserve(devTotal + 64);
+        write_pass();
+        CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
+        W.stats.kernel_launches += 1;
+        lane_sync(W);
+    }
+    const int nUn = *W.hUnresN.p;
+    std::vector<DpUnresolved> unres((size_t)nUn);
+    if (nUn > kUnresHead) {
+        CK(cudaMemcpyAsync(unres.data(), W.dUnres.p, (size_t)nUn * sizeof(DpUnresolved), cudaMemcpyDeviceToHost, st));
+        lane_sync(W);
+    } else if (nUn > 0) {
+        memcpy(unres.data(), W.hUnres.p, (size_t)nUn * sizeof(DpUnresolved));
+    }
+    std::sort(unres.begin(), unres.end(), [](const DpUnresolved& x, const DpUnresolved& y) { return x.read < y.read; });
+    W.stats.short_reads += nShort;
     W.stats.ms_host_logic += now_ms() - t0;
+    W.hp[3] += now_ms() - t0;
+    const double tReplay = now_ms();
 
     // ---- unresolved reads: replay Map() on the host against cached window results, round by round ----
-    std::vector<std::vector<dph::Hit>> late(active.size());
-    std::vector<int> slotOf;  // read index -> slot in `cache` / `late`
-    if (!active.empty()) {
+    std::vector<std::vector<dph::Hit>> late((size_t)nUn);
+    if (nUn > 0) {
         t0 = now_ms();
-        if (needDownload) {  // rare: the hit buffer was full
-            if (unsigned ov = download_windows(W, nWin0)) {
-                forget_attempt(W, before);
-                W.stats.short_reads -= nShort;
-                return ov;
-            }
-        }
-        std::vector<ReadCache> cache(active.size());
-        slotOf.assign((size_t)n, -1);
+        std::vector<ReadCache> cache((size_t)nUn);
+        std::vector<int> slotOf((size_t)n, -1);  // read index -> slot in `cache` / `late`
         std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
-        if (needDownload) roundMaps.emplace_back(W.hOutMaps.p, W.hOutMaps.p + W.hOutTotal + 1);
-        for (size_t a = 0; a < active.size(); a++) {
-            int i = active[a];
-            slotOf[(size_t)i] = (int)a;
-            long long len = W.hRel.p[i + 1] - W.hRel.p[i];
-            const bool raw = W.hStatus.p[i] == DP_READ_UNRESOLVED;  // raw window hits delivered by the finish kernel
-            const int nA = raw ? (W.hFinN.p[i] & 0xffff) : 0, nB = raw ? (W.hFinN.p[i] >> 16) : 0;
-            for (int s = 0; s < 2; s++) {
-                size_t wI = 2 * (size_t)i + s;
+        std::vector<int> todo((size_t)nUn);
+        for (int a = 0; a < nUn; a++) {
+            const int i = unres[(size_t)a].read;
+            todo[(size_t)a] = i;
+            slotOf[(size_t)i] = a;
+            const long long len = W.hRel.p[i + 1] - W.hRel.p[i];
+            const int nA = unres[(size_t)a].nA, nB = unres[(size_t)a].nB;
+            for (int s2 = 0; s2 < 2; s2++) {
                 dph::WinRef ref;
                 if (len <= 2ll * e) {
-                    if (s == 1) continue;
+                    if (s2 == 1) continue;
                     ref.start = 0;
                     ref.len = (int)len;
                     ref.whole = 1;
                 } else {
-                    ref.start = s == 0 ? 0 : (int)(len - e);
+                    ref.start = s2 == 0 ? 0 : (int)(len - e);
                     ref.len = e;
                     ref.whole = 0;
                 }
-                if (raw) {
-                    ref.n = s == 0 ? nA : nB;
-                    ref.maps = W.hFinMaps.p + W.hFinOff.p[i] + (s == 0 ? 0 : nA);
-                } else {
-                    ref.n = W.hOutN.p[wI];
-                    ref.maps = roundMaps[0].data() + W.hOutOff.p[wI];
-                }
-                cache[a].wins.push_back(ref);
+                ref.n = s2 == 0 ? nA : nB;  // raw window hits delivered by the finish kernel
+                ref.maps = W.hFinMaps.p + fOff[i] + (s2 == 0 ? 0 : nA);
+                cache[(size_t)a].wins.push_back(ref);
             }
         }
         dph::Params P;
@@ -1295,7 +1325,6 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         P.circular = M.circular != 0;
         dph::ReadMapper rm(P);
         W.stats.ms_host_logic += now_ms() - t0;
-        std::vector<int> todo = active;
         while (!todo.empty()) {
             t0 = now_ms();
             std::vector<DpWindow> wins;
@@ -1332,31 +1361,39 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
             W.stats.ms_host_logic += now_ms() - t0;
         }
     }
-    // ---- assemble the sub-batch output in read order ----
+    // ---- the sub-batch's output: the delivered block as it is, with the late results spliced in where the raw hits
+    //      of the unresolved reads sit ----
+    W.hp[4] += now_ms() - tReplay;
     t0 = now_ms();
-    size_t total = 0;
-    for (int64_t i = 0; i < n; i++)
-        if (W.hStatus.p[i] == DP_READ_DONE) total += (size_t)W.hFinN.p[i];
-    for (auto& v : late) total += v.size();
-    out.maps.resize(total);
-    size_t pos = 0;
     const dp_mapping* fin = reinterpret_cast<const dp_mapping*>(W.hFinMaps.p);
-    for (int64_t i = 0; i < n; i++) {
-        if (W.hStatus.p[i] == DP_READ_DONE) {
-            int cnt = W.hFinN.p[i];
-            counts[r0 + i] = cnt;
-            if (cnt == 1) out.maps[pos] = fin[W.hFinOff.p[i]];
-            else if (cnt > 1) memcpy(out.maps.data() + pos, fin + W.hFinOff.p[i], (size_t)cnt * sizeof(dp_mapping));
-            pos += (size_t)cnt;
-        } else {
-            const std::vector<dph::Hit>& v = late[(size_t)slotOf[(size_t)i]];
-            counts[r0 + i] = (int)v.size();
+    size_t total = devTotal;
+    for (int a = 0; a < nUn; a++)
+        total += late[(size_t)a].size() - (size_t)(fOff[unres[(size_t)a].read + 1] - fOff[unres[(size_t)a].read]);
+    out.maps.resize(total);
+    {
+        size_t pos = 0, src = 0;
+        int64_t prevRead = 0;
+        long long delta = 0;  // (records before read i in the output) - fOff[i]
+        for (int a = 0; a <= nUn; a++) {
+            const int64_t u = a < nUn ? unres[(size_t)a].read : n;
+            const size_t segEnd = fOff[u];  // finished reads [prevRead, u): one block
+            if (segEnd > src) memcpy(out.maps.data() + pos, fin + src, (segEnd - src) * sizeof(dp_mapping));
+            pos += segEnd - src;
+            for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int)(fOff[i + 1] - fOff[i]);
+            if (a == nUn) break;
+            const std::vector<dph::Hit>& v = late[(size_t)a];
+            counts[r0 + u] = (int)v.size();
             for (const dph::Hit& h : v) out.maps[pos++] = to_abi(h);
+            src = fOff[u + 1];
+            delta += (long long)v.size() - (long long)(fOff[u + 1] - fOff[u]);
+            prevRead = u + 1;
         }
+        (void)delta;
+        if (pos != total) throw std::runtime_error("internal error: sub-batch assembly mismatch");
     }
-    out.maps.resize(pos);
     absorb_counters(W);
     W.stats.ms_host_logic += now_ms() - t0;
+    W.hp[5] += now_ms() - t0;
     return 0;
 }
 
@@ -1603,6 +1640,14 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         free(maps);
         free(off);
         throw std::runtime_error("internal error: result assembly mismatch");
+    }
+    if (getenv("DP_HOST_PROFILE")) {  // where the lanes' host threads spent the call (ms, summed over sub-batches)
+        for (int l = 0; l < nLanes; l++) {
+            Lane& W = *M.lanes[(size_t)l];
+            fprintf(stderr, "[dp host] lane %d: tables %.2f launch %.2f wait %.2f post %.2f replay+rounds %.2f assemble %.2f | call %.2f ms\n",
+                    l, W.hp[0], W.hp[1] - W.hp[0], W.hp[2], W.hp[3], W.hp[4], W.hp[5], now_ms() - tStart);
+            for (double& x : W.hp) x = 0;
+        }
     }
     memset(&M.stats, 0, sizeof(M.stats));
     for (int l = 0; l < nLanes; l++) add_stats(M.stats, M.lanes[(size_t)l]->stats);

@@ -10,11 +10,6 @@
 
 #define DP_FIN_CAP 8  // hits per window handled on the device; more -> host path
 
-// DONE: finMaps holds the read's final mappings. UNRESOLVED: finMaps holds the raw hits of its two round-0 windows
-// (first window's, then the second's; finN = nA | nB << 16) for the host replay. NOHITS: as UNRESOLVED but the hit
-// buffer was full, the host fetches the window results itself.
-enum { DP_READ_DONE = 0, DP_READ_UNRESOLVED = 1, DP_READ_UNRESOLVED_NOHITS = 2 };
-
 // read table: lengths and packed-word demand from the (sub-batch relative) byte offsets
 __global__ void dp_read_table_kernel(const long long* __restrict__ seqOff, long long n, int* __restrict__ readLen,
                                      long long* __restrict__ wordsNeeded) {
@@ -135,26 +130,38 @@ __device__ __forceinline__ DpMappingDev dp_store_hit(const DpHit& h) {
     return m;
 }
 
-// status / finN / finOff / finMaps may live in page-locked host memory mapped into the device address space: the
-// kernel then delivers the sub-batch's results straight to the host (posted writes), with no copy call afterwards.
+// Map()'s first decision for one read, in two passes around a device-wide exclusive scan so that the records land in
+// READ ORDER (the host then takes a sub-batch's results as one block instead of visiting every read):
+//   WRITE = false: cnt[r] = records the read delivers — its final mappings if Map() returns at this point, else the raw
+//                  hits of its two round-0 windows (first window's, then the second's) for the replay of the later rounds;
+//   WRITE = true : the same decision again (cheaper than parking the records), records written at off[r] (the scan of
+//                  cnt); reads that are not finished are appended to `unres` as {read, nA, nB}.
+// finMaps may live in page-locked host memory mapped into the device address space: consecutive reads write consecutive
+// records, so the posted writes coalesce and the sub-batch needs no copy call for its records. When the records do not
+// fit finCapacity nothing is written (the host grows the buffer and repeats this pass).
+struct DpUnresolved {
+    int read, nA, nB;
+};
+
+template <bool WRITE>
 __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, const int* __restrict__ readLen,
                                                                long long n, int minLen,
                                                                const int* __restrict__ outN,
                                                                const unsigned* __restrict__ outOff,
                                                                const DpMappingDev* __restrict__ outMaps,
-                                                               unsigned char* __restrict__ status,
-                                                               int* __restrict__ finN, unsigned* __restrict__ finOff,
+                                                               int* __restrict__ cnt, const unsigned* __restrict__ off,
                                                                DpMappingDev* __restrict__ finMaps,
-                                                               unsigned long long* __restrict__ finCursor,
                                                                unsigned long long finCapacity,
-                                                               const DpCounters* __restrict__ ctr,
+                                                               DpUnresolved* __restrict__ unres, int* __restrict__ nUnres,
+                                                               int unresCap, const DpCounters* __restrict__ ctr,
                                                                DpCounters* __restrict__ hostCtr) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // the launch's work counters and overflow flags travel with the results (every kernel that updates them has
     // finished: same stream)
-    if (r == 0 && hostCtr) *hostCtr = *ctr;
-    const bool live = r < n;  // every lane stays for the warp-wide allocation below
-    const long long qlen = live ? readLen[r] : 0;
+    if (WRITE && r == 0 && hostCtr) *hostCtr = *ctr;
+    if (!WRITE && r == n) cnt[n] = 0;
+    if (r >= n) return;
+    const long long qlen = readLen[r];
     const int e = I.edge;
     DpHit A[DP_FIN_CAP], B[DP_FIN_CAP], M[DP_FIN_CAP];
     int nOut = 0;
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
     int nOut2 = 0;
     bool done = true;
     int nA = 0, nB = 0;
-    if (live && qlen >= minLen) {
+    if (qlen >= minLen) {
         nA = outN[2 * r];
         nB = outN[2 * r + 1];
         if (nA > DP_FIN_CAP || nB > DP_FIN_CAP) {
@@ -211,39 +218,27 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
             }
         }
     }
-    // one bump allocation per warp (a single-address atomic per read serialises in L2)
-    bool rawOk = true;
-    if (!done && (nA > 0xffff || nB > 0x7fff)) rawOk = false;
-    const int tot = !live ? 0 : (done ? nOut + nOut2 : (rawOk ? nA + nB : 0));
-    int incl = tot;
-    for (int d = 1; d < 32; d <<= 1) {
-        int y = __shfl_up_sync(DP_FULL, incl, d);
-        if ((int)(threadIdx.x & 31) >= d) incl += y;
-    }
-    unsigned long long warpBase = 0;
-    const int warpTot = __shfl_sync(DP_FULL, incl, 31);
-    if ((threadIdx.x & 31) == 31 && warpTot) warpBase = atomicAdd(finCursor, (unsigned long long)warpTot);
-    warpBase = __shfl_sync(DP_FULL, warpBase, 31);
-    if (!live) return;
-    const unsigned long long base = warpBase + (unsigned)(incl - tot);
-    if (base + (unsigned)tot > finCapacity || !rawOk) {  // no room: the host path fetches the windows and redoes this read
-        status[r] = DP_READ_UNRESOLVED_NOHITS;
-        finN[r] = 0;
-        finOff[r] = 0;
+    if (!WRITE) {
+        cnt[r] = done ? nOut + nOut2 : nA + nB;
         return;
     }
+    if (!done) {  // the later rounds of Map() replay this read against the raw hits delivered below
+        const int slot = atomicAdd(nUnres, 1);
+        if (slot < unresCap) {
+            DpUnresolved u;
+            u.read = (int)r;
+            u.nA = nA;
+            u.nB = nB;
+            unres[slot] = u;
+        }
+    }
+    if ((unsigned long long)off[n] > finCapacity) return;
+    const unsigned base = off[r];
     if (done) {
         for (int i = 0; i < nOut; i++) finMaps[base + i] = dp_store_hit(outList[i]);
         for (int i = 0; i < nOut2; i++) finMaps[base + nOut + i] = dp_store_hit(outList2[i]);
-        status[r] = DP_READ_DONE;
-        finN[r] = tot;
-        finOff[r] = (unsigned)base;
-    } else {
-        // hand the raw window hits to the host replay (removeDominated above worked on copies)
+    } else {  // (removeDominated above worked on copies)
         for (int i = 0; i < nA; i++) finMaps[base + i] = outMaps[outOff[2 * r] + i];
         for (int i = 0; i < nB; i++) finMaps[base + nA + i] = outMaps[outOff[2 * r + 1] + i];
-        status[r] = DP_READ_UNRESOLVED;
-        finN[r] = nA | (nB << 16);
-        finOff[r] = (unsigned)base;
     }
 }
