@@ -67,6 +67,7 @@ _SIGNATURES = {
     "dp_mapper_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "dp_mapper_destroy": (None, [c_vp]),
+    "dp_mapper_map_batch_packed": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "dp_mapper_index_image_size": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "dp_mapper_index_export": (ctypes.c_int, [c_vp, c_vp, c_i64]),
     "dp_mapper_create_from_index": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),
@@ -135,6 +136,30 @@ def pack(ascii_seq, device=0):
     out = np.zeros((a.size + 3) // 4, dtype=np.uint8)
     _check(lib().dp_pack(a.ctypes.data, a.size, out.ctypes.data, device))
     return out
+
+
+def pack_batch(bases, offsets):
+    """Host-side stand-in for what the Go reader hands over: every read of an ASCII batch as sequence.packedSequence
+    bytes (sequence/sequence.go:67-93: 4 bases per byte, first base in the top bits, tail byte zero-padded), back to back.
+    Returns (packed uint8, byte_offsets int64[n+1], lengths int64[n]). numpy only (test and bench input preparation)."""
+    bases = _u8(bases)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lengths = np.diff(offsets)
+    nbytes = (lengths + 3) // 4
+    byte_off = np.zeros(offsets.size, dtype=np.int64)
+    np.cumsum(nbytes, out=byte_off[1:])
+    code = (((bases >> 1) ^ ((bases & 4) >> 2)) & 3).astype(np.uint8)  # the pack kernel's base code (asm_amd64.s:33-78)
+    out = np.zeros(int(byte_off[-1]), dtype=np.uint8)
+    if lengths.size and np.all(lengths == lengths[0]) and lengths[0] % 4 == 0 and offsets[0] == 0:
+        c = code[: offsets[-1]].reshape(-1, 4)
+        out[:] = (c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]
+    else:
+        for i in range(lengths.size):
+            c = np.zeros(int(nbytes[i]) * 4, dtype=np.uint8)
+            c[: lengths[i]] = code[offsets[i]: offsets[i + 1]]
+            c = c.reshape(-1, 4)
+            out[byte_off[i]: byte_off[i + 1]] = (c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]
+    return out, byte_off, lengths.astype(np.int64)
 
 
 def kmer_counts(ascii_seq, k, counts=None, device=0):
@@ -279,6 +304,21 @@ class Mapper:
         out_p, off_p = c_vp(), c_vp()
         _check(lib().dp_mapper_map_batch(self._h, n, bases.ctypes.data, offsets.ctypes.data, ctypes.byref(out_p),
                                          ctypes.byref(off_p)))
+        return self._collect(n, out_p, off_p)
+
+    def map_batch_packed(self, packed, byte_offsets, lengths):
+        """Mapper.Map over reads that are packed already (sequence.packedSequence bytes, see pack_batch). `packed`: numpy
+        uint8 array, or an int (raw host or device pointer, e.g. a pinned or CUDA torch tensor's data_ptr())."""
+        byte_offsets = np.ascontiguousarray(byte_offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        n = lengths.size
+        if not isinstance(packed, int):
+            packed = _u8(packed)
+            self._keep = packed
+            packed = packed.ctypes.data
+        out_p, off_p = c_vp(), c_vp()
+        _check(lib().dp_mapper_map_batch_packed(self._h, n, packed, byte_offsets.ctypes.data, lengths.ctypes.data,
+                                                ctypes.byref(out_p), ctypes.byref(off_p)))
         return self._collect(n, out_p, off_p)
 
     def map_batch_ptr(self, host_ptr, offsets):

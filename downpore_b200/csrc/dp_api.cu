@@ -155,8 +155,15 @@ struct Lane {
     size_t hOutTotal = 0;
     bool pendingStageTimes = false;
     bool reduceTimed = false;
-    const unsigned char* curAscii = nullptr;  // device-visible ASCII of the current sub-batch (device or mapped host)
+    const unsigned char* curAscii = nullptr;  // device-visible reads of the current sub-batch (device or mapped host)
     bool curAsciiIsHost = false;
+    // Buffers are sized for the largest sub-batch of the current call the first time a lane touches them (floors set by
+    // map_batch_impl), not grown piece by piece as the lane happens to meet larger sub-batches: a cudaFree in the middle
+    // of a call synchronises the device under every other lane.
+    size_t floorReads = 0, floorWins = 0, floorSeeds = 0, floorBytes = 0;
+    bool curPacked = false;  // the reads are sequence.packedSequence bytes (dp_mapper_map_batch_packed), not ASCII
+    DBuf<long long> dByteOff;  // packed input: first byte of each read, relative to curAscii
+    HBuf<long long> hByteRel;
     cudaEvent_t evReady = nullptr, evPulled = nullptr;  // hand-over to / from the mapper's pull stream
     std::vector<Timer> timers;
     dp_stats stats{};
@@ -654,8 +661,9 @@ LookupBlockPlan plan_block_lookup(const DpIndexDev& I, double avgRun) {
     return P;
 }
 
-void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries) {
+void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWinNow, size_t seedEntriesNow) {
     const DpIndexDev& I = M.I;
+    const size_t nWin = std::max(nWinNow, W.floorWins), seedEntries = std::max(seedEntriesNow, W.floorSeeds);  // what is reserved
     W.dWins.reserve(nWin);
     W.wsOff.reserve(2 * nWin);
     W.wsN.reserve(2 * nWin);
@@ -750,11 +758,61 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         const int stageStride = ((I.maxWindow + 15) / 16 + 3) * 16;  // the 16-byte blocks of the longest window
         const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * 2 * stageStride <= 96 * 1024;
-        if (W.curAsciiIsHost && bulkPull && tmaPull) {
+        if (W.curPacked && W.curAsciiIsHost && bulkPull && tmaPull) {
+            // reads that arrive packed, in pinned host memory: the same TMA pull (a quarter of the bytes), then the
+            // realign + byte swap from the HBM staging buffer
+            const int pkStride = ((I.maxWindow / 4 + 15) / 16 + 3) * 16;
+            W.dStage.reserve((std::max(nWin, W.floorWins) + 1) * (size_t)pkStride);
+            W.dStagePos.reserve(std::max(nWin, W.floorWins));
+            W.dPullWork.reserve(1);
+            {
+                std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
+                CK(cudaEventRecord(W.evReady, st));
+                CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
+                CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
+                // (pieces of 250-500 bytes: the link is bound by the read requests in flight, 64 single-warp CTAs measured
+                // best — 24.3 ms per 1M reads against 35.5 with 32, 25.5 with 128 and 29 with zero-copy loads)
+                const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 64)));
+                CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
+                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * pkStride, M.pullStream>>>(
+                    W.curAscii, W.dSeqOff.p, W.dByteOff.p, W.dWins.p, (int)nWin, W.dStage.p, pkStride, W.dStagePos.p,
+                    W.dPullWork.p);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(W.evPulled, M.pullStream));
+            }
+            CK(cudaStreamWaitEvent(st, W.evPulled, 0));
+            int fullBlocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 6);
+            dp_pack_windows_packed_kernel<<<fullBlocks, 256, 0, st>>>(W.curAscii, W.dByteOff.p, W.dSeqOff.p, dWordOff, W.dWins.p,
+                                                                      (int)nWin, const_cast<unsigned*>(dWords), W.dStage.p,
+                                                                      W.dStagePos.p);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_PACK].b, st));
+            W.stats.kernel_launches += 1;
+        } else if (W.curPacked) {
+            // reads that arrive packed: realign + byte swap of just the queried bytes (zero-copy out of mapped host
+            // memory when that is where they live: the round-0 pulls of all lanes go through the shared pull stream)
+            const bool viaPull = W.curAsciiIsHost && bulkPull;
+            cudaStream_t ps = viaPull ? M.pullStream : st;
+            std::unique_lock<std::mutex> lk(M.pullMu, std::defer_lock);
+            if (viaPull) {
+                lk.lock();  // (wait, kernel, record) must enter the pull stream as one unit
+                CK(cudaEventRecord(W.evReady, st));
+                CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
+            }
+            CK(cudaEventRecord(W.timers[T_PACK].a, ps));
+            dp_pack_windows_packed_kernel<<<blocks, 256, 0, ps>>>(W.curAscii, W.dByteOff.p, W.dSeqOff.p, dWordOff, W.dWins.p,
+                                                                  (int)nWin, const_cast<unsigned*>(dWords), nullptr, nullptr);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(W.timers[T_PACK].b, ps));
+            if (viaPull) {
+                CK(cudaEventRecord(W.evPulled, M.pullStream));
+                CK(cudaStreamWaitEvent(st, W.evPulled, 0));
+            }
+        } else if (W.curAsciiIsHost && bulkPull && tmaPull) {
             // the PCIe leg as TMA bulk copies into an HBM staging buffer (a few single-warp CTAs on the shared pull
             // stream), then the pack from HBM at full width on the lane's own stream
-            W.dStage.reserve((nWin + 1) * (size_t)stageStride);
-            W.dStagePos.reserve(nWin);
+            W.dStage.reserve((std::max(nWin, W.floorWins) + 1) * (size_t)stageStride);
+            W.dStagePos.reserve(std::max(nWin, W.floorWins));
             W.dPullWork.reserve(1);
             {
                 std::lock_guard<std::mutex> lk(M.pullMu);  // (wait, kernel, record) must enter the pull stream as one unit
@@ -764,7 +822,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
                 CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
                 dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * stageStride, M.pullStream>>>(
-                    W.curAscii, W.dSeqOff.p, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p, W.dPullWork.p);
+                    W.curAscii, W.dSeqOff.p, nullptr, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p, W.dPullWork.p);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
@@ -1071,7 +1129,7 @@ unsigned run_windows(dp_mapper& M, Lane& W, const DpWindow* wins, size_t nWin, c
     for (size_t i = 0; i < nWin; i++) seedEntries += 2 * (size_t)(wins[i].len + 2);
     ensure_window_capacity(M, W, nWin, seedEntries);
     if (W.curAsciiIsHost)
-        for (size_t i = 0; i < nWin; i++) W.stats.h2d_bytes += wins[i].len + 32;
+        for (size_t i = 0; i < nWin; i++) W.stats.h2d_bytes += W.curPacked ? wins[i].len / 4 + 32 : wins[i].len + 32;
     CK(cudaMemcpyAsync(W.dWins.p, wins, nWin * sizeof(DpWindow), cudaMemcpyHostToDevice, W.stream));
     launch_windows(M, W, nWin, seedEntries, dWords, dWordOff, dReadLen);
     return download_windows(W, nWin);
@@ -1152,8 +1210,8 @@ inline size_t round0_seed_bound(long long len, int e, int minLen) {
 // Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device, with the lane's current
 // capacities (W.caps). Returns 0 and fills counts[r0..r1) and `out` (ordered by read), or returns the DP_OV_* bits of
 // a capacity that was too small: nothing is delivered then and the caller reruns the range with more room (map_range).
-unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
-                      int* counts, SubOut& out) {
+unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff,
+                      int64_t r0, int64_t r1, int* counts, SubOut& out) {
     const int64_t n = r1 - r0;
     cudaStream_t st = W.stream;
     const dp_stats before = W.stats;
@@ -1163,7 +1221,8 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
     // ---- read tables on the device: lengths, packed-word offsets ----
     double t0 = now_ms();
-    W.hRel.reserve((size_t)n + 1);
+    const size_t nR = std::max<size_t>((size_t)n, W.floorReads);  // what is reserved
+    W.hRel.reserve(nR + 1);
     long long maxLen = 0;
     int64_t nWinReal = 0, nShort = 0;
     size_t seedEntries0 = 0;  // worst case: every k-mer of every round-0 window is a seed on both strands
@@ -1179,11 +1238,11 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
     W.hp[0] += now_ms() - t0;
     const long long totalBytes = W.hRel.p[n];
-    const size_t wordCap = (size_t)(totalBytes / 16 + 2 * n + 16);
-    W.dSeqOff.reserve((size_t)n + 1);
-    W.dWordsNeeded.reserve((size_t)n + 1);
-    W.dWordOff.reserve((size_t)n + 1);
-    W.dReadLen.reserve((size_t)n);
+    const size_t wordCap = std::max<size_t>((size_t)totalBytes, W.floorBytes) / 16 + 2 * nR + 16;
+    W.dSeqOff.reserve(nR + 1);
+    W.dWordsNeeded.reserve(nR + 1);
+    W.dWordOff.reserve(nR + 1);
+    W.dReadLen.reserve(nR);
     W.dWords.reserve(wordCap);
     CK(cudaMemcpyAsync(W.dSeqOff.p, W.hRel.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     dp_read_table_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(W.dSeqOff.p, n, W.dReadLen.p, W.dWordsNeeded.p);
@@ -1196,6 +1255,13 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     }
     W.stats.kernel_launches += 2;
     W.curAscii = dAscii;
+    W.curPacked = byteOff != nullptr;
+    if (byteOff) {  // packed reads: dAscii points at the first byte of read r0
+        W.hByteRel.reserve(nR);
+        W.dByteOff.reserve(nR);
+        for (int64_t i = 0; i < n; i++) W.hByteRel.p[i] = byteOff[r0 + i] - byteOff[r0];
+        CK(cudaMemcpyAsync(W.dByteOff.p, W.hByteRel.p, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+    }
     // ---- round 0 entirely on the device: windows, performMapping stages, Map()'s first decision ----
     const size_t nWin0 = 2 * (size_t)n;
     if (seedEntries0 >= 0xffffffffull) throw std::runtime_error("internal error: sub-batch cut too large");  // (map_batch_impl cuts by this bound)
@@ -1207,19 +1273,22 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     if (W.curAsciiIsHost) {  // bytes the windowed pack pulls over the link: the round-0 windows (+ one word ahead)
         for (int64_t i = 0; i < n; i++) {
             long long len = W.hRel.p[i + 1] - W.hRel.p[i];
-            if (len >= minLen) W.stats.h2d_bytes += (len <= 2ll * e) ? len : std::min<long long>(len, 2ll * (e + 32));
+            if (len >= minLen) {
+                const long long b = (len <= 2ll * e) ? len : std::min<long long>(len, 2ll * (e + 32));
+                W.stats.h2d_bytes += W.curPacked ? b / 4 + 16 : b;
+            }
         }
     }
     // Map()'s first decision per read, delivered in read order: count pass, device-wide scan, write pass straight into
     // mapped page-locked host memory (consecutive reads, consecutive records: coalesced posted writes)
     const int kUnresHead = 4096;  // unresolved reads copied with the results; a longer list is fetched afterwards
-    W.dFinN.reserve((size_t)n + 1);
-    W.dFinOff.reserve((size_t)n + 1);
-    W.hFinOff.reserve((size_t)n + 1);
-    W.dUnres.reserve((size_t)n + 1);
+    W.dFinN.reserve(nR + 1);
+    W.dFinOff.reserve(nR + 1);
+    W.hFinOff.reserve(nR + 1);
+    W.dUnres.reserve(nR + 1);
     W.hUnres.reserve((size_t)kUnresHead);
     W.hUnresN.reserve(1);
-    if (W.hFinMaps.cap < (size_t)n * 4 + 64) W.hFinMaps.reserve((size_t)n * 4 + 64);
+    if (W.hFinMaps.cap < nR * 4 + 64) W.hFinMaps.reserve(nR * 4 + 64);
     CK(cudaEventRecord(W.timers[T_FINISH].a, st));
     dp_finish_round0_kernel<false><<<div_up(n + 1, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
                                                                        W.outMaps.p, W.dFinN.p, nullptr, nullptr, 0, nullptr,
@@ -1411,8 +1480,8 @@ Caps default_caps() {
 // range is recomputed; when the candidate lists would outgrow the lane's memory budget the range is cut into pieces
 // first (a single read always fits: a window strand has at most C candidates). The lane's capacities return to their
 // defaults afterwards (the buffers stay grown).
-void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, int64_t r0, int64_t r1,
-               int* counts, SubOut& out) {
+void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff, int64_t r0,
+               int64_t r1, int* counts, SubOut& out) {
     const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);  // (tests: 0 = single reads)
     for (;;) {
         const int64_t n = r1 - r0;
@@ -1425,13 +1494,14 @@ void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t
                 if (a == b) continue;
                 SubOut part;
                 const Caps keep = W.caps;
-                map_range(M, W, dAscii + (offsets[a] - offsets[r0]), offsets, a, b, counts, part);
+                const int64_t* so = byteOff ? byteOff : offsets;  // where a read starts in the caller's buffer
+                map_range(M, W, dAscii + (so[a] - so[r0]), offsets, byteOff, a, b, counts, part);
                 W.caps = keep;
                 out.maps.insert(out.maps.end(), part.maps.begin(), part.maps.end());
             }
             return;
         }
-        const unsigned ov = map_subbatch(M, W, dAscii, offsets, r0, r1, counts, out);
+        const unsigned ov = map_subbatch(M, W, dAscii, offsets, byteOff, r0, r1, counts, out);
         if (!ov) return;
         if (!grow_caps(W.caps, ov, M.I.numChunks))
             throw std::runtime_error("a window of this batch needs more than 2^20 mappings or chains on the device");
@@ -1518,14 +1588,18 @@ void upload_ascii(Lane& W, const uint8_t* bases, const int64_t* offsets, int64_t
 }
 
 // Shared driver of the two batch entry points. `hostBases` xor `devBases` is set.
+// `offsets`: cumulative bases (= byte offsets of ASCII reads). `byteOff` (packed reads only): first byte of each read in the
+// caller's buffer, n_reads + 1 entries (the last one = one past the last read's bytes).
 void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, const uint8_t* devBases,
-                    const int64_t* offsets, dp_mapping** out, int64_t** out_offsets) {
+                    const int64_t* offsets, dp_mapping** out, int64_t** out_offsets, const int64_t* byteOff = nullptr) {
+    const int64_t* srcOff = byteOff ? byteOff : offsets;  // where a read starts in the caller's buffer
     CK(cudaSetDevice(M.device));
     double tStart = now_ms();
     // sub-batch boundaries. Sizes ramp up at the start and down at the end: the first pull / first kernels start
     // (and the last host pass ends) on a quarter-size piece, so less of the pipeline's fill and drain is exposed.
     std::vector<int64_t> cuts;
     cuts.push_back(0);
+    size_t floorReads = 0, floorBytes = 0, floorSeeds = 0;  // the largest sub-batch: what every lane sizes its buffers for
     {
         const bool ramp = !(getenv("DP_RAMP") && atoi(getenv("DP_RAMP")) == 0);  // DP_RAMP=0: equal pieces (profiling)
         const int64_t full = kSubBatchReads, tail = ramp ? full / 4 + full / 2 : 0;
@@ -1545,13 +1619,21 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                 if (seedBound > kSubBatchSeedEntries && r1 > r0) break;
                 r1++;
             }
-            if (r1 == r0) r1 = r0 + 1;
+            if (r1 == r0) {
+                seedBound = round0_seed_bound(offsets[r0 + 1] - offsets[r0], M.edge, M.k + 12);
+                r1 = r0 + 1;
+            }
+            floorSeeds = std::max(floorSeeds, seedBound);
             cuts.push_back(r1);
             r0 = r1;
         }
     }
     const size_t nSub = cuts.size() - 1;
     const int nLanes = (int)std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1));
+    for (size_t sI = 0; sI < nSub; sI++) {
+        floorReads = std::max(floorReads, (size_t)(cuts[sI + 1] - cuts[sI]));
+        floorBytes = std::max(floorBytes, (size_t)(offsets[cuts[sI + 1]] - offsets[cuts[sI]]));
+    }
     // Pinned (or registered) caller memory is read in place through its device mapping; pageable memory is staged.
     const unsigned char* mappedBase = nullptr;
     if (hostBases && !getenv("DP_NO_ZEROCOPY")) {
@@ -1566,6 +1648,10 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     for (int l = 0; l < nLanes; l++) {
         Lane& W = get_lane(M, (size_t)l);
         memset(&W.stats, 0, sizeof(W.stats));
+        W.floorReads = floorReads;
+        W.floorWins = 2 * floorReads;
+        W.floorBytes = floorBytes;
+        W.floorSeeds = floorSeeds;
     }
     std::vector<int> counts((size_t)n_reads + 1, 0);
     std::vector<SubOut> subs(nSub);
@@ -1582,17 +1668,17 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                 const unsigned char* dA;
                 W.curAsciiIsHost = false;
                 if (hostBases && mappedBase) {
-                    dA = mappedBase + offsets[r0];  // the kernels read the caller's pinned buffer in place
+                    dA = mappedBase + srcOff[r0];  // the kernels read the caller's pinned buffer in place
                     W.curAsciiIsHost = true;
                 } else if (hostBases) {
-                    upload_ascii(W, hostBases, offsets, r0, r1, false);
-                    W.stats.h2d_bytes += offsets[r1] - offsets[r0];
+                    upload_ascii(W, hostBases, srcOff, r0, r1, false);
+                    W.stats.h2d_bytes += srcOff[r1] - srcOff[r0];
                     dA = W.dAscii.p;
                 } else {
-                    dA = devBases + offsets[r0];
+                    dA = devBases + srcOff[r0];
                 }
                 W.caps = default_caps();
-                map_range(M, W, dA, offsets, r0, r1, counts.data(), subs[sI]);
+                map_range(M, W, dA, offsets, byteOff, r0, r1, counts.data(), subs[sI]);
                 W.caps = default_caps();
             }
             lane_sync(W);
@@ -1942,6 +2028,25 @@ int dp_mapper_map_batch(dp_mapper* m, int64_t n_reads, const uint8_t* bases, con
     API_CATCH
 }
 
+int dp_mapper_map_batch_packed(dp_mapper* m, int64_t n_reads, const uint8_t* packed, const int64_t* byte_offsets,
+                               const int64_t* lengths, dp_mapping** out, int64_t** out_offsets) {
+    API_TRY
+    if (!m || !byte_offsets || !lengths || !out || !out_offsets || n_reads < 0 || (!packed && n_reads > 0))
+        throw std::runtime_error("bad argument");
+    std::vector<int64_t> bases((size_t)n_reads + 1, 0);
+    for (int64_t i = 0; i < n_reads; i++) {
+        if (lengths[i] < 0 || byte_offsets[i + 1] - byte_offsets[i] < (lengths[i] + 3) / 4)
+            throw std::runtime_error("a packed read needs (length + 3) / 4 bytes between its offset and the next");
+        bases[(size_t)i + 1] = bases[(size_t)i] + lengths[i];
+    }
+    cudaPointerAttributes attr;
+    const bool onDevice = n_reads > 0 && cudaPointerGetAttributes(&attr, packed) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    map_batch_impl(*m, n_reads, onDevice ? nullptr : packed, onDevice ? packed : nullptr, bases.data(), out, out_offsets,
+                   byte_offsets);
+    API_CATCH
+}
+
 int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* query_name, int64_t query_len,
                        const char* ref_name, char* buf, int buf_len) {
     if (!m || !mp || !buf) return -1;
@@ -2055,6 +2160,7 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     CK(cudaMemcpyAsync(W.dReadLen.p, rl, sizeof(rl), cudaMemcpyHostToDevice, st));
     W.curAscii = W.dAscii.p;
     W.curAsciiIsHost = false;
+    W.curPacked = false;
     DpWindow w;
     w.read = 0;
     w.start = (int)start;

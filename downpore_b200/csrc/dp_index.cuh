@@ -137,6 +137,80 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Windowed pack for reads that ARRIVE PACKED (dp_mapper_map_batch_packed): the caller hands over what the reference's
+// own reader produces, sequence.packedSequence bytes (sequence/sequence.go:67-93: four bases per byte, first base in the
+// two most significant bits, tail byte left-aligned and zero-padded) — a quarter of a byte per base crosses the link
+// instead of one. A read starts at any byte of the batch buffer, so the window's bytes are realigned with funnel shifts
+// and byte-swapped into the 16-bases-per-word layout (first base in the top bits of the word). One warp per window; a
+// lane loads one aligned 16-byte block (out of device memory, or mapped pinned host memory: coalesced zero-copy reads
+// of just the queried bytes) and writes four words; neighbours exchange blocks by shuffle.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 6) dp_pack_windows_packed_kernel(const unsigned char* __restrict__ packed,
+                                                                        const long long* __restrict__ byteOff,  // [n] first byte of each read
+                                                                        const long long* __restrict__ seqOff,   // [n+1] cumulative bases
+                                                                        const long long* __restrict__ wordOff,
+                                                                        const DpWindow* __restrict__ wins, int nWin,
+                                                                        unsigned* __restrict__ words,
+                                                                        const unsigned char* __restrict__ stage,
+                                                                        const unsigned* __restrict__ stagePos) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nWarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned lane = dp_lane();
+    for (int w = warp; w < nWin; w += nWarps) {
+        DpWindow win = wins[w];
+        if (win.len <= 0) continue;
+        const long long readLen = seqOff[win.read + 1] - seqOff[win.read];
+        long long w0 = win.start >> 4;
+        long long w1 = ((long long)win.start + win.len - 1) >> 4;  // last word holding a window base
+        long long wLast = (readLen - 1) >> 4;                      // last word holding a read base
+        if (w1 < wLast) w1++;                                      // k-mer extraction reads one word ahead
+        const long long nWords = w1 - w0 + 1;
+        unsigned* out = words + wordOff[win.read] + w0;
+        const unsigned char* rd = packed + byteOff[win.read];
+        const unsigned char* src = rd + w0 * 4;                    // first byte of word w0
+        const unsigned mis = (unsigned)((unsigned long long)src & 15ull);
+        const uint4* blk = (const uint4*)(src - mis);              // aligned block holding that byte
+        // (staged: dp_pull_windows_kernel has copied these blocks to stage + 16 * stagePos[w])
+        if (stage) blk = (const uint4*)stage + stagePos[w];
+        const unsigned char* srcEnd = rd + ((readLen + 3) >> 2);   // one past the read's last byte
+        const long long lastBlk = ((long long)((unsigned long long)(srcEnd - 1) - (unsigned long long)(src - mis))) >> 4;
+        const long long needBlk = ((long long)mis + 4 * nWords - 1) >> 4;  // last block holding a byte of these words
+        const unsigned q = mis >> 2, sh = (mis & 3) * 8;
+        for (long long b0 = 0; b0 * 4 < nWords; b0 += 31) {  // 31 output blocks of four words per trip
+            const long long b = b0 + lane;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b <= lastBlk && b <= needBlk) v = __ldg(blk + b);  // never past the block holding the read's last byte
+            uint4 nx;
+            nx.x = __shfl_down_sync(DP_FULL, v.x, 1);
+            nx.y = __shfl_down_sync(DP_FULL, v.y, 1);
+            nx.z = __shfl_down_sync(DP_FULL, v.z, 1);
+            nx.w = __shfl_down_sync(DP_FULL, v.w, 1);
+            unsigned a0, a1, a2, a3, a4;
+            switch (q) {  // warp-uniform
+                case 0: a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w; a4 = nx.x; break;
+                case 1: a0 = v.y; a1 = v.z; a2 = v.w; a3 = nx.x; a4 = nx.y; break;
+                case 2: a0 = v.z; a1 = v.w; a2 = nx.x; a3 = nx.y; a4 = nx.z; break;
+                default: a0 = v.w; a1 = nx.x; a2 = nx.y; a3 = nx.z; a4 = nx.w; break;
+            }
+            if (lane < 31) {
+                const unsigned x[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                                       __funnelshift_r(a3, a4, sh)};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const long long g = 4 * b + t;
+                    if (g < nWords) {
+                        unsigned pv = __byte_perm(x[t], 0u, 0x0123);  // first byte of the read on top
+                        long long remain = readLen - (w0 + g) * 16;   // bases of the read in this word
+                        if (remain < 16) pv &= remain > 0 ? (~0u << (unsigned)(2 * (16 - remain))) : 0u;
+                        out[g] = pv;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The PCIe leg of the windowed pack as a copy-engine-like kernel: the 16-byte blocks that dp_pack_windows_kernel reads
 // for window w are moved from the caller's pinned buffer (host memory mapped into the device address space) to slot w
 // of a staging buffer in HBM by TMA bulk copies — host -> shared memory (cp.async.bulk, completion on an mbarrier) ->
@@ -148,8 +222,11 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
 #define DP_PULL_SLOTS 16   // ring slots per CTA
 #define DP_PULL_AHEAD 12   // loads in flight per CTA (the other slots are being stored)
 
+// `byteOff` != null: the reads are packedSequence bytes (read r starts at ascii + byteOff[r], four bases per byte) and
+// the blocks moved are the ones dp_pack_windows_packed_kernel reads.
 __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char* __restrict__ ascii,
                                                              const long long* __restrict__ seqOff,
+                                                             const long long* __restrict__ byteOff,
                                                              const DpWindow* __restrict__ wins, int nWin,
                                                              unsigned char* __restrict__ stage, int stageStride,
                                                              unsigned* __restrict__ stagePos, unsigned* __restrict__ work) {
@@ -188,12 +265,23 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
                 long long w1 = ((long long)win.start + win.len - 1) >> 4;
                 if (w1 < ((readLen - 1) >> 4)) w1++;
                 const long long nWords = w1 - w0 + 1;
-                const unsigned char* s0 = ascii + readBase + w0 * 16;
-                const unsigned mis = (unsigned)((unsigned long long)s0 & 15ull);
-                const unsigned char* blk = s0 - mis;
-                const long long lastBlk = (long long)((unsigned long long)(ascii + readBase + readLen - 1) - (unsigned long long)blk) >> 4;
-                src = (unsigned long long)blk;
-                bytes = (unsigned)(min(lastBlk, nWords) + 1) * 16u;
+                if (byteOff) {
+                    const unsigned char* rd = ascii + byteOff[win.read];
+                    const unsigned char* s0 = rd + w0 * 4;
+                    const unsigned mis = (unsigned)((unsigned long long)s0 & 15ull);
+                    const unsigned char* blk = s0 - mis;
+                    const long long lastBlk = (long long)((unsigned long long)(rd + ((readLen + 3) >> 2) - 1) - (unsigned long long)blk) >> 4;
+                    const long long needBlk = ((long long)mis + 4 * nWords - 1) >> 4;
+                    src = (unsigned long long)blk;
+                    bytes = (unsigned)(min(lastBlk, needBlk) + 1) * 16u;
+                } else {
+                    const unsigned char* s0 = ascii + readBase + w0 * 16;
+                    const unsigned mis = (unsigned)((unsigned long long)s0 & 15ull);
+                    const unsigned char* blk = s0 - mis;
+                    const long long lastBlk = (long long)((unsigned long long)(ascii + readBase + readLen - 1) - (unsigned long long)blk) >> 4;
+                    src = (unsigned long long)blk;
+                    bytes = (unsigned)(min(lastBlk, nWords) + 1) * 16u;
+                }
             }
         }
         // A window that starts where its predecessor ends (the tail window of one read and the head window of the

@@ -98,6 +98,19 @@ int dp_mapper_map_batch(dp_mapper* m, int64_t n_reads, const uint8_t* bases, con
 int dp_mapper_map_batch_device(dp_mapper* m, int64_t n_reads, const uint8_t* d_bases, const int64_t* offsets,
                                dp_mapping** out, int64_t** out_offsets);
 
+/*
+ * Mapper.Map over a batch of reads that are PACKED ALREADY, in the reference's own in-memory form: the Go host's reader
+ * hands the mapper `packedSequence`s (sequence/seqio.go:158,219 -> sequence.NewPackedSequence, sequence/sequence.go:67-93:
+ * four bases per byte, first base in the two most significant bits, tail byte left-aligned and zero-padded), so this is
+ * the entry a cgo host calls with the bytes it already holds and only a quarter of a byte per base crosses PCIe.
+ * `packed` holds the reads' byte strings back to back or with gaps: read i starts at packed[byte_offsets[i]] and has
+ * lengths[i] bases (byte_offsets has n_reads + 1 non-decreasing entries, the last one bounds the buffer). `packed` may be
+ * pageable host memory, page-locked host memory (dp_host_alloc: read in place, only the queried windows cross the link)
+ * or device memory. Results as dp_mapper_map_batch, identical to mapping the same reads as ASCII.
+ */
+int dp_mapper_map_batch_packed(dp_mapper* m, int64_t n_reads, const uint8_t* packed, const int64_t* byte_offsets,
+                               const int64_t* lengths, dp_mapping** out, int64_t** out_offsets);
+
 /* mapping.AsString (mapping/mapping.go:112-122): writes one PAF line (no newline) into buf; returns its length or -1. */
 int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* query_name, int64_t query_len,
                        const char* ref_name, char* buf, int buf_len);

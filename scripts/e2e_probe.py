@@ -20,3 +20,16 @@ for it in range(3):
 for it in range(6):
     t = time.time(); gm.map_batch_ptr(pinned.data_ptr(), offs); dt = time.time() - t
     st = gm.stats(); print("pinned %.2f ms  h2d %.0f MB  pack %.1f" % (dt * 1e3, st["h2d_bytes"] / 1e6, st["ms_pack"]), flush=True)
+# packed entry (dp_mapper_map_batch_packed) under pull variants given as extra arguments: 'ENV=V ENV2=V' ...
+pk, boff, lens = dp.pack_batch(pinned.numpy(), offs)
+pkp = torch.from_numpy(pk).pin_memory()
+for v in sys.argv[3:] or [""]:
+    env = dict(kv.split("=") for kv in v.split()) if v else {}
+    os.environ.update(env)
+    ts = []
+    for it in range(7):
+        t = time.time(); gm.map_batch_packed(pkp.data_ptr(), boff, lens); ts.append((time.time() - t) * 1e3)
+    st = gm.stats()
+    print("packed [%s] ms %s  h2d %.0f MB  pack %.1f" % (v, " ".join("%.1f" % x for x in ts), st["h2d_bytes"] / 1e6, st["ms_pack"]), flush=True)
+    for k in env:
+        del os.environ[k]

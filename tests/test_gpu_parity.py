@@ -177,6 +177,41 @@ def test_pinned_host_reads_on_mixed_reads(pair, env):
     assert 0 < st["h2d_bytes"] < len(bases)  # windows only
 
 
+def test_packed_reads_entry_point(pair):
+    """dp_mapper_map_batch_packed: the reads handed over as the reference's own packedSequence bytes
+    (sequence/sequence.go:67-93) map exactly like their ASCII — pageable, page-locked (zero-copy pull of the queried
+    bytes) and device-resident buffers; ragged, short, chimeric, empty, tiny, all-N and lowercase reads; a leading pad
+    byte so that reads start at every byte alignment; the packed bytes themselves equal the oracle's NewPackedSequence."""
+    import torch
+    ref, circular, om, gm = pair
+    reads = mixed_reads(ref, circular, seed=43, n=150, rl=4999)
+    good = synth.reads(ref, 92, 2, 3000, circular=circular)
+    reads += [np.zeros(0, dtype=np.uint8), np.frombuffer(b"ACGTACGTACGTACGTACGTAC", dtype=np.uint8),
+              np.frombuffer(b"N" * 2500, dtype=np.uint8), np.char.lower(good[:3000].view("S1")).view(np.uint8), good[3000:]]
+    bases = np.concatenate(reads)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    orow, ooff, _ = om.map_batch(bases, offs, threads=4)
+    packed, boff, lens = dp.pack_batch(bases, offs)
+    for i in (0, 3, len(reads) - 1, len(reads) - 2):
+        assert bytes(packed[boff[i]:boff[i + 1]]) == bytes(po.Packed(reads[i].tobytes()).bytes()) or len(reads[i]) == 0
+    packed = np.concatenate([np.zeros(1, dtype=np.uint8), packed, np.zeros(16, dtype=np.uint8)])
+    boff = boff + 1
+    for mode in ("pageable", "pinned", "device"):
+        if mode == "pageable":
+            maps, off = gm.map_batch_packed(packed, boff, lens)
+        elif mode == "pinned":
+            t = torch.from_numpy(packed).pin_memory()
+            for env in ({"DP_PULL_TMA": "0"}, {"DP_PULL_CTAS": "3"}, {}):  # zero-copy loads; TMA pull (few / default CTAs)
+                with _Env(env):
+                    maps, off = gm.map_batch_packed(t.data_ptr(), boff, lens)
+                assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), (mode, env)
+            assert 0 < gm.stats()["h2d_bytes"] < len(packed)  # windows only
+        else:
+            t = torch.from_numpy(packed).cuda()
+            maps, off = gm.map_batch_packed(t.data_ptr(), boff, lens)
+        assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), mode
+
+
 def test_edge_inputs(pair):
     """Empty batch; empty, tiny (< k + 12 bases: no mapping), all-N and lowercase reads between ordinary ones; the same
     through pageable, pinned and device-resident entry points."""
