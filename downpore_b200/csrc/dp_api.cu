@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -204,8 +205,13 @@ struct dp_mapper {
     DpIndexDev I{};
     long long nChunkPostings = 0, nSeedPostings = 0;
     size_t indexBytes = 0;
+    // Lanes are handed out per call (LaneSet): concurrent callers of one mapper — the reference runs num_workers goroutines
+    // against one Mapper, commands/map.go:84-86 — each work on their own lanes.
     std::vector<std::unique_ptr<Lane>> lanes;
-    dp_stats stats{};
+    std::vector<char> laneBusy;
+    std::mutex laneMu;
+    std::condition_variable laneCv;
+    dp_stats stats{};  // of the call that finished last (guarded by laneMu)
 
     ~dp_mapper() {
         lanes.clear();
@@ -1532,19 +1538,52 @@ void add_stats(dp_stats& a, const dp_stats& b) {
     a.short_reads += b.short_reads;
 }
 
-Lane& get_lane(dp_mapper& M, size_t idx) {
-    while (M.lanes.size() <= idx) {
-        std::unique_ptr<Lane> L(new Lane());
-        CK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&L->evReady, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&L->evPulled, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&L->evSync, cudaEventDisableTiming | cudaEventBlockingSync));
-        L->timers.resize(T_N);
-        for (auto& t : L->timers) t.init();
-        M.lanes.push_back(std::move(L));
+const size_t kMaxLanes = 12;  // per mapper, over all concurrent calls
+
+// The lanes one call works with: up to `want` idle ones (created on demand while the mapper has fewer than kMaxLanes);
+// a caller that finds every lane taken waits for the first to come back.
+struct LaneSet {
+    dp_mapper& M;
+    std::vector<Lane*> lanes;
+    std::vector<size_t> idx;
+    LaneSet(dp_mapper& m, size_t want) : M(m) {
+        std::unique_lock<std::mutex> lk(M.laneMu);
+        for (;;) {
+            for (size_t i = 0; i < M.lanes.size() && lanes.size() < want; i++)
+                if (!M.laneBusy[i]) take(i);
+            while (lanes.size() < want && M.lanes.size() < kMaxLanes) {
+                std::unique_ptr<Lane> L(new Lane());
+                CK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&L->evReady, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&L->evPulled, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&L->evSync, cudaEventDisableTiming | cudaEventBlockingSync));
+                L->timers.resize(T_N);
+                for (auto& t : L->timers) t.init();
+                M.lanes.push_back(std::move(L));
+                M.laneBusy.push_back(0);
+                take(M.lanes.size() - 1);
+            }
+            if (!lanes.empty()) return;
+            M.laneCv.wait(lk);
+        }
     }
-    return *M.lanes[idx];
-}
+    ~LaneSet() {
+        {
+            std::lock_guard<std::mutex> lk(M.laneMu);
+            for (size_t i : idx) M.laneBusy[i] = 0;
+        }
+        M.laneCv.notify_all();
+    }
+    LaneSet(const LaneSet&) = delete;
+    LaneSet& operator=(const LaneSet&) = delete;
+
+   private:
+    void take(size_t i) {
+        M.laneBusy[i] = 1;
+        lanes.push_back(M.lanes[i].get());
+        idx.push_back(i);
+    }
+};
 
 const int64_t kSubBatchReads = 1 << 16;
 const int64_t kSubBatchBytes = 1ll << 30;
@@ -1629,7 +1668,8 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         }
     }
     const size_t nSub = cuts.size() - 1;
-    const int nLanes = (int)std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1));
+    LaneSet held(M, std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1)));
+    const int nLanes = (int)held.lanes.size();
     for (size_t sI = 0; sI < nSub; sI++) {
         floorReads = std::max(floorReads, (size_t)(cuts[sI + 1] - cuts[sI]));
         floorBytes = std::max(floorBytes, (size_t)(offsets[cuts[sI + 1]] - offsets[cuts[sI]]));
@@ -1646,7 +1686,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         cudaGetLastError();
     }
     for (int l = 0; l < nLanes; l++) {
-        Lane& W = get_lane(M, (size_t)l);
+        Lane& W = *held.lanes[(size_t)l];
         memset(&W.stats, 0, sizeof(W.stats));
         W.floorReads = floorReads;
         W.floorWins = 2 * floorReads;
@@ -1660,7 +1700,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     auto work = [&](int l) {
         try {
             CK(cudaSetDevice(M.device));
-            Lane& W = *M.lanes[(size_t)l];
+            Lane& W = *held.lanes[(size_t)l];
             for (;;) {
                 size_t sI = nextSub.fetch_add(1);
                 if (sI >= nSub) break;
@@ -1729,17 +1769,22 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     }
     if (getenv("DP_HOST_PROFILE")) {  // where the lanes' host threads spent the call (ms, summed over sub-batches)
         for (int l = 0; l < nLanes; l++) {
-            Lane& W = *M.lanes[(size_t)l];
+            Lane& W = *held.lanes[(size_t)l];
             fprintf(stderr, "[dp host] lane %d: tables %.2f launch %.2f wait %.2f post %.2f replay+rounds %.2f assemble %.2f | call %.2f ms\n",
                     l, W.hp[0], W.hp[1] - W.hp[0], W.hp[2], W.hp[3], W.hp[4], W.hp[5], now_ms() - tStart);
             for (double& x : W.hp) x = 0;
         }
     }
-    memset(&M.stats, 0, sizeof(M.stats));
-    for (int l = 0; l < nLanes; l++) add_stats(M.stats, M.lanes[(size_t)l]->stats);
-    M.stats.bases = offsets[n_reads] - offsets[0];
-    M.stats.mappings = total;
-    M.stats.ms_total = now_ms() - tStart;
+    {
+        dp_stats st2;
+        memset(&st2, 0, sizeof(st2));
+        for (int l = 0; l < nLanes; l++) add_stats(st2, held.lanes[(size_t)l]->stats);
+        st2.bases = offsets[n_reads] - offsets[0];
+        st2.mappings = total;
+        st2.ms_total = now_ms() - tStart;
+        std::lock_guard<std::mutex> lk(M.laneMu);
+        M.stats = st2;
+    }
     *out = maps;
     *out_offsets = off;
 }
@@ -2143,7 +2188,8 @@ int dp_mapper_probe_window(dp_mapper* m, const uint8_t* read_ascii, int64_t read
     }
     if (start < 0 || end > read_len || end - start < m->k + 12 || end - start > 2 * m->edge)
         throw std::runtime_error("bad probe window");
-    Lane& W = get_lane(*m, 0);
+    LaneSet held(*m, 1);
+    Lane& W = *held.lanes[0];
     memset(&W.stats, 0, sizeof(W.stats));
     cudaStream_t st = W.stream;
     W.dAscii.reserve((size_t)read_len + 64);

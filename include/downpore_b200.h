@@ -14,8 +14,10 @@
  *   - input buffers are borrowed for the duration of the call only (cgo rule: no Go pointer is retained);
  *   - output buffers are allocated by the library with malloc() and released with dp_free();
  *   - a dp_mapper is bound to one CUDA device; create one per GPU and shard read batches across them
- *     (reads are independent: commands/map.go:84-86). dp_mapper_map_batch may be called from one thread at a
- *     time per mapper;
+ *     (reads are independent: commands/map.go:84-86). The batch entry points may be called from several threads at once
+ *     on one mapper, as the reference's num_workers goroutines call Mapper.Map (each call works on its own lanes — a
+ *     stream and a workspace — of at most 12 per mapper; a caller that finds all of them taken waits);
+ *     dp_mapper_get_stats reports the call that finished last;
  *   - there is no CPU fallback: every entry point fails if no CUDA device is usable.
  */
 #ifndef DOWNPORE_B200_H

@@ -107,3 +107,22 @@ def test_cli_output_identical_to_oracle(tmp_path, fastq, circular):
     got = run([host()] + args2)
     assert want.returncode == 0 and got.returncode == 0, (want.stderr, got.stderr)
     assert got.stdout == want.stdout and counters(got.stderr) == counters(want.stderr)
+
+
+@pytest.mark.gpu
+def test_cli_on_two_gpus_in_one_process(tmp_path):
+    """DOWNPORE_GPUS=0,1: one mapping thread per GPU inside one process, the index built on the first GPU and opened on the
+    second from its image (dp_mapper_index_export -> dp_mapper_create_from_index, the peer-copy route INTEGRATION.md
+    recommends to a Go host); output identical to the single-GPU run and to the oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    po.build()
+    ref_path, reads_path = write_inputs(str(tmp_path), False, True)
+    args = ["-input", reads_path, "-r", ref_path, "-ci", "true"]
+    want = run([ORACLE_MAP] + args)
+    one = run([host()] + args, env={"DOWNPORE_BATCH": "8", "DOWNPORE_GPUS": "0"})
+    two = run([host()] + args, env={"DOWNPORE_BATCH": "8", "DOWNPORE_GPUS": "0,1"})
+    assert want.returncode == 0 and one.returncode == 0 and two.returncode == 0, (one.stderr, two.stderr)
+    assert two.stdout == one.stdout == want.stdout
+    assert counters(two.stderr) == counters(want.stderr)

@@ -212,6 +212,38 @@ def test_packed_reads_entry_point(pair):
         assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), mode
 
 
+def test_concurrent_callers_of_one_mapper(pair):
+    """The reference runs num_workers goroutines against one Mapper (commands/map.go:84-86): several threads may call
+    dp_mapper_map_batch on one mapper at once (each call works on its own lanes) and get what a lone caller gets."""
+    import threading
+    ref, circular, om, gm = pair
+    batches = []
+    for t in range(4):
+        reads = mixed_reads(ref, circular, seed=60 + t, n=120, rl=4000 + 500 * t)
+        bases = np.concatenate(reads)
+        offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+        batches.append((bases, offs))
+    alone = [gm.map_batch(b, o) for b, o in batches]
+    got = [None] * len(batches)
+    errs = []
+
+    def call(i):
+        try:
+            for _ in range(3):
+                got[i] = gm.map_batch(*batches[i])
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=call, args=(i,)) for i in range(len(batches))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for (m1, o1), (m2, o2) in zip(alone, got):
+        assert np.array_equal(o1, o2) and np.array_equal(rows_of(m1), rows_of(m2))
+
+
 def test_edge_inputs(pair):
     """Empty batch; empty, tiny (< k + 12 bases: no mapping), all-N and lowercase reads between ordinary ones; the same
     through pageable, pinned and device-resident entry points."""
