@@ -84,6 +84,14 @@ _SIGNATURES = {
                                               c_vp, c_vp, c_i64, c_vp, c_vp, c_i64]),
     "dp_pack": (ctypes.c_int, [c_vp, c_i64, c_vp, ctypes.c_int]),
     "dp_kmer_counts": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, ctypes.c_int]),
+    "dp_split_records": (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                        ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "dp_mapper_map_batch_spans": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
+    "dp_mapper_paf_block": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_char_p, ctypes.POINTER(c_vp),
+                                           ctypes.POINTER(c_i64)]),
+    "dp_device_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t, ctypes.c_int]),
+    "dp_device_free": (None, [c_vp, ctypes.c_int]),
+    "dp_device_copy": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int]),
 }
 
 
@@ -178,6 +186,48 @@ def host_alloc(nbytes):
     buf = (ctypes.c_ubyte * nbytes).from_address(p.value)
     weakref.finalize(buf, lib().dp_host_free, p.value)
     return np.frombuffer(buf, dtype=np.uint8)
+
+
+RECORD_DTYPE = np.dtype([("name_start", "<i8"), ("name_len", "<i8"), ("seq_start", "<i8"), ("seq_len", "<i8")])
+
+
+class DeviceImage:
+    """A file image (or a piece of one) uploaded once into device memory (dp_device_alloc / dp_device_copy)."""
+
+    def __init__(self, data, device=0):
+        a = _u8(data)
+        self.nbytes, self.device = int(a.size), device
+        p = c_vp()
+        _check(lib().dp_device_alloc(ctypes.byref(p), max(self.nbytes, 1), device))
+        self.ptr = p.value
+        self._fin = weakref.finalize(self, lib().dp_device_free, p.value, device)
+        _check(lib().dp_device_copy(self.ptr, a.ctypes.data, self.nbytes, device))
+
+
+def _image_ptr(image):
+    if isinstance(image, DeviceImage):
+        return image.ptr, image.nbytes, None
+    if isinstance(image, tuple):  # (raw pointer, bytes)
+        return int(image[0]), int(image[1]), None
+    a = _u8(image)
+    return a.ctypes.data, int(a.size), a
+
+
+def split_records(image, min_length=0, final=True, is_fastq=0, device=0):
+    """readFasta's record rules (sequence/seqio.go:188-267) on the device: the (name, sequence) spans of a FASTA/FASTQ file
+    image. `image`: bytes / numpy uint8 / DeviceImage / (pointer, nbytes). Returns (records[RECORD_DTYPE], consumed,
+    is_fastq): with final=False only the records in front of the piece's last name line, `consumed` = where it starts."""
+    ptr, n, keep = _image_ptr(image)
+    rec_p, nrec, cons, fq = c_vp(), c_i64(), c_i64(), ctypes.c_int(int(is_fastq))
+    _check(lib().dp_split_records(ptr, n, int(min_length), int(bool(final)), ctypes.byref(fq), device, ctypes.byref(rec_p),
+                                  ctypes.byref(nrec), ctypes.byref(cons)))
+    k = int(nrec.value)
+    if k:
+        recs = _adopt(rec_p, k * RECORD_DTYPE.itemsize, RECORD_DTYPE)
+    else:
+        lib().dp_free(rec_p)
+        recs = np.zeros(0, dtype=RECORD_DTYPE)
+    return recs, int(cons.value), int(fq.value)
 
 
 def probe_gather_gbs(table_bytes=8 << 30, device=0):
@@ -320,6 +370,31 @@ class Mapper:
         _check(lib().dp_mapper_map_batch_packed(self._h, n, packed, byte_offsets.ctypes.data, lengths.ctypes.data,
                                                 ctypes.byref(out_p), ctypes.byref(off_p)))
         return self._collect(n, out_p, off_p)
+
+    def map_batch_spans(self, image, records):
+        """Mapper.Map over reads mapped where they lie in a file image (records of split_records)."""
+        ptr, _, keep = _image_ptr(image)
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        n = records.size
+        out_p, off_p = c_vp(), c_vp()
+        _check(lib().dp_mapper_map_batch_spans(self._h, n, ptr, records.ctypes.data, ctypes.byref(out_p),
+                                               ctypes.byref(off_p)))
+        return self._collect(n, out_p, off_p)
+
+    def paf_block(self, image, records, maps, out_off):
+        """Mapper.AsString for every mapping of a batch, formatted on the device -> bytes (lines end in a newline)."""
+        ptr, _, keep = _image_ptr(image)
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        maps = np.ascontiguousarray(maps, dtype=MAPPING_DTYPE)
+        out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+        txt_p, nb = c_vp(), c_i64()
+        _check(lib().dp_mapper_paf_block(self._h, records.size, ptr, records.ctypes.data, maps.ctypes.data,
+                                         out_off.ctypes.data, self.ref_name.encode(), ctypes.byref(txt_p),
+                                         ctypes.byref(nb)))
+        try:
+            return ctypes.string_at(txt_p.value, nb.value)
+        finally:
+            lib().dp_free(txt_p)
 
     def map_batch_ptr(self, host_ptr, offsets):
         """Same as map_batch for a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""

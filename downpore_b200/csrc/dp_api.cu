@@ -21,6 +21,7 @@
 #include "dp_finish.cuh"
 #include "dp_host_map.hpp"
 #include "dp_index.cuh"
+#include "dp_io.cuh"
 #include "dp_map.cuh"
 
 namespace {
@@ -162,6 +163,7 @@ struct Lane {
     // map_batch_impl), not grown piece by piece as the lane happens to meet larger sub-batches: a cudaFree in the middle
     // of a call synchronises the device under every other lane.
     size_t floorReads = 0, floorWins = 0, floorSeeds = 0, floorBytes = 0;
+    bool curSpans = false;   // ASCII reads at arbitrary places of the caller's buffer (dp_mapper_map_batch_spans): dByteOff
     bool curPacked = false;  // the reads are sequence.packedSequence bytes (dp_mapper_map_batch_packed), not ASCII
     DBuf<long long> dByteOff;  // packed input: first byte of each read, relative to curAscii
     HBuf<long long> hByteRel;
@@ -761,6 +763,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         // PCIe-bound when the reads are pulled from host memory: keep its footprint at two CTAs per SM so the lanes'
         // compute kernels stay resident beside it
         int perSm = W.curAsciiIsHost ? 2 : 6;
+        const long long* spanOff = W.curSpans ? W.dByteOff.p : nullptr;  // ASCII reads addressed by their own offsets
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         const int stageStride = ((I.maxWindow + 15) / 16 + 3) * 16;  // the 16-byte blocks of the longest window
         const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * 2 * stageStride <= 96 * 1024;
@@ -781,7 +784,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 64)));
                 CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
                 dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * pkStride, M.pullStream>>>(
-                    W.curAscii, W.dSeqOff.p, W.dByteOff.p, W.dWins.p, (int)nWin, W.dStage.p, pkStride, W.dStagePos.p,
+                    W.curAscii, W.dSeqOff.p, W.dByteOff.p, true, W.dWins.p, (int)nWin, W.dStage.p, pkStride, W.dStagePos.p,
                     W.dPullWork.p);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
@@ -828,13 +831,14 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
                 CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
                 dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * stageStride, M.pullStream>>>(
-                    W.curAscii, W.dSeqOff.p, nullptr, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p, W.dPullWork.p);
+                    W.curAscii, W.dSeqOff.p, spanOff, false, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p,
+                    W.dPullWork.p);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
             CK(cudaStreamWaitEvent(st, W.evPulled, 0));
             int fullBlocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * 6);
-            dp_pack_windows_kernel<<<fullBlocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+            dp_pack_windows_kernel<<<fullBlocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, spanOff, dWordOff, W.dWins.p, (int)nWin,
                                                                const_cast<unsigned*>(dWords), W.dStage.p, W.dStagePos.p);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, st));
@@ -844,7 +848,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             CK(cudaEventRecord(W.evReady, st));
             CK(cudaStreamWaitEvent(M.pullStream, W.evReady, 0));
             CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
-            dp_pack_windows_kernel<<<blocks, 256, 0, M.pullStream>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+            dp_pack_windows_kernel<<<blocks, 256, 0, M.pullStream>>>(W.curAscii, W.dSeqOff.p, spanOff, dWordOff, W.dWins.p, (int)nWin,
                                                                     const_cast<unsigned*>(dWords), nullptr, nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, M.pullStream));
@@ -852,7 +856,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
             CK(cudaStreamWaitEvent(st, W.evPulled, 0));
         } else {
             CK(cudaEventRecord(W.timers[T_PACK].a, st));
-            dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, dWordOff, W.dWins.p, (int)nWin,
+            dp_pack_windows_kernel<<<blocks, 256, 0, st>>>(W.curAscii, W.dSeqOff.p, spanOff, dWordOff, W.dWins.p, (int)nWin,
                                                            const_cast<unsigned*>(dWords), nullptr, nullptr);
             CK(cudaGetLastError());
             CK(cudaEventRecord(W.timers[T_PACK].b, st));
@@ -1217,7 +1221,7 @@ inline size_t round0_seed_bound(long long len, int e, int minLen) {
 // capacities (W.caps). Returns 0 and fills counts[r0..r1) and `out` (ordered by read), or returns the DP_OV_* bits of
 // a capacity that was too small: nothing is delivered then and the caller reruns the range with more room (map_range).
 unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff,
-                      int64_t r0, int64_t r1, int* counts, SubOut& out) {
+                      bool packed, int64_t r0, int64_t r1, int* counts, SubOut& out) {
     const int64_t n = r1 - r0;
     cudaStream_t st = W.stream;
     const dp_stats before = W.stats;
@@ -1261,8 +1265,9 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     }
     W.stats.kernel_launches += 2;
     W.curAscii = dAscii;
-    W.curPacked = byteOff != nullptr;
-    if (byteOff) {  // packed reads: dAscii points at the first byte of read r0
+    W.curPacked = byteOff != nullptr && packed;
+    W.curSpans = byteOff != nullptr && !packed;
+    if (byteOff) {  // reads addressed by their own offsets: dAscii points at the first byte of read r0
         W.hByteRel.reserve(nR);
         W.dByteOff.reserve(nR);
         for (int64_t i = 0; i < n; i++) W.hByteRel.p[i] = byteOff[r0 + i] - byteOff[r0];
@@ -1486,8 +1491,8 @@ Caps default_caps() {
 // range is recomputed; when the candidate lists would outgrow the lane's memory budget the range is cut into pieces
 // first (a single read always fits: a window strand has at most C candidates). The lane's capacities return to their
 // defaults afterwards (the buffers stay grown).
-void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff, int64_t r0,
-               int64_t r1, int* counts, SubOut& out) {
+void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff, bool packed,
+               int64_t r0, int64_t r1, int* counts, SubOut& out) {
     const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);  // (tests: 0 = single reads)
     for (;;) {
         const int64_t n = r1 - r0;
@@ -1501,13 +1506,13 @@ void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t
                 SubOut part;
                 const Caps keep = W.caps;
                 const int64_t* so = byteOff ? byteOff : offsets;  // where a read starts in the caller's buffer
-                map_range(M, W, dAscii + (so[a] - so[r0]), offsets, byteOff, a, b, counts, part);
+                map_range(M, W, dAscii + (so[a] - so[r0]), offsets, byteOff, packed, a, b, counts, part);
                 W.caps = keep;
                 out.maps.insert(out.maps.end(), part.maps.begin(), part.maps.end());
             }
             return;
         }
-        const unsigned ov = map_subbatch(M, W, dAscii, offsets, byteOff, r0, r1, counts, out);
+        const unsigned ov = map_subbatch(M, W, dAscii, offsets, byteOff, packed, r0, r1, counts, out);
         if (!ov) return;
         if (!grow_caps(W.caps, ov, M.I.numChunks))
             throw std::runtime_error("a window of this batch needs more than 2^20 mappings or chains on the device");
@@ -1627,10 +1632,11 @@ void upload_ascii(Lane& W, const uint8_t* bases, const int64_t* offsets, int64_t
 }
 
 // Shared driver of the two batch entry points. `hostBases` xor `devBases` is set.
-// `offsets`: cumulative bases (= byte offsets of ASCII reads). `byteOff` (packed reads only): first byte of each read in the
-// caller's buffer, n_reads + 1 entries (the last one = one past the last read's bytes).
+// `offsets`: cumulative bases (= byte offsets of back-to-back ASCII reads). `byteOff` (packed reads, or ASCII reads mapped where
+// they lie in a file image): first byte of each read in the caller's buffer, n_reads + 1 entries (the last one bounds the buffer).
 void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, const uint8_t* devBases,
-                    const int64_t* offsets, dp_mapping** out, int64_t** out_offsets, const int64_t* byteOff = nullptr) {
+                    const int64_t* offsets, dp_mapping** out, int64_t** out_offsets, const int64_t* byteOff = nullptr,
+                    bool packed = false) {
     const int64_t* srcOff = byteOff ? byteOff : offsets;  // where a read starts in the caller's buffer
     CK(cudaSetDevice(M.device));
     double tStart = now_ms();
@@ -1718,7 +1724,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                     dA = devBases + srcOff[r0];
                 }
                 W.caps = default_caps();
-                map_range(M, W, dA, offsets, byteOff, r0, r1, counts.data(), subs[sI]);
+                map_range(M, W, dA, offsets, byteOff, packed, r0, r1, counts.data(), subs[sI]);
                 W.caps = default_caps();
             }
             lane_sync(W);
@@ -2088,7 +2094,7 @@ int dp_mapper_map_batch_packed(dp_mapper* m, int64_t n_reads, const uint8_t* pac
     const bool onDevice = n_reads > 0 && cudaPointerGetAttributes(&attr, packed) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();
     map_batch_impl(*m, n_reads, onDevice ? nullptr : packed, onDevice ? packed : nullptr, bases.data(), out, out_offsets,
-                   byte_offsets);
+                   byte_offsets, true);
     API_CATCH
 }
 
@@ -2101,6 +2107,257 @@ int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* que
                      (long long)query_len, mp->q_offset, (long long)query_len - mp->q_inset, mp->rc ? "-" : "+",
                      ref_name, m->refLen, (long long)mp->start, (long long)mp->end, mp->ids, mappedLength);
     return (n < 0 || n >= buf_len) ? -1 : n;
+}
+
+// ---- input / output side on the device (dp_io.cuh) --------------------------------------------------------------
+extern "C++" {
+namespace {
+
+template <class T>
+void exclusive_sum(const int* in, T* out, size_t n, DBuf<unsigned char>& tmp, cudaStream_t st) {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, st);
+    tmp.reserve(tb);
+    tb = tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, (int)n, st));
+}
+
+// the pointer a kernel of `device` can read `p` through; `staged` receives a device copy when `p` is pageable host memory
+const unsigned char* device_view(const uint8_t* p, size_t bytes, DBuf<unsigned char>& staged, bool forceCopy = false) {
+    cudaPointerAttributes attr;
+    const bool known = cudaPointerGetAttributes(&attr, p) == cudaSuccess;
+    cudaGetLastError();
+    if (known && attr.type == cudaMemoryTypeDevice) return p;
+    if (known && attr.type == cudaMemoryTypeManaged) return p;
+    if (known && attr.type == cudaMemoryTypeHost && !forceCopy) {
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, const_cast<uint8_t*>(p), 0) == cudaSuccess) return static_cast<const unsigned char*>(d);
+        cudaGetLastError();
+    }
+    staged.reserve(bytes + 64);
+    CK(cudaMemcpy(staged.p, p, bytes, cudaMemcpyDefault));
+    return staged.p;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int dp_device_alloc(void** out, size_t bytes, int device) {
+    API_TRY
+    if (!out) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(out, bytes ? bytes : 1));
+    API_CATCH
+}
+
+void dp_device_free(void* p, int device) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+
+int dp_device_copy(void* dst, const void* src, size_t bytes, int device) {
+    API_TRY
+    if ((!dst || !src) && bytes) throw std::runtime_error("bad argument");
+    CK(cudaSetDevice(device));
+    if (bytes) CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    API_CATCH
+}
+
+int dp_split_records(const uint8_t* image, int64_t bytes, int64_t min_length, int final_piece, int* is_fastq, int device,
+                     dp_record** records, int64_t* n_records, int64_t* consumed) {
+    API_TRY
+    if (!records || !n_records || bytes < 0 || (!image && bytes > 0)) throw std::runtime_error("bad argument");
+    static_assert(sizeof(dp_record) == sizeof(DpRecordDev), "dp_record layout");
+    CK(cudaSetDevice(device));
+    *records = nullptr;
+    *n_records = 0;
+    if (consumed) *consumed = final_piece ? bytes : 0;
+    if (bytes == 0) {
+        *records = (dp_record*)malloc(sizeof(dp_record));
+        return 0;
+    }
+    cudaStream_t st = nullptr;  // (a one-off pass per file piece: the default stream keeps it simple)
+    DBuf<unsigned char> staged, scanTmp, cls;
+    // host memory is copied once (two passes read every byte; the link should carry it once)
+    const unsigned char* buf = device_view(image, (size_t)bytes, staged, true);
+    const unsigned mis = (unsigned)((unsigned long long)buf & 15ull);
+    const long long nTiles = ((long long)bytes + mis + DP_IO_TILE - 1) / DP_IO_TILE;
+    if (nTiles + 1 >= (1ll << 31)) throw std::runtime_error("file piece too large: at most 2^31 tiles of 64 bytes");
+    DBuf<int> cnt, off;
+    cnt.reserve((size_t)nTiles + 1);
+    off.reserve((size_t)nTiles + 1);
+    const int tb = 256;
+    dp_line_starts_kernel<false><<<div_up(nTiles + 1, tb), tb, 0, st>>>(buf, bytes, nTiles, cnt.p, nullptr, nullptr);
+    CK(cudaGetLastError());
+    exclusive_sum(cnt.p, off.p, (size_t)nTiles + 1, scanTmp, st);
+    int extra = 0;
+    CK(cudaMemcpy(&extra, off.p + nTiles, sizeof(int), cudaMemcpyDeviceToHost));
+    const long long nLines = 1 + (long long)extra;
+    DBuf<long long> lineStart, candSeq, candName, res;
+    lineStart.reserve((size_t)nLines);
+    dp_line_starts_kernel<true><<<div_up(nTiles + 1, tb), tb, 0, st>>>(buf, bytes, nTiles, nullptr, off.p, lineStart.p);
+    CK(cudaGetLastError());
+    cls.reserve((size_t)nLines);
+    dp_line_class_kernel<<<div_up(nLines, tb), tb, 0, st>>>(buf, lineStart.p, nLines, cls.p);
+    CK(cudaGetLastError());
+    candSeq.reserve((size_t)nLines);
+    candName.reserve((size_t)nLines);
+    res.reserve(4);
+    unsigned char lastByte = 0;
+    CK(cudaMemcpy(&lastByte, buf + bytes - 1, 1, cudaMemcpyDeviceToHost));
+    dp_record_walk_kernel<<<1, 32, 0, st>>>(cls.p, nLines, lastByte == '\n', final_piece != 0, is_fastq && *is_fastq, candSeq.p,
+                                            candName.p, res.p);
+    CK(cudaGetLastError());
+    long long hres[4];
+    CK(cudaMemcpy(hres, res.p, sizeof(hres), cudaMemcpyDeviceToHost));
+    if (hres[1]) throw std::runtime_error("Invalid fastq format (on + line)");  // the reference's log.Fatal (seqio.go:226,242)
+    const long long nCand = hres[0];
+    long long dropName = -1;
+    if (!final_piece) {
+        dropName = hres[2];
+        if (dropName == 0) throw std::runtime_error("the piece holds no complete record after its first name line: pass a larger piece");
+        long long cut = 0;
+        CK(cudaMemcpy(&cut, lineStart.p + dropName, sizeof(long long), cudaMemcpyDeviceToHost));
+        if (consumed) *consumed = cut;
+        if (is_fastq) *is_fastq = (int)hres[3];
+    } else if (is_fastq) {
+        *is_fastq = 0;
+    }
+    DBuf<int> keep, koff;
+    keep.reserve((size_t)nCand + 1);
+    koff.reserve((size_t)nCand + 1);
+    dp_record_finish_kernel<false><<<div_up(nCand + 1, tb), tb, 0, st>>>(buf, bytes, lineStart.p, nLines, candSeq.p, candName.p, nCand,
+                                                                        min_length, dropName, keep.p, nullptr, nullptr);
+    CK(cudaGetLastError());
+    exclusive_sum(keep.p, koff.p, (size_t)nCand + 1, scanTmp, st);
+    int nKept = 0;
+    CK(cudaMemcpy(&nKept, koff.p + nCand, sizeof(int), cudaMemcpyDeviceToHost));
+    DBuf<DpRecordDev> recs;
+    recs.reserve((size_t)nKept + 1);
+    dp_record_finish_kernel<true><<<div_up(nCand + 1, tb), tb, 0, st>>>(buf, bytes, lineStart.p, nLines, candSeq.p, candName.p, nCand,
+                                                                       min_length, dropName, nullptr, koff.p, recs.p);
+    CK(cudaGetLastError());
+    dp_record* outRecs = (dp_record*)malloc(sizeof(dp_record) * (size_t)(nKept ? nKept : 1));
+    if (!outRecs) throw std::runtime_error("out of host memory for the records");
+    cudaError_t e = cudaMemcpy(outRecs, recs.p, sizeof(dp_record) * (size_t)nKept, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        free(outRecs);
+        CK(e);
+    }
+    *records = outRecs;
+    *n_records = nKept;
+    API_CATCH
+}
+
+int dp_mapper_map_batch_spans(dp_mapper* m, int64_t n_reads, const uint8_t* image, const dp_record* records, dp_mapping** out,
+                              int64_t** out_offsets) {
+    API_TRY
+    if (!m || !out || !out_offsets || n_reads < 0 || ((!image || !records) && n_reads > 0)) throw std::runtime_error("bad argument");
+    std::vector<int64_t> bases((size_t)n_reads + 1, 0), starts((size_t)n_reads + 1, 0);
+    int64_t bound = 0;
+    for (int64_t i = 0; i < n_reads; i++) {
+        const dp_record& r = records[i];
+        if (r.seq_len < 0 || r.seq_start < 0 || (i > 0 && r.seq_start < records[i - 1].seq_start + records[i - 1].seq_len))
+            throw std::runtime_error("records must lie in the image in ascending order without overlap");
+        bases[(size_t)i + 1] = bases[(size_t)i] + r.seq_len;
+        starts[(size_t)i] = r.seq_start;
+        bound = r.seq_start + r.seq_len;
+    }
+    starts[(size_t)n_reads] = bound;
+    cudaPointerAttributes attr;
+    const bool onDevice = n_reads > 0 && cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    map_batch_impl(*m, n_reads, onDevice ? nullptr : image, onDevice ? image : nullptr, bases.data(), out, out_offsets,
+                   starts.data(), false);
+    API_CATCH
+}
+
+int dp_mapper_paf_block(const dp_mapper* m, int64_t n_reads, const uint8_t* image, const dp_record* records,
+                        const dp_mapping* maps, const int64_t* out_offsets, const char* ref_name, char** text,
+                        int64_t* text_bytes) {
+    API_TRY
+    if (!m || !text || !text_bytes || !ref_name || n_reads < 0 || ((!records || !out_offsets || !image) && n_reads > 0))
+        throw std::runtime_error("bad argument");
+    static_assert(sizeof(dp_mapping) == sizeof(DpMappingDev), "dp_mapping layout");
+    CK(cudaSetDevice(m->device));
+    const long long nMaps = n_reads > 0 ? out_offsets[n_reads] : 0;
+    if (nMaps > 0 && !maps) throw std::runtime_error("bad argument");
+    *text = nullptr;
+    *text_bytes = 0;
+    if (nMaps == 0) {
+        *text = (char*)malloc(1);
+        return 0;
+    }
+    DpPafParams P;
+    memset(&P, 0, sizeof(P));
+    P.refLen = m->refLen;
+    P.circular = m->circular;
+    const size_t rl = strlen(ref_name);
+    if (rl >= sizeof(P.refName)) throw std::runtime_error("reference name longer than 255 bytes");
+    memcpy(P.refName, ref_name, rl);
+    P.refNameLen = (int)rl;
+    // the names: read where they lie when the image is device-visible, else gathered into one block first
+    DBuf<unsigned char> staged;
+    std::vector<dp_record> recs(records, records + n_reads);
+    const unsigned char* names = nullptr;
+    {
+        cudaPointerAttributes attr;
+        const bool known = cudaPointerGetAttributes(&attr, image) == cudaSuccess;
+        cudaGetLastError();
+        if (known && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) names = image;
+        else if (known && attr.type == cudaMemoryTypeHost) {
+            void* d = nullptr;
+            if (cudaHostGetDevicePointer(&d, const_cast<uint8_t*>(image), 0) == cudaSuccess) names = static_cast<const unsigned char*>(d);
+            cudaGetLastError();
+        }
+        if (!names) {
+            std::vector<unsigned char> blk;
+            for (int64_t i = 0; i < n_reads; i++) {
+                const int64_t a = (int64_t)blk.size();
+                if (records[i].name_len < 0 || records[i].name_start < 0) throw std::runtime_error("bad record");
+                blk.insert(blk.end(), image + records[i].name_start, image + records[i].name_start + records[i].name_len);
+                recs[(size_t)i].name_start = a;
+            }
+            staged.reserve(blk.size() + 64);
+            CK(cudaMemcpy(staged.p, blk.data(), blk.size(), cudaMemcpyHostToDevice));
+            names = staged.p;
+        }
+    }
+    DBuf<DpRecordDev> dRecs;
+    DBuf<DpMappingDev> dMaps;
+    DBuf<long long> dOutOff, lineOff;
+    DBuf<int> lineLen;
+    DBuf<unsigned char> scanTmp;
+    DBuf<char> dText;
+    dRecs.reserve((size_t)n_reads);
+    dMaps.reserve((size_t)nMaps);
+    dOutOff.reserve((size_t)n_reads + 1);
+    lineLen.reserve((size_t)nMaps + 1);
+    lineOff.reserve((size_t)nMaps + 1);
+    CK(cudaMemcpy(dRecs.p, recs.data(), sizeof(dp_record) * (size_t)n_reads, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dMaps.p, maps, sizeof(dp_mapping) * (size_t)nMaps, cudaMemcpyDefault));
+    CK(cudaMemcpy(dOutOff.p, out_offsets, sizeof(int64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice));
+    const int tb = 128;
+    dp_paf_kernel<false><<<div_up(nMaps + 1, tb), tb>>>(P, dMaps.p, nMaps, dOutOff.p, n_reads, names, dRecs.p, lineLen.p, nullptr, nullptr);
+    CK(cudaGetLastError());
+    exclusive_sum(lineLen.p, lineOff.p, (size_t)nMaps + 1, scanTmp, nullptr);
+    long long total = 0;
+    CK(cudaMemcpy(&total, lineOff.p + nMaps, sizeof(long long), cudaMemcpyDeviceToHost));
+    dText.reserve((size_t)total + 1);
+    dp_paf_kernel<true><<<div_up(nMaps + 1, tb), tb>>>(P, dMaps.p, nMaps, dOutOff.p, n_reads, names, dRecs.p, nullptr, lineOff.p, dText.p);
+    CK(cudaGetLastError());
+    char* outText = (char*)malloc((size_t)total + 1);
+    if (!outText) throw std::runtime_error("out of host memory for the PAF text");
+    cudaError_t e = cudaMemcpy(outText, dText.p, (size_t)total, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        free(outText);
+        CK(e);
+    }
+    outText[total] = 0;
+    *text = outText;
+    *text_bytes = total;
+    API_CATCH
 }
 
 int dp_mapper_get_stats(const dp_mapper* m, dp_stats* out) {

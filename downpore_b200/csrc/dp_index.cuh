@@ -61,8 +61,11 @@ __global__ void __launch_bounds__(256) dp_pack_kernel(const unsigned char* __res
 // (one LDG.128 each, 512 contiguous bytes per warp), neighbours exchange blocks by shuffle, and 31 packed words are
 // written. Each source byte crosses the bus once (+1/31 overlap).
 // ---------------------------------------------------------------------------------------------------------------
+// `byteOff` != null (dp_mapper_map_batch_spans): read r starts at ascii + byteOff[r] instead of ascii + seqOff[r] (reads
+// mapped where they lie in a file image, name lines between them).
 __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned char* __restrict__ ascii,
                                                               const long long* __restrict__ seqOff,
+                                                              const long long* __restrict__ byteOff,
                                                               const long long* __restrict__ wordOff,
                                                               const DpWindow* __restrict__ wins, int nWin,
                                                               unsigned* __restrict__ words,
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_kernel(const unsigned 
     for (int w = warp; w < nWin; w += nWarps) {
         DpWindow win = wins[w];
         if (win.len <= 0) continue;
-        const long long readBase = seqOff[win.read];
-        const long long readLen = seqOff[win.read + 1] - readBase;
+        const long long readLen = seqOff[win.read + 1] - seqOff[win.read];
+        const long long readBase = byteOff ? byteOff[win.read] : seqOff[win.read];
         // packed words covering the window, plus the following word when it still holds bases of the read
         long long w0 = win.start >> 4;
         long long w1 = ((long long)win.start + win.len - 1) >> 4;  // last word holding a window base
@@ -222,11 +225,11 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_packed_kernel(const un
 #define DP_PULL_SLOTS 16   // ring slots per CTA
 #define DP_PULL_AHEAD 12   // loads in flight per CTA (the other slots are being stored)
 
-// `byteOff` != null: the reads are packedSequence bytes (read r starts at ascii + byteOff[r], four bases per byte) and
-// the blocks moved are the ones dp_pack_windows_packed_kernel reads.
+// `byteOff` != null: read r starts at ascii + byteOff[r]; `packed`: the reads are packedSequence bytes (four bases per
+// byte) and the blocks moved are the ones dp_pack_windows_packed_kernel reads.
 __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char* __restrict__ ascii,
                                                              const long long* __restrict__ seqOff,
-                                                             const long long* __restrict__ byteOff,
+                                                             const long long* __restrict__ byteOff, bool packed,
                                                              const DpWindow* __restrict__ wins, int nWin,
                                                              unsigned char* __restrict__ stage, int stageStride,
                                                              unsigned* __restrict__ stagePos, unsigned* __restrict__ work) {
@@ -259,14 +262,14 @@ __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char
         if (w < nWin) {
             const DpWindow win = wins[w];
             if (win.len > 0) {
-                const long long readBase = seqOff[win.read];
-                const long long readLen = seqOff[win.read + 1] - readBase;
+                const long long readLen = seqOff[win.read + 1] - seqOff[win.read];
+                const long long readBase = byteOff ? byteOff[win.read] : seqOff[win.read];
                 const long long w0 = win.start >> 4;
                 long long w1 = ((long long)win.start + win.len - 1) >> 4;
                 if (w1 < ((readLen - 1) >> 4)) w1++;
                 const long long nWords = w1 - w0 + 1;
-                if (byteOff) {
-                    const unsigned char* rd = ascii + byteOff[win.read];
+                if (packed) {
+                    const unsigned char* rd = ascii + readBase;
                     const unsigned char* s0 = rd + w0 * 4;
                     const unsigned mis = (unsigned)((unsigned long long)s0 & 15ull);
                     const unsigned char* blk = s0 - mis;

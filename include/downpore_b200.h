@@ -117,6 +117,49 @@ int dp_mapper_map_batch_packed(dp_mapper* m, int64_t n_reads, const uint8_t* pac
 int dp_mapper_paf_line(const dp_mapper* m, const dp_mapping* mp, const char* query_name, int64_t query_len,
                        const char* ref_name, char* buf, int buf_len);
 
+/*
+ * Input and output side on the device.
+ *
+ * dp_split_records: the record rules of the reference's reader, readFasta's first pass (sequence/seqio.go:188-267),
+ * applied on `device` to a FASTA/FASTQ file image — or to one piece of it — `image` in host or device memory:
+ * the first line is a header; every later line that starts with 'A'..'T' is a sequence under the name line in force
+ * (its line minus the last byte, kept when the line with its newline has at least min_length bytes); once a line
+ * starting with '@' has been seen each sequence line is followed by a '+' line (anything else: error "Invalid fastq
+ * format", the reference's log.Fatal) and a quality line. *records = malloc'ed table of name and sequence spans
+ * (names TrimSpace'd, positions relative to `image`), in file order.
+ * Pieces: with final_piece = 0 only the records in front of the piece's last name line are returned and *consumed is
+ * where that line starts — hand the bytes from there on over again at the head of the next piece; *is_fastq (may be
+ * NULL) carries the '@' state from piece to piece (start with 0). final_piece = 1: the image ends the file.
+ */
+typedef struct dp_record {
+    int64_t name_start, name_len; /* the read's name (the reference's f.names entry) */
+    int64_t seq_start, seq_len;   /* the read's bases */
+} dp_record;
+int dp_split_records(const uint8_t* image, int64_t bytes, int64_t min_length, int final_piece, int* is_fastq, int device,
+                     dp_record** records, int64_t* n_records, int64_t* consumed);
+
+/*
+ * Mapper.Map over reads that are mapped where they lie in a file image (records of dp_split_records, ascending and
+ * non-overlapping): no per-read copy on the host. `image` may be pageable or page-locked host memory or device memory.
+ * Results as dp_mapper_map_batch on the same reads.
+ */
+int dp_mapper_map_batch_spans(dp_mapper* m, int64_t n_reads, const uint8_t* image, const dp_record* records,
+                              dp_mapping** out, int64_t** out_offsets);
+
+/*
+ * Mapper.AsString (mapping/mapping.go:112-122) for every mapping of a batch, formatted on the device: *text = malloc'ed
+ * block of PAF lines, each ended by '\n' (what commands/map.go:92 prints), in the order of `maps`; names are read from
+ * `image` through `records`, the query length is the record's seq_len.
+ */
+int dp_mapper_paf_block(const dp_mapper* m, int64_t n_reads, const uint8_t* image, const dp_record* records,
+                        const dp_mapping* maps, const int64_t* out_offsets, const char* ref_name, char** text,
+                        int64_t* text_bytes);
+
+/* Device memory for file images (a host uploads a piece once and hands the device pointer to the three calls above). */
+int dp_device_alloc(void** out, size_t bytes, int device);
+void dp_device_free(void* p, int device);
+int dp_device_copy(void* dst, const void* src, size_t bytes, int device); /* any direction */
+
 int dp_mapper_get_stats(const dp_mapper* m, dp_stats* out);
 
 /* Index facts: out5 = {num_seeds, num_chunks, chunk_postings (seed occurrences over chunks),

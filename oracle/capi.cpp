@@ -442,4 +442,29 @@ int dpo_map_batch(void* p, long long n_reads, const char* bases, const long long
 }
 void dpo_free(void* p) { free(p); }
 
+
+// ----- readFasta's first pass (seqio.cpp) -----------------------------------
+// Returns a malloc'ed blob: for every record int64 name length, name bytes, int64 sequence length, sequence bytes;
+// *n_records = records, *blob_bytes = size. nullptr on the reference's log.Fatal (invalid fastq).
+unsigned char* dpo_parse_fasta(const char* content, long long n, long long minLength, long long* n_records, long long* blob_bytes) {
+    DPO_TRY
+    std::vector<FastaRecord> recs = ParseFasta(std::string(content, (size_t)n), minLength);
+    size_t total = 0;
+    for (auto& r : recs) total += 16 + r.name.size() + r.seq.size();
+    unsigned char* blob = (unsigned char*)malloc(total ? total : 1);
+    size_t o = 0;
+    for (auto& r : recs) {
+        long long a = (long long)r.name.size(), b = (long long)r.seq.size();
+        memcpy(blob + o, &a, 8);
+        memcpy(blob + o + 8, r.name.data(), r.name.size());
+        o += 8 + r.name.size();
+        memcpy(blob + o, &b, 8);
+        memcpy(blob + o + 8, r.seq.data(), r.seq.size());
+        o += 8 + r.seq.size();
+    }
+    *n_records = (long long)recs.size();
+    *blob_bytes = (long long)total;
+    return blob;
+    DPO_CATCH(nullptr)
+}
 }  // extern "C"

@@ -89,6 +89,7 @@ def lib():
         "dpo_window_mappings": (c_ll, [c_vp, c_vp, c_ll, c_ll, c_ll, ctypes.c_int, c_vp, c_ll]),
         "dpo_map_batch": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
         "dpo_free": (None, [c_vp]),
+        "dpo_parse_fasta": (c_vp, [c_vp, c_ll, c_ll, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -504,6 +505,27 @@ class Mapper:
         rows = np.ctypeslib.as_array(rows_p, shape=(max(total, 1) * 6,))[: total * 6].reshape(total, 6).copy()
         lib().dpo_free(rows_p)
         return rows, out_off, dict(zip(COUNTER_NAMES, (int(x) for x in ctr)))
+
+
+def parse_fasta(content, min_length=0):
+    """readFasta's first pass (sequence/seqio.go:188-267) -> [(name bytes, sequence bytes)]; raises on the reference's
+    log.Fatal (invalid fastq)."""
+    content = bytes(content)
+    n, nb = c_ll(), c_ll()
+    p = lib().dpo_parse_fasta(content, len(content), min_length, ctypes.byref(n), ctypes.byref(nb))
+    if not p:
+        raise RuntimeError(_err())
+    blob = ctypes.string_at(p, nb.value)
+    lib().dpo_free(p)
+    out, o = [], 0
+    for _ in range(n.value):
+        a = int.from_bytes(blob[o:o + 8], "little")
+        name = blob[o + 8:o + 8 + a]
+        o += 8 + a
+        b = int.from_bytes(blob[o:o + 8], "little")
+        out.append((name, blob[o + 8:o + 8 + b]))
+        o += 8 + b
+    return out
 
 
 def paf_lines(rows, out_off, names, lengths, ref_name, ref_len, circular):

@@ -110,6 +110,24 @@ def test_cli_output_identical_to_oracle(tmp_path, fastq, circular):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fastq,circular", [(False, True), (True, False)])
+def test_cli_device_io_identical_to_oracle(tmp_path, fastq, circular):
+    """DOWNPORE_DEVICE_IO=1: the file goes to the GPU as it is; records are split, reads mapped where they lie and PAF
+    lines formatted on the device (dp_split_records, dp_mapper_map_batch_spans, dp_mapper_paf_block). Small pieces: the
+    piece cutting, the carried fastq state and the piece-order output are exercised."""
+    po.build()
+    ref_path, reads_path = write_inputs(str(tmp_path), fastq, circular)
+    args = ["-input", reads_path, "-r", ref_path, "-ci", "true" if circular else "false"]
+    want = run([ORACLE_MAP] + args)
+    assert want.returncode == 0, want.stderr
+    for piece in (1 << 30, 40000, 9000):
+        got = run([host()] + args, env={"DOWNPORE_DEVICE_IO": "1", "DOWNPORE_PIECE_BYTES": str(piece)})
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want.stdout, piece
+        assert counters(got.stderr) == counters(want.stderr)
+
+
+@pytest.mark.gpu
 def test_cli_on_two_gpus_in_one_process(tmp_path):
     """DOWNPORE_GPUS=0,1: one mapping thread per GPU inside one process, the index built on the first GPU and opened on the
     second from its image (dp_mapper_index_export -> dp_mapper_create_from_index, the peer-copy route INTEGRATION.md

@@ -340,8 +340,145 @@ int main(int argc, char** argv) {
     }
     double t2 = now_s();
 
-    // ---- reads: a reader thread fills pinned batches; one mapping thread per GPU drains them; output in input order ----
     MappedFile in(args["input"]);
+    if (getenv("DOWNPORE_DEVICE_IO") && atoi(getenv("DOWNPORE_DEVICE_IO")) != 0) {
+        // ---- the host-free route: the file goes to the GPUs piece by piece as it is; records are split
+        // (dp_split_records), reads mapped where they lie (dp_mapper_map_batch_spans) and PAF lines formatted
+        // (dp_mapper_paf_block) on the device; the host only cuts pieces, counts and writes the text in piece order ----
+        const size_t pieceBytes = getenv("DOWNPORE_PIECE_BYTES") ? (size_t)atoll(getenv("DOWNPORE_PIECE_BYTES")) : ((size_t)1 << 30);
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t filePos = 0;
+        int fq = 0;
+        bool fileDone = in.n == 0;
+        long long nextSeq = 0, nextToPrint = 0;
+        struct Piece {
+            char* text = nullptr;
+            int64_t textBytes = 0;
+            long long cnt[5] = {0, 0, 0, 0, 0};
+        };
+        std::map<long long, Piece> done;
+        std::string err;
+        double mapSeconds = 0;
+        auto worker = [&](size_t d) {
+            void* dImage = nullptr;
+            size_t dCap = 0;
+            for (;;) {
+                dp_record* recs = nullptr;
+                int64_t nRecs = 0;
+                long long seq;
+                {   // cutting is sequential: where a piece ends is only known once it has been split
+                    std::unique_lock<std::mutex> lk(mu);
+                    if (fileDone || !err.empty()) break;
+                    size_t want = pieceBytes;
+                    for (;;) {
+                        const size_t len = std::min(want, in.n - filePos);
+                        const bool final = filePos + len == in.n;
+                        if (len > dCap) {
+                            dp_device_free(dImage, devices[d]);
+                            dImage = nullptr;
+                            if (dp_device_alloc(&dImage, len + len / 8, devices[d])) { err = dp_last_error(); break; }
+                            dCap = len + len / 8;
+                        }
+                        int64_t consumed = 0;
+                        int fqNext = fq;
+                        if (dp_device_copy(dImage, in.p + filePos, len, devices[d])) { err = dp_last_error(); break; }
+                        if (dp_split_records((const uint8_t*)dImage, (int64_t)len, minLength, final ? 1 : 0, &fqNext, devices[d], &recs,
+                                             &nRecs, &consumed)) {
+                            if (!final && strstr(dp_last_error(), "larger piece")) {  // one record longer than the piece
+                                want *= 2;
+                                continue;
+                            }
+                            err = dp_last_error();
+                            break;
+                        }
+                        fq = fqNext;
+                        filePos += final ? len : (size_t)consumed;
+                        if (final) fileDone = true;
+                        break;
+                    }
+                    if (!err.empty()) {
+                        cv.notify_all();
+                        break;
+                    }
+                    seq = nextSeq++;
+                }
+                Piece pc;
+                dp_mapping* maps = nullptr;
+                int64_t* offs = nullptr;
+                const double ta = now_s();
+                bool ok = dp_mapper_map_batch_spans(mappers[d], nRecs, (const uint8_t*)dImage, recs, &maps, &offs) == 0;
+                const double tb = now_s();
+                ok = ok && dp_mapper_paf_block(mappers[d], nRecs, (const uint8_t*)dImage, recs, maps, offs, refName.c_str(), &pc.text,
+                                               &pc.textBytes) == 0;
+                if (ok)
+                    for (int64_t i = 0; i < nRecs; i++) {
+                        const int64_t c = offs[i + 1] - offs[i];
+                        pc.cnt[4] += recs[i].seq_len;
+                        if (c == 1) pc.cnt[0]++;
+                        else if (c > 1) pc.cnt[1]++;
+                        else pc.cnt[3]++;
+                        pc.cnt[2] += c;
+                    }
+                if (wantStats && ok) {
+                    dp_stats st;
+                    dp_mapper_get_stats(mappers[d], &st);
+                    fprintf(stderr, "[dp_map] gpu %d piece %lld: %lld reads, map %.1f ms, PAF text %.1f ms (%lld bytes)\n", devices[d], seq,
+                            (long long)nRecs, (tb - ta) * 1e3, (now_s() - tb) * 1e3, (long long)pc.textBytes);
+                }
+                dp_free(maps);
+                dp_free(offs);
+                dp_free(recs);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!ok) err = dp_last_error();
+                    mapSeconds += tb - ta;
+                    done[seq] = pc;
+                }
+                cv.notify_all();
+                if (!ok) break;
+            }
+            dp_device_free(dImage, devices[d]);
+            cv.notify_all();
+        };
+        std::vector<std::thread> workers;
+        size_t running = devices.size();
+        for (size_t d = 0; d < devices.size(); d++)
+            workers.emplace_back([&, d] {
+                worker(d);
+                std::lock_guard<std::mutex> lk(mu);
+                running--;
+                cv.notify_all();
+            });
+        long long cnt[5] = {0, 0, 0, 0, 0};
+        for (;;) {
+            Piece pc;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return done.count(nextToPrint) || running == 0; });
+                if (!done.count(nextToPrint)) break;
+                pc = done[nextToPrint];
+                done.erase(nextToPrint);
+                nextToPrint++;
+            }
+            if (pc.text) fwrite(pc.text, 1, (size_t)pc.textBytes, stdout);
+            dp_free(pc.text);
+            for (int i = 0; i < 5; i++) cnt[i] += pc.cnt[i];
+        }
+        for (auto& w : workers) w.join();
+        if (!err.empty()) fatal((err.find("Invalid fastq") != std::string::npos ? "" : "dp_map (device io): ") + err);
+        fflush(stdout);
+        const double t3 = now_s();
+        fprintf(stderr, "Uniquely mapped: %lld\nMultiple mappings: %lld\ntotal: %lld\nUnmapped: %lld\n", cnt[0], cnt[1], cnt[2], cnt[3]);
+        if (wantStats)
+            fprintf(stderr, "[dp_map] %s; device io; gpus=%zu count+values=%.3fs index=%.3fs read+map+print=%.3fs (map calls %.3fs) "
+                            "bases=%lld Gbp/s(end to end)=%.3f\n",
+                    dp_version(), devices.size(), t1 - t0, t2 - t1, t3 - t2, mapSeconds, cnt[4], cnt[4] / (t3 - t2) / 1e9);
+        for (dp_mapper* m : mappers) dp_mapper_destroy(m);
+        return 0;
+    }
+
+    // ---- reads: a reader thread fills pinned batches; one mapping thread per GPU drains them; output in input order ----
     const size_t nSlots = devices.size() + 2;
     std::vector<Batch> slots(nSlots);
     for (auto& b : slots) {
