@@ -18,6 +18,7 @@
 
 #include "../../include/downpore_b200.h"
 #include "dp_common.cuh"
+#include "dp_host.hpp"
 #include "dp_finish.cuh"
 #include "dp_host_map.hpp"
 #include "dp_index.cuh"
@@ -28,66 +29,6 @@ namespace {
 
 thread_local std::string g_err;
 
-#define CK(call)                                                                                              \
-    do {                                                                                                      \
-        cudaError_t e_ = (call);                                                                              \
-        if (e_ != cudaSuccess)                                                                                \
-            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + \
-                                     std::to_string(__LINE__));                                               \
-    } while (0)
-
-template <class T>
-struct DBuf {  // device buffer, grow-only
-    T* p = nullptr;
-    size_t cap = 0;
-    ~DBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    void reserve(size_t n) {
-        if (n <= cap) return;
-        release();
-        size_t want = n + n / 8 + 64;
-        CK(cudaMalloc((void**)&p, want * sizeof(T)));
-        cap = want;
-    }
-    size_t bytes() const { return cap * sizeof(T); }
-};
-
-template <class T>
-struct HBuf {  // page-locked host buffer mapped into the device address space (d = device view), grow-only
-    T* p = nullptr;
-    T* d = nullptr;
-    size_t cap = 0;
-    ~HBuf() {
-        if (p) cudaFreeHost(p);
-    }
-    void reserve(size_t n) {
-        if (n <= cap) return;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        size_t want = n + n / 8 + 64;
-        CK(cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocMapped));
-        CK(cudaHostGetDevicePointer((void**)&d, p, 0));
-        cap = want;
-    }
-};
-
-struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    void init() {
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
-    }
-    ~Timer() {
-        if (a) cudaEventDestroy(a);
-        if (b) cudaEventDestroy(b);
-    }
-};
-
-inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -228,6 +169,8 @@ namespace {
 // index construction (mapping.NewMapper, mapping/mapping.go:67-109)
 // ----------------------------------------------------------------------------------------------------------------
 void build_mid_postings(dp_mapper& M);
+void build_postings(dp_mapper& M, DBuf<unsigned long long>& keys, unsigned long long P2, unsigned numSeeds, unsigned C,
+                    unsigned maxChunkSeeds);
 
 void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     const int k = M.k;
@@ -423,13 +366,28 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     if (P2 >= 0xffffffffull) throw std::runtime_error("index too large for 32-bit posting offsets");
     M.chunkPos.reserve((size_t)P2 + 1);
     M.chunkSeed.reserve((size_t)P2 + 1);
-    DBuf<unsigned long long> keys, keysSorted;
+    DBuf<unsigned long long> keys;
     keys.reserve((size_t)P2 + 1);
-    keysSorted.reserve((size_t)P2 + 1);
     dp_chunk_scan_kernel<<<scanBlocks, 256, 0, st>>>(M.refWords.p, M.table.p, dDescs.p, C, k, 1, nullptr, M.chunkOff.p,
                                                      M.chunkPos.p, M.chunkSeed.p, keys.p);
     CK(cudaGetLastError());
 
+    build_postings(M, keys, P2, numSeeds, C, maxChunkSeeds);
+    M.refWords.release();  // only index construction reads the packed reference
+}
+
+// Second half of index construction, shared by `map` (chunks of the reference) and `overlap` (seed-space chunks of the
+// reads): from the chunk -> seeds lists (M.chunkOff / chunkPos / chunkSeed) and their (seed, chunk) keys to the two
+// seed -> ... CSRs, the extract kernel's prefix filter, the mid-lookup copy, and M.I.
+void build_postings(dp_mapper& M, DBuf<unsigned long long>& keys, unsigned long long P2, unsigned numSeeds, unsigned C,
+                    unsigned maxChunkSeeds) {
+    const int k = M.k;
+    const int e = M.edge;
+    const long long L = M.refLen;
+    cudaStream_t st = M.stream;
+    const long long nTable = (1ll << (2 * k)) / 32;
+    DBuf<unsigned long long> keysSorted;
+    keysSorted.reserve((size_t)P2 + 1);
     // ---- seed -> distinct chunks: radix sort of (seed, chunk) keys, unique, CSR ----
     M.seedOff.reserve((size_t)numSeeds + 2);
     unsigned long long P1 = 0;
@@ -536,7 +494,6 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
     I.chunkScanLen = M.chunkScanLen.p;
     M.nChunkPostings = (long long)P2;
     M.nSeedPostings = (long long)P1;
-    M.refWords.release();  // only index construction reads the packed reference
     M.indexBytes = M.table.bytes() + M.seedOff.bytes() + M.seedChunks.bytes() +
                    M.chunkOff.bytes() + M.chunkPos.bytes() + M.chunkSeed.bytes() + M.chunkOffset.bytes() +
                    M.postOff.bytes() + M.postChunk.bytes() + M.postPos.bytes() + M.filter.bytes() +
@@ -1928,6 +1885,8 @@ void check_image_header(const DpImageHeader& H, int64_t bytes) {
         return 1;                      \
     }                                  \
     return 0;
+
+void dp_set_last_error(const char* msg) { g_err = msg ? msg : ""; }
 
 extern "C" {
 

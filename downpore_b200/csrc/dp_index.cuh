@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256) dp_chunk_scan_kernel(const unsigned* __re
                 unsigned idx = off + n + __popc(m & lt);
                 chunkPos[idx] = j;
                 chunkSeed[idx] = rank;
-                keys[idx] = ((unsigned long long)rank << 32) | c;
+                if (keys) keys[idx] = ((unsigned long long)rank << 32) | c;
             }
             n += __popc(m);
         }

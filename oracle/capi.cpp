@@ -266,6 +266,28 @@ int dpo_kmer_counts(const char* ref_ascii, long long n, int k, unsigned long lon
     DPO_CATCH(1)
 }
 
+// accumulating batch form (getKmerValues of the overlap command counts every read): counts_io += occurrences
+int dpo_kmer_counts_batch(const char* bases, const long long* offsets, long long nReads, int k, unsigned long long* counts_io) {
+    DPO_TRY
+    std::vector<uint64_t> counts(counts_io, counts_io + ((size_t)1 << (2 * k)));
+    for (long long i = 0; i < nReads; i++) {
+        if (offsets[i + 1] - offsets[i] < k) continue;
+        PackedSeq r = NewPackedSequence(i, std::string(bases + offsets[i], (size_t)(offsets[i + 1] - offsets[i])), nullptr);
+        KmerOccurrences(r, k, counts);
+    }
+    memcpy(counts_io, counts.data(), counts.size() * sizeof(uint64_t));
+    return 0;
+    DPO_CATCH(1)
+}
+int dpo_kmer_values_from_counts(unsigned long long* counts, int k, double* values_out) {
+    DPO_TRY
+    std::vector<uint64_t> c(counts, counts + ((size_t)1 << (2 * k)));
+    std::vector<double> v = KmerValues(c, k);
+    memcpy(values_out, v.data(), v.size() * sizeof(double));
+    return 0;
+    DPO_CATCH(1)
+}
+
 // ----- mapper -----------------------------------------------------------------
 struct OMapper {
     Mapper m;
@@ -466,5 +488,70 @@ unsigned char* dpo_parse_fasta(const char* content, long long n, long long minLe
     *blob_bytes = (long long)total;
     return blob;
     DPO_CATCH(nullptr)
+}
+
+// ----- one round of `downpore overlap` (overlap.cpp) -------------------------
+// params7 = {overlapSize, k, numSeeds, seedBatchSize, chunkSize, queryBatchSize}; returns a handle or nullptr.
+void* dpo_overlap_round(const char* bases, const long long* offsets, long long nReads, const unsigned char* ignore,
+                        long long firstSequence, const double* values, const long long* params6, double hitFraction) {
+    DPO_TRY
+    std::vector<PackedSeq> reads;
+    reads.reserve((size_t)nReads);
+    for (long long i = 0; i < nReads; i++)
+        reads.push_back(NewPackedSequence(i, std::string(bases + offsets[i], (size_t)(offsets[i + 1] - offsets[i])), nullptr));
+    std::vector<uint8_t> ign((size_t)nReads, 0);
+    if (ignore) ign.assign(ignore, ignore + nReads);
+    OverlapParams P;
+    P.overlapSize = params6[0];
+    P.k = params6[1];
+    P.numSeeds = params6[2];
+    P.seedBatchSize = params6[3];
+    P.chunkSize = params6[4];
+    P.queryBatchSize = params6[5];
+    P.hitFraction = hitFraction;
+    OverlapRound* R = new OverlapRound();
+    try {
+        OverlapRoundRun(reads, ign, firstSequence, values, P, *R);
+    } catch (...) {
+        delete R;
+        throw;
+    }
+    return R;
+    DPO_CATCH(nullptr)
+}
+void dpo_overlap_free(void* h) { delete (OverlapRound*)h; }
+// what: 0 header {numSeeds, numQueries, numChunks, numHits, numQuerySeqs, nextFirstSequence}
+//       1 seed k-mers in seed id order
+//       2 queries:  per query {ID, SequenceID, rc, length, offset, inset, nSegments, segments...}
+//       3 chunks:   per chunk {id, length, offset, inset, nSegments, segments...}
+//       4 hits:     per hit {queryID, rc, target, n, MatchA..., MatchB...}
+// Returns the number of int64 the section holds; fills out when cap suffices.
+long long dpo_overlap_get(void* h, int what, long long* out, long long cap) {
+    OverlapRound& R = *(OverlapRound*)h;
+    std::vector<long long> v;
+    if (what == 0) {
+        v = {R.index.size, (long long)R.queries.size(), (long long)R.index.sequences.size(), (long long)R.hits.size(), R.numQuerySeqs,
+             R.nextFirstSequence};
+    } else if (what == 1) {
+        for (gint i = 0; i < R.index.size; i++) v.push_back(R.index.seedMap[(size_t)i]);
+    } else if (what == 2) {
+        for (auto& q : R.queries) {
+            v.insert(v.end(), {q.ID, q.SequenceID, q.rc ? 1 : 0, q.Query.length, q.Query.offset, q.Query.inset, (long long)q.Query.segments.size()});
+            v.insert(v.end(), q.Query.segments.begin(), q.Query.segments.end());
+        }
+    } else if (what == 3) {
+        for (auto& c : R.index.sequences) {
+            v.insert(v.end(), {c.id, c.length, c.offset, c.inset, (long long)c.segments.size()});
+            v.insert(v.end(), c.segments.begin(), c.segments.end());
+        }
+    } else if (what == 4) {
+        for (auto& x : R.hits) {
+            v.insert(v.end(), {x.queryID, x.rc ? 1 : 0, x.target, (long long)x.MatchA.size()});
+            v.insert(v.end(), x.MatchA.begin(), x.MatchA.end());
+            v.insert(v.end(), x.MatchB.begin(), x.MatchB.end());
+        }
+    }
+    if ((long long)v.size() <= cap && out) memcpy(out, v.data(), v.size() * sizeof(long long));
+    return (long long)v.size();
 }
 }  // extern "C"

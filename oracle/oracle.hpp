@@ -213,6 +213,34 @@ void IndexSequences(SeedIndex& g);                                              
 std::vector<uint64_t> Matches(const SeedIndex& g, const SeedSequence& query, double hitFraction, Counters* c);  // :335-353
 
 // ----------------------------------------------------------------------------
+// overlap/overlap.go + commands/overlap.go:115-160 — one round of `downpore overlap` up to the seed-match stream
+// (overlap.cpp; canonical order = num_workers 1)
+// ----------------------------------------------------------------------------
+struct OverlapParams {
+    gint overlapSize = 1000, k = 10, numSeeds = 15, seedBatchSize = 10000, chunkSize = 10000, queryBatchSize = 20000;
+    double hitFraction = 0.25;
+};
+struct OverlapQuery {  // overlap.go:10-16
+    gint ID = 0, SequenceID = 0;
+    SeedSequence Query;
+    bool rc = false;
+};
+struct OverlapHit {  // the *seeds.SeedMatch matchWorker sends: SeqA = the query, SeqB = index.sequences[target]
+    gint queryID = 0;
+    bool rc = false;
+    gint target = 0;
+    std::vector<gint> MatchA, MatchB;
+};
+struct OverlapRound {
+    SeedIndex index;
+    std::vector<OverlapQuery> queries;
+    std::vector<OverlapHit> hits;
+    gint numQuerySeqs = 0, nextFirstSequence = 0;
+};
+void OverlapRoundRun(const std::vector<PackedSeq>& reads, const std::vector<uint8_t>& ignore, gint firstSequence,
+                     const double* values, const OverlapParams& P, OverlapRound& out);
+
+// ----------------------------------------------------------------------------
 // util/sequtil/kmers.go + commands/map.go:45-71
 // ----------------------------------------------------------------------------
 void KmerOccurrences(const PackedSeq& seq, gint k, std::vector<uint64_t>& counts);  // kmers.go:53-69 (accumulates)

@@ -89,6 +89,11 @@ def lib():
         "dpo_window_mappings": (c_ll, [c_vp, c_vp, c_ll, c_ll, c_ll, ctypes.c_int, c_vp, c_ll]),
         "dpo_map_batch": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
         "dpo_free": (None, [c_vp]),
+        "dpo_kmer_counts_batch": (ctypes.c_int, [c_vp, c_vp, c_ll, ctypes.c_int, c_vp]),
+        "dpo_kmer_values_from_counts": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
+        "dpo_overlap_round": (c_vp, [c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, ctypes.c_double]),
+        "dpo_overlap_free": (None, [c_vp]),
+        "dpo_overlap_get": (c_ll, [c_vp, ctypes.c_int, c_vp, c_ll]),
         "dpo_parse_fasta": (c_vp, [c_vp, c_ll, c_ll, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
     }
     for name, (res, args) in sig.items():
@@ -505,6 +510,78 @@ class Mapper:
         rows = np.ctypeslib.as_array(rows_p, shape=(max(total, 1) * 6,))[: total * 6].reshape(total, 6).copy()
         lib().dpo_free(rows_p)
         return rows, out_off, dict(zip(COUNTER_NAMES, (int(x) for x in ctr)))
+
+
+OVERLAP_DEFAULTS = dict(overlap_size=1000, k=10, num_seeds=15, seed_batch_size=10000, chunk_size=10000,
+                        query_batch_size=20000, min_hits=0.25)
+
+
+def overlap_values(bases, offsets, k):
+    """getKmerValues (commands/overlap.go:41-95) without a seed_values file: the formula and the TopOccurrences cut of
+    `map` (kmer_values), counted over ALL reads."""
+    bases = _u8(bases)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    counts = np.zeros(4 ** k, dtype=np.uint64)
+    if lib().dpo_kmer_counts_batch(bases.ctypes.data_as(c_vp), offsets.ctypes.data_as(c_vp), offsets.size - 1, k,
+                                   counts.ctypes.data_as(c_vp)) != 0:
+        raise RuntimeError(_err())
+    return kmer_values_from_counts(counts, k)
+
+
+def kmer_values_from_counts(counts, k):
+    counts = np.ascontiguousarray(counts, dtype=np.uint64).copy()
+    out = np.zeros(4 ** k, dtype=np.float64)
+    if lib().dpo_kmer_values_from_counts(counts.ctypes.data_as(c_vp), k, out.ctypes.data_as(c_vp)) != 0:
+        raise RuntimeError(_err())
+    return out
+
+
+class OverlapRound:
+    """One round of `downpore overlap` up to the seed-match stream (oracle/overlap.cpp)."""
+
+    def __init__(self, bases, offsets, values, first_sequence=0, ignore=None, **params):
+        p = dict(OVERLAP_DEFAULTS)
+        p.update(params)
+        self.params = p
+        bases = _u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert values.size == 4 ** p["k"]
+        ign = None if ignore is None else np.ascontiguousarray(ignore, dtype=np.uint8)
+        p6 = np.array([p["overlap_size"], p["k"], p["num_seeds"], p["seed_batch_size"], p["chunk_size"], p["query_batch_size"]],
+                      dtype=np.int64)
+        self.h = lib().dpo_overlap_round(bases.ctypes.data_as(c_vp), offsets.ctypes.data_as(c_vp), n,
+                                         None if ign is None else ign.ctypes.data_as(c_vp), first_sequence,
+                                         values.ctypes.data_as(c_vp), p6.ctypes.data_as(c_vp), float(p["min_hits"]))
+        if not self.h:
+            raise RuntimeError(_err())
+        hd = self._get(0)
+        self.num_seeds, self.num_queries, self.num_chunks, self.num_hits, self.num_query_seqs, self.next_first_sequence = (int(x) for x in hd)
+        self.seed_kmers = self._get(1)
+        v, at, self.queries = self._get(2), 0, []
+        for _ in range(self.num_queries):
+            qid, sid, rc, ln, off, ins, ns = (int(x) for x in v[at:at + 7])
+            self.queries.append(dict(id=qid, sequence_id=sid, rc=bool(rc), length=ln, offset=off, inset=ins, segments=v[at + 7:at + 7 + ns].copy()))
+            at += 7 + ns
+        v, at, self.chunks = self._get(3), 0, []
+        for _ in range(self.num_chunks):
+            rid, ln, off, ins, ns = (int(x) for x in v[at:at + 5])
+            self.chunks.append(dict(read=rid, length=ln, offset=off, inset=ins, segments=v[at + 5:at + 5 + ns].copy()))
+            at += 5 + ns
+        v, at, self.hits = self._get(4), 0, []
+        for _ in range(self.num_hits):
+            qid, rc, tgt, m = (int(x) for x in v[at:at + 4])
+            self.hits.append(dict(query_id=qid, rc=bool(rc), target=tgt, match_a=v[at + 4:at + 4 + m].copy(), match_b=v[at + 4 + m:at + 4 + 2 * m].copy()))
+            at += 4 + 2 * m
+        lib().dpo_overlap_free(c_vp(self.h))
+        self.h = None
+
+    def _get(self, what):
+        n = lib().dpo_overlap_get(c_vp(self.h), what, None, 0)
+        out = np.zeros(max(int(n), 1), dtype=np.int64)
+        lib().dpo_overlap_get(c_vp(self.h), what, out.ctypes.data_as(c_vp), int(n))
+        return out[:int(n)]
 
 
 def parse_fasta(content, min_length=0):

@@ -106,7 +106,7 @@ def test_split_records_in_pieces(fastq):
 
 @pytest.fixture(scope="module")
 def mapper_pair():
-    ref = synth.genome(400_000, 3)
+    ref = synth.reference(3, 400_000)
     vals = po.kmer_values(ref, K)
     om = po.Mapper(ref, vals, circular=True, k=K)
     gm = dp.Mapper(ref, vals, circular=True, k=K)
