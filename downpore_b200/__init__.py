@@ -43,6 +43,20 @@ class Stats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class OverlapRoundStruct(ctypes.Structure):
+    _fields_ = [("num_seeds", c_i64), ("num_queries", c_i64), ("num_query_seqs", c_i64), ("next_first_sequence", c_i64),
+                ("num_chunks", c_i64), ("num_hits", c_i64), ("num_matches", c_i64), ("hits", c_vp), ("matches", c_vp),
+                ("read_seeds", c_i64), ("chunk_seeds", c_i64), ("seed_postings", c_i64), ("candidates", c_i64),
+                ("pairs", c_i64), ("kernel_launches", c_i64), ("ms_total", ctypes.c_double),
+                ("ms_select", ctypes.c_double), ("ms_queries", ctypes.c_double), ("ms_scan", ctypes.c_double),
+                ("ms_chunk", ctypes.c_double), ("ms_index", ctypes.c_double), ("ms_lookup", ctypes.c_double),
+                ("ms_align", ctypes.c_double), ("ms_collect", ctypes.c_double)]
+
+
+OVERLAP_HIT_DTYPE = np.dtype([("query_id", "<i4"), ("rc", "<i4"), ("target", "<i4"), ("n", "<i4"), ("at", "<i8")])
+assert OVERLAP_HIT_DTYPE.itemsize == 24
+
+
 def build(force=False):
     """Compile csrc/ for sm_100a into libdownpore_b200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp"))]
@@ -92,6 +106,15 @@ _SIGNATURES = {
     "dp_device_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t, ctypes.c_int]),
     "dp_device_free": (None, [c_vp, ctypes.c_int]),
     "dp_device_copy": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int]),
+    "dp_overlapper_create": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "dp_overlapper_kmer_counts": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_overlapper_set_values": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_overlapper_round": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "dp_overlapper_queries": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "dp_overlapper_chunks": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "dp_overlapper_seed_kmers": (ctypes.c_int, [c_vp, c_vp]),
+    "dp_overlapper_destroy": (None, [c_vp]),
 }
 
 
@@ -136,6 +159,16 @@ def _adopt(ptr, nbytes, dtype):
     buf = (ctypes.c_char * nbytes).from_address(ptr.value)
     weakref.finalize(buf, lib().dp_free, ptr.value)
     return np.frombuffer(buf, dtype=dtype)
+
+
+def _adopt_or_empty(addr, nbytes, dtype):
+    """malloc'ed output of the library (address as an int or None) -> numpy array that frees it."""
+    if not addr:
+        return np.zeros(0, dtype=dtype)
+    if nbytes <= 0:
+        lib().dp_free(addr)
+        return np.zeros(0, dtype=dtype)
+    return _adopt(c_vp(addr), nbytes, dtype)
 
 
 def pack(ascii_seq, device=0):
@@ -506,3 +539,116 @@ def replicate_index(mapper, src=0, device=0, group=None, ref_name="ref"):
     if rank == src:
         return mapper
     return Mapper.from_index(image.data_ptr(), n, device=device, ref_name=ref_name)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# `downpore overlap`: one round up to the seed-match stream (overlap.Overlapper, overlap/overlap.go:24-29)
+# ---------------------------------------------------------------------------------------------------------------------
+OVERLAP_DEFAULTS = dict(overlap_size=1000, k=10, num_seeds=15, seed_batch_size=10000, chunk_size=10000,
+                        query_batch_size=20000, min_hits=0.25)  # commands/overlap.go:26-27
+
+
+class OverlapRound:
+    """Result of Overlapper.round(): counters, timings, and the hits (a structured array + the MatchA/MatchB pool)."""
+
+    def __init__(self, st, hits, matches):
+        for name, _ in OverlapRoundStruct._fields_:
+            if name not in ("hits", "matches"):
+                setattr(self, name, getattr(st, name))
+        self.hits = hits
+        self.matches = matches
+
+    def hit(self, i):
+        """(query_id, rc, target, MatchA, MatchB) of hit i."""
+        h = self.hits[i]
+        at, n = int(h["at"]), int(h["n"])
+        return int(h["query_id"]), bool(h["rc"]), int(h["target"]), self.matches[at:at + n], self.matches[at + n:at + 2 * n]
+
+
+class Overlapper:
+    """The sequence set of `downpore overlap` (himem) on one GPU plus overlap.Overlapper's three steps as one round:
+    PrepareQueries, AddSequences, FindOverlaps (commands/overlap.go:115-160)."""
+
+    def __init__(self, bases, offsets, kmer_values=None, device=0, **params):
+        p = dict(OVERLAP_DEFAULTS)
+        p.update(params)
+        self.params = p
+        self.k = p["k"]
+        bases = _u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n_reads = offsets.size - 1
+        self.device = device
+        vals = None
+        if kmer_values is not None:
+            vals = np.ascontiguousarray(kmer_values, dtype=np.float64)
+            if vals.size != 4 ** self.k:
+                raise ValueError("kmer_values must have 4^k entries")
+        h = c_vp()
+        _check(lib().dp_overlapper_create(bases.ctypes.data_as(c_vp), offsets.ctypes.data_as(c_vp), self.n_reads, self.k,
+                                          None if vals is None else vals.ctypes.data_as(c_vp), p["overlap_size"],
+                                          p["num_seeds"], p["seed_batch_size"], p["chunk_size"], p["query_batch_size"],
+                                          float(p["min_hits"]), device, ctypes.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, lib().dp_overlapper_destroy, h)
+
+    def close(self):
+        if self._h is not None:
+            self._fin()
+            self._h = None
+
+    def kmer_counts(self):
+        """sequtil.KmerOccurrences over every read (commands/overlap.go:43)."""
+        counts = np.zeros(4 ** self.k, dtype=np.uint64)
+        _check(lib().dp_overlapper_kmer_counts(self._h, counts.ctypes.data_as(c_vp)))
+        return counts
+
+    def set_values(self, kmer_values):
+        vals = np.ascontiguousarray(kmer_values, dtype=np.float64)
+        if vals.size != 4 ** self.k:
+            raise ValueError("kmer_values must have 4^k entries")
+        _check(lib().dp_overlapper_set_values(self._h, vals.ctypes.data_as(c_vp)))
+
+    def round(self, first_sequence=0, ignore=None):
+        st = OverlapRoundStruct()
+        ign = None
+        if ignore is not None:
+            ign = np.ascontiguousarray(ignore, dtype=np.uint8)
+            if ign.size != self.n_reads:
+                raise ValueError("ignore must have one flag per read")
+        _check(lib().dp_overlapper_round(self._h, None if ign is None else ign.ctypes.data_as(c_vp), int(first_sequence),
+                                         ctypes.byref(st)))
+        hits = _adopt_or_empty(st.hits, st.num_hits * OVERLAP_HIT_DTYPE.itemsize, OVERLAP_HIT_DTYPE)
+        matches = _adopt_or_empty(st.matches, st.num_matches * 2, np.uint16)
+        self._last = st
+        return OverlapRound(st, hits, matches)
+
+    def seed_kmers(self):
+        out = np.zeros(max(int(self._last.num_seeds), 1), dtype=np.int64)
+        _check(lib().dp_overlapper_seed_kmers(self._h, out.ctypes.data_as(c_vp)))
+        return out[:int(self._last.num_seeds)]
+
+    def _segments(self, fn, n, width, *head):
+        meta = np.zeros((max(n, 1), width), dtype=np.int64)
+        seg_off = np.zeros(n + 1, dtype=np.int64)
+        segs = c_vp()
+        _check(fn(self._h, *head, meta.ctypes.data_as(c_vp), seg_off.ctypes.data_as(c_vp), ctypes.byref(segs)))
+        flat = _adopt_or_empty(segs.value, int(seg_off[n]) * 8, np.int64)
+        return meta[:n], seg_off, flat
+
+    def queries(self):
+        """[{id, sequence_id, rc, length, offset, inset, segments}] of the last round."""
+        n = int(self._last.num_queries)
+        meta, so, flat = self._segments(lib().dp_overlapper_queries, n, 6)
+        return [dict(id=int(m[0]), sequence_id=int(m[1]), rc=bool(m[2]), length=int(m[3]), offset=int(m[4]), inset=int(m[5]),
+                     segments=flat[so[i]:so[i + 1]]) for i, m in enumerate(meta)]
+
+    def chunks(self, ids=None):
+        """[{read, length, offset, inset, segments}] of the requested chunks (all by default) of the last round."""
+        if ids is None:
+            n, head = int(self._last.num_chunks), (None, 0)
+        else:
+            ida = np.ascontiguousarray(ids, dtype=np.int32)
+            n, head = ida.size, (ida.ctypes.data_as(c_vp), ida.size)
+        meta, so, flat = self._segments(lib().dp_overlapper_chunks, n, 5, *head)
+        return [dict(read=int(m[0]), length=int(m[1]), offset=int(m[2]), inset=int(m[3]), segments=flat[so[i]:so[i + 1]])
+                for i, m in enumerate(meta)]

@@ -2600,3 +2600,5 @@ int dp_kmer_counts(const uint8_t* ascii, int64_t len, int k, uint64_t* counts, i
 }
 
 }  // extern "C"
+
+#include "dp_overlap_api.cuh"

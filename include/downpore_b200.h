@@ -180,6 +180,77 @@ int dp_mapper_create_from_index(const void* image, int64_t bytes, int device, dp
 /* The mapper's parameters: out8 = {k, circular, ref_len, query_size, seed_rate, chunk_size, filter_bits, device}. */
 int dp_mapper_params(const dp_mapper* m, int64_t* out8);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * `downpore overlap` (BASELINE config 5): one ROUND of commands/overlap.go:115-160 up to the stream of seed
+ * matches overlapper.FindOverlaps delivers. The seam is the Go interface
+ *     overlap.Overlapper { PrepareQueries; AddSequences; FindOverlaps; SetOverlapSize }   (overlap/overlap.go:24-29)
+ * over a sequence.SequenceSet (sequence/seqio.go; himem: all reads cached) and a seeds.SeedIndex rebuilt every round
+ * (commands/overlap.go:125-127). What stays on the host: the round loop, overlap.BuildConsensus over the matches of one
+ * query and the PAF lines (commands/overlap.go:163-233), SequenceSet.SetIgnore.
+ * Where the reference leaves an order to the goroutine scheduler (AddSeeds reads the k-mer table unlocked while other
+ * workers write it; chunk ids and match order are arrival orders) the result is that of num_workers = 1: reads in file
+ * order, chunks numbered in emission order, queries in slice order (forward, then reverse complement), candidates in
+ * ascending chunk order.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dp_overlapper dp_overlapper;
+
+/* one *seeds.SeedMatch of FindOverlaps' channel (overlap/overlap.go:374-376) */
+typedef struct dp_overlap_hit {
+    int32_t query_id; /* SeedMatch.QueryID: the slice (shared by its forward and reverse-complement query) */
+    int32_t rc;       /* SeedMatch.ReverseComplementQuery */
+    int32_t target;   /* chunk id: SeqB = index.GetSeedSequence(target) (dp_overlapper_chunks) */
+    int32_t n;        /* len(MatchA) = len(MatchB) */
+    int64_t at;       /* MatchA = matches[at .. at+n), MatchB = matches[at+n .. at+2n): seed indices in SeqA / SeqB */
+} dp_overlap_hit;
+
+typedef struct dp_overlap_round {
+    int64_t num_seeds;           /* index.Size() after PrepareQueries */
+    int64_t num_queries;         /* len(queries): two per slice; 0 ends the command (commands/overlap.go:132-134) */
+    int64_t num_query_seqs;      /* numQuerySeqs (commands/overlap.go:136-145) */
+    int64_t next_first_sequence; /* firstSequence of the next round */
+    int64_t num_chunks;          /* index.GetNumSequences() after AddSequences */
+    int64_t num_hits;
+    int64_t num_matches;         /* entries of `matches` */
+    dp_overlap_hit* hits;        /* malloc'ed, delivery order: queries ascending, targets ascending; dp_free */
+    uint16_t* matches;           /* malloc'ed; dp_free */
+    /* work counters and device timings (CUDA events on the overlapper's stream) */
+    int64_t read_seeds;          /* seed occurrences over all reads sent to AddSequences */
+    int64_t chunk_seeds;         /* seed occurrences over all chunks */
+    int64_t seed_postings;       /* distinct (seed, chunk) pairs */
+    int64_t candidates;          /* candidate chunks over all queries (SeedIndex.Matches) */
+    int64_t pairs;               /* PairwiseAlignments calls (including the recomputed ones of a wave) */
+    int64_t kernel_launches;
+    double ms_total;             /* wall time of the call */
+    double ms_select, ms_queries, ms_scan, ms_chunk, ms_index, ms_lookup, ms_align, ms_collect;
+} dp_overlap_round;
+
+/*
+ * sequence.NewFastaSequenceSet (himem) + the parameters of commands/overlap.go:26-28: packs the reads onto `device`.
+ *   bases_ascii / offsets : the reads that passed the min_length = overlap_size filter, concatenated (n_reads + 1 offsets)
+ *   kmer_values           : 4^k doubles (getKmerValues, commands/overlap.go:41-95) or NULL: set later with
+ *                           dp_overlapper_set_values after dp_overlapper_kmer_counts
+ * FASTA only: FASTQ qualities (which weight AddSeeds' values, seeds/seeds.go:96-98) are not taken.
+ */
+int dp_overlapper_create(const uint8_t* bases_ascii, const int64_t* offsets, int64_t n_reads, int k,
+                         const double* kmer_values, int overlap_size, int num_seeds, int seed_batch_size, int chunk_size,
+                         int query_batch_size, double min_hits, int device, dp_overlapper** out);
+/* sequtil.KmerOccurrences over every read (commands/overlap.go:43): counts[4^k] += occurrences */
+int dp_overlapper_kmer_counts(dp_overlapper* o, uint64_t* counts);
+int dp_overlapper_set_values(dp_overlapper* o, const double* kmer_values);
+/*
+ * One round: PrepareQueries(num_seeds, seed_batch_size, values, GetNSequencesFrom(first_sequence, query_batch_size),
+ * QueryEdges), AddSequences(GetSequences()), FindOverlaps(queries).  ignore: n_reads flags (SequenceSet.SetIgnore) or NULL.
+ */
+int dp_overlapper_round(dp_overlapper* o, const uint8_t* ignore, int64_t first_sequence, dp_overlap_round* out);
+/* The seed sequences of the last round, as the reference's segments (gap, seed, gap, ..., gap) with its seed ids:
+ *   queries: meta = num_queries x {ID, SequenceID, rc, length, offset, inset}; seg_off[num_queries + 1]; *segs malloc'ed
+ *   chunks : ids (NULL = all num_chunks); meta = n x {read, length, offset, inset, n_seeds}; seg_off[n + 1]; *segs malloc'ed
+ *   seed_kmers: the k-mer of every seed id (seedMap), num_seeds entries */
+int dp_overlapper_queries(dp_overlapper* o, int64_t* meta, int64_t* seg_off, int64_t** segs);
+int dp_overlapper_chunks(dp_overlapper* o, const int32_t* ids, int64_t n, int64_t* meta, int64_t* seg_off, int64_t** segs);
+int dp_overlapper_seed_kmers(dp_overlapper* o, int64_t* kmers_out);
+void dp_overlapper_destroy(dp_overlapper* o);
+
 /* Test probes (stage dumps for parity tests; not needed by a host). */
 /* seed k-mers, ascending k-mer value; out must hold num_seeds entries */
 int dp_mapper_seed_kmers(const dp_mapper* m, int64_t* out);
