@@ -46,7 +46,7 @@ class Stats(ctypes.Structure):
 class OverlapRoundStruct(ctypes.Structure):
     _fields_ = [("num_seeds", c_i64), ("num_queries", c_i64), ("num_query_seqs", c_i64), ("next_first_sequence", c_i64),
                 ("num_chunks", c_i64), ("num_hits", c_i64), ("num_matches", c_i64), ("hits", c_vp), ("matches", c_vp),
-                ("read_seeds", c_i64), ("chunk_seeds", c_i64), ("seed_postings", c_i64), ("candidates", c_i64),
+                ("read_seeds", c_i64), ("chunk_seeds", c_i64), ("seed_postings", c_i64), ("posting_entries", c_i64), ("candidates", c_i64),
                 ("pairs", c_i64), ("kernel_launches", c_i64), ("ms_total", ctypes.c_double),
                 ("ms_select", ctypes.c_double), ("ms_queries", ctypes.c_double), ("ms_scan", ctypes.c_double),
                 ("ms_chunk", ctypes.c_double), ("ms_index", ctypes.c_double), ("ms_lookup", ctypes.c_double),

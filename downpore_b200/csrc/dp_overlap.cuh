@@ -24,7 +24,7 @@
 #include "dp_map.cuh"
 
 #define OV_MAXSLICE 8192   // bases of one query slice (< 2 * overlap_size)
-#define OV_MAXBLK 1024     // k-blocks of one slice in AddSeeds
+#define OV_MAXBLK 512      // k-blocks of one slice in AddSeeds (a slice of 8192 bases holds at most 8192 / 18)
 #define OV_MAXN 256        // num_seeds
 #define OV_QMAX 512        // seeds of one query
 #define OV_AMAX 512        // reduced query seeds PairwiseAlignments can hold: seedAligner.reduced has overlap/2 ints
@@ -81,23 +81,30 @@ __device__ __forceinline__ unsigned ov_ldcg(const unsigned* p) { return __ldcg(p
 //   E  registration of the list, every k-mer followed by its reverse complement (seeds.go:131-154): duplicates inside
 //      the list by __match_any_sync, ids by ballot prefix.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) ov_select_kernel(const unsigned* __restrict__ words,
-                                                       const long long* __restrict__ readBase,
-                                                       const int* __restrict__ readLen,
-                                                       const unsigned char* __restrict__ ignore, int nReads,
-                                                       int firstSequence, OvParams P,
-                                                       const double* __restrict__ values, unsigned* bits,
-                                                       unsigned* __restrict__ regKmer, int regCap,
-                                                       OvSlice* __restrict__ slices, int sliceCap,
-                                                       OvSelectOut* __restrict__ out, unsigned* __restrict__ err) {
-    __shared__ unsigned shMask[OV_MAXSLICE / 32 + 2];
+#define OV_SEL_THREADS 256
+__global__ void __launch_bounds__(OV_SEL_THREADS) ov_select_kernel(const unsigned* __restrict__ words,
+                                                                   const long long* __restrict__ readBase,
+                                                                   const int* __restrict__ readLen,
+                                                                   const unsigned char* __restrict__ ignore, int nReads,
+                                                                   int firstSequence, OvParams P,
+                                                                   const double* __restrict__ values, unsigned* bits,
+                                                                   unsigned* __restrict__ regKmer, int regCap,
+                                                                   OvSlice* __restrict__ slices, int sliceCap,
+                                                                   OvSelectOut* __restrict__ out,
+                                                                   unsigned* __restrict__ err) {
+    __shared__ unsigned sw[2][OV_MAXSLICE / 16 + 4];       // the packed words of the read's (one or two) slices
+    __shared__ unsigned shMask[2][OV_MAXSLICE / 32 + 2];   // seed flags of their k-mer positions
     __shared__ int shBlk[OV_MAXBLK];
     __shared__ double shVal[OV_MAXBLK];
     __shared__ unsigned shKmer[OV_MAXBLK];
+    __shared__ double shV2[OV_MAXSLICE / 3 + 16];          // value of every position of every kept block
     __shared__ unsigned shTop[OV_MAXN];
-    const unsigned lane = dp_lane();
+    __shared__ unsigned shNew[2 * OV_MAXN];                // k-mers the read's first slice registered
+    __shared__ int shNb, shNewN, shSize;
+    const unsigned tid = threadIdx.x, lane = dp_lane(), wib = tid >> 5;
     const unsigned lt = dp_lanemask_lt();
     const int k = P.k;
+    const unsigned kShift = 32u - 2u * (unsigned)k;
     int size = 0, nSlices = 0, sent = 0, lastRead = -1;
     for (int id = firstSequence; id < nReads && sent < P.queryBatch; id++) {
         if (ignore && ignore[id]) continue;
@@ -105,81 +112,110 @@ __global__ void __launch_bounds__(32) ov_select_kernel(const unsigned* __restric
         if (size >= P.seedLimit) break;
         const int rlen = readLen[id];
         const int nsl = rlen < P.overlap * 2 ? 1 : 2;
+        const int len = nsl == 1 ? rlen : P.overlap;
+        if (nSlices + nsl > sliceCap || len > OV_MAXSLICE) {
+            if (tid == 0) atomicOr(err, 1u);
+            break;
+        }
+        const int nPos = len - k + 1;
+        const int nW = nPos > 0 ? (nPos + 31) >> 5 : 0;
+        __syncthreads();
+        // ---- the slices' words and the seed flags of all their positions (the table as the previous read left it) ----
         for (int sl = 0; sl < nsl; sl++) {
-            const int start = (nsl == 1 || sl == 0) ? 0 : rlen - P.overlap;
-            const int len = nsl == 1 ? rlen : P.overlap;
-            if (nSlices >= sliceCap || len > OV_MAXSLICE) {
-                if (lane == 0) atomicOr(err, 1u);
-                break;
-            }
-            if (lane == 0) {
+            const long long base = readBase[id] + (sl ? rlen - P.overlap : 0);
+            const int nw = (int)(((base & 15) + len + 15) >> 4) + 1;
+            for (int i = (int)tid; i < nw; i += OV_SEL_THREADS) sw[sl][i] = __ldg(words + (base >> 4) + i);
+            if (tid < 2) shMask[sl][nW + tid] = 0;
+        }
+        if (tid == 0) {
+            for (int sl = 0; sl < nsl; sl++) {
                 OvSlice s;
                 s.read = id;
-                s.start = start;
+                s.start = sl ? rlen - P.overlap : 0;
                 s.len = len;
                 s.pad = 0;
-                slices[nSlices] = s;
+                slices[nSlices + sl] = s;
             }
-            nSlices++;
-            lastRead = id;
-            const long long base = readBase[id] + start;
-            // ---- A: flags of positions 0 .. len-k ----
-            const int nPos = len - k + 1;
-            const int nW = nPos > 0 ? (nPos + 31) >> 5 : 0;
-            for (int w = (int)lane; w < nW + 2; w += 32) {
-                unsigned m = 0;
-                if (w < nW) {
-                    const int p1 = min(32, nPos - w * 32);
-                    for (int b = 0; b < p1; b++) {
-                        unsigned km = dp_kmer_at(words, base + (long long)w * 32 + b, k);
-                        m |= ((ov_ldcg(bits + (km >> 5)) >> (km & 31)) & 1u) << b;
-                    }
+            shNewN = 0;
+        }
+        __syncthreads();
+        for (int sl = 0; sl < nsl; sl++) {
+            const unsigned bo = (unsigned)((readBase[id] + (sl ? rlen - P.overlap : 0)) & 15);
+            for (int p0 = 0; p0 < nPos; p0 += OV_SEL_THREADS) {
+                const int p = p0 + (int)tid;
+                unsigned f = 0;
+                if (p < nPos) {
+                    const unsigned o = bo + (unsigned)p;
+                    const unsigned km = __funnelshift_l(sw[sl][(o >> 4) + 1], sw[sl][o >> 4], (o & 15u) * 2u) >> kShift;
+                    f = (ov_ldcg(bits + (km >> 5)) >> (km & 31)) & 1u;
                 }
-                shMask[w] = m;
+                const unsigned m = __ballot_sync(DP_FULL, f);
+                if (lane == 0 && p0 + (int)(wib * 32) < nPos) shMask[sl][(p0 >> 5) + wib] = m;
             }
-            __syncwarp();
+        }
+        __syncthreads();
+        for (int sl = 0; sl < nsl; sl++) {
+            const unsigned bo = (unsigned)((readBase[id] + (sl ? rlen - P.overlap : 0)) & 15);
+            auto kmer_at = [&](int p) -> unsigned {
+                const unsigned o = bo + (unsigned)p;
+                return __funnelshift_l(sw[sl][(o >> 4) + 1], sw[sl][o >> 4], (o & 15u) * 2u) >> kShift;
+            };
+            if (sl == 1) {
+                // the first slice's seeds: flag their occurrences in the second slice
+                const int nn = shNewN;
+                for (int p = (int)tid; p < nPos; p += OV_SEL_THREADS) {
+                    const unsigned km = kmer_at(p);
+                    bool hit = false;
+                    for (int j = 0; j < nn; j++) hit |= shNew[j] == km;
+                    if (hit) atomicOr(&shMask[1][p >> 5], 1u << (p & 31));
+                }
+                __syncthreads();
+            }
             // ---- B: block walk ----
-            int nb = 0;
-            for (int p0 = 0; p0 + k < len - k;) {
-                const int lo = p0 + 1;
-                const int w = lo >> 5, sh = lo & 31;
-                unsigned v = shMask[w] >> sh;
-                if (sh) v |= shMask[w + 1] << (32 - sh);
-                v &= (1u << k) - 1u;
-                if (v) {
-                    p0 = lo + (__ffs(v) - 1) + 2 * k;
-                } else {
-                    if (nb < OV_MAXBLK) {
-                        if (lane == 0) shBlk[nb] = p0;
-                    } else if (lane == 0) {
-                        atomicOr(err, 1u);
+            if (tid == 0) {
+                int nb = 0;
+                for (int p0 = 0; p0 + k < len - k;) {
+                    const int lo = p0 + 1;
+                    const int w = lo >> 5, sh = lo & 31;
+                    unsigned v = shMask[sl][w] >> sh;
+                    if (sh) v |= shMask[sl][w + 1] << (32 - sh);
+                    v &= (1u << k) - 1u;
+                    if (v) {
+                        p0 = lo + (__ffs(v) - 1) + 2 * k;
+                    } else {
+                        if (nb < OV_MAXBLK) shBlk[nb] = p0;
+                        else atomicOr(err, 1u);
+                        nb++;
+                        p0 += 3 * k;
                     }
-                    nb++;
-                    p0 += 3 * k;
                 }
+                shNb = nb > OV_MAXBLK ? OV_MAXBLK : nb;
             }
-            if (nb > OV_MAXBLK) nb = OV_MAXBLK;
-            __syncwarp();
-            // ---- C: best k-mer of every block ----
-            for (int b = (int)lane; b < nb; b += 32) {
-                const int p0 = shBlk[b];
+            __syncthreads();
+            const int nb = shNb;
+            // ---- C: best-valued k-mer of every block (first maximum, value > 0) ----
+            for (int i = (int)tid; i < nb * k; i += OV_SEL_THREADS) {
+                const int b = i / k, s = i - b * k;
+                shV2[i] = __ldg(values + kmer_at(shBlk[b] + 1 + s));
+            }
+            for (int t = (int)tid; t < P.numSeeds; t += OV_SEL_THREADS) shTop[t] = 0;
+            __syncthreads();
+            for (int b = (int)tid; b < nb; b += OV_SEL_THREADS) {
                 double bestValue = 0.0;
                 unsigned bestSeed = 0;
-                for (int s = p0 + 1; s <= p0 + k; s++) {
-                    unsigned km = dp_kmer_at(words, base + s, k);
-                    double val = __ldg(values + km);
+                for (int s = 0; s < k; s++) {
+                    const double val = shV2[b * k + s];
                     if (val > bestValue) {
                         bestValue = val;
-                        bestSeed = km;
+                        bestSeed = kmer_at(shBlk[b] + 1 + s);
                     }
                 }
                 shVal[b] = bestValue;
                 shKmer[b] = bestSeed;
             }
-            for (int t = (int)lane; t < P.numSeeds; t += 32) shTop[t] = 0;
-            __syncwarp();
+            __syncthreads();
             // ---- D: topN ----
-            for (int b = (int)lane; b < nb; b += 32) {
+            for (int b = (int)tid; b < nb; b += OV_SEL_THREADS) {
                 const double v = shVal[b];
                 if (v > 0.0) {
                     int rank = 0;
@@ -190,33 +226,46 @@ __global__ void __launch_bounds__(32) ov_select_kernel(const unsigned* __restric
                     if (rank < P.numSeeds) shTop[P.numSeeds - 1 - rank] = shKmer[b];
                 }
             }
-            __syncwarp();
-            // ---- E: registration ----
-            for (int e0 = 0; e0 < 2 * P.numSeeds; e0 += 32) {
-                const int e = e0 + (int)lane;
-                const bool valid = e < 2 * P.numSeeds;
-                unsigned km = 0x80000000u | lane;
-                if (valid) {
-                    km = shTop[e >> 1];
-                    if (e & 1) km = dp_revcomp(km, k);
+            __syncthreads();
+            // ---- E: registration (warp 0) ----
+            if (wib == 0) {
+                int sz = size, nn = shNewN;
+                for (int e0 = 0; e0 < 2 * P.numSeeds; e0 += 32) {
+                    const int e = e0 + (int)lane;
+                    const bool valid = e < 2 * P.numSeeds;
+                    unsigned km = 0x80000000u | lane;
+                    if (valid) {
+                        km = shTop[e >> 1];
+                        if (e & 1) km = dp_revcomp(km, k);
+                    }
+                    const unsigned mm = __match_any_sync(DP_FULL, km);
+                    bool isNew = false;
+                    if (valid && (unsigned)(__ffs(mm) - 1) == lane)
+                        isNew = ((ov_ldcg(bits + (km >> 5)) >> (km & 31)) & 1u) == 0;
+                    const unsigned mn = __ballot_sync(DP_FULL, isNew);
+                    if (isNew) {
+                        const int pre = __popc(mn & lt);
+                        if (sz + pre < regCap) regKmer[sz + pre] = km;
+                        else atomicOr(err, 1u);
+                        atomicOr(bits + (km >> 5), 1u << (km & 31));
+                        if (sl == 0 && nn + pre < 2 * OV_MAXN) shNew[nn + pre] = km;
+                    }
+                    sz += __popc(mn);
+                    nn += __popc(mn);
+                    __syncwarp();
                 }
-                const unsigned mm = __match_any_sync(DP_FULL, km);
-                bool isNew = false;
-                if (valid && (unsigned)(__ffs(mm) - 1) == lane)
-                    isNew = ((ov_ldcg(bits + (km >> 5)) >> (km & 31)) & 1u) == 0;
-                const unsigned mn = __ballot_sync(DP_FULL, isNew);
-                if (isNew) {
-                    const int idn = size + __popc(mn & lt);
-                    if (idn < regCap) regKmer[idn] = km;
-                    else atomicOr(err, 1u);
-                    atomicOr(bits + (km >> 5), 1u << (km & 31));
+                if (lane == 0) {
+                    shSize = sz;
+                    if (sl == 0) shNewN = nn;
                 }
-                size += __popc(mn);
-                __syncwarp();
             }
+            __syncthreads();
+            size = shSize;
         }
+        nSlices += nsl;
+        lastRead = id;
     }
-    if (lane == 0) {
+    if (tid == 0) {
         out->size = size;
         out->nSlices = nSlices;
         out->lastRead = lastRead;
@@ -271,6 +320,121 @@ __global__ void ov_sentinel_kernel(const unsigned* __restrict__ rOff, const int*
     unsigned e = rOff[i + 1] - 1;
     rPos[e] = readLen[i];
     rSeed[e] = 0xffffffffu;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AddSequences' scan: SeedIndex.NewSeedSequence on every read that is not ignored (seeds/seeds.go:33-50 through
+// AddSequenceWorker, :357-363). The per-round cost that grows with the read set: every base of every read is visited.
+// One warp per read, persistent CTAs (one per SM) that keep the seed flags in shared memory — all of them for k <= 10
+// (4^k bits <= 128 KiB), their 2^20-bit k-mer-prefix fold above that (positives are confirmed in the L2-resident table).
+// Inside a block of 1024 positions every lane owns 32 consecutive ones (dp_map.cuh's lane-contiguous scheme: the
+// lane's 32+k-1 bases sit in three registers, every k-mer is one funnel shift away):
+//   pass A  hit masks of all blocks -> shared memory, count;
+//   one atomicAdd allocates the read's slice of the seed arrays (count + 1: the sentinel), in whatever order the
+//           warps arrive (rStart / rCount instead of a CSR);
+//   pass B  the hits gather {flags, rank} and write (position, rank) in scan order.
+// ---------------------------------------------------------------------------------------------------------------
+#define OV_SCAN_CACHE 12  // blocks of hit masks kept per warp between the passes (longer reads are scanned twice)
+
+template <bool EXACT>
+__global__ void __launch_bounds__(1024, 1) ov_scan_kernel(const unsigned* __restrict__ words,
+                                                          const long long* __restrict__ readBase,
+                                                          const int* __restrict__ readLen,
+                                                          const unsigned char* __restrict__ ignore, int nReads, int k,
+                                                          const uint2* __restrict__ table,
+                                                          const unsigned* __restrict__ filter, int fBits,
+                                                          unsigned long long* cursor, unsigned long long cap,
+                                                          unsigned* __restrict__ rStart, unsigned* __restrict__ rCount,
+                                                          int* __restrict__ rPos, unsigned* __restrict__ rSeed) {
+    extern __shared__ unsigned dp_smem[];
+    const unsigned lane = dp_lane();
+    const int wib = threadIdx.x >> 5;
+    const unsigned fWords = ((1u << fBits) + 31u) >> 5;
+    for (unsigned i = threadIdx.x; i < fWords; i += blockDim.x) dp_smem[i] = __ldg(filter + i);
+    __syncthreads();
+    const unsigned* filt = dp_smem;
+    unsigned* hm = dp_smem + ((fWords + 3u) & ~3u) + (size_t)wib * OV_SCAN_CACHE * 32;
+    const unsigned kShift = 32u - 2u * (unsigned)k;
+    const unsigned fShift = 32u - (unsigned)fBits;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < nReads; r += nWarps) {
+        const long long base = readBase[r];
+        const int nJ = (ignore && ignore[r]) ? 0 : max(0, readLen[r] - k + 1);
+        const int nBlk = (nJ + 1023) >> 10;
+        auto block_mask = [&](int b) -> unsigned {
+            const int pb = (b << 10) + ((int)lane << 5);
+            const int nValid = min(32, max(0, nJ - pb));
+            DpLaneBases B = dp_lane_bases(words, base + pb, pb < nJ + 32, k, lane);
+            unsigned fm = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const unsigned x = i < 16 ? __funnelshift_l(B.a1, B.a0, 2 * i) : __funnelshift_l(B.a2, B.a1, 2 * (i - 16));
+                const unsigned hx = x >> fShift;
+                fm |= (__funnelshift_r(filt[hx >> 5], 0u, hx) & 1u) << i;
+            }
+            fm &= nValid >= 32 ? 0xffffffffu : ((1u << nValid) - 1u);
+            if (!EXACT) {  // confirm the filter positives
+                unsigned h = 0;
+                while (fm) {
+                    const unsigned i = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                    h |= ((__ldg(&table[kmer >> 5].x) >> (kmer & 31u)) & 1u) << i;
+                }
+                fm = h;
+            }
+            return fm;
+        };
+        unsigned cnt = 0;
+        for (int b = 0; b < nBlk; b++) {
+            const unsigned m = block_mask(b);
+            if (b < OV_SCAN_CACHE) hm[(b << 5) + lane] = m;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        unsigned tot = cnt;
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(DP_FULL, tot, d);
+        unsigned long long at = 0;
+        if (lane == 0) {
+            at = atomicAdd(cursor, (unsigned long long)tot + 1ull);
+            rStart[r] = (unsigned)at;
+            rCount[r] = tot;
+        }
+        at = __shfl_sync(DP_FULL, at, 0);
+        if (at + tot + 1ull > cap) continue;  // the host sees the cursor beyond the capacity and grows the arrays
+        if (lane == 0) {
+            rPos[at + tot] = readLen[r];
+            rSeed[at + tot] = 0xffffffffu;
+        }
+        unsigned blockBase = 0;
+        for (int b = 0; b < nBlk; b++) {
+            unsigned m = b < OV_SCAN_CACHE ? hm[(b << 5) + lane] : block_mask(b);
+            const unsigned mine = __popc(m);
+            unsigned incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned y = __shfl_up_sync(DP_FULL, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            unsigned long long idx = at + blockBase + incl - mine;
+            blockBase += __shfl_sync(DP_FULL, incl, 31);
+            // (the neighbour's words come by shuffle inside dp_lane_bases: every lane takes part when any lane has a hit)
+            if (__any_sync(DP_FULL, m != 0)) {
+                const int pb = (b << 10) + ((int)lane << 5);
+                DpLaneBases B = dp_lane_bases(words, base + pb, pb < nJ + 32, k, lane);
+                while (m) {
+                    const unsigned i = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned kmer = dp_fwd_at(B, i) >> kShift;
+                    const uint2 e = __ldg(table + (kmer >> 5));
+                    rSeed[idx] = e.y + __popc(e.x & ((1u << (kmer & 31)) - 1u));
+                    rPos[idx] = pb + (int)i;
+                    idx++;
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -372,7 +536,8 @@ __global__ void __launch_bounds__(128) ov_build_queries_kernel(const OvSlice* __
 //   GetNextSeedOffset(i)     = pos[i+1] - pos[i]           (i = -1: pos[0] + k)
 //   GetSeedOffsetFromEnd(i)  = length - pos[i] - k
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void ov_chunk_kernel(const unsigned* __restrict__ rOff, const int* __restrict__ rPos,
+__global__ void ov_chunk_kernel(const unsigned* __restrict__ rStart, const unsigned* __restrict__ rCount,
+                                const int* __restrict__ rPos,
                                 const int* __restrict__ readLen, const unsigned char* __restrict__ ignore, int nReads,
                                 OvParams P, int pass, unsigned* __restrict__ counts,
                                 const unsigned* __restrict__ pieceOff, OvChunk* __restrict__ chunks,
@@ -380,8 +545,8 @@ __global__ void ov_chunk_kernel(const unsigned* __restrict__ rOff, const int* __
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nReads) return;
     unsigned cnt = 0;
-    const unsigned ro = rOff[r];
-    const int n = (int)(rOff[r + 1] - ro) - 1;
+    const unsigned ro = rStart[r];
+    const int n = (int)rCount[r];
     const int length = readLen[r];
     const int k = P.k;
     OvChunk* outp = pass ? chunks + pieceOff[r] : nullptr;
@@ -477,41 +642,62 @@ __global__ void __launch_bounds__(256) ov_keys_kernel(const OvChunk* __restrict_
     }
 }
 
+// sorted distinct (seed, chunk) keys -> CSR: the chunk column, and seedOff[] from the places where the seed changes (no
+// atomics: a counter per seed under 60 M increments is a serial queue)
+__global__ void ov_seed_bounds_kernel(const unsigned long long* __restrict__ keys, unsigned long long n, unsigned numSeeds,
+                                      unsigned* __restrict__ seedOff, unsigned* __restrict__ seedChunks) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    const unsigned s = (unsigned)(key >> 32);
+    seedChunks[i] = (unsigned)key;
+    const long long prev = i ? (long long)(keys[i - 1] >> 32) : -1ll;
+    for (long long t = prev + 1; t <= (long long)s; t++) seedOff[t] = (unsigned)i;
+    if (i == n - 1)
+        for (unsigned t = s + 1; t <= numSeeds; t++) seedOff[t] = (unsigned)n;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // SeedIndex.Matches (seeds/seeds.go:335-353) -> util.GetSharedIDs (util/bitset.go:308-411) for the queries of a round,
 // restated over posting runs (the refinement of the clamped levels and of the level-16
-// under-count is dp_map.cuh's dp_refine_emit). One CTA per query, a 32-bit counter per chunk in HBM (lower half:
-// included runs containing the chunk; upper half: those among them that repeat an earlier run's seed):
-//   inclusion filter (ordered, one thread on prefetched run lengths) -> counters += runs (all threads, coalesced along
-//   the runs) -> ordered scan of the touched counter range: threshold, compaction in chunk order, counters back to
-//   zero -> refinement + distinct counts by warp 0 into the round's candidate pool.
+// under-count is dp_map.cuh's dp_refine_emit). One CTA per query; the chunk ids are walked in tiles of 65536 whose
+// 16-bit counters live in shared memory (a round's index holds 10^5..10^6 chunks: counters in HBM cost one L2 atomic per
+// posting, 5 ms per round; in shared memory the postings are read once and that is all the traffic):
+//   inclusion filter (ordered, one thread on prefetched run lengths)
+//   per tile: every run's postings inside the tile (runs ascend: one lower_bound from the previous tile's end) ->
+//             shared-memory counters -> ordered threshold scan, compaction in chunk order
+//   refinement + distinct counts by warp 0 into the round's candidate pool.
 // minCount = int(hitFraction * n + 0.5) in fp64 (no fused multiply-add).
 // ---------------------------------------------------------------------------------------------------------------
-#define OV_LTHREADS 256
+#define OV_LTHREADS 512
+#define OV_TILE 65536u
 
-__global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, const unsigned* __restrict__ qOff,
-                                                                const unsigned* __restrict__ qSeed, int nQueries,
-                                                                double hitFraction, unsigned* counters, unsigned cStride,
-                                                                unsigned long long* candScratch, unsigned candCap,
-                                                                unsigned* __restrict__ qCandOff,
-                                                                int* __restrict__ qCandN,
-                                                                unsigned* __restrict__ poolChunk,
-                                                                unsigned short* __restrict__ poolDist,
-                                                                unsigned long long* cursor, unsigned long long poolCap,
-                                                                unsigned* __restrict__ err) {
-    __shared__ unsigned eSeed[OV_QMAX], eOff[OV_QMAX], ePre[OV_QMAX + 1], eEndW[OV_QMAX];
+__global__ void __launch_bounds__(OV_LTHREADS, 1) ov_lookup_kernel(DpIndexDev I, const unsigned* __restrict__ qOff,
+                                                                   const unsigned* __restrict__ qSeed, int nQueries,
+                                                                   double hitFraction,
+                                                                   unsigned long long* candScratch, unsigned candCap,
+                                                                   unsigned* __restrict__ qCandOff,
+                                                                   int* __restrict__ qCandN,
+                                                                   unsigned* __restrict__ poolChunk,
+                                                                   unsigned short* __restrict__ poolDist,
+                                                                   unsigned long long* cursor, unsigned long long poolCap,
+                                                                   unsigned long long* __restrict__ postingCount,
+                                                                   unsigned* __restrict__ err) {
+    extern __shared__ unsigned cntw[];  // OV_TILE / 2 words: two 16-bit counters each
     __shared__ unsigned tSeed[OV_QMAX], tOff[OV_QMAX], tCnt[OV_QMAX];
-    __shared__ unsigned char eDup[OV_QMAX];
-    __shared__ unsigned short order[OV_QMAX];
+    __shared__ unsigned eSeed[OV_QMAX], eOff[OV_QMAX], ePre[OV_QMAX + 1], eEndW[OV_QMAX];
+    __shared__ unsigned cur[OV_QMAX], tPre[OV_QMAX + 1];
+    __shared__ unsigned char eFirst[OV_QMAX];
+    __shared__ unsigned short dupList[OV_QMAX], order[OV_QMAX];
     __shared__ int sim[2];
-    __shared__ int shN[4];  // nInc, nAllDistinct, (unused), (unused)
+    __shared__ int shN[4];  // nInc, nAllDistinct, candidates out, nDup
     __shared__ unsigned shRange[2];
     __shared__ unsigned warpTot[OV_LTHREADS / 32];
     __shared__ unsigned shBase;
     const unsigned tid = threadIdx.x, lane = dp_lane(), wib = tid >> 5;
     const unsigned C = I.numChunks;
-    unsigned* cnt = counters + (size_t)blockIdx.x * cStride;
     unsigned long long* cand = candScratch + (size_t)blockIdx.x * candCap;
+    unsigned long long postings = 0;
     for (int q = blockIdx.x; q < nQueries; q += gridDim.x) {
         const unsigned qb = qOff[q];
         const int n = (int)(qOff[q + 1] - qb);
@@ -572,7 +758,8 @@ __global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, co
                     T = minCount > 1 ? minCount : 1;
                 }
                 const bool q6 = minCount >= 13 && minCount <= 24;
-                // repeats of an earlier run's seed, last word of each run
+                // first occurrences among the included runs, first / last chunk of each run
+                unsigned cmin = 0xffffffffu, cmax = 0;
                 for (int j = (int)tid; j < nInc; j += OV_LTHREADS) {
                     const unsigned s = eSeed[j];
                     bool dup = false;
@@ -581,84 +768,127 @@ __global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, co
                             dup = true;
                             break;
                         }
-                    eDup[j] = dup ? 1 : 0;
+                    eFirst[j] = dup ? 0 : 1;
                     const unsigned c = ePre[j];
-                    eEndW[j] = c ? (__ldg(I.seedChunks + eOff[j] + c - 1) >> 6) : 0u;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    unsigned tot = 0;
-                    for (int j = 0; j < nInc; j++) {
-                        const unsigned c = ePre[j];
-                        ePre[j] = tot;
-                        tot += c;
+                    unsigned last = 0;
+                    if (c) {
+                        last = __ldg(I.seedChunks + eOff[j] + c - 1);
+                        cmin = min(cmin, __ldg(I.seedChunks + eOff[j]));
+                        cmax = max(cmax, last);
                     }
-                    ePre[nInc] = tot;
-                }
-                __syncthreads();
-                const unsigned total = ePre[nInc];
-                // ---- gather ----
-                unsigned cmin = 0xffffffffu, cmax = 0;
-                for (unsigned p = tid; p < total; p += OV_LTHREADS) {
-                    int lo = 0, hi = nInc;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (ePre[mid] <= p) lo = mid;
-                        else hi = mid;
-                    }
-                    const unsigned chunk = __ldg(I.seedChunks + eOff[lo] + (p - ePre[lo]));
-                    atomicAdd(cnt + chunk, eDup[lo] ? 0x10001u : 1u);
-                    cmin = min(cmin, chunk);
-                    cmax = max(cmax, chunk);
+                    eEndW[j] = c ? (last >> 6) : 0u;
+                    cur[j] = 0;
                 }
                 if (cmin != 0xffffffffu) {
                     atomicMin(&shRange[0], cmin);
                     atomicMax(&shRange[1], cmax);
                 }
                 __syncthreads();
-                // ---- ordered scan of the touched range ----
+                if (tid == 0) {
+                    unsigned tot = 0;
+                    int nDup = 0;
+                    for (int j = 0; j < nInc; j++) {
+                        const unsigned c = ePre[j];
+                        ePre[j] = tot;
+                        tot += c;
+                        if (!eFirst[j]) dupList[nDup++] = (unsigned short)j;
+                    }
+                    ePre[nInc] = tot;
+                    shN[3] = nDup;
+                }
+                __syncthreads();
+                postings += tid == 0 ? ePre[nInc] : 0u;
                 unsigned nCand = 0;
                 if (shRange[0] != 0xffffffffu) {
-                    const unsigned c0 = shRange[0] & ~3u, c1 = shRange[1];
-                    for (unsigned tb = c0; tb <= c1; tb += OV_LTHREADS * 4) {
-                        const unsigned cb = tb + tid * 4;
-                        unsigned v[4] = {0, 0, 0, 0};
-                        if (cb <= c1) {
-                            if (cb + 3 < C && (cStride & 3u) == 0) {
-                                uint4 x = *reinterpret_cast<const uint4*>(cnt + cb);
-                                v[0] = x.x;
-                                v[1] = x.y;
-                                v[2] = x.z;
-                                v[3] = x.w;
-                            } else {
+                    const unsigned tile0 = shRange[0] / OV_TILE, tile1 = shRange[1] / OV_TILE;
+                    for (unsigned tile = tile0; tile <= tile1; tile++) {
+                        const unsigned tStart = tile * OV_TILE;
+                        const unsigned tEnd = min(C, tStart + OV_TILE);
+                        const unsigned tWords = (tEnd - tStart + 1) >> 1;
+                        // the part of every run that lies inside the tile
+                        for (int j = (int)tid; j < nInc; j += OV_LTHREADS) {
+                            const unsigned len = ePre[j + 1] - ePre[j];
+                            unsigned lo = cur[j], hi = len;
+                            const unsigned* run = I.seedChunks + eOff[j];
+                            while (lo < hi) {
+                                const unsigned mid = (lo + hi) >> 1;
+                                if (__ldg(run + mid) < tEnd) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            tPre[j] = lo - cur[j];
+                        }
+                        for (unsigned i = tid; i < tWords; i += OV_LTHREADS) cntw[i] = 0;
+                        __syncthreads();
+                        if (wib == 0) {  // exclusive prefix of the in-tile lengths
+                            unsigned carry = 0;
+                            for (int j0 = 0; j0 < nInc; j0 += 32) {
+                                const int j = j0 + (int)lane;
+                                const unsigned c = j < nInc ? tPre[j] : 0u;
+                                unsigned x = c;
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    unsigned y = __shfl_up_sync(DP_FULL, x, d);
+                                    if ((int)lane >= d) x += y;
+                                }
+                                if (j < nInc) tPre[j] = carry + x - c;
+                                carry += __shfl_sync(DP_FULL, x, 31);
+                            }
+                            if (lane == 0) tPre[nInc] = carry;
+                        }
+                        __syncthreads();
+                        const unsigned tTot = tPre[nInc];
+                        if (tTot == 0) continue;  // (uniform)
+                        for (unsigned p = tid; p < tTot; p += OV_LTHREADS) {
+                            int lo = 0, hi = nInc;
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (tPre[mid] <= p) lo = mid;
+                                else hi = mid;
+                            }
+                            const unsigned chunk = __ldg(I.seedChunks + eOff[lo] + cur[lo] + (p - tPre[lo]));
+                            const unsigned loc = chunk - tStart;
+                            atomicAdd(&cntw[loc >> 1], 1u << ((loc & 1u) * 16u));
+                        }
+                        __syncthreads();
+                        for (int j = (int)tid; j < nInc; j += OV_LTHREADS) cur[j] += tPre[j + 1] - tPre[j];
+                        // ordered threshold scan of the tile
+                        for (unsigned wb = 0; wb < tWords; wb += OV_LTHREADS * 2) {
+                            const unsigned wi = wb + tid * 2;
+                            unsigned v[4] = {0, 0, 0, 0};
+                            if (wi < tWords) {
+                                const unsigned x = cntw[wi];
+                                v[0] = x & 0xffffu;
+                                v[1] = x >> 16;
+                                if (wi + 1 < tWords) {
+                                    const unsigned y = cntw[wi + 1];
+                                    v[2] = y & 0xffffu;
+                                    v[3] = y >> 16;
+                                }
+                            }
+                            unsigned mine = 0;
+                            for (int i = 0; i < 4; i++) mine += (int)v[i] >= T;
+                            unsigned x = mine;
+                            for (int d = 1; d < 32; d <<= 1) {
+                                unsigned y = __shfl_up_sync(DP_FULL, x, d);
+                                if ((int)lane >= d) x += y;
+                            }
+                            if (lane == 31) warpTot[wib] = x;
+                            __syncthreads();
+                            unsigned before = 0, all = 0;
+                            for (unsigned w = 0; w < OV_LTHREADS / 32; w++) {
+                                if (w < wib) before += warpTot[w];
+                                all += warpTot[w];
+                            }
+                            if (all) {
+                                unsigned idx = nCand + before + x - mine;
                                 for (int i = 0; i < 4; i++)
-                                    if (cb + i < C) v[i] = cnt[cb + i];
+                                    if ((int)v[i] >= T) {
+                                        if (idx < candCap) cand[idx] = ((unsigned long long)(tStart + wi * 2 + i) << 32) | v[i];
+                                        idx++;
+                                    }
+                                nCand += all;
                             }
-                            for (int i = 0; i < 4; i++)
-                                if (v[i]) cnt[cb + i] = 0;
+                            __syncthreads();
                         }
-                        unsigned mine = 0;
-                        for (int i = 0; i < 4; i++) mine += (int)(v[i] & 0xffffu) >= T;
-                        unsigned x = mine;  // block exclusive scan
-                        for (int d = 1; d < 32; d <<= 1) {
-                            unsigned y = __shfl_up_sync(DP_FULL, x, d);
-                            if ((int)lane >= d) x += y;
-                        }
-                        if (lane == 31) warpTot[wib] = x;
-                        __syncthreads();
-                        unsigned before = 0, all = 0;
-                        for (unsigned w = 0; w < OV_LTHREADS / 32; w++) {
-                            if (w < wib) before += warpTot[w];
-                            all += warpTot[w];
-                        }
-                        unsigned idx = nCand + before + x - mine;
-                        for (int i = 0; i < 4; i++)
-                            if ((int)(v[i] & 0xffffu) >= T) {
-                                if (idx < candCap) cand[idx] = ((unsigned long long)(cb + i) << 32) | v[i];
-                                idx++;
-                            }
-                        nCand += all;
-                        __syncthreads();
                     }
                 }
                 if (nCand > candCap) {
@@ -677,9 +907,9 @@ __global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, co
                         X.eOff = eOff;
                         X.ePre = ePre;
                         X.eEndW = eEndW;
-                        X.eFirst = nullptr;
-                        X.dup = nullptr;
-                        X.nDup = 0;
+                        X.eFirst = eFirst;
+                        X.dup = dupList;
+                        X.nDup = shN[3];
                         X.order = order;
                         X.sim = sim;
                         X.nInc = nInc;
@@ -688,8 +918,9 @@ __global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, co
                         X.clamped = clamped;
                         X.q6 = q6;
                         X.nAllDistinct = shN[1];
+                        __threadfence_block();
                         __syncwarp();
-                        int no = dp_refine_emit<true>(I, X, cand, (int)nCand, poolChunk + at, poolDist + at, (int)nCand);
+                        int no = dp_refine_emit<false>(I, X, cand, (int)nCand, poolChunk + at, poolDist + at, (int)nCand);
                         if (lane == 0) {
                             shBase = (unsigned)at;
                             shN[2] = no;
@@ -712,6 +943,7 @@ __global__ void __launch_bounds__(OV_LTHREADS) ov_lookup_kernel(DpIndexDev I, co
             qCandN[q] = nCandOut;
         }
     }
+    if (postings) atomicAdd(postingCount, postings);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1178,7 +1410,7 @@ __global__ void ov_export_chunk_meta_kernel(const OvChunk* __restrict__ chunks, 
     meta[i * 5 + 4] = c.n;
 }
 __global__ void ov_export_chunk_segs_kernel(const OvChunk* __restrict__ chunks, const unsigned* __restrict__ ids, int n,
-                                            const unsigned* __restrict__ rOff, const int* __restrict__ rPos,
+                                            const unsigned* __restrict__ rStart, const int* __restrict__ rPos,
                                             const unsigned* __restrict__ rSeed, const unsigned* __restrict__ regOfRank,
                                             int k, const long long* __restrict__ segOff, long long* __restrict__ segs) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1186,7 +1418,7 @@ __global__ void ov_export_chunk_segs_kernel(const OvChunk* __restrict__ chunks, 
     if (w >= n) return;
     const OvChunk c = chunks[ids[w]];
     long long* out = segs + segOff[w];
-    const unsigned r0 = rOff[c.read];
+    const unsigned r0 = rStart[c.read];
     for (unsigned i = lane; i <= c.n; i += 32) {
         const unsigned g = c.first + i;
         // gap before seed i of the piece (i == n: the gap behind its last seed)

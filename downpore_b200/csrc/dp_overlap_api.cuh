@@ -28,7 +28,9 @@ struct dp_overlapper {
     DBuf<unsigned> qOff, qSeed, qDistinct;
     DBuf<int> qPos, qND;
     DBuf<unsigned short> qSlot;
-    DBuf<unsigned> rOff, rSeed;
+    DBuf<unsigned> rStart, rCount, rSeed, filter;
+    unsigned long long seedCap = 0;
+    bool scanAttr = false;
     DBuf<int> rPos;
     DBuf<unsigned> pieceOff, keyOff;
     DBuf<OvChunk> chunks;
@@ -36,8 +38,8 @@ struct dp_overlapper {
     DBuf<unsigned> seedOff, seedChunks, seedCount;
     DBuf<unsigned char> tmp;
     // lookup
-    DBuf<unsigned> counters, qCandOff, poolChunk;
-    size_t countersZeroed = 0;
+    DBuf<unsigned> qCandOff, poolChunk;
+    bool lookupAttr = false;
     DBuf<unsigned long long> candScratch, cursors;  // cursors: [0] candidate pool, [1] match pool, [2] pairs
     DBuf<int> qCandN;
     DBuf<unsigned short> poolDist;
@@ -89,7 +91,7 @@ unsigned ov_fetch_err(dp_overlapper& O) {
 
 void ov_check_fatal(unsigned e) {
     if (e & 1u) throw std::runtime_error("overlap: a capacity of the seed selection was exceeded (slice longer than 8192 bases, "
-                                         "more than 1024 k-blocks in a slice, or more slices than 2 x query_batch_size)");
+                                         "more than 512 k-blocks in a slice, or more slices than 2 x query_batch_size)");
     if (e & 2u) throw std::runtime_error("overlap: a query slice holds more than 512 seeds (unsupported)");
     if (e & 16u) throw std::runtime_error("overlap: the reference panics on this input (seedAligner.reduced overflows, "
                                           "seeds/alignment.go:341-388)");
@@ -183,13 +185,14 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
     O.bits.reserve((size_t)nTable);
     CK(cudaMemsetAsync(O.bits.p, 0, (size_t)nTable * sizeof(unsigned), st));
     O.err.reserve(1);
+    O.cursors.reserve(8);
     CK(cudaMemsetAsync(O.err.p, 0, sizeof(unsigned), st));
     const int regCap = P.seedLimit + 4 * P.numSeeds + 64;
     const int sliceCap = 2 * P.queryBatch + 2;
     O.regKmer.reserve((size_t)regCap);
     O.slices.reserve((size_t)sliceCap);
     O.selOut.reserve(1);
-    ov_select_kernel<<<1, 32, 0, st>>>(O.words.p, O.readBase.p, O.readLen.p, O.ignore.p, (int)nReads, (int)firstSequence, P,
+    ov_select_kernel<<<1, OV_SEL_THREADS, 0, st>>>(O.words.p, O.readBase.p, O.readLen.p, O.ignore.p, (int)nReads, (int)firstSequence, P,
                                        O.values.p, O.bits.p, O.regKmer.p, regCap, O.slices.p, sliceCap, O.selOut.p, O.err.p);
     CK(cudaGetLastError());
     OvSelectOut so;
@@ -257,32 +260,56 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
     CK(cudaGetLastError());
     mark(2);
     // ---- AddSequences: every read's seed sequence ----
-    ov_read_descs_kernel<<<div_up(nReads, 256), 256, 0, st>>>(O.readBase.p, O.readLen.p, O.ignore.p, (int)nReads, k, O.descs.p);
-    CK(cudaMemsetAsync(O.counts.p, 0, ((size_t)nReads + 1) * sizeof(unsigned), st));
-    scanBlocks = std::min<int>(div_up(nReads, 8), O.smCount * 8);
-    dp_chunk_scan_kernel<<<scanBlocks, 256, 0, st>>>(O.words.p, O.table.p, O.descs.p, (unsigned)nReads, k, 0, O.counts.p,
-                                                     nullptr, nullptr, nullptr, nullptr);
-    ov_add_one_kernel<<<div_up(nReads, 256), 256, 0, st>>>(O.counts.p, (int)nReads);
-    O.rOff.reserve((size_t)nReads + 2);
     {
-        // 64-bit total first: the CSR offsets are 32-bit
-        ov_scan_u32(O, O.counts.p, O.rOff.p, nReads + 1);
+        const int fBits = std::min(20, 2 * k);
+        const bool exact = 2 * k <= 20;
+        const unsigned* filt = O.bits.p;
+        if (!exact) {
+            const size_t fw = (((size_t)1 << fBits) + 31) / 32;
+            O.filter.reserve(fw);
+            CK(cudaMemsetAsync(O.filter.p, 0, fw * sizeof(unsigned), st));
+            dp_filter_build_kernel<<<div_up(nTable, 256), 256, 0, st>>>(O.table.p, nTable, k, fBits, O.filter.p);
+            filt = O.filter.p;
+        }
+        const size_t fWords = (((size_t)1 << fBits) + 31) / 32;
+        const size_t smem = (((fWords + 3) & ~(size_t)3) + (size_t)32 * OV_SCAN_CACHE * 32) * sizeof(unsigned);
+        if (!O.scanAttr) {
+            CK(cudaFuncSetAttribute(ov_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CK(cudaFuncSetAttribute(ov_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            O.scanAttr = true;
+        }
+        O.rStart.reserve((size_t)nReads + 1);
+        O.rCount.reserve((size_t)nReads + 1);
+        if (O.seedCap == 0) O.seedCap = (unsigned long long)(O.totalBases / 48) + (unsigned long long)nReads + 4096;
+        for (;;) {
+            if (O.seedCap >= 0xfffffff0ull) throw std::runtime_error("overlap: more than 2^32 seed occurrences in the read set");
+            O.rPos.reserve((size_t)O.seedCap + 2);
+            O.rSeed.reserve((size_t)O.seedCap + 2);
+            CK(cudaMemsetAsync(O.cursors.p + 3, 0, sizeof(unsigned long long), st));
+            const int grid = (int)std::min<long long>(O.smCount, (nReads + 31) / 32);
+            if (exact)
+                ov_scan_kernel<true><<<grid, 1024, smem, st>>>(O.words.p, O.readBase.p, O.readLen.p, O.ignore.p, (int)nReads, k,
+                                                             O.table.p, filt, fBits, O.cursors.p + 3, O.seedCap, O.rStart.p,
+                                                             O.rCount.p, O.rPos.p, O.rSeed.p);
+            else
+                ov_scan_kernel<false><<<grid, 1024, smem, st>>>(O.words.p, O.readBase.p, O.readLen.p, O.ignore.p, (int)nReads, k,
+                                                              O.table.p, filt, fBits, O.cursors.p + 3, O.seedCap, O.rStart.p,
+                                                              O.rCount.p, O.rPos.p, O.rSeed.p);
+            CK(cudaGetLastError());
+            unsigned long long used = 0;
+            CK(cudaMemcpyAsync(&used, O.cursors.p + 3, sizeof(used), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            O.nReadSeeds = used;
+            if (used <= O.seedCap) break;
+            O.seedCap = used + used / 16 + 4096;
+        }
     }
-    unsigned Rn = 0;
-    CK(cudaMemcpyAsync(&Rn, O.rOff.p + nReads, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    O.nReadSeeds = Rn;
-    O.rPos.reserve((size_t)Rn + 2);
-    O.rSeed.reserve((size_t)Rn + 2);
-    dp_chunk_scan_kernel<<<scanBlocks, 256, 0, st>>>(O.words.p, O.table.p, O.descs.p, (unsigned)nReads, k, 1, nullptr, O.rOff.p,
-                                                     O.rPos.p, O.rSeed.p, nullptr);
-    ov_sentinel_kernel<<<div_up(nReads, 256), 256, 0, st>>>(O.rOff.p, O.readLen.p, (int)nReads, O.rPos.p, O.rSeed.p);
-    CK(cudaGetLastError());
+    const unsigned long long Rn = O.nReadSeeds;
     mark(3);
     // ---- chunkWorker ----
     O.pieceOff.reserve((size_t)nReads + 2);
     CK(cudaMemsetAsync(O.counts.p, 0, ((size_t)nReads + 1) * sizeof(unsigned), st));
-    ov_chunk_kernel<<<div_up(nReads, 128), 128, 0, st>>>(O.rOff.p, O.rPos.p, O.readLen.p, O.ignore.p, (int)nReads, P, 0,
+    ov_chunk_kernel<<<div_up(nReads, 128), 128, 0, st>>>(O.rStart.p, O.rCount.p, O.rPos.p, O.readLen.p, O.ignore.p, (int)nReads, P, 0,
                                                          O.counts.p, nullptr, nullptr, O.err.p);
     ov_scan_u32(O, O.counts.p, O.pieceOff.p, nReads + 1);
     unsigned C = 0;
@@ -297,7 +324,7 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
         return;
     }
     O.chunks.reserve((size_t)C + 1);
-    ov_chunk_kernel<<<div_up(nReads, 128), 128, 0, st>>>(O.rOff.p, O.rPos.p, O.readLen.p, O.ignore.p, (int)nReads, P, 1, nullptr,
+    ov_chunk_kernel<<<div_up(nReads, 128), 128, 0, st>>>(O.rStart.p, O.rCount.p, O.rPos.p, O.readLen.p, O.ignore.p, (int)nReads, P, 1, nullptr,
                                                          O.pieceOff.p, O.chunks.p, O.err.p);
     O.keyOff.reserve((size_t)C + 2);
     if (O.counts.cap < (size_t)C + 2) O.counts.reserve((size_t)C + 2);
@@ -332,12 +359,11 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
     }
     O.nSeedPostings = P1;
     O.seedChunks.reserve((size_t)P1 + 4);
-    O.seedCount.reserve((size_t)S + 2);
     O.seedOff.reserve((size_t)S + 2);
-    CK(cudaMemsetAsync(O.seedCount.p, 0, ((size_t)S + 2) * sizeof(unsigned), st));
     if (P1 > 0)
-        dp_posting_fill_kernel<<<div_up((long long)P1, 256), 256, 0, st>>>(O.keys.p, (long long)P1, O.seedCount.p, O.seedChunks.p);
-    ov_scan_u32(O, O.seedCount.p, O.seedOff.p, (long long)S + 1);
+        ov_seed_bounds_kernel<<<div_up((long long)P1, 256), 256, 0, st>>>(O.keys.p, P1, (unsigned)S, O.seedOff.p, O.seedChunks.p);
+    else
+        CK(cudaMemsetAsync(O.seedOff.p, 0, ((size_t)S + 2) * sizeof(unsigned), st));
     CK(cudaGetLastError());
     mark(5);
     DpIndexDev I{};
@@ -348,19 +374,14 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
     I.seedChunks = O.seedChunks.p;
     I.table = O.table.p;
     // ---- Matches: candidate chunks of every query ----
-    const int lookupGrid = std::min(nQ, O.smCount * 2);
-    const unsigned cStride = (C + 3u) & ~3u;
-    {
-        const size_t need = (size_t)lookupGrid * cStride;
-        if (O.counters.cap < need || O.countersZeroed < need) {
-            O.counters.reserve(need);
-            CK(cudaMemsetAsync(O.counters.p, 0, O.counters.cap * sizeof(unsigned), st));
-            O.countersZeroed = O.counters.cap;
-        }
+    const int lookupGrid = std::min(nQ, O.smCount);
+    const size_t lookupSmem = (size_t)OV_TILE / 2 * sizeof(unsigned);
+    if (!O.lookupAttr) {
+        CK(cudaFuncSetAttribute(ov_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lookupSmem));
+        O.lookupAttr = true;
     }
     O.qCandOff.reserve((size_t)nQ + 1);
     O.qCandN.reserve((size_t)nQ + 1);
-    O.cursors.reserve(4);
     if (O.candCap == 0) O.candCap = 1u << 14;
     if (O.poolCap == 0) O.poolCap = 1ull << 20;
     for (;;) {
@@ -368,11 +389,13 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
         O.candScratch.reserve((size_t)lookupGrid * candCap);
         O.poolChunk.reserve((size_t)O.poolCap);
         O.poolDist.reserve((size_t)O.poolCap);
-        CK(cudaMemsetAsync(O.cursors.p, 0, 4 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(O.cursors.p, 0, 3 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(O.err.p, 0, sizeof(unsigned), st));
-        ov_lookup_kernel<<<lookupGrid, OV_LTHREADS, 0, st>>>(I, O.qOff.p, O.qSeed.p, nQ, P.hitFraction, O.counters.p, cStride,
-                                                             O.candScratch.p, candCap, O.qCandOff.p, O.qCandN.p, O.poolChunk.p,
-                                                             O.poolDist.p, O.cursors.p, O.poolCap, O.err.p);
+        CK(cudaMemsetAsync(O.cursors.p + 4, 0, sizeof(unsigned long long), st));
+        ov_lookup_kernel<<<lookupGrid, OV_LTHREADS, lookupSmem, st>>>(I, O.qOff.p, O.qSeed.p, nQ, P.hitFraction, O.candScratch.p,
+                                                                      candCap, O.qCandOff.p, O.qCandN.p, O.poolChunk.p,
+                                                                      O.poolDist.p, O.cursors.p, O.poolCap, O.cursors.p + 4,
+                                                                      O.err.p);
         CK(cudaGetLastError());
         const unsigned e = ov_fetch_err(O);
         ov_check_fatal(e);
@@ -388,9 +411,11 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
         }
         break;
     }
-    unsigned long long nPool = 0;
+    unsigned long long nPool = 0, nPost = 0;
     CK(cudaMemcpy(&nPool, O.cursors.p, sizeof(nPool), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&nPost, O.cursors.p + 4, sizeof(nPost), cudaMemcpyDeviceToHost));
     R->candidates = (int64_t)nPool;
+    R->posting_entries = (int64_t)nPost;
     mark(6);
     // ---- matchWorker ----
     const int W = 64;
@@ -673,7 +698,7 @@ int dp_overlapper_chunks(dp_overlapper* o, const int32_t* ids, int64_t n, int64_
         dSegOff.reserve((size_t)n + 1);
         dSegs.reserve((size_t)total + 1);
         CK(cudaMemcpyAsync(dSegOff.p, seg_off, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, o->st));
-        ov_export_chunk_segs_kernel<<<div_up(n * 32, 128), 128, 0, o->st>>>(o->chunks.p, dIds.p, (int)n, o->rOff.p, o->rPos.p,
+        ov_export_chunk_segs_kernel<<<div_up(n * 32, 128), 128, 0, o->st>>>(o->chunks.p, dIds.p, (int)n, o->rStart.p, o->rPos.p,
                                                                            o->rSeed.p, o->regOfRank.p, o->P.k, dSegOff.p, dSegs.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h, dSegs.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, o->st));

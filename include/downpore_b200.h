@@ -217,6 +217,7 @@ typedef struct dp_overlap_round {
     int64_t read_seeds;          /* seed occurrences over all reads sent to AddSequences */
     int64_t chunk_seeds;         /* seed occurrences over all chunks */
     int64_t seed_postings;       /* distinct (seed, chunk) pairs */
+    int64_t posting_entries;     /* seed -> chunk postings gathered by the Matches kernel */
     int64_t candidates;          /* candidate chunks over all queries (SeedIndex.Matches) */
     int64_t pairs;               /* PairwiseAlignments calls (including the recomputed ones of a wave) */
     int64_t kernel_launches;
