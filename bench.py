@@ -559,6 +559,83 @@ def side_workload(dp, synth, torch, po, args, name, rank, world, local, dev, cor
          globals()["WORKLOAD"], args.reads) = keep
 
 
+def overlap_workload(dp, synth, po, args, device, cores, peak):
+    """BASELINE config 5 (`downpore overlap`): reads simulated from reference 1 (seed 15), overlap defaults
+    (commands/overlap.go:26-27). A step = one ROUND of commands/overlap.go:115-160 up to the seed-match stream
+    (PrepareQueries, AddSequences over the whole read set, FindOverlaps) through dp_overlapper_round: the read set stays
+    on the device between rounds (the reference's himem cache), the round's ignore flags go in and its hits come out
+    every step. Gbp/s counts the bases of the read set, every one of which AddSequences visits every round."""
+    n, L = args.overlap_reads, 10_000
+    ref = synth.reference(1, 4_600_000)
+    rd = synth.reads(ref, 15, n, L, circular=True)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    t0 = time.time()
+    g = dp.Overlapper(rd, offs, None, device=device)
+    create_s = time.time() - t0
+    t0 = time.time()
+    vals = dp.kmer_values(g.kmer_counts(), 10)
+    g.set_values(vals)
+    values_s = time.time() - t0
+    ignore = np.zeros(n, dtype=np.uint8)
+    first, warm, steps = 0, 2, max(3, min(args.steps, 10))
+    res, wall, stage = [], [], {}
+    for i in range(warm + steps):
+        t0 = time.time()
+        r = g.round(first_sequence=first, ignore=ignore)
+        dt = time.time() - t0
+        first = r.next_first_sequence
+        if i >= warm:
+            res.append(r)
+            wall.append(dt)
+            for key in ("ms_select", "ms_queries", "ms_scan", "ms_chunk", "ms_index", "ms_lookup", "ms_align", "ms_collect"):
+                stage[key] = stage.get(key, 0.0) + getattr(r, key) / steps
+    g.close()
+    ms = 1e3 * sum(wall) / steps
+    dev_ms = sum(stage.values())
+    last = res[-1]
+    # the scan kernel: packed reads in, (position, seed) pairs + a sentinel per read out
+    scan_bytes = n * L / 4 + 8.0 * (last.read_seeds + n)
+    out = {"workload": "BASELINE config 5: %d simulated 10 kb ONT-like reads of the 4.6 Mb reference (%.0fx coverage), "
+                       "`downpore overlap` defaults (k 10, 15 seeds per query slice, 10000 seeds and 20000 queries per "
+                       "round); one step = one round up to the seed-match stream" % (n, n * L / 4.6e6),
+           "reads": n, "read_len": L, "n_gpus": 1, "steps": steps, "warmup": warm,
+           "value": n * L / (dev_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": dev_ms,
+           "e2e": {"value": n * L / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms,
+                   "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(last.num_hits * 24 + last.num_matches * 2),
+                   "entry": "dp_overlapper_round: ignore flags in, hit records and MatchA/MatchB lists out; wall clock of "
+                            "the call"},
+           "rounds_per_s": 1e3 / ms, "queries_per_round": int(last.num_queries), "hits_per_round": int(last.num_hits),
+           "chunks": int(last.num_chunks), "read_seeds": int(last.read_seeds), "seed_postings": int(last.seed_postings),
+           "posting_entries": int(last.posting_entries), "candidates": int(last.candidates), "pairs": int(last.pairs),
+           "stage_ms": stage, "create_s": create_s, "kmer_values_s": values_s, "gpu_launches": int(last.kernel_launches),
+           "roofline": {"kernel": "ov_scan_kernel (AddSequences: NewSeedSequence over every read)", "bound": "shared memory / issue",
+                        "achieved": scan_bytes / (stage["ms_scan"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": scan_bytes / (stage["ms_scan"] * 1e-3) / 1e9 / peak,
+                        "note": "algorithmic bytes = packed reads (1/4 B per base) + 8 B per seed occurrence and per read; "
+                                "the kernel's limiter is the seed-flag lookup in shared memory (one per base), see "
+                                "profiles/"},
+           "note": "rounds of a run are sequential (each round's ignore flags come from the host's consensus step over "
+                   "the previous round's hits); a full run over this read set is about reads / 167 rounds"}
+    if po is not None and args.overlap_cpu_reads > 0:
+        m = min(args.overlap_cpu_reads, n)
+        ov = po.overlap_values(rd[: m * L], offs[: m + 1], 10)
+        t0 = time.time()
+        o = po.OverlapRound(rd[: m * L], offs[: m + 1], ov)
+        dt = time.time() - t0
+        g2 = dp.Overlapper(rd[: m * L], offs[: m + 1], ov, device=device)
+        r2 = g2.round()
+        same = (int(r2.num_hits) == o.num_hits and int(r2.num_chunks) == o.num_chunks and all(
+            (a[0], a[1], a[2]) == (h["query_id"], h["rc"], h["target"]) and np.array_equal(a[3], h["match_a"])
+            and np.array_equal(a[4], h["match_b"]) for a, h in zip((r2.hit(i) for i in range(int(r2.num_hits))), o.hits)))
+        g2.close()
+        out["cpu_baseline"] = {"value": m * L / dt / 1e9, "unit": "Gbp/s", "cores": 1, "kind": "port",
+                               "sample": "one round over the first %d reads (the oracle's round is single-threaded: the "
+                                         "canonical num_workers = 1 order)" % m,
+                               "ms_per_round": 1e3 * dt, "gpu_ms_per_round_same_sample": r2.ms_total,
+                               "parity_with_gpu_on_sample": bool(same)}
+    return out
+
+
 def run_ours(args):
     import torch
     rank, world, local = dist_setup(args.gpus)
@@ -646,11 +723,26 @@ def run_ours(args):
                                                    affinity_before)
             except Exception as ex:
                 configs["config4"] = {"error": str(ex)}
+    if rank == 0 and world == 1 and args.workload == "config2" and not args.no_side_configs and args.overlap_reads > 0:
+        try:
+            configs["config5"] = overlap_workload(dp, synth, po, args, local, cores, peak)
+        except Exception as ex:
+            configs["config5"] = {"error": str(ex)}
     if configs:
         line["configs"] = configs
         for cname, c in configs.items():  # flat copies where the driver's parser keeps them
             if "error" in c:
                 roofline["%s_error" % cname] = c["error"]
+                continue
+            if cname == "config5":
+                roofline["config5_value_Gbps"] = c["value"]
+                roofline["config5_e2e_Gbps"] = c["e2e"]["value"]
+                roofline["config5_ms_per_round"] = c["ms_per_step"]
+                roofline["config5_reads"] = c["reads"]
+                roofline["config5_scan_frac"] = c["roofline"]["frac"]
+                if "cpu_baseline" in c:
+                    roofline["config5_cpu_Gbps"] = c["cpu_baseline"]["value"]
+                    roofline["config5_parity_on_sample"] = c["cpu_baseline"]["parity_with_gpu_on_sample"]
                 continue
             roofline["%s_value_Gbps" % cname] = c["value"]
             roofline["%s_e2e_Gbps" % cname] = c["e2e"]["value"]
@@ -703,6 +795,9 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true", help="skip BASELINE configs 3 (every N) and 4 (N = 8) after the headline workload")
     ap.add_argument("--config4", action="store_true", help="also run BASELINE config 4 (3.1 Gb reference) below eight GPUs")
     ap.add_argument("--side-reads", type=int, default=0, help="reads per GPU per step of the side configs (default: their own)")
+    ap.add_argument("--overlap-reads", type=int, default=int(os.environ.get("DP_BENCH_OVERLAP_READS", 500_000)),
+                    help="reads of BASELINE config 5 (`overlap`, N = 1 only; 0 skips it)")
+    ap.add_argument("--overlap-cpu-reads", type=int, default=20_000, help="reads of the oracle's overlap round (cpu_baseline)")
     ap.add_argument("--no-hbm-regime", action="store_true", help="skip the lookup measurement on the 3.1 Gb reference (BASELINE config 4)")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "rebuild"],
                     help="N>1: replicate rank 0's index by one NCCL broadcast (default) or rebuild it on every rank")

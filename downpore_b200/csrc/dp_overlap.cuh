@@ -3,7 +3,7 @@
 // FindOverlaps / matchWorker (:320-387).
 //
 // Where the reference leaves an order to the goroutine scheduler the canonical choice is num_workers = 1 (the order
-// oracle/overlap.cpp states): reads in file order, chunks numbered in emission order, queries in slice order with the
+// the test oracle states): reads in file order, chunks numbered in emission order, queries in slice order with the
 // forward query in front of its reverse complement, candidates in ascending chunk order.
 //
 // Data in HBM for one round
