@@ -34,6 +34,69 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Large result arrays are recycled through dp_free: a fresh 40 MB malloc per call costs ten thousand page faults on the
+// threads that fill it (milliseconds of a 20 ms step). Blocks of a megabyte and more that come back through dp_free are
+// kept (a handful, bounded in bytes) and handed out again with their pages in place; everything else is plain malloc/free.
+struct ResultBlocks {
+    struct Block {
+        void* p;
+        size_t bytes;
+    };
+    std::mutex mu;
+    std::vector<Block> live, idle;
+    size_t idleBytes = 0;
+};
+ResultBlocks& result_blocks() {
+    static ResultBlocks* rb = new ResultBlocks();  // (never destroyed: dp_free may run from finalisers at exit)
+    return *rb;
+}
+const size_t kResultBlockMin = 1u << 20, kResultIdleMax = 8, kResultIdleBytes = 2ull << 30;
+
+void* result_alloc(size_t bytes) {
+    if (bytes < kResultBlockMin) return malloc(bytes ? bytes : 1);
+    ResultBlocks& rb = result_blocks();
+    {
+        std::lock_guard<std::mutex> lk(rb.mu);
+        size_t best = rb.idle.size();
+        for (size_t i = 0; i < rb.idle.size(); i++)
+            if (rb.idle[i].bytes >= bytes && rb.idle[i].bytes / 4 <= bytes && (best == rb.idle.size() || rb.idle[i].bytes < rb.idle[best].bytes))
+                best = i;
+        if (best < rb.idle.size()) {
+            const ResultBlocks::Block b = rb.idle[best];
+            rb.idle.erase(rb.idle.begin() + (long)best);
+            rb.idleBytes -= b.bytes;
+            rb.live.push_back(b);
+            return b.p;
+        }
+    }
+    void* p = malloc(bytes);
+    if (p) {
+        std::lock_guard<std::mutex> lk(rb.mu);
+        rb.live.push_back({p, bytes});
+    }
+    return p;
+}
+
+void result_free(void* p) {
+    if (!p) return;
+    ResultBlocks& rb = result_blocks();
+    {
+        std::lock_guard<std::mutex> lk(rb.mu);
+        for (size_t i = 0; i < rb.live.size(); i++)
+            if (rb.live[i].p == p) {
+                const ResultBlocks::Block b = rb.live[i];
+                rb.live.erase(rb.live.begin() + (long)i);
+                if (rb.idle.size() < kResultIdleMax && rb.idleBytes + b.bytes <= kResultIdleBytes) {
+                    rb.idle.push_back(b);
+                    rb.idleBytes += b.bytes;
+                    return;
+                }
+                break;
+            }
+    }
+    free(p);
+}
+
 }  // namespace
 
 // Per-lane workspace: one stream plus every buffer a sub-batch needs. Two lanes let the host work of one sub-batch
@@ -130,6 +193,8 @@ struct dp_mapper {
     // into lock step: both wait on the link, then both wait on the SMs).
     cudaStream_t pullStream = nullptr;
     std::mutex pullMu;
+    cudaEvent_t evTrace = nullptr;  // DP_TRACE: time zero of the call's device timeline (recorded on the pull stream)
+    double traceHost0 = 0;
     // parameters
     int k = 0, circular = 0, seedRate = 0, edge = 0, chunkSize = 0;
     long long refLen = 0;
@@ -155,9 +220,13 @@ struct dp_mapper {
     std::mutex laneMu;
     std::condition_variable laneCv;
     dp_stats stats{};  // of the call that finished last (guarded by laneMu)
+    // blocks the sub-batches' records are assembled in, kept between sub-batches and calls (no fresh pages per call)
+    std::vector<std::vector<dp_mapping>> spare;
+    std::mutex spareMu;
 
     ~dp_mapper() {
         lanes.clear();
+        if (evTrace) cudaEventDestroy(evTrace);
         if (pullStream) cudaStreamDestroy(pullStream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -702,7 +771,7 @@ void ensure_window_capacity(dp_mapper& M, Lane& W, size_t nWinNow, size_t seedEn
     W.fcSlowList.reserve(nWin);
 }
 
-enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_REDUCE, T_N };
+enum { T_PACK = 0, T_EXTRACT, T_LOOKUP, T_CHAIN, T_FINISH, T_REDUCE, T_PULL, T_N };
 enum { CUR_SEEDS = 0, CUR_OUT = 1, CUR_FIN = 2 };
 
 // Launches the three performMapping stages for the `nWin` windows already in W.dWins (device). Results stay on the
@@ -744,6 +813,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                     W.curAscii, W.dSeqOff.p, W.dByteOff.p, true, W.dWins.p, (int)nWin, W.dStage.p, pkStride, W.dStagePos.p,
                     W.dPullWork.p);
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(W.timers[T_PULL].b, M.pullStream));
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
             CK(cudaStreamWaitEvent(st, W.evPulled, 0));
@@ -791,6 +861,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                     W.curAscii, W.dSeqOff.p, spanOff, false, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p,
                     W.dPullWork.p);
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(W.timers[T_PULL].b, M.pullStream));
                 CK(cudaEventRecord(W.evPulled, M.pullStream));
             }
             CK(cudaStreamWaitEvent(st, W.evPulled, 0));
@@ -1178,7 +1249,7 @@ inline size_t round0_seed_bound(long long len, int e, int minLen) {
 // capacities (W.caps). Returns 0 and fills counts[r0..r1) and `out` (ordered by read), or returns the DP_OV_* bits of
 // a capacity that was too small: nothing is delivered then and the caller reruns the range with more room (map_range).
 unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff,
-                      bool packed, int64_t r0, int64_t r1, int* counts, SubOut& out) {
+                      bool packed, int64_t r0, int64_t r1, int64_t* counts, SubOut& out) {
     const int64_t n = r1 - r0;
     cudaStream_t st = W.stream;
     const dp_stats before = W.stats;
@@ -1291,6 +1362,19 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         W.hp[2] += now_ms() - tw;
     }
     collect_stage_times(W);
+    if (M.evTrace) {  // DP_TRACE=1: the sub-batch's device timeline, ms since the call started
+        auto at = [&](cudaEvent_t e) {
+            float ms = -1;
+            if (cudaEventElapsedTime(&ms, M.evTrace, e) != cudaSuccess) cudaGetLastError();
+            return ms;
+        };
+        fprintf(stderr, "[dp trace] reads %lld+%lld host: enq %.2f synced %.2f | dev: pull %.2f-%.2f pack -%.2f extract %.2f-%.2f "
+                        "lookup -%.2f reduce -%.2f chain -%.2f finish %.2f-%.2f\n",
+                (long long)r0, (long long)n, t0 - M.traceHost0, now_ms() - M.traceHost0, at(W.timers[T_PACK].a),
+                at(W.timers[T_PULL].b), at(W.timers[T_PACK].b), at(W.timers[T_EXTRACT].a), at(W.timers[T_EXTRACT].b),
+                at(W.timers[T_LOOKUP].b), W.reduceTimed ? at(W.timers[T_REDUCE].b) : -1.f, at(W.timers[T_CHAIN].b),
+                at(W.timers[T_FINISH].a), at(W.timers[T_FINISH].b));
+    }
     {
         float ms;
         CK(cudaEventElapsedTime(&ms, W.timers[T_FINISH].a, W.timers[T_FINISH].b));
@@ -1416,10 +1500,10 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
             const size_t segEnd = fOff[u];  // finished reads [prevRead, u): one block
             if (segEnd > src) memcpy(out.maps.data() + pos, fin + src, (segEnd - src) * sizeof(dp_mapping));
             pos += segEnd - src;
-            for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int)(fOff[i + 1] - fOff[i]);
+            for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int64_t)(fOff[i + 1] - fOff[i]);
             if (a == nUn) break;
             const std::vector<dph::Hit>& v = late[(size_t)a];
-            counts[r0 + u] = (int)v.size();
+            counts[r0 + u] = (int64_t)v.size();
             for (const dph::Hit& h : v) out.maps[pos++] = to_abi(h);
             src = fOff[u + 1];
             delta += (long long)v.size() - (long long)(fOff[u + 1] - fOff[u]);
@@ -1449,7 +1533,7 @@ Caps default_caps() {
 // first (a single read always fits: a window strand has at most C candidates). The lane's capacities return to their
 // defaults afterwards (the buffers stay grown).
 void map_range(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff, bool packed,
-               int64_t r0, int64_t r1, int* counts, SubOut& out) {
+               int64_t r0, int64_t r1, int64_t* counts, SubOut& out) {
     const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);  // (tests: 0 = single reads)
     for (;;) {
         const int64_t n = r1 - r0;
@@ -1597,6 +1681,18 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     const int64_t* srcOff = byteOff ? byteOff : offsets;  // where a read starts in the caller's buffer
     CK(cudaSetDevice(M.device));
     double tStart = now_ms();
+    const bool trace = getenv("DP_TRACE") != nullptr;
+    if (trace) {
+        if (!M.evTrace) CK(cudaEventCreate(&M.evTrace));
+        CK(cudaEventRecord(M.evTrace, M.pullStream));
+        M.traceHost0 = tStart;
+    } else if (M.evTrace) {
+        cudaEventDestroy(M.evTrace);
+        M.evTrace = nullptr;
+    }
+    auto mark = [&](const char* what) {
+        if (trace) fprintf(stderr, "[dp trace] host %.2f ms: %s\n", now_ms() - tStart, what);
+    };
     // sub-batch boundaries. Sizes ramp up at the start and down at the end: the first pull / first kernels start
     // (and the last host pass ends) on a quarter-size piece, so less of the pipeline's fill and drain is exposed.
     std::vector<int64_t> cuts;
@@ -1604,7 +1700,8 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     size_t floorReads = 0, floorBytes = 0, floorSeeds = 0;  // the largest sub-batch: what every lane sizes its buffers for
     {
         const bool ramp = !(getenv("DP_RAMP") && atoi(getenv("DP_RAMP")) == 0);  // DP_RAMP=0: equal pieces (profiling)
-        const int64_t full = kSubBatchReads, tail = ramp ? full / 4 + full / 2 : 0;
+        const int64_t full = std::max<int64_t>(4, std::min<int64_t>(kSubBatchReads, env_int("DP_SUB_READS", (int)kSubBatchReads)));  // (tests: many small sub-batches)
+        const int64_t tail = ramp ? full / 4 + full / 2 : 0;
         int idx = ramp ? 0 : 2;
         for (int64_t r0 = 0; r0 < n_reads; idx++) {
             int64_t remaining = n_reads - r0;
@@ -1616,7 +1713,16 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
             // seed lists, 32-bit offsets — large query_size values cut smaller sub-batches instead of failing)
             int64_t r1 = r0;
             size_t seedBound = 0;
-            while (r1 < n_reads && r1 - r0 < want && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) {
+            // (no read's round-0 windows produce more than 4 * (e + 2) entries: when the piece fits both limits by that
+            // bound it is cut without looking at its reads — a million offsets walked one by one cost a millisecond
+            // before the first kernel of the call could start)
+            const int64_t rq = std::min<int64_t>(n_reads, r0 + want);
+            const size_t quick = (size_t)(rq - r0) * 4 * (size_t)(M.edge + 2);
+            if (offsets[rq] - offsets[r0] <= kSubBatchBytes && quick <= kSubBatchSeedEntries) {
+                r1 = rq;
+                seedBound = quick;
+            }
+            while (r1 < rq && offsets[r1 + 1] - offsets[r0] <= kSubBatchBytes) {
                 seedBound += round0_seed_bound(offsets[r1 + 1] - offsets[r1], M.edge, M.k + 12);
                 if (seedBound > kSubBatchSeedEntries && r1 > r0) break;
                 r1++;
@@ -1630,6 +1736,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
             r0 = r1;
         }
     }
+    mark("sub-batch cuts done");
     const size_t nSub = cuts.size() - 1;
     LaneSet held(M, std::min<size_t>((size_t)lane_count(), std::max<size_t>(nSub, 1)));
     const int nLanes = (int)held.lanes.size();
@@ -1656,10 +1763,71 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         W.floorBytes = floorBytes;
         W.floorSeeds = floorSeeds;
     }
-    std::vector<int> counts((size_t)n_reads + 1, 0);
     std::vector<SubOut> subs(nSub);
     std::atomic<size_t> nextSub(0);
     std::vector<std::string> errs((size_t)nLanes);
+    // The result arrays are filled while the call runs: a sub-batch is copied to its place as soon as every sub-batch
+    // in front of it has reported its size (by the lane thread that closes the gap), so nothing is left to concatenate
+    // when the last lane finishes. Room for two records per read is reserved up front (untouched pages cost nothing);
+    // a batch that needs more (repeat-rich reads) is finished the slow way below.
+    struct {
+        std::mutex mu;
+        std::vector<char> done;
+        size_t frontier = 0;       // first sub-batch that has not been given its place
+        int64_t frontierBase = 0;  // records in front of it
+        bool spilled = false;
+    } pl;
+    pl.done.assign(nSub, 0);
+    size_t mapsCap = (size_t)n_reads * 2 + 4096;
+    if (getenv("DP_RESULT_CAP")) mapsCap = (size_t)std::max(1, env_int("DP_RESULT_CAP", 1));  // (tests: force the slow way)
+    // (off[i] holds read i's record COUNT, written by the lane that maps it, until its sub-batch is given its place)
+    int64_t* off = (int64_t*)result_alloc(sizeof(int64_t) * ((size_t)n_reads + 1));
+    dp_mapping* maps = (dp_mapping*)result_alloc(sizeof(dp_mapping) * mapsCap);
+    if (!off || !maps) {
+        dp_free(off);
+        dp_free(maps);
+        throw std::runtime_error("out of host memory for the result");
+    }
+    std::atomic<int> bad(0);
+    auto place_one = [&](size_t sI, int64_t base) {
+        if (!subs[sI].maps.empty()) memcpy(maps + base, subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
+        int64_t run = base;
+        for (int64_t i = cuts[sI]; i < cuts[sI + 1]; i++) {
+            const int64_t c = off[i];
+            off[i] = run;
+            run += c;
+        }
+        if (run != base + (int64_t)subs[sI].maps.size()) bad.store(1);
+        subs[sI].maps.clear();  // the block goes back to the mapper for the next sub-batch (of this or a later call)
+        std::lock_guard<std::mutex> lk(M.spareMu);
+        if (M.spare.size() < 2 * kMaxLanes) M.spare.push_back(std::move(subs[sI].maps));
+        std::vector<dp_mapping>().swap(subs[sI].maps);
+    };
+    auto deliver = [&](size_t sI) {
+        size_t first = 0, last = 0;
+        int64_t base = 0;
+        {
+            std::lock_guard<std::mutex> lk(pl.mu);
+            pl.done[sI] = 1;
+            first = last = pl.frontier;
+            base = pl.frontierBase;
+            while (last < nSub && pl.done[last] && !pl.spilled) {
+                const int64_t t = (int64_t)subs[last].maps.size();
+                if ((size_t)(pl.frontierBase + t) > mapsCap) {
+                    pl.spilled = true;
+                    break;
+                }
+                pl.frontierBase += t;
+                last++;
+            }
+            pl.frontier = last;
+        }
+        for (size_t q = first; q < last; q++) {
+            const int64_t t = (int64_t)subs[q].maps.size();
+            place_one(q, base);
+            base += t;
+        }
+    };
     auto work = [&](int l) {
         try {
             CK(cudaSetDevice(M.device));
@@ -1681,8 +1849,18 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
                     dA = devBases + srcOff[r0];
                 }
                 W.caps = default_caps();
-                map_range(M, W, dA, offsets, byteOff, packed, r0, r1, counts.data(), subs[sI]);
+                {
+                    std::lock_guard<std::mutex> lk(M.spareMu);
+                    if (!M.spare.empty()) {
+                        subs[sI].maps = std::move(M.spare.back());
+                        M.spare.pop_back();
+                    }
+                }
+                map_range(M, W, dA, offsets, byteOff, packed, r0, r1, off, subs[sI]);
                 W.caps = default_caps();
+                const double tp = now_ms();
+                deliver(sI);
+                W.hp[5] += now_ms() - tp;
             }
             lane_sync(W);
         } catch (const std::exception& ex) {
@@ -1690,44 +1868,42 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
             if (errs[(size_t)l].empty()) errs[(size_t)l] = "unknown error";
         }
     };
+    mark("lanes start");
     std::vector<std::thread> th;
     for (int l = 1; l < nLanes; l++) th.emplace_back(work, l);
     work(0);
     for (auto& t : th) t.join();
+    mark("lanes joined");
     for (auto& e : errs)
-        if (!e.empty()) throw std::runtime_error(e);
-    // ---- concatenate (the lanes' threads copy their sub-batches into place in parallel) ----
-    std::vector<int64_t> subBase(nSub + 1, 0);
-    for (size_t sI = 0; sI < nSub; sI++) subBase[sI + 1] = subBase[sI] + (int64_t)subs[sI].maps.size();
-    const int64_t total = subBase[nSub];
-    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_reads + 1));
-    dp_mapping* maps = (dp_mapping*)malloc(sizeof(dp_mapping) * (size_t)(total ? total : 1));
-    if (!off || !maps) {
-        free(off);
-        free(maps);
-        throw std::runtime_error("out of host memory for the result");
-    }
-    std::atomic<int> bad(0);
-    auto place = [&](int t) {
-        for (size_t sI = (size_t)t; sI < nSub; sI += (size_t)nLanes) {
-            if (!subs[sI].maps.empty())
-                memcpy(maps + subBase[sI], subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
-            int64_t run = subBase[sI];
-            for (int64_t i = cuts[sI]; i < cuts[sI + 1]; i++) {
-                off[i] = run;
-                run += counts[(size_t)i];
-            }
-            if (run != subBase[sI + 1]) bad.store(1);
+        if (!e.empty()) {
+            dp_free(maps);
+            dp_free(off);
+            throw std::runtime_error(e);
         }
-    };
-    th.clear();
-    for (int l = 1; l < nLanes; l++) th.emplace_back(place, l);
-    place(0);
-    for (auto& t : th) t.join();
+    int64_t total = pl.frontierBase;
+    if (pl.frontier < nSub) {  // more than two records per read: the rest is placed now, in an array of the exact size
+        for (size_t sI = pl.frontier; sI < nSub; sI++) total += (int64_t)subs[sI].maps.size();
+        dp_mapping* grown = (dp_mapping*)result_alloc(sizeof(dp_mapping) * (size_t)(total ? total : 1));
+        if (!grown) {
+            dp_free(maps);
+            dp_free(off);
+            throw std::runtime_error("out of host memory for the result");
+        }
+        if (pl.frontierBase) memcpy(grown, maps, sizeof(dp_mapping) * (size_t)pl.frontierBase);
+        dp_free(maps);
+        maps = grown;
+        int64_t base = pl.frontierBase;
+        for (size_t sI = pl.frontier; sI < nSub; sI++) {
+            const int64_t t = (int64_t)subs[sI].maps.size();
+            place_one(sI, base);
+            base += t;
+        }
+    }
     off[n_reads] = total;
+    mark("results in place");
     if (bad.load()) {
-        free(maps);
-        free(off);
+        dp_free(maps);
+        dp_free(off);
         throw std::runtime_error("internal error: result assembly mismatch");
     }
     if (getenv("DP_HOST_PROFILE")) {  // where the lanes' host threads spent the call (ms, summed over sub-batches)
@@ -1892,7 +2068,7 @@ extern "C" {
 
 const char* dp_last_error(void) { return g_err.c_str(); }
 const char* dp_version(void) { return "downpore_b200 0.2 (sm_100a)"; }
-void dp_free(void* p) { free(p); }
+void dp_free(void* p) { result_free(p); }
 
 int dp_host_alloc(void** out, size_t bytes) {
     API_TRY

@@ -12,7 +12,8 @@
  *   - every function returns 0 on success, non-zero on failure; dp_last_error() returns a thread-local message
  *     (the reference only log.Fatal()s / panics on this path, so every error is fatal to the host);
  *   - input buffers are borrowed for the duration of the call only (cgo rule: no Go pointer is retained);
- *   - output buffers are allocated by the library with malloc() and released with dp_free();
+ *   - output buffers are allocated by the library and released with dp_free() — never free(): the large result arrays
+ *     of the batch entry points are recycled through it (pages stay mapped from one call to the next);
  *   - a dp_mapper is bound to one CUDA device; create one per GPU and shard read batches across them
  *     (reads are independent: commands/map.go:84-86). The batch entry points may be called from several threads at once
  *     on one mapper, as the reference's num_workers goroutines call Mapper.Map (each call works on its own lanes — a

@@ -212,6 +212,21 @@ def test_packed_reads_entry_point(pair):
         assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), mode
 
 
+def test_result_delivery_in_pieces(pair):
+    """A batch cut into many sub-batches (six lanes finishing them out of order) is delivered in read order, also when the
+    result outgrows the room reserved up front and the rest is placed after the lanes have finished."""
+    ref, circular, om, gm = pair
+    reads = mixed_reads(ref, circular, seed=71, n=260, rl=3000)
+    bases, offs = make_golden.concat(reads)
+    orow, ooff, _ = om.map_batch(bases, offs, threads=4)
+    for env in ({"DP_SUB_READS": "16"}, {"DP_SUB_READS": "16", "DP_RESULT_CAP": "40"}, {"DP_SUB_READS": "7", "DP_LANES": "3"},
+                {"DP_SUB_READS": "64", "DP_RESULT_CAP": "1"}):
+        with _Env(env):
+            for _ in range(3):
+                maps, off = gm.map_batch(bases, offs)
+                assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), env
+
+
 def test_concurrent_callers_of_one_mapper(pair):
     """The reference runs num_workers goroutines against one Mapper (commands/map.go:84-86): several threads may call
     dp_mapper_map_batch on one mapper at once (each call works on its own lanes) and get what a lone caller gets."""
