@@ -20,10 +20,10 @@
 #include "dp_common.cuh"
 #include "dp_host.hpp"
 #include "dp_finish.cuh"
-#include "dp_host_map.hpp"
 #include "dp_index.cuh"
 #include "dp_io.cuh"
 #include "dp_map.cuh"
+#include "dp_rounds.cuh"
 
 namespace {
 
@@ -109,6 +109,7 @@ struct Caps {
     int resultCap = 128;        // mappings of one window before sort/dedupe (general chain kernel)
     int chainCap = 64;          // chains kept for one candidate (general chain kernel)
     unsigned candStride = 1024; // candidate chunks per window strand (min(C, .))
+    int roundsScale = 1;        // later rounds of Map(): scratch per read and window cache, in units of their defaults
 };
 const int kCapMax = 1 << 20;
 
@@ -156,6 +157,17 @@ struct Lane {
     HBuf<unsigned char> hStage;
     HBuf<DpUnresolved> hUnres;
     DBuf<DpUnresolved> dUnres;
+    // later rounds of Map() on the device (dp_rounds.cuh): window cache, requests, results, per-thread scratch
+    DBuf<int> rdHead, rdWinSlot, rdResN, rdLists;
+    DBuf<int4> rdEnt;
+    DBuf<int2> rdEnt2;
+    DBuf<DpMappingDev> rdCache, rdResMaps;
+    DBuf<unsigned char> rdDone;
+    DBuf<unsigned> rdResOff, rdCur;
+    DBuf<DpHit> rdHits;
+    HBuf<unsigned> hRdCur, hRdResOff;
+    HBuf<int> hRdResN;
+    HBuf<DpMappingDev> hRdResMaps;
     HBuf<DpMappingDev> hOutMaps, hFinMaps;
     HBuf<long long> hRel;
     size_t hOutTotal = 0;
@@ -1208,6 +1220,10 @@ bool grow_caps(Caps& c, unsigned bits, unsigned numChunks) {
     if (bits & DP_OV_OUTPOOL) up(c.outStride);
     if (bits & DP_OV_RESULTS) up(c.resultCap);
     if (bits & DP_OV_CHAINS) up(c.chainCap);
+    if (bits & DP_OV_ROUNDS) {
+        if (c.roundsScale >= 4096) ok = false;
+        c.roundsScale = std::min(c.roundsScale * 4, 4096);
+    }
     if (bits & DP_OV_CANDS) {
         if (c.candStride >= numChunks) ok = false;  // (a window strand has at most C candidates)
         c.candStride = (unsigned)std::min<unsigned long long>((unsigned long long)c.candStride * 4, numChunks);
@@ -1215,26 +1231,10 @@ bool grow_caps(Caps& c, unsigned bits, unsigned numChunks) {
     return ok;
 }
 
-struct ReadCache {
-    std::vector<dph::WinRef> wins;
-};
-
 // Output of one sub-batch: mappings grouped per read in input order.
 struct SubOut {
     std::vector<dp_mapping> maps;
 };
-
-inline dp_mapping to_abi(const dph::Hit& h) {
-    dp_mapping m;
-    memset(&m, 0, sizeof(m));
-    m.start = h.start;
-    m.end = h.end;
-    m.q_offset = (int32_t)h.qOffset;
-    m.q_inset = (int32_t)h.qInset;
-    m.ids = (int32_t)h.ids;
-    m.rc = h.rc ? 1 : 0;
-    return m;
-}
 
 static_assert(sizeof(dp_mapping) == sizeof(DpMappingDev), "ABI record and device record share one layout");
 
@@ -1243,6 +1243,103 @@ static_assert(sizeof(dp_mapping) == sizeof(DpMappingDev), "ABI record and device
 inline size_t round0_seed_bound(long long len, int e, int minLen) {
     if (len < minLen) return 0;
     return len <= 2ll * e ? 2 * (size_t)(len + 2) : 4 * (size_t)(e + 2);
+}
+
+// Later rounds of Mapper.Map for the `nUn` reads round 0 left open (W.dUnres), entirely on the device: strategy kernel
+// (one replay of Map() per open read against its window cache) -> the windows it asks for, through the same window
+// kernels as round 0 -> collect kernel -> strategy kernel again, until no read asks for a window. Per round the host
+// reads one counter block; the reads' final records arrive in W.hRdResN / hRdResOff / hRdResMaps (indexed by slot =
+// position in W.dUnres). Returns the overflow bits of a capacity that was too small (nothing is delivered then).
+unsigned rounds_on_device(dp_mapper& M, Lane& W, int nUn, int64_t n, int minLen) {
+    cudaStream_t st = W.stream;
+    const size_t scale = (size_t)W.caps.roundsScale;
+    const int e = M.edge;
+    const size_t slots = std::max<size_t>((size_t)nUn, 64);
+    const int nThreads = (int)std::min<size_t>((slots + 63) / 64 * 64, 4096);
+    DpRoundsDev R;
+    memset(&R, 0, sizeof(R));
+    // (DP_ROUNDS_HITS / DP_ROUNDS_LIST / DP_ROUNDS_CACHE: tests start from tiny capacities to walk the retries)
+    R.hitCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_HITS", 256)) * scale, 1u << 20);
+    R.listCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_LIST", 128)) * scale, 1u << 20);
+    R.entCap = (unsigned)std::min<size_t>((32 * slots + 64) * scale, 0x7fffffffu);
+    R.cacheCap = (unsigned)std::min<size_t>(((size_t)std::max(1, env_int("DP_ROUNDS_CACHE", 256)) * slots + 4096) * scale, 0xfffffff0u);
+    R.resCap = (unsigned)std::min<size_t>((16 * slots + 1024) * scale, 0xfffffff0u);
+    W.rdHead.reserve(slots);
+    W.rdEnt.reserve(R.entCap);
+    W.rdEnt2.reserve(R.entCap);
+    W.rdCache.reserve(R.cacheCap);
+    W.rdWinSlot.reserve(W.dWins.cap);
+    W.rdDone.reserve(slots);
+    W.rdResN.reserve(slots);
+    W.rdResOff.reserve(slots);
+    W.rdResMaps.reserve(R.resCap);
+    W.rdHits.reserve((size_t)nThreads * R.hitCap);
+    W.rdLists.reserve((size_t)nThreads * DP_RL_LISTS * R.listCap);
+    W.rdCur.reserve(DP_RC_N);
+    W.hRdCur.reserve(DP_RC_N);
+    W.hRdResN.reserve(slots);
+    W.hRdResOff.reserve(slots);
+    R.unres = W.dUnres.p;
+    R.nSlots = nUn;
+    R.readLen = W.dReadLen.p;
+    R.head = W.rdHead.p;
+    R.ent = W.rdEnt.p;
+    R.ent2 = W.rdEnt2.p;
+    R.cacheMaps = W.rdCache.p;
+    R.wins = W.dWins.p;
+    R.winSlot = W.rdWinSlot.p;
+    R.winCap = (unsigned)std::min<size_t>(W.dWins.cap, (size_t)2 * (size_t)n);  // (a replay asks for at most two windows)
+    R.done = W.rdDone.p;
+    R.resN = W.rdResN.p;
+    R.resOff = W.rdResOff.p;
+    R.resMaps = W.rdResMaps.p;
+    R.hits = W.rdHits.p;
+    R.lists = W.rdLists.p;
+    R.cur = W.rdCur.p;
+    R.edge = e;
+    R.circular = M.circular;
+    R.refLen = M.refLen;
+    CK(cudaMemsetAsync(W.rdCur.p, 0, DP_RC_N * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(W.rdHead.p, 0xff, (size_t)nUn * sizeof(int), st));
+    dp_rounds_seed_kernel<<<div_up(nUn, 128), 128, 0, st>>>(R, minLen, W.outN.p, W.outOff.p, W.outMaps.p);
+    CK(cudaGetLastError());
+    W.stats.kernel_launches += 1;
+    for (;;) {
+        CK(cudaMemsetAsync(W.rdCur.p + DP_RC_REQ, 0, sizeof(unsigned), st));
+        CK(cudaMemsetAsync(W.rdCur.p + DP_RC_OPEN, 0, 3 * sizeof(unsigned), st));  // open reads, summed window lengths
+        dp_rounds_replay_kernel<<<nThreads / 64, 64, 0, st>>>(R, minLen);
+        CK(cudaGetLastError());
+        W.stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(W.hRdCur.p, W.rdCur.p, DP_RC_N * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(W.hCtr.p, W.dCtr.p, sizeof(DpCounters), cudaMemcpyDeviceToHost, st));
+        {
+            const double tw = now_ms();
+            lane_sync(W);
+            W.hp[2] += now_ms() - tw;
+        }
+        collect_stage_times(W);
+        if (W.hCtr.p->overflow) return W.hCtr.p->overflow;  // (of the window launch in front of this replay)
+        if (W.hRdCur.p[DP_RC_OVF]) return DP_OV_ROUNDS;
+        const size_t nReq = W.hRdCur.p[DP_RC_REQ];
+        if (nReq == 0) break;
+        if (nReq > R.winCap) throw std::runtime_error("internal error: more window requests than two per open read");
+        const unsigned long long lenSum = (unsigned long long)W.hRdCur.p[DP_RC_LEN_LO] | ((unsigned long long)W.hRdCur.p[DP_RC_LEN_HI] << 32);
+        const size_t seedEntries = 2 * ((size_t)lenSum + 2 * nReq);
+        ensure_window_capacity(M, W, nReq, seedEntries);
+        if (W.curAsciiIsHost) W.stats.h2d_bytes += (int64_t)(W.curPacked ? lenSum / 4 + 32 * nReq : lenSum + 32 * nReq);
+        launch_windows(M, W, nReq, seedEntries, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
+        dp_rounds_collect_kernel<<<div_up((long long)nReq, 128), 128, 0, st>>>(R, (int)nReq, W.outN.p, W.outOff.p, W.outMaps.p,
+                                                                              (unsigned long long)nReq * W.caps.outStride);
+        CK(cudaGetLastError());
+        W.stats.kernel_launches += 1;
+    }
+    const size_t total = W.hRdCur.p[DP_RC_RES];
+    W.hRdResMaps.reserve(total + 1);
+    CK(cudaMemcpyAsync(W.hRdResN.p, W.rdResN.p, (size_t)nUn * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(W.hRdResOff.p, W.rdResOff.p, (size_t)nUn * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (total) CK(cudaMemcpyAsync(W.hRdResMaps.p, W.rdResMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+    lane_sync(W);
+    return 0;
 }
 
 // Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device, with the lane's current
@@ -1403,113 +1500,49 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     } else if (nUn > 0) {
         memcpy(unres.data(), W.hUnres.p, (size_t)nUn * sizeof(DpUnresolved));
     }
-    std::sort(unres.begin(), unres.end(), [](const DpUnresolved& x, const DpUnresolved& y) { return x.read < y.read; });
     W.stats.short_reads += nShort;
     W.stats.ms_host_logic += now_ms() - t0;
     W.hp[3] += now_ms() - t0;
-    const double tReplay = now_ms();
+    const double tRounds = now_ms();
 
-    // ---- unresolved reads: replay Map() on the host against cached window results, round by round ----
-    std::vector<std::vector<dph::Hit>> late((size_t)nUn);
+    // ---- unresolved reads: the later rounds of Map() on the device (dp_rounds.cuh) ----
     if (nUn > 0) {
-        t0 = now_ms();
-        std::vector<ReadCache> cache((size_t)nUn);
-        std::vector<int> slotOf((size_t)n, -1);  // read index -> slot in `cache` / `late`
-        std::vector<std::vector<DpMappingDev>> roundMaps;  // window results must outlive the replays
-        std::vector<int> todo((size_t)nUn);
-        for (int a = 0; a < nUn; a++) {
-            const int i = unres[(size_t)a].read;
-            todo[(size_t)a] = i;
-            slotOf[(size_t)i] = a;
-            const long long len = W.hRel.p[i + 1] - W.hRel.p[i];
-            const int nA = unres[(size_t)a].nA, nB = unres[(size_t)a].nB;
-            for (int s2 = 0; s2 < 2; s2++) {
-                dph::WinRef ref;
-                if (len <= 2ll * e) {
-                    if (s2 == 1) continue;
-                    ref.start = 0;
-                    ref.len = (int)len;
-                    ref.whole = 1;
-                } else {
-                    ref.start = s2 == 0 ? 0 : (int)(len - e);
-                    ref.len = e;
-                    ref.whole = 0;
-                }
-                ref.n = s2 == 0 ? nA : nB;  // raw window hits delivered by the finish kernel
-                ref.maps = W.hFinMaps.p + fOff[i] + (s2 == 0 ? 0 : nA);
-                cache[(size_t)a].wins.push_back(ref);
-            }
-        }
-        dph::Params P;
-        P.refLen = M.refLen;
-        P.edge = e;
-        P.circular = M.circular != 0;
-        dph::ReadMapper rm(P);
-        W.stats.ms_host_logic += now_ms() - t0;
-        while (!todo.empty()) {
-            t0 = now_ms();
-            std::vector<DpWindow> wins;
-            std::vector<int> next;
-            for (int i : todo) {
-                int slot = slotOf[(size_t)i];
-                const ReadCache& rc = cache[(size_t)slot];
-                long long len = W.hRel.p[i + 1] - W.hRel.p[i];
-                bool done = rm.run(i, len, rc.wins.data(), (int)rc.wins.size(), wins, late[(size_t)slot]);
-                if (!done) next.push_back(i);
-            }
-            W.stats.ms_host_logic += now_ms() - t0;
-            if (wins.empty()) break;
-            if (unsigned ov = run_windows(M, W, wins.data(), wins.size(), W.dWords.p, W.dWordOff.p, W.dReadLen.p)) {
-                forget_attempt(W, before);
-                W.stats.short_reads -= nShort;
-                return ov;
-            }
-            t0 = now_ms();
-            roundMaps.emplace_back();
-            std::vector<DpMappingDev>& keep = roundMaps.back();
-            keep.assign(W.hOutMaps.p, W.hOutMaps.p + W.hOutTotal);
-            keep.resize(W.hOutTotal + 1);
-            for (size_t wI = 0; wI < wins.size(); wI++) {
-                dph::WinRef ref;
-                ref.start = wins[wI].start;
-                ref.len = wins[wI].len;
-                ref.whole = wins[wI].whole;
-                ref.n = W.hOutN.p[wI];
-                ref.maps = keep.data() + W.hOutOff.p[wI];
-                cache[(size_t)slotOf[(size_t)wins[wI].read]].wins.push_back(ref);
-            }
-            todo.swap(next);
-            W.stats.ms_host_logic += now_ms() - t0;
+        if (unsigned ov = rounds_on_device(M, W, nUn, n, minLen)) {
+            forget_attempt(W, before);
+            W.stats.short_reads -= nShort;
+            return ov;
         }
     }
-    // ---- the sub-batch's output: the delivered block as it is, with the late results spliced in where the raw hits
-    //      of the unresolved reads sit ----
-    W.hp[4] += now_ms() - tReplay;
+    W.hp[4] += now_ms() - tRounds;
+    // ---- the sub-batch's output: the delivered block as it is, with the late results spliced in where the unresolved
+    //      reads sit (they delivered nothing in round 0) ----
     t0 = now_ms();
     const dp_mapping* fin = reinterpret_cast<const dp_mapping*>(W.hFinMaps.p);
+    std::vector<int> order((size_t)nUn);  // slots by read
+    for (int a = 0; a < nUn; a++) order[(size_t)a] = a;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return unres[(size_t)x].read < unres[(size_t)y].read; });
     size_t total = devTotal;
-    for (int a = 0; a < nUn; a++)
-        total += late[(size_t)a].size() - (size_t)(fOff[unres[(size_t)a].read + 1] - fOff[unres[(size_t)a].read]);
+    for (int a = 0; a < nUn; a++) total += (size_t)W.hRdResN.p[a];
     out.maps.resize(total);
     {
         size_t pos = 0, src = 0;
         int64_t prevRead = 0;
-        long long delta = 0;  // (records before read i in the output) - fOff[i]
         for (int a = 0; a <= nUn; a++) {
-            const int64_t u = a < nUn ? unres[(size_t)a].read : n;
+            const int slot = a < nUn ? order[(size_t)a] : -1;
+            const int64_t u = a < nUn ? unres[(size_t)slot].read : n;
             const size_t segEnd = fOff[u];  // finished reads [prevRead, u): one block
             if (segEnd > src) memcpy(out.maps.data() + pos, fin + src, (segEnd - src) * sizeof(dp_mapping));
             pos += segEnd - src;
+            src = segEnd;
             for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int64_t)(fOff[i + 1] - fOff[i]);
             if (a == nUn) break;
-            const std::vector<dph::Hit>& v = late[(size_t)a];
-            counts[r0 + u] = (int64_t)v.size();
-            for (const dph::Hit& h : v) out.maps[pos++] = to_abi(h);
-            src = fOff[u + 1];
-            delta += (long long)v.size() - (long long)(fOff[u + 1] - fOff[u]);
+            const int nLate = W.hRdResN.p[slot];
+            counts[r0 + u] = nLate;
+            if (nLate)
+                memcpy(out.maps.data() + pos, W.hRdResMaps.p + W.hRdResOff.p[slot], (size_t)nLate * sizeof(dp_mapping));
+            pos += (size_t)nLate;
             prevRead = u + 1;
         }
-        (void)delta;
         if (pos != total) throw std::runtime_error("internal error: sub-batch assembly mismatch");
     }
     absorb_counters(W);
@@ -2219,16 +2252,57 @@ int dp_mapper_map_batch_packed(dp_mapper* m, int64_t n_reads, const uint8_t* pac
     API_TRY
     if (!m || !byte_offsets || !lengths || !out || !out_offsets || n_reads < 0 || (!packed && n_reads > 0))
         throw std::runtime_error("bad argument");
-    std::vector<int64_t> bases((size_t)n_reads + 1, 0);
-    for (int64_t i = 0; i < n_reads; i++) {
-        if (lengths[i] < 0 || byte_offsets[i + 1] - byte_offsets[i] < (lengths[i] + 3) / 4)
-            throw std::runtime_error("a packed read needs (length + 3) / 4 bytes between its offset and the next");
-        bases[(size_t)i + 1] = bases[(size_t)i] + lengths[i];
+    // cumulative bases of the reads (what the ASCII entry is handed): checked and summed by a few threads in pieces, in
+    // a recycled block — a million reads walked by one thread into fresh memory cost 2-3 ms before the first kernel
+    const double tIn = now_ms();
+    struct Scratch {
+        int64_t* p;
+        explicit Scratch(size_t n) : p((int64_t*)result_alloc(sizeof(int64_t) * n)) {
+            if (!p) throw std::runtime_error("out of host memory");
+        }
+        ~Scratch() { result_free(p); }
+    } bases((size_t)n_reads + 1);
+    {
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(8, n_reads / 65536));
+        std::vector<int64_t> partial((size_t)T + 1, 0);
+        std::atomic<int> badRead(0);
+        auto piece = [&](int t, bool second) {
+            const int64_t a = n_reads * t / T, b = n_reads * (t + 1) / T;
+            if (!second) {
+                int64_t sum = 0;
+                bool ok = true;
+                for (int64_t i = a; i < b; i++) {
+                    ok &= lengths[i] >= 0 && byte_offsets[i + 1] - byte_offsets[i] >= (lengths[i] + 3) / 4;
+                    sum += lengths[i];
+                }
+                partial[(size_t)t + 1] = sum;
+                if (!ok) badRead.store(1);
+            } else {
+                int64_t run = partial[(size_t)t];
+                for (int64_t i = a; i < b; i++) {
+                    bases.p[i] = run;
+                    run += lengths[i];
+                }
+            }
+        };
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; t++) th.emplace_back(piece, t, pass == 1);
+            piece(0, pass == 1);
+            for (auto& x : th) x.join();
+            if (pass == 0) {
+                if (badRead.load())
+                    throw std::runtime_error("a packed read needs (length + 3) / 4 bytes between its offset and the next");
+                for (int t = 0; t < T; t++) partial[(size_t)t + 1] += partial[(size_t)t];
+            }
+        }
+        bases.p[n_reads] = partial[(size_t)T];
     }
+    if (getenv("DP_TRACE")) fprintf(stderr, "[dp trace] packed entry: read table in %.2f ms\n", now_ms() - tIn);
     cudaPointerAttributes attr;
     const bool onDevice = n_reads > 0 && cudaPointerGetAttributes(&attr, packed) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();
-    map_batch_impl(*m, n_reads, onDevice ? nullptr : packed, onDevice ? packed : nullptr, bases.data(), out, out_offsets,
+    map_batch_impl(*m, n_reads, onDevice ? nullptr : packed, onDevice ? packed : nullptr, bases.p, out, out_offsets,
                    byte_offsets, true);
     API_CATCH
 }

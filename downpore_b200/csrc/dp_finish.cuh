@@ -4,11 +4,11 @@
 // Round 0 of every read is fixed: the whole read if len <= 2*edge, else its first and last `edge` bases. After the
 // window kernels have produced the hits of those windows, one thread per read finishes the read here if Map() would
 // return at this point (short read; end-to-end pair found; or len < 3*edge). Everything else is flagged unresolved
-// and continues on the host replay path (dp_host_map.hpp) — a fraction of a percent of reads on ONT-like data.
+// and continues with the later rounds of Map() (dp_rounds.cuh) — a fraction of a percent of reads on ONT-like data.
 #pragma once
 #include "dp_common.cuh"
 
-#define DP_FIN_CAP 8  // hits per window handled on the device; more -> host path
+#define DP_FIN_CAP 8  // hits per window handled here; more -> the general strategy kernel (dp_rounds.cuh)
 
 // read table: lengths and packed-word demand from the (sub-batch relative) byte offsets
 __global__ void dp_read_table_kernel(const long long* __restrict__ seqOff, long long n, int* __restrict__ readLen,
@@ -132,8 +132,8 @@ __device__ __forceinline__ DpMappingDev dp_store_hit(const DpHit& h) {
 
 // Map()'s first decision for one read, in two passes around a device-wide exclusive scan so that the records land in
 // READ ORDER (the host then takes a sub-batch's results as one block instead of visiting every read):
-//   WRITE = false: cnt[r] = records the read delivers — its final mappings if Map() returns at this point, else the raw
-//                  hits of its two round-0 windows (first window's, then the second's) for the replay of the later rounds;
+//   WRITE = false: cnt[r] = records the read delivers — its final mappings if Map() returns at this point, else none
+//                  (the later rounds deliver them, dp_rounds.cuh);
 //   WRITE = true : the same decision again (cheaper than parking the records), records written at off[r] (the scan of
 //                  cnt); reads that are not finished are appended to `unres` as {read, nA, nB}.
 // finMaps may live in page-locked host memory mapped into the device address space: consecutive reads write consecutive
@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
         }
     }
     if (!WRITE) {
-        cnt[r] = done ? nOut + nOut2 : nA + nB;
+        cnt[r] = done ? nOut + nOut2 : 0;
         return;
     }
-    if (!done) {  // the later rounds of Map() replay this read against the raw hits delivered below
+    if (!done) {  // the later rounds of Map() take over (the window results stay on the device)
         const int slot = atomicAdd(nUnres, 1);
         if (slot < unresCap) {
             DpUnresolved u;
@@ -237,8 +237,5 @@ __global__ void __launch_bounds__(128) dp_finish_round0_kernel(DpIndexDev I, con
     if (done) {
         for (int i = 0; i < nOut; i++) finMaps[base + i] = dp_store_hit(outList[i]);
         for (int i = 0; i < nOut2; i++) finMaps[base + nOut + i] = dp_store_hit(outList2[i]);
-    } else {  // (removeDominated above worked on copies)
-        for (int i = 0; i < nA; i++) finMaps[base + i] = outMaps[outOff[2 * r] + i];
-        for (int i = 0; i < nB; i++) finMaps[base + nA + i] = outMaps[outOff[2 * r + 1] + i];
     }
 }

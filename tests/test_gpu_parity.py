@@ -212,6 +212,63 @@ def test_packed_reads_entry_point(pair):
         assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), mode
 
 
+def chimera_reads(ref, circular, seed=81, n=120):
+    """A read set where Map() rarely returns after its first decision: two- and three-segment chimeras of every size class
+    (mapNext's short and long paths, findSplitPoint with one- and two-sided matches), junk inserts (no match at all in the
+    middle: both recursive calls), reads with a noisy end, plus ordinary reads."""
+    rng = np.random.default_rng(seed)
+    out = []
+    pieces = {L: synth.reads(ref, seed + L, n, L, circular=circular) for L in (1200, 1700, 2600, 3400, 5200, 8000)}
+
+    def piece(L, i):
+        return pieces[L][(i % n) * L:((i % n) + 1) * L]
+
+    sizes = list(pieces)
+    for i in range(n):
+        a, b = sizes[rng.integers(len(sizes))], sizes[rng.integers(len(sizes))]
+        kind = i % 6
+        if kind == 0:
+            out.append(np.concatenate([piece(a, i), piece(b, i + 7)]))
+        elif kind == 1:
+            out.append(np.concatenate([piece(a, i), piece(b, i + 3), piece(sizes[rng.integers(len(sizes))], i + 11)]))
+        elif kind == 2:  # junk in the middle
+            junk = rng.integers(0, 4, size=int(rng.integers(300, 2500))).astype(np.uint8)
+            out.append(np.concatenate([piece(a, i), np.frombuffer(b"ACGT", dtype=np.uint8)[junk], piece(b, i + 5)]))
+        elif kind == 3:  # noisy front end
+            junk = rng.integers(0, 4, size=int(rng.integers(200, 1400))).astype(np.uint8)
+            out.append(np.concatenate([np.frombuffer(b"ACGT", dtype=np.uint8)[junk], piece(b, i)]))
+        elif kind == 4:  # noisy back end
+            junk = rng.integers(0, 4, size=int(rng.integers(200, 1400))).astype(np.uint8)
+            out.append(np.concatenate([piece(a, i), np.frombuffer(b"ACGT", dtype=np.uint8)[junk]]))
+        else:
+            out.append(piece(a, i))
+    return out
+
+
+def test_later_rounds_of_map_on_the_device(pair):
+    """Map()'s rounds after the first (mapping/mapping.go:305-383 mapNext, :207-288 findSplitPoint) run on the device for
+    the reads the first decision leaves open: a chimera-heavy read set (five reads in six are chimeric or have a junk end)
+    maps exactly like the oracle — also from scratch capacities so small that the strategy kernel has to hand the
+    sub-batch back for a rerun with more room, and in several small sub-batches."""
+    ref, circular, om, gm = pair
+    reads = chimera_reads(ref, circular)
+    bases, offs = make_golden.concat(reads)
+    orow, ooff, octr = om.map_batch(bases, offs, threads=4)
+    for env in ({}, {"DP_ROUNDS_HITS": "3", "DP_ROUNDS_LIST": "2"}, {"DP_ROUNDS_CACHE": "1", "DP_SUB_READS": "32"},
+                {"DP_SUB_READS": "16", "DP_LANES": "2"}):
+        with _Env(env):
+            maps, off = gm.map_batch(bases, offs)
+        assert np.array_equal(off, ooff), env
+        assert np.array_equal(rows_of(maps), orow), env
+        st = gm.stats()
+        assert st["rounds"] > 2 or env.get("DP_SUB_READS"), st
+        if not env:
+            for key in ("windows", "kmer_lookups", "query_seeds", "posting_runs", "posting_entries", "candidates",
+                        "chain_cells", "mappings"):
+                assert st[key] == octr[key], key
+            assert st["windows"] > 2.5 * len(reads)  # most reads went past their two round-0 windows
+
+
 def test_result_delivery_in_pieces(pair):
     """A batch cut into many sub-batches (six lanes finishing them out of order) is delivered in read order, also when the
     result outgrows the room reserved up front and the rest is placed after the lanes have finished."""
