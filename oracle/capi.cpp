@@ -246,6 +246,109 @@ long long dpo_pairwise_alignments(const long long* aSeg, long long na, const lon
     DPO_CATCH(-1)
 }
 
+// SeedSequence.Match (seeds/sequence.go:361-394) on explicit segment lists. mode 1: as performMapping calls it
+// (mapping/mapping.go:518-552): querySet / seqSet = the seeds of the query / of seq, both sequences Reduced first;
+// mode 0: dynamicMatch on the sequences as they are. out: per match {length, MatchA..., MatchB..., coveredA, coveredB}
+// (GetBasesCovered, :830-858); returns values written (or needed), matches in *nMatches (-1: Match returned nil).
+long long dpo_match(const long long* seqSeg, long long ns, const long long* querySeg, long long nq, long long minMatch,
+                    long long k, int mode, long long* out, long long cap, long long* nMatches) {
+    DPO_TRY SeedSequence seq, query;
+    seq.segments.assign(seqSeg, seqSeg + ns);
+    query.segments.assign(querySeg, querySeg + nq);
+    std::vector<SeedMatch> ms;
+    bool nil = false;
+    if (mode == 1) {
+        IntSet qSet = NewIntSet(), sSet = NewIntSet();
+        for (long long i = 1; i < nq; i += 2) Add(qSet, (uint64_t)querySeg[i]);
+        for (long long i = 1; i < ns; i += 2) Add(sSet, (uint64_t)seqSeg[i]);
+        ms = Match(seq, query, qSet, sSet, minMatch, k, &nil);
+    } else {
+        ms = DynamicMatch(seq, query, minMatch, k);
+    }
+    long long w = 0;
+    for (const SeedMatch& m : ms) {
+        gint ca = 0, cb = 0;
+        GetBasesCovered(m, k, &ca, &cb);
+        if (w < cap) out[w] = (long long)m.MatchA.size();
+        w++;
+        for (gint v : m.MatchA) {
+            if (w < cap) out[w] = v;
+            w++;
+        }
+        for (gint v : m.MatchB) {
+            if (w < cap) out[w] = v;
+            w++;
+        }
+        if (w < cap) out[w] = ca;
+        w++;
+        if (w < cap) out[w] = cb;
+        w++;
+    }
+    if (nMatches) *nMatches = nil ? -1 : (long long)ms.size();
+    return w;
+    DPO_CATCH(-1)
+}
+
+// SeedSequence.Reduced (seeds/sequence.go:85-123) with makeIndex: out = reduced segments, index = original positions;
+// returns the number of segment values (-1: nil, fewer than minSeeds whitelisted seeds)
+long long dpo_reduced(const long long* seg, long long n, const long long* whitelist, long long nw, long long k,
+                      long long minSeeds, long long* out, long long* index) {
+    DPO_TRY SeedSequence s, r;
+    s.segments.assign(seg, seg + n);
+    IntSet wl = NewIntSet();
+    for (long long i = 0; i < nw; i++) Add(wl, (uint64_t)whitelist[i]);
+    std::vector<gint> idx;
+    if (!Reduced(s, wl, k, minSeeds, &r, &idx)) return -1;
+    for (size_t i = 0; i < r.segments.size(); i++) out[i] = r.segments[i];
+    for (size_t i = 0; i < idx.size(); i++) index[i] = idx[i];
+    return (long long)r.segments.size();
+    DPO_CATCH(-2)
+}
+
+// GetSeedOffset / GetSeedOffsetFromEnd (seeds/sequence.go:1239-1246, 1269-1276)
+long long dpo_seed_offset(const long long* seg, long long n, long long index, long long k, int from_end) {
+    SeedSequence s;
+    s.segments.assign(seg, seg + n);
+    return from_end ? GetSeedOffsetFromEnd(s, index, k) : GetSeedOffset(s, index, k);
+}
+
+// mapEnds' pairing step (mapping/mapping.go:167-203: removeDominated, matchPairs with isConsistent) on explicit hits.
+// hits: rows of 6 {Start, End, QueryOffset, QueryInset, RC, ids}. out: remainingA rows, remainingB rows, matched rows;
+// counts3 = their row counts (matched count -1 when matched == nil).
+int dpo_pair_ends(long long refLen, int circular, long long queryLen, const long long* hitsA, long long nA,
+                  const long long* hitsB, long long nB, long long* out, long long* counts3) {
+    DPO_TRY auto load = [](const long long* h, long long n) {
+        std::vector<Mapping> v((size_t)n);
+        for (long long i = 0; i < n; i++) {
+            v[(size_t)i].Start = h[6 * i];
+            v[(size_t)i].End = h[6 * i + 1];
+            v[(size_t)i].QueryOffset = h[6 * i + 2];
+            v[(size_t)i].QueryInset = h[6 * i + 3];
+            v[(size_t)i].RC = h[6 * i + 4] != 0;
+            v[(size_t)i].ids = h[6 * i + 5];
+        }
+        return v;
+    };
+    std::vector<Mapping> ra, rb, mt;
+    bool nil = true;
+    PairEndsPublic(refLen, circular != 0, queryLen, load(hitsA, nA), load(hitsB, nB), &ra, &rb, &mt, &nil);
+    long long w = 0;
+    for (const std::vector<Mapping>* v : {&ra, &rb, &mt})
+        for (const Mapping& mp : *v) {
+            out[w++] = mp.Start;
+            out[w++] = mp.End;
+            out[w++] = mp.QueryOffset;
+            out[w++] = mp.QueryInset;
+            out[w++] = mp.RC ? 1 : 0;
+            out[w++] = mp.ids;
+        }
+    counts3[0] = (long long)ra.size();
+    counts3[1] = (long long)rb.size();
+    counts3[2] = nil ? -1 : (long long)mt.size();
+    return 0;
+    DPO_CATCH(1)
+}
+
 // ----- k-mer statistics ---------------------------------------------------------
 // values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
 int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {

@@ -597,6 +597,39 @@ Next mapNext(MapCtx& x, const PackedSeq& query, MList openA, MList openB) {  // 
 
 }  // namespace
 
+// mapEnds' pairing step (mapping.go:167-171) on explicit hit lists: removeDominated on both, updateQuery, matchPairs.
+// For the hand-worked vectors of tests/test_oracle_handworked.py (only refLen and circular of the mapper are used).
+void PairEndsPublic(gint refLen, bool circular, gint queryLen, const std::vector<Mapping>& hitsA,
+                    const std::vector<Mapping>& hitsB, std::vector<Mapping>* remA, std::vector<Mapping>* remB,
+                    std::vector<Mapping>* matched, bool* matchedNil) {
+    Mapper m;
+    m.circular = circular;
+    m.reference.length = refLen;
+    MapCtx x(m, nullptr);
+    MList openA, openB;
+    for (const Mapping& h : hitsA) {
+        Mapping* p = x.make();
+        *p = h;
+        p->queryLen = -1;
+        openA.push_back(p);
+    }
+    for (const Mapping& h : hitsB) {
+        Mapping* p = x.make();
+        *p = h;
+        p->queryLen = -1;
+        openB.push_back(p);
+    }
+    openA = removeDominated(openA, queryLen, nullptr);
+    openB = removeDominated(openB, queryLen, nullptr);
+    updateQuery(openA, queryLen);
+    updateQuery(openB, queryLen);
+    Pairs r = matchPairs(x, openA, openB);
+    for (Mapping* p : r.remainingA) remA->push_back(*p);
+    for (Mapping* p : r.remainingB) remB->push_back(*p);
+    for (Mapping* p : r.matched) matched->push_back(*p);
+    *matchedNil = r.matchedNil;
+}
+
 std::vector<Mapping> performMappingPublic(const Mapper& m, const PackedSeq& query, Counters* c) {
     MapCtx x(m, c);
     MList r = performMapping(x, query);

@@ -141,6 +141,7 @@ bool Reduced(const SeedSequence& s, const IntSet& whitelist, gint k, gint minSee
              SeedSequence* reduced, std::vector<gint>* index);          // sequence.go:85-123
 std::vector<SeedMatch> Match(const SeedSequence& seq, const SeedSequence& query, const IntSet& querySet,
                              const IntSet& seqSet, gint minMatch, gint k, bool* nil_result);  // :361-394
+std::vector<SeedMatch> DynamicMatch(const SeedSequence& seq, const SeedSequence& query, gint minMatch, gint k);  // :401-471 (no Reduced)
 void GetBasesCovered(const SeedMatch& m, gint k, gint* countA, gint* countB);  // sequence.go:830-858
 uint64_t ReverseComplementKmer(uint64_t seed, uint64_t k);             // sequence.go:125-132
 
@@ -271,6 +272,8 @@ void NewMapper(Mapper& m, const PackedSeq& reference, bool circular, gint k, con
 // Map (mapping.go:430-487). Returned mappings are in the slice order the reference returns.
 std::vector<Mapping> Map(const Mapper& m, const PackedSeq& query, Counters* c);
 std::vector<Mapping> performMappingPublic(const Mapper& m, const PackedSeq& query, Counters* c);  // mapping.go:489-611
+void PairEndsPublic(gint refLen, bool circular, gint queryLen, const std::vector<Mapping>& hitsA, const std::vector<Mapping>& hitsB,
+                    std::vector<Mapping>* remA, std::vector<Mapping>* remB, std::vector<Mapping>* matched, bool* matchedNil);  // :167-203
 std::string AsString(const Mapper& m, const Mapping& mp, const std::string& qname);  // mapping.go:112-122
 
 // ----------------------------------------------------------------------------

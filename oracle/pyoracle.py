@@ -397,6 +397,75 @@ def pairwise_alignments(a_segments, b_segments, min_matches, k, max_length=500):
     return res
 
 
+def match(seq_segments, query_segments, min_match, k, reduced=True):
+    """SeedSequence.Match (seeds/sequence.go:361-394) of `seq` against `query` on explicit segment lists. reduced=True: as
+    performMapping calls it (querySet / seqSet = the seeds of the query / of seq); False: dynamicMatch on the sequences as
+    they are. Returns None when Match returns nil, else [(MatchA, MatchB, coveredA, coveredB), ...] (GetBasesCovered)."""
+    sq = np.ascontiguousarray(seq_segments, dtype=np.int64)
+    q = np.ascontiguousarray(query_segments, dtype=np.int64)
+    lib().dpo_match.restype = ctypes.c_longlong
+    cap = 1 << 16
+    out = np.empty(cap, dtype=np.int64)
+    nm = ctypes.c_longlong(0)
+    w = lib().dpo_match(sq.ctypes.data_as(c_vp), ctypes.c_longlong(sq.size), q.ctypes.data_as(c_vp), ctypes.c_longlong(q.size),
+                        ctypes.c_longlong(int(min_match)), ctypes.c_longlong(int(k)), ctypes.c_int(1 if reduced else 0),
+                        out.ctypes.data_as(c_vp), ctypes.c_longlong(cap), ctypes.byref(nm))
+    if w < 0:
+        raise RuntimeError(_err())
+    if nm.value < 0:
+        return None
+    res, at = [], 0
+    for _ in range(nm.value):
+        n = int(out[at])
+        res.append((list(out[at + 1:at + 1 + n]), list(out[at + 1 + n:at + 1 + 2 * n]), int(out[at + 1 + 2 * n]),
+                    int(out[at + 2 + 2 * n])))
+        at += 3 + 2 * n
+    return res
+
+
+def reduced(segments, whitelist, k, min_seeds):
+    """SeedSequence.Reduced (seeds/sequence.go:85-123): (segments, index) or None."""
+    sg = np.ascontiguousarray(segments, dtype=np.int64)
+    wl = np.ascontiguousarray(whitelist, dtype=np.int64)
+    out = np.empty(sg.size, dtype=np.int64)
+    idx = np.empty(sg.size, dtype=np.int64)
+    lib().dpo_reduced.restype = ctypes.c_longlong
+    n = lib().dpo_reduced(sg.ctypes.data_as(c_vp), ctypes.c_longlong(sg.size), wl.ctypes.data_as(c_vp),
+                          ctypes.c_longlong(wl.size), ctypes.c_longlong(int(k)), ctypes.c_longlong(int(min_seeds)),
+                          out.ctypes.data_as(c_vp), idx.ctypes.data_as(c_vp))
+    if n == -1:
+        return None
+    if n < 0:
+        raise RuntimeError(_err())
+    return list(out[:n]), list(idx[:n // 2])
+
+
+def seed_offset(segments, index, k, from_end=False):
+    """GetSeedOffset / GetSeedOffsetFromEnd (seeds/sequence.go:1239-1246, 1269-1276)."""
+    sg = np.ascontiguousarray(segments, dtype=np.int64)
+    lib().dpo_seed_offset.restype = ctypes.c_longlong
+    return int(lib().dpo_seed_offset(sg.ctypes.data_as(c_vp), ctypes.c_longlong(sg.size), ctypes.c_longlong(int(index)),
+                                     ctypes.c_longlong(int(k)), ctypes.c_int(1 if from_end else 0)))
+
+
+def pair_ends(ref_len, circular, query_len, hits_a, hits_b):
+    """mapEnds' pairing step (mapping/mapping.go:167-203) on explicit hits, rows {Start, End, QueryOffset, QueryInset, RC,
+    ids}: (remainingA, remainingB, matched) as lists of rows; matched is None where the reference returns nil."""
+    a = np.ascontiguousarray(hits_a, dtype=np.int64).reshape(-1, 6)
+    b = np.ascontiguousarray(hits_b, dtype=np.int64).reshape(-1, 6)
+    out = np.zeros(6 * (len(a) + len(b)) + 6, dtype=np.int64)
+    cnt = np.zeros(3, dtype=np.int64)
+    if lib().dpo_pair_ends(ctypes.c_longlong(int(ref_len)), ctypes.c_int(1 if circular else 0), ctypes.c_longlong(int(query_len)),
+                           a.ctypes.data_as(c_vp), ctypes.c_longlong(len(a)), b.ctypes.data_as(c_vp), ctypes.c_longlong(len(b)),
+                           out.ctypes.data_as(c_vp), cnt.ctypes.data_as(c_vp)):
+        raise RuntimeError(_err())
+    rows = out.reshape(-1, 6)
+    na, nb, nm = int(cnt[0]), int(cnt[1]), int(cnt[2])
+    ra = [list(map(int, r)) for r in rows[:na]]
+    rb = [list(map(int, r)) for r in rows[na:na + nb]]
+    return ra, rb, (None if nm < 0 else [list(map(int, r)) for r in rows[na + nb:na + nb + nm]])
+
+
 def kmer_values(ref, k):
     """values[] of commands/map.go:45-71 for a single-record reference (canonical tie order, Q10)."""
     a = _u8(ref)

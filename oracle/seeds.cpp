@@ -285,6 +285,16 @@ std::vector<SeedMatch> Match(const SeedSequence& seq, const SeedSequence& query,
 
 void set_match_counters(Counters* c) { tl_counters = c; }
 
+// dynamicMatch on two sequences as they are (no Reduced): what the hand-worked vectors of tests/test_oracle_handworked.py pin
+std::vector<SeedMatch> DynamicMatch(const SeedSequence& seq, const SeedSequence& query, gint minMatch, gint k) {
+    std::vector<SeedMatch> ms = dynamicMatch(seq, query, minMatch, k);
+    for (SeedMatch& m : ms) {
+        m.SeqA = &query;
+        m.SeqB = &seq;
+    }
+    return ms;
+}
+
 // sequence.go:830-858
 void GetBasesCovered(const SeedMatch& m, gint k, gint* outA, gint* outB) {
     gint countA = (gint)m.MatchA.size() * k;
