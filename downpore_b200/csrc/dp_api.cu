@@ -1,7 +1,5 @@
 // downpore_b200 — host driver and C ABI (include/downpore_b200.h). No CPU fallback: everything fails loudly without
 // a usable CUDA device.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -24,6 +22,7 @@
 #include "dp_io.cuh"
 #include "dp_map.cuh"
 #include "dp_rounds.cuh"
+#include "dp_sort.cuh"
 
 namespace {
 
@@ -100,7 +99,7 @@ void result_free(void* p) {
 }  // namespace
 
 // Per-lane workspace: one stream plus every buffer a sub-batch needs. Two lanes let the host work of one sub-batch
-// (result assembly, the rare replay rounds) overlap the kernels of the next.
+// (result assembly, waiting for the rare later rounds of Map()) overlap the kernels of the next.
 // Capacities of one launch of the window kernels. None is a limit of the library: a launch that runs out of one flags
 // it (DpCounters.overflow), the host grows it and recomputes the affected reads (map_range below) — the reference keeps
 // every hit (mapping/mapping.go:504 sizes `results` by the candidate count, :518-552 append without bound).
@@ -114,7 +113,7 @@ struct Caps {
 const int kCapMax = 1 << 20;
 
 struct Lane {
-    double hp[6] = {0, 0, 0, 0, 0, 0};  // DP_HOST_PROFILE: host ms in tables / launches / wait / post / replay / assemble
+    double hp[6] = {0, 0, 0, 0, 0, 0};  // DP_HOST_PROFILE: host ms in tables / launches / wait / post / later rounds / assemble
     cudaStream_t stream = nullptr;
     Caps caps;
     HBuf<DpCounters> hCtr;  // counters + overflow flags of the current attempt, as of its last synchronise
@@ -361,12 +360,9 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
         pc.reserve((size_t)nTable + 1);
         prefix.reserve((size_t)nTable + 1);
         dp_popc_kernel<<<div_up(nTable, 256), 256, 0, st>>>(bits.p, pc.p, nTable);
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, pc.p, prefix.p, (int)nTable + 1, st);
         DBuf<unsigned char> tmp;
-        tmp.reserve(tmpBytes);
         CK(cudaMemsetAsync(pc.p + nTable, 0, sizeof(unsigned), st));
-        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, pc.p, prefix.p, (int)nTable + 1, st));
+        dp_exclusive_sum(pc.p, prefix.p, (long long)nTable + 1, tmp, st);
         dp_table_kernel<<<div_up(nTable, 256), 256, 0, st>>>(bits.p, prefix.p, M.table.p, nTable);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&numSeeds, prefix.p + nTable, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -429,11 +425,8 @@ void build_index(dp_mapper& M, const uint8_t* ref, const double* values) {
                                                      nullptr, nullptr, nullptr);
     CK(cudaGetLastError());
     {
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts.p, M.chunkOff.p, (int)C + 1, st);
         DBuf<unsigned char> tmp;
-        tmp.reserve(tmpBytes);
-        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, counts.p, M.chunkOff.p, (int)C + 1, st));
+        dp_exclusive_sum(counts.p, M.chunkOff.p, (long long)C + 1, tmp, st);
         CK(cudaStreamSynchronize(st));
     }
     std::vector<unsigned> hCounts(C + 1);
@@ -478,13 +471,19 @@ void build_postings(dp_mapper& M, DBuf<unsigned long long>& keys, unsigned long 
         // stable LSD radix sort: equal (seed, chunk) keys keep their input order, which is ascending scan position
         M.postPos.reserve((size_t)P2 + 1);
         M.postChunk.reserve((size_t)P2 + 1);
-        size_t tmpBytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, M.chunkPos.p, M.postPos.p, (int)P2, 0,
-                                        endBit, st);
         DBuf<unsigned char> tmp;
-        tmp.reserve(tmpBytes);
-        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysSorted.p, M.chunkPos.p, M.postPos.p, (int)P2, 0,
-                                           endBit, st));
+        DBuf<unsigned> hist;
+        {
+            DBuf<unsigned long long> keysScratch;
+            DBuf<unsigned> valsScratch;
+            if (endBit > 8) {
+                keysScratch.reserve((size_t)P2 + 1);
+                valsScratch.reserve((size_t)P2 + 1);
+            }
+            dp_radix_sort(keys.p, keysSorted.p, keysScratch.p, reinterpret_cast<const unsigned*>(M.chunkPos.p),
+                          reinterpret_cast<unsigned*>(M.postPos.p), valsScratch.p, (long long)P2, 0, endBit, hist, tmp, st);
+            CK(cudaStreamSynchronize(st));  // (the scratch arrays go out of scope)
+        }
         {
             DBuf<unsigned> seedCountAll;
             seedCountAll.reserve((size_t)numSeeds + 2);
@@ -493,20 +492,16 @@ void build_postings(dp_mapper& M, DBuf<unsigned long long>& keys, unsigned long 
             dp_posting_all_kernel<<<div_up((long long)P2, 256), 256, 0, st>>>(keysSorted.p, (long long)P2,
                                                                              seedCountAll.p, M.postChunk.p);
             CK(cudaGetLastError());
-            size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, seedCountAll.p, M.postOff.p, (int)numSeeds + 1, st);
-            DBuf<unsigned char> t2;
-            t2.reserve(tb);
-            CK(cub::DeviceScan::ExclusiveSum(t2.p, tb, seedCountAll.p, M.postOff.p, (int)numSeeds + 1, st));
+            dp_exclusive_sum(seedCountAll.p, M.postOff.p, (long long)numSeeds + 1, tmp, st);
             CK(cudaStreamSynchronize(st));
         }
         DBuf<unsigned long long> nSel;
         nSel.reserve(1);
-        size_t tmpBytes2 = 0;
-        cub::DeviceSelect::Unique(nullptr, tmpBytes2, keysSorted.p, keys.p, nSel.p, (int)P2, st);
-        DBuf<unsigned char> tmp2;
-        tmp2.reserve(tmpBytes2);
-        CK(cub::DeviceSelect::Unique(tmp2.p, tmpBytes2, keysSorted.p, keys.p, nSel.p, (int)P2, st));
+        {
+            DBuf<unsigned> upos;
+            dp_unique_sorted(keysSorted.p, keys.p, nSel.p, (long long)P2, upos, tmp, st);
+            CK(cudaStreamSynchronize(st));
+        }
         CK(cudaMemcpyAsync(&P1, nSel.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
@@ -520,11 +515,8 @@ void build_postings(dp_mapper& M, DBuf<unsigned long long>& keys, unsigned long 
                                                                               M.seedChunks.p);
             CK(cudaGetLastError());
         }
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, seedCount.p, M.seedOff.p, (int)numSeeds + 1, st);
         DBuf<unsigned char> tmp;
-        tmp.reserve(tmpBytes);
-        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, seedCount.p, M.seedOff.p, (int)numSeeds + 1, st));
+        dp_exclusive_sum(seedCount.p, M.seedOff.p, (long long)numSeeds + 1, tmp, st);
         CK(cudaStreamSynchronize(st));
     }
 
@@ -601,11 +593,8 @@ void build_mid_postings(dp_mapper& M) {
     M.midSeed.reserve((size_t)S);
     dp_mid_blocks_kernel<<<div_up((long long)S + 1, 256), 256, 0, st>>>(I.seedOff, S, blocks.p);
     CK(cudaGetLastError());
-    size_t tmpBytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, blocks.p, midOff.p, (int)S + 1, st);
     DBuf<unsigned char> tmp;
-    tmp.reserve(tmpBytes);
-    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, blocks.p, midOff.p, (int)S + 1, st));
+    dp_exclusive_sum(blocks.p, midOff.p, (long long)S + 1, tmp, st);
     unsigned total = 0;
     CK(cudaMemcpyAsync(&total, midOff.p + S, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1120,7 +1109,7 @@ void collect_stage_times(Lane& W) {  // call after a stream synchronize
 }
 
 // How a lane's host thread waits for its stream. Spinning (the runtime's default with few contexts) answers fastest,
-// but lanes x ranks-per-node threads spinning on fewer cores starve each other and the Map() replay. DP_SYNC=spin|block
+// but lanes x ranks-per-node threads spinning on fewer cores starve each other. DP_SYNC=spin|block
 // overrides; by default block when LOCAL_WORLD_SIZE (torchrun) x lanes exceeds the cores this process may run on.
 int lane_count();
 bool sync_mode_blocking() {
@@ -1382,13 +1371,8 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     CK(cudaMemcpyAsync(W.dSeqOff.p, W.hRel.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     dp_read_table_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(W.dSeqOff.p, n, W.dReadLen.p, W.dWordsNeeded.p);
     CK(cudaGetLastError());
-    {
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, W.dWordsNeeded.p, W.dWordOff.p, (int)n + 1, st);
-        W.scanTmp.reserve(tmpBytes);
-        CK(cub::DeviceScan::ExclusiveSum(W.scanTmp.p, tmpBytes, W.dWordsNeeded.p, W.dWordOff.p, (int)n + 1, st));
-    }
-    W.stats.kernel_launches += 2;
+    dp_exclusive_sum(W.dWordsNeeded.p, W.dWordOff.p, (long long)n + 1, W.scanTmp, st);
+    W.stats.kernel_launches += 3;
     W.curAscii = dAscii;
     W.curPacked = byteOff != nullptr && packed;
     W.curSpans = byteOff != nullptr && !packed;
@@ -1430,12 +1414,7 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
                                                                        W.outMaps.p, W.dFinN.p, nullptr, nullptr, 0, nullptr,
                                                                        nullptr, 0, W.dCtr.p, nullptr);
     CK(cudaGetLastError());
-    {
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, W.dFinN.p, W.dFinOff.p, (int)n + 1, st);
-        W.scanTmp.reserve(tmpBytes);
-        CK(cub::DeviceScan::ExclusiveSum(W.scanTmp.p, tmpBytes, W.dFinN.p, W.dFinOff.p, (int)n + 1, st));
-    }
+    dp_exclusive_sum(W.dFinN.p, W.dFinOff.p, (long long)n + 1, W.scanTmp, st);
     auto write_pass = [&]() {
         CK(cudaMemsetAsync(W.cursor.p + CUR_FIN, 0, sizeof(unsigned long long), st));
         dp_finish_round0_kernel<true><<<div_up(n, 128), 128, 0, st>>>(
@@ -1450,7 +1429,7 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hUnres.p, W.dUnres.p, (size_t)std::min<int64_t>(n, kUnresHead) * sizeof(DpUnresolved),
                        cudaMemcpyDeviceToHost, st));
-    W.stats.kernel_launches += 4;
+    W.stats.kernel_launches += 5;
     W.stats.ms_host_logic += now_ms() - t0;
     W.hp[1] += now_ms() - t0;
     {
@@ -2079,9 +2058,39 @@ void check_image_header(const DpImageHeader& H, int64_t bytes) {
     if (memcmp(H.magic, "DPB200IX", 8) != 0) throw std::runtime_error("not a downpore_b200 index image");
     if (H.version != kImageVersion) throw std::runtime_error("index image version mismatch");
     if ((int64_t)H.totalBytes > bytes) throw std::runtime_error("index image truncated");
-    if (H.k < 5 || H.k > 15 || H.numChunks == 0) throw std::runtime_error("index image header corrupt");
+    // the same parameter ranges as dp_mapper_create, and the layout exactly as image_layout() derives it from the
+    // header's counts: an image (it is also the on-disk index) that was cut, edited or written by another version is
+    // refused here instead of giving out-of-bounds device reads later
+    if (H.k < 5 || H.k > 15 || H.numChunks == 0 || H.numSeeds == 0) throw std::runtime_error("index image header corrupt");
+    if (H.seedRate < H.k + 4 || H.edge < 4 * H.k || H.edge > 16000 || H.chunkSize > 60000 || H.chunkSize < 2 * H.edge ||
+        H.refLen < 2ll * H.edge || H.refLen < H.seedRate || H.filterBits < 0 || H.filterBits > 2 * H.k || H.filterBits > 24 ||
+        (H.circular != 0 && H.circular != 1))
+        throw std::runtime_error("index image parameters out of range");
+    if (H.nSeedPostings <= 0 || H.nChunkPostings <= 0 || H.nSeedPostings > H.nChunkPostings ||
+        (uint64_t)H.nChunkPostings >= 0xffffffffull || H.maxChunkSeeds == 0 || (uint64_t)H.maxChunkSeeds > (uint64_t)H.nChunkPostings)
+        throw std::runtime_error("index image counts corrupt");
+    dp_mapper probe;
+    probe.k = H.k;
+    probe.filterBits = H.filterBits;
+    probe.I.numSeeds = H.numSeeds;
+    probe.I.numChunks = H.numChunks;
+    probe.nSeedPostings = H.nSeedPostings;
+    probe.nChunkPostings = H.nChunkPostings;
+    DpImageHeader E;
+    image_layout(probe, E);
+    if (E.totalBytes != H.totalBytes) throw std::runtime_error("index image layout corrupt");
     for (int i = 0; i < IX_N; i++)
-        if (H.off[i] % kImageAlign || H.off[i] + H.bytes[i] > H.totalBytes) throw std::runtime_error("index image layout corrupt");
+        if (H.off[i] != E.off[i] || H.bytes[i] != E.bytes[i]) throw std::runtime_error("index image layout corrupt");
+}
+
+// the CSR arrays of an image must end where the header says they do (a cheap whole-payload consistency check)
+void check_image_payload(const dp_mapper& M, const DpImageHeader& H) {
+    unsigned ends[3];
+    CK(cudaMemcpy(&ends[0], M.I.seedOff + H.numSeeds, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ends[1], M.I.postOff + H.numSeeds, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ends[2], M.I.chunkOff + H.numChunks, 4, cudaMemcpyDeviceToHost));
+    if (ends[0] != (unsigned)H.nSeedPostings || ends[1] != (unsigned)H.nChunkPostings || ends[2] != (unsigned)H.nChunkPostings)
+        throw std::runtime_error("index image payload corrupt (posting offsets do not match the header)");
 }
 
 }  // namespace
@@ -2218,6 +2227,7 @@ int dp_mapper_create_from_index(const void* image, int64_t bytes, int device, dp
     CK(cudaMemcpy(M->hChunkInset.data(), I.chunkInset, C * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(M->hChunkScanLen.data(), I.chunkScanLen, C * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(M->hChunkLen.data(), b + H.off[IX_CHUNKLEN], C * 4, cudaMemcpyDeviceToHost));
+    check_image_payload(*M, H);
     build_mid_postings(*M);
     *out = M.release();
     API_CATCH
@@ -2324,11 +2334,7 @@ namespace {
 
 template <class T>
 void exclusive_sum(const int* in, T* out, size_t n, DBuf<unsigned char>& tmp, cudaStream_t st) {
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, st);
-    tmp.reserve(tb);
-    tb = tmp.cap;
-    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, (int)n, st));
+    dp_exclusive_sum(in, out, (long long)n, tmp, st);
 }
 
 // the pointer a kernel of `device` can read `p` through; `staged` receives a device copy when `p` is pageable host memory

@@ -34,7 +34,9 @@ struct dp_overlapper {
     DBuf<int> rPos;
     DBuf<unsigned> pieceOff, keyOff;
     DBuf<OvChunk> chunks;
-    DBuf<unsigned long long> keys, keysSorted, nSel;
+    DBuf<unsigned long long> keys, keysSorted, keysScratch, nSel;
+    DBuf<unsigned> sortHist, uniquePos;
+    DBuf<unsigned char> scanTmp;  // scratch of dp_exclusive_scan only (its first bytes are the scan's ticket)
     DBuf<unsigned> seedOff, seedChunks, seedCount;
     DBuf<unsigned char> tmp;
     // lookup
@@ -70,16 +72,10 @@ struct dp_overlapper {
 namespace {
 
 void ov_scan_u32(dp_overlapper& O, const unsigned* in, unsigned* out, long long n) {
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, O.st);
-    O.tmp.reserve(tb + 16);
-    CK(cub::DeviceScan::ExclusiveSum(O.tmp.p, tb, in, out, (int)n, O.st));
+    dp_exclusive_sum(in, out, n, O.scanTmp, O.st);
 }
 void ov_scan_u64(dp_overlapper& O, const unsigned long long* in, unsigned long long* out, long long n) {
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, O.st);
-    O.tmp.reserve(tb + 16);
-    CK(cub::DeviceScan::ExclusiveSum(O.tmp.p, tb, in, out, (int)n, O.st));
+    dp_exclusive_sum(in, out, n, O.scanTmp, O.st);
 }
 
 unsigned ov_fetch_err(dp_overlapper& O) {
@@ -345,15 +341,11 @@ void ov_round(dp_overlapper& O, const uint8_t* ignoreHost, long long firstSequen
         // keys are written in chunk order, so a STABLE sort on the seed bits alone orders them by (seed, chunk)
         int endBit = 33;
         while ((1ull << (endBit - 32)) < (unsigned long long)S + 1 && endBit < 64) endBit++;
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tb, O.keys.p, O.keysSorted.p, (int)P2, 32, endBit, st);
-        O.tmp.reserve(tb + 16);
-        CK(cub::DeviceRadixSort::SortKeys(O.tmp.p, tb, O.keys.p, O.keysSorted.p, (int)P2, 32, endBit, st));
+        if (endBit - 32 > 8) O.keysScratch.reserve((size_t)P2 + 1);
+        dp_radix_sort(O.keys.p, O.keysSorted.p, O.keysScratch.p, nullptr, nullptr, nullptr, (long long)P2, 32, endBit, O.sortHist,
+                      O.scanTmp, st);
         O.nSel.reserve(1);
-        size_t tb2 = 0;
-        cub::DeviceSelect::Unique(nullptr, tb2, O.keysSorted.p, O.keys.p, O.nSel.p, (int)P2, st);
-        O.tmp.reserve(tb2 + 16);
-        CK(cub::DeviceSelect::Unique(O.tmp.p, tb2, O.keysSorted.p, O.keys.p, O.nSel.p, (int)P2, st));
+        dp_unique_sorted(O.keysSorted.p, O.keys.p, O.nSel.p, (long long)P2, O.uniquePos, O.scanTmp, st);
         CK(cudaMemcpyAsync(&P1, O.nSel.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }

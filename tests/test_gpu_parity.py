@@ -548,6 +548,20 @@ def test_index_image_round_trip(tmp_path):
     bad[:8] = 0
     with pytest.raises(dp.DownporeError):
         dp.Mapper.from_index(bad.ctypes.data, n)
+    # header fields that do not fit the layout or the parameter ranges, and a payload whose offsets do not end where the
+    # header says, are refused too (the image is also the on-disk index format)
+    hdr = np.frombuffer(host[:64].tobytes(), dtype=np.int32).copy()
+    for word, value in ((3, 3), (5, 2), (6, 7), (8, 40), (12, int(hdr[12]) + 1), (13, int(hdr[13]) + 1)):  # k, seedRate, edge, filterBits, numSeeds, numChunks
+        bad = host.copy()
+        bad[:64].view(np.int32)[word] = value
+        with pytest.raises(dp.DownporeError):
+            dp.Mapper.from_index(bad.ctypes.data, n)
+    bad = host.copy()
+    off_seedoff = int(np.frombuffer(host[:512].tobytes(), dtype=np.uint64)[88 // 8 + 2])  # DpImageHeader.off[IX_SEEDOFF]
+    n_seeds = int(hdr[12])
+    bad[off_seedoff + 4 * n_seeds: off_seedoff + 4 * n_seeds + 4].view(np.uint32)[0] += 1
+    with pytest.raises(dp.DownporeError):
+        dp.Mapper.from_index(bad.ctypes.data, n)
     gm.close()
 
 
