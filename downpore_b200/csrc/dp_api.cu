@@ -168,6 +168,7 @@ struct Lane {
     HBuf<int> hRdResN;
     HBuf<DpMappingDev> hRdResMaps;
     HBuf<DpMappingDev> hOutMaps, hFinMaps;
+    DBuf<DpMappingDev> dFinMaps;  // the finished records of a sub-batch in read order, before their copy to hFinMaps
     HBuf<long long> hRel;
     size_t hOutTotal = 0;
     bool pendingStageTimes = false;
@@ -1399,8 +1400,9 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
             }
         }
     }
-    // Map()'s first decision per read, delivered in read order: count pass, device-wide scan, write pass straight into
-    // mapped page-locked host memory (consecutive reads, consecutive records: coalesced posted writes)
+    // Map()'s first decision per read, delivered in read order: count pass, device-wide scan, write pass into HBM and one
+    // copy of the block to page-locked host memory (DP_FINISH_HBM=0: the write pass stores straight into mapped host
+    // memory instead — posted writes over PCIe from a kernel that then sits on its SMs for the length of the transfer)
     const int kUnresHead = 4096;  // unresolved reads copied with the results; a longer list is fetched afterwards
     W.dFinN.reserve(nR + 1);
     W.dFinOff.reserve(nR + 1);
@@ -1409,6 +1411,9 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     W.hUnres.reserve((size_t)kUnresHead);
     W.hUnresN.reserve(1);
     if (W.hFinMaps.cap < nR * 4 + 64) W.hFinMaps.reserve(nR * 4 + 64);
+    const bool viaHbm = env_int("DP_FINISH_HBM", 1) != 0;
+    if (viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
+    const size_t copyHead = std::min<size_t>(W.hFinMaps.cap, (size_t)n + (size_t)n / 4 + 64);  // records copied before their count is known
     CK(cudaEventRecord(W.timers[T_FINISH].a, st));
     dp_finish_round0_kernel<false><<<div_up(n + 1, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
                                                                        W.outMaps.p, W.dFinN.p, nullptr, nullptr, 0, nullptr,
@@ -1418,13 +1423,14 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     auto write_pass = [&]() {
         CK(cudaMemsetAsync(W.cursor.p + CUR_FIN, 0, sizeof(unsigned long long), st));
         dp_finish_round0_kernel<true><<<div_up(n, 128), 128, 0, st>>>(
-            M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p, W.outMaps.p, nullptr, W.dFinOff.p, W.hFinMaps.d,
-            (unsigned long long)W.hFinMaps.cap, W.dUnres.p, reinterpret_cast<int*>(W.cursor.p + CUR_FIN), (int)n + 1, W.dCtr.p,
+            M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p, W.outMaps.p, nullptr, W.dFinOff.p,
+            viaHbm ? W.dFinMaps.p : W.hFinMaps.d, (unsigned long long)W.hFinMaps.cap, W.dUnres.p, reinterpret_cast<int*>(W.cursor.p + CUR_FIN), (int)n + 1, W.dCtr.p,
             W.hCtr.d);
         CK(cudaGetLastError());
     };
     write_pass();
     CK(cudaEventRecord(W.timers[T_FINISH].b, st));
+    if (viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, copyHead * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hFinOff.p, W.dFinOff.p, ((size_t)n + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hUnres.p, W.dUnres.p, (size_t)std::min<int64_t>(n, kUnresHead) * sizeof(DpUnresolved),
@@ -1466,9 +1472,15 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     const size_t devTotal = fOff[n];
     if (devTotal > W.hFinMaps.cap) {  // more records than the delivery buffer holds (repeat-rich reads): grow, write again
         W.hFinMaps.reserve(devTotal + 64);
+        if (viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
         write_pass();
+        if (viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, devTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
         W.stats.kernel_launches += 1;
+        lane_sync(W);
+    } else if (viaHbm && devTotal > copyHead) {  // the tail the first copy did not cover
+        CK(cudaMemcpyAsync(W.hFinMaps.p + copyHead, W.dFinMaps.p + copyHead, (devTotal - copyHead) * sizeof(DpMappingDev),
+                           cudaMemcpyDeviceToHost, st));
         lane_sync(W);
     }
     const int nUn = *W.hUnresN.p;
