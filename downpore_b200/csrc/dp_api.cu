@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -164,6 +165,10 @@ struct Lane {
     DBuf<unsigned char> rdDone;
     DBuf<unsigned> rdResOff, rdCur;
     DBuf<DpHit> rdHits;
+    DpRoundsDev roundsDev{};  // the rounds in flight on this lane (rounds_begin -> rounds_run)
+    int rdThreads = 0;
+    std::unique_ptr<Lane> rounds;    // workspace + stream for the later rounds of this lane's previous sub-batch
+    cudaEvent_t evRounds = nullptr;  // round-0 hits filed in the rounds workspace
     HBuf<unsigned> hRdCur, hRdResOff;
     HBuf<int> hRdResN;
     HBuf<DpMappingDev> hRdResMaps;
@@ -189,6 +194,8 @@ struct Lane {
     int candStride = 0;
     int extractWarps = 0, lookupWarps = 0, chainWarps = 0;
     ~Lane() {
+        rounds.reset();
+        if (evRounds) cudaEventDestroy(evRounds);
         if (evReady) cudaEventDestroy(evReady);
         if (evPulled) cudaEventDestroy(evPulled);
         if (evSync) cudaEventDestroy(evSync);
@@ -1238,62 +1245,76 @@ inline size_t round0_seed_bound(long long len, int e, int minLen) {
 // Later rounds of Mapper.Map for the `nUn` reads round 0 left open (W.dUnres), entirely on the device: strategy kernel
 // (one replay of Map() per open read against its window cache) -> the windows it asks for, through the same window
 // kernels as round 0 -> collect kernel -> strategy kernel again, until no read asks for a window. Per round the host
-// reads one counter block; the reads' final records arrive in W.hRdResN / hRdResOff / hRdResMaps (indexed by slot =
-// position in W.dUnres). Returns the overflow bits of a capacity that was too small (nothing is delivered then).
-unsigned rounds_on_device(dp_mapper& M, Lane& W, int nUn, int64_t n, int minLen) {
+// reads one counter block; the reads' final records arrive in hRdResN / hRdResOff / hRdResMaps of the lane that ran the
+// rounds (indexed by slot = position in dUnres).
+//
+// Two steps, so that the rounds of one sub-batch can run NEXT TO round 0 of the lane's next sub-batch (a few hundred
+// windows make ~40 tiny, latency-bound launches and three synchronisations: done in line they cost 16 % of a step while
+// the big kernels wait): rounds_begin files the round-0 hits of the open reads in the window cache of lane R (on W's
+// stream: they live in W's window-result pool, which W's next launch overwrites); rounds_run does the rest on R's
+// stream with R's window buffers. R == W runs them in line (pieces, retries).
+void rounds_begin(dp_mapper& M, Lane& W, Lane& R, int nUn, int64_t n, int minLen) {
     cudaStream_t st = W.stream;
-    const size_t scale = (size_t)W.caps.roundsScale;
-    const int e = M.edge;
+    const size_t scale = (size_t)R.caps.roundsScale;
     const size_t slots = std::max<size_t>((size_t)nUn, 64);
     const int nThreads = (int)std::min<size_t>((slots + 63) / 64 * 64, 4096);
-    DpRoundsDev R;
-    memset(&R, 0, sizeof(R));
+    DpRoundsDev& D = R.roundsDev;
+    memset(&D, 0, sizeof(D));
     // (DP_ROUNDS_HITS / DP_ROUNDS_LIST / DP_ROUNDS_CACHE: tests start from tiny capacities to walk the retries)
-    R.hitCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_HITS", 256)) * scale, 1u << 20);
-    R.listCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_LIST", 128)) * scale, 1u << 20);
-    R.entCap = (unsigned)std::min<size_t>((32 * slots + 64) * scale, 0x7fffffffu);
-    R.cacheCap = (unsigned)std::min<size_t>(((size_t)std::max(1, env_int("DP_ROUNDS_CACHE", 256)) * slots + 4096) * scale, 0xfffffff0u);
-    R.resCap = (unsigned)std::min<size_t>((16 * slots + 1024) * scale, 0xfffffff0u);
-    W.rdHead.reserve(slots);
-    W.rdEnt.reserve(R.entCap);
-    W.rdEnt2.reserve(R.entCap);
-    W.rdCache.reserve(R.cacheCap);
-    W.rdWinSlot.reserve(W.dWins.cap);
-    W.rdDone.reserve(slots);
-    W.rdResN.reserve(slots);
-    W.rdResOff.reserve(slots);
-    W.rdResMaps.reserve(R.resCap);
-    W.rdHits.reserve((size_t)nThreads * R.hitCap);
-    W.rdLists.reserve((size_t)nThreads * DP_RL_LISTS * R.listCap);
-    W.rdCur.reserve(DP_RC_N);
-    W.hRdCur.reserve(DP_RC_N);
-    W.hRdResN.reserve(slots);
-    W.hRdResOff.reserve(slots);
-    R.unres = W.dUnres.p;
-    R.nSlots = nUn;
-    R.readLen = W.dReadLen.p;
-    R.head = W.rdHead.p;
-    R.ent = W.rdEnt.p;
-    R.ent2 = W.rdEnt2.p;
-    R.cacheMaps = W.rdCache.p;
-    R.wins = W.dWins.p;
-    R.winSlot = W.rdWinSlot.p;
-    R.winCap = (unsigned)std::min<size_t>(W.dWins.cap, (size_t)2 * (size_t)n);  // (a replay asks for at most two windows)
-    R.done = W.rdDone.p;
-    R.resN = W.rdResN.p;
-    R.resOff = W.rdResOff.p;
-    R.resMaps = W.rdResMaps.p;
-    R.hits = W.rdHits.p;
-    R.lists = W.rdLists.p;
-    R.cur = W.rdCur.p;
-    R.edge = e;
-    R.circular = M.circular;
-    R.refLen = M.refLen;
-    CK(cudaMemsetAsync(W.rdCur.p, 0, DP_RC_N * sizeof(unsigned), st));
-    CK(cudaMemsetAsync(W.rdHead.p, 0xff, (size_t)nUn * sizeof(int), st));
-    dp_rounds_seed_kernel<<<div_up(nUn, 128), 128, 0, st>>>(R, minLen, W.outN.p, W.outOff.p, W.outMaps.p);
+    D.hitCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_HITS", 256)) * scale, 1u << 20);
+    D.listCap = (int)std::min<size_t>((size_t)std::max(1, env_int("DP_ROUNDS_LIST", 128)) * scale, 1u << 20);
+    D.entCap = (unsigned)std::min<size_t>((32 * slots + 64) * scale, 0x7fffffffu);
+    D.cacheCap = (unsigned)std::min<size_t>(((size_t)std::max(1, env_int("DP_ROUNDS_CACHE", 256)) * slots + 4096) * scale, 0xfffffff0u);
+    D.resCap = (unsigned)std::min<size_t>((16 * slots + 1024) * scale, 0xfffffff0u);
+    if (&R != &W) R.dWins.reserve(2 * slots + 64);  // the windows the replays ask for (at most two per open read and round)
+    R.rdHead.reserve(slots);
+    R.rdEnt.reserve(D.entCap);
+    R.rdEnt2.reserve(D.entCap);
+    R.rdCache.reserve(D.cacheCap);
+    R.rdWinSlot.reserve(R.dWins.cap);
+    R.rdDone.reserve(slots);
+    R.rdResN.reserve(slots);
+    R.rdResOff.reserve(slots);
+    R.rdResMaps.reserve(D.resCap);
+    R.rdHits.reserve((size_t)nThreads * D.hitCap);
+    R.rdLists.reserve((size_t)nThreads * DP_RL_LISTS * D.listCap);
+    R.rdCur.reserve(DP_RC_N);
+    R.hRdCur.reserve(DP_RC_N);
+    R.hRdResN.reserve(slots);
+    R.hRdResOff.reserve(slots);
+    R.rdThreads = nThreads;
+    D.unres = W.dUnres.p;  // (these two tables move to R with the rest of the sub-batch's tables: the pointers stay valid)
+    D.nSlots = nUn;
+    D.readLen = W.dReadLen.p;
+    D.head = R.rdHead.p;
+    D.ent = R.rdEnt.p;
+    D.ent2 = R.rdEnt2.p;
+    D.cacheMaps = R.rdCache.p;
+    D.wins = R.dWins.p;
+    D.winSlot = R.rdWinSlot.p;
+    D.winCap = (unsigned)std::min<size_t>(R.dWins.cap, (size_t)2 * (size_t)n);
+    D.done = R.rdDone.p;
+    D.resN = R.rdResN.p;
+    D.resOff = R.rdResOff.p;
+    D.resMaps = R.rdResMaps.p;
+    D.hits = R.rdHits.p;
+    D.lists = R.rdLists.p;
+    D.cur = R.rdCur.p;
+    D.edge = M.edge;
+    D.circular = M.circular;
+    D.refLen = M.refLen;
+    CK(cudaMemsetAsync(R.rdCur.p, 0, DP_RC_N * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(R.rdHead.p, 0xff, (size_t)nUn * sizeof(int), st));
+    dp_rounds_seed_kernel<<<div_up(nUn, 128), 128, 0, st>>>(D, minLen, W.outN.p, W.outOff.p, W.outMaps.p);
     CK(cudaGetLastError());
     W.stats.kernel_launches += 1;
+}
+
+// Returns the overflow bits of a capacity that was too small (nothing is delivered then).
+unsigned rounds_run(dp_mapper& M, Lane& W, int nUn, int minLen) {
+    cudaStream_t st = W.stream;
+    const DpRoundsDev& R = W.roundsDev;
+    const int nThreads = W.rdThreads;
     for (;;) {
         CK(cudaMemsetAsync(W.rdCur.p + DP_RC_REQ, 0, sizeof(unsigned), st));
         CK(cudaMemsetAsync(W.rdCur.p + DP_RC_OPEN, 0, 3 * sizeof(unsigned), st));  // open reads, summed window lengths
@@ -1332,20 +1353,69 @@ unsigned rounds_on_device(dp_mapper& M, Lane& W, int nUn, int64_t n, int minLen)
     return 0;
 }
 
-// Maps reads [r0, r1) whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device, with the lane's current
-// capacities (W.caps). Returns 0 and fills counts[r0..r1) and `out` (ordered by read), or returns the DP_OV_* bits of
-// a capacity that was too small: nothing is delivered then and the caller reruns the range with more room (map_range).
-unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff,
-                      bool packed, int64_t r0, int64_t r1, int64_t* counts, SubOut& out) {
+// One sub-batch between the two halves of its processing (sub_begin: everything of round 0 enqueued; sub_complete: the
+// results taken) and, when its later rounds were handed to the lane's rounds workspace, until they have run.
+struct SubState {
+    int64_t r0 = 0, n = 0;
+    dp_stats before{};
+    int64_t nShort = 0;
+    int minLen = 0;
+    bool viaHbm = false;
+    size_t copyHead = 0;
+    double tEnq = 0;
+    // deferred rounds
+    bool pending = false;
+    size_t sI = 0;
+    int nUn = 0;
+    size_t devTotal = 0;
+    std::vector<DpUnresolved> unres;
+    dp_stats round0{};   // what round 0 added to the lane's statistics (taken back if the sub-batch has to be redone)
+    dp_stats roundsBefore{};
+};
+
+template <class T>
+void swap_buf(DBuf<T>& a, DBuf<T>& b) {
+    std::swap(a.p, b.p);
+    std::swap(a.cap, b.cap);
+}
+template <class T>
+void swap_buf(HBuf<T>& a, HBuf<T>& b) {
+    std::swap(a.p, b.p);
+    std::swap(a.d, b.d);
+    std::swap(a.cap, b.cap);
+}
+
+void finish_write_pass(dp_mapper& M, Lane& W, int64_t n, int minLen, bool viaHbm) {
+    cudaStream_t st = W.stream;
+    CK(cudaMemsetAsync(W.cursor.p + CUR_FIN, 0, sizeof(unsigned long long), st));
+    dp_finish_round0_kernel<true><<<div_up(n, 128), 128, 0, st>>>(
+        M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p, W.outMaps.p, nullptr, W.dFinOff.p,
+        viaHbm ? W.dFinMaps.p : W.hFinMaps.d, (unsigned long long)W.hFinMaps.cap, W.dUnres.p,
+        reinterpret_cast<int*>(W.cursor.p + CUR_FIN), (int)n + 1, W.dCtr.p, W.hCtr.d);
+    CK(cudaGetLastError());
+}
+
+const int kUnresHead = 4096;  // unresolved reads copied with the results; a longer list is fetched afterwards
+
+// Enqueues round 0 of reads [r0, r1) (whose ASCII lives at dAscii + (offsets[i] - offsets[r0]) on the device) with the
+// lane's current capacities (W.caps): read tables, windows, performMapping stages, Map()'s first decision, the copies of
+// its results. Nothing is waited for.
+void sub_begin(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff, bool packed,
+               int64_t r0, int64_t r1, SubState& S) {
     const int64_t n = r1 - r0;
     cudaStream_t st = W.stream;
-    const dp_stats before = W.stats;
+    S.r0 = r0;
+    S.n = n;
+    S.before = W.stats;
+    S.pending = false;
     reset_counters(W);
     const int k = M.k;
     const int e = M.edge;
     const int minLen = k + 12;  // shorter reads: the reference's scans over-read their slice (undefined); no mappings
+    S.minLen = minLen;
     // ---- read tables on the device: lengths, packed-word offsets ----
     double t0 = now_ms();
+    S.tEnq = t0;
     const size_t nR = std::max<size_t>((size_t)n, W.floorReads);  // what is reserved
     W.hRel.reserve(nR + 1);
     long long maxLen = 0;
@@ -1360,6 +1430,7 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         else nShort++;
         seedEntries0 += round0_seed_bound(len, e, minLen);
     }
+    S.nShort = nShort;
     if (maxLen > 0x7fffff00ll) throw std::runtime_error("read too long");
     W.hp[0] += now_ms() - t0;
     const long long totalBytes = W.hRel.p[n];
@@ -1403,7 +1474,6 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     // Map()'s first decision per read, delivered in read order: count pass, device-wide scan, write pass into HBM and one
     // copy of the block to page-locked host memory (DP_FINISH_HBM=0: the write pass stores straight into mapped host
     // memory instead — posted writes over PCIe from a kernel that then sits on its SMs for the length of the transfer)
-    const int kUnresHead = 4096;  // unresolved reads copied with the results; a longer list is fetched afterwards
     W.dFinN.reserve(nR + 1);
     W.dFinOff.reserve(nR + 1);
     W.hFinOff.reserve(nR + 1);
@@ -1411,26 +1481,18 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     W.hUnres.reserve((size_t)kUnresHead);
     W.hUnresN.reserve(1);
     if (W.hFinMaps.cap < nR * 4 + 64) W.hFinMaps.reserve(nR * 4 + 64);
-    const bool viaHbm = env_int("DP_FINISH_HBM", 1) != 0;
-    if (viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
-    const size_t copyHead = std::min<size_t>(W.hFinMaps.cap, (size_t)n + (size_t)n / 4 + 64);  // records copied before their count is known
+    S.viaHbm = env_int("DP_FINISH_HBM", 1) != 0;
+    if (S.viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
+    S.copyHead = std::min<size_t>(W.hFinMaps.cap, (size_t)n + (size_t)n / 4 + 64);  // records copied before their count is known
     CK(cudaEventRecord(W.timers[T_FINISH].a, st));
     dp_finish_round0_kernel<false><<<div_up(n + 1, 128), 128, 0, st>>>(M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p,
                                                                        W.outMaps.p, W.dFinN.p, nullptr, nullptr, 0, nullptr,
                                                                        nullptr, 0, W.dCtr.p, nullptr);
     CK(cudaGetLastError());
     dp_exclusive_sum(W.dFinN.p, W.dFinOff.p, (long long)n + 1, W.scanTmp, st);
-    auto write_pass = [&]() {
-        CK(cudaMemsetAsync(W.cursor.p + CUR_FIN, 0, sizeof(unsigned long long), st));
-        dp_finish_round0_kernel<true><<<div_up(n, 128), 128, 0, st>>>(
-            M.I, W.dReadLen.p, n, minLen, W.outN.p, W.outOff.p, W.outMaps.p, nullptr, W.dFinOff.p,
-            viaHbm ? W.dFinMaps.p : W.hFinMaps.d, (unsigned long long)W.hFinMaps.cap, W.dUnres.p, reinterpret_cast<int*>(W.cursor.p + CUR_FIN), (int)n + 1, W.dCtr.p,
-            W.hCtr.d);
-        CK(cudaGetLastError());
-    };
-    write_pass();
+    finish_write_pass(M, W, n, minLen, S.viaHbm);
     CK(cudaEventRecord(W.timers[T_FINISH].b, st));
-    if (viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, copyHead * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+    if (S.viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, S.copyHead * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hFinOff.p, W.dFinOff.p, ((size_t)n + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hUnres.p, W.dUnres.p, (size_t)std::min<int64_t>(n, kUnresHead) * sizeof(DpUnresolved),
@@ -1438,6 +1500,90 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
     W.stats.kernel_launches += 5;
     W.stats.ms_host_logic += now_ms() - t0;
     W.hp[1] += now_ms() - t0;
+}
+
+// The sub-batch's output: the delivered block as it is, with the late results spliced in where the unresolved reads sit
+// (they delivered nothing in round 0). F holds the block (hFinOff / hFinMaps), L the late results (hRdRes*). `dest` is
+// asked for room once the number of records is known: the sub-batch's place in the call's result array when every
+// sub-batch in front of it has reported its size already, else a block of its own.
+typedef std::function<dp_mapping*(size_t)> SubDest;
+void sub_assemble(Lane& F, Lane& L, const SubState& S, const std::vector<DpUnresolved>& unres, int64_t* counts, const SubDest& dest) {
+    const int64_t n = S.n, r0 = S.r0;
+    const int nUn = (int)unres.size();
+    const unsigned* fOff = F.hFinOff.p;
+    const size_t devTotal = fOff[n];
+    const dp_mapping* fin = reinterpret_cast<const dp_mapping*>(F.hFinMaps.p);
+    std::vector<int> order((size_t)nUn);  // slots by read
+    for (int a = 0; a < nUn; a++) order[(size_t)a] = a;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return unres[(size_t)x].read < unres[(size_t)y].read; });
+    size_t total = devTotal;
+    for (int a = 0; a < nUn; a++) total += (size_t)L.hRdResN.p[a];
+    dp_mapping* out = dest(total);
+    size_t pos = 0, src = 0;
+    int64_t prevRead = 0;
+    for (int a = 0; a <= nUn; a++) {
+        const int slot = a < nUn ? order[(size_t)a] : -1;
+        const int64_t u = a < nUn ? unres[(size_t)slot].read : n;
+        const size_t segEnd = fOff[u];  // finished reads [prevRead, u): one block
+        if (segEnd > src) memcpy(out + pos, fin + src, (segEnd - src) * sizeof(dp_mapping));
+        pos += segEnd - src;
+        src = segEnd;
+        for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int64_t)(fOff[i + 1] - fOff[i]);
+        if (a == nUn) break;
+        const int nLate = L.hRdResN.p[slot];
+        counts[r0 + u] = nLate;
+        if (nLate) memcpy(out + pos, L.hRdResMaps.p + L.hRdResOff.p[slot], (size_t)nLate * sizeof(dp_mapping));
+        pos += (size_t)nLate;
+        prevRead = u + 1;
+    }
+    if (pos != total) throw std::runtime_error("internal error: sub-batch assembly mismatch");
+}
+
+dp_stats stats_diff(const dp_stats& a, const dp_stats& b) {
+    dp_stats d = a;
+    d.ms_pack -= b.ms_pack;
+    d.ms_extract -= b.ms_extract;
+    d.ms_lookup -= b.ms_lookup;
+    d.ms_chain -= b.ms_chain;
+    d.ms_reduce -= b.ms_reduce;
+    d.ms_finish -= b.ms_finish;
+    d.ms_host_logic -= b.ms_host_logic;
+    d.ms_h2d -= b.ms_h2d;
+    d.rounds -= b.rounds;
+    d.windows -= b.windows;
+    d.kmer_lookups -= b.kmer_lookups;
+    d.query_seeds -= b.query_seeds;
+    d.posting_runs -= b.posting_runs;
+    d.posting_entries -= b.posting_entries;
+    d.candidates -= b.candidates;
+    d.chain_cells -= b.chain_cells;
+    d.mappings -= b.mappings;
+    d.kernel_launches -= b.kernel_launches;
+    d.h2d_bytes -= b.h2d_bytes;
+    d.retries -= b.retries;
+    d.short_reads -= b.short_reads;
+    return d;
+}
+void take_back_work(dp_stats& st, const dp_stats& d) {
+    st.windows -= d.windows;
+    st.h2d_bytes -= d.h2d_bytes;
+    st.kmer_lookups -= d.kmer_lookups;
+    st.query_seeds -= d.query_seeds;
+    st.posting_runs -= d.posting_runs;
+    st.posting_entries -= d.posting_entries;
+    st.candidates -= d.candidates;
+    st.chain_cells -= d.chain_cells;
+    st.short_reads -= d.short_reads;
+}
+
+// Takes the results of round 0 (waits for the lane's stream). Returns the DP_OV_* bits of a capacity that was too small
+// (nothing is delivered then and the caller reruns the range with more room, map_range); else 0 with counts[r0..r1) and
+// `out` filled — or, when `defer` and the sub-batch has open reads, with S.pending set: their later rounds have been
+// handed to the lane's rounds workspace (sub_finish_rounds takes them up) and nothing is filled yet.
+unsigned sub_complete(dp_mapper& M, Lane& W, SubState& S, bool defer, int64_t* counts, const SubDest& dest) {
+    cudaStream_t st = W.stream;
+    const int64_t n = S.n;
+    const int minLen = S.minLen;
     {
         const double tw = now_ms();
         lane_sync(W);
@@ -1452,7 +1598,7 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         };
         fprintf(stderr, "[dp trace] reads %lld+%lld host: enq %.2f synced %.2f | dev: pull %.2f-%.2f pack -%.2f extract %.2f-%.2f "
                         "lookup -%.2f reduce -%.2f chain -%.2f finish %.2f-%.2f\n",
-                (long long)r0, (long long)n, t0 - M.traceHost0, now_ms() - M.traceHost0, at(W.timers[T_PACK].a),
+                (long long)S.r0, (long long)n, S.tEnq - M.traceHost0, now_ms() - M.traceHost0, at(W.timers[T_PACK].a),
                 at(W.timers[T_PULL].b), at(W.timers[T_PACK].b), at(W.timers[T_EXTRACT].a), at(W.timers[T_EXTRACT].b),
                 at(W.timers[T_LOOKUP].b), W.reduceTimed ? at(W.timers[T_REDUCE].b) : -1.f, at(W.timers[T_CHAIN].b),
                 at(W.timers[T_FINISH].a), at(W.timers[T_FINISH].b));
@@ -1464,82 +1610,125 @@ unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const 
         W.stats.ms_finish += ms;
     }
     if (W.hCtr.p->overflow) {  // a capacity of round 0 was too small: the caller grows it and reruns the range
-        forget_attempt(W, before);
+        forget_attempt(W, S.before);
         return W.hCtr.p->overflow;
     }
-    t0 = now_ms();
+    double t0 = now_ms();
     const unsigned* fOff = W.hFinOff.p;
     const size_t devTotal = fOff[n];
     if (devTotal > W.hFinMaps.cap) {  // more records than the delivery buffer holds (repeat-rich reads): grow, write again
         W.hFinMaps.reserve(devTotal + 64);
-        if (viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
-        write_pass();
-        if (viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, devTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
+        if (S.viaHbm) W.dFinMaps.reserve(W.hFinMaps.cap);
+        finish_write_pass(M, W, n, minLen, S.viaHbm);
+        if (S.viaHbm) CK(cudaMemcpyAsync(W.hFinMaps.p, W.dFinMaps.p, devTotal * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(W.hUnresN.p, W.cursor.p + CUR_FIN, sizeof(int), cudaMemcpyDeviceToHost, st));
         W.stats.kernel_launches += 1;
         lane_sync(W);
-    } else if (viaHbm && devTotal > copyHead) {  // the tail the first copy did not cover
-        CK(cudaMemcpyAsync(W.hFinMaps.p + copyHead, W.dFinMaps.p + copyHead, (devTotal - copyHead) * sizeof(DpMappingDev),
+    } else if (S.viaHbm && devTotal > S.copyHead) {  // the tail the first copy did not cover
+        CK(cudaMemcpyAsync(W.hFinMaps.p + S.copyHead, W.dFinMaps.p + S.copyHead, (devTotal - S.copyHead) * sizeof(DpMappingDev),
                            cudaMemcpyDeviceToHost, st));
         lane_sync(W);
     }
     const int nUn = *W.hUnresN.p;
-    std::vector<DpUnresolved> unres((size_t)nUn);
+    S.unres.resize((size_t)nUn);
     if (nUn > kUnresHead) {
-        CK(cudaMemcpyAsync(unres.data(), W.dUnres.p, (size_t)nUn * sizeof(DpUnresolved), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(S.unres.data(), W.dUnres.p, (size_t)nUn * sizeof(DpUnresolved), cudaMemcpyDeviceToHost, st));
         lane_sync(W);
     } else if (nUn > 0) {
-        memcpy(unres.data(), W.hUnres.p, (size_t)nUn * sizeof(DpUnresolved));
+        memcpy(S.unres.data(), W.hUnres.p, (size_t)nUn * sizeof(DpUnresolved));
     }
-    W.stats.short_reads += nShort;
+    W.stats.short_reads += S.nShort;
     W.stats.ms_host_logic += now_ms() - t0;
     W.hp[3] += now_ms() - t0;
-    const double tRounds = now_ms();
 
     // ---- unresolved reads: the later rounds of Map() on the device (dp_rounds.cuh) ----
+    if (nUn > 0 && defer && W.rounds) {
+        // handed to the rounds workspace: the hits of the open reads are filed there (on this stream, before this lane's
+        // next launch overwrites them), the sub-batch's tables and its delivered block move over, and the lane is free
+        // for its next sub-batch; the rounds run on the other stream next to it
+        Lane& R = *W.rounds;
+        absorb_counters(W);  // round 0's counters are final
+        S.round0 = stats_diff(W.stats, S.before);
+        S.roundsBefore = R.stats;
+        R.caps = W.caps;
+        R.floorReads = R.floorWins = R.floorSeeds = R.floorBytes = 0;  // (its window buffers are sized by what the rounds ask for)
+        R.curAscii = W.curAscii;
+        R.curAsciiIsHost = W.curAsciiIsHost;
+        R.curPacked = W.curPacked;
+        R.curSpans = W.curSpans;
+        reset_counters(R);
+        rounds_begin(M, W, R, nUn, n, minLen);
+        CK(cudaEventRecord(W.evRounds, st));
+        CK(cudaStreamWaitEvent(R.stream, W.evRounds, 0));
+        swap_buf(W.dUnres, R.dUnres);
+        swap_buf(W.dReadLen, R.dReadLen);
+        swap_buf(W.dSeqOff, R.dSeqOff);
+        swap_buf(W.dWordOff, R.dWordOff);
+        swap_buf(W.dWords, R.dWords);
+        swap_buf(W.dByteOff, R.dByteOff);
+        swap_buf(W.hFinOff, R.hFinOff);
+        swap_buf(W.hFinMaps, R.hFinMaps);
+        S.nUn = nUn;
+        S.devTotal = devTotal;
+        S.pending = true;
+        return 0;
+    }
+    const double tRounds = now_ms();
     if (nUn > 0) {
-        if (unsigned ov = rounds_on_device(M, W, nUn, n, minLen)) {
-            forget_attempt(W, before);
-            W.stats.short_reads -= nShort;
+        rounds_begin(M, W, W, nUn, n, minLen);
+        if (unsigned ov = rounds_run(M, W, nUn, minLen)) {
+            forget_attempt(W, S.before);
+            W.stats.short_reads -= S.nShort;
             return ov;
         }
+        if (M.evTrace)
+            fprintf(stderr, "[dp trace] reads %lld+%lld later rounds of %d reads in line: host %.2f - %.2f ms\n", (long long)S.r0,
+                    (long long)n, nUn, tRounds - M.traceHost0, now_ms() - M.traceHost0);
     }
     W.hp[4] += now_ms() - tRounds;
-    // ---- the sub-batch's output: the delivered block as it is, with the late results spliced in where the unresolved
-    //      reads sit (they delivered nothing in round 0) ----
     t0 = now_ms();
-    const dp_mapping* fin = reinterpret_cast<const dp_mapping*>(W.hFinMaps.p);
-    std::vector<int> order((size_t)nUn);  // slots by read
-    for (int a = 0; a < nUn; a++) order[(size_t)a] = a;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return unres[(size_t)x].read < unres[(size_t)y].read; });
-    size_t total = devTotal;
-    for (int a = 0; a < nUn; a++) total += (size_t)W.hRdResN.p[a];
-    out.maps.resize(total);
-    {
-        size_t pos = 0, src = 0;
-        int64_t prevRead = 0;
-        for (int a = 0; a <= nUn; a++) {
-            const int slot = a < nUn ? order[(size_t)a] : -1;
-            const int64_t u = a < nUn ? unres[(size_t)slot].read : n;
-            const size_t segEnd = fOff[u];  // finished reads [prevRead, u): one block
-            if (segEnd > src) memcpy(out.maps.data() + pos, fin + src, (segEnd - src) * sizeof(dp_mapping));
-            pos += segEnd - src;
-            src = segEnd;
-            for (int64_t i = prevRead; i < u; i++) counts[r0 + i] = (int64_t)(fOff[i + 1] - fOff[i]);
-            if (a == nUn) break;
-            const int nLate = W.hRdResN.p[slot];
-            counts[r0 + u] = nLate;
-            if (nLate)
-                memcpy(out.maps.data() + pos, W.hRdResMaps.p + W.hRdResOff.p[slot], (size_t)nLate * sizeof(dp_mapping));
-            pos += (size_t)nLate;
-            prevRead = u + 1;
-        }
-        if (pos != total) throw std::runtime_error("internal error: sub-batch assembly mismatch");
-    }
+    sub_assemble(W, W, S, S.unres, counts, dest);
     absorb_counters(W);
     W.stats.ms_host_logic += now_ms() - t0;
     W.hp[5] += now_ms() - t0;
     return 0;
+}
+
+// The later rounds of a sub-batch that sub_complete handed to the rounds workspace, then its assembly. Returns the
+// overflow bits when a capacity of the rounds was too small: the statistics of the sub-batch are taken back and the
+// caller maps it again in line (map_range), where every capacity has its way out.
+unsigned sub_finish_rounds(dp_mapper& M, Lane& W, SubState& S, int64_t* counts, const SubDest& dest) {
+    Lane& R = *W.rounds;
+    S.pending = false;
+    const double tRounds = now_ms();
+    const unsigned ov = rounds_run(M, R, S.nUn, S.minLen);
+    W.hp[4] += now_ms() - tRounds;
+    if (M.evTrace)
+        fprintf(stderr, "[dp trace] reads %lld+%lld later rounds of %d reads next to the lane's next sub-batch: host %.2f - %.2f ms\n",
+                (long long)S.r0, (long long)S.n, S.nUn, tRounds - M.traceHost0, now_ms() - M.traceHost0);
+    if (ov) {  // (an abandoned attempt keeps its time and launches in the statistics but not its work counts)
+        take_back_work(R.stats, stats_diff(R.stats, S.roundsBefore));
+        take_back_work(W.stats, S.round0);
+        W.stats.retries += 1;
+        return ov;
+    }
+    absorb_counters(R);
+    const double t0 = now_ms();
+    sub_assemble(R, R, S, S.unres, counts, dest);
+    W.stats.ms_host_logic += now_ms() - t0;
+    W.hp[5] += now_ms() - t0;
+    return 0;
+}
+
+// One sub-batch in line: round 0, the later rounds, the assembly.
+unsigned map_subbatch(dp_mapper& M, Lane& W, const unsigned char* dAscii, const int64_t* offsets, const int64_t* byteOff,
+                      bool packed, int64_t r0, int64_t r1, int64_t* counts, SubOut& out) {
+    SubState S;
+    sub_begin(M, W, dAscii, offsets, byteOff, packed, r0, r1, S);
+    return sub_complete(M, W, S, false, counts, [&](size_t total) {
+        out.maps.resize(total);
+        return out.maps.data();
+    });
 }
 
 // (DP_CAP_OUT / DP_CAP_RESULTS / DP_CAP_CHAINS / DP_CAP_CANDS: tests start from tiny capacities to walk the retries)
@@ -1629,6 +1818,21 @@ struct LaneSet {
                 CK(cudaEventCreateWithFlags(&L->evSync, cudaEventDisableTiming | cudaEventBlockingSync));
                 L->timers.resize(T_N);
                 for (auto& t : L->timers) t.init();
+                CK(cudaEventCreateWithFlags(&L->evRounds, cudaEventDisableTiming));
+                L->rounds.reset(new Lane());
+                {   // the rounds' launches are tiny and latency-bound: in front of the queued blocks of the big kernels
+                    int lo = 0, hi = 0;
+                    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    if (env_int("DP_ROUNDS_PRIO", 1))
+                        CK(cudaStreamCreateWithPriority(&L->rounds->stream, cudaStreamNonBlocking, hi));
+                    else
+                        CK(cudaStreamCreateWithFlags(&L->rounds->stream, cudaStreamNonBlocking));
+                }
+                CK(cudaEventCreateWithFlags(&L->rounds->evReady, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&L->rounds->evPulled, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&L->rounds->evSync, cudaEventDisableTiming | cudaEventBlockingSync));
+                L->rounds->timers.resize(T_N);
+                for (auto& t : L->rounds->timers) t.init();
                 M.lanes.push_back(std::move(L));
                 M.laneBusy.push_back(0);
                 take(M.lanes.size() - 1);
@@ -1782,6 +1986,7 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     for (int l = 0; l < nLanes; l++) {
         Lane& W = *held.lanes[(size_t)l];
         memset(&W.stats, 0, sizeof(W.stats));
+        if (W.rounds) memset(&W.rounds->stats, 0, sizeof(W.rounds->stats));
         W.floorReads = floorReads;
         W.floorWins = 2 * floorReads;
         W.floorBytes = floorBytes;
@@ -1790,18 +1995,24 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     std::vector<SubOut> subs(nSub);
     std::atomic<size_t> nextSub(0);
     std::vector<std::string> errs((size_t)nLanes);
-    // The result arrays are filled while the call runs: a sub-batch is copied to its place as soon as every sub-batch
-    // in front of it has reported its size (by the lane thread that closes the gap), so nothing is left to concatenate
-    // when the last lane finishes. Room for two records per read is reserved up front (untouched pages cost nothing);
-    // a batch that needs more (repeat-rich reads) is finished the slow way below.
+    // The result arrays are filled while the call runs. A sub-batch reports its number of records as soon as it is known;
+    // its place is known once every sub-batch in front of it has reported. In the common case (sub-batches finish roughly
+    // in order) that is before its block is assembled, and the block is assembled where it belongs; else it is assembled
+    // in a block of its own and copied later, by whichever lane thread has a moment (none is left with a queue of
+    // copies when the last kernels have finished). Room for two records per read is reserved up front (untouched pages
+    // cost nothing); a batch that needs more (repeat-rich reads) is finished the slow way below.
     struct {
         std::mutex mu;
-        std::vector<char> done;
+        std::vector<char> reported, based, direct, ready, placed;
+        std::vector<int64_t> total, base;
         size_t frontier = 0;       // first sub-batch that has not been given its place
         int64_t frontierBase = 0;  // records in front of it
         bool spilled = false;
+        std::vector<size_t> waiting;  // given a place, assembled in a block of their own, not copied yet
     } pl;
-    pl.done.assign(nSub, 0);
+    for (auto* v : {&pl.reported, &pl.based, &pl.direct, &pl.ready, &pl.placed}) v->assign(nSub, 0);
+    pl.total.assign(nSub, 0);
+    pl.base.assign(nSub, 0);
     size_t mapsCap = (size_t)n_reads * 2 + 4096;
     if (getenv("DP_RESULT_CAP")) mapsCap = (size_t)std::max(1, env_int("DP_RESULT_CAP", 1));  // (tests: force the slow way)
     // (off[i] holds read i's record COUNT, written by the lane that maps it, until its sub-batch is given its place)
@@ -1813,79 +2024,178 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         throw std::runtime_error("out of host memory for the result");
     }
     std::atomic<int> bad(0);
-    auto place_one = [&](size_t sI, int64_t base) {
-        if (!subs[sI].maps.empty()) memcpy(maps + base, subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
+    auto counts_to_offsets = [&](size_t sI, int64_t base) {
         int64_t run = base;
         for (int64_t i = cuts[sI]; i < cuts[sI + 1]; i++) {
             const int64_t c = off[i];
             off[i] = run;
             run += c;
         }
-        if (run != base + (int64_t)subs[sI].maps.size()) bad.store(1);
+        if (run != base + pl.total[sI]) bad.store(1);
+    };
+    auto place_one = [&](size_t sI, int64_t base) {  // a block of its own -> its place
+        if (!subs[sI].maps.empty()) memcpy(maps + base, subs[sI].maps.data(), subs[sI].maps.size() * sizeof(dp_mapping));
+        counts_to_offsets(sI, base);
         subs[sI].maps.clear();  // the block goes back to the mapper for the next sub-batch (of this or a later call)
         std::lock_guard<std::mutex> lk(M.spareMu);
         if (M.spare.size() < 2 * kMaxLanes) M.spare.push_back(std::move(subs[sI].maps));
         std::vector<dp_mapping>().swap(subs[sI].maps);
     };
-    auto deliver = [&](size_t sI) {
-        size_t first = 0, last = 0;
-        int64_t base = 0;
-        {
-            std::lock_guard<std::mutex> lk(pl.mu);
-            pl.done[sI] = 1;
-            first = last = pl.frontier;
-            base = pl.frontierBase;
-            while (last < nSub && pl.done[last] && !pl.spilled) {
-                const int64_t t = (int64_t)subs[last].maps.size();
-                if ((size_t)(pl.frontierBase + t) > mapsCap) {
-                    pl.spilled = true;
-                    break;
-                }
-                pl.frontierBase += t;
-                last++;
+    // (call with pl.mu held) gives places to the reported sub-batches at the frontier
+    auto advance = [&]() {
+        while (pl.frontier < nSub && pl.reported[pl.frontier] && !pl.spilled) {
+            const size_t q = pl.frontier;
+            if ((size_t)(pl.frontierBase + pl.total[q]) > mapsCap) {
+                pl.spilled = true;
+                break;
             }
-            pl.frontier = last;
-        }
-        for (size_t q = first; q < last; q++) {
-            const int64_t t = (int64_t)subs[q].maps.size();
-            place_one(q, base);
-            base += t;
+            pl.base[q] = pl.frontierBase;
+            pl.based[q] = 1;
+            pl.frontierBase += pl.total[q];
+            pl.frontier++;
+            if (pl.ready[q] && !pl.placed[q]) pl.waiting.push_back(q);
         }
     };
+    // the size of sub-batch q is known: its place in the result array if it has one already, else null
+    auto report = [&](size_t q, size_t total) -> dp_mapping* {
+        std::lock_guard<std::mutex> lk(pl.mu);
+        pl.total[q] = (int64_t)total;
+        pl.reported[q] = 1;
+        advance();
+        if (!pl.based[q]) return nullptr;
+        pl.direct[q] = 1;
+        return maps + pl.base[q];
+    };
+    // copies of sub-batches that wait for one (any lane thread, one at a time)
+    auto drain = [&]() {
+        for (;;) {
+            size_t q;
+            {
+                std::lock_guard<std::mutex> lk(pl.mu);
+                if (pl.waiting.empty()) return;
+                q = pl.waiting.back();
+                pl.waiting.pop_back();
+                pl.placed[q] = 1;
+            }
+            place_one(q, pl.base[q]);
+        }
+    };
+    // sub-batch q is assembled (in place, or in subs[q])
+    auto deliver = [&](size_t q) {
+        bool inPlace = false, copyNow = false;
+        {
+            std::lock_guard<std::mutex> lk(pl.mu);
+            if (!pl.reported[q]) {  // (came through map_range: assembled in a block of its own before its size was reported)
+                pl.total[q] = (int64_t)subs[q].maps.size();
+                pl.reported[q] = 1;
+                advance();
+            }
+            inPlace = pl.direct[q] != 0;
+            pl.ready[q] = 1;
+            if (!inPlace && pl.based[q] && !pl.placed[q]) {
+                // (advance() may have queued it a moment ago: take it back, this thread copies it now)
+                for (size_t i = 0; i < pl.waiting.size(); i++)
+                    if (pl.waiting[i] == q) {
+                        pl.waiting.erase(pl.waiting.begin() + (long)i);
+                        break;
+                    }
+                pl.placed[q] = 1;
+                copyNow = true;
+            }
+            if (inPlace) pl.placed[q] = 1;
+        }
+        if (inPlace) counts_to_offsets(q, pl.base[q]);
+        if (copyNow) place_one(q, pl.base[q]);
+        drain();
+    };
+    // The later rounds of a sub-batch run next to round 0 of the lane's next one when the reads are resident on the
+    // device (DP_ROUNDS_DEFER=0/1 overrides): in line, all lanes reach their rounds at about the same time and the GPU
+    // sees nothing but a few hundred windows' worth of tiny launches for 3 ms of an 18 ms step. Reads pulled out of
+    // host memory keep them in line — there the step is the PCIe pulls and the rounds hide under them (measured: deferring
+    // costs 1.5 ms per step). Never for pageable reads: they are staged in one buffer per lane.
+    const bool deferRounds = hostBases ? env_int("DP_ROUNDS_DEFER", 0) != 0 && mappedBase : env_int("DP_ROUNDS_DEFER", 1) != 0;
+    const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);
     auto work = [&](int l) {
         try {
             CK(cudaSetDevice(M.device));
             Lane& W = *held.lanes[(size_t)l];
+            SubState pend;               // the sub-batch whose later rounds are in the lane's rounds workspace
+            std::vector<size_t> redo;    // sub-batches whose rounds ran out of a capacity
+            auto take_spare = [&](size_t q) {
+                std::lock_guard<std::mutex> lk(M.spareMu);
+                if (subs[q].maps.capacity() == 0 && !M.spare.empty()) {
+                    subs[q].maps = std::move(M.spare.back());
+                    M.spare.pop_back();
+                }
+            };
+            auto deliver_timed = [&](size_t q) {
+                const double tp = now_ms();
+                deliver(q);
+                W.hp[5] += now_ms() - tp;
+            };
+            auto source_of = [&](size_t q) -> const unsigned char* {
+                const int64_t r0 = cuts[q], r1 = cuts[q + 1];
+                W.curAsciiIsHost = false;
+                if (hostBases && mappedBase) {
+                    W.curAsciiIsHost = true;
+                    return mappedBase + srcOff[r0];  // the kernels read the caller's pinned buffer in place
+                }
+                if (hostBases) {
+                    upload_ascii(W, hostBases, srcOff, r0, r1, false);
+                    W.stats.h2d_bytes += srcOff[r1] - srcOff[r0];
+                    return W.dAscii.p;
+                }
+                return devBases + srcOff[r0];
+            };
+            auto in_line = [&](size_t q, const unsigned char* src) {  // with the way out of every capacity (map_range)
+                W.caps = default_caps();
+                take_spare(q);
+                map_range(M, W, src, offsets, byteOff, packed, cuts[q], cuts[q + 1], off, subs[q]);
+                W.caps = default_caps();
+                deliver_timed(q);
+            };
+            auto dest_of = [&](size_t q) -> SubDest {
+                return [&, q](size_t total) -> dp_mapping* {
+                    if (dp_mapping* there = report(q, total)) return there;
+                    take_spare(q);
+                    subs[q].maps.resize(total);
+                    return subs[q].maps.data();
+                };
+            };
+            auto finish_pending = [&]() {  // the later rounds of the lane's previous sub-batch, then its delivery
+                if (!pend.pending) return;
+                const size_t q = pend.sI;
+                if (sub_finish_rounds(M, W, pend, off, dest_of(q))) redo.push_back(q);  // (mapped again in line below)
+                else deliver_timed(q);
+            };
             for (;;) {
                 size_t sI = nextSub.fetch_add(1);
                 if (sI >= nSub) break;
-                int64_t r0 = cuts[sI], r1 = cuts[sI + 1];
-                const unsigned char* dA;
-                W.curAsciiIsHost = false;
-                if (hostBases && mappedBase) {
-                    dA = mappedBase + srcOff[r0];  // the kernels read the caller's pinned buffer in place
-                    W.curAsciiIsHost = true;
-                } else if (hostBases) {
-                    upload_ascii(W, hostBases, srcOff, r0, r1, false);
-                    W.stats.h2d_bytes += srcOff[r1] - srcOff[r0];
-                    dA = W.dAscii.p;
+                const int64_t r0 = cuts[sI], r1 = cuts[sI + 1];
+                W.caps = default_caps();
+                const size_t candBytes = (size_t)4 * (size_t)(r1 - r0) * std::min<size_t>(M.I.numChunks, W.caps.candStride) * 6;
+                if (!deferRounds || candBytes > candBudget) {
+                    finish_pending();
+                    in_line(sI, source_of(sI));
+                    continue;
+                }
+                // round 0 of this sub-batch is enqueued, THEN the rounds of the previous one run next to it
+                const unsigned char* dA = source_of(sI);
+                SubState cur;
+                sub_begin(M, W, dA, offsets, byteOff, packed, r0, r1, cur);
+                finish_pending();
+                if (sub_complete(M, W, cur, true, off, dest_of(sI))) {  // a capacity of round 0 was too small
+                    in_line(sI, dA);
+                } else if (cur.pending) {
+                    cur.sI = sI;
+                    pend = std::move(cur);
                 } else {
-                    dA = devBases + srcOff[r0];
+                    deliver_timed(sI);
                 }
                 W.caps = default_caps();
-                {
-                    std::lock_guard<std::mutex> lk(M.spareMu);
-                    if (!M.spare.empty()) {
-                        subs[sI].maps = std::move(M.spare.back());
-                        M.spare.pop_back();
-                    }
-                }
-                map_range(M, W, dA, offsets, byteOff, packed, r0, r1, off, subs[sI]);
-                W.caps = default_caps();
-                const double tp = now_ms();
-                deliver(sI);
-                W.hp[5] += now_ms() - tp;
             }
+            finish_pending();
+            for (size_t q : redo) in_line(q, source_of(q));
             lane_sync(W);
         } catch (const std::exception& ex) {
             errs[(size_t)l] = ex.what();
@@ -1904,9 +2214,10 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
             dp_free(off);
             throw std::runtime_error(e);
         }
+    drain();  // (copies that became possible after the lane that could have made them had finished)
     int64_t total = pl.frontierBase;
     if (pl.frontier < nSub) {  // more than two records per read: the rest is placed now, in an array of the exact size
-        for (size_t sI = pl.frontier; sI < nSub; sI++) total += (int64_t)subs[sI].maps.size();
+        for (size_t sI = pl.frontier; sI < nSub; sI++) total += pl.total[sI];
         dp_mapping* grown = (dp_mapping*)result_alloc(sizeof(dp_mapping) * (size_t)(total ? total : 1));
         if (!grown) {
             dp_free(maps);
@@ -1918,9 +2229,8 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
         maps = grown;
         int64_t base = pl.frontierBase;
         for (size_t sI = pl.frontier; sI < nSub; sI++) {
-            const int64_t t = (int64_t)subs[sI].maps.size();
             place_one(sI, base);
-            base += t;
+            base += pl.total[sI];
         }
     }
     off[n_reads] = total;
@@ -1941,7 +2251,10 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     {
         dp_stats st2;
         memset(&st2, 0, sizeof(st2));
-        for (int l = 0; l < nLanes; l++) add_stats(st2, held.lanes[(size_t)l]->stats);
+        for (int l = 0; l < nLanes; l++) {
+            add_stats(st2, held.lanes[(size_t)l]->stats);
+            if (held.lanes[(size_t)l]->rounds) add_stats(st2, held.lanes[(size_t)l]->rounds->stats);
+        }
         st2.bases = offsets[n_reads] - offsets[0];
         st2.mappings = total;
         st2.ms_total = now_ms() - tStart;
