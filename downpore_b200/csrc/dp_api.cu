@@ -801,8 +801,9 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
         const long long* spanOff = W.curSpans ? W.dByteOff.p : nullptr;  // ASCII reads addressed by their own offsets
         int blocks = (int)std::min<size_t>((nWin + 7) / 8, (size_t)M.smCount * perSm);
         const int stageStride = ((I.maxWindow + 15) / 16 + 3) * 16;  // the 16-byte blocks of the longest window
-        const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS * 2 * stageStride <= 96 * 1024;
-        if (W.curPacked && W.curAsciiIsHost && bulkPull && tmaPull) {
+        const bool tmaPull = env_int("DP_PULL_TMA", 1) != 0 && (size_t)DP_PULL_SLOTS_ASCII * 2 * stageStride <= 96 * 1024;
+        if (W.curPacked && W.curAsciiIsHost && bulkPull && env_int("DP_PULL_TMA", 1) != 0 &&
+            (size_t)DP_PULL_SLOTS_PACKED * 2 * (((I.maxWindow / 4 + 15) / 16 + 3) * 16) <= 96 * 1024) {
             // reads that arrive packed, in pinned host memory: the same TMA pull (a quarter of the bytes), then the
             // realign + byte swap from the HBM staging buffer
             const int pkStride = ((I.maxWindow / 4 + 15) / 16 + 3) * 16;
@@ -818,7 +819,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                 // best — 24.3 ms per 1M reads against 35.5 with 32, 25.5 with 128 and 29 with zero-copy loads)
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 64)));
                 CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
-                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * pkStride, M.pullStream>>>(
+                dp_pull_windows_kernel<DP_PULL_SLOTS_PACKED, 12><<<pullCtas, 32, (size_t)DP_PULL_SLOTS_PACKED * 2 * pkStride, M.pullStream>>>(
                     W.curAscii, W.dSeqOff.p, W.dByteOff.p, true, W.dWins.p, (int)nWin, W.dStage.p, pkStride, W.dStagePos.p,
                     W.dPullWork.p);
                 CK(cudaGetLastError());
@@ -866,7 +867,7 @@ void launch_windows(dp_mapper& M, Lane& W, size_t nWin, size_t seedEntries, cons
                 CK(cudaEventRecord(W.timers[T_PACK].a, M.pullStream));
                 const int pullCtas = (int)std::min<size_t>((nWin + 31) / 32, (size_t)std::max(1, env_int("DP_PULL_CTAS", 32)));
                 CK(cudaMemsetAsync(W.dPullWork.p, 0, sizeof(unsigned), M.pullStream));
-                dp_pull_windows_kernel<<<pullCtas, 32, (size_t)DP_PULL_SLOTS * 2 * stageStride, M.pullStream>>>(
+                dp_pull_windows_kernel<DP_PULL_SLOTS_ASCII, 12><<<pullCtas, 32, (size_t)DP_PULL_SLOTS_ASCII * 2 * stageStride, M.pullStream>>>(
                     W.curAscii, W.dSeqOff.p, spanOff, false, W.dWins.p, (int)nWin, W.dStage.p, stageStride, W.dStagePos.p,
                     W.dPullWork.p);
                 CK(cudaGetLastError());
@@ -2311,7 +2312,7 @@ std::unique_ptr<dp_mapper> open_mapper(int device) {
     CK(cudaStreamCreateWithPriority(&M->pullStream, cudaStreamNonBlocking, hi));
     // (per device; set here, before any lane thread exists)
     CK(cudaFuncSetAttribute(dp_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(dp_pull_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(dp_pull_windows_kernel<DP_PULL_SLOTS_ASCII, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_mid_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(dp_lookup_block_kernel<256, 4, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

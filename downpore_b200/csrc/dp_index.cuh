@@ -222,11 +222,15 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_packed_kernel(const un
 // scripts/pcie_probe2.cu), so the SMs stay free for the compute kernels of the other lanes; the pack itself then runs
 // from HBM. The other 31 lanes of the warp only prepare the copy descriptors, 32 windows at a time.
 // ---------------------------------------------------------------------------------------------------------------
-#define DP_PULL_SLOTS 16   // ring slots per CTA
-#define DP_PULL_AHEAD 12   // loads in flight per CTA (the other slots are being stored)
+// ring slots per CTA / loads in flight per CTA (the other slots are being stored). A deeper ring (32 / 28) buys nothing for
+// the 250-560 byte pieces of packed reads: next to the compute kernels the pull is bound by how fast its one thread per CTA
+// gets to issue (32 CTAs: 31 ms per step, 64: 21, 128: 24), not by the bytes in flight
+#define DP_PULL_SLOTS_ASCII 16
+#define DP_PULL_SLOTS_PACKED 16
 
 // `byteOff` != null: read r starts at ascii + byteOff[r]; `packed`: the reads are packedSequence bytes (four bases per
 // byte) and the blocks moved are the ones dp_pack_windows_packed_kernel reads.
+template <int DP_PULL_SLOTS, int DP_PULL_AHEAD>
 __global__ void __launch_bounds__(32) dp_pull_windows_kernel(const unsigned char* __restrict__ ascii,
                                                              const long long* __restrict__ seqOff,
                                                              const long long* __restrict__ byteOff, bool packed,
