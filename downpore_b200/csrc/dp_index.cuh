@@ -222,9 +222,12 @@ __global__ void __launch_bounds__(256, 6) dp_pack_windows_packed_kernel(const un
 // scripts/pcie_probe2.cu), so the SMs stay free for the compute kernels of the other lanes; the pack itself then runs
 // from HBM. The other 31 lanes of the warp only prepare the copy descriptors, 32 windows at a time.
 // ---------------------------------------------------------------------------------------------------------------
-// ring slots per CTA / loads in flight per CTA (the other slots are being stored). A deeper ring (32 / 28) buys nothing for
-// the 250-560 byte pieces of packed reads: next to the compute kernels the pull is bound by how fast its one thread per CTA
-// gets to issue (32 CTAs: 31 ms per step, 64: 21, 128: 24), not by the bytes in flight
+// ring slots per CTA / loads in flight per CTA (the other slots are being stored). Alone, 16 CTAs pull 250-560 byte pieces
+// at 45 GB/s (scripts/pcie_probe3.cu); next to the compute kernels of the other lanes the pull of a step takes 31 ms with
+// 32 CTAs, 21 with 64, 24 with 128. Measured and rejected: a deeper ring (32 slots, 28 loads in flight: same), eight
+// lanes of the warp issuing copies side by side (16 CTAs x 8 lanes: 27 ms, 64 x 8: 22-23) — what the pull runs out of is
+// the memory path of the SMs it shares with the compute kernels, neither bytes in flight nor issue slots: it wants to be
+// spread over about 64 SMs.
 #define DP_PULL_SLOTS_ASCII 16
 #define DP_PULL_SLOTS_PACKED 16
 
