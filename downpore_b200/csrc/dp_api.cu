@@ -1257,8 +1257,11 @@ inline size_t round0_seed_bound(long long len, int e, int minLen) {
 void rounds_begin(dp_mapper& M, Lane& W, Lane& R, int nUn, int64_t n, int minLen) {
     cudaStream_t st = W.stream;
     const size_t scale = (size_t)R.caps.roundsScale;
-    const size_t slots = std::max<size_t>((size_t)nUn, 64);
-    const int nThreads = (int)std::min<size_t>((slots + 63) / 64 * 64, 4096);
+    // (sizes in powers of two from 1024 slots: the number of open reads changes from sub-batch to sub-batch, the buffers
+    // should not — a cudaFree in the middle of a call synchronises the device under every lane)
+    size_t slots = 1024;
+    while (slots < (size_t)nUn) slots *= 2;
+    const int nThreads = (int)std::min<size_t>(((size_t)std::max(nUn, 64) + 63) / 64 * 64, 4096);
     DpRoundsDev& D = R.roundsDev;
     memset(&D, 0, sizeof(D));
     // (DP_ROUNDS_HITS / DP_ROUNDS_LIST / DP_ROUNDS_CACHE: tests start from tiny capacities to walk the retries)
@@ -1277,8 +1280,8 @@ void rounds_begin(dp_mapper& M, Lane& W, Lane& R, int nUn, int64_t n, int minLen
     R.rdResN.reserve(slots);
     R.rdResOff.reserve(slots);
     R.rdResMaps.reserve(D.resCap);
-    R.rdHits.reserve((size_t)nThreads * D.hitCap);
-    R.rdLists.reserve((size_t)nThreads * DP_RL_LISTS * D.listCap);
+    R.rdHits.reserve((size_t)std::min<size_t>(slots, 4096) * D.hitCap);
+    R.rdLists.reserve((size_t)std::min<size_t>(slots, 4096) * DP_RL_LISTS * D.listCap);
     R.rdCur.reserve(DP_RC_N);
     R.hRdCur.reserve(DP_RC_N);
     R.hRdResN.reserve(slots);
@@ -1337,6 +1340,10 @@ unsigned rounds_run(dp_mapper& M, Lane& W, int nUn, int minLen) {
         if (nReq > R.winCap) throw std::runtime_error("internal error: more window requests than two per open read");
         const unsigned long long lenSum = (unsigned long long)W.hRdCur.p[DP_RC_LEN_LO] | ((unsigned long long)W.hRdCur.p[DP_RC_LEN_HI] << 32);
         const size_t seedEntries = 2 * ((size_t)lenSum + 2 * nReq);
+        if (W.floorWins < nReq) {  // (a rounds workspace starts from nothing: its floors double, so its buffers settle)
+            W.floorWins = std::max<size_t>(2048, 2 * nReq);
+            W.floorSeeds = std::max(W.floorSeeds, (size_t)W.floorWins * 2 * (size_t)(2 * M.edge + 2));
+        }
         ensure_window_capacity(M, W, nReq, seedEntries);
         if (W.curAsciiIsHost) W.stats.h2d_bytes += (int64_t)(W.curPacked ? lenSum / 4 + 32 * nReq : lenSum + 32 * nReq);
         launch_windows(M, W, nReq, seedEntries, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
@@ -1346,7 +1353,11 @@ unsigned rounds_run(dp_mapper& M, Lane& W, int nUn, int minLen) {
         W.stats.kernel_launches += 1;
     }
     const size_t total = W.hRdCur.p[DP_RC_RES];
-    W.hRdResMaps.reserve(total + 1);
+    {
+        size_t room = 4096;
+        while (room < total + 1) room *= 2;
+        W.hRdResMaps.reserve(room);
+    }
     CK(cudaMemcpyAsync(W.hRdResN.p, W.rdResN.p, (size_t)nUn * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(W.hRdResOff.p, W.rdResOff.p, (size_t)nUn * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     if (total) CK(cudaMemcpyAsync(W.hRdResMaps.p, W.rdResMaps.p, total * sizeof(DpMappingDev), cudaMemcpyDeviceToHost, st));
@@ -1652,11 +1663,21 @@ unsigned sub_complete(dp_mapper& M, Lane& W, SubState& S, bool defer, int64_t* c
         S.round0 = stats_diff(W.stats, S.before);
         S.roundsBefore = R.stats;
         R.caps = W.caps;
-        R.floorReads = R.floorWins = R.floorSeeds = R.floorBytes = 0;  // (its window buffers are sized by what the rounds ask for)
+        R.floorReads = R.floorBytes = 0;  // (its window buffers are sized by what the rounds ask for: floors that only double)
         R.curAscii = W.curAscii;
         R.curAsciiIsHost = W.curAsciiIsHost;
         R.curPacked = W.curPacked;
         R.curSpans = W.curSpans;
+        // the buffers that trade places below: the workspace's copies as large as the lane's, once (equal capacities:
+        // after the first sub-batches nothing is allocated in the middle of a call any more)
+        R.dUnres.reserve_exact(W.dUnres.cap);
+        R.dReadLen.reserve_exact(W.dReadLen.cap);
+        R.dSeqOff.reserve_exact(W.dSeqOff.cap);
+        R.dWordOff.reserve_exact(W.dWordOff.cap);
+        R.dWords.reserve_exact(W.dWords.cap);
+        R.dByteOff.reserve_exact(W.dByteOff.cap);
+        R.hFinOff.reserve_exact(W.hFinOff.cap);
+        R.hFinMaps.reserve_exact(W.hFinMaps.cap);
         reset_counters(R);
         rounds_begin(M, W, R, nUn, n, minLen);
         CK(cudaEventRecord(W.evRounds, st));

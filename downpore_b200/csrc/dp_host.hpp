@@ -36,6 +36,12 @@ struct DBuf {  // device buffer, grow-only
         CK(cudaMalloc((void**)&p, want * sizeof(T)));
         cap = want;
     }
+    void reserve_exact(size_t n) {  // (for a buffer that trades places with another: equal capacities end the growth)
+        if (n <= cap) return;
+        release();
+        CK(cudaMalloc((void**)&p, n * sizeof(T)));
+        cap = n;
+    }
     size_t bytes() const { return cap * sizeof(T); }
 };
 
@@ -55,6 +61,14 @@ struct HBuf {  // page-locked host buffer mapped into the device address space (
         CK(cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer((void**)&d, p, 0));
         cap = want;
+    }
+    void reserve_exact(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        CK(cudaHostAlloc((void**)&p, n * sizeof(T), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&d, p, 0));
+        cap = n;
     }
 };
 
