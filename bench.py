@@ -80,6 +80,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_T0 = time.time()
+
+
+def progress(msg):
+    """Phase marks on stderr (seconds since start): where a run spent its time, should a box be slow."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1f s] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -301,6 +311,7 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
     """One workload (the module-level REF_LEN/READ_LEN/... selected by select_workload) on this rank's GPU: builds or
     receives the index, maps `args.reads` reads per step device-resident (`value`) and from pinned host memory (`e2e`),
     and times every kernel family on a single lane. Returns a dict of rank-local and reduced results."""
+    progress("workload %s: reference" % WORKLOAD)
     ref = synth.reference(REF_SEED, REF_LEN)
     t_c0 = time.time()
     t_counts = t_index = t_repl = 0.0
@@ -328,6 +339,7 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
         torch.cuda.synchronize()
         t_index = time.time() - t1
     info = gm.index_info()
+    progress("index built; generating reads")
 
     n = args.reads
     first = rank * n  # weak scaling: every rank maps its own n reads of the same read set
@@ -338,6 +350,8 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
     d_reads = pinned.to(dev, non_blocking=False)
     torch.cuda.synchronize()
     bases_rank = n * READ_LEN
+
+    progress("reads on the device; timing")
 
     def step_device():
         return gm.map_batch_device(d_reads.data_ptr(), offs)
@@ -381,6 +395,7 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
     mapped_frac = float((np.diff(off) > 0).mean())
     d2h_bytes = int(len(maps) * 32 + (n + 1) * 8)
 
+    progress("value timed; e2e (ASCII entry)")
     # ---- end to end from pinned host memory: `e2e` ----
     for _ in range(min(warmup, 2)):
         step_host()
@@ -400,6 +415,7 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
     # ---- end to end with the reads in the form the reference's reader hands to Mapper.Map: packedSequence bytes
     #      (sequence/seqio.go:158,219; 4 bases per byte) in pinned host memory -> dp_mapper_map_batch_packed. The packing
     #      is input preparation (done here on the GPU with torch, outside the timed region), as the ASCII batch is. ----
+    progress("e2e (packed entry)")
     assert READ_LEN % 4 == 0
     pk_pinned = torch.empty(n * READ_LEN // 4, dtype=torch.uint8).pin_memory()
     piece = 1 << 28
@@ -437,11 +453,15 @@ def measure(dp, synth, torch, args, rank, world, local, dev, steps, warmup, want
     #      concurrently running kernels overlap and each reads long) ----
     iso = None
     if want_iso:
+        progress("single-lane stage times")
         os.environ["DP_LANES"] = "1"
+        os.environ["DP_ROUNDS_DEFER"] = "0"  # (the later rounds in line: on their own stream they would overlap the brackets)
         step_device()
         step_device()
         iso = gm.stats()
         del os.environ["DP_LANES"]
+        del os.environ["DP_ROUNDS_DEFER"]
+    progress("workload %s measured" % WORKLOAD)
 
     total_bases = sum_over_ranks(float(bases_rank), world, dev)
     S = steps
@@ -558,7 +578,9 @@ def side_workload(dp, synth, torch, po, args, name, rank, world, local, dev, cor
                             "ms_lookup_per_step_single_lane": k["lookup"]["ms_per_step"], "kernels": k},
                "stats_per_step": r["stats_per_step"]}
         if rank == 0 and parity_reads > 0 and not args.no_cpu_baseline and r["_vals"] is not None:
+            progress("%s: cpu baseline (oracle index + %d reads)" % (name, min(parity_reads, args.reads)))
             out["cpu_baseline"] = cpu_sample(po, r, min(parity_reads, args.reads), cores, all_cores)
+            progress("%s: cpu baseline done" % name)
         return out
     finally:
         (globals()["REF_LEN"], globals()["READ_LEN"], globals()["REF_SEED"], globals()["READ_SEED"], globals()["CIRCULAR"],
@@ -626,6 +648,7 @@ def overlap_workload(dp, synth, po, args, device, cores, peak):
         m = min(args.overlap_cpu_reads, n)
         ov = po.overlap_values(rd[: m * L], offs[: m + 1], 10)
         t0 = time.time()
+        progress("config5: oracle round on %d reads" % m)
         o = po.OverlapRound(rd[: m * L], offs[: m + 1], ov)
         dt = time.time() - t0
         g2 = dp.Overlapper(rd[: m * L], offs[: m + 1], ov, device=device)
@@ -711,7 +734,9 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         cores = len(affinity_before or os.sched_getaffinity(0)) or 1
         if world == 1:
+            progress("cpu baseline (oracle) on %d reads" % min(args.cpu_sample, n))
             line["cpu_baseline"] = cpu_sample(po, r, min(args.cpu_sample, n), cores, affinity_before)
+            progress("cpu baseline done")
     del r
 
     # ---- the other BASELINE configs in the same run: config 3 at every N; config 4 (3.1 Gb reference, index built on
@@ -768,7 +793,9 @@ def run_ours(args):
     #      (313k chunks, 677M postings, 15 GB index >> L2), 15 kb reads, single lane ----
     if rank == 0 and world == 1 and not args.no_hbm_regime:
         try:
+            progress("lookup on the 3.1 Gb reference (hbm regime)")
             h = hbm_regime(dp, synth, local, peak, peak_src, gather_gbs)
+            progress("hbm regime done")
             line["roofline_hbm_regime"] = h
             for k2 in ("frac", "frac_actual_bytes", "achieved", "achieved_actual_bytes", "ms_lookup", "Gbp_per_s", "kernel",
                        "workload", "traffic"):
