@@ -1270,7 +1270,14 @@ void rounds_begin(dp_mapper& M, Lane& W, Lane& R, int nUn, int64_t n, int minLen
     D.entCap = (unsigned)std::min<size_t>((32 * slots + 64) * scale, 0x7fffffffu);
     D.cacheCap = (unsigned)std::min<size_t>(((size_t)std::max(1, env_int("DP_ROUNDS_CACHE", 256)) * slots + 4096) * scale, 0xfffffff0u);
     D.resCap = (unsigned)std::min<size_t>((16 * slots + 1024) * scale, 0xfffffff0u);
-    if (&R != &W) R.dWins.reserve(2 * slots + 64);  // the windows the replays ask for (at most two per open read and round)
+    if (&R != &W) {
+        // a rounds workspace sizes its window buffers for two windows per slot (what the replays of one round can ask for)
+        // and their worst-case seed lists, in the same powers of two as the slots: they settle after the first sub-batches
+        // and — the window list holds the requests — never move while the rounds run
+        R.floorWins = std::max(R.floorWins, 2 * slots);
+        R.floorSeeds = std::max(R.floorSeeds, R.floorWins * 2 * (size_t)(2 * M.edge + 2));
+        R.dWins.reserve(R.floorWins + 64);
+    }
     R.rdHead.reserve(slots);
     R.rdEnt.reserve(D.entCap);
     R.rdEnt2.reserve(D.entCap);
@@ -1340,11 +1347,8 @@ unsigned rounds_run(dp_mapper& M, Lane& W, int nUn, int minLen) {
         if (nReq > R.winCap) throw std::runtime_error("internal error: more window requests than two per open read");
         const unsigned long long lenSum = (unsigned long long)W.hRdCur.p[DP_RC_LEN_LO] | ((unsigned long long)W.hRdCur.p[DP_RC_LEN_HI] << 32);
         const size_t seedEntries = 2 * ((size_t)lenSum + 2 * nReq);
-        if (W.floorWins < nReq) {  // (a rounds workspace starts from nothing: its floors double, so its buffers settle)
-            W.floorWins = std::max<size_t>(2048, 2 * nReq);
-            W.floorSeeds = std::max(W.floorSeeds, (size_t)W.floorWins * 2 * (size_t)(2 * M.edge + 2));
-        }
         ensure_window_capacity(M, W, nReq, seedEntries);
+        if (W.dWins.p != R.wins) throw std::runtime_error("internal error: the window list moved under the rounds");
         if (W.curAsciiIsHost) W.stats.h2d_bytes += (int64_t)(W.curPacked ? lenSum / 4 + 32 * nReq : lenSum + 32 * nReq);
         launch_windows(M, W, nReq, seedEntries, W.dWords.p, W.dWordOff.p, W.dReadLen.p);
         dp_rounds_collect_kernel<<<div_up((long long)nReq, 128), 128, 0, st>>>(R, (int)nReq, W.outN.p, W.outOff.p, W.outMaps.p,
