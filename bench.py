@@ -28,13 +28,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures:
-# profiles/r1k_ncu_summary.txt (one 65536-read sub-batch of config 2; chain = dp_chain_thread_kernel) and
-# profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of config 4)
-TRAFFIC_PER_LAUNCH = {"pack": 169.5e6, "extract": 49.3e6, "lookup": 41.0e6, "reduce": 95.8e6, "chain": 81.1e6,
-                      "finish": 5.8e6, "lookup_block": 56.87e9}
+# profiles/r2ad_ncu_summary.txt (one 65536-read sub-batch of config 2 on a single lane, the code of this round; lookup =
+# dp_lookup_small_kernel 33.2 MB + the deferral pass of dp_lookup_kernel 8.1 MB; chain = dp_chain_thread_kernel; finish = its
+# count and write passes) and profiles/r1h_ncu_lookup_block_3.1Gb.txt (80000 window strands against the 3.1 Gb reference of
+# config 4)
+TRAFFIC_PER_LAUNCH = {"pack": 169.8e6, "extract": 50.0e6, "lookup": 41.3e6, "reduce": 93.9e6, "chain": 80.7e6,
+                      "finish": 11.9e6, "lookup_block": 56.87e9}
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures (config 2 is L2-resident: SURVEY 8d asks for
-# issue utilisation beside the HBM fraction there); lookup = dp_lookup_small_kernel (profiles/r1q_ncu_lookup_small.txt)
-ISSUE_ACTIVE_PCT = {"pack": 55.5, "extract": 61.2, "lookup": 68.1, "reduce": 47.1, "chain": 37.8, "finish": 5.9,
+# issue utilisation beside the HBM fraction there); lookup = dp_lookup_small_kernel
+ISSUE_ACTIVE_PCT = {"pack": 56.3, "extract": 68.5, "lookup": 68.0, "reduce": 54.0, "chain": 38.0, "finish": 15.6,
                     "lookup_block": 48.2}
 
 K = 11
