@@ -269,6 +269,42 @@ def test_later_rounds_of_map_on_the_device(pair):
             assert st["windows"] > 2.5 * len(reads)  # most reads went past their two round-0 windows
 
 
+def test_later_rounds_next_to_round0(pair):
+    """The later rounds of a sub-batch run on the lane's rounds workspace next to round 0 of its next sub-batch when the
+    reads are resident on the device (and, with DP_ROUNDS_DEFER=1, when they are pulled out of page-locked memory): many
+    small sub-batches per lane (the sub-batch's tables change hands every time), chimera-heavy reads (every sub-batch has
+    open reads), also from scratch capacities so small that the rounds hand the sub-batch back to be mapped again in
+    line, and with a result array that outgrows its reservation."""
+    import torch
+    ref, circular, om, gm = pair
+    reads = chimera_reads(ref, circular, seed=83, n=150)
+    bases, offs = make_golden.concat(reads)
+    orow, ooff, octr = om.map_batch(bases, offs, threads=4)
+    dev = torch.from_numpy(bases).cuda()
+    pinned = torch.from_numpy(bases).pin_memory()
+    for env in ({"DP_SUB_READS": "16"}, {"DP_SUB_READS": "8", "DP_LANES": "2"}, {"DP_SUB_READS": "16", "DP_ROUNDS_HITS": "3"},
+                {"DP_SUB_READS": "32", "DP_ROUNDS_CACHE": "1", "DP_ROUNDS_LIST": "2"}, {"DP_SUB_READS": "16", "DP_RESULT_CAP": "30"},
+                {"DP_SUB_READS": "16", "DP_ROUNDS_DEFER": "0"}):
+        with _Env(env):
+            for _ in range(2):
+                maps, off = gm.map_batch_device(dev.data_ptr(), offs)
+                assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), ("device", env)
+            if env == {"DP_SUB_READS": "16"}:  # the work counters do not depend on where the rounds run. (Against the oracle
+                # `windows` can be one short on this read set: findSplitPoint may ask for a window Map() has queried
+                # before — the reference maps it again, the window cache answers it.)
+                st = gm.stats()
+                with _Env({"DP_ROUNDS_DEFER": "0"}):
+                    gm.map_batch_device(dev.data_ptr(), offs)
+                    st_line = gm.stats()
+                keys = ("windows", "kmer_lookups", "query_seeds", "posting_runs", "posting_entries", "candidates",
+                        "chain_cells", "mappings", "rounds")
+                assert [st[k2] for k2 in keys[:-1]] == [st_line[k2] for k2 in keys[:-1]], (
+                    {k2: (st[k2], st_line[k2], octr.get(k2)) for k2 in keys})
+        with _Env(dict(env, DP_ROUNDS_DEFER=env.get("DP_ROUNDS_DEFER", "1"))):
+            maps, off = gm.map_batch_ptr(pinned.data_ptr(), offs)
+            assert np.array_equal(off, ooff) and np.array_equal(rows_of(maps), orow), ("pinned", env)
+
+
 def test_result_delivery_in_pieces(pair):
     """A batch cut into many sub-batches (six lanes finishing them out of order) is delivered in read order, also when the
     result outgrows the room reserved up front and the rest is placed after the lanes have finished."""
