@@ -349,6 +349,12 @@ int dpo_pair_ends(long long refLen, int circular, long long queryLen, const long
     DPO_CATCH(1)
 }
 
+// gapRange (seeds/alignment.go:411-424): out2 = {minGap, maxGap}
+void dpo_gap_range(long long gap, long long k, long long* out2) {
+    out2[0] = gapRangeMin(gap, k);
+    out2[1] = gapRangeMax(gap, k);
+}
+
 // ----- k-mer statistics ---------------------------------------------------------
 // values (4^k doubles) for a single-record reference, commands/map.go:45-71 with the canonical tie order
 int dpo_kmer_values(const char* ref_ascii, long long n, int k, double* values_out) {

@@ -466,6 +466,13 @@ def pair_ends(ref_len, circular, query_len, hits_a, hits_b):
     return ra, rb, (None if nm < 0 else [list(map(int, r)) for r in rows[na + nb:na + nb + nm]])
 
 
+def gap_range(gap, k):
+    """gapRange (seeds/alignment.go:411-424): (minGap, maxGap)."""
+    out = np.zeros(2, dtype=np.int64)
+    lib().dpo_gap_range(ctypes.c_longlong(int(gap)), ctypes.c_longlong(int(k)), out.ctypes.data_as(c_vp))
+    return int(out[0]), int(out[1])
+
+
 def kmer_values(ref, k):
     """values[] of commands/map.go:45-71 for a single-record reference (canonical tie order, Q10)."""
     a = _u8(ref)

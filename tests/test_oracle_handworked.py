@@ -151,3 +151,86 @@ def test_is_consistent_middle_band_by_hand():
     b = [150, 1100, 1200, 7800, 0, 90]
     assert po.pair_ends(100000, True, 10000, [a], [b])[2] == [[99000, 1100, 0, 7800, 0, 190]]
     assert po.pair_ends(100000, False, 10000, [a], [b])[2] is None
+
+
+def _uniform_segments(gaps_after, lead, trail, first_seed=100):
+    """segments of a seed sequence with distinct seeds first_seed, first_seed+1, ..: lead, s0, gaps_after[0], s1, .., trail"""
+    seg = [lead]
+    for i, g in enumerate(gaps_after + [trail]):
+        seg += [first_seed + i, g]
+    return seg
+
+
+def test_seed_space_chunking_by_hand():
+    """chunkWorker (overlap/overlap.go:253-318), k = 10, chunk_size 3000 bases, overlap 1000, on 400 seeds that sit 20 bases
+    apart (gap 10), 5 bases of lead, 7 of trail: length 5 + 400*10 + 399*10 + 7 = 8002, numChunks = 8002/3000 + 1 = 3.
+
+    GetNextSeedOffset(i) = gap after seed i + k = 20 (17 after the last seed, 15 for i = -1: the lead + k).
+    Piece 1: prevSeedIndex 0, totalOffset = GetSeedOffset(0) = 5. The count loop stops at 100 seeds (2000 bases < 3000):
+      newFirstGap = 15 - 10 = 5, length 2005, SubSequence(0, 99, 2005, offset 5 - 5 = 0, inset 8002 - 5 - 2005 + 5 = 5997);
+      totalOffset = 5 + 2000 = 2005, prevSeedIndex = 100, then back 5 seeds (5 * 20 = 100 < overlap/2 = 500, the count of
+      5 stops it): prevSeedIndex 95, totalOffset 1905 (= 5 + 95*20: the position of seed 95).
+    Piece 2: (95, 194): newFirstGap 10, length 2010, offset 1895, inset 8002 - 1905 - 2010 + 10 = 4097; on to 190 / 3805.
+    Piece 3: (190, 289): length 2010, offset 3795, inset 2197; on to 285 / 5705.
+    285 >= 400 - 150: the rest in one piece (:268-277): length = GetSeedOffsetFromEnd(285) + k + newFirstGap =
+      (8002 - (5 + 285*20 + 10)) + 10 + 10 = 2287 + 20 = 2307, SubSequence(285, 399, 2307, 5705 - 10 = 5695, 0).
+    Every piece satisfies offset + length + inset = 8002. A piece's segments are s.segments[2*start : 2*end + 3]."""
+    s = _uniform_segments([10] * 399, 5, 7)
+    got = po.chunk_seed_sequence(s, 8002, 3000, 15, 1000, 10)
+    want = [(0, 99, 2005, 0, 5997), (95, 194, 2010, 1895, 4097), (190, 289, 2010, 3795, 2197), (285, 399, 2307, 5695, 0)]
+    assert [(ln, off, ins) for _, ln, off, ins in got] == [w[2:] for w in want]
+    for (seg, _, _, _), (a, b, _, _, _) in zip(got, want):
+        assert list(seg) == s[2 * a: 2 * b + 3]
+    # a sequence of one chunk_size or with fewer than 3 * min_seeds seeds goes in whole (:259-263) - or not at all
+    short = _uniform_segments([10] * 39, 5, 7)
+    assert [(ln, off, ins) for _, ln, off, ins in po.chunk_seed_sequence(short, 802, 3000, 15, 1000, 10)] == [(802, 0, 0)]
+    assert po.chunk_seed_sequence(_uniform_segments([10] * 9, 5, 7), 202, 3000, 15, 1000, 10) == []
+
+
+def test_seed_space_chunking_with_a_dropped_piece_by_hand():
+    """The same walk over 510 seeds with a sparse stretch: seeds 0..199 are 20 bases apart, the ten gaps after seeds
+    199..208 are 490 (500 bases per step), seeds 209..509 are 20 apart again; lead 5, trail 7. pos[199] = 3985,
+    pos[209] = 8985, pos[509] = 14985, length 15002. min_seeds = 16.
+
+    Pieces 1 and 2 as before: (0, 99, 2005, 0, 12997), (95, 194, 2010, 1895, 11097); on to seed 190, totalOffset 3805.
+    From seed 190 the count loop adds 9 * 20 = 180, then 500 per seed: 680, 1180, 1680, 2180, 2680, 3180 >= 3000 after 15
+    seeds (190..204) — fewer than min_seeds: the piece is dropped (:303-314). prevSeedIndex = 205. The walk back by
+    overlap/2 that follows does NOT happen: unlike the branch that keeps a piece, this one does not reset lengthInBases
+    before its loop, so `lengthInBases < overlap/2` reads 3180 < 500. (My first derivation reset it, walked one seed back
+    and expected offset 2815 for the next piece; the restatement said 3315 — and the source agrees with the restatement.)
+    totalOffset stays 3805 although seed 205 sits at 6985: from here on offset and inset no longer tile the read.
+    From seed 205: 4 * 500 = 2000, + 20 (the short gap after 209) = 2020, + 49 * 20 = 3000 after 54 seeds (205..258):
+      newFirstGap = GetNextSeedOffset(204) - k = 490, length 3490, offset 3805 - 490 = 3315,
+      inset 15002 - 3805 - 3490 + 490 = 8197; totalOffset = 3805 + 3000 = 6805, back five seeds of 20: seed 254, 6705.
+    (254, 353): length 2010, offset 6695, inset 15002 - 6705 - 2010 + 10 = 6297; on to 349 / 8605.
+    (349, 448): length 2010, offset 8595, inset 4397; on to 444 / 10505.
+    444 >= 510 - 150: the rest: GetSeedOffsetFromEnd(444) = 15002 - (8985 + 235*20 + 10) = 1307, length 1327,
+      SubSequence(444, 509, 1327, 10495, 0)."""
+    gaps = [10] * 199 + [490] * 10 + [10] * 300
+    s = _uniform_segments(gaps, 5, 7)
+    assert len(s) == 2 * 510 + 1
+    got = po.chunk_seed_sequence(s, 15002, 3000, 16, 1000, 10)
+    want = [(0, 99, 2005, 0, 12997), (95, 194, 2010, 1895, 11097), (205, 258, 3490, 3315, 8197), (254, 353, 2010, 6695, 6297),
+            (349, 448, 2010, 8595, 4397), (444, 509, 1327, 10495, 0)]
+    assert [(ln, off, ins) for _, ln, off, ins in got] == [w[2:] for w in want]
+    for (seg, _, _, _), (a, b, _, _, _) in zip(got, want):
+        assert list(seg) == s[2 * a: 2 * b + 3]
+    # with min_seeds = 15 the sparse piece is kept: (190, 204) of 3180 + 10 bases at offset 3795
+    got15 = po.chunk_seed_sequence(s, 15002, 3000, 15, 1000, 10)
+    assert [(ln, off, ins) for _, ln, off, ins in got15][2] == (3190, 3795, 15002 - 3805 - 3190 + 10)
+
+
+def test_gap_range_by_hand():
+    """gapRange (seeds/alignment.go:411-424): minGap = gap*2/3 - k, maxGap = gap*3/2 + k + 1 (Go's integer division truncates
+    towards zero); a negative minGap becomes -k (and a negative maxGap 0); otherwise a maxGap below 20 becomes 20 with
+    minGap 0.
+      gap 100, k 10: 66 - 10 = 56, 150 + 11 = 161
+      gap   6, k 10: 4 - 10 = -6 -> -10; 9 + 11 = 20 stays
+      gap -30, k 10: -20 - 10 = -30 -> -10; -45 + 11 = -34 -> 0
+      gap  16, k 10: 10 - 10 = 0 (not negative); 24 + 11 = 35 >= 20 stays
+      gap   6, k  4: 4 - 4 = 0; 9 + 5 = 14 < 20 -> (0, 20)"""
+    assert po.gap_range(100, 10) == (56, 161)
+    assert po.gap_range(6, 10) == (-10, 20)
+    assert po.gap_range(-30, 10) == (-10, 0)
+    assert po.gap_range(16, 10) == (0, 35)
+    assert po.gap_range(6, 4) == (0, 20)
