@@ -234,3 +234,58 @@ def test_gap_range_by_hand():
     assert po.gap_range(-30, 10) == (-10, 0)
     assert po.gap_range(16, 10) == (0, 35)
     assert po.gap_range(6, 4) == (0, 20)
+
+
+def _kmer_id(s):
+    """A = 0, C = 1, G = 2, T = 3, first base most significant (sequence/sequence.go:520-528 KmerValue)."""
+    v = 0
+    for c in s:
+        v = v * 4 + "ACGT".index(c)
+    return v
+
+
+def _rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def test_add_seeds_by_hand():
+    """AddSeeds (seeds/seeds.go:62-156), k = 5, on the 62 bases below with an empty index.
+
+    The walk (:83-127): kmer = KmerAt(0), nextIndex = 5; a block rolls NextKmer k times, i.e. examines the k-mers that START
+    at p0+1 .. p0+5; after a block nextIndex += k, kmer = KmerAt(nextIndex), nextIndex += k: the next block starts 3k = 15
+    further on. With 62 bases (loop while nextIndex < 57) the blocks examine starts 1-5, 16-20, 31-35, 46-50.
+    Values: start 3 (TCACA) 5.0; starts 17 (GCTCA) and 18 (CTCAC) 7.0 each; start 48 (GAGAG) 2.0; everything else 0.
+      block 1: best = TCACA 5.0      block 2: GCTCA 7.0 (`value > bestValue` is strict: the first of the two wins)
+      block 3: nothing above 0.0: bestValue stays 0 and the insertion below places nothing      block 4: GAGAG 2.0
+    topN insertion (:108-120; slot 0 is the bottom, a new value passes every smaller one), minSeeds = 3:
+      5.0 -> [0, 0, 5];  7.0 -> [0, 5, 7];  2.0 passes only the 0 -> [2, 5, 7]  =  GAGAG, TCACA, GCTCA
+    Registration (:131-154) in that order, each k-mer followed by its reverse complement:
+      GAGAG, CTCTC, TCACA, TGTGA, GCTCA, TGAGC.
+    With minSeeds = 4 the bottom slot stays unfilled and holds k-mer 0: AAAAA and TTTTT are registered FIRST."""
+    s1 = "GGATCACAGTCTACACTGCTCACTCCAACCCCGGCCCCTGAGTCCGAGGAGAGGGTGCTTCA"
+    assert len(s1) == 62 and (s1[3:8], s1[17:22], s1[18:23], s1[48:53]) == ("TCACA", "GCTCA", "CTCAC", "GAGAG")
+    ranks = [0.0] * 4 ** 5
+    ranks[_kmer_id("TCACA")] = 5.0
+    ranks[_kmer_id("GCTCA")] = 7.0
+    ranks[_kmer_id("CTCAC")] = 7.0
+    ranks[_kmer_id("GAGAG")] = 2.0
+    want = ["GAGAG", "CTCTC", "TCACA", "TGTGA", "GCTCA", "TGAGC"]
+    assert [_rc(x) for x in want[0::2]] == want[1::2]
+    g = po.SeedIndex(5)
+    g.add_seeds(s1.encode(), 3, ranks)
+    assert list(g.seeds()) == [_kmer_id(x) for x in want]
+    g4 = po.SeedIndex(5)
+    g4.add_seeds(s1.encode(), 4, ranks)
+    assert list(g4.seeds()) == [_kmer_id(x) for x in ["AAAAA", "TTTTT"] + want]
+
+    # A second sequence against the index of the first call: a block that meets a seed is abandoned (:91-94).
+    #   s2 holds GCTCA (a seed now) at start 3: block 1 examines starts 1 (GTGCT, value 100: discarded with the block), 2, and
+    #   3 -> reset at nextIndex = 8; nextIndex += 5 -> KmerAt(13) -> nextIndex = 18: block 2 examines starts 14-18, where
+    #   start 15 (TAGCC) has value 9.0; block 3 (starts 29-33) has nothing. minSeeds = 2: topN = [0, TAGCC] -> AAAAA, TTTTT,
+    #   TAGCC, GGCTA are appended.
+    s2 = "CGTGCTCAACCGTCGTAGCCATGCTGCTTCATTGCAGGTT"
+    assert len(s2) == 40 and s2[3:8] == "GCTCA" and s2[15:20] == "TAGCC" and s2[1:6] == "GTGCT"
+    ranks[_kmer_id("GTGCT")] = 100.0
+    ranks[_kmer_id("TAGCC")] = 9.0
+    g.add_seeds(s2.encode(), 2, ranks)
+    assert list(g.seeds()) == [_kmer_id(x) for x in want + ["AAAAA", "TTTTT", "TAGCC", "GGCTA"]]
