@@ -2139,7 +2139,10 @@ void map_batch_impl(dp_mapper& M, int64_t n_reads, const uint8_t* hostBases, con
     // sees nothing but a few hundred windows' worth of tiny launches for 3 ms of an 18 ms step. Reads pulled out of
     // host memory keep them in line — there the step is the PCIe pulls and the rounds hide under them (measured: deferring
     // costs 1.5 ms per step). Never for pageable reads: they are staged in one buffer per lane.
-    const bool deferRounds = hostBases ? env_int("DP_ROUNDS_DEFER", 0) != 0 && mappedBase : env_int("DP_ROUNDS_DEFER", 1) != 0;
+    // And not for indexes whose lookup scratch lives in HBM (more than 24 000 chunks: 8 GB per workspace at human scale, and
+    // a step of hundreds of milliseconds in which the rounds do not show): a second workspace per lane would be waste.
+    const bool deferRounds = (hostBases ? env_int("DP_ROUNDS_DEFER", 0) != 0 && mappedBase : env_int("DP_ROUNDS_DEFER", 1) != 0) &&
+                             M.I.numChunks <= kLookupSmemChunks;
     const size_t candBudget = std::max<size_t>(1, (size_t)env_int("DP_CAND_BUDGET_MB", 8192) << 20);
     auto work = [&](int l) {
         try {
