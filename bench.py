@@ -550,11 +550,11 @@ def e2e_dict(r):
             "ascii_value": r["e2e"], "ascii_ms_per_step": r["e2e_ms_per_step"],
             "ascii_h2d_bytes_per_step": r["h2d_bytes_per_step"],
             "ascii_host_buffer_bytes_per_step": r["host_buffer_bytes_per_step"],
-            "note": "per GPU. The reads stay in the caller's pinned buffer; only the queried windows cross PCIe (packed "
-                    "entry: zero-copy loads of the windows' bytes; ASCII entry: a TMA pull kernel, cp.async.bulk host -> "
-                    "shared memory -> HBM staging), so h2d bytes < host buffer bytes; the finish kernel writes the "
-                    "mapping records in read order into mapped host memory. ascii_* = dp_mapper_map_batch on pinned "
-                    "ASCII reads (the input form the CPU arm is given)"}
+            "note": "per GPU. The reads stay in the caller's pinned buffer; only the queried windows cross PCIe (a TMA pull "
+                    "kernel for either entry: cp.async.bulk host -> shared memory -> HBM staging; a quarter of the bytes "
+                    "for packed reads), so h2d bytes < host buffer bytes; the mapping records are written in read order "
+                    "into HBM and copied as one block per sub-batch into the call's result array. ascii_* = "
+                    "dp_mapper_map_batch on pinned ASCII reads (the input form the CPU arm is given)"}
 
 
 LOOKUP_KERNEL = {"config2": "dp_lookup_small_kernel + dp_lookup_kernel (window strands with more than 32 seeds)",
