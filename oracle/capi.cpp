@@ -349,6 +349,29 @@ int dpo_pair_ends(long long refLen, int circular, long long queryLen, const long
     DPO_CATCH(1)
 }
 
+// SeedIndex.Matches (seeds/seeds.go:335-353) against an index of explicit seed sequences: chunkSegs = the chunks' segment
+// lists back to back, chunkOff[nChunks+1] their bounds; AddSequence + IndexSequences (seeds.go:272-305, 372-384) over
+// numSeeds seed ids, then Matches(query, hitFraction). Returns the number of chunk ids written to out (ascending).
+long long dpo_matches(const long long* chunkSegs, const long long* chunkOff, long long nChunks, long long numSeeds,
+                      const long long* querySeg, long long nq, double hitFraction, long long* out, long long cap) {
+    DPO_TRY SeedIndex g;
+    NewSeedIndex(g, 5);
+    g.size = numSeeds;
+    g.sequenceSets.assign((size_t)numSeeds, NewIntSet());
+    for (long long c = 0; c < nChunks; c++) {
+        SeedSequence s;
+        s.segments.assign(chunkSegs + chunkOff[c], chunkSegs + chunkOff[c + 1]);
+        AddSequence(g, std::move(s));
+    }
+    IndexSequences(g);
+    SeedSequence q;
+    q.segments.assign(querySeg, querySeg + nq);
+    std::vector<uint64_t> ids = Matches(g, q, hitFraction, nullptr);
+    for (size_t i = 0; i < ids.size() && (long long)i < cap; i++) out[i] = (long long)ids[i];
+    return (long long)ids.size();
+    DPO_CATCH(-1)
+}
+
 // gapRange (seeds/alignment.go:411-424): out2 = {minGap, maxGap}
 void dpo_gap_range(long long gap, long long k, long long* out2) {
     out2[0] = gapRangeMin(gap, k);

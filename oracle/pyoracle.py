@@ -466,6 +466,31 @@ def pair_ends(ref_len, circular, query_len, hits_a, hits_b):
     return ra, rb, (None if nm < 0 else [list(map(int, r)) for r in rows[na + nb:na + nb + nm]])
 
 
+def matches(chunk_seeds, num_seeds, query_seeds, hit_fraction):
+    """SeedIndex.Matches (seeds/seeds.go:335-353) of a query (its seeds in order) against chunks given as seed lists (gaps are
+    irrelevant to it and set to 1): the candidate chunk ids."""
+    def seg(seeds):
+        out = [1]
+        for x in seeds:
+            out += [int(x), 1]
+        return out
+    segs, off = [], [0]
+    for c in chunk_seeds:
+        segs += seg(c)
+        off.append(len(segs))
+    cs = np.ascontiguousarray(segs, dtype=np.int64)
+    co = np.ascontiguousarray(off, dtype=np.int64)
+    q = np.ascontiguousarray(seg(query_seeds), dtype=np.int64)
+    out = np.zeros(max(1, len(chunk_seeds)), dtype=np.int64)
+    lib().dpo_matches.restype = ctypes.c_longlong
+    n = lib().dpo_matches(cs.ctypes.data_as(c_vp), co.ctypes.data_as(c_vp), ctypes.c_longlong(len(chunk_seeds)),
+                          ctypes.c_longlong(int(num_seeds)), q.ctypes.data_as(c_vp), ctypes.c_longlong(q.size),
+                          ctypes.c_double(float(hit_fraction)), out.ctypes.data_as(c_vp), ctypes.c_longlong(out.size))
+    if n < 0:
+        raise RuntimeError(_err())
+    return [int(x) for x in out[:n]]
+
+
 def gap_range(gap, k):
     """gapRange (seeds/alignment.go:411-424): (minGap, maxGap)."""
     out = np.zeros(2, dtype=np.int64)

@@ -289,3 +289,25 @@ def test_add_seeds_by_hand():
     ranks[_kmer_id("TAGCC")] = 9.0
     g.add_seeds(s2.encode(), 2, ranks)
     assert list(g.seeds()) == [_kmer_id(x) for x in want + ["AAAAA", "TTTTT", "TAGCC", "GGCTA"]]
+
+
+def test_matches_by_hand():
+    """SeedIndex.Matches (seeds/seeds.go:335-353) over six chunks and ten seeds:
+        c0 {0, 1, 2, 3}   c1 {0, 4, 5}   c2 {0, 1, 2, 6, 7}   c3 {0, 8}   c4 {0, 9, 3}   c5 {0}
+    Query seeds in order 0, 1, 1, 2, 3, 9, 6, 7. The sets handed to GetSharedIDs (:340-346): seed 0 sits in all six
+    chunks (Size() == len(sequences): left out); the second 1 repeats its predecessor (left out); 1, 2, 3, 9, 6, 7 go in:
+    six sets >= 5, minCount = int(0.25 * 6 + 0.5) = 2. Chunks per set: 1 {c0, c2}, 2 {c0, c2}, 3 {c0, c4}, 9 {c4}, 6 {c2},
+    7 {c2} -> c0 counts 3, c2 counts 4, c4 counts 2, the rest 0: ids with at least two sets = 0, 2, 4 (all ids sit in one
+    64-bit word: no set is dropped on the way, and level 2 of the four-level soft union is exact, util/bitset.go:376-387)."""
+    chunks = [[0, 1, 2, 3], [0, 4, 5], [0, 1, 2, 6, 7], [0, 8], [0, 9, 3], [0]]
+    assert po.matches(chunks, 10, [0, 1, 1, 2, 3, 9, 6, 7], 0.25) == [0, 2, 4]
+    # hitFraction 0.5: minCount = int(3.5) = 3 -> c0 (3) and c2 (4)
+    assert po.matches(chunks, 10, [0, 1, 1, 2, 3, 9, 6, 7], 0.5) == [0, 2]
+    # four usable seeds only (1, 2, 3, 9): 'not many usable seeds in the query' -> nothing (:347-349)
+    assert po.matches(chunks, 10, [0, 1, 2, 3, 9], 0.25) == []
+    # a repeat that is NOT adjacent counts twice (:342 only compares with the previous included seed):
+    # 1, 2, 1, 3, 9, 6 -> six sets, minCount 2: c0 = 1 + 1 + 1 + 1 = 4, c2 = 1 + 1 + 1 + 1 = 4, c4 = 2
+    assert po.matches(chunks, 10, [1, 2, 1, 3, 9, 6], 0.25) == [0, 2, 4]
+    # ... which matters at the threshold: 4, 5, 4, 5, 8 -> five sets (minCount int(1.75) = 1 -> level 1: any chunk hit):
+    # c1 (4, 5, 4, 5) and c3 (8)
+    assert po.matches(chunks, 10, [4, 5, 4, 5, 8], 0.25) == [1, 3]
